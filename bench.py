@@ -1,0 +1,341 @@
+#!/usr/bin/env python
+"""bench.py — the UCE edit-solve hot path on B200 (BASELINE.json metric: concepts/sec).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2]
+
+A *step* is one complete edit solve of the workload: shared factor + apply over every
+cross-attention k/v projection (BASELINE configs[1] by default: SD-1.4 shapes, 50 erase +
+100 preserve concepts, 32 projections, K=768).  `value` = concepts/s with the concept rows and
+projection weights already resident in HBM (CUDA-graph replay, CUDA-event timed, max over
+ranks); `e2e` = the same metric through the host-buffer C-ABI call (uce_edit_host_f32) with
+pinned host tensors, H2D and D2H inside the timed region.  N>1: every rank solves its own
+independent edit job (weak scaling, no data-path collective); the layer-sharded single job with
+its all-gather is reported under "sharded".  `--impl reference` times the CPU restatement of the
+reference's algorithm (oracle/uce_oracle.py: the reference itself is Python and cannot travel
+to the GPU box) on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "concepts/sec (edit-solve)"
+UNIT = "concepts/s"
+WORKLOAD_DESC = {
+    "cfg1": "cfg1: SDv1.4-shaped, erase 2 preserve 3, one attn2 (to_k,to_v [320,768])",
+    "cfg2": "cfg2: SDv1.4 erase 50 preserve 100, all 32 cross-attn k/v projections, K=768",
+    "cfg3": "cfg3: SDv1.4 debias-shaped 10 edit rows, 32 projections, K=768",
+    "cfg4": "cfg4: SDXL erase 1000, 140 projections, K=2048",
+}
+
+
+# ------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------ CPU baseline
+def cpu_port_time(prob, budget_s=20.0, min_reps=1, stratify=1):
+    """Time the fp32 restatement of the reference (oracle.erase_port_f32) on the host cores."""
+    from oracle import uce_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    ne = prob["n_edit"]
+    ce, cp = prob["C"][:ne], prob["C"][ne:]
+    W = prob["W"][::stratify]
+    frac = sum(w.shape[0] for w in W) / sum(w.shape[0] for w in prob["W"])
+    reps, t_tot = 0, 0.0
+    while reps < min_reps or (t_tot < budget_s / 2 and reps < 50):
+        t0 = time.perf_counter()
+        O.erase_port_f32(W, ce, prob["G"], cp, 1.0, 1.0, prob["lamb"])
+        t_tot += time.perf_counter() - t0
+        reps += 1
+    return t_tot / reps, reps, len(W), frac
+
+
+def run_reference(args, rank, world):
+    from uce_b200.synthetic import problem
+    if rank != 0:
+        return
+    prob = problem(args.workload, seed=0)
+    n = prob["C"].shape[0]
+    t1, _, _, _ = cpu_port_time(prob, budget_s=0.0, min_reps=1)          # warm-up + sizing
+    stratify = 1
+    if (args.steps + args.warmup) * t1 > 150.0:
+        stratify = 4
+    for _ in range(max(0, args.warmup - 1)):
+        cpu_port_time(prob, 0.0, 1, stratify)
+    ts = []
+    frac = 1.0
+    for _ in range(args.steps):
+        t, _, nl, frac = cpu_port_time(prob, 0.0, 1, stratify)
+        ts.append(t / frac if stratify > 1 else t)
+    ms = 1e3 * sum(ts) / len(ts)
+    val = n / (ms / 1e3)
+    sample = (f"full workload per step ({len(prob['W'])} projections)" if stratify == 1 else
+              f"every {stratify}th projection per step, time scaled by rows fraction {frac:.3f}")
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD_DESC[args.workload], "implementation": "CPU fp32 restatement of uce_sd_erase.py:45-82 (oracle port)"},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------ ours
+def run_ours(args, rank, world, local_rank):
+    import torch.distributed as dist
+    from uce_b200.solver import EditSolver
+    from uce_b200.synthetic import problem
+
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    prob = problem(args.workload, seed=rank)
+    n, ne, K, lamb = prob["C"].shape[0], prob["n_edit"], prob["K"], prob["lamb"]
+    dims = prob["dims"]
+    w_bytes = 4 * K * sum(dims)
+    R = max(2, int(-(-400e6 // (2 * w_bytes))))          # weight sets so that the rotating footprint exceeds L2 (126 MB) several times
+    R = min(R, 8)
+    Cd, Gd = prob["C"].to(dev), prob["G"].to(dev)
+    sets_in = [[w.to(dev) for w in prob["W"]]]
+    for _ in range(R - 1):
+        sets_in.append([w.clone() for w in sets_in[0]])
+    sets_out = [[torch.empty_like(w) for w in s] for s in sets_in]
+    solver = EditSolver(K, max(16, n), dev)
+    if args.apply_impl is not None:
+        solver.set_apply_impl(args.apply_impl)
+
+    def step(i):
+        solver.factor(Cd, Gd, prob["scales"], ne, lamb)
+        solver.apply(sets_in[i % R], sets_out[i % R])
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    # ---- warm-up (eager), then one CUDA graph per weight set ----
+    for i in range(max(args.warmup, 3)):
+        step(i)
+    solver.check()
+    info = solver.info()
+    launches_per_step = info["launches_factor"] + info["launches_apply"]
+    graphs = None
+    if not args.no_graph:
+        graphs = []
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for i in range(R):
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=side):
+                    step(i)
+                graphs.append(g)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        for i in range(max(args.warmup, 3)):
+            graphs[i % R].replay()
+    torch.cuda.synchronize(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    # ---- timed region: exactly K steps ----
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier(); torch.cuda.synchronize(dev)
+    ev0.record()
+    for i in range(args.steps):
+        if graphs:
+            graphs[i % R].replay()
+        else:
+            step(i)
+    ev1.record()
+    torch.cuda.synchronize(dev); barrier()
+    total_ms = ev0.elapsed_time(ev1)
+    solver.check()
+
+    # ---- per-kernel durations (profile events inside the library, eager launches) ----
+    solver.set_profile(True)
+    tf, t1, t2 = [], [], []
+    for i in range(min(args.steps, 20)):
+        step(i)
+        a, b, c = solver.timings()
+        tf.append(a); t1.append(b); t2.append(c)
+    solver.set_profile(False)
+    f_ms, a1_ms, a2_ms = (sum(x) / len(x) for x in (tf, t1, t2))
+
+    # ---- end to end through the host-buffer C-ABI call ----
+    h_in = [w.pin_memory() for w in prob["W"]]
+    h_out = [torch.empty_like(w).pin_memory() for w in prob["W"]]
+    hC, hG = prob["C"].pin_memory(), prob["G"].pin_memory()
+    for _ in range(3):
+        solver.edit_host(hC, hG, prob["scales"], ne, lamb, h_in, h_out)
+    e2e_steps = max(3, min(args.steps, 20))
+    barrier(); torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        solver.edit_host(hC, hG, prob["scales"], ne, lamb, h_in, h_out)
+    torch.cuda.synchronize(dev)
+    e2e_ms = 1e3 * (time.perf_counter() - t0) / e2e_steps
+    clocks = sampler.stop()
+
+    # ---- reductions over ranks ----
+    if world > 1:
+        t = torch.tensor([total_ms, e2e_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms, e2e_ms = t.tolist()
+
+    sharded = None
+    if world > 1:
+        sharded = bench_sharded(solver, prob, dev, rank, world, args)
+
+    if rank == 0:
+        ms_per_step = total_ms / args.steps
+        value = world * n / (ms_per_step / 1e3)
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak_bw, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)") if "hbm_gbs" in peaks else (6650.0, "fallback (B200_PROFILING.md)")
+        # algorithmic bytes of the apply: read W_old once + write W_new once (fp32) + E and Q once
+        alg_bytes = 2 * w_bytes + 2 * 4 * K * max(info["rank"], 1)
+        dom_ms = a1_ms + a2_ms
+        achieved = alg_bytes / (dom_ms / 1e3) / 1e9
+        roof = {"bound": "hbm", "kernel": "apply (W_new = W_old + (W_old E^T) Q over all projections)", "achieved": achieved,
+                "peak": peak_bw, "unit": "GB/s", "frac": achieved / peak_bw, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes": alg_bytes, "kernel_ms": dom_ms, "stage_ms": [a1_ms, a2_ms], "factor_ms": f_ms}
+        cpu = None
+        if not args.no_cpu:
+            t_cpu, reps, nl, frac = cpu_port_time(prob, budget_s=args.cpu_budget, min_reps=1)
+            cpu = {"value": n / t_cpu, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                   "sample": f"{reps} repetitions of the full {args.workload} workload ({nl} projections), oracle.erase_port_f32, torch {torch.get_num_threads()} threads"}
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic",
+                "config": {"workload": WORKLOAD_DESC[args.workload], "concept_rows": n, "n_edit": ne, "projections": len(dims), "K": K,
+                           "factor": f"fp64 {info['mode_name']} system {info['sys_n']}x{info['sys_n']}, rank {info['rank']}, dense={info['dense']}",
+                           "l2": f"inputs rotate over {R} weight sets ({R * 2 * w_bytes / 1e6:.0f} MB in+out) > 126 MB L2, no flush",
+                           "launch": "eager" if not graphs else "one CUDA graph replay per step",
+                           "parallelism": f"{world} independent edit jobs (one per GPU)" if world > 1 else "1 GPU"},
+                "clocks": clocks,
+                "e2e": {"value": world * n / (e2e_ms / 1e3), "unit": UNIT, "ms_per_step": e2e_ms,
+                        "h2d_bytes_per_step": w_bytes + 4 * K * (n + ne), "d2h_bytes_per_step": w_bytes,
+                        "api": "uce_edit_host_f32 (pinned host tensors)"},
+                "gpu_launches": launches_per_step * args.steps,
+                "roofline": roof}
+        if cpu:
+            line["cpu_baseline"] = cpu
+        if sharded:
+            line["sharded"] = sharded
+        print(json.dumps(line), flush=True)
+    solver.close()
+
+
+def bench_sharded(solver, prob, dev, rank, world, args):
+    """One edit job, projections dealt round-robin to ranks, ONE all-gather of the edited weights."""
+    import torch.distributed as dist
+    from uce_b200.sharding import all_gather_layers, shard_layers
+    n, ne, K = prob["C"].shape[0], prob["n_edit"], prob["K"]
+    from uce_b200.synthetic import problem
+    p0 = problem(args.workload, seed=0)                    # every rank: the same job
+    Cd, Gd = p0["C"].to(dev), p0["G"].to(dev)
+    mine = shard_layers(len(p0["W"]), world, rank)
+    W = [p0["W"][i].to(dev) for i in mine]
+    dims = p0["dims"]
+    def once():
+        out = solver.edit(Cd, Gd, p0["scales"], ne, p0["lamb"], W, check=False)
+        return all_gather_layers(dict(zip(mine, out)), dims, K, dev)
+    for _ in range(3):
+        once()
+    torch.cuda.synchronize(dev); dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    reps = 10
+    for _ in range(reps):
+        once()
+    e1.record(); torch.cuda.synchronize(dev)
+    t = torch.tensor([e0.elapsed_time(e1) / reps], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = t.item()
+    return {"ms_per_job": ms, "value": n / (ms / 1e3), "unit": UNIT, "collective": "1 all_gather_into_tensor (NCCL) of packed edited weights",
+            "scaling": "strong"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--workload", choices=list(WORKLOAD_DESC), default="cfg2")
+    ap.add_argument("--apply-impl", type=int, default=None, help="0 auto, 1 SIMT, 2 tcgen05")
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-budget", type=float, default=20.0)
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the UCE hot path has no CPU fallback (use --impl reference for the CPU baseline)")
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        run_ours(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

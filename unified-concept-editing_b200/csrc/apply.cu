@@ -1,0 +1,171 @@
+// Phase 2 of the UCE edit: per-projection apply, batched over all projections.
+//
+//   low rank :  P = W_old E^T  [d, r]      (the reference's guide outputs v* = W_old c, uce_sd_erase.py:45-53,
+//                                            folded with the edit rows into E = G_e - C_e)
+//               W_new = W_old + P Q         (mat1 @ inverse(mat2), uce_sd_erase.py:61-82)
+//   dense    :  W_new = W_old + W_old D,  D = E^T Q  [K, K]   (when r > K/2)
+//
+// This file holds the fp32 SIMT implementation (grouped over projections through a flattened
+// row-tile list); apply_tc.cu holds the tcgen05 3xTF32 implementation validated against it.
+#include "uce_ws.h"
+#include "gemm_simt.cuh"
+#include <algorithm>
+
+namespace uce {
+
+int apply_tc_lowrank(uce_ws* ws, const LayerRef* layers_dev, const LayerRef* layers_host, int n_layers, int total_tiles64,
+                     cudaStream_t st, int* launches);   // apply_tc.cu
+bool apply_tc_available(const uce_ws* ws);
+
+__device__ __forceinline__ int find_layer(const LayerRef* layers, int n_layers, int tile) {
+    int lo = 0, hi = n_layers - 1;
+    while (lo < hi) {
+        int mid = (lo + hi + 1) >> 1;
+        if (layers[mid].tile_begin <= tile) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+
+// stage 1: P[tile rows, :r_pad] = W_old[rows, :] . E^T
+__global__ void __launch_bounds__(SG_THREADS) apply_simt_p_kernel(const LayerRef* layers, int n_layers, int K, int r_pad,
+                                                                  const float* E, float* P) {
+    __shared__ float As[SG_BK][SG_BM + 4];
+    __shared__ float Bs[SG_BK][SG_BN + 4];
+    const int tile = blockIdx.y;
+    const LayerRef L = layers[find_layer(layers, n_layers, tile)];
+    const int lt = tile - L.tile_begin;
+    SimtGemmArgs<float, float, float, float> g;
+    g.M = min(SG_BM, L.d - lt * SG_BM); g.N = r_pad; g.Kd = K;
+    g.A = L.w_old + (long)lt * SG_BM * K; g.sa_m = K; g.sa_k = 1;
+    g.B = E; g.sb_n = K; g.sb_k = 1;
+    g.C = P + (long)tile * SG_BM * r_pad; g.ldc = r_pad;
+    g.Add = nullptr; g.ldadd = 0; g.alpha = 1.f; g.beta = 0.f; g.lower_only = 0;
+    simt_gemm_tile<float, float, float, float>(g, 0, blockIdx.x, As, Bs);
+}
+
+// stage 2: W_new[rows, :] = W_old[rows, :] + P[rows, :r_pad] . Qt^T   (Qt [K, r_pad])
+__global__ void __launch_bounds__(SG_THREADS) apply_simt_w_kernel(const LayerRef* layers, int n_layers, int K, int r_pad,
+                                                                  const float* Qt, const float* P) {
+    __shared__ float As[SG_BK][SG_BM + 4];
+    __shared__ float Bs[SG_BK][SG_BN + 4];
+    const int tile = blockIdx.y;
+    const LayerRef L = layers[find_layer(layers, n_layers, tile)];
+    const int lt = tile - L.tile_begin;
+    SimtGemmArgs<float, float, float, float> g;
+    g.M = min(SG_BM, L.d - lt * SG_BM); g.N = K; g.Kd = r_pad;
+    g.A = P + (long)tile * SG_BM * r_pad; g.sa_m = r_pad; g.sa_k = 1;
+    g.B = Qt; g.sb_n = r_pad; g.sb_k = 1;
+    g.C = L.w_new + (long)lt * SG_BM * K; g.ldc = K;
+    g.Add = L.w_old + (long)lt * SG_BM * K; g.ldadd = K; g.alpha = 1.f; g.beta = 1.f; g.lower_only = 0;
+    simt_gemm_tile<float, float, float, float>(g, 0, blockIdx.x, As, Bs);
+}
+
+// dense: out[rows, :] = (add ? W_old : 0) + W_old[rows, :] . Dt^T ; out = W_new or scratch
+__global__ void __launch_bounds__(SG_THREADS) apply_simt_dense_kernel(const LayerRef* layers, int n_layers, int K, const float* Dt,
+                                                                      float* scratch) {
+    __shared__ float As[SG_BK][SG_BM + 4];
+    __shared__ float Bs[SG_BK][SG_BN + 4];
+    const int tile = blockIdx.y;
+    const LayerRef L = layers[find_layer(layers, n_layers, tile)];
+    const int lt = tile - L.tile_begin;
+    SimtGemmArgs<float, float, float, float> g;
+    g.M = min(SG_BM, L.d - lt * SG_BM); g.N = K; g.Kd = K;
+    g.A = L.w_old + (long)lt * SG_BM * K; g.sa_m = K; g.sa_k = 1;
+    g.B = Dt; g.sb_n = K; g.sb_k = 1;
+    if (scratch) {   // in-place edit: delta goes to scratch first (other CTAs still read these rows of W_old)
+        g.C = scratch + (long)tile * SG_BM * K; g.ldc = K; g.Add = nullptr; g.ldadd = 0; g.beta = 0.f;
+    } else {
+        g.C = L.w_new + (long)lt * SG_BM * K; g.ldc = K; g.Add = g.A; g.ldadd = K; g.beta = 1.f;
+    }
+    g.alpha = 1.f; g.lower_only = 0;
+    simt_gemm_tile<float, float, float, float>(g, 0, blockIdx.x, As, Bs);
+}
+
+__global__ void add_scratch_kernel(const LayerRef* layers, int n_layers, int K, const float* scratch) {
+    const int tile = blockIdx.x;
+    const LayerRef L = layers[find_layer(layers, n_layers, tile)];
+    const int lt = tile - L.tile_begin;
+    const int rows = min(SG_BM, L.d - lt * SG_BM);
+    const float* s = scratch + (long)tile * SG_BM * K;
+    const float* wo = L.w_old + (long)lt * SG_BM * K;
+    float* wn = L.w_new + (long)lt * SG_BM * K;
+    for (long i = threadIdx.x; i < (long)rows * K; i += blockDim.x) wn[i] = wo[i] + s[i];
+}
+
+__global__ void copy_layers_kernel(const LayerRef* layers, int n_layers, int K) {
+    const int tile = blockIdx.x;
+    const LayerRef L = layers[find_layer(layers, n_layers, tile)];
+    if (L.w_new == L.w_old) return;
+    const int lt = tile - L.tile_begin;
+    const int rows = min(SG_BM, L.d - lt * SG_BM);
+    const float* wo = L.w_old + (long)lt * SG_BM * K;
+    float* wn = L.w_new + (long)lt * SG_BM * K;
+    for (long i = threadIdx.x; i < (long)rows * K; i += blockDim.x) wn[i] = wo[i];
+}
+
+int apply_dev(uce_ws* ws, const float* const* W_old, float* const* W_new, const int* d, int n_layers, cudaStream_t st,
+              bool no_profile) {
+    int slot_begin = 0;
+    const int K = ws->K;
+    if (ws->mode == 0) { set_error("uce_apply before uce_factor"); return UCE_E_STATE; }
+    if (n_layers > ws->layers_cap / 4) { set_error("too many layers per call (%d > %d)", n_layers, ws->layers_cap / 4); return UCE_E_STATE; }
+    // The layer table is staged in a ring of pinned slots: the async H2D copy below reads the slot when it
+    // EXECUTES (also on every replay of a captured graph), so consecutive calls must not share a slot.
+    if (ws->ring_pos + n_layers > ws->layers_cap) ws->ring_pos = 0;
+    slot_begin = ws->ring_pos;
+    ws->ring_pos += n_layers;
+    LayerRef* hl = ws->h_layers + slot_begin;
+    int tiles = 0; bool inplace = false;
+    for (int l = 0; l < n_layers; ++l) {
+        if (!W_old[l] || !W_new[l] || d[l] <= 0) { set_error("layer %d: null pointer or d <= 0", l); return UCE_E_ARG; }
+        hl[l] = LayerRef{W_old[l], W_new[l], d[l], tiles};
+        tiles += ceil_div(d[l], SG_BM);
+        inplace |= (W_old[l] == W_new[l]);
+    }
+    LayerRef* dl = ws->layers_dev + slot_begin;
+    UCE_CUDA(cudaMemcpyAsync(dl, hl, n_layers * sizeof(LayerRef), cudaMemcpyHostToDevice, st));
+    int launches = 0;
+    const int r_pad = ws->rank_pad;
+    const bool prof = ws->profile && !no_profile;
+    ws->pev_mid = 0;
+    if (prof) UCE_CUDA(cudaEventRecord(ws->pev[2], st));
+    if (ws->rank == 0) {   // no active edit rows: the edit is the identity
+        copy_layers_kernel<<<tiles, 256, 0, st>>>(dl, n_layers, K);
+        UCE_LAUNCH_CHECK(); ++launches;
+        ws->launches_apply = launches;
+        if (prof) UCE_CUDA(cudaEventRecord(ws->pev[4], st));
+        return 0;
+    }
+    const size_t need = ws->dense ? (inplace ? (size_t)tiles * SG_BM * K : 0) : (size_t)tiles * SG_BM * r_pad;
+    // P scratch is shared by successive apply calls; they are ordered on one stream (host path: s_compute)
+    if (need > ws->P_cap) {
+        if (ws->P) { UCE_CUDA(cudaStreamSynchronize(st)); UCE_CUDA(cudaFree(ws->P)); ws->P = nullptr; }
+        ws->P_cap = need + need / 4;
+        UCE_CUDA(cudaMalloc(&ws->P, ws->P_cap * sizeof(float)));
+    }
+    if (!ws->dense) {
+        const bool use_tc = (ws->apply_impl == 2) || (ws->apply_impl == 0 && apply_tc_available(ws));
+        if (use_tc) {
+            int rc = apply_tc_lowrank(ws, dl, hl, n_layers, tiles, st, &launches);
+            if (rc) return rc;
+        } else {
+            apply_simt_p_kernel<<<dim3(ceil_div(r_pad, SG_BN), tiles), SG_THREADS, 0, st>>>(dl, n_layers, K, r_pad, ws->E, ws->P);
+            UCE_LAUNCH_CHECK(); ++launches;
+            if (prof) { UCE_CUDA(cudaEventRecord(ws->pev[3], st)); ws->pev_mid = 1; }
+            apply_simt_w_kernel<<<dim3(ceil_div(K, SG_BN), tiles), SG_THREADS, 0, st>>>(dl, n_layers, K, r_pad, ws->Qt, ws->P);
+            UCE_LAUNCH_CHECK(); ++launches;
+        }
+    } else {
+        apply_simt_dense_kernel<<<dim3(ceil_div(K, SG_BN), tiles), SG_THREADS, 0, st>>>(dl, n_layers, K, ws->Dt, inplace ? ws->P : nullptr);
+        UCE_LAUNCH_CHECK(); ++launches;
+        if (inplace) {
+            add_scratch_kernel<<<tiles, 256, 0, st>>>(dl, n_layers, K, ws->P);
+            UCE_LAUNCH_CHECK(); ++launches;
+        }
+    }
+    ws->launches_apply = launches;
+    if (prof) UCE_CUDA(cudaEventRecord(ws->pev[4], st));
+    return 0;
+}
+
+}  // namespace uce

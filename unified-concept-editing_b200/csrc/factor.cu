@@ -1,0 +1,269 @@
+// Phase 1 of the UCE edit: the projection-independent factor.
+//
+// Reference semantics (trainscripts/uce_sd_erase.py:58-82): every projection l gets
+//     W_new = (lamb W + sum_i s_i (W g_i) c_i^T) (lamb I + sum_i s_i c_i c_i^T)^-1 .
+// Since (W g_i) is linear in W, W_new = W + (W E^T) Q with
+//     E = G_e - C_e                              [n_edit, K]
+//     Q = S_e C_e (lamb I + C^T S C)^-1          [n_edit, K]
+// and Q is the same for all projections.  Q is obtained in fp64 from the smaller of two
+// equivalent SPD systems:
+//   dual   (n <= K):  H = lamb S^-1 + C C^T  [n,n];   Q = (rows `edit` of H^-1) C
+//   primal (n >  K):  B = lamb I + C^T S C   [K,K];   Q^T = B^-1 (C_e^T S_e)
+// (Woodbury; the dual form never places lamb next to the O(1e5) Gram entries in fp32 —
+// SURVEY.md §7 H1.)  Internally rows are ordered preserve-first / edit-last.
+//
+// General-size path: blocked right-looking Cholesky (NB = 32) in global memory, diagonal blocks
+// factored and inverted by one CTA, panels / trailing updates / triangular solves expressed
+// as strided fp64 SIMT GEMMs.
+#include "uce_ws.h"
+#include "gemm_simt.cuh"
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+namespace uce {
+
+// ---------------------------------------------------------------------------------------------
+// pack: Cp[r,:] = C[src[r],:]   (all active rows, internal order)
+//       E[j,:]  = G[e_j,:] - C[e_j,:] for the active edit rows (internal rows n_pres + j); pad rows 0
+//       Cs64[r,:] = s_r * Cp[r,:]  (primal only)
+__global__ void pack_rows_kernel(const float* __restrict__ C, const float* __restrict__ G,
+                                 const int* __restrict__ src, const double* __restrict__ dadd, int n_act,
+                                 int n_pres, int rank_pad, int K, float* __restrict__ Cp, float* __restrict__ E,
+                                 double* __restrict__ Cs64) {
+    int r = blockIdx.x;                 // 0 .. n_act + (rank_pad - n_edit) - 1
+    int n_edit = n_act - n_pres;
+    if (r < n_act) {
+        int s = src[r];
+        const float* c = C + (long)s * K;
+        float* cp = Cp + (long)r * K;
+        const bool is_edit = r >= n_pres;
+        const float* g = is_edit ? G + (long)s * K : nullptr;   // edit rows come first in the API: s < n_edit_api
+        float* e = is_edit ? E + (long)(r - n_pres) * K : nullptr;
+        double sc = Cs64 ? dadd[r] : 0.0;
+        for (int k = threadIdx.x; k < K; k += blockDim.x) {
+            float v = c[k];
+            cp[k] = v;
+            if (is_edit) e[k] = g[k] - v;
+            if (Cs64) Cs64[(long)r * K + k] = sc * (double)v;
+        }
+    } else {
+        int j = n_edit + (r - n_act);   // padded E row
+        if (j < rank_pad)
+            for (int k = threadIdx.x; k < K; k += blockDim.x) E[(long)j * K + k] = 0.f;
+    }
+}
+
+// H[r,r] += dadd[r] (r < n) ; H[r,r] = 1 for the padding rows; (dual: dadd = lamb/s_r, primal: lamb)
+__global__ void finish_diag_kernel(double* H, int ld, int n, int n_pad, const double* dadd, double lamb_primal) {
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_pad) return;
+    if (r < n) H[(long)r * ld + r] += dadd ? dadd[r] : lamb_primal;
+    else       H[(long)r * ld + r] = 1.0;
+}
+
+// dual rhs: X[r,j] = (r == n_pres + j);  primal rhs: X[m,j] = Cs64[n_pres + j, m]
+__global__ void fill_rhs_kernel(double* X, int ldx, int n_pad, int n_rhs, int n_pres, const double* Cs64, int K) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    int r = blockIdx.y;
+    if (j >= n_rhs || r >= n_pad) return;
+    double v;
+    if (Cs64) v = (r < K) ? Cs64[(long)(n_pres + j) * K + r] : 0.0;
+    else      v = (r == n_pres + j) ? 1.0 : 0.0;
+    X[(long)r * ldx + j] = v;
+}
+
+// Factor one NB x NB diagonal block in place (lower) and emit its inverse.
+__global__ void __launch_bounds__(UCE_NB* UCE_NB) potrf_diag_kernel(double* H, int ld, int kb, double* Linv, int* flag) {
+    __shared__ double a[UCE_NB][UCE_NB + 1];
+    __shared__ double inv[UCE_NB][UCE_NB + 1];
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    double* blk = H + (long)kb * UCE_NB * ld + (long)kb * UCE_NB;
+    a[ty][tx] = blk[(long)ty * ld + tx];
+    for (int j = 0; j < UCE_NB; ++j) {
+        __syncthreads();
+        if (tx == j && ty == j) {
+            double p = a[j][j];
+            if (!(p > 0.0)) { atomicCAS(flag, 0, 1 + kb); p = 1.0; }
+            a[j][j] = sqrt(p);
+        }
+        __syncthreads();
+        if (tx == j && ty > j) a[ty][j] /= a[j][j];
+        __syncthreads();
+        if (tx > j && ty >= tx) a[ty][tx] -= a[ty][j] * a[tx][j];
+    }
+    __syncthreads();
+    // inverse of the lower-triangular block: thread (ty == 0, tx = c) solves column c
+    if (ty == 0) {
+        const int c = tx;
+        for (int i = 0; i < c; ++i) inv[i][c] = 0.0;
+        inv[c][c] = 1.0 / a[c][c];
+        for (int i = c + 1; i < UCE_NB; ++i) {
+            double s = 0.0;
+            for (int j = c; j < i; ++j) s += a[i][j] * inv[j][c];
+            inv[i][c] = -s / a[i][i];
+        }
+    }
+    __syncthreads();
+    blk[(long)ty * ld + tx] = (tx <= ty) ? a[ty][tx] : 0.0;
+    Linv[((long)kb * UCE_NB + ty) * UCE_NB + tx] = inv[ty][tx];
+}
+
+// Q[j,k] (f32, ld K) and Qt[k,j] (f32, ld rank_pad) from the fp64 solution.
+//   dual  : handled by GEMM (Q = X^T Cp), this kernel only transposes Q -> Qt
+//   primal: X = Q^T [K_pad, n_rhs] -> both
+__global__ void emit_q_kernel(const double* X, int ldx, int from_x, int rank, int rank_pad, int K, float* Q, float* Qt) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    int j = blockIdx.y;
+    if (k >= K || j >= rank_pad) return;
+    float v = 0.f;
+    if (j < rank) {
+        if (from_x) { v = (float)X[(long)k * ldx + j]; Q[(long)j * K + k] = v; }
+        else        v = Q[(long)j * K + k];
+    } else {
+        Q[(long)j * K + k] = 0.f;
+    }
+    Qt[(long)k * rank_pad + j] = v;
+}
+
+#define UCE_RT(expr)                                                                             \
+    do {                                                                                         \
+        cudaError_t _e = (expr);                                                                 \
+        if (_e != cudaSuccess) {                                                                 \
+            set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return (int)_e;                                                                      \
+        }                                                                                        \
+        ++launches;                                                                              \
+    } while (0)
+
+// Blocked Cholesky of the sys_n x sys_n matrix in ws->H (lower), then solve H X = rhs in place.
+// fwd_from: first block row whose rhs is non-zero (dual: rhs = unit vectors of the edit rows).
+static int cholesky_solve(uce_ws* ws, int n_pad, int n_rhs, int ldx, int fwd_from, cudaStream_t st, int& launches) {
+    const int nb = UCE_NB, nblk = n_pad / nb, ld = n_pad;
+    double* H = ws->H; double* X = ws->X; double* Linv = ws->Linv;
+    for (int k = 0; k < nblk; ++k) {
+        potrf_diag_kernel<<<1, dim3(nb, nb), 0, st>>>(H, ld, k, Linv, ws->flag);
+        UCE_RT(cudaGetLastError());
+        int rest = n_pad - (k + 1) * nb;
+        if (rest > 0) {
+            double* panel = H + (long)(k + 1) * nb * ld + (long)k * nb;            // [rest, nb], ld
+            // L_ik = H_ik * Linv_kk^T   (in place)
+            UCE_RT((simt_gemm<double, double, double, double>(st, rest, nb, nb, panel, ld, 1, Linv + (long)k * nb * nb, nb, 1,
+                                                              panel, ld)));
+            // H_ij -= L_ik L_jk^T   (lower tiles only)
+            double* trail = H + (long)(k + 1) * nb * ld + (long)(k + 1) * nb;
+            UCE_RT((simt_gemm<double, double, double, double>(st, rest, rest, nb, panel, ld, 1, panel, ld, 1, trail, ld, -1.0,
+                                                              trail, ld, 1.0, /*lower_only=*/1)));
+        }
+    }
+    // forward: L Y = rhs
+    for (int k = fwd_from; k < nblk; ++k) {
+        double* xk = X + (long)k * nb * ldx;
+        UCE_RT((simt_gemm<double, double, double, double>(st, nb, n_rhs, nb, Linv + (long)k * nb * nb, nb, 1, xk, 1, ldx, xk, ldx)));
+        int rest = n_pad - (k + 1) * nb;
+        if (rest > 0) {
+            double* panel = H + (long)(k + 1) * nb * ld + (long)k * nb;
+            double* xr = X + (long)(k + 1) * nb * ldx;
+            UCE_RT((simt_gemm<double, double, double, double>(st, rest, n_rhs, nb, panel, ld, 1, xk, 1, ldx, xr, ldx, -1.0, xr, ldx,
+                                                              1.0)));
+        }
+    }
+    // backward: L^T X = Y
+    for (int k = nblk - 1; k >= 0; --k) {
+        double* xk = X + (long)k * nb * ldx;
+        UCE_RT((simt_gemm<double, double, double, double>(st, nb, n_rhs, nb, Linv + (long)k * nb * nb, 1, nb, xk, 1, ldx, xk, ldx)));
+        if (k > 0) {
+            double* lrow = H + (long)k * nb * ld;          // L[k-block rows, 0 : k*nb]
+            UCE_RT((simt_gemm<double, double, double, double>(st, k * nb, n_rhs, nb, lrow, 1, ld, xk, 1, ldx, X, ldx, -1.0, X, ldx,
+                                                              1.0)));
+        }
+    }
+    return 0;
+}
+
+int factor_dev(uce_ws* ws, const float* C, const float* G, const float* scales, int n_rows, int n_edit_api, float lamb,
+               cudaStream_t st) {
+    const int K = ws->K;
+    int launches = 0;
+    ws->mode = 0;
+    // The pinned staging below is read by async copies when they execute: wait until the copies of the
+    // previous call have been consumed before overwriting it (skipped while capturing a graph — a captured
+    // graph re-reads the staging on replay, so it stays valid only while the workspace keeps this problem).
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    UCE_CUDA(cudaStreamIsCapturing(st, &cap));
+    if (cap == cudaStreamCaptureStatusNone && ws->stage_pending) { UCE_CUDA(cudaEventSynchronize(ws->ev_stage)); ws->stage_pending = 0; }
+    // ---- host: active rows, internal order = preserve first, edit last ----
+    int n_pres = 0, n_edit = 0;
+    for (int i = n_edit_api; i < n_rows; ++i)
+        if (scales[i] != 0.f) ws->h_src_idx[n_pres++] = i;
+    for (int i = 0; i < n_edit_api; ++i)
+        if (scales[i] != 0.f) ws->h_src_idx[n_pres + n_edit++] = i;
+    const int n = n_pres + n_edit;
+    ws->n_act = n; ws->n_edit = n_edit; ws->n_pres = n_pres; ws->lamb = lamb;
+    ws->rank = n_edit;
+    ws->rank_pad = std::max(UCE_RANK_PAD, round_up(n_edit, UCE_RANK_PAD));
+    ws->dense = (n_edit > K / 2) ? 1 : 0;
+    ws->launches_factor = 0;
+    if (n_edit == 0) { ws->mode = (n <= K) ? 1 : 2; ws->sys_n = 0; return 0; }   // nothing to edit: W_new = W_old
+
+    // the dual system needs S^-1 > 0; with a negative scale fall back to the primal K x K system
+    // (still Cholesky: fails with UCE_E_NOT_SPD at uce_ws_check if lamb I + C^T S C is indefinite)
+    bool dual = (n <= K);
+    for (int r = 0; r < n; ++r) dual = dual && (scales[ws->h_src_idx[r]] > 0.f);
+    for (int r = 0; r < n; ++r) {
+        double s = (double)scales[ws->h_src_idx[r]];
+        ws->h_diag_add[r] = dual ? (double)lamb / s : s;
+    }
+    if (!dual && !ws->Cs64) UCE_CUDA(cudaMalloc(&ws->Cs64, (size_t)ws->max_rows * K * sizeof(double)));
+    if (ws->dense && !ws->Dt) UCE_CUDA(cudaMalloc(&ws->Dt, (size_t)K * K * sizeof(float)));
+    UCE_CUDA(cudaMemcpyAsync(ws->src_idx, ws->h_src_idx, n * sizeof(int), cudaMemcpyHostToDevice, st));
+    UCE_CUDA(cudaMemcpyAsync(ws->diag_add, ws->h_diag_add, n * sizeof(double), cudaMemcpyHostToDevice, st));
+    UCE_CUDA(cudaMemsetAsync(ws->flag, 0, sizeof(int), st));
+    if (cap == cudaStreamCaptureStatusNone) { UCE_CUDA(cudaEventRecord(ws->ev_stage, st)); ws->stage_pending = 1; }
+
+    pack_rows_kernel<<<n + (ws->rank_pad - n_edit), 256, 0, st>>>(C, G, ws->src_idx, ws->diag_add, n, n_pres, ws->rank_pad, K,
+                                                                  ws->Cp, ws->E, dual ? nullptr : ws->Cs64);
+    UCE_RT(cudaGetLastError());
+
+    const int n_sys = dual ? n : K;
+    const int n_pad = round_up(n_sys, UCE_NB);
+    const int ldx = ws->max_rows;   // row stride of X
+    ws->sys_n = n_pad;
+    UCE_CUDA(cudaMemsetAsync(ws->H, 0, (size_t)n_pad * n_pad * sizeof(double), st));
+    if (dual) {
+        // H = Cp Cp^T (fp64 accumulate of exact fp32 products), lower tiles
+        UCE_RT((simt_gemm<float, float, double, double>(st, n, n, K, ws->Cp, K, 1, ws->Cp, K, 1, ws->H, n_pad, 1.0, nullptr, 0, 0.0, 1)));
+        finish_diag_kernel<<<ceil_div(n_pad, 256), 256, 0, st>>>(ws->H, n_pad, n, n_pad, ws->diag_add, 0.0);
+        UCE_RT(cudaGetLastError());
+    } else {
+        // B = Cp^T S Cp : A[m,r] = Cs64[r,m], B[nn,r] = Cp[r,nn]
+        UCE_RT((simt_gemm<double, float, double, double>(st, K, K, n, ws->Cs64, 1, K, ws->Cp, 1, K, ws->H, n_pad, 1.0, nullptr, 0, 0.0, 1)));
+        finish_diag_kernel<<<ceil_div(n_pad, 256), 256, 0, st>>>(ws->H, n_pad, K, n_pad, nullptr, (double)lamb);
+        UCE_RT(cudaGetLastError());
+    }
+    if (ws->debug) {
+        if (!ws->Hcopy) UCE_CUDA(cudaMalloc(&ws->Hcopy, (size_t)ws->sys_max * ws->sys_max * sizeof(double)));
+        UCE_CUDA(cudaMemcpyAsync(ws->Hcopy, ws->H, (size_t)n_pad * n_pad * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    }
+    fill_rhs_kernel<<<dim3(ceil_div(n_edit, 128), n_pad), 128, 0, st>>>(ws->X, ldx, n_pad, n_edit, n_pres, dual ? nullptr : ws->Cs64, K);
+    UCE_RT(cudaGetLastError());
+
+    int rc = cholesky_solve(ws, n_pad, n_edit, ldx, dual ? n_pres / UCE_NB : 0, st, launches);
+    if (rc) return rc;
+
+    if (dual) {
+        // Q[j,k] = sum_r X[r,j] Cp[r,k]
+        UCE_RT((simt_gemm<double, float, double, float>(st, n_edit, K, n, ws->X, 1, ldx, ws->Cp, 1, K, ws->Q, K)));
+    }
+    emit_q_kernel<<<dim3(ceil_div(K, 128), ws->rank_pad), 128, 0, st>>>(ws->X, ldx, dual ? 0 : 1, n_edit, ws->rank_pad, K, ws->Q, ws->Qt);
+    UCE_RT(cudaGetLastError());
+    if (ws->dense) {
+        // Dt[a,b] = D[b,a] = sum_j E[j,b] Q[j,a]
+        UCE_RT((simt_gemm<float, float, double, float>(st, K, K, n_edit, ws->Q, 1, K, ws->E, 1, K, ws->Dt, K)));
+    }
+    ws->mode = dual ? 1 : 2;
+    ws->launches_factor = launches;
+    return 0;
+}
+
+}  // namespace uce

@@ -1,0 +1,274 @@
+// C ABI of libuce_b200 (include/uce_b200.h).
+#include "../../include/uce_b200.h"
+#include "uce_ws.h"
+#include <cstdarg>
+#include <cstring>
+#include <algorithm>
+#include <new>
+
+namespace uce {
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+}  // namespace uce
+using namespace uce;
+
+extern "C" {
+
+int uce_abi_version(void) { return UCE_B200_ABI_VERSION; }
+const char* uce_last_error(void) { return g_err; }
+
+int uce_ws_create(int device, int K, int max_rows, uce_ws** out) {
+    if (!out || K <= 0 || max_rows <= 0) { set_error("uce_ws_create: bad argument"); return UCE_E_ARG; }
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
+        cudaGetLastError();
+        set_error("uce_ws_create: CUDA device %d not available (%d devices)", device, ndev);
+        return UCE_E_NO_DEVICE;
+    }
+    cudaDeviceProp prop;
+    UCE_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        set_error("uce_ws_create: device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+        return UCE_E_NO_DEVICE;
+    }
+    UCE_CUDA(cudaSetDevice(device));
+    uce_ws* ws = new (std::nothrow) uce_ws();
+    if (!ws) { set_error("out of host memory"); return UCE_E_STATE; }
+    ws->device = device; ws->K = K; ws->max_rows = std::max(max_rows, UCE_RANK_PAD);
+    ws->sm_count = prop.multiProcessorCount;
+    ws->sys_max = round_up(K, UCE_NB);
+    const int mr = ws->max_rows;
+    const int rp = round_up(mr, UCE_RANK_PAD);
+    ws->layers_cap = 16384;
+#define WS_ALLOC(ptr, bytes) do { cudaError_t e_ = cudaMalloc((void**)&(ptr), (bytes)); if (e_ != cudaSuccess) { \
+        set_error("cudaMalloc(%zu) failed: %s", (size_t)(bytes), cudaGetErrorString(e_)); uce_ws_destroy(ws); return (int)e_; } } while (0)
+#define WS_HOST(ptr, bytes) do { cudaError_t e_ = cudaMallocHost((void**)&(ptr), (bytes)); if (e_ != cudaSuccess) { \
+        set_error("cudaMallocHost(%zu) failed: %s", (size_t)(bytes), cudaGetErrorString(e_)); uce_ws_destroy(ws); return (int)e_; } } while (0)
+    WS_ALLOC(ws->Cp, (size_t)mr * K * sizeof(float));
+    WS_ALLOC(ws->E, (size_t)rp * K * sizeof(float));
+    WS_ALLOC(ws->Q, (size_t)rp * K * sizeof(float));
+    WS_ALLOC(ws->Qt, (size_t)rp * K * sizeof(float));
+    WS_ALLOC(ws->H, (size_t)ws->sys_max * ws->sys_max * sizeof(double));
+    WS_ALLOC(ws->Linv, (size_t)ws->sys_max * UCE_NB * sizeof(double));
+    WS_ALLOC(ws->X, (size_t)ws->sys_max * mr * sizeof(double));
+    WS_ALLOC(ws->src_idx, (size_t)mr * sizeof(int));
+    WS_ALLOC(ws->diag_add, (size_t)mr * sizeof(double));
+    WS_ALLOC(ws->flag, sizeof(int));
+    WS_ALLOC(ws->layers_dev, (size_t)ws->layers_cap * sizeof(LayerRef));
+    WS_HOST(ws->h_src_idx, (size_t)mr * sizeof(int));
+    WS_HOST(ws->h_diag_add, (size_t)mr * sizeof(double));
+    WS_HOST(ws->h_layers, (size_t)ws->layers_cap * sizeof(LayerRef));
+    WS_HOST(ws->h_flag, sizeof(int));
+    UCE_CUDA(cudaMemset(ws->flag, 0, sizeof(int)));
+    UCE_CUDA(cudaEventCreateWithFlags(&ws->ev_stage, cudaEventDisableTiming));
+    *out = ws;
+    return 0;
+}
+
+int uce_ws_destroy(uce_ws* ws) {
+    if (!ws) return 0;
+    cudaSetDevice(ws->device);
+    cudaDeviceSynchronize();
+    void* dev[] = {ws->Cp, ws->Cs64, ws->E, ws->Q, ws->Qt, ws->Dt, ws->H, ws->Hcopy, ws->Linv, ws->X, ws->src_idx,
+                   ws->diag_add, ws->flag, ws->P, ws->layers_dev, ws->hostpath_C, ws->hostpath_G, ws->hostpath_W};
+    for (void* p : dev) if (p) cudaFree(p);
+    void* host[] = {ws->h_src_idx, ws->h_diag_add, ws->h_layers, ws->h_flag};
+    for (void* p : host) if (p) cudaFreeHost(p);
+    for (auto e : ws->pev) if (e) cudaEventDestroy(e);
+    if (ws->ev_stage) cudaEventDestroy(ws->ev_stage);
+    for (auto e : ws->ev_h2d) cudaEventDestroy(e);
+    for (auto e : ws->ev_done) cudaEventDestroy(e);
+    if (ws->s_compute) cudaStreamDestroy(ws->s_compute);
+    if (ws->s_h2d) cudaStreamDestroy(ws->s_h2d);
+    if (ws->s_d2h) cudaStreamDestroy(ws->s_d2h);
+    delete ws;
+    return 0;
+}
+
+int uce_ws_set_apply_impl(uce_ws* ws, int impl) {
+    if (!ws) return UCE_E_ARG;
+    int prev = ws->apply_impl;
+    ws->apply_impl = impl;
+    return prev;
+}
+
+int uce_ws_set_debug(uce_ws* ws, int on) {
+    if (!ws) return UCE_E_ARG;
+    int prev = ws->debug;
+    ws->debug = on;
+    return prev;
+}
+
+int uce_ws_set_profile(uce_ws* ws, int on) {
+    if (!ws) return UCE_E_ARG;
+    int prev = ws->profile;
+    if (on && !ws->pev[0]) {
+        UCE_CUDA(cudaSetDevice(ws->device));
+        for (auto& e : ws->pev) UCE_CUDA(cudaEventCreate(&e));
+    }
+    ws->profile = on;
+    return prev;
+}
+
+int uce_ws_timings(uce_ws* ws, float ms[3]) {
+    if (!ws || !ms || !ws->pev[0]) { set_error("uce_ws_timings: profiling was never enabled"); return UCE_E_STATE; }
+    UCE_CUDA(cudaSetDevice(ws->device));
+    ms[0] = ms[1] = ms[2] = 0.f;
+    UCE_CUDA(cudaEventSynchronize(ws->pev[4]));
+    UCE_CUDA(cudaEventElapsedTime(&ms[0], ws->pev[0], ws->pev[1]));
+    if (ws->pev_mid) {
+        UCE_CUDA(cudaEventElapsedTime(&ms[1], ws->pev[2], ws->pev[3]));
+        UCE_CUDA(cudaEventElapsedTime(&ms[2], ws->pev[3], ws->pev[4]));
+    } else {
+        UCE_CUDA(cudaEventElapsedTime(&ms[1], ws->pev[2], ws->pev[4]));
+    }
+    return 0;
+}
+
+static int check_factor_args(uce_ws* ws, const void* C, const void* G, const float* scales, int n_rows, int n_edit) {
+    if (!ws || !C || !scales || n_rows <= 0 || n_edit < 0 || n_edit > n_rows || (n_edit > 0 && !G)) {
+        set_error("uce_factor: bad argument (n_rows=%d n_edit=%d)", n_rows, n_edit);
+        return UCE_E_ARG;
+    }
+    if (n_rows > ws->max_rows) {
+        set_error("uce_factor: n_rows=%d exceeds workspace max_rows=%d", n_rows, ws->max_rows);
+        return UCE_E_STATE;
+    }
+    return 0;
+}
+
+int uce_factor_dev_f32(uce_ws* ws, const float* C, const float* G, const float* scales_host, int n_rows, int n_edit,
+                       float lamb, void* stream) {
+    int rc = check_factor_args(ws, C, G, scales_host, n_rows, n_edit);
+    if (rc) return rc;
+    UCE_CUDA(cudaSetDevice(ws->device));
+    if (ws->profile) UCE_CUDA(cudaEventRecord(ws->pev[0], (cudaStream_t)stream));
+    rc = factor_dev(ws, C, G, scales_host, n_rows, n_edit, lamb, (cudaStream_t)stream);
+    if (ws->profile) UCE_CUDA(cudaEventRecord(ws->pev[1], (cudaStream_t)stream));
+    return rc;
+}
+
+int uce_apply_dev_f32(uce_ws* ws, const float* const* W_old, float* const* W_new, const int* d, int n_layers, void* stream) {
+    if (!ws || !W_old || !W_new || !d || n_layers <= 0) { set_error("uce_apply: bad argument"); return UCE_E_ARG; }
+    UCE_CUDA(cudaSetDevice(ws->device));
+    return apply_dev(ws, W_old, W_new, d, n_layers, (cudaStream_t)stream, false);
+}
+
+int uce_ws_check(uce_ws* ws, void* stream) {
+    if (!ws) return UCE_E_ARG;
+    UCE_CUDA(cudaSetDevice(ws->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    UCE_CUDA(cudaMemcpyAsync(ws->h_flag, ws->flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+    UCE_CUDA(cudaStreamSynchronize(st));
+    if (*ws->h_flag != 0) {
+        set_error("Cholesky failed in block %d: lamb*I + C^T S C is not positive definite", *ws->h_flag - 1);
+        return UCE_E_NOT_SPD;
+    }
+    return 0;
+}
+
+int uce_ws_info(uce_ws* ws, int* mode, int* rank, int* dense, int* sys_n, int* launches_factor, int* launches_apply) {
+    if (!ws) return UCE_E_ARG;
+    if (mode) *mode = ws->mode;
+    if (rank) *rank = ws->rank;
+    if (dense) *dense = ws->dense;
+    if (sys_n) *sys_n = ws->sys_n;
+    if (launches_factor) *launches_factor = ws->launches_factor;
+    if (launches_apply) *launches_apply = ws->launches_apply;
+    return 0;
+}
+
+int uce_ws_debug_read(uce_ws* ws, int which, void* out, size_t cap) {
+    if (!ws || !out) return UCE_E_ARG;
+    UCE_CUDA(cudaSetDevice(ws->device));
+    UCE_CUDA(cudaDeviceSynchronize());
+    const size_t n = ws->sys_n, K = ws->K;
+    const void* src = nullptr; size_t bytes = 0;
+    switch (which) {
+        case 0: src = ws->Hcopy; bytes = n * n * sizeof(double); break;
+        case 1: src = ws->H; bytes = n * n * sizeof(double); break;
+        case 2: src = ws->Q; bytes = (size_t)ws->rank * K * sizeof(float); break;
+        case 3: src = ws->E; bytes = (size_t)ws->rank * K * sizeof(float); break;
+        case 4: src = ws->Dt; bytes = K * K * sizeof(float); break;
+        default: set_error("debug_read: unknown selector %d", which); return UCE_E_ARG;
+    }
+    if (!src) { set_error("debug_read: buffer %d not populated (set debug before factor?)", which); return UCE_E_STATE; }
+    if (bytes > cap) { set_error("debug_read: need %zu bytes, have %zu", bytes, cap); return UCE_E_ARG; }
+    UCE_CUDA(cudaMemcpy(out, src, bytes, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+// Whole edit from host buffers: copies pipelined against compute in groups of layers.
+int uce_edit_host_f32(uce_ws* ws, const float* C, const float* G, const float* scales, int n_rows, int n_edit, float lamb,
+                      const float* const* W_old, float* const* W_new, const int* d, int n_layers) {
+    int rc = check_factor_args(ws, C, G, scales, n_rows, n_edit);
+    if (rc) return rc;
+    if (!W_old || !W_new || !d || n_layers <= 0 || n_layers > ws->layers_cap / 4) { set_error("uce_edit_host: bad layer arguments"); return UCE_E_ARG; }
+    UCE_CUDA(cudaSetDevice(ws->device));
+    const int K = ws->K;
+    if (!ws->s_compute) {
+        UCE_CUDA(cudaStreamCreateWithFlags(&ws->s_compute, cudaStreamNonBlocking));
+        UCE_CUDA(cudaStreamCreateWithFlags(&ws->s_h2d, cudaStreamNonBlocking));
+        UCE_CUDA(cudaStreamCreateWithFlags(&ws->s_d2h, cudaStreamNonBlocking));
+        UCE_CUDA(cudaMalloc(&ws->hostpath_C, (size_t)ws->max_rows * K * sizeof(float)));
+        UCE_CUDA(cudaMalloc(&ws->hostpath_G, (size_t)ws->max_rows * K * sizeof(float)));
+    }
+    size_t total = 0;
+    for (int l = 0; l < n_layers; ++l) {
+        if (d[l] <= 0 || !W_old[l] || !W_new[l]) { set_error("uce_edit_host: layer %d invalid", l); return UCE_E_ARG; }
+        total += (size_t)d[l] * K;
+    }
+    if (total > ws->hostpath_W_cap) {
+        if (ws->hostpath_W) { UCE_CUDA(cudaDeviceSynchronize()); UCE_CUDA(cudaFree(ws->hostpath_W)); ws->hostpath_W = nullptr; }
+        UCE_CUDA(cudaMalloc(&ws->hostpath_W, total * sizeof(float)));
+        ws->hostpath_W_cap = total;
+    }
+    // groups of layers of roughly equal bytes: enough groups to overlap H2D(g+1) / apply(g) / D2H(g-1)
+    const int target_groups = std::min(n_layers, 8);
+    const size_t per_group = (total + target_groups - 1) / target_groups;
+    std::vector<int> gbeg{0};
+    { size_t acc = 0; for (int l = 0; l < n_layers; ++l) { acc += (size_t)d[l] * K; if (acc >= per_group && l + 1 < n_layers) { gbeg.push_back(l + 1); acc = 0; } } }
+    gbeg.push_back(n_layers);
+    const int ng = (int)gbeg.size() - 1;
+    while ((int)ws->ev_h2d.size() < ng + 1) {
+        cudaEvent_t a, b;
+        UCE_CUDA(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+        UCE_CUDA(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+        ws->ev_h2d.push_back(a); ws->ev_done.push_back(b);
+    }
+    // concept rows first, then the factor on the compute stream while the weights stream in
+    UCE_CUDA(cudaMemcpyAsync(ws->hostpath_C, C, (size_t)n_rows * K * sizeof(float), cudaMemcpyHostToDevice, ws->s_h2d));
+    if (n_edit > 0) UCE_CUDA(cudaMemcpyAsync(ws->hostpath_G, G, (size_t)n_edit * K * sizeof(float), cudaMemcpyHostToDevice, ws->s_h2d));
+    UCE_CUDA(cudaEventRecord(ws->ev_h2d[ng], ws->s_h2d));
+    UCE_CUDA(cudaStreamWaitEvent(ws->s_compute, ws->ev_h2d[ng], 0));
+    rc = factor_dev(ws, ws->hostpath_C, ws->hostpath_G, scales, n_rows, n_edit, lamb, ws->s_compute);
+    if (rc) { cudaDeviceSynchronize(); return rc; }
+    std::vector<const float*> po(n_layers); std::vector<float*> pn(n_layers);
+    { size_t off = 0; for (int l = 0; l < n_layers; ++l) { po[l] = ws->hostpath_W + off; pn[l] = ws->hostpath_W + off; off += (size_t)d[l] * K; } }
+    int launches = 0;
+    for (int g = 0; g < ng; ++g) {
+        for (int l = gbeg[g]; l < gbeg[g + 1]; ++l)
+            UCE_CUDA(cudaMemcpyAsync(pn[l], W_old[l], (size_t)d[l] * K * sizeof(float), cudaMemcpyHostToDevice, ws->s_h2d));
+        UCE_CUDA(cudaEventRecord(ws->ev_h2d[g], ws->s_h2d));
+        UCE_CUDA(cudaStreamWaitEvent(ws->s_compute, ws->ev_h2d[g], 0));
+        rc = apply_dev(ws, po.data() + gbeg[g], pn.data() + gbeg[g], d + gbeg[g], gbeg[g + 1] - gbeg[g], ws->s_compute, true);
+        if (rc) { cudaDeviceSynchronize(); return rc; }
+        launches += ws->launches_apply;
+        UCE_CUDA(cudaEventRecord(ws->ev_done[g], ws->s_compute));
+        UCE_CUDA(cudaStreamWaitEvent(ws->s_d2h, ws->ev_done[g], 0));
+        for (int l = gbeg[g]; l < gbeg[g + 1]; ++l)
+            UCE_CUDA(cudaMemcpyAsync(W_new[l], pn[l], (size_t)d[l] * K * sizeof(float), cudaMemcpyDeviceToHost, ws->s_d2h));
+    }
+    ws->launches_apply = launches;
+    UCE_CUDA(cudaStreamSynchronize(ws->s_d2h));
+    UCE_CUDA(cudaStreamSynchronize(ws->s_compute));
+    return uce_ws_check(ws, ws->s_compute);
+}
+
+}  // extern "C"

@@ -1,0 +1,67 @@
+// Internal definition of the opaque workspace behind include/uce_b200.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <vector>
+#include "uce_common.cuh"
+
+constexpr int UCE_NB = 32;        // Cholesky block size (fp64)
+constexpr int UCE_RANK_PAD = 16;  // rank of E/Q is padded to a multiple of this (UMMA N granularity)
+
+struct uce_ws {
+    int device = 0, K = 0, max_rows = 0;
+    int sm_count = 0;
+    int sys_max = 0;      // largest padded linear system (round_up(K, NB))
+    // ---- state of the last factor ----
+    int mode = 0;         // 0 none, 1 dual (n x n), 2 primal (K x K)
+    int n_act = 0, n_edit = 0, n_pres = 0;   // active (scale != 0) rows
+    int sys_n = 0;        // padded system size
+    int rank = 0, rank_pad = 0;
+    int dense = 0;
+    float lamb = 0.f;
+    int launches_factor = 0, launches_apply = 0;
+    int apply_impl = 0;   // 0 auto, 1 simt, 2 tcgen05
+    int debug = 0;
+    int profile = 0;
+    cudaEvent_t pev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // factor begin/end, apply begin/mid/end
+    int pev_mid = 0;
+    // ---- device buffers ----
+    float*  Cp = nullptr;     // [max_rows, K] active concept rows, internal order (preserve first, edit last)
+    double* Cs64 = nullptr;   // [max_rows, K] s_r * Cp (primal only, lazily allocated)
+    float*  E = nullptr;      // [rank_pad, K]  G_e - C_e  (zero padded rows)
+    float*  Q = nullptr;      // [rank_pad, K]
+    float*  Qt = nullptr;     // [K, rank_pad]
+    float*  Dt = nullptr;     // [K, K]   dense factor (lazily allocated)
+    double* H = nullptr;      // [sys_max, sys_max]
+    double* Hcopy = nullptr;  // debug copy of the assembled system (lazily allocated)
+    double* Linv = nullptr;   // [sys_max/NB][NB][NB]
+    double* X = nullptr;      // [sys_max, max_rows]  rhs / solution
+    int*    src_idx = nullptr;   // [max_rows] API row of internal row r
+    double* diag_add = nullptr;  // [max_rows] lamb / s_r  (dual)  or s_r (primal)
+    int*    flag = nullptr;      // device: 0 ok, else 1 + failing block
+    float*  P = nullptr;         // apply scratch [rows_pad_total, rank_pad]
+    size_t  P_cap = 0;
+    uce::LayerRef* layers_dev = nullptr;
+    int layers_cap = 0;
+    int ring_pos = 0;
+    int stage_pending = 0;
+    cudaEvent_t ev_stage = nullptr;   // marks consumption of the factor's pinned staging
+    // ---- pinned host staging ----
+    int*    h_src_idx = nullptr;
+    double* h_diag_add = nullptr;
+    uce::LayerRef* h_layers = nullptr;
+    int*    h_flag = nullptr;
+    // ---- host-buffer path (uce_edit_host_f32) ----
+    cudaStream_t s_compute = nullptr, s_h2d = nullptr, s_d2h = nullptr;
+    float* hostpath_C = nullptr; float* hostpath_G = nullptr;
+    float* hostpath_W = nullptr; size_t hostpath_W_cap = 0;   // device staging for all layers (in place)
+    std::vector<cudaEvent_t> ev_h2d, ev_done;
+};
+
+namespace uce {
+// factor.cu
+int factor_dev(uce_ws* ws, const float* C, const float* G, const float* scales_host, int n_rows, int n_edit,
+               float lamb, cudaStream_t st);
+// apply.cu
+int apply_dev(uce_ws* ws, const float* const* W_old, float* const* W_new, const int* d, int n_layers,
+              cudaStream_t st, bool no_profile = false);
+}  // namespace uce

@@ -1,0 +1,88 @@
+"""Drop-in for the reference's iterative debias edit, ``get_ratios()`` / ``UCE()`` of
+trainscripts/uce_sd_debias.py:14-149, with the solve on the B200 solver.
+
+Per iteration the reference regenerates images with the current weights, classifies them,
+turns the label fractions into ``direction_scale`` (ratio = desired − observed, dead-band
+``max_diff``; :28-35), nudges the edit targets v*_e += sum_j ratio_ej (W_old c_dj) IN PLACE
+(cumulative over iterations, :124-126) and re-solves from W_old (:114-140).  In row form the
+cumulative target is the guide row  g_e = c_e + sum_j A_ej c_dj  with A the running sum of the
+direction scales, which is what is handed to the solver.
+"""
+from __future__ import annotations
+
+import os
+import time
+
+import numpy as np
+import torch
+
+from .concepts import embed_concepts, select_projections
+from .solver import EditSolver
+
+
+def get_ratios(pipe, clip, uce_module_names, uce_weights, edit_concepts, debias_concepts, desired_ratios, max_diff,
+               step_size=0.1, num_images_per_prompt=10, num_inference_steps=20, guidance_scale=7.5):
+    """Mirror of uce_sd_debias.py:14-35 (``step_size`` is accepted and unused, as there)."""
+    state = {name + ".weight": w for name, w in zip(uce_module_names, uce_weights)}
+    pipe.unet.load_state_dict(state, strict=False)
+    direction_scale = []
+    for concept in edit_concepts:
+        images = pipe(concept, num_inference_steps=num_inference_steps, num_images_per_prompt=num_images_per_prompt,
+                      guidance_scale=guidance_scale).images
+        results = clip(images, candidate_labels=debias_concepts)
+        top1 = np.array([r[0]["label"] for r in results])
+        ratios = np.array([want - (np.sum(top1 == c) / len(top1)) for c, want in zip(debias_concepts, desired_ratios)])
+        if max(ratios) < max_diff and abs(min(ratios)) < max_diff:
+            ratios = 0 * ratios
+        direction_scale.append(ratios)
+    return np.array(direction_scale)
+
+
+def UCE(pipe, clip, edit_concepts, debias_concepts, preserve_concepts, edit_scale, preserve_scale, lamb, save_dir, exp_name,
+        max_diff, step_size, num_images_per_prompt, num_inference_steps, guidance_scale,
+        max_iterations=30, desired_ratios=(0.5, 0.5), device="cuda:0", solver: EditSolver | None = None, verbose=True):
+    projections = select_projections(pipe.unet)
+    names = [n for n, _ in projections]
+    dev = torch.device(device)
+    rows = embed_concepts(pipe, list(edit_concepts) + list(debias_concepts) + list(preserve_concepts), device)
+    c_edit = torch.stack([rows[e] for e in edit_concepts]).to(dev)
+    c_deb = torch.stack([rows[c] for c in debias_concepts]).to(dev)
+    c_pres = [rows[p].to(dev) for p in preserve_concepts]
+    C = torch.cat([c_edit] + ([torch.stack(c_pres)] if c_pres else []), 0)
+    scales = [float(edit_scale)] * len(edit_concepts) + [float(preserve_scale)] * len(c_pres)
+    w_old = [m.weight.detach().to(dev, torch.float32).contiguous().clone() for _, m in projections]
+    K = w_old[0].shape[1]
+    own = solver is None
+    if own:
+        solver = EditSolver(K, max(16, C.shape[0]), dev)
+
+    pipe = pipe.to(torch.bfloat16)          # generation dtype (uce_sd_debias.py:90); the solve stays fp32
+    current = [w.clone() for w in w_old]    # weights the next generation round uses (:45-46)
+    A = np.zeros((len(edit_concepts), len(debias_concepts)), dtype=np.float64)
+    start = time.time()
+    iterations = 0
+    for iteration in range(max_iterations):
+        direction_scale = get_ratios(pipe=pipe, clip=clip, uce_module_names=names, uce_weights=current,
+                                     edit_concepts=edit_concepts, debias_concepts=debias_concepts,
+                                     desired_ratios=desired_ratios, max_diff=max_diff, step_size=step_size,
+                                     num_images_per_prompt=num_images_per_prompt,
+                                     num_inference_steps=num_inference_steps, guidance_scale=guidance_scale)
+        if np.abs(direction_scale).max() == 0:
+            if verbose:
+                print("All concepts are debiased")
+            break
+        A += direction_scale
+        G = c_edit + torch.from_numpy(A).to(dev, torch.float64).matmul(c_deb.to(torch.float64)).to(torch.float32)
+        current = solver.edit(C, G, scales, len(edit_concepts), lamb, w_old)
+        iterations += 1
+    elapsed = time.time() - start
+    state = {name + ".weight": w for name, w in zip(names, current)}
+    if save_dir is not None:
+        from safetensors.torch import save_file
+        os.makedirs(save_dir, exist_ok=True)
+        save_file({k: v.detach().cpu().contiguous() for k, v in state.items()}, os.path.join(save_dir, exp_name + ".safetensors"))
+    if own:
+        solver.close()
+    if verbose:
+        print(f"\n\nDebiased concepts using UCE\nModel edited in {elapsed} seconds\n")
+    return state

@@ -30,6 +30,19 @@ sys.path.insert(0, ROOT)
 
 import torch  # noqa: E402
 
+_T0 = time.time()
+
+
+def log(msg):
+    print(f"[bench +{time.time() - _T0:6.1f}s] {msg}", file=sys.stderr, flush=True)
+
+
+def host_threads():
+    """Threads for the CPU arm: all cores up to a cap (the reference's loop is thousands of tiny rank-1
+    updates; beyond a few dozen threads torch's intra-op pool only adds synchronisation cost)."""
+    return int(os.environ.get("UCE_CPU_THREADS", min(os.cpu_count() or 1, 32)))
+
+
 METRIC = "concepts/sec (edit-solve)"
 UNIT = "concepts/s"
 WORKLOAD_DESC = {
@@ -83,7 +96,7 @@ class ClockSampler:
 def cpu_port_time(prob, budget_s=20.0, min_reps=1, stratify=1):
     """Time the fp32 restatement of the reference (oracle.erase_port_f32) on the host cores."""
     from oracle import uce_oracle as O
-    torch.set_num_threads(os.cpu_count() or 1)
+    torch.set_num_threads(host_threads())
     ne = prob["n_edit"]
     ce, cp = prob["C"][:ne], prob["C"][ne:]
     W = prob["W"][::stratify]
@@ -122,7 +135,7 @@ def run_reference(args, rank, world):
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD_DESC[args.workload], "implementation": "CPU fp32 restatement of uce_sd_erase.py:45-82 (oracle port)"},
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": host_threads(), "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -157,12 +170,14 @@ def run_ours(args, rank, world, local_rank):
 
     sampler = ClockSampler(local_rank)
     sampler.start()
+    log(f"inputs resident: {R} weight sets, {w_bytes/1e6:.1f} MB each")
     # ---- warm-up (eager), then one CUDA graph per weight set ----
     for i in range(max(args.warmup, 3)):
         step(i)
     solver.check()
     info = solver.info()
     launches_per_step = info["launches_factor"] + info["launches_apply"]
+    log(f"eager warm-up done: {info}")
     graphs = None
     if not args.no_graph:
         graphs = []
@@ -178,6 +193,7 @@ def run_ours(args, rank, world, local_rank):
         for i in range(max(args.warmup, 3)):
             graphs[i % R].replay()
     torch.cuda.synchronize(dev)
+    log("graphs captured and replayed" if graphs else "eager mode")
 
     def barrier():
         if world > 1:
@@ -196,6 +212,7 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.synchronize(dev); barrier()
     total_ms = ev0.elapsed_time(ev1)
     solver.check()
+    log(f"timed region: {total_ms / args.steps:.4f} ms/step")
 
     # ---- per-kernel durations (profile events inside the library, eager launches) ----
     solver.set_profile(True)
@@ -206,6 +223,7 @@ def run_ours(args, rank, world, local_rank):
         tf.append(a); t1.append(b); t2.append(c)
     solver.set_profile(False)
     f_ms, a1_ms, a2_ms = (sum(x) / len(x) for x in (tf, t1, t2))
+    log(f"profiled: factor {f_ms:.4f} ms, apply {a1_ms:.4f} + {a2_ms:.4f} ms")
 
     # ---- end to end through the host-buffer C-ABI call ----
     h_in = [w.pin_memory() for w in prob["W"]]
@@ -221,6 +239,7 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.synchronize(dev)
     e2e_ms = 1e3 * (time.perf_counter() - t0) / e2e_steps
     clocks = sampler.stop()
+    log(f"e2e: {e2e_ms:.3f} ms/step")
 
     # ---- reductions over ranks ----
     if world > 1:
@@ -250,8 +269,10 @@ def run_ours(args, rank, world, local_rank):
                 "algorithmic_bytes": alg_bytes, "kernel_ms": dom_ms, "stage_ms": [a1_ms, a2_ms], "factor_ms": f_ms}
         cpu = None
         if not args.no_cpu:
+            log(f"cpu baseline on {host_threads()} threads ...")
             t_cpu, reps, nl, frac = cpu_port_time(prob, budget_s=args.cpu_budget, min_reps=1)
-            cpu = {"value": n / t_cpu, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+            log(f"cpu baseline: {t_cpu:.3f} s per solve ({reps} reps)")
+            cpu = {"value": n / t_cpu, "unit": UNIT, "cores": host_threads(), "kind": "port",
                    "sample": f"{reps} repetitions of the full {args.workload} workload ({nl} projections), oracle.erase_port_f32, torch {torch.get_num_threads()} threads"}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",

@@ -1,0 +1,105 @@
+"""CPU tests of the host logic: CLI surface (flags/defaults of the reference scripts), concept
+parsing/expansion rules, projection selection, sharding layout, C-ABI symbols."""
+import ctypes
+import importlib.util
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _load(path, name):
+    spec = importlib.util.spec_from_file_location(name, os.path.join(ROOT, path))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m
+
+
+def test_erase_cli_flags_and_defaults():
+    m = _load("trainscripts/uce_sd_erase.py", "cli_erase")
+    a = m.build_parser().parse_args(["--edit_concepts", "Van Gogh; Picasso", "--concept_type", "art"])
+    assert (a.model_id, a.device, a.erase_scale, a.preserve_scale, a.lamb) == ("CompVis/stable-diffusion-v1-4", "cuda:0", 1, 1, 0.5)
+    assert (a.expand_prompts, a.save_dir, a.exp_name, a.guide_concepts, a.preserve_concepts) == ("false", "../uce_models", None, None, None)
+    edit, guide, pres = m.resolve(a)
+    assert edit == ["Van Gogh", "Picasso"] and guide == ["art", "art"] and pres == []
+    a = m.build_parser().parse_args(["--edit_concepts", "dog", "--concept_type", "object", "--expand_prompts", "true",
+                                     "--preserve_concepts", "cat; bird"])
+    edit, guide, pres = m.resolve(a)
+    assert edit == ["dog", "image of dog", "photo of dog", "portrait of dog", "picture of dog", "painting of dog"]
+    assert guide == ["", "image of ", "photo of ", "portrait of ", "picture of ", "painting of "]
+    assert pres == ["cat", "bird"]
+    a = m.build_parser().parse_args(["--edit_concepts", "a;b", "--guide_concepts", "x;y;z", "--concept_type", "art"])
+    with pytest.raises(Exception):
+        m.resolve(a)
+    with pytest.raises(SystemExit):
+        m.build_parser().parse_args(["--edit_concepts", "a", "--concept_type", "unsafe"])
+
+
+def test_art_expansion_wording():
+    from uce_b200.concepts import expand_prompts
+    e, g = expand_prompts(["Monet"], ["art"], "art")
+    assert e[1:] == ["painting by Monet", "art by Monet", "artwork by Monet", "picture by Monet", "style of Monet"]
+    assert g[1:] == ["painting by art", "art by art", "artwork by art", "picture by art", "style of art"]
+
+
+def test_debias_cli_flags_and_defaults():
+    m = _load("trainscripts/uce_sd_debias.py", "cli_debias")
+    a = m.build_parser().parse_args(["--edit_concepts", "doctor", "--debias_concepts", "male; female"])
+    assert a.desired_ratios == [0.5, 0.5] and a.max_iterations == 30 and a.max_diff == 0.05 and a.step_size == 0.1
+    assert (a.num_images_per_prompt, a.num_inference_steps, a.guidance_scale, a.edit_scale) == (10, 20, 7.5, 1)
+
+
+def test_projection_selection_and_token_rule():
+    from oracle.fake_pipe import FakePipe, layer_table
+    from uce_b200.concepts import concept_row, select_projections
+    pipe = FakePipe(layer_table("sd14"))
+    sel = select_projections(pipe.unet)
+    assert len(sel) == 32 and all("attn2" in n and n.endswith(("to_k", "to_v")) for n, _ in sel)
+    assert sel[0][0] == "down_blocks.0.attentions.0.transformer_blocks.0.attn2.to_k"
+    assert sel[-1][0] == "mid_block.attentions.0.transformer_blocks.0.attn2.to_v"
+    assert sum(m.weight.shape[0] for _, m in sel) == 24960
+    assert len(select_projections(FakePipe(layer_table("sdxl")).unet)) == 140
+    emb = pipe.encode_prompt("a b c")[0]
+    assert torch.equal(concept_row(pipe, "a b c", "cpu"), emb[0, 3])     # BOS + 3 words: last real token index 3
+    assert torch.equal(concept_row(pipe, "", "cpu"), pipe.encode_prompt("")[0][0, 0])   # empty prompt keeps BOS
+
+
+def test_build_rows_keeps_duplicates():
+    from uce_b200.erase import build_rows
+    rows = {"a": torch.ones(4), "b": 2 * torch.ones(4), "g": torch.zeros(4)}
+    C, G, s, ne = build_rows(rows, ["a", "a"], ["g", "g"], ["b", "b", "b"], 2.0, 3.0)
+    assert C.shape == (5, 4) and G.shape == (2, 4) and ne == 2 and s == [2.0, 2.0, 3.0, 3.0, 3.0]
+
+
+def test_pack_layout_roundtrip():
+    from uce_b200.sharding import pack_layout, shard_layers
+    dims = [320, 640, 1280, 320, 640]
+    per, where = pack_layout(dims, 8, 2)
+    assert shard_layers(5, 2, 0) == [0, 2, 4] and shard_layers(5, 2, 1) == [1, 3]
+    assert per == (320 + 1280 + 640) * 8
+    assert where[2] == (0, 320 * 8) and where[3] == (1, 640 * 8)
+
+
+def test_c_abi_exports_every_declared_symbol():
+    """The shared library loads without a GPU and exports exactly what include/uce_b200.h declares."""
+    from uce_b200 import _native
+    hdr = open(os.path.join(ROOT, "include", "uce_b200.h")).read()
+    declared = set(re.findall(r"\b(uce_[a-z0-9_]+)\s*\(", hdr))
+    lib = ctypes.CDLL(_native.LIB_PATH)
+    for sym in declared:
+        assert hasattr(lib, sym), sym
+    assert declared == set(_native.SIGNATURES), declared ^ set(_native.SIGNATURES)
+    assert _native.lib().uce_abi_version() == 1
+
+
+def test_no_gpu_fails_loudly():
+    from uce_b200.solver import EditSolver
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(RuntimeError):
+        EditSolver(768, 16, "cuda:0")
+    with pytest.raises(RuntimeError):
+        EditSolver(768, 16, "cpu")

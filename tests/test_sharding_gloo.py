@@ -1,0 +1,54 @@
+"""world_size-2 gloo test (CPU) of the multi-GPU host logic: round-robin layer sharding,
+packed layout, ONE all-gather, reassembly.  The per-shard edit is done by the oracle here (test
+infrastructure) — on GPUs the same code path runs the CUDA solver per rank (bench.py "sharded")."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import uce_oracle as O
+        from uce_b200.sharding import all_gather_layers, shard_layers
+        from uce_b200.synthetic import concept_rows, weights
+        K, dims = 32, [8, 24, 16, 8, 40]
+        rows = concept_rows(9, K, seed=1)
+        W = weights(dims, K, seed=1)
+        mine = shard_layers(len(W), world, rank)
+        local = {}
+        for i in mine:
+            e = O.erase_exact_f64([W[i]], rows[:2], rows[7:9], rows[2:7], 1.0, 1.0, 0.5)[0]
+            local[i] = torch.from_numpy(e).float()
+        full = all_gather_layers(local, dims, K, torch.device("cpu"))
+        ref = [torch.from_numpy(e).float() for e in O.erase_exact_f64(W, rows[:2], rows[7:9], rows[2:7], 1.0, 1.0, 0.5)]
+        ok = all(torch.equal(a, b) for a, b in zip(full, ref)) and len(full) == len(dims)
+        q.put((rank, ok))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_layer_sharding_allgather_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, True), (1, True)]

@@ -62,7 +62,7 @@ def test_golden_erase(name):
 def _numpy_system(C, scales, n_edit, lamb, K):
     """fp64 restatement of the system the device assembles (internal order: preserve first, edit last)."""
     C = C.double().numpy()
-    s = np.asarray(scales, dtype=np.float64)
+    s = np.asarray(scales, dtype=np.float32).astype(np.float64)     # the C ABI takes fp32 scales
     order = list(range(n_edit, C.shape[0])) + list(range(n_edit))
     Cp, sp = C[order], s[order]
     if C.shape[0] <= K:
@@ -94,7 +94,7 @@ def test_intermediates(n_edit, n_pres, K):
     L_ref = np.linalg.cholesky(H_ref)
     assert np.abs(L - L_ref).max() <= 1e-9 * np.abs(L_ref).max(), "cholesky factor"
     # Q = S_e C_e (lamb I + C^T S C)^-1
-    Cd, sd = C.double().numpy(), np.asarray(scales)
+    Cd, sd = C.double().numpy(), np.asarray(scales, dtype=np.float32).astype(np.float64)
     B = lamb * np.eye(K) + Cd.T @ (sd[:, None] * Cd)
     Q_ref = np.linalg.solve(B, (sd[:n_edit, None] * Cd[:n_edit]).T).T
     Q = s.debug_read(2).double().numpy()
@@ -104,7 +104,7 @@ def test_intermediates(n_edit, n_pres, K):
     s.close()
 
 
-@pytest.mark.parametrize("impl", [1])
+@pytest.mark.parametrize("impl", [1, 2])
 def test_cfg2_full_model(impl):
     """BASELINE configs[1]: 50 erase + 100 preserve, all 32 SD-1.4 projections."""
     from uce_b200.synthetic import problem
@@ -257,4 +257,29 @@ def test_linearity_in_w():
     c = _run(s, p["C"], p["G"], p["scales"], p["n_edit"], p["lamb"], [x + y for x, y in zip(W1, W2)])
     for x, y, z in zip(a, b, c):
         assert O.rel_fro(x + y, z) <= 1e-6
+    s.close()
+
+
+@pytest.mark.parametrize("n_edit,K,dims", [(2, 768, [320, 320]), (33, 768, [128, 64, 200]), (50, 768, [320, 640, 1280]),
+                                           (90, 256, [128, 384]), (128, 512, [256, 72]), (10, 2048, [640, 1280])])
+def test_tcgen05_apply_matches_simt_and_oracle(n_edit, K, dims):
+    """The tcgen05 3xTF32 fused apply against the SIMT fp32 apply and the fp64 oracle: rank pads 32..128,
+    row tails (d % 128 != 0), SD-1.4 and SDXL text widths."""
+    from uce_b200.synthetic import concept_rows, weights
+    n_pres = 20
+    rows = concept_rows(n_edit + n_pres + n_edit, K, seed=n_edit)
+    C, G = rows[: n_edit + n_pres], rows[n_edit + n_pres:]
+    W = weights(dims, K, seed=4)
+    scales = [1.0] * (n_edit + n_pres)
+    s = _solver(K, C.shape[0])
+    simt = _run(s, C, G, scales, n_edit, 0.5, W, impl=1)
+    tc = _run(s, C, G, scales, n_edit, 0.5, W, impl=2)
+    assert s.info()["launches_apply"] == 1
+    exact = O.erase_exact_f64(W, C[:n_edit], G, C[n_edit:], 1.0, 1.0, 0.5)
+    for a, b, e in zip(simt, tc, exact):
+        assert O.rel_fro(b, e) <= TOL_EXACT, ("tc vs exact", O.rel_fro(b, e), O.rel_fro(a, e))
+        assert O.rel_fro(b, a) <= 2e-6, ("tc vs simt", O.rel_fro(b, a))
+    tc2 = _run(s, C, G, scales, n_edit, 0.5, W, impl=2, inplace=True)
+    for a, b in zip(tc, tc2):
+        assert torch.equal(a, b)
     s.close()

@@ -1,9 +1,469 @@
-// tcgen05 3xTF32 implementation of the low-rank apply (placeholder until the kernel lands).
+// Fused low-rank apply on the 5th-gen tensor cores (tcgen05 / TMEM / TMA), fp32 fidelity via 3xTF32.
+//
+//   W_new[rows,:] = W_old[rows,:] + (W_old[rows,:] E^T) Q            (uce_sd_erase.py:45-82, see apply.cu)
+//
+// One CTA per 128-row tile of one projection.  HBM traffic = read W_old once + write W_new once; the second
+// read of the tile (epilogue addend) is an L2 hit.
+//
+//   phase A  P[128,R] = W_tile[128,K] . E[R,K]^T   accumulated in TMEM columns [0,R)
+//            * 8 producer warps stream W_tile from global (LDG.128, 4 chunks in flight per thread), split every
+//              value into hi = rna_tf32(w) and lo = w - hi IN REGISTERS and store both into 128B-swizzled K-major
+//              smem tiles (an elementwise transform TMA cannot do)
+//            * 1 TMA warp fetches the matching [R,32] tiles of the pre-split E_hi / E_lo (L2 resident)
+//            * 1 MMA thread issues per 8-wide k-step  hi.hi + lo.hi + hi.lo  (tcgen05.mma kind::tf32, M=128, N=R)
+//   phase B  dW^T[K-chunk of 128, 128 rows] = Qt[128,R] . P[128,R]^T in two ping-pong TMEM accumulators
+//            * P is read back from TMEM, split hi/lo and written to smem as the B operand
+//            * Qt_hi / Qt_lo tiles arrive by TMA; 3 MMAs per k-step again
+//            * the transposed product puts consecutive W columns on consecutive TMEM lanes, so the epilogue's
+//              per-register global accesses (W_old addend load, W_new store) are 128-byte coalesced per warp
+//
+// Requirements: K % 128 == 0, rank_pad in {32, 64, 96, 128}, 16-byte aligned weights.  Anything else goes to
+// the SIMT kernels in apply.cu.
 #include "uce_ws.h"
+#include <cuda.h>
+#include <cstdint>
+
 namespace uce {
-bool apply_tc_available(const uce_ws*) { return false; }
-int apply_tc_lowrank(uce_ws*, const LayerRef*, const LayerRef*, int, int, cudaStream_t, int*) {
-    set_error("tcgen05 apply not built");
-    return UCE_E_STATE;
+
+constexpr int TC_TILE_M = 128;
+constexpr int TC_PRODUCER_WARPS = 8;
+constexpr int TC_THREADS = (TC_PRODUCER_WARPS + 2) * 32;   // + TMA warp + MMA warp
+constexpr int TC_QT_STAGES = 2;
+constexpr int TC_PF = 4;                                    // W chunks in flight per producer thread
+
+struct TcMaps { CUtensorMap e_hi, e_lo, qt_hi, qt_lo; };
+
+// ------------------------------------------------------------------------------------------ PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    long long t0 = 0;
+    for (uint32_t spin = 0;; ++spin) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (done) return;
+        if ((spin & 255u) == 255u) {          // watchdog: a protocol bug must fail loudly, never hang the GPU
+            const long long now = clock64();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 4000000000ll) {
+                printf("uce apply_tc: mbarrier timeout (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
+                __trap();
+            }
+        }
+    }
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst), "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)map) : "memory");
+}
+
+// K-major, 128B-swizzled operand tile (rows of 32 fp32 = 128 B, 8-row groups 1024 B apart), Blackwell descriptor v1
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);          // start address, 16-byte units, bits [0,14)
+    d |= (uint64_t)1 << 16;                            // leading byte offset (unused for swizzled K-major), bits [16,30)
+    d |= (uint64_t)(1024 >> 4) << 32;                  // stride byte offset between 8-row groups, bits [32,46)
+    d |= (uint64_t)1 << 46;                            // descriptor version 1 (sm_100)
+    d |= (uint64_t)2 << 61;                            // layout type SWIZZLE_128B
+    return d;
+}
+// kind::tf32, fp32 accumulate, A and B K-major
+__device__ __forceinline__ uint32_t umma_idesc_tf32(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float tf32_hi(float x) {
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+    return __uint_as_float(u);
+}
+__device__ __forceinline__ float4 ldg_nc_v4(const float* p) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ float ldg_f32(const float* p) {
+    float r;
+    asm volatile("ld.global.f32 %0, [%1];" : "=f"(r) : "l"(p) : "memory");
+    return r;
+}
+__device__ __forceinline__ void sts_v4(uint32_t addr, float a, float b, float c, float d) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+__device__ __forceinline__ int tc_find_layer(const LayerRef* layers, int n_layers, int tile) {
+    int lo = 0, hi = n_layers - 1;
+    while (lo < hi) {
+        int mid = (lo + hi + 1) >> 1;
+        if (layers[mid].tile_begin <= tile) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+
+// Shared-memory carve-up (bytes), identical on host and device.
+struct TcSmem {
+    int stages_a;        // W/E pipeline depth
+    int stage_a_bytes;   // W_hi 16K + W_lo 16K + E_hi R*128 + E_lo R*128
+    int region_a;        // max(stages_a * stage_a_bytes, P_hi + P_lo)
+    int qt_off;          // Qt stages after region A
+    int bar_off;
+    int total;
+};
+__host__ __device__ inline TcSmem tc_smem_layout(int R) {
+    TcSmem s;
+    s.stages_a = (R <= 64) ? 3 : 2;
+    s.stage_a_bytes = 32768 + 2 * R * 128;
+    int a = s.stages_a * s.stage_a_bytes;
+    int p = 2 * TC_TILE_M * R * 4;
+    s.region_a = a > p ? a : p;
+    s.qt_off = s.region_a;
+    s.bar_off = s.qt_off + TC_QT_STAGES * 32768;
+    s.total = s.bar_off + 256;
+    return s;
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+apply_tc_kernel(const LayerRef* __restrict__ layers, int n_layers, int K, int R,
+                const __grid_constant__ TcMaps maps) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // dynamic smem base is at least 16-byte aligned; swizzled tiles need 1024
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const TcSmem L = tc_smem_layout(R);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    // ---- barriers ----
+    const uint32_t bars = base + L.bar_off;
+    auto bar_full_w = [&](int s) { return bars + 8u * s; };               // [0,3)
+    auto bar_full_e = [&](int s) { return bars + 8u * (3 + s); };         // [3,6)
+    auto bar_empty  = [&](int s) { return bars + 8u * (6 + s); };         // [6,9)
+    const uint32_t bar_p_full = bars + 8u * 9, bar_p_smem = bars + 8u * 10;
+    auto bar_q_full  = [&](int t) { return bars + 8u * (11 + t); };       // [11,13)
+    auto bar_q_empty = [&](int t) { return bars + 8u * (13 + t); };       // [13,15)
+    auto bar_acc_full  = [&](int b) { return bars + 8u * (15 + b); };     // [15,17)
+    auto bar_acc_empty = [&](int b) { return bars + 8u * (17 + b); };     // [17,19)
+    const uint32_t tmem_slot = bars + 8u * 20;
+
+    const int tile = blockIdx.x;
+    const LayerRef Lr = layers[tc_find_layer(layers, n_layers, tile)];
+    const int lt = tile - Lr.tile_begin;
+    const int rows_valid = min(TC_TILE_M, Lr.d - lt * TC_TILE_M);
+    const float* __restrict__ w_old = Lr.w_old + (size_t)lt * TC_TILE_M * K;
+    float* __restrict__ w_new = Lr.w_new + (size_t)lt * TC_TILE_M * K;
+    const int n_chunks = K / 32;          // phase A k-chunks (32 fp32 = one swizzle atom row)
+    const int n_kc = K / 128;             // phase B chunks of 128 W columns
+    const int n_rc = R / 32;              // r atoms
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < 3; ++s) { mbar_init(bar_full_w(s), TC_PRODUCER_WARPS); mbar_init(bar_full_e(s), 1); mbar_init(bar_empty(s), 1); }
+        mbar_init(bar_p_full, 1); mbar_init(bar_p_smem, TC_PRODUCER_WARPS);
+        for (int t = 0; t < 2; ++t) { mbar_init(bar_q_full(t), 1); mbar_init(bar_q_empty(t), 1); mbar_init(bar_acc_full(t), 1); mbar_init(bar_acc_empty(t), TC_PRODUCER_WARPS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == TC_PRODUCER_WARPS + 1) {   // MMA warp owns the TMEM allocation (all 512 columns: one CTA per SM)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (warp == TC_PRODUCER_WARPS && lane == 0) {
+        tma_prefetch_desc(&maps.e_hi); tma_prefetch_desc(&maps.e_lo); tma_prefetch_desc(&maps.qt_hi); tma_prefetch_desc(&maps.qt_lo);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    const int SA = L.stages_a;
+    auto stage_w_hi = [&](int s) { return base + (uint32_t)(s * L.stage_a_bytes); };
+    auto stage_w_lo = [&](int s) { return base + (uint32_t)(s * L.stage_a_bytes + 16384); };
+    auto stage_e_hi = [&](int s) { return base + (uint32_t)(s * L.stage_a_bytes + 32768); };
+    auto stage_e_lo = [&](int s) { return base + (uint32_t)(s * L.stage_a_bytes + 32768 + R * 128); };
+    auto p_hi_atom = [&](int rc) { return base + (uint32_t)(rc * 16384); };
+    auto p_lo_atom = [&](int rc) { return base + (uint32_t)(TC_TILE_M * R * 4 + rc * 16384); };
+    auto qt_hi_st = [&](int t) { return base + (uint32_t)(L.qt_off + t * 32768); };
+    auto qt_lo_st = [&](int t) { return base + (uint32_t)(L.qt_off + t * 32768 + 16384); };
+
+    if (warp < TC_PRODUCER_WARPS) {
+        // =============================== W producers, then P converters, then epilogue ===============================
+        const int t = threadIdx.x;                 // 0..255
+        const int c16 = t & 7;                     // 16-byte chunk within the 128-byte row segment
+        const int r0 = t >> 3;                     // rows r0 + 32 p, p = 0..3
+        float4 buf[TC_PF][4];
+        auto load_chunk = [&](int c, float4 (&dst)[4]) {
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {
+                const int row = r0 + 32 * p;
+                if (row < rows_valid) dst[p] = ldg_nc_v4(w_old + (size_t)row * K + c * 32 + c16 * 4);
+                else dst[p] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        };
+#pragma unroll
+        for (int i = 0; i < TC_PF - 1; ++i) load_chunk(i, buf[i]);
+        for (int c0 = 0; c0 < n_chunks; c0 += TC_PF) {
+#pragma unroll
+            for (int u = 0; u < TC_PF; ++u) {
+                const int c = c0 + u;
+                if (c + TC_PF - 1 < n_chunks) load_chunk(c + TC_PF - 1, buf[(u + TC_PF - 1) % TC_PF]);
+                const int s = c % SA;
+                const uint32_t ph = (uint32_t)((c / SA) & 1);
+                mbar_wait(bar_empty(s), ph ^ 1u);
+                const uint32_t hi_base = stage_w_hi(s), lo_base = stage_w_lo(s);
+#pragma unroll
+                for (int p = 0; p < 4; ++p) {
+                    const int row = r0 + 32 * p;
+                    const uint32_t off = (uint32_t)(row * 128 + ((c16 ^ (row & 7)) << 4));
+                    const float4 v = buf[u][p];
+                    const float hx = tf32_hi(v.x), hy = tf32_hi(v.y), hz = tf32_hi(v.z), hw = tf32_hi(v.w);
+                    sts_v4(hi_base + off, hx, hy, hz, hw);
+                    sts_v4(lo_base + off, v.x - hx, v.y - hy, v.z - hz, v.w - hw);
+                }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_full_w(s));
+            }
+        }
+        // ---- P: TMEM -> registers -> hi/lo -> swizzled smem (B operand of phase B) ----
+        const int q = warp & 3, half = warp >> 2;
+        const int prow = 32 * q + lane;            // TMEM lane == row of the tile
+        mbar_wait(bar_p_full, 0);
+        tc_fence_after();
+        for (int rc = half; rc < n_rc; rc += 2) {
+            uint32_t v[32];
+            tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(rc * 32), v);
+            const uint32_t hb = p_hi_atom(rc), lb = p_lo_atom(rc);
+#pragma unroll
+            for (int ch = 0; ch < 8; ++ch) {
+                const uint32_t off = (uint32_t)(prow * 128 + ((ch ^ (prow & 7)) << 4));
+                const float a = __uint_as_float(v[4 * ch]), b = __uint_as_float(v[4 * ch + 1]);
+                const float cc = __uint_as_float(v[4 * ch + 2]), d = __uint_as_float(v[4 * ch + 3]);
+                const float ha = tf32_hi(a), hb2 = tf32_hi(b), hc = tf32_hi(cc), hd = tf32_hi(d);
+                sts_v4(hb + off, ha, hb2, hc, hd);
+                sts_v4(lb + off, a - ha, b - hb2, cc - hc, d - hd);
+            }
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_p_smem);
+        // ---- epilogue: W_new = W_old + dW, transposed accumulator (lane = W column, register = W row) ----
+        for (int kc = 0; kc < n_kc; ++kc) {
+            const int b = kc & 1;
+            mbar_wait(bar_acc_full(b), (uint32_t)((kc >> 1) & 1));
+            tc_fence_after();
+            const int col = kc * 128 + 32 * q + lane;
+#pragma unroll 1
+            for (int g = 0; g < 2; ++g) {
+                const int jrow0 = 64 * half + 32 * g;        // first tile row held by this load
+                uint32_t v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(256 + 128 * b + jrow0), v);
+                float w[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                    w[i] = (jrow0 + i < rows_valid) ? ldg_f32(w_old + (size_t)(jrow0 + i) * K + col) : 0.f;
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                    if (jrow0 + i < rows_valid) w_new[(size_t)(jrow0 + i) * K + col] = w[i] + __uint_as_float(v[i]);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_acc_empty(b));
+        }
+    } else if (warp == TC_PRODUCER_WARPS) {
+        // =============================== TMA warp: E tiles (phase A), Qt tiles (phase B) ===============================
+        if (lane == 0) {
+            const uint32_t e_bytes = 2u * (uint32_t)R * 128u;
+            for (int c = 0; c < n_chunks; ++c) {
+                const int s = c % SA;
+                const uint32_t ph = (uint32_t)((c / SA) & 1);
+                mbar_wait(bar_empty(s), ph ^ 1u);
+                mbar_arrive_expect_tx(bar_full_e(s), e_bytes);
+                tma_load_2d(stage_e_hi(s), &maps.e_hi, bar_full_e(s), c * 32, 0);
+                tma_load_2d(stage_e_lo(s), &maps.e_lo, bar_full_e(s), c * 32, 0);
+            }
+            int it = 0;
+            for (int kc = 0; kc < n_kc; ++kc)
+                for (int rc = 0; rc < n_rc; ++rc, ++it) {
+                    const int t = it % TC_QT_STAGES;
+                    const uint32_t ph = (uint32_t)((it / TC_QT_STAGES) & 1);
+                    mbar_wait(bar_q_empty(t), ph ^ 1u);
+                    mbar_arrive_expect_tx(bar_q_full(t), 32768u);
+                    tma_load_2d(qt_hi_st(t), &maps.qt_hi, bar_q_full(t), rc * 32, kc * 128);
+                    tma_load_2d(qt_lo_st(t), &maps.qt_lo, bar_q_full(t), rc * 32, kc * 128);
+                }
+        }
+    } else {
+        // =============================== MMA issuer ===============================
+        if (lane == 0) {
+            const uint32_t idesc_a = umma_idesc_tf32(128, R);
+            for (int c = 0; c < n_chunks; ++c) {
+                const int s = c % SA;
+                const uint32_t ph = (uint32_t)((c / SA) & 1);
+                mbar_wait(bar_full_w(s), ph);
+                mbar_wait(bar_full_e(s), ph);
+                tc_fence_after();
+                const uint64_t a_hi = umma_desc_sw128(stage_w_hi(s)), a_lo = umma_desc_sw128(stage_w_lo(s));
+                const uint64_t b_hi = umma_desc_sw128(stage_e_hi(s)), b_lo = umma_desc_sw128(stage_e_lo(s));
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {          // 4 x (8 tf32 = 32 bytes) inside the 128-byte swizzle atom
+                    const uint64_t adv = (uint64_t)(k * 2);
+                    umma_tf32(tmem_base, a_hi + adv, b_hi + adv, idesc_a, (c | k) != 0);
+                    umma_tf32(tmem_base, a_lo + adv, b_hi + adv, idesc_a, 1);
+                    umma_tf32(tmem_base, a_hi + adv, b_lo + adv, idesc_a, 1);
+                }
+                umma_commit(bar_empty(s));
+            }
+            umma_commit(bar_p_full);
+            // ---- phase B ----
+            mbar_wait(bar_p_smem, 0);
+            tc_fence_after();
+            const uint32_t idesc_b = umma_idesc_tf32(128, 128);
+            int it = 0;
+            for (int kc = 0; kc < n_kc; ++kc) {
+                const int b = kc & 1;
+                mbar_wait(bar_acc_empty(b), (uint32_t)(((kc >> 1) & 1) ^ 1));
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + 256u + 128u * (uint32_t)b;
+                for (int rc = 0; rc < n_rc; ++rc, ++it) {
+                    const int t = it % TC_QT_STAGES;
+                    const uint32_t ph = (uint32_t)((it / TC_QT_STAGES) & 1);
+                    mbar_wait(bar_q_full(t), ph);
+                    tc_fence_after();
+                    const uint64_t a_hi = umma_desc_sw128(qt_hi_st(t)), a_lo = umma_desc_sw128(qt_lo_st(t));
+                    const uint64_t b_hi = umma_desc_sw128(p_hi_atom(rc)), b_lo = umma_desc_sw128(p_lo_atom(rc));
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const uint64_t adv = (uint64_t)(k * 2);
+                        umma_tf32(d_tmem, a_hi + adv, b_hi + adv, idesc_b, (rc | k) != 0);
+                        umma_tf32(d_tmem, a_lo + adv, b_hi + adv, idesc_b, 1);
+                        umma_tf32(d_tmem, a_hi + adv, b_lo + adv, idesc_b, 1);
+                    }
+                    umma_commit(bar_q_empty(t));
+                }
+                umma_commit(bar_acc_full(b));
+            }
+        }
+    }
+    // ---- teardown ----
+    tc_fence_before();
+    __syncthreads();
+    if (warp == TC_PRODUCER_WARPS + 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+// hi = rna_tf32(x), lo = x - hi for the small pre-split operands (E and Qt)
+__global__ void split_tf32_kernel(const float* __restrict__ x, float* __restrict__ hi, float* __restrict__ lo, long n) {
+    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { float v = x[i], h = tf32_hi(v); hi[i] = h; lo[i] = v - h; }
+}
+
+// ------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+// row-major [rows, cols] fp32, box [box_rows, 32 cols], 128B swizzle
+static int make_map(CUtensorMap* m, const float* ptr, int rows, int cols, int box_rows) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) { set_error("cuTensorMapEncodeTiled entry point not found"); return UCE_E_STATE; }
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)cols * sizeof(float)};
+    cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1u, 1u};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return UCE_E_STATE; }
+    return 0;
+}
+
+bool apply_tc_available(const uce_ws* ws) {
+    const int R = ws->rank_pad;
+    return ws->K % 128 == 0 && R >= 32 && R <= 128 && R % 32 == 0 && !ws->dense && ws->rank > 0 && get_encode() != nullptr;
+}
+
+int apply_tc_split_operands(uce_ws* ws, cudaStream_t st, int* launches) {
+    const long n = (long)ws->rank_pad * ws->K;
+    split_tf32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ws->E, ws->E_hi, ws->E_lo, n);
+    UCE_LAUNCH_CHECK();
+    split_tf32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ws->Qt, ws->Qt_hi, ws->Qt_lo, n);
+    UCE_LAUNCH_CHECK();
+    *launches += 2;
+    return 0;
+}
+
+int apply_tc_lowrank(uce_ws* ws, const LayerRef* layers_dev, const LayerRef* layers_host, int n_layers, int total_tiles,
+                     cudaStream_t st, int* launches) {
+    const int K = ws->K, R = ws->rank_pad;
+    if (!apply_tc_available(ws)) { set_error("tcgen05 apply unavailable for K=%d rank_pad=%d dense=%d", K, R, ws->dense); return UCE_E_STATE; }
+    for (int l = 0; l < n_layers; ++l)
+        if (((uintptr_t)layers_host[l].w_old & 15) || ((uintptr_t)layers_host[l].w_new & 15)) { set_error("tcgen05 apply needs 16-byte aligned weights"); return UCE_E_ARG; }
+    TcMaps maps;
+    int rc;
+    if ((rc = make_map(&maps.e_hi, ws->E_hi, R, K, R))) return rc;
+    if ((rc = make_map(&maps.e_lo, ws->E_lo, R, K, R))) return rc;
+    if ((rc = make_map(&maps.qt_hi, ws->Qt_hi, K, R, 128))) return rc;
+    if ((rc = make_map(&maps.qt_lo, ws->Qt_lo, K, R, 128))) return rc;
+    const TcSmem L = tc_smem_layout(R);
+    const int smem = L.total + 1024;   // slack for the manual 1024-byte alignment
+    static int configured = 0;
+    if (configured < smem) {
+        UCE_CUDA(cudaFuncSetAttribute(apply_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured = smem;
+    }
+    apply_tc_kernel<<<total_tiles, TC_THREADS, smem, st>>>(layers_dev, n_layers, K, R, maps);
+    UCE_LAUNCH_CHECK();
+    *launches += 1;
+    return 0;
+}
+
 }  // namespace uce

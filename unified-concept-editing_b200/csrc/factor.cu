@@ -262,6 +262,10 @@ int factor_dev(uce_ws* ws, const float* C, const float* G, const float* scales, 
         UCE_RT((simt_gemm<float, float, double, float>(st, K, K, n_edit, ws->Q, 1, K, ws->E, 1, K, ws->Dt, K)));
     }
     ws->mode = dual ? 1 : 2;
+    if (apply_tc_available(ws) && ws->apply_impl != 1) {
+        int rc2 = apply_tc_split_operands(ws, st, &launches);
+        if (rc2) return rc2;
+    }
     ws->launches_factor = launches;
     return 0;
 }

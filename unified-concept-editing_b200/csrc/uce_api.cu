@@ -3,6 +3,7 @@
 #include "uce_ws.h"
 #include <cstdarg>
 #include <cstring>
+#include <cstdlib>
 #include <algorithm>
 #include <new>
 
@@ -46,6 +47,7 @@ int uce_ws_create(int device, int K, int max_rows, uce_ws** out) {
     const int mr = ws->max_rows;
     const int rp = round_up(mr, UCE_RANK_PAD);
     ws->layers_cap = 16384;
+    if (const char* e = getenv("UCE_APPLY_IMPL")) ws->apply_impl = atoi(e);   // 0 auto, 1 SIMT, 2 tcgen05 (debugging aid)
 #define WS_ALLOC(ptr, bytes) do { cudaError_t e_ = cudaMalloc((void**)&(ptr), (bytes)); if (e_ != cudaSuccess) { \
         set_error("cudaMalloc(%zu) failed: %s", (size_t)(bytes), cudaGetErrorString(e_)); uce_ws_destroy(ws); return (int)e_; } } while (0)
 #define WS_HOST(ptr, bytes) do { cudaError_t e_ = cudaMallocHost((void**)&(ptr), (bytes)); if (e_ != cudaSuccess) { \
@@ -54,6 +56,10 @@ int uce_ws_create(int device, int K, int max_rows, uce_ws** out) {
     WS_ALLOC(ws->E, (size_t)rp * K * sizeof(float));
     WS_ALLOC(ws->Q, (size_t)rp * K * sizeof(float));
     WS_ALLOC(ws->Qt, (size_t)rp * K * sizeof(float));
+    WS_ALLOC(ws->E_hi, (size_t)rp * K * sizeof(float));
+    WS_ALLOC(ws->E_lo, (size_t)rp * K * sizeof(float));
+    WS_ALLOC(ws->Qt_hi, (size_t)rp * K * sizeof(float));
+    WS_ALLOC(ws->Qt_lo, (size_t)rp * K * sizeof(float));
     WS_ALLOC(ws->H, (size_t)ws->sys_max * ws->sys_max * sizeof(double));
     WS_ALLOC(ws->Linv, (size_t)ws->sys_max * UCE_NB * sizeof(double));
     WS_ALLOC(ws->X, (size_t)ws->sys_max * mr * sizeof(double));
@@ -75,7 +81,7 @@ int uce_ws_destroy(uce_ws* ws) {
     if (!ws) return 0;
     cudaSetDevice(ws->device);
     cudaDeviceSynchronize();
-    void* dev[] = {ws->Cp, ws->Cs64, ws->E, ws->Q, ws->Qt, ws->Dt, ws->H, ws->Hcopy, ws->Linv, ws->X, ws->src_idx,
+    void* dev[] = {ws->Cp, ws->Cs64, ws->E, ws->Q, ws->Qt, ws->Dt, ws->E_hi, ws->E_lo, ws->Qt_hi, ws->Qt_lo, ws->H, ws->Hcopy, ws->Linv, ws->X, ws->src_idx,
                    ws->diag_add, ws->flag, ws->P, ws->layers_dev, ws->hostpath_C, ws->hostpath_G, ws->hostpath_W};
     for (void* p : dev) if (p) cudaFree(p);
     void* host[] = {ws->h_src_idx, ws->h_diag_add, ws->h_layers, ws->h_flag};

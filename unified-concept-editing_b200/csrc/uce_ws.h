@@ -5,7 +5,7 @@
 #include "uce_common.cuh"
 
 constexpr int UCE_NB = 32;        // Cholesky block size (fp64)
-constexpr int UCE_RANK_PAD = 16;  // rank of E/Q is padded to a multiple of this (UMMA N granularity)
+constexpr int UCE_RANK_PAD = 32;  // rank of E/Q is padded to a multiple of this (UMMA N granularity)
 
 struct uce_ws {
     int device = 0, K = 0, max_rows = 0;
@@ -31,6 +31,7 @@ struct uce_ws {
     float*  Q = nullptr;      // [rank_pad, K]
     float*  Qt = nullptr;     // [K, rank_pad]
     float*  Dt = nullptr;     // [K, K]   dense factor (lazily allocated)
+    float  *E_hi = nullptr, *E_lo = nullptr, *Qt_hi = nullptr, *Qt_lo = nullptr;   // tf32 hi/lo splits for the tcgen05 apply
     double* H = nullptr;      // [sys_max, sys_max]
     double* Hcopy = nullptr;  // debug copy of the assembled system (lazily allocated)
     double* Linv = nullptr;   // [sys_max/NB][NB][NB]
@@ -64,4 +65,7 @@ int factor_dev(uce_ws* ws, const float* C, const float* G, const float* scales_h
 // apply.cu
 int apply_dev(uce_ws* ws, const float* const* W_old, float* const* W_new, const int* d, int n_layers,
               cudaStream_t st, bool no_profile = false);
+// apply_tc.cu
+bool apply_tc_available(const uce_ws* ws);
+int apply_tc_split_operands(uce_ws* ws, cudaStream_t st, int* launches);
 }  // namespace uce

@@ -38,9 +38,11 @@ def log(msg):
 
 
 def host_threads():
-    """Threads for the CPU arm: all cores up to a cap (the reference's loop is thousands of tiny rank-1
-    updates; beyond a few dozen threads torch's intra-op pool only adds synchronisation cost)."""
-    return int(os.environ.get("UCE_CPU_THREADS", min(os.cpu_count() or 1, 32)))
+    """Threads for the CPU arm.  The reference's loop is thousands of tiny rank-1 updates and 768x768 inverses;
+    measured on the 128-core GPU-box host (profiles/cpu_threads_probe_r01.txt) torch's intra-op pool is fastest at
+    8 threads (4: 1.8x slower, 16: 2.1x, 32: 12x, 64: 87x, 128: 1950x slower), so 8 is "all the threads it can
+    use"; override with UCE_CPU_THREADS."""
+    return int(os.environ.get("UCE_CPU_THREADS", min(os.cpu_count() or 1, 8)))
 
 
 METRIC = "concepts/sec (edit-solve)"

@@ -62,6 +62,10 @@ int uce_ws_destroy(uce_ws *ws);
  * CPU path. */
 int uce_ws_set_apply_impl(uce_ws *ws, int impl);
 
+/* Select the factor path: 0 = auto (single-CTA low-latency kernel when n <= 160 rows and the dual system
+ * applies, general blocked path otherwise), 1 = always the general blocked path. Returns the previous value. */
+int uce_ws_set_factor_impl(uce_ws *ws, int impl);
+
 /* Debug mode keeps a copy of the assembled system matrix for uce_ws_debug_read(…, 0, …).
  * Returns the previous value. */
 int uce_ws_set_debug(uce_ws *ws, int on);

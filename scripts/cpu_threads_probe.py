@@ -8,7 +8,7 @@ p = problem("cfg2", seed=0)
 ne = p["n_edit"]
 W = p["W"][::8]
 print("cpu_count", os.cpu_count(), flush=True)
-for nt in (4, 8, 16, 32, 64, 128, os.cpu_count()):
+for nt in (2, 4, 8, 12, 16, 32):
     if nt > os.cpu_count():
         continue
     torch.set_num_threads(nt)

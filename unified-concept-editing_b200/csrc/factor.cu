@@ -221,6 +221,20 @@ int factor_dev(uce_ws* ws, const float* C, const float* G, const float* scales, 
     UCE_CUDA(cudaMemsetAsync(ws->flag, 0, sizeof(int), st));
     if (cap == cudaStreamCaptureStatusNone) { UCE_CUDA(cudaEventRecord(ws->ev_stage, st)); ws->stage_pending = 1; }
 
+    if (factor_small_applicable(ws, n, dual)) {
+        int rc = factor_small(ws, C, G, n, n_pres, n_edit, st, &launches);
+        if (rc) return rc;
+        if (ws->debug) {   // the debug copy shows the assembled system (the kernel adds the diagonal in shared memory only)
+            finish_diag_kernel<<<ceil_div(ws->sys_n, 256), 256, 0, st>>>(ws->Hcopy, ws->sys_n, n, ws->sys_n, ws->diag_add, 0.0);
+            UCE_RT(cudaGetLastError());
+        }
+        if (ws->dense) {
+            UCE_RT((simt_gemm<float, float, double, float>(st, K, K, n_edit, ws->Q, 1, K, ws->E, 1, K, ws->Dt, K)));
+        }
+        ws->mode = 1;
+        ws->launches_factor = launches;
+        return 0;
+    }
     pack_rows_kernel<<<n + (ws->rank_pad - n_edit), 256, 0, st>>>(C, G, ws->src_idx, ws->diag_add, n, n_pres, ws->rank_pad, K,
                                                                   ws->Cp, ws->E, dual ? nullptr : ws->Cs64);
     UCE_RT(cudaGetLastError());

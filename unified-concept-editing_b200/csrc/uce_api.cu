@@ -104,6 +104,13 @@ int uce_ws_set_apply_impl(uce_ws* ws, int impl) {
     return prev;
 }
 
+int uce_ws_set_factor_impl(uce_ws* ws, int impl) {
+    if (!ws) return UCE_E_ARG;
+    int prev = ws->force_general;
+    ws->force_general = (impl == 1);
+    return prev;
+}
+
 int uce_ws_set_debug(uce_ws* ws, int on) {
     if (!ws) return UCE_E_ARG;
     int prev = ws->debug;

@@ -21,6 +21,7 @@ struct uce_ws {
     int launches_factor = 0, launches_apply = 0;
     int apply_impl = 0;   // 0 auto, 1 simt, 2 tcgen05
     int debug = 0;
+    int force_general = 0;   // 1: always use the general blocked factor (testing)
     int profile = 0;
     cudaEvent_t pev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // factor begin/end, apply begin/mid/end
     int pev_mid = 0;
@@ -65,6 +66,9 @@ int factor_dev(uce_ws* ws, const float* C, const float* G, const float* scales_h
 // apply.cu
 int apply_dev(uce_ws* ws, const float* const* W_old, float* const* W_new, const int* d, int n_layers,
               cudaStream_t st, bool no_profile = false);
+// factor_small.cu
+bool factor_small_applicable(const uce_ws* ws, int n, bool dual);
+int factor_small(uce_ws* ws, const float* C, const float* G, int n, int n_pres, int n_edit, cudaStream_t st, int* launches);
 // apply_tc.cu
 bool apply_tc_available(const uce_ws* ws);
 int apply_tc_split_operands(uce_ws* ws, cudaStream_t st, int* launches);

@@ -51,6 +51,10 @@ class EditSolver:
     def set_apply_impl(self, impl: int) -> int:
         return N.lib().uce_ws_set_apply_impl(self._h, int(impl))
 
+    def set_factor_impl(self, impl: int) -> int:
+        """0 auto (low-latency single-CTA factor when it applies), 1 general blocked path."""
+        return N.lib().uce_ws_set_factor_impl(self._h, int(impl))
+
     def set_debug(self, on: bool) -> int:
         return N.lib().uce_ws_set_debug(self._h, int(bool(on)))
 

@@ -29,7 +29,7 @@ constexpr int TC_TILE_M = 128;
 constexpr int TC_PRODUCER_WARPS = 8;
 constexpr int TC_THREADS = (TC_PRODUCER_WARPS + 2) * 32;   // + TMA warp + MMA warp
 constexpr int TC_QT_STAGES = 2;
-constexpr int TC_PF = 4;                                    // W chunks in flight per producer thread
+constexpr int TC_PF = 6;                                    // W chunks in flight per producer thread (96 KB per SM)
 
 struct TcMaps { CUtensorMap e_hi, e_lo, qt_hi, qt_lo; };
 
@@ -118,15 +118,31 @@ __device__ __forceinline__ float tf32_hi(float x) {
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
     return __uint_as_float(u);
 }
-__device__ __forceinline__ float4 ldg_nc_v4(const float* p) {
+// L2 policies: the W_old tile is read twice (phase A from HBM, epilogue addend from L2) -> keep it (evict_last);
+// W_new is written once and never read here -> evict_first, so that it does not push W_old tiles out of L2.
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ float4 ldg_nc_v4(const float* p, uint64_t pol) {
     float4 r;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p), "l"(pol));
     return r;
 }
 __device__ __forceinline__ float ldg_f32(const float* p) {
     float r;
     asm volatile("ld.global.f32 %0, [%1];" : "=f"(r) : "l"(p) : "memory");
     return r;
+}
+__device__ __forceinline__ void stg_f32_hint(float* p, float v, uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(p), "f"(v), "l"(pol) : "memory");
 }
 __device__ __forceinline__ void sts_v4(uint32_t addr, float a, float b, float c, float d) {
     asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
@@ -229,20 +245,22 @@ apply_tc_kernel(const LayerRef* __restrict__ layers, int n_layers, int K, int R,
         const int c16 = t & 7;                     // 16-byte chunk within the 128-byte row segment
         const int r0 = t >> 3;                     // rows r0 + 32 p, p = 0..3
         float4 buf[TC_PF][4];
+        const uint64_t pol_keep = l2_policy_evict_last(), pol_stream = l2_policy_evict_first();
         auto load_chunk = [&](int c, float4 (&dst)[4]) {
 #pragma unroll
             for (int p = 0; p < 4; ++p) {
                 const int row = r0 + 32 * p;
-                if (row < rows_valid) dst[p] = ldg_nc_v4(w_old + (size_t)row * K + c * 32 + c16 * 4);
+                if (row < rows_valid) dst[p] = ldg_nc_v4(w_old + (size_t)row * K + c * 32 + c16 * 4, pol_keep);
                 else dst[p] = make_float4(0.f, 0.f, 0.f, 0.f);
             }
         };
 #pragma unroll
-        for (int i = 0; i < TC_PF - 1; ++i) load_chunk(i, buf[i]);
+        for (int i = 0; i < TC_PF - 1; ++i) if (i < n_chunks) load_chunk(i, buf[i]);
         for (int c0 = 0; c0 < n_chunks; c0 += TC_PF) {
 #pragma unroll
             for (int u = 0; u < TC_PF; ++u) {
                 const int c = c0 + u;
+                if (c >= n_chunks) break;
                 if (c + TC_PF - 1 < n_chunks) load_chunk(c + TC_PF - 1, buf[(u + TC_PF - 1) % TC_PF]);
                 const int s = c % SA;
                 const uint32_t ph = (uint32_t)((c / SA) & 1);
@@ -288,21 +306,33 @@ apply_tc_kernel(const LayerRef* __restrict__ layers, int n_layers, int K, int R,
         // ---- epilogue: W_new = W_old + dW, transposed accumulator (lane = W column, register = W row) ----
         for (int kc = 0; kc < n_kc; ++kc) {
             const int b = kc & 1;
+            const int col = kc * 128 + 32 * q + lane;
+            const int jrow0 = 64 * half;                     // this warp's 64 tile rows (two TMEM loads of 32 columns)
+            // addend W_old[jrow0 .. +64, col]: issued BEFORE waiting for the accumulator so the L2 latency hides under the MMAs
+            float w[64];
+            const float* wp = w_old + (size_t)jrow0 * K + col;
+            if (rows_valid == TC_TILE_M) {
+#pragma unroll
+                for (int i = 0; i < 64; ++i) w[i] = ldg_f32(wp + (size_t)i * K);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 64; ++i) w[i] = (jrow0 + i < rows_valid) ? ldg_f32(wp + (size_t)i * K) : 0.f;
+            }
             mbar_wait(bar_acc_full(b), (uint32_t)((kc >> 1) & 1));
             tc_fence_after();
-            const int col = kc * 128 + 32 * q + lane;
-#pragma unroll 1
+            float* op = w_new + (size_t)jrow0 * K + col;
+#pragma unroll
             for (int g = 0; g < 2; ++g) {
-                const int jrow0 = 64 * half + 32 * g;        // first tile row held by this load
                 uint32_t v[32];
-                tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(256 + 128 * b + jrow0), v);
-                float w[32];
+                tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(256 + 128 * b + jrow0 + 32 * g), v);
+                if (rows_valid == TC_TILE_M) {
 #pragma unroll
-                for (int i = 0; i < 32; ++i)
-                    w[i] = (jrow0 + i < rows_valid) ? ldg_f32(w_old + (size_t)(jrow0 + i) * K + col) : 0.f;
+                    for (int i = 0; i < 32; ++i) stg_f32_hint(op + (size_t)(32 * g + i) * K, w[32 * g + i] + __uint_as_float(v[i]), pol_stream);
+                } else {
 #pragma unroll
-                for (int i = 0; i < 32; ++i)
-                    if (jrow0 + i < rows_valid) w_new[(size_t)(jrow0 + i) * K + col] = w[i] + __uint_as_float(v[i]);
+                    for (int i = 0; i < 32; ++i)
+                        if (jrow0 + 32 * g + i < rows_valid) stg_f32_hint(op + (size_t)(32 * g + i) * K, w[32 * g + i] + __uint_as_float(v[i]), pol_stream);
+                }
             }
             tc_fence_before();
             __syncwarp();

@@ -221,7 +221,7 @@ int factor_dev(uce_ws* ws, const float* C, const float* G, const float* scales, 
     UCE_CUDA(cudaMemsetAsync(ws->flag, 0, sizeof(int), st));
     if (cap == cudaStreamCaptureStatusNone) { UCE_CUDA(cudaEventRecord(ws->ev_stage, st)); ws->stage_pending = 1; }
 
-    if (factor_small_applicable(ws, n, dual)) {
+    if (factor_small_applicable(ws, n, n_edit, dual)) {
         int rc = factor_small(ws, C, G, n, n_pres, n_edit, st, &launches);
         if (rc) return rc;
         if (ws->debug) {   // the debug copy shows the assembled system (the kernel adds the diagonal in shared memory only)

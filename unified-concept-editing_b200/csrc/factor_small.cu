@@ -2,9 +2,10 @@
 // 4 kernels instead of the ~35 launches of the general blocked path in factor.cu.
 //
 //   gram_splitk   H = Cp Cp^T, fp64 accumulation of exact fp32 products, 32x32 tiles x split-K over many CTAs
-//   chol_small    ONE CTA: H (+ lamb/s on the diagonal) into shared memory, blocked Cholesky (NB = 32: warp-shuffle
-//                 factorisation of the diagonal block, warp-parallel inverse, panel + trailing updates by all 512
-//                 threads), then  Z = H^-1[:, edit]  by blocked forward/backward substitution
+//   chol_small    ONE CTA: H (+ lamb/s on the diagonal) into shared memory (lower block triangle), blocked Cholesky
+//                 (NB = 32: left-looking factorisation of the diagonal block by one warp, column-sweep inverse by all
+//                 warps, panel + trailing updates by all 512 threads), then  Z = H^-1[:, edit]  by blocked
+//                 forward/backward substitution with the right-hand sides in shared memory too
 //   q_emit        Q = Z^T Cp (fp64 accumulate) -> Q, Qt and the TF32 hi/lo splits consumed by the tcgen05 apply
 //
 // Same algebra and same fp64 precision as the general path (trainscripts/uce_sd_erase.py:63,71,79,82 — the
@@ -60,141 +61,141 @@ __global__ void __launch_bounds__(256) gram_splitk_kernel(const float* __restric
 }
 
 // ---------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ double warp_sum(double v) {
+// Single-CTA Cholesky + solve, everything in shared memory:
+//   SB   lower block triangle of H, 32 x 32 blocks of pitch 33, block (bi,bj) at index bi(bi+1)/2 + bj
+//   XS   right-hand sides / solution  [n_pad][xl]   (n_edit <= 64 columns)
+// After step kb the diagonal block holds L_kk in its lower triangle, the strictly-lower part of L_kk^-1
+// transposed in its strict upper triangle, and 1 / L_ii in invd[].
+constexpr int FS_T = 512;
+constexpr int FS_BLK = FS_NB * (FS_NB + 1);      // doubles per block (pitch 33)
+constexpr int FS_MAX_RHS = 64;
+
+__device__ __forceinline__ int fs_blk(int bi, int bj) { return (bi * (bi + 1) / 2 + bj) * FS_BLK; }
+
+// 1 / sqrt(d) in fp64 without the slow software sqrt/div: fp32 seed + 3 Newton steps (relative error < 1e-15)
+__device__ __forceinline__ double fs_rsqrt(double d) {
+    double y = (double)rsqrtf((float)d);
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
+    for (int i = 0; i < 3; ++i) y = y * (1.5 - 0.5 * d * y * y);
+    return y;
 }
-
-// Warp-level Cholesky of a 32 x 32 block: lane i holds row i in registers; template recursion keeps every
-// register index a compile-time constant (a runtime-indexed array would live in local memory).
-template <int J, int Kc>
-__device__ __forceinline__ void chol_row_update(double (&a)[FS_NB], int lane) {
-    if constexpr (Kc < FS_NB) {
-        const double akj = __shfl_sync(0xffffffffu, a[J], Kc);     // L[Kc][J]
-        if (lane >= Kc) a[Kc] -= a[J] * akj;
-        chol_row_update<J, Kc + 1>(a, lane);
-    }
-}
-template <int J>
-__device__ __forceinline__ void chol_column(double (&a)[FS_NB], int lane, bool& bad) {
-    if constexpr (J < FS_NB) {
-        double d = __shfl_sync(0xffffffffu, a[J], J);
-        if (!(d > 0.0)) { bad = true; d = 1.0; }
-        const double s = sqrt(d), inv = 1.0 / s;
-        if (lane == J) a[J] = s; else if (lane > J) a[J] *= inv;
-        chol_row_update<J, J + 1>(a, lane);
-        chol_column<J + 1>(a, lane, bad);
-    }
-}
-template <int J>
-__device__ __forceinline__ void block_load(double (&a)[FS_NB], const double* row) {
-    if constexpr (J < FS_NB) { a[J] = row[J]; block_load<J + 1>(a, row); }
-}
-template <int J>
-__device__ __forceinline__ void block_store(const double (&a)[FS_NB], double* row, int lane) {
-    if constexpr (J < FS_NB) { row[J] = (J <= lane) ? a[J] : 0.0; block_store<J + 1>(a, row, lane); }
-}
-
-// Kept out of line so that the 64 registers of the row block do not compete with the caller's live values.
-__device__ __noinline__ void chol_diag_block(double* row, int lane, int* flag, int kb) {
-    double a[FS_NB];
-    block_load<0>(a, row);
-    bool bad = false;
-    chol_column<0>(a, lane, bad);
-    if (bad && lane == 0) atomicCAS(flag, 0, 1 + kb);
-    block_store<0>(a, row, lane);
-}
-
-// Single-CTA Cholesky + solve.  S: dynamic smem [n_pad][n_pad + 1] doubles.
-constexpr int FS_T = 512;   // threads of the single factor CTA (128 registers each: the diagonal block lives in registers)
 
 __global__ void __launch_bounds__(FS_T, 1)
 chol_small_kernel(double* __restrict__ Hg, int n, int n_pad, const double* __restrict__ dadd, int n_pres, int n_edit,
-                  double* __restrict__ Linv_g, double* __restrict__ X, int ldx, int write_back, int* flag) {
-    extern __shared__ double S[];
-    __shared__ double Dinv[FS_NB][FS_NB + 1];
-    const int lds = n_pad + 1;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+                  double* __restrict__ Z, int ldz, int write_back, int* flag) {
+    extern __shared__ double smem_d[];
     const int nblk = n_pad / FS_NB;
+    double* SB = smem_d;
+    double* XS = SB + (nblk * (nblk + 1) / 2) * FS_BLK;
+    const int xl = n_edit | 1;
+    double* invd = XS + n_pad * xl;               // [n_pad]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NW = FS_T / 32;
 
-    for (int idx = tid; idx < n_pad * n_pad; idx += FS_T) {
-        const int r = idx / n_pad, c = idx % n_pad;
-        double v = (r < n && c <= r) ? Hg[(long)r * n_pad + c] : 0.0;
-        if (r == c) v = (r < n) ? v + dadd[r] : 1.0;
-        S[r * lds + c] = v;
-    }
-    // rhs: unit vectors of the edit rows (internal order: preserve rows first)
+    // ---- load the lower block triangle (+ diagonal term, identity padding) ----
+    for (int bi = 0, b = 0; bi < nblk; ++bi)
+        for (int bj = 0; bj <= bi; ++bj, ++b)
+            for (int idx = tid; idx < FS_NB * FS_NB; idx += FS_T) {
+                const int rr = idx >> 5, cc = idx & 31, r = bi * FS_NB + rr, c = bj * FS_NB + cc;
+                double v = (r < n && c <= r) ? Hg[(long)r * n_pad + c] : 0.0;
+                if (r == c) v = (r < n) ? v + dadd[r] : 1.0;
+                SB[b * FS_BLK + rr * (FS_NB + 1) + cc] = v;
+            }
     for (int idx = tid; idx < n_pad * n_edit; idx += FS_T) {
         const int r = idx / n_edit, j = idx % n_edit;
-        __stcg(&X[(long)r * ldx + j], (r == n_pres + j) ? 1.0 : 0.0);
+        XS[r * xl + j] = (r == n_pres + j) ? 1.0 : 0.0;
     }
     __syncthreads();
 
     for (int kb = 0; kb < nblk; ++kb) {
+        double* D = SB + fs_blk(kb, kb);
         const int o = kb * FS_NB;
-        // (a) diagonal block, one warp, rows in registers
+        // (a) left-looking Cholesky of the diagonal block by one warp (lane = row); no stores inside the dot products
         if (warp == 0) {
-            chol_diag_block(&S[(o + lane) * lds + o], lane, flag, kb);
-        }
-        __syncthreads();
-        // (b) inverse of the lower-triangular diagonal block: warp c -> column c
-        for (int c = warp; c < FS_NB; c += FS_T / 32) {
-            double x = 0.0;
-            if (lane == c) x = 1.0 / S[(o + c) * lds + o + c];
-            for (int i = c + 1; i < FS_NB; ++i) {
-                const double part = (lane >= c && lane < i) ? S[(o + i) * lds + o + lane] * x : 0.0;
-                const double s = warp_sum(part);
-                if (lane == i) x = -s / S[(o + i) * lds + o + i];
+            bool bad = false;
+            for (int j = 0; j < FS_NB; ++j) {
+                double acc = D[lane * (FS_NB + 1) + j];
+#pragma unroll 8
+                for (int k = 0; k < j; ++k) acc = fma(-D[lane * (FS_NB + 1) + k], D[j * (FS_NB + 1) + k], acc);
+                double d = __shfl_sync(0xffffffffu, acc, j);
+                if (!(d > 0.0)) { bad = true; d = 1.0; }
+                const double y = fs_rsqrt(d);
+                if (lane == j) { D[j * (FS_NB + 1) + j] = d * y; invd[o + j] = y; }
+                else if (lane > j) D[lane * (FS_NB + 1) + j] = acc * y;
+                __syncwarp();
             }
-            Dinv[lane][c] = x;     // x == 0 above the diagonal
-            Linv_g[((long)kb * FS_NB + lane) * FS_NB + c] = x;
+            if (bad && lane == 0) atomicCAS(flag, 0, 1 + kb);
         }
         __syncthreads();
-        const int rest = n_pad - (o + FS_NB);
-        if (rest > 0) {
-            // (c) panel  L_ik = H_ik Linv^T   (results staged in registers: the panel is updated in place)
+        // (b) inverse of L_kk by column sweeps (warp = column c, lane = row): x_j = (delta_jc - acc_j) / L_jj
+        for (int c = warp; c < FS_NB; c += NW) {
+            double acc = 0.0, mine = 0.0;
+            for (int j = c; j < FS_NB; ++j) {
+                const double cand = ((lane == c) ? 1.0 : 0.0) - acc;
+                const double xj = __shfl_sync(0xffffffffu, cand, j) * invd[o + j];
+                if (lane == j) mine = xj;
+                if (lane > j) acc = fma(D[lane * (FS_NB + 1) + j], xj, acc);
+            }
+            if (lane > c) D[c * (FS_NB + 1) + lane] = mine;      // strict upper triangle <- transposed strict lower of L^-1
+        }
+        __syncthreads();
+        const int mb = nblk - kb - 1;                            // block rows below
+        if (mb > 0) {
+            // (c) panel  L_ik = H_ik L_kk^-T  for the mb blocks below (staged: updated in place)
             double out[FS_MAX_N * FS_NB / FS_T];
 #pragma unroll
             for (int it = 0; it < FS_MAX_N * FS_NB / FS_T; ++it) {
                 const int idx = tid + it * FS_T;
                 out[it] = 0.0;
-                if (idx < rest * FS_NB) {
-                    const int r = o + FS_NB + idx / FS_NB, c = idx % FS_NB;
-                    double s = 0.0;
+                if (idx < mb * FS_NB * FS_NB) {
+                    const int bi = kb + 1 + idx / (FS_NB * FS_NB), rr = (idx >> 5) & 31, c = idx & 31;
+                    const double* A = SB + fs_blk(bi, kb) + rr * (FS_NB + 1);
+                    double s2 = A[c] * invd[o + c];                                  // j == c term (diagonal of L^-1)
 #pragma unroll 8
-                    for (int j = 0; j < FS_NB; ++j) s = fma(S[r * lds + o + j], Dinv[c][j], s);
-                    out[it] = s;
+                    for (int j = 0; j < c; ++j) s2 = fma(A[j], D[j * (FS_NB + 1) + c], s2);   // Linv[c][j] stored at D[j][c]
+                    out[it] = s2;
                 }
             }
             __syncthreads();
 #pragma unroll
             for (int it = 0; it < FS_MAX_N * FS_NB / FS_T; ++it) {
                 const int idx = tid + it * FS_T;
-                if (idx < rest * FS_NB) S[(o + FS_NB + idx / FS_NB) * lds + o + idx % FS_NB] = out[it];
+                if (idx < mb * FS_NB * FS_NB) {
+                    const int bi = kb + 1 + idx / (FS_NB * FS_NB), rr = (idx >> 5) & 31, c = idx & 31;
+                    SB[fs_blk(bi, kb) + rr * (FS_NB + 1) + c] = out[it];
+                }
             }
             __syncthreads();
-            // (d) trailing update of the lower triangle
-            for (int idx = tid; idx < rest * rest; idx += FS_T) {
-                const int r = o + FS_NB + idx / rest, c = o + FS_NB + idx % rest;
-                if (c > r) continue;
-                double s = 0.0;
+            // (d) trailing update of the lower block triangle:  H_ij -= L_ik L_jk^T
+            const int npairs = mb * (mb + 1) / 2;
+            for (int idx = tid; idx < npairs * FS_NB * FS_NB; idx += FS_T) {
+                int pr = idx / (FS_NB * FS_NB), ti = 0;
+                while ((ti + 1) * (ti + 2) / 2 <= pr) ++ti;
+                const int tj = pr - ti * (ti + 1) / 2;
+                const int rr = (idx >> 5) & 31, c = idx & 31;
+                if (ti == tj && c > rr) continue;
+                const double* A = SB + fs_blk(kb + 1 + ti, kb) + rr * (FS_NB + 1);
+                const double* B = SB + fs_blk(kb + 1 + tj, kb) + c * (FS_NB + 1);
+                double s2 = 0.0;
 #pragma unroll 8
-                for (int j = 0; j < FS_NB; ++j) s = fma(S[r * lds + o + j], S[c * lds + o + j], s);
-                S[r * lds + c] -= s;
+                for (int j = 0; j < FS_NB; ++j) s2 = fma(A[j], B[j], s2);
+                SB[fs_blk(kb + 1 + ti, kb + 1 + tj) + rr * (FS_NB + 1) + c] -= s2;
             }
             __syncthreads();
         }
     }
-    if (write_back)
-        for (int idx = tid; idx < n_pad * n_pad; idx += FS_T) Hg[idx] = S[(idx / n_pad) * lds + idx % n_pad];
+    if (write_back) {   // debug: L back to global (row-major [n_pad][n_pad], zeros above the diagonal)
+        for (int idx = tid; idx < n_pad * n_pad; idx += FS_T) {
+            const int r = idx / n_pad, c = idx % n_pad;
+            Hg[idx] = (c <= r) ? SB[fs_blk(r >> 5, c >> 5) + (r & 31) * (FS_NB + 1) + (c & 31)] : 0.0;
+        }
+    }
 
-    // ---- forward substitution  L Y = rhs  (blocks above the first edit row stay zero) ----
-    constexpr int XR = (FS_NB * FS_MAX_N + FS_T - 1) / FS_T;     // staged outputs per thread for a 32 x n_edit block
+    // ---- forward substitution  L Y = rhs  (block rows above the first edit row stay zero) ----
+    constexpr int XR = FS_NB * FS_MAX_RHS / FS_T;      // staged outputs per thread for one 32 x n_edit block
     for (int kb = n_pres / FS_NB; kb < nblk; ++kb) {
+        const double* D = SB + fs_blk(kb, kb);
         const int o = kb * FS_NB;
-        for (int c = warp; c < FS_NB; c += FS_T / 32) Dinv[lane][c] = Linv_g[((long)kb * FS_NB + lane) * FS_NB + c];
-        __syncthreads();
         double out[XR];
 #pragma unroll
         for (int it = 0; it < XR; ++it) {
@@ -202,33 +203,33 @@ chol_small_kernel(double* __restrict__ Hg, int n, int n_pad, const double* __res
             out[it] = 0.0;
             if (idx < FS_NB * n_edit) {
                 const int rr = idx / n_edit, j = idx % n_edit;
-                double s = 0.0;
-                for (int c = 0; c <= rr; ++c) s = fma(Dinv[rr][c], __ldcg(&X[(long)(o + c) * ldx + j]), s);
-                out[it] = s;
+                double s2 = invd[o + rr] * XS[(o + rr) * xl + j];
+                for (int c = 0; c < rr; ++c) s2 = fma(D[c * (FS_NB + 1) + rr], XS[(o + c) * xl + j], s2);   // Linv[rr][c]
+                out[it] = s2;
             }
         }
         __syncthreads();
 #pragma unroll
         for (int it = 0; it < XR; ++it) {
             const int idx = tid + it * FS_T;
-            if (idx < FS_NB * n_edit) __stcg(&X[(long)(o + idx / n_edit) * ldx + idx % n_edit], out[it]);
+            if (idx < FS_NB * n_edit) XS[(o + idx / n_edit) * xl + idx % n_edit] = out[it];
         }
         __syncthreads();
         const int rest = n_pad - (o + FS_NB);
         for (int idx = tid; idx < rest * n_edit; idx += FS_T) {
             const int r = o + FS_NB + idx / n_edit, j = idx % n_edit;
-            double s = 0.0;
+            const double* A = SB + fs_blk(r >> 5, kb) + (r & 31) * (FS_NB + 1);
+            double s2 = 0.0;
 #pragma unroll 8
-            for (int c = 0; c < FS_NB; ++c) s = fma(S[r * lds + o + c], __ldcg(&X[(long)(o + c) * ldx + j]), s);
-            __stcg(&X[(long)r * ldx + j], __ldcg(&X[(long)r * ldx + j]) - s);
+            for (int c = 0; c < FS_NB; ++c) s2 = fma(A[c], XS[(o + c) * xl + j], s2);
+            XS[r * xl + j] -= s2;
         }
         __syncthreads();
     }
     // ---- backward substitution  L^T Z = Y ----
     for (int kb = nblk - 1; kb >= 0; --kb) {
+        const double* D = SB + fs_blk(kb, kb);
         const int o = kb * FS_NB;
-        for (int c = warp; c < FS_NB; c += FS_T / 32) Dinv[lane][c] = Linv_g[((long)kb * FS_NB + lane) * FS_NB + c];
-        __syncthreads();
         double out[XR];
 #pragma unroll
         for (int it = 0; it < XR; ++it) {
@@ -236,47 +237,53 @@ chol_small_kernel(double* __restrict__ Hg, int n, int n_pad, const double* __res
             out[it] = 0.0;
             if (idx < FS_NB * n_edit) {
                 const int rr = idx / n_edit, j = idx % n_edit;
-                double s = 0.0;
-                for (int c = rr; c < FS_NB; ++c) s = fma(Dinv[c][rr], __ldcg(&X[(long)(o + c) * ldx + j]), s);
-                out[it] = s;
+                double s2 = invd[o + rr] * XS[(o + rr) * xl + j];
+                for (int c = rr + 1; c < FS_NB; ++c) s2 = fma(D[rr * (FS_NB + 1) + c], XS[(o + c) * xl + j], s2);   // Linv[c][rr]
+                out[it] = s2;
             }
         }
         __syncthreads();
 #pragma unroll
         for (int it = 0; it < XR; ++it) {
             const int idx = tid + it * FS_T;
-            if (idx < FS_NB * n_edit) __stcg(&X[(long)(o + idx / n_edit) * ldx + idx % n_edit], out[it]);
+            if (idx < FS_NB * n_edit) XS[(o + idx / n_edit) * xl + idx % n_edit] = out[it];
         }
         __syncthreads();
         for (int idx = tid; idx < o * n_edit; idx += FS_T) {
             const int r = idx / n_edit, j = idx % n_edit;
-            double s = 0.0;
+            const double* A = SB + fs_blk(kb, r >> 5) + (r & 31);          // L[o + c][r] = block(kb, r/32)[c][r%32]
+            double s2 = 0.0;
 #pragma unroll 8
-            for (int c = 0; c < FS_NB; ++c) s = fma(S[(o + c) * lds + r], __ldcg(&X[(long)(o + c) * ldx + j]), s);
-            __stcg(&X[(long)r * ldx + j], __ldcg(&X[(long)r * ldx + j]) - s);
+            for (int c = 0; c < FS_NB; ++c) s2 = fma(A[c * (FS_NB + 1)], XS[(o + c) * xl + j], s2);
+            XS[r * xl + j] -= s2;
         }
         __syncthreads();
     }
+    for (int idx = tid; idx < n * n_edit; idx += FS_T) Z[(long)(idx / n_edit) * ldz + idx % n_edit] = XS[(idx / n_edit) * xl + idx % n_edit];
 }
 
 // ---------------------------------------------------------------------------------------------------------
 // Q[j, k] = sum_r Z[r, j] Cp[r, k]  (fp64 accumulate), emitted as Q, Qt and the tf32 hi/lo splits of Qt.
-// grid: K / 32 column tiles; 256 threads.
-__global__ void __launch_bounds__(256) q_emit_kernel(const double* __restrict__ Z, int ldx, const float* __restrict__ Cp, int n,
+// grid: K / 32 column tiles; 256 threads; Z staged in shared memory.
+__global__ void __launch_bounds__(256) q_emit_kernel(const double* __restrict__ Z, int ldz, const float* __restrict__ Cp, int n,
                                                      int n_edit, int r_pad, int K, float* __restrict__ Q, float* __restrict__ Qt,
                                                      float* __restrict__ Qt_hi, float* __restrict__ Qt_lo) {
-    __shared__ float Cs[FS_MAX_N][33];
+    extern __shared__ double Zs[];                    // [n][n_edit]
+    float* Cs = reinterpret_cast<float*>(Zs + (size_t)n * n_edit);   // [n][33]
     const int k0 = blockIdx.x * 32, tid = threadIdx.x;
+    for (int idx = tid; idx < n * n_edit; idx += 256) Zs[idx] = Z[(long)(idx / n_edit) * ldz + idx % n_edit];
     for (int idx = tid; idx < n * 32; idx += 256) {
         const int r = idx / 32, c = idx % 32;
-        Cs[r][c] = (k0 + c < K) ? Cp[(long)r * K + k0 + c] : 0.f;
+        Cs[r * 33 + c] = (k0 + c < K) ? Cp[(long)r * K + k0 + c] : 0.f;
     }
     __syncthreads();
     const int c = tid % 32;
     for (int j = tid / 32; j < r_pad; j += 8) {
         double s = 0.0;
-        if (j < n_edit)
-            for (int r = 0; r < n; ++r) s = fma(Z[(long)r * ldx + j], (double)Cs[r][c], s);
+        if (j < n_edit) {
+#pragma unroll 4
+            for (int r = 0; r < n; ++r) s = fma(Zs[r * n_edit + j], (double)Cs[r * 33 + c], s);
+        }
         const float v = (float)s;
         if (k0 + c < K) {
             Q[(long)j * K + k0 + c] = v;
@@ -315,15 +322,15 @@ __global__ void pack_rows_split_kernel(const float* __restrict__ C, const float*
     }
 }
 
-bool factor_small_applicable(const uce_ws* ws, int n, bool dual) {
-    return dual && n <= FS_MAX_N && !ws->force_general;
+bool factor_small_applicable(const uce_ws* ws, int n, int n_edit, bool dual) {
+    return dual && n <= FS_MAX_N && n_edit <= FS_MAX_RHS && !ws->force_general;
 }
 
 // Preconditions: ws->h_src_idx / h_diag_add staged and copied, flag cleared, n_edit > 0.
 int factor_small(uce_ws* ws, const float* C, const float* G, int n, int n_pres, int n_edit, cudaStream_t st, int* launches) {
     const int K = ws->K;
     const int n_pad = round_up(n, FS_NB);
-    const int ldx = ws->max_rows;
+    const int ldz = ws->max_rows;
     ws->sys_n = n_pad;
     pack_rows_split_kernel<<<n + (ws->rank_pad - n_edit), 256, 0, st>>>(C, G, ws->src_idx, n, n_pres, ws->rank_pad, K, ws->Cp, ws->E,
                                                                          ws->E_hi, ws->E_lo);
@@ -334,18 +341,23 @@ int factor_small(uce_ws* ws, const float* C, const float* G, int n, int n_pres, 
     UCE_LAUNCH_CHECK(); ++*launches;
     if (ws->debug) {
         if (!ws->Hcopy) UCE_CUDA(cudaMalloc(&ws->Hcopy, (size_t)ws->sys_max * ws->sys_max * sizeof(double)));
-        // debug copy holds the assembled system: gram + diagonal (the kernel adds the diagonal in smem only)
         UCE_CUDA(cudaMemcpyAsync(ws->Hcopy, ws->H, (size_t)n_pad * n_pad * sizeof(double), cudaMemcpyDeviceToDevice, st));
     }
-    const size_t smem = (size_t)n_pad * (n_pad + 1) * sizeof(double);
-    static size_t configured = 0;
-    if (configured < smem) {
-        UCE_CUDA(cudaFuncSetAttribute(chol_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
+    const size_t smem_c = ((size_t)(nt * (nt + 1) / 2) * FS_BLK + (size_t)n_pad * (n_edit | 1) + n_pad) * sizeof(double);
+    static size_t conf_c = 0;
+    if (conf_c < smem_c) {
+        UCE_CUDA(cudaFuncSetAttribute(chol_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
+        conf_c = smem_c;
     }
-    chol_small_kernel<<<1, FS_T, smem, st>>>(ws->H, n, n_pad, ws->diag_add, n_pres, n_edit, ws->Linv, ws->X, ldx, ws->debug, ws->flag);
+    chol_small_kernel<<<1, FS_T, smem_c, st>>>(ws->H, n, n_pad, ws->diag_add, n_pres, n_edit, ws->X, ldz, ws->debug, ws->flag);
     UCE_LAUNCH_CHECK(); ++*launches;
-    q_emit_kernel<<<ceil_div(K, 32), 256, 0, st>>>(ws->X, ldx, ws->Cp, n, n_edit, ws->rank_pad, K, ws->Q, ws->Qt, ws->Qt_hi, ws->Qt_lo);
+    const size_t smem_q = (size_t)n * n_edit * sizeof(double) + (size_t)n * 33 * sizeof(float);
+    static size_t conf_q = 0;
+    if (conf_q < smem_q) {
+        UCE_CUDA(cudaFuncSetAttribute(q_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_q));
+        conf_q = smem_q;
+    }
+    q_emit_kernel<<<ceil_div(K, 32), 256, smem_q, st>>>(ws->X, ldz, ws->Cp, n, n_edit, ws->rank_pad, K, ws->Q, ws->Qt, ws->Qt_hi, ws->Qt_lo);
     UCE_LAUNCH_CHECK(); ++*launches;
     return 0;
 }

@@ -67,7 +67,7 @@ int factor_dev(uce_ws* ws, const float* C, const float* G, const float* scales_h
 int apply_dev(uce_ws* ws, const float* const* W_old, float* const* W_new, const int* d, int n_layers,
               cudaStream_t st, bool no_profile = false);
 // factor_small.cu
-bool factor_small_applicable(const uce_ws* ws, int n, bool dual);
+bool factor_small_applicable(const uce_ws* ws, int n, int n_edit, bool dual);
 int factor_small(uce_ws* ws, const float* C, const float* G, int n, int n_pres, int n_edit, cudaStream_t st, int* launches);
 // apply_tc.cu
 bool apply_tc_available(const uce_ws* ws);

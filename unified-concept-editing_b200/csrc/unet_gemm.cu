@@ -1,0 +1,258 @@
+// bf16 tcgen05 GEMM of the SD U-Net denoise step: every Linear, 1x1 conv, 3x3 conv
+// (implicit GEMM) and the two attention contractions run through this one kernel.
+//
+//     D[b][m][n] = alpha * sum_k A[b][m][k] * B[b][n][k]  (+ bias[n]) (+ rowbias[img(m)][n]) (+ residual[b][m][n])
+//
+// * operands are K-major bf16, fetched by TMA into 128B-swizzled smem stages (3-stage mbarrier pipeline);
+//   accumulation in TMEM (fp32) by tcgen05.mma.kind::f16, M = 128, N = 128 per CTA, K step 64.
+// * conv3x3 is an implicit GEMM without im2col: activations are NHWC, the A tile of an output rectangle
+//   (tn x th x tw = 128 pixels) for tap (ky,kx) is ONE 4-D TMA box shifted by the tap offset; out-of-image
+//   coordinates are zero-filled by the TMA unit (= the conv padding), stride 2 uses the tensor map's element
+//   strides.  Weights are stored tap-major [Cout][ky][kx][Cin].
+// * warp roles: warp 0 TMA producer, warp 1 MMA issuer (+TMEM alloc), warps 2-5 epilogue (TMEM -> registers ->
+//   bias / time-embedding / residual -> bf16 or fp32 global stores).  96 KB smem -> two CTAs per SM overlap each
+//   other's epilogues.
+#include "tc_common.cuh"
+#include "unet_gemm.h"
+#include <cuda_bf16.h>
+
+namespace uce {
+using namespace tc;
+
+constexpr int UG_BM = 128, UG_BN = 128, UG_BK = 64, UG_STAGES = 3;
+constexpr int UG_THREADS = 192;
+constexpr int UG_STAGE_BYTES = (UG_BM + UG_BN) * UG_BK * 2;     // 32 KB
+constexpr int UG_SMEM = UG_STAGES * UG_STAGE_BYTES + 1024 + 256;
+
+__global__ void __launch_bounds__(UG_THREADS, 2) unet_gemm_kernel(const __grid_constant__ GemmDesc g) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bars = base + UG_STAGES * UG_STAGE_BYTES;
+    auto bar_full = [&](int s) { return bars + 8u * s; };
+    auto bar_empty = [&](int s) { return bars + 8u * (UG_STAGES + s); };
+    const uint32_t bar_acc = bars + 8u * (2 * UG_STAGES);
+    const uint32_t tmem_slot = bars + 8u * (2 * UG_STAGES + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    const int n_tile = blockIdx.x, m_tile = blockIdx.y, b = blockIdx.z;
+    const int kpt = g.cin / UG_BK + ((g.cin % UG_BK) ? 1 : 0);     // k-iterations per tap
+    const int n_k = g.taps * kpt;
+
+    // conv: decode the output rectangle of this m-tile
+    int img0 = 0, h0 = 0, w0 = 0;
+    if (g.conv) {
+        const int tiles_w = g.Wo / g.tw, tiles_h = g.Ho / g.th;
+        int t = m_tile;
+        w0 = (t % tiles_w) * g.tw; t /= tiles_w;
+        h0 = (t % tiles_h) * g.th; t /= tiles_h;
+        img0 = t * g.tn;
+    }
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < UG_STAGES; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1); }
+        mbar_init(bar_acc, 1);
+        mbar_fence_init();
+        tma_prefetch_desc(&g.tmA); tma_prefetch_desc(&g.tmB);
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, UG_BN);
+    fence_before();
+    __syncthreads();
+    fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int it = 0; it < n_k; ++it) {
+                const int s = it % UG_STAGES;
+                mbar_wait(bar_empty(s), (uint32_t)(((it / UG_STAGES) & 1) ^ 1));
+                const uint32_t a_dst = base + s * UG_STAGE_BYTES, b_dst = a_dst + UG_BM * UG_BK * 2;
+                mbar_arrive_expect_tx(bar_full(s), UG_STAGE_BYTES);
+                const int tap = it / kpt, c0 = (it % kpt) * UG_BK;
+                if (g.conv) {
+                    const int ky = tap / 3, kx = tap % 3;
+                    tma_load_4d(a_dst, &g.tmA, bar_full(s), c0, w0 * g.stride + kx - g.pad, h0 * g.stride + ky - g.pad, img0);
+                } else {
+                    tma_load_3d(a_dst, &g.tmA, bar_full(s), c0, m_tile * UG_BM, b);
+                }
+                tma_load_3d(b_dst, &g.tmB, bar_full(s), tap * g.cin + c0, n_tile * UG_BN, g.b_batched ? b : 0);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = idesc_bf16(UG_BM, UG_BN);
+            for (int it = 0; it < n_k; ++it) {
+                const int s = it % UG_STAGES;
+                mbar_wait(bar_full(s), (uint32_t)((it / UG_STAGES) & 1));
+                fence_after();
+                const uint64_t a_desc = umma_desc_sw128(base + s * UG_STAGE_BYTES);
+                const uint64_t b_desc = umma_desc_sw128(base + s * UG_STAGE_BYTES + UG_BM * UG_BK * 2);
+#pragma unroll
+                for (int k = 0; k < UG_BK / 16; ++k)
+                    umma_bf16(tmem_base, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (it | k) != 0);
+                umma_commit(bar_empty(s));
+            }
+            umma_commit(bar_acc);
+        }
+    } else {
+        // ---- epilogue: TMEM lane = tile row ----
+        const int q = warp & 3;                       // TMEM lane quarter this warp may touch
+        const int r = 32 * q + lane;                  // tile row
+        long row;                                     // output row index within the batch (pixel index for conv)
+        int img = 0;
+        bool row_ok;
+        if (g.conv) {
+            const int per_img = g.th * g.tw;
+            const int ti = r / per_img, rem = r % per_img;
+            img = img0 + ti;
+            const int hh = h0 + rem / g.tw, ww = w0 + rem % g.tw;
+            row = ((long)img * g.Ho + hh) * g.Wo + ww;
+            row_ok = true;
+        } else {
+            row = (long)m_tile * UG_BM + r;
+            row_ok = row < g.M;
+            if (g.rows_per_img > 0) img = (int)(row / g.rows_per_img);
+        }
+        mbar_wait(bar_acc, 0);
+        fence_after();
+        const int n_base = n_tile * UG_BN;
+        const long obase = (long)b * g.out_batch_stride + row * g.ldo;
+        const long rbase = (long)b * g.res_batch_stride + row * g.ldr;
+#pragma unroll 1
+        for (int c = 0; c < UG_BN; c += 32) {
+            uint32_t v[32];
+            tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)c, v);
+            if (!row_ok || n_base + c >= g.N) continue;
+            float f[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) f[i] = g.alpha * __uint_as_float(v[i]);
+            const int n0 = n_base + c;
+            const bool full = (n0 + 32 <= g.N);
+            if (g.bias) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) if (full || n0 + i < g.N) f[i] += g.bias[n0 + i];
+            }
+            if (g.rowbias) {
+                const float* rb = g.rowbias + (long)img * g.N + n0;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) if (full || n0 + i < g.N) f[i] += rb[i];
+            }
+            if (g.residual) {
+                const __nv_bfloat16* rp = g.residual + rbase + n0;
+                if (full && ((g.ldr & 7) == 0)) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const uint4 u = *reinterpret_cast<const uint4*>(rp + 8 * j);
+                        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) { const float2 t2 = __bfloat1622float2(h2[e]); f[8 * j + 2 * e] += t2.x; f[8 * j + 2 * e + 1] += t2.y; }
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) if (n0 + i < g.N) f[i] += __bfloat162float(rp[i]);
+                }
+            }
+            if (g.out_fp32) {
+                float* op = reinterpret_cast<float*>(g.out) + obase + n0;
+                if (full && ((g.ldo & 3) == 0)) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) *reinterpret_cast<float4*>(op + 4 * j) = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) if (n0 + i < g.N) op[i] = f[i];
+                }
+            } else {
+                __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(g.out) + obase + n0;
+                if (full && ((g.ldo & 7) == 0)) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        uint4 u;
+                        __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) h2[e] = __floats2bfloat162_rn(f[8 * j + 2 * e], f[8 * j + 2 * e + 1]);
+                        *reinterpret_cast<uint4*>(op + 8 * j) = u;
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) if (n0 + i < g.N) op[i] = __float2bfloat16(f[i]);
+                }
+            }
+        }
+    }
+    fence_before();
+    __syncthreads();
+    if (warp == 1) { fence_after(); tmem_dealloc(tmem_base, UG_BN); }
+}
+
+// ------------------------------------------------------------------------------------------ host
+static int encode_bf16_map(CUtensorMap* m, const void* ptr, int rank, const long* dims, const long* strides_elems,
+                           const int* box, const int* estr) {
+    EncodeTiledFn enc = tensor_map_encoder();
+    if (!enc) return -1;
+    cuuint64_t gd[5]; cuuint64_t gs[4]; cuuint32_t bx[5]; cuuint32_t es[5];
+    for (int i = 0; i < rank; ++i) { gd[i] = (cuuint64_t)dims[i]; bx[i] = (cuuint32_t)box[i]; es[i] = (cuuint32_t)(estr ? estr[i] : 1); }
+    for (int i = 1; i < rank; ++i) gs[i - 1] = (cuuint64_t)strides_elems[i] * 2;
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), gd, gs, bx, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : (int)r;
+}
+
+int gemm_desc_linear(GemmDesc* g, const void* A, long lda, long a_batch_stride, const void* B, long ldb, long b_batch_stride,
+                     int M, int N, int Kd, int batch) {
+    memset(g, 0, sizeof(*g));
+    g->M = M; g->N = N; g->Kd = Kd; g->batch = batch; g->conv = 0; g->taps = 1; g->cin = Kd; g->alpha = 1.f;
+    g->b_batched = b_batch_stride != 0;
+    {
+        long dims[3] = {Kd, M, batch}, str[3] = {1, lda, a_batch_stride ? a_batch_stride : (long)M * lda};
+        int box[3] = {UG_BK, UG_BM, 1};
+        if (encode_bf16_map(&g->tmA, A, 3, dims, str, box, nullptr)) return -1;
+    }
+    {
+        long dims[3] = {Kd, N, g->b_batched ? batch : 1}, str[3] = {1, ldb, b_batch_stride ? b_batch_stride : (long)N * ldb};
+        int box[3] = {UG_BK, UG_BN, 1};
+        if (encode_bf16_map(&g->tmB, B, 3, dims, str, box, nullptr)) return -1;
+    }
+    return 0;
+}
+
+int gemm_desc_conv(GemmDesc* g, const void* act_nhwc, int NB, int Hin, int Win, int Cin, const void* w_tapmajor, int Cout,
+                   int ksize, int stride) {
+    memset(g, 0, sizeof(*g));
+    const int pad = ksize / 2;
+    const int Ho = (Hin + 2 * pad - ksize) / stride + 1, Wo = (Win + 2 * pad - ksize) / stride + 1;
+    g->conv = 1; g->taps = ksize * ksize; g->cin = Cin; g->stride = stride; g->pad = pad; g->alpha = 1.f;
+    g->Ho = Ho; g->Wo = Wo; g->NBimg = NB; g->batch = 1;
+    g->M = NB * Ho * Wo; g->N = Cout; g->Kd = g->taps * Cin;
+    // output rectangle of 128 pixels
+    int tw = Wo < 128 ? Wo : 128, th = 128 / tw; if (th > Ho) th = Ho;
+    int tn = 128 / (tw * th);
+    if (tw * th * tn != 128 || Wo % tw || Ho % th || NB % tn) return -2;
+    g->tw = tw; g->th = th; g->tn = tn;
+    {
+        long dims[4] = {Cin, Win, Hin, NB}, str[4] = {1, Cin, (long)Win * Cin, (long)Hin * Win * Cin};
+        int box[4] = {UG_BK, (tw - 1) * stride + 1, (th - 1) * stride + 1, tn};
+        int es[4] = {1, stride, stride, 1};
+        if (encode_bf16_map(&g->tmA, act_nhwc, 4, dims, str, box, es)) return -1;
+    }
+    {
+        long dims[3] = {(long)g->taps * Cin, Cout, 1}, str[3] = {1, (long)g->taps * Cin, (long)Cout * g->taps * Cin};
+        int box[3] = {UG_BK, UG_BN, 1};
+        if (encode_bf16_map(&g->tmB, w_tapmajor, 3, dims, str, box, nullptr)) return -1;
+    }
+    return 0;
+}
+
+int gemm_launch(const GemmDesc& g, cudaStream_t st) {
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(unet_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, UG_SMEM);
+        if (e != cudaSuccess) return (int)e;
+        configured = true;
+    }
+    dim3 grid((g.N + UG_BN - 1) / UG_BN, (g.M + UG_BM - 1) / UG_BM, g.batch);
+    unet_gemm_kernel<<<grid, UG_THREADS, UG_SMEM, st>>>(g);
+    return (int)cudaGetLastError();
+}
+
+}  // namespace uce

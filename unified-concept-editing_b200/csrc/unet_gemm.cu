@@ -34,7 +34,8 @@ __global__ void __launch_bounds__(UG_THREADS, 2) unet_gemm_kernel(const __grid_c
     const uint32_t tmem_slot = bars + 8u * (2 * UG_STAGES + 1);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-    const int n_tile = blockIdx.x, m_tile = blockIdx.y, b = blockIdx.z;
+    const int n_tile = blockIdx.x, m_tile = blockIdx.y;
+    const int b1 = blockIdx.z % g.b1cnt, b2 = blockIdx.z / g.b1cnt;
     const int kpt = g.cin / UG_BK + ((g.cin % UG_BK) ? 1 : 0);     // k-iterations per tap
     const int n_k = g.taps * kpt;
 
@@ -73,9 +74,9 @@ __global__ void __launch_bounds__(UG_THREADS, 2) unet_gemm_kernel(const __grid_c
                     const int ky = tap / 3, kx = tap % 3;
                     tma_load_4d(a_dst, &g.tmA, bar_full(s), c0, w0 * g.stride + kx - g.pad, h0 * g.stride + ky - g.pad, img0);
                 } else {
-                    tma_load_3d(a_dst, &g.tmA, bar_full(s), c0, m_tile * UG_BM, b);
+                    tma_load_4d(a_dst, &g.tmA, bar_full(s), c0, m_tile * UG_BM, g.a_batched ? b1 : 0, g.a_batched ? b2 : 0);
                 }
-                tma_load_3d(b_dst, &g.tmB, bar_full(s), tap * g.cin + c0, n_tile * UG_BN, g.b_batched ? b : 0);
+                tma_load_4d(b_dst, &g.tmB, bar_full(s), tap * g.cin + c0, n_tile * UG_BN, g.b_batched ? b1 : 0, g.b_batched ? b2 : 0);
             }
         }
     } else if (warp == 1) {
@@ -116,8 +117,8 @@ __global__ void __launch_bounds__(UG_THREADS, 2) unet_gemm_kernel(const __grid_c
         mbar_wait(bar_acc, 0);
         fence_after();
         const int n_base = n_tile * UG_BN;
-        const long obase = (long)b * g.out_batch_stride + row * g.ldo;
-        const long rbase = (long)b * g.res_batch_stride + row * g.ldr;
+        const long obase = (long)b1 * g.out_b1_stride + (long)b2 * g.out_b2_stride + row * g.ldo;
+        const long rbase = (long)b1 * g.res_b1_stride + (long)b2 * g.res_b2_stride + row * g.ldr;
 #pragma unroll 1
         for (int c = 0; c < UG_BN; c += 32) {
             uint32_t v[32];
@@ -198,20 +199,22 @@ static int encode_bf16_map(CUtensorMap* m, const void* ptr, int rank, const long
     return r == CUDA_SUCCESS ? 0 : (int)r;
 }
 
-int gemm_desc_linear(GemmDesc* g, const void* A, long lda, long a_batch_stride, const void* B, long ldb, long b_batch_stride,
-                     int M, int N, int Kd, int batch) {
+int gemm_desc_linear(GemmDesc* g, const void* A, long lda, long a_b1_stride, long a_b2_stride, const void* B, long ldb,
+                     long b_b1_stride, long b_b2_stride, int M, int N, int Kd, int b1cnt, int b2cnt, int a_batched, int b_batched) {
     memset(g, 0, sizeof(*g));
-    g->M = M; g->N = N; g->Kd = Kd; g->batch = batch; g->conv = 0; g->taps = 1; g->cin = Kd; g->alpha = 1.f;
-    g->b_batched = b_batch_stride != 0;
+    g->M = M; g->N = N; g->Kd = Kd; g->batch = b1cnt * b2cnt; g->b1cnt = b1cnt; g->conv = 0; g->taps = 1; g->cin = Kd; g->alpha = 1.f;
+    g->a_batched = a_batched; g->b_batched = b_batched;
     {
-        long dims[3] = {Kd, M, batch}, str[3] = {1, lda, a_batch_stride ? a_batch_stride : (long)M * lda};
-        int box[3] = {UG_BK, UG_BM, 1};
-        if (encode_bf16_map(&g->tmA, A, 3, dims, str, box, nullptr)) return -1;
+        long dims[4] = {Kd, M, a_batched ? b1cnt : 1, a_batched ? b2cnt : 1};
+        long str[4] = {1, lda, a_batched && a_b1_stride ? a_b1_stride : (long)M * lda, a_batched && a_b2_stride ? a_b2_stride : (long)M * lda};
+        int box[4] = {UG_BK, UG_BM, 1, 1};
+        if (encode_bf16_map(&g->tmA, A, 4, dims, str, box, nullptr)) return -1;
     }
     {
-        long dims[3] = {Kd, N, g->b_batched ? batch : 1}, str[3] = {1, ldb, b_batch_stride ? b_batch_stride : (long)N * ldb};
-        int box[3] = {UG_BK, UG_BN, 1};
-        if (encode_bf16_map(&g->tmB, B, 3, dims, str, box, nullptr)) return -1;
+        long dims[4] = {Kd, N, b_batched ? b1cnt : 1, b_batched ? b2cnt : 1};
+        long str[4] = {1, ldb, b_batched && b_b1_stride ? b_b1_stride : (long)N * ldb, b_batched && b_b2_stride ? b_b2_stride : (long)N * ldb};
+        int box[4] = {UG_BK, UG_BN, 1, 1};
+        if (encode_bf16_map(&g->tmB, B, 4, dims, str, box, nullptr)) return -1;
     }
     return 0;
 }
@@ -222,7 +225,7 @@ int gemm_desc_conv(GemmDesc* g, const void* act_nhwc, int NB, int Hin, int Win, 
     const int pad = ksize / 2;
     const int Ho = (Hin + 2 * pad - ksize) / stride + 1, Wo = (Win + 2 * pad - ksize) / stride + 1;
     g->conv = 1; g->taps = ksize * ksize; g->cin = Cin; g->stride = stride; g->pad = pad; g->alpha = 1.f;
-    g->Ho = Ho; g->Wo = Wo; g->NBimg = NB; g->batch = 1;
+    g->Ho = Ho; g->Wo = Wo; g->NBimg = NB; g->batch = 1; g->b1cnt = 1; g->a_batched = 0; g->b_batched = 0;
     g->M = NB * Ho * Wo; g->N = Cout; g->Kd = g->taps * Cin;
     // output rectangle of 128 pixels
     int tw = Wo < 128 ? Wo : 128, th = 128 / tw; if (th > Ho) th = Ho;
@@ -236,9 +239,10 @@ int gemm_desc_conv(GemmDesc* g, const void* act_nhwc, int NB, int Hin, int Win, 
         if (encode_bf16_map(&g->tmA, act_nhwc, 4, dims, str, box, es)) return -1;
     }
     {
-        long dims[3] = {(long)g->taps * Cin, Cout, 1}, str[3] = {1, (long)g->taps * Cin, (long)Cout * g->taps * Cin};
-        int box[3] = {UG_BK, UG_BN, 1};
-        if (encode_bf16_map(&g->tmB, w_tapmajor, 3, dims, str, box, nullptr)) return -1;
+        long dims[4] = {(long)g->taps * Cin, Cout, 1, 1};
+        long str[4] = {1, (long)g->taps * Cin, (long)Cout * g->taps * Cin, (long)Cout * g->taps * Cin};
+        int box[4] = {UG_BK, UG_BN, 1, 1};
+        if (encode_bf16_map(&g->tmB, w_tapmajor, 4, dims, str, box, nullptr)) return -1;
     }
     return 0;
 }

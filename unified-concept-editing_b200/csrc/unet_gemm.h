@@ -1,0 +1,32 @@
+// Descriptor of one bf16 tcgen05 GEMM / implicit-GEMM convolution launch (see unet_gemm.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cstring>
+
+namespace uce {
+
+struct GemmDesc {
+    CUtensorMap tmA, tmB;      // A: linear {K, M, b1, b2} or conv {C, W, H, N};  B: {K, N, b1, b2}
+    int M, N, Kd;              // per-batch problem (conv: M = NB*Ho*Wo, Kd = taps*Cin)
+    int batch, b1cnt;          // grid.z = batch; z -> (b1 = z % b1cnt, b2 = z / b1cnt)
+    int a_batched, b_batched;  // whether the operand's tensor map is indexed by (b1, b2)
+    int conv, taps, cin, stride, pad;
+    int tw, th, tn, Wo, Ho, NBimg;
+    int rows_per_img;          // linear: image index of a row = row / rows_per_img (for rowbias); 0 = none
+    float alpha;
+    void* out; int out_fp32; long ldo, out_b1_stride, out_b2_stride;
+    const float* bias;         // [N]
+    const float* rowbias;      // [images][N]
+    const __nv_bfloat16* residual; long ldr, res_b1_stride, res_b2_stride;
+};
+
+// A [b2][b1][M][Kd] via strides (elements), B likewise; batch = b1cnt * b2cnt.
+int gemm_desc_linear(GemmDesc* g, const void* A, long lda, long a_b1_stride, long a_b2_stride, const void* B, long ldb,
+                     long b_b1_stride, long b_b2_stride, int M, int N, int Kd, int b1cnt, int b2cnt, int a_batched, int b_batched);
+int gemm_desc_conv(GemmDesc* g, const void* act_nhwc, int NB, int Hin, int Win, int Cin, const void* w_tapmajor, int Cout,
+                   int ksize, int stride);
+int gemm_launch(const GemmDesc& g, cudaStream_t st);
+
+}  // namespace uce

@@ -1,0 +1,367 @@
+// Memory-bound kernels of the SD U-Net denoise step: GroupNorm(+SiLU), LayerNorm, softmax,
+// GEGLU, nearest upsample, channel concat, the 4-channel input/output convolutions, timestep embedding and the
+// fused classifier-free-guidance + scheduler update.  Activations are NHWC bf16; all kernels use 16-byte vector
+// accesses along the channel dimension and warp-shuffle reductions.
+#include "unet_ops.h"
+#include <cuda_bf16.h>
+#include <cstdint>
+
+namespace uce {
+
+__device__ __forceinline__ float warp_sum_f(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max_f(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { const float2 t = __bfloat1622float2(h[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+    uint4 u;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+    return u;
+}
+__device__ __forceinline__ float silu_f(float x) { return x / (1.f + __expf(-x)); }
+
+// ---------------------------------------------------------------------------------------------- GroupNorm
+// stats[(img*G + g)*2 + {0,1}] += (sum, sum of squares) over the pixels of this CTA's slab.
+// grid (slabs, NB); block 256.
+__global__ void __launch_bounds__(256) gn_stats_kernel(const __nv_bfloat16* __restrict__ x, int HW, int C, int G, int pix_per_cta,
+                                                       float* __restrict__ stats) {
+    extern __shared__ float red[];                 // [2 * G]
+    const int img = blockIdx.y, p0 = blockIdx.x * pix_per_cta;
+    const int vec_per_pix = C / 8, cpg = C / G;
+    for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) red[i] = 0.f;
+    __syncthreads();
+    const __nv_bfloat16* base = x + ((long)img * HW + p0) * C;
+    const int npix = min(pix_per_cta, HW - p0);
+    // a thread owns one 8-channel column (coalesced across the warp) and walks the slab's pixels; per-channel partial
+    // sums stay in registers and are binned into the group accumulators once at the end
+    for (int cv = threadIdx.x; cv < vec_per_pix; cv += blockDim.x) {
+        float s[8], ss[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { s[i] = 0.f; ss[i] = 0.f; }
+#pragma unroll 4
+        for (int p = 0; p < npix; ++p) {
+            float f[8];
+            unpack8(*reinterpret_cast<const uint4*>(base + (long)p * C + cv * 8), f);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { s[i] += f[i]; ss[i] += f[i] * f[i]; }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int g = (cv * 8 + i) / cpg;
+            atomicAdd(&red[2 * g], s[i]); atomicAdd(&red[2 * g + 1], ss[i]);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) atomicAdd(&stats[(long)img * G * 2 + i], red[i]);
+}
+
+// y = (x - mean) * rstd * gamma + beta, optional SiLU.  One thread per 8-channel vector.
+__global__ void __launch_bounds__(256) gn_apply_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, long n_vec, int HW,
+                                                       int C, int G, const float* __restrict__ stats, const float* __restrict__ gamma,
+                                                       const float* __restrict__ beta, float eps, int silu) {
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n_vec) return;
+    const int vec_per_pix = C / 8, cpg = C / G;
+    const int cv = (int)(idx % vec_per_pix);
+    const int img = (int)(idx / ((long)vec_per_pix * HW));
+    const uint4 u = *reinterpret_cast<const uint4*>(x + idx * 8);
+    float f[8];
+    unpack8(u, f);
+    const float inv_n = 1.f / ((float)HW * cpg);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int c = cv * 8 + i, g = c / cpg;
+        const float s = stats[((long)img * G + g) * 2], ss = stats[((long)img * G + g) * 2 + 1];
+        const float mean = s * inv_n;
+        const float var = fmaxf(ss * inv_n - mean * mean, 0.f);
+        float v = (f[i] - mean) * rsqrtf(var + eps) * gamma[c] + beta[c];
+        f[i] = silu ? silu_f(v) : v;
+    }
+    *reinterpret_cast<uint4*>(y + idx * 8) = pack8(f);
+}
+
+// ---------------------------------------------------------------------------------------------- LayerNorm
+// one warp per row of C channels (C % 8 == 0, C <= 1280): row cached in registers (two-pass variance).
+__global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, long rows, int C,
+                                                        const float* __restrict__ gamma, const float* __restrict__ beta, float eps) {
+    const long row = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const int nvec = C / 8;
+    float f[5][8];                                  // up to 5 vectors per lane (C <= 1280)
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+        const int v = lane + 32 * i;
+        if (v < nvec) {
+            unpack8(*reinterpret_cast<const uint4*>(x + row * C + v * 8), f[i]);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) s += f[i][e];
+        }
+    }
+    const float mean = warp_sum_f(s) / C;
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < 5; ++i)
+        if (lane + 32 * i < nvec)
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { const float d = f[i][e] - mean; ss += d * d; }
+    const float rstd = rsqrtf(warp_sum_f(ss) / C + eps);
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+        const int v = lane + 32 * i;
+        if (v < nvec) {
+            float o[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[e] = (f[i][e] - mean) * rstd * gamma[v * 8 + e] + beta[v * 8 + e];
+            *reinterpret_cast<uint4*>(y + row * C + v * 8) = pack8(o);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- softmax
+// P[row, 0:ldp] (bf16) = softmax(S[row, 0:Lk]) (fp32 logits, already scaled), zero beyond Lk.  One CTA of 128 threads per row.
+__global__ void __launch_bounds__(128) softmax_kernel(const float* __restrict__ S, long lds, __nv_bfloat16* __restrict__ P, long ldp, int Lk) {
+    __shared__ float red[4];
+    const long row = blockIdx.x;
+    const float* s = S + row * lds;
+    __nv_bfloat16* p = P + row * ldp;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float m = -INFINITY;
+    for (int i = tid; i < Lk; i += 128) m = fmaxf(m, s[i]);
+    m = warp_max_f(m);
+    if (lane == 0) red[warp] = m;
+    __syncthreads();
+    m = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+    __syncthreads();
+    float sum = 0.f;
+    for (int i = tid; i < Lk; i += 128) sum += __expf(s[i] - m);
+    sum = warp_sum_f(sum);
+    if (lane == 0) red[warp] = sum;
+    __syncthreads();
+    const float inv = 1.f / (red[0] + red[1] + red[2] + red[3]);
+    for (int i = tid; i < (int)ldp; i += 128) p[i] = __float2bfloat16(i < Lk ? __expf(s[i] - m) * inv : 0.f);
+}
+
+// ---------------------------------------------------------------------------------------------- elementwise
+// GEGLU: y[r, c] = x[r, c] * gelu_erf(x[r, 4C' + c]),  x [rows, 2*H], y [rows, H]
+__global__ void __launch_bounds__(256) geglu_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, long rows, int Hd) {
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int vpr = Hd / 8;
+    if (idx >= rows * vpr) return;
+    const long r = idx / vpr; const int v = (int)(idx % vpr);
+    float a[8], g[8];
+    unpack8(*reinterpret_cast<const uint4*>(x + r * 2 * Hd + v * 8), a);
+    unpack8(*reinterpret_cast<const uint4*>(x + r * 2 * Hd + Hd + v * 8), g);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] *= 0.5f * g[i] * (1.f + erff(g[i] * 0.70710678118654752f));
+    *reinterpret_cast<uint4*>(y + r * Hd + v * 8) = pack8(a);
+}
+
+__global__ void __launch_bounds__(256) silu_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, long n) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] = __float2bfloat16(silu_f(__bfloat162float(x[i])));
+}
+
+// nearest 2x upsample, NHWC
+__global__ void __launch_bounds__(256) upsample2x_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int NB, int H, int W, int C) {
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int vpp = C / 8;
+    const long total = (long)NB * 4 * H * W * vpp;
+    if (idx >= total) return;
+    const int v = (int)(idx % vpp); long p = idx / vpp;
+    const int wo = (int)(p % (2 * W)); p /= 2 * W;
+    const int ho = (int)(p % (2 * H)); const int n = (int)(p / (2 * H));
+    *reinterpret_cast<uint4*>(y + idx * 8) = *reinterpret_cast<const uint4*>(x + (((long)n * H + ho / 2) * W + wo / 2) * C + v * 8);
+}
+
+// channel concat: y[..., 0:C1] = a, y[..., C1:C1+C2] = b
+__global__ void __launch_bounds__(256) concat_c_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b,
+                                                       __nv_bfloat16* __restrict__ y, long pixels, int C1, int C2) {
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int vpp = (C1 + C2) / 8;
+    if (idx >= pixels * vpp) return;
+    const long p = idx / vpp; const int v = (int)(idx % vpp);
+    const int c = v * 8;
+    const uint4 u = (c < C1) ? *reinterpret_cast<const uint4*>(a + p * C1 + c) : *reinterpret_cast<const uint4*>(b + p * C2 + (c - C1));
+    *reinterpret_cast<uint4*>(y + idx * 8) = u;
+}
+
+// conv_in: 3x3, 4 -> Cout, input NCHW (fp32 latents), output NHWC bf16.  One thread per (pixel, 8 output channels).
+__global__ void __launch_bounds__(256) conv_in_kernel(const float* __restrict__ x, const float* __restrict__ w /*[Cout][4][3][3]*/,
+                                                      const float* __restrict__ bias, __nv_bfloat16* __restrict__ y, int NB, int H, int W, int Cout) {
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int vpp = Cout / 8;
+    if (idx >= (long)NB * H * W * vpp) return;
+    const int v = (int)(idx % vpp); long p = idx / vpp;
+    const int ww = (int)(p % W); p /= W; const int hh = (int)(p % H); const int n = (int)(p / H);
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = bias[v * 8 + i];
+    for (int ci = 0; ci < 4; ++ci)
+        for (int ky = 0; ky < 3; ++ky) {
+            const int iy = hh + ky - 1;
+            if (iy < 0 || iy >= H) continue;
+            for (int kx = 0; kx < 3; ++kx) {
+                const int ix = ww + kx - 1;
+                if (ix < 0 || ix >= W) continue;
+                const float xv = x[(((long)n * 4 + ci) * H + iy) * W + ix];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) acc[i] += xv * w[(((v * 8 + i) * 4 + ci) * 3 + ky) * 3 + kx];
+            }
+        }
+    *reinterpret_cast<uint4*>(y + idx * 8) = pack8(acc);
+}
+
+// conv_out: 3x3, Cin -> 4, input NHWC bf16 (already normalised + SiLU), output NCHW fp32.  One warp per pixel.
+__global__ void __launch_bounds__(256) conv_out_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w /*[4][3][3][Cin]*/,
+                                                       const float* __restrict__ bias, float* __restrict__ y, int NB, int H, int W, int Cin) {
+    const long pix = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (pix >= (long)NB * H * W) return;
+    long p = pix;
+    const int ww = (int)(p % W); p /= W; const int hh = (int)(p % H); const int n = (int)(p / H);
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int ky = 0; ky < 3; ++ky) {
+        const int iy = hh + ky - 1;
+        if (iy < 0 || iy >= H) continue;
+        for (int kx = 0; kx < 3; ++kx) {
+            const int ix = ww + kx - 1;
+            if (ix < 0 || ix >= W) continue;
+            const __nv_bfloat16* xp = x + (((long)n * H + iy) * W + ix) * Cin;
+            for (int c = lane * 8; c < Cin; c += 256) {
+                float f[8];
+                unpack8(*reinterpret_cast<const uint4*>(xp + c), f);
+#pragma unroll
+                for (int o = 0; o < 4; ++o) {
+                    const float* wp = w + ((o * 3 + ky) * 3 + kx) * Cin + c;
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) acc[o] += f[e] * wp[e];
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 0; o < 4; ++o) {
+        const float s = warp_sum_f(acc[o]);
+        if (lane == 0) y[(((long)n * 4 + o) * H + hh) * W + ww] = s + bias[o];
+    }
+}
+
+// sinusoidal timestep embedding [cos | sin] (flip_sin_to_cos, freq_shift 0), fp32 math, bf16 out, same t for all images
+__global__ void timestep_embedding_kernel(float t, int dim, int NB, __nv_bfloat16* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int half = dim / 2;
+    if (i >= half) return;
+    const float freq = expf(-logf(10000.f) * (float)i / (float)half);
+    const float a = t * freq;
+    for (int n = 0; n < NB; ++n) {
+        out[(long)n * dim + i] = __float2bfloat16(cosf(a));
+        out[(long)n * dim + half + i] = __float2bfloat16(sinf(a));
+    }
+}
+
+// classifier-free guidance + linear scheduler update on fp32 NCHW latents:
+//   eps = eps_u + gs (eps_t - eps_u);   e = sum_k ck[k] * hist_k  (hist_0 = eps, PLMS multistep);  x <- cx x + ce e
+// eps2 = [uncond batch | text batch]; eps_out receives the guided eps (kept by the host as PLMS history).
+__global__ void __launch_bounds__(256) cfg_step_kernel(const float* __restrict__ eps2, long n, float gs, float* __restrict__ eps_out,
+                                                       const float* __restrict__ h1, const float* __restrict__ h2, const float* __restrict__ h3,
+                                                       float c0, float c1, float c2, float c3, float cx, float ce,
+                                                       const float* __restrict__ x_in, float* __restrict__ x_out) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float eu = eps2[i], et = eps2[n + i];
+    const float eps = eu + gs * (et - eu);
+    if (eps_out) eps_out[i] = eps;
+    float e = c0 * eps;
+    if (h1) e += c1 * h1[i];
+    if (h2) e += c2 * h2[i];
+    if (h3) e += c3 * h3[i];
+    x_out[i] = cx * x_in[i] + ce * e;
+}
+
+// ---------------------------------------------------------------------------------------------- launchers
+#define OPS_CHECK() do { cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) return (int)e_; } while (0)
+
+int op_groupnorm(const __nv_bfloat16* x, __nv_bfloat16* y, int NB, int HW, int C, int G, float* stats, const float* gamma, const float* beta,
+                 float eps, int silu, cudaStream_t st) {
+    cudaError_t e = cudaMemsetAsync(stats, 0, (size_t)NB * G * 2 * sizeof(float), st);
+    if (e != cudaSuccess) return (int)e;
+    const int pix_per_cta = HW >= 1024 ? 64 : (HW >= 64 ? 16 : HW);
+    gn_stats_kernel<<<dim3((HW + pix_per_cta - 1) / pix_per_cta, NB), 256, 2 * G * sizeof(float), st>>>(x, HW, C, G, pix_per_cta, stats);
+    OPS_CHECK();
+    const long n_vec = (long)NB * HW * C / 8;
+    gn_apply_kernel<<<(unsigned)((n_vec + 255) / 256), 256, 0, st>>>(x, y, n_vec, HW, C, G, stats, gamma, beta, eps, silu);
+    OPS_CHECK();
+    return 0;
+}
+int op_layernorm(const __nv_bfloat16* x, __nv_bfloat16* y, long rows, int C, const float* gamma, const float* beta, float eps, cudaStream_t st) {
+    layernorm_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(x, y, rows, C, gamma, beta, eps);
+    OPS_CHECK();
+    return 0;
+}
+int op_softmax(const float* S, long lds, __nv_bfloat16* P, long ldp, long rows, int Lk, cudaStream_t st) {
+    softmax_kernel<<<(unsigned)rows, 128, 0, st>>>(S, lds, P, ldp, Lk);
+    OPS_CHECK();
+    return 0;
+}
+int op_geglu(const __nv_bfloat16* x, __nv_bfloat16* y, long rows, int Hd, cudaStream_t st) {
+    const long n = rows * (Hd / 8);
+    geglu_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, y, rows, Hd);
+    OPS_CHECK();
+    return 0;
+}
+int op_silu(const __nv_bfloat16* x, __nv_bfloat16* y, long n, cudaStream_t st) {
+    silu_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, y, n);
+    OPS_CHECK();
+    return 0;
+}
+int op_upsample2x(const __nv_bfloat16* x, __nv_bfloat16* y, int NB, int H, int W, int C, cudaStream_t st) {
+    const long n = (long)NB * 4 * H * W * (C / 8);
+    upsample2x_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, y, NB, H, W, C);
+    OPS_CHECK();
+    return 0;
+}
+int op_concat_c(const __nv_bfloat16* a, const __nv_bfloat16* b, __nv_bfloat16* y, long pixels, int C1, int C2, cudaStream_t st) {
+    const long n = pixels * ((C1 + C2) / 8);
+    concat_c_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(a, b, y, pixels, C1, C2);
+    OPS_CHECK();
+    return 0;
+}
+int op_conv_in(const float* x, const float* w, const float* bias, __nv_bfloat16* y, int NB, int H, int W, int Cout, cudaStream_t st) {
+    const long n = (long)NB * H * W * (Cout / 8);
+    conv_in_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, w, bias, y, NB, H, W, Cout);
+    OPS_CHECK();
+    return 0;
+}
+int op_conv_out(const __nv_bfloat16* x, const float* w, const float* bias, float* y, int NB, int H, int W, int Cin, cudaStream_t st) {
+    const long pix = (long)NB * H * W;
+    conv_out_kernel<<<(unsigned)((pix + 7) / 8), 256, 0, st>>>(x, w, bias, y, NB, H, W, Cin);
+    OPS_CHECK();
+    return 0;
+}
+int op_timestep_embedding(float t, int dim, int NB, __nv_bfloat16* out, cudaStream_t st) {
+    timestep_embedding_kernel<<<(dim / 2 + 127) / 128, 128, 0, st>>>(t, dim, NB, out);
+    OPS_CHECK();
+    return 0;
+}
+int op_cfg_step(const float* eps2, long n, float gs, float* eps_out, const float* h1, const float* h2, const float* h3, float c0, float c1,
+                float c2, float c3, float cx, float ce, const float* x_in, float* x_out, cudaStream_t st) {
+    cfg_step_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(eps2, n, gs, eps_out, h1, h2, h3, c0, c1, c2, c3, cx, ce, x_in, x_out);
+    OPS_CHECK();
+    return 0;
+}
+
+}  // namespace uce

@@ -114,7 +114,7 @@ int apply_dev(uce_ws* ws, const float* const* W_old, float* const* W_new, const 
     slot_begin = ws->ring_pos;
     ws->ring_pos += n_layers;
     LayerRef* hl = ws->h_layers + slot_begin;
-    const bool use_tc = !ws->dense && ws->rank > 0 && ((ws->apply_impl == 2) || (ws->apply_impl == 0 && apply_tc_available(ws)));
+    const bool use_tc = !ws->dense && ws->rank > 0 && ((ws->apply_impl == 2) || (ws->apply_impl == 0 && apply_tc_available(ws) && n_layers <= 160));
     const int tile_rows = use_tc ? 128 : SG_BM;
     int tiles = 0; bool inplace = false;
     for (int l = 0; l < n_layers; ++l) {

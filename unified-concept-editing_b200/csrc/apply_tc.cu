@@ -6,9 +6,11 @@
 // read of the tile (epilogue addend) is an L2 hit.
 //
 //   phase A  P[128,R] = W_tile[128,K] . E[R,K]^T   accumulated in TMEM columns [0,R)
-//            * 8 producer warps stream W_tile from global (LDG.128, 4 chunks in flight per thread), split every
-//              value into hi = rna_tf32(w) and lo = w - hi IN REGISTERS and store both into 128B-swizzled K-major
-//              smem tiles (an elementwise transform TMA cannot do)
+//            * 1 TMA warp streams raw fp32 W chunks [128 x 32] into a 5-deep smem ring (80 KB in flight per SM,
+//              one tensor map per projection passed as a __grid_constant__ array, L2 evict_last)
+//            * 8 transform warps split every value into hi = rna_tf32(w) and lo = w - hi and write both into the
+//              128B-swizzled K-major MMA stages (they hold no global loads, so their generic->async proxy fence
+//              is cheap — an earlier LDG-based version lost its prefetch to that fence, see profiles/)
 //            * 1 TMA warp fetches the matching [R,32] tiles of the pre-split E_hi / E_lo (L2 resident)
 //            * 1 MMA thread issues per 8-wide k-step  hi.hi + lo.hi + hi.lo  (tcgen05.mma kind::tf32, M=128, N=R)
 //   phase B  dW^T[K-chunk of 128, 128 rows] = Qt[128,R] . P[128,R]^T in two ping-pong TMEM accumulators
@@ -27,11 +29,15 @@ namespace uce {
 
 constexpr int TC_TILE_M = 128;
 constexpr int TC_PRODUCER_WARPS = 8;
-constexpr int TC_THREADS = (TC_PRODUCER_WARPS + 2) * 32;   // + TMA warp + MMA warp
+constexpr int TC_THREADS = (TC_PRODUCER_WARPS + 3) * 32;   // + W TMA warp + E/Qt TMA warp + MMA warp
 constexpr int TC_QT_STAGES = 2;
-constexpr int TC_PF = 6;                                    // W chunks in flight per producer thread (96 KB per SM)
+constexpr int TC_NRAW = 5;                                  // raw W chunks in flight per SM (5 x 16 KB by TMA)
+constexpr int TC_SA = 2;                                    // hi/lo MMA stages
+constexpr int TC_MAX_LAYERS = 160;                          // per-launch tensor maps for W_old (one per projection)
+constexpr int WARP_W_TMA = TC_PRODUCER_WARPS, WARP_E_TMA = TC_PRODUCER_WARPS + 1, WARP_MMA = TC_PRODUCER_WARPS + 2;
 
 struct TcMaps { CUtensorMap e_hi, e_lo, qt_hi, qt_lo; };
+struct TcWMaps { CUtensorMap w[TC_MAX_LAYERS]; };
 
 // ------------------------------------------------------------------------------------------ PTX helpers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -144,6 +150,15 @@ __device__ __forceinline__ float ldg_f32(const float* p) {
 __device__ __forceinline__ void stg_f32_hint(float* p, float v, uint64_t pol) {
     asm volatile("st.global.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(p), "f"(v), "l"(pol) : "memory");
 }
+__device__ __forceinline__ float4 lds_v4(uint32_t addr) {
+    float4 r;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(addr) : "memory");
+    return r;
+}
+__device__ __forceinline__ void tma_load_2d_hint(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, uint64_t pol) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+                 ::"r"(dst), "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1), "l"(pol) : "memory");
+}
 __device__ __forceinline__ void sts_v4(uint32_t addr, float a, float b, float c, float d) {
     asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
@@ -158,30 +173,30 @@ __device__ __forceinline__ int tc_find_layer(const LayerRef* layers, int n_layer
 }
 
 // Shared-memory carve-up (bytes), identical on host and device.
+//   [0, raw)            raw ring: TC_NRAW x 16 KB fp32 W chunks written by TMA; phase B: the two Qt stages alias it
+//   [raw, raw + a)      TC_SA x {W_hi 16K, W_lo 16K, E_hi R*128, E_lo R*128}; phase B: P_hi | P_lo alias it
 struct TcSmem {
-    int stages_a;        // W/E pipeline depth
-    int stage_a_bytes;   // W_hi 16K + W_lo 16K + E_hi R*128 + E_lo R*128
-    int region_a;        // max(stages_a * stage_a_bytes, P_hi + P_lo)
-    int qt_off;          // Qt stages after region A
+    int stage_a_bytes;
+    int a_off;
+    int region_a;
     int bar_off;
     int total;
 };
 __host__ __device__ inline TcSmem tc_smem_layout(int R) {
     TcSmem s;
-    s.stages_a = (R <= 64) ? 3 : 2;
     s.stage_a_bytes = 32768 + 2 * R * 128;
-    int a = s.stages_a * s.stage_a_bytes;
+    s.a_off = TC_NRAW * 16384;
+    int a = TC_SA * s.stage_a_bytes;
     int p = 2 * TC_TILE_M * R * 4;
     s.region_a = a > p ? a : p;
-    s.qt_off = s.region_a;
-    s.bar_off = s.qt_off + TC_QT_STAGES * 32768;
-    s.total = s.bar_off + 256;
+    s.bar_off = s.a_off + s.region_a;
+    s.total = s.bar_off + 512;
     return s;
 }
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
 apply_tc_kernel(const LayerRef* __restrict__ layers, int n_layers, int K, int R,
-                const __grid_constant__ TcMaps maps) {
+                const __grid_constant__ TcMaps maps, const __grid_constant__ TcWMaps wmaps) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // dynamic smem base is at least 16-byte aligned; swizzled tiles need 1024
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -190,18 +205,21 @@ apply_tc_kernel(const LayerRef* __restrict__ layers, int n_layers, int K, int R,
 
     // ---- barriers ----
     const uint32_t bars = base + L.bar_off;
-    auto bar_full_w = [&](int s) { return bars + 8u * s; };               // [0,3)
-    auto bar_full_e = [&](int s) { return bars + 8u * (3 + s); };         // [3,6)
-    auto bar_empty  = [&](int s) { return bars + 8u * (6 + s); };         // [6,9)
-    const uint32_t bar_p_full = bars + 8u * 9, bar_p_smem = bars + 8u * 10;
-    auto bar_q_full  = [&](int t) { return bars + 8u * (11 + t); };       // [11,13)
-    auto bar_q_empty = [&](int t) { return bars + 8u * (13 + t); };       // [13,15)
-    auto bar_acc_full  = [&](int b) { return bars + 8u * (15 + b); };     // [15,17)
-    auto bar_acc_empty = [&](int b) { return bars + 8u * (17 + b); };     // [17,19)
-    const uint32_t tmem_slot = bars + 8u * 20;
+    auto bar_raw_full  = [&](int r) { return bars + 8u * r; };                 // [0,5)   TMA -> transform warps
+    auto bar_raw_empty = [&](int r) { return bars + 8u * (5 + r); };           // [5,10)
+    auto bar_full_w = [&](int s) { return bars + 8u * (10 + s); };             // [10,12) transform warps -> MMA
+    auto bar_full_e = [&](int s) { return bars + 8u * (12 + s); };             // [12,14) TMA (E tiles) -> MMA
+    auto bar_empty  = [&](int s) { return bars + 8u * (14 + s); };             // [14,16) MMA -> transform warps, E TMA
+    const uint32_t bar_p_full = bars + 8u * 16, bar_p_smem = bars + 8u * 17;
+    auto bar_q_full  = [&](int t) { return bars + 8u * (18 + t); };
+    auto bar_q_empty = [&](int t) { return bars + 8u * (20 + t); };
+    auto bar_acc_full  = [&](int b) { return bars + 8u * (22 + b); };
+    auto bar_acc_empty = [&](int b) { return bars + 8u * (24 + b); };
+    const uint32_t tmem_slot = bars + 8u * 27;
 
     const int tile = blockIdx.x;
-    const LayerRef Lr = layers[tc_find_layer(layers, n_layers, tile)];
+    const int layer = tc_find_layer(layers, n_layers, tile);
+    const LayerRef Lr = layers[layer];
     const int lt = tile - Lr.tile_begin;
     const int rows_valid = min(TC_TILE_M, Lr.d - lt * TC_TILE_M);
     const float* __restrict__ w_old = Lr.w_old + (size_t)lt * TC_TILE_M * K;
@@ -211,16 +229,18 @@ apply_tc_kernel(const LayerRef* __restrict__ layers, int n_layers, int K, int R,
     const int n_rc = R / 32;              // r atoms
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < 3; ++s) { mbar_init(bar_full_w(s), TC_PRODUCER_WARPS); mbar_init(bar_full_e(s), 1); mbar_init(bar_empty(s), 1); }
+        for (int r = 0; r < TC_NRAW; ++r) { mbar_init(bar_raw_full(r), 1); mbar_init(bar_raw_empty(r), TC_PRODUCER_WARPS); }
+        for (int s = 0; s < TC_SA; ++s) { mbar_init(bar_full_w(s), TC_PRODUCER_WARPS); mbar_init(bar_full_e(s), 1); mbar_init(bar_empty(s), 1); }
         mbar_init(bar_p_full, 1); mbar_init(bar_p_smem, TC_PRODUCER_WARPS);
         for (int t = 0; t < 2; ++t) { mbar_init(bar_q_full(t), 1); mbar_init(bar_q_empty(t), 1); mbar_init(bar_acc_full(t), 1); mbar_init(bar_acc_empty(t), TC_PRODUCER_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == TC_PRODUCER_WARPS + 1) {   // MMA warp owns the TMEM allocation (all 512 columns: one CTA per SM)
+    if (warp == WARP_MMA) {   // MMA warp owns the TMEM allocation (all 512 columns: one CTA per SM)
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    if (warp == TC_PRODUCER_WARPS && lane == 0) {
+    if (warp == WARP_E_TMA && lane == 0) {
+        tma_prefetch_desc(&wmaps.w[layer]);
         tma_prefetch_desc(&maps.e_hi); tma_prefetch_desc(&maps.e_lo); tma_prefetch_desc(&maps.qt_hi); tma_prefetch_desc(&maps.qt_lo);
     }
     tc_fence_before();
@@ -229,56 +249,44 @@ apply_tc_kernel(const LayerRef* __restrict__ layers, int n_layers, int K, int R,
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
-    const int SA = L.stages_a;
-    auto stage_w_hi = [&](int s) { return base + (uint32_t)(s * L.stage_a_bytes); };
-    auto stage_w_lo = [&](int s) { return base + (uint32_t)(s * L.stage_a_bytes + 16384); };
-    auto stage_e_hi = [&](int s) { return base + (uint32_t)(s * L.stage_a_bytes + 32768); };
-    auto stage_e_lo = [&](int s) { return base + (uint32_t)(s * L.stage_a_bytes + 32768 + R * 128); };
-    auto p_hi_atom = [&](int rc) { return base + (uint32_t)(rc * 16384); };
-    auto p_lo_atom = [&](int rc) { return base + (uint32_t)(TC_TILE_M * R * 4 + rc * 16384); };
-    auto qt_hi_st = [&](int t) { return base + (uint32_t)(L.qt_off + t * 32768); };
-    auto qt_lo_st = [&](int t) { return base + (uint32_t)(L.qt_off + t * 32768 + 16384); };
+    auto raw_st = [&](int r) { return base + (uint32_t)(r * 16384); };
+    auto stage_w_hi = [&](int s) { return base + (uint32_t)(L.a_off + s * L.stage_a_bytes); };
+    auto stage_w_lo = [&](int s) { return base + (uint32_t)(L.a_off + s * L.stage_a_bytes + 16384); };
+    auto stage_e_hi = [&](int s) { return base + (uint32_t)(L.a_off + s * L.stage_a_bytes + 32768); };
+    auto stage_e_lo = [&](int s) { return base + (uint32_t)(L.a_off + s * L.stage_a_bytes + 32768 + R * 128); };
+    auto p_hi_atom = [&](int rc) { return base + (uint32_t)(L.a_off + rc * 16384); };
+    auto p_lo_atom = [&](int rc) { return base + (uint32_t)(L.a_off + TC_TILE_M * R * 4 + rc * 16384); };
+    auto qt_hi_st = [&](int t) { return base + (uint32_t)(t * 32768); };
+    auto qt_lo_st = [&](int t) { return base + (uint32_t)(t * 32768 + 16384); };
 
     if (warp < TC_PRODUCER_WARPS) {
         // =============================== W producers, then P converters, then epilogue ===============================
         const int t = threadIdx.x;                 // 0..255
         const int c16 = t & 7;                     // 16-byte chunk within the 128-byte row segment
         const int r0 = t >> 3;                     // rows r0 + 32 p, p = 0..3
-        float4 buf[TC_PF][4];
-        const uint64_t pol_keep = l2_policy_evict_last(), pol_stream = l2_policy_evict_first();
-        auto load_chunk = [&](int c, float4 (&dst)[4]) {
+        const uint64_t pol_stream = l2_policy_evict_first();
+        for (int c = 0; c < n_chunks; ++c) {
+            const int r = c % TC_NRAW, s = c % TC_SA;
+            mbar_wait(bar_raw_full(r), (uint32_t)((c / TC_NRAW) & 1));
+            mbar_wait(bar_empty(s), (uint32_t)(((c / TC_SA) & 1) ^ 1));
+            const uint32_t raw = raw_st(r), hi_base = stage_w_hi(s), lo_base = stage_w_lo(s);
+            float4 v[4];
 #pragma unroll
             for (int p = 0; p < 4; ++p) {
                 const int row = r0 + 32 * p;
-                if (row < rows_valid) dst[p] = ldg_nc_v4(w_old + (size_t)row * K + c * 32 + c16 * 4, pol_keep);
-                else dst[p] = make_float4(0.f, 0.f, 0.f, 0.f);
+                v[p] = lds_v4(raw + (uint32_t)(row * 128 + ((c16 ^ (row & 7)) << 4)));     // same swizzled slot the TMA wrote
             }
-        };
 #pragma unroll
-        for (int i = 0; i < TC_PF - 1; ++i) if (i < n_chunks) load_chunk(i, buf[i]);
-        for (int c0 = 0; c0 < n_chunks; c0 += TC_PF) {
-#pragma unroll
-            for (int u = 0; u < TC_PF; ++u) {
-                const int c = c0 + u;
-                if (c >= n_chunks) break;
-                if (c + TC_PF - 1 < n_chunks) load_chunk(c + TC_PF - 1, buf[(u + TC_PF - 1) % TC_PF]);
-                const int s = c % SA;
-                const uint32_t ph = (uint32_t)((c / SA) & 1);
-                mbar_wait(bar_empty(s), ph ^ 1u);
-                const uint32_t hi_base = stage_w_hi(s), lo_base = stage_w_lo(s);
-#pragma unroll
-                for (int p = 0; p < 4; ++p) {
-                    const int row = r0 + 32 * p;
-                    const uint32_t off = (uint32_t)(row * 128 + ((c16 ^ (row & 7)) << 4));
-                    const float4 v = buf[u][p];
-                    const float hx = tf32_hi(v.x), hy = tf32_hi(v.y), hz = tf32_hi(v.z), hw = tf32_hi(v.w);
-                    sts_v4(hi_base + off, hx, hy, hz, hw);
-                    sts_v4(lo_base + off, v.x - hx, v.y - hy, v.z - hz, v.w - hw);
-                }
-                fence_proxy_async();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bar_full_w(s));
+            for (int p = 0; p < 4; ++p) {
+                const int row = r0 + 32 * p;
+                const uint32_t off = (uint32_t)(row * 128 + ((c16 ^ (row & 7)) << 4));
+                const float hx = tf32_hi(v[p].x), hy = tf32_hi(v[p].y), hz = tf32_hi(v[p].z), hw = tf32_hi(v[p].w);
+                sts_v4(hi_base + off, hx, hy, hz, hw);
+                sts_v4(lo_base + off, v[p].x - hx, v[p].y - hy, v[p].z - hz, v[p].w - hw);
             }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) { mbar_arrive(bar_full_w(s)); mbar_arrive(bar_raw_empty(r)); }
         }
         // ---- P: TMEM -> registers -> hi/lo -> swizzled smem (B operand of phase B) ----
         const int q = warp & 3, half = warp >> 2;
@@ -338,17 +346,33 @@ apply_tc_kernel(const LayerRef* __restrict__ layers, int n_layers, int K, int R,
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_acc_empty(b));
         }
-    } else if (warp == TC_PRODUCER_WARPS) {
-        // =============================== TMA warp: E tiles (phase A), Qt tiles (phase B) ===============================
+    } else if (warp == WARP_W_TMA) {
+        // =============================== TMA warp 1: raw W chunks, TC_NRAW deep ===============================
+        if (lane == 0) {
+            const uint64_t pol_keep = l2_policy_evict_last();     // the tile is read again by the epilogue: keep it in L2
+            const CUtensorMap* wm = &wmaps.w[layer];
+            for (int c = 0; c < n_chunks; ++c) {
+                const int r = c % TC_NRAW;
+                mbar_wait(bar_raw_empty(r), (uint32_t)(((c / TC_NRAW) & 1) ^ 1));
+                mbar_arrive_expect_tx(bar_raw_full(r), 16384u);
+                tma_load_2d_hint(raw_st(r), wm, bar_raw_full(r), c * 32, lt * TC_TILE_M, pol_keep);
+            }
+        }
+    } else if (warp == WARP_E_TMA) {
+        // =============================== TMA warp 2: E tiles (phase A), Qt tiles (phase B) ===============================
         if (lane == 0) {
             const uint32_t e_bytes = 2u * (uint32_t)R * 128u;
             for (int c = 0; c < n_chunks; ++c) {
-                const int s = c % SA;
-                const uint32_t ph = (uint32_t)((c / SA) & 1);
-                mbar_wait(bar_empty(s), ph ^ 1u);
+                const int s = c % TC_SA;
+                mbar_wait(bar_empty(s), (uint32_t)(((c / TC_SA) & 1) ^ 1));
                 mbar_arrive_expect_tx(bar_full_e(s), e_bytes);
                 tma_load_2d(stage_e_hi(s), &maps.e_hi, bar_full_e(s), c * 32, 0);
                 tma_load_2d(stage_e_lo(s), &maps.e_lo, bar_full_e(s), c * 32, 0);
+            }
+            // the Qt stages alias the raw ring: wait until the transform warps have drained every raw stage
+            for (int r = 0; r < TC_NRAW; ++r) {
+                const int uses = (n_chunks - r + TC_NRAW - 1) / TC_NRAW;      // completed phases of raw_empty[r]
+                if (uses > 0) mbar_wait(bar_raw_empty(r), (uint32_t)((uses - 1) & 1));
             }
             int it = 0;
             for (int kc = 0; kc < n_kc; ++kc)
@@ -366,8 +390,8 @@ apply_tc_kernel(const LayerRef* __restrict__ layers, int n_layers, int K, int R,
         if (lane == 0) {
             const uint32_t idesc_a = umma_idesc_tf32(128, R);
             for (int c = 0; c < n_chunks; ++c) {
-                const int s = c % SA;
-                const uint32_t ph = (uint32_t)((c / SA) & 1);
+                const int s = c % TC_SA;
+                const uint32_t ph = (uint32_t)((c / TC_SA) & 1);
                 mbar_wait(bar_full_w(s), ph);
                 mbar_wait(bar_full_e(s), ph);
                 tc_fence_after();
@@ -416,7 +440,7 @@ apply_tc_kernel(const LayerRef* __restrict__ layers, int n_layers, int K, int R,
     // ---- teardown ----
     tc_fence_before();
     __syncthreads();
-    if (warp == TC_PRODUCER_WARPS + 1) {
+    if (warp == WARP_MMA) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
     }
@@ -475,14 +499,18 @@ int apply_tc_lowrank(uce_ws* ws, const LayerRef* layers_dev, const LayerRef* lay
                      cudaStream_t st, int* launches) {
     const int K = ws->K, R = ws->rank_pad;
     if (!apply_tc_available(ws)) { set_error("tcgen05 apply unavailable for K=%d rank_pad=%d dense=%d", K, R, ws->dense); return UCE_E_STATE; }
+    if (n_layers > TC_MAX_LAYERS) { set_error("tcgen05 apply takes at most %d projections per call", TC_MAX_LAYERS); return UCE_E_STATE; }
     for (int l = 0; l < n_layers; ++l)
         if (((uintptr_t)layers_host[l].w_old & 15) || ((uintptr_t)layers_host[l].w_new & 15)) { set_error("tcgen05 apply needs 16-byte aligned weights"); return UCE_E_ARG; }
     TcMaps maps;
+    static TcWMaps wmaps;      // 20 KB: kept off the stack; copied into the launch by value
     int rc;
     if ((rc = make_map(&maps.e_hi, ws->E_hi, R, K, R))) return rc;
     if ((rc = make_map(&maps.e_lo, ws->E_lo, R, K, R))) return rc;
     if ((rc = make_map(&maps.qt_hi, ws->Qt_hi, K, R, 128))) return rc;
     if ((rc = make_map(&maps.qt_lo, ws->Qt_lo, K, R, 128))) return rc;
+    for (int l = 0; l < n_layers; ++l)
+        if ((rc = make_map(&wmaps.w[l], layers_host[l].w_old, layers_host[l].d, K, TC_TILE_M))) return rc;
     const TcSmem L = tc_smem_layout(R);
     const int smem = L.total + 1024;   // slack for the manual 1024-byte alignment
     static int configured = 0;
@@ -490,7 +518,7 @@ int apply_tc_lowrank(uce_ws* ws, const LayerRef* layers_dev, const LayerRef* lay
         UCE_CUDA(cudaFuncSetAttribute(apply_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured = smem;
     }
-    apply_tc_kernel<<<total_tiles, TC_THREADS, smem, st>>>(layers_dev, n_layers, K, R, maps);
+    apply_tc_kernel<<<total_tiles, TC_THREADS, smem, st>>>(layers_dev, n_layers, K, R, maps, wmaps);
     UCE_LAUNCH_CHECK();
     *launches += 1;
     return 0;

@@ -114,9 +114,17 @@ chol_small_kernel(double* __restrict__ Hg, int n, int n_pad, const double* __res
         if (warp == 0) {
             bool bad = false;
             for (int j = 0; j < FS_NB; ++j) {
-                double acc = D[lane * (FS_NB + 1) + j];
-#pragma unroll 8
-                for (int k = 0; k < j; ++k) acc = fma(-D[lane * (FS_NB + 1) + k], D[j * (FS_NB + 1) + k], acc);
+                // four independent partial sums: the fp64 FMA chain, not the loads, is the critical path here
+                double acc = D[lane * (FS_NB + 1) + j], a1 = 0.0, a2 = 0.0, a3 = 0.0;
+                const double* ri = D + lane * (FS_NB + 1);
+                const double* rj = D + j * (FS_NB + 1);
+                int k = 0;
+                for (; k + 4 <= j; k += 4) {
+                    acc = fma(-ri[k], rj[k], acc); a1 = fma(-ri[k + 1], rj[k + 1], a1);
+                    a2 = fma(-ri[k + 2], rj[k + 2], a2); a3 = fma(-ri[k + 3], rj[k + 3], a3);
+                }
+                for (; k < j; ++k) acc = fma(-ri[k], rj[k], acc);
+                acc += (a1 + a2) + a3;
                 double d = __shfl_sync(0xffffffffu, acc, j);
                 if (!(d > 0.0)) { bad = true; d = 1.0; }
                 const double y = fs_rsqrt(d);

@@ -253,6 +253,13 @@ def run_ours(args, rank, world, local_rank):
     if world > 1:
         sharded = bench_sharded(solver, prob, dev, rank, world, args)
 
+    denoise = None
+    if rank == 0 and not args.no_denoise:
+        try:
+            denoise = bench_denoise(dev, args)
+        except Exception as exc:      # the solver line is the contract; report the denoise failure instead of losing it
+            denoise = {"error": f"{type(exc).__name__}: {exc}"}
+            log(f"denoise bench failed: {denoise['error']}")
     if rank == 0:
         ms_per_step = total_ms / args.steps
         value = world * n / (ms_per_step / 1e3)
@@ -294,8 +301,71 @@ def run_ours(args, rank, world, local_rank):
             line["cpu_baseline"] = cpu
         if sharded:
             line["sharded"] = sharded
+        if denoise:
+            line["denoise"] = denoise
         print(json.dumps(line), flush=True)
     solver.close()
+
+
+def bench_denoise(dev, args):
+    """BASELINE metric part 2: denoise-steps/sec/GPU at 512x512 (64x64 latents), bs=1 with classifier-free guidance
+    (2 samples per U-Net call), SD-1.4 configuration, seeded synthetic weights; one CUDA-graph replay per step
+    (U-Net + guidance + scheduler update)."""
+    from uce_b200.generate import Denoiser
+    from uce_b200.synthetic import unet_random_state
+    from uce_b200.unet import UNetEngine, cfg_step
+    from uce_b200.unet_spec import SD14, param_count
+    log("denoise: building SD-1.4 U-Net (859.5 M synthetic parameters) ...")
+    state = unet_random_state(SD14, seed=0)
+    eng = UNetEngine(SD14, batch=2, H=64, W=64, device=dev)
+    eng.load_state_dict(state)
+    del state
+    eng.finalize()
+    log(f"denoise: engine ready, {eng.launch_count()} kernels per U-Net call")
+    den = Denoiser(eng, 1)
+    g = torch.Generator().manual_seed(2219)
+    den.x.copy_(torch.randn(1, 4, 64, 64, generator=g))
+    ctx = torch.randn(2, 77, 768, generator=g).to(dev)
+    c = (55 / 24, -59 / 24, 37 / 24, -9 / 24)
+
+    def step():
+        den.x2[:1].copy_(den.x); den.x2[1:].copy_(den.x)
+        eng.forward(den.x2, 481.0, ctx, out=den.eps2)
+        cfg_step(den.eps2, 7.5, den.x, den.x, c, 1.0, -0.001, hist=den.hist[:3], eps_out=den.scratch)
+
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize(dev)
+    graph = None
+    if not args.no_graph:
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=side):
+                step()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        for _ in range(3):
+            graph.replay()
+    torch.cuda.synchronize(dev)
+    K = max(5, min(args.steps, 50))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        graph.replay() if graph else step()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / K
+    bound_ms = 0.902            # SURVEY.md Appendix A: per-op max(tensor, HBM) lower bound of one NB=2 U-Net call at nominal peaks
+    out = {"metric": "denoise-steps/sec/GPU @512x512 (bs=1, CFG)", "value": 1e3 / ms, "unit": "steps/s", "ms_per_step": ms, "steps": K,
+           "config": {"model": "SD-1.4 U-Net shapes, synthetic weights", "params": param_count(SD14), "latents": "1x4x64x64", "unet_batch": 2,
+                      "dtype": "bf16 storage, fp32 accumulate", "launch": "one CUDA graph replay per step" if graph else "eager",
+                      "kernels_per_step": eng.launch_count() + 3},
+           "roofline": {"bound": "mixed (per-op max of tensor and HBM, summed)", "achieved_ms": ms, "bound_ms": bound_ms, "frac": bound_ms / ms,
+                        "algorithmic_flops": 1.608e12, "achieved_tflops": 1.608 / ms}}
+    log(f"denoise: {ms:.3f} ms/step = {1e3 / ms:.1f} steps/s")
+    eng.close()
+    return out
 
 
 def bench_sharded(solver, prob, dev, rank, world, args):
@@ -338,6 +408,7 @@ def main():
     ap.add_argument("--apply-impl", type=int, default=None, help="0 auto, 1 SIMT, 2 tcgen05")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-denoise", action="store_true", help="skip the U-Net denoise-step measurement")
     ap.add_argument("--cpu-budget", type=float, default=20.0)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

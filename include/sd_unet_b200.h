@@ -53,6 +53,10 @@ int sd_unet_finalize(sd_unet *u);
 /* eps[batch,4,H,W] (fp32, NCHW) = UNet(x[batch,4,H,W] fp32 NCHW, t, ctx[batch,context_len,cross_attention_dim] fp32). */
 int sd_unet_forward(sd_unet *u, const float *x, float t, const float *ctx, float *eps, void *stream);
 
+/* Update the timestep a CUDA graph captured around sd_unet_forward will read on its next replay (the captured
+ * forward copies t from a pinned host slot; this writes that slot). */
+int sd_unet_set_timestep(sd_unet *u, float t);
+
 /* Fused classifier-free guidance + scheduler update on fp32 NCHW latents of n = images*4*H*W elements:
  *   eps = eps_u + gs (eps_t - eps_u)  with eps2 = [uncond | text];  e = c[0] eps + c[1] h1 + c[2] h2 + c[3] h3;
  *   x_out = cx x_in + ce e.   eps_out (optional) receives the guided eps (PLMS history). h1..h3 may be NULL. */

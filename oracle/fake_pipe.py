@@ -211,3 +211,39 @@ class ScriptedClip:
             rest = [c for c in candidate_labels if c != lab]
             out.append([{"label": lab, "score": 0.9}] + [{"label": r, "score": 0.1 / max(1, len(rest))} for r in rest])
         return out
+
+
+class _StateDictHolder:
+    def __init__(self, state):
+        self._state = state
+
+    def state_dict(self):
+        return dict(self._state)
+
+
+class FakeGenPipe:
+    """Synthetic generation pipeline for the generate_images() drop-in: a tiny U-Net state dict (diffusers names),
+    seeded prompt embeddings, and a deterministic stand-in for VAE decode + image post-processing."""
+
+    def __init__(self, cfg, weights, latent_size=16, seed=0):
+        self.cfg = cfg
+        self.unet = _StateDictHolder(weights)
+        self.latent_size = latent_size
+        self.seed = seed
+
+    def _emb(self, text, n):
+        g = torch.Generator().manual_seed((zlib.crc32(text.encode()) + 7 * self.seed) % (2 ** 31))
+        return torch.randn(1, 77, self.cfg["cross_attention_dim"], generator=g).expand(n, -1, -1).contiguous()
+
+    def encode_prompt(self, prompt, device=None, num_images_per_prompt=1, do_classifier_free_guidance=True, **kw):
+        return self._emb(prompt, num_images_per_prompt), self._emb("", num_images_per_prompt)
+
+    @staticmethod
+    def latents_to_uint8(latents):
+        x = torch.sigmoid(latents.float().cpu()[:, :3])
+        x = torch.nn.functional.interpolate(x, scale_factor=4, mode="nearest")
+        return (x.permute(0, 2, 3, 1) * 255).round().to(torch.uint8).numpy()
+
+    def decode_latents_to_pil(self, latents):
+        from PIL import Image
+        return [Image.fromarray(a) for a in self.latents_to_uint8(latents)]

@@ -1,5 +1,7 @@
 """GPU parity of the U-Net denoise engine (C ABI include/sd_unet_b200.h) against the CPU torch restatement
 oracle/unet_oracle.py.  bf16 storage with fp32 accumulation: tolerance is relative to each tensor's RMS."""
+import os
+
 import pytest
 import torch
 
@@ -36,4 +38,99 @@ def test_tiny_unet_forward_matches_oracle(hw):
     assert report["temb"] < 2e-2 and report["conv_in"] < 1e-2, report
     assert report["eps"] < 5e-2, report
     assert torch.isfinite(out).all()
+    eng.close()
+
+
+def _tiny():
+    from uce_b200.unet_spec import tiny_config
+    cfg = tiny_config(ch=(64, 128), ctx_dim=64, heads=4, groups=8)
+    return cfg, U.random_weights(cfg, seed=5)
+
+
+@pytest.mark.parametrize("sched,steps", [("pndm", 6), ("ddim", 5)])
+def test_denoise_loop_matches_oracle(sched, steps):
+    """CFG + scheduler + U-Net over several steps (PLMS history, saved-sample special case) vs the fp32 CPU loop."""
+    from uce_b200.generate import Denoiser
+    from uce_b200.unet import UNetEngine
+    cfg, P = _tiny()
+    g = torch.Generator().manual_seed(1)
+    lat = torch.randn(2, 4, 16, 16, generator=g)
+    ctx = torch.randn(4, 77, cfg["cross_attention_dim"], generator=g)
+    ref = U.denoise_loop(P, lat, ctx, steps=steps, guidance_scale=7.5, scheduler=sched, cfg=cfg)
+    eng = UNetEngine(cfg, batch=4, H=16, W=16)
+    eng.load_state_dict(P)
+    eng.finalize()
+    out = Denoiser(eng, 2).run(lat, ctx, steps=steps, guidance_scale=7.5, scheduler=sched).cpu()
+    err = _rel(out, ref)
+    print(sched, "latents rel err after", steps, "steps:", err)
+    assert err < 6e-2, err
+    eng.close()
+
+
+def test_cfg_step_kernel_exact():
+    from uce_b200.unet import cfg_step
+    g = torch.Generator().manual_seed(2)
+    n = 2 * 4 * 16 * 16
+    eps2 = torch.randn(2 * n, generator=g).cuda()
+    x = torch.randn(n, generator=g).cuda()
+    h = [torch.randn(n, generator=g).cuda() for _ in range(3)]
+    out, eo = torch.empty_like(x), torch.empty_like(x)
+    c = (55 / 24, -59 / 24, 37 / 24, -9 / 24)
+    cfg_step(eps2, 7.5, x, out, c, 1.01, -0.02, hist=h, eps_out=eo)
+    eps = eps2[:n] + 7.5 * (eps2[n:] - eps2[:n])
+    ref = 1.01 * x + (-0.02) * (c[0] * eps + c[1] * h[0] + c[2] * h[1] + c[3] * h[2])
+    assert torch.allclose(eo, eps, rtol=1e-6, atol=1e-6) and torch.allclose(out, ref, rtol=1e-5, atol=1e-5)
+
+
+def test_generate_images_drop_in(tmp_path):
+    """generate_images(): CSV rows, seeds, case filter, file naming, strict=False weight overlay — against the oracle loop."""
+    import numpy as np
+    import pandas as pd
+    from PIL import Image
+    from safetensors.torch import save_file
+    from oracle.fake_pipe import FakeGenPipe
+    from uce_b200.generate import generate_images
+    cfg, P = _tiny()
+    pipe = FakeGenPipe(cfg, P, latent_size=16)
+    csv = tmp_path / "p.csv"
+    pd.DataFrame({"case_number": [0, 1, 2], "prompt": ["a cat", "Starry Night by Van Gogh", "a dog"], "evaluation_seed": [11, 2219, 5]}).to_csv(csv)
+    # an "edited" attn2 weight overlay, as written by the edit solver
+    key = "down_blocks.0.attentions.0.transformer_blocks.0.attn2.to_k.weight"
+    edited = {key: P[key] * 0.5}
+    save_file(edited, str(tmp_path / "uce.safetensors"))
+    generate_images("unused", str(tmp_path / "uce.safetensors"), str(csv), str(tmp_path), exp_name="out", device="cuda:0",
+                    torch_dtype=torch.bfloat16, guidance_scale=7.5, num_inference_steps=4, num_images_per_prompt=2,
+                    from_case=1, till_case=2, pipe=pipe, unet_config=cfg)
+    files = sorted(os.listdir(tmp_path / "out"))
+    assert files == ["1_0.png", "1_1.png", "2_0.png", "2_1.png"]
+    P2 = dict(P); P2.update(edited)
+    for case, prompt, seed in [(1, "Starry Night by Van Gogh", 2219), (2, "a dog", 5)]:
+        text, uncond = pipe.encode_prompt(prompt, num_images_per_prompt=2)
+        lat = torch.randn((2, 4, 16, 16), generator=torch.Generator().manual_seed(seed), dtype=torch.bfloat16).float()
+        ref = FakeGenPipe.latents_to_uint8(U.denoise_loop(P2, lat, torch.cat([uncond, text]), steps=4, cfg=cfg))
+        for i in range(2):
+            got = np.asarray(Image.open(tmp_path / "out" / f"{case}_{i}.png")).astype(np.int32)
+            assert got.shape == ref[i].shape
+            assert np.abs(got - ref[i].astype(np.int32)).mean() < 3.0, (case, i, np.abs(got - ref[i]).mean())
+
+
+def test_sd14_shapes_forward_matches_oracle():
+    """The real SD-1.4 U-Net configuration (859.5 M parameters, 8 heads of 40/80/160, 77x768 context) at 32x32 latents."""
+    from uce_b200.unet import UNetEngine
+    from uce_b200.unet_spec import SD14
+    P = U.random_weights(SD14, seed=0)
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(2, 4, 32, 32, generator=g)
+    ctx = torch.randn(2, 77, 768, generator=g)
+    taps = {}
+    torch.set_num_threads(8)
+    ref = U.unet_forward(P, x, 801.0, ctx, SD14, taps=taps)
+    eng = UNetEngine(SD14, batch=2, H=32, W=32)
+    eng.load_state_dict(P)
+    eng.finalize()
+    out = eng.forward(x.cuda(), 801.0, ctx.cuda()).cpu()
+    rep = {k: _rel(eng.read_tap(k), taps[k]) for k in ["conv_in", "down.0.1", "down.2.1", "mid", "up.1.2", "up.3.2"]}
+    rep["eps"] = _rel(out, ref)
+    print("SD-1.4 per-tap relative error:", {k: round(v, 4) for k, v in rep.items()})
+    assert rep["eps"] < 5e-2 and torch.isfinite(out).all(), rep
     eng.close()

@@ -495,6 +495,12 @@ int sd_unet_forward(sd_unet* u, const float* x, float t, const float* ctx, float
     return 0;
 }
 
+int sd_unet_set_timestep(sd_unet* u, float t) {
+    if (!u || !u->h_t) { sd_err("sd_unet_set_timestep: engine not finalized"); return SD_E_STATE; }
+    *u->h_t = t;
+    return 0;
+}
+
 int sd_cfg_step(const float* eps2, long n, float gs, float* eps_out, const float* h1, const float* h2, const float* h3, const float c[4],
                 float cx, float ce, const float* x_in, float* x_out, void* stream) {
     if (!eps2 || !c || !x_in || !x_out || n <= 0) { sd_err("sd_cfg_step: bad argument"); return SD_E_ARG; }

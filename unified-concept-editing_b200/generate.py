@@ -1,0 +1,119 @@
+"""Edited-model image generation: drop-in for ``generate_images()`` of the reference's
+evalscripts/generate-images-sd.py:10-46 with the denoise loop (U-Net, classifier-free guidance, scheduler) on the
+B200 engine.  Text encoding and VAE decoding stay with the caller's pipeline object, exactly the pieces the
+reference also takes from diffusers (SURVEY.md §8f lists them as the next rows).
+
+Row sharding: rank r of a torch.distributed job takes CSV rows r::world — rows are independent,
+so the steady state has no collective."""
+from __future__ import annotations
+
+import os
+
+import torch
+
+from .schedulers import make_plan
+from .unet import UNetEngine, cfg_step
+from .unet_spec import SD14
+
+
+class Denoiser:
+    """The hot loop of StableDiffusionPipeline.__call__ for ``images`` samples of ONE prompt on given initial latents."""
+
+    def __init__(self, engine: UNetEngine, images: int):
+        assert engine.batch == 2 * images
+        self.eng, self.B = engine, images
+        dev = engine.device
+        shp = (images, 4, engine.H, engine.W)
+        self.x = torch.empty(shp, device=dev)
+        self.x2 = torch.empty((2 * images, 4, engine.H, engine.W), device=dev)
+        self.eps2 = torch.empty_like(self.x2)
+        self.saved = torch.empty(shp, device=dev)
+        self.hist = [torch.zeros(shp, device=dev) for _ in range(4)]
+        self.scratch = torch.zeros(shp, device=dev)
+
+    def run(self, latents: torch.Tensor, ctx_uncond_text: torch.Tensor, steps=50, guidance_scale=7.5, scheduler="pndm"):
+        """latents [B,4,H,W] (any float dtype, device or host), ctx [2B,77,D] ordered [uncond | text] -> final latents fp32."""
+        self.x.copy_(latents.to(self.x.device, torch.float32))
+        ctx = ctx_uncond_text.to(self.x.device, torch.float32).contiguous()
+        hist = []                                   # most recent first
+        free = list(self.hist)
+        for plan in make_plan(scheduler, steps):
+            self.x2[: self.B].copy_(self.x); self.x2[self.B:].copy_(self.x)
+            self.eng.forward(self.x2, float(plan.t), ctx, out=self.eps2)
+            if plan.save_sample:
+                self.saved.copy_(self.x)
+            x_in = self.saved if plan.use_saved_sample else self.x
+            if plan.append_eps:
+                buf = free.pop() if free else hist.pop()
+                eps_out = buf
+            else:
+                buf, eps_out = None, self.scratch
+            cfg_step(self.eps2, guidance_scale, x_in, self.x, plan.coeffs, plan.cx, plan.ce, hist=hist[:3], eps_out=eps_out)
+            if buf is not None:
+                hist.insert(0, buf)
+                if len(hist) > 3:
+                    free.append(hist.pop())
+        return self.x
+
+
+def _rank_world():
+    if torch.distributed.is_available() and torch.distributed.is_initialized():
+        return torch.distributed.get_rank(), torch.distributed.get_world_size()
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+
+
+def generate_images(model_id, uce_model_path, prompts_path, save_path, exp_name="test", device="cuda:0", torch_dtype=torch.bfloat16,
+                    guidance_scale=7.5, num_inference_steps=100, num_images_per_prompt=10, from_case=0, till_case=1000000,
+                    pipe=None, scheduler="pndm", unet_config=SD14):
+    """Same signature and outputs as the reference (``{save_path}/{exp_name}/{case_number}_{i}.png``); ``pipe`` lets a
+    caller inject an already-loaded (or synthetic) pipeline object."""
+    import pandas as pd
+    if pipe is None:
+        try:
+            from diffusers import DiffusionPipeline
+        except ImportError as exc:
+            raise SystemExit(f"diffusers is required to load '{model_id}' (text encoder, VAE, weights): {exc}")
+        pipe = DiffusionPipeline.from_pretrained(model_id, torch_dtype=torch_dtype, safety_checker=None).to(device)
+    state = {k: v for k, v in pipe.unet.state_dict().items()}
+    if uce_model_path is not None:
+        from safetensors.torch import load_file
+        state.update(load_file(uce_model_path))          # load_state_dict(strict=False) semantics (generate-images-sd.py:17-19)
+    latent = getattr(pipe, "latent_size", 64)
+    eng = UNetEngine(unet_config, batch=2 * num_images_per_prompt, H=latent, W=latent, device=device)
+    eng.load_state_dict(state, strict=False)
+    eng.finalize()
+    den = Denoiser(eng, num_images_per_prompt)
+
+    df = pd.read_csv(prompts_path)
+    folder = f"{save_path}/{exp_name}"
+    os.makedirs(folder, exist_ok=True)
+    rank, world = _rank_world()
+    idx = 0
+    for _, row in df.iterrows():
+        case_number = row.case_number
+        if not (case_number >= from_case and case_number <= till_case):
+            continue
+        mine = (idx % world) == rank
+        idx += 1
+        if not mine:
+            continue
+        prompt, seed = str(row.prompt), row.evaluation_seed
+        text, uncond = pipe.encode_prompt(prompt=prompt, device=device, num_images_per_prompt=num_images_per_prompt,
+                                          do_classifier_free_guidance=True)[:2]
+        ctx = torch.cat([uncond, text]).to(torch.float32)
+        gen = torch.Generator().manual_seed(int(seed))
+        lat = torch.randn((num_images_per_prompt, 4, latent, latent), generator=gen, dtype=torch_dtype)   # CPU generator, pipe dtype
+        out = den.run(lat, ctx, steps=num_inference_steps, guidance_scale=guidance_scale, scheduler=scheduler)
+        images = pipe.decode_latents_to_pil(out) if hasattr(pipe, "decode_latents_to_pil") else _decode(pipe, out, torch_dtype)
+        for num, im in enumerate(images):
+            im.save(f"{folder}/{case_number}_{num}.png")
+    eng.close()
+
+
+def _decode(pipe, latents, dtype):
+    """vae.decode(latents / 0.18215) -> (x/2+0.5).clamp(0,1) -> uint8 NHWC -> PIL."""
+    from PIL import Image
+    sf = getattr(pipe.vae.config, "scaling_factor", 0.18215)
+    img = pipe.vae.decode((latents / sf).to(dtype)).sample
+    img = (img.float() / 2 + 0.5).clamp(0, 1).permute(0, 2, 3, 1).cpu().numpy()
+    return [Image.fromarray((x * 255).round().astype("uint8")) for x in img]

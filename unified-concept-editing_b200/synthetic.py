@@ -44,3 +44,24 @@ def problem(name: str, seed: int = 0, correlated: bool = True, pin_memory: bool 
     G = rows[ne + npz:].expand(ne, K).contiguous()          # one shared guide row ("art")
     return dict(name=name, K=K, C=C, G=G, scales=[1.0] * (ne + npz), n_edit=ne, lamb=0.5,
                 W=weights(w["dims"], K, seed, pin_memory=pin_memory), dims=list(w["dims"]))
+
+
+def unet_random_state(cfg, seed: int = 0):
+    """Seeded synthetic U-Net parameters (diffusers names) with fan-in scaling so activations stay O(1)
+    (norm gains ~1, small biases) — there is no network access for real checkpoints."""
+    import math
+    from .unet_spec import param_shapes
+    g = torch.Generator().manual_seed(seed)
+    state = {}
+    for name, shp in param_shapes(cfg).items():
+        if name.endswith(".weight") and len(shp) == 1:
+            w = 1.0 + 0.1 * torch.randn(shp, generator=g)
+        elif name.endswith(".bias"):
+            w = 0.02 * torch.randn(shp, generator=g)
+        else:
+            fan_in = 1
+            for d in shp[1:]:
+                fan_in *= d
+            w = torch.randn(shp, generator=g) / math.sqrt(fan_in)
+        state[name] = w
+    return state

@@ -25,6 +25,7 @@ SD_SIGNATURES = {
     "sd_unet_set_weight": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.POINTER(C.c_long), C.c_int]),
     "sd_unet_finalize": (C.c_int, [C.c_void_p]),
     "sd_unet_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "sd_unet_set_timestep": (C.c_int, [C.c_void_p, C.c_float]),
     "sd_cfg_step": (C.c_int, [C.c_void_p, C.c_long, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_float),
                               C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
     "sd_unet_launch_count": (C.c_int, [C.c_void_p]),
@@ -116,6 +117,10 @@ class UNetEngine:
         with torch.cuda.device(self.device):
             _check(_lib().sd_unet_forward(self._h, C.c_void_p(x.data_ptr()), float(t), C.c_void_p(ctx.data_ptr()), C.c_void_p(out.data_ptr()), self._stream()))
         return out
+
+    def set_timestep(self, t: float):
+        """Timestep read by the next replay of a CUDA graph captured around forward()."""
+        _check(_lib().sd_unet_set_timestep(self._h, float(t)))
 
     def launch_count(self) -> int:
         return _lib().sd_unet_launch_count(self._h)

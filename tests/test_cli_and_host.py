@@ -95,6 +95,16 @@ def test_c_abi_exports_every_declared_symbol():
     assert _native.lib().uce_abi_version() == 1
 
 
+def test_sd_unet_c_abi_exports_every_declared_symbol():
+    from uce_b200 import _native, unet
+    hdr = open(os.path.join(ROOT, "include", "sd_unet_b200.h")).read()
+    declared = set(re.findall(r"\b(sd_[a-z0-9_]+)\s*\(", hdr))
+    lib = ctypes.CDLL(_native.LIB_PATH)
+    for sym in declared:
+        assert hasattr(lib, sym), sym
+    assert declared == set(unet.SD_SIGNATURES), declared ^ set(unet.SD_SIGNATURES)
+
+
 def test_no_gpu_fails_loudly():
     from uce_b200.solver import EditSolver
     if torch.cuda.is_available():
@@ -103,3 +113,6 @@ def test_no_gpu_fails_loudly():
         EditSolver(768, 16, "cuda:0")
     with pytest.raises(RuntimeError):
         EditSolver(768, 16, "cpu")
+    from uce_b200.unet import UNetEngine
+    with pytest.raises(RuntimeError):
+        UNetEngine(device="cuda:0")

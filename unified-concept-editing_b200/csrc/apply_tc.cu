@@ -30,7 +30,6 @@ namespace uce {
 constexpr int TC_TILE_M = 128;
 constexpr int TC_PRODUCER_WARPS = 8;
 constexpr int TC_THREADS = (TC_PRODUCER_WARPS + 3) * 32;   // + W TMA warp + E/Qt TMA warp + MMA warp
-constexpr int TC_QT_STAGES = 2;
 constexpr int TC_NRAW = 5;                                  // raw W chunks in flight per SM (5 x 16 KB by TMA)
 constexpr int TC_SA = 2;                                    // hi/lo MMA stages
 constexpr int TC_MAX_LAYERS = 160;                          // per-launch tensor maps for W_old (one per projection)
@@ -173,23 +172,26 @@ __device__ __forceinline__ int tc_find_layer(const LayerRef* layers, int n_layer
 }
 
 // Shared-memory carve-up (bytes), identical on host and device.
-//   [0, raw)            raw ring: TC_NRAW x 16 KB fp32 W chunks written by TMA; phase B: the two Qt stages alias it
-//   [raw, raw + a)      TC_SA x {W_hi 16K, W_lo 16K, E_hi R*128, E_lo R*128}; phase B: P_hi | P_lo alias it
+//   [0, 80K)                 raw ring: TC_NRAW x 16 KB fp32 W chunks written by TMA
+//   [80K, 80K + ne*e_stage)  E ring: ne x {E_hi R*128, E_lo R*128}   (deep enough to hide the L2 latency of the E tiles)
+//   [.., + 64K)              TC_SA x {W_hi 16K, W_lo 16K}
+//   phase B: P_hi | P_lo occupy the LAST 2*128*R*4 bytes of that span, the Qt ring (nq x 32 KB) its beginning.
 struct TcSmem {
-    int stage_a_bytes;
-    int a_off;
-    int region_a;
-    int bar_off;
-    int total;
+    int ne, nq;
+    int e_stage_bytes, e_off, w_off, p_off;
+    int bar_off, total;
 };
 __host__ __device__ inline TcSmem tc_smem_layout(int R) {
     TcSmem s;
-    s.stage_a_bytes = 32768 + 2 * R * 128;
-    s.a_off = TC_NRAW * 16384;
-    int a = TC_SA * s.stage_a_bytes;
-    int p = 2 * TC_TILE_M * R * 4;
-    s.region_a = a > p ? a : p;
-    s.bar_off = s.a_off + s.region_a;
+    s.ne = (R <= 64) ? 4 : (R <= 96 ? 3 : 2);
+    s.e_stage_bytes = 2 * R * 128;
+    s.e_off = TC_NRAW * 16384;
+    s.w_off = s.e_off + s.ne * s.e_stage_bytes;
+    const int end = s.w_off + TC_SA * 32768;
+    s.p_off = end - 2 * TC_TILE_M * R * 4;
+    int nq = s.p_off / 32768;
+    s.nq = nq > 4 ? 4 : nq;
+    s.bar_off = end;
     s.total = s.bar_off + 512;
     return s;
 }
@@ -205,17 +207,18 @@ apply_tc_kernel(const LayerRef* __restrict__ layers, int n_layers, int K, int R,
 
     // ---- barriers ----
     const uint32_t bars = base + L.bar_off;
-    auto bar_raw_full  = [&](int r) { return bars + 8u * r; };                 // [0,5)   TMA -> transform warps
+    auto bar_raw_full  = [&](int r) { return bars + 8u * r; };                 // [0,5)   W TMA -> transform warps
     auto bar_raw_empty = [&](int r) { return bars + 8u * (5 + r); };           // [5,10)
     auto bar_full_w = [&](int s) { return bars + 8u * (10 + s); };             // [10,12) transform warps -> MMA
-    auto bar_full_e = [&](int s) { return bars + 8u * (12 + s); };             // [12,14) TMA (E tiles) -> MMA
-    auto bar_empty  = [&](int s) { return bars + 8u * (14 + s); };             // [14,16) MMA -> transform warps, E TMA
-    const uint32_t bar_p_full = bars + 8u * 16, bar_p_smem = bars + 8u * 17;
-    auto bar_q_full  = [&](int t) { return bars + 8u * (18 + t); };
-    auto bar_q_empty = [&](int t) { return bars + 8u * (20 + t); };
-    auto bar_acc_full  = [&](int b) { return bars + 8u * (22 + b); };
-    auto bar_acc_empty = [&](int b) { return bars + 8u * (24 + b); };
-    const uint32_t tmem_slot = bars + 8u * 27;
+    auto bar_empty  = [&](int s) { return bars + 8u * (12 + s); };             // [12,14) MMA -> transform warps
+    auto bar_full_e  = [&](int s) { return bars + 8u * (14 + s); };            // [14,18) E TMA -> MMA
+    auto bar_empty_e = [&](int s) { return bars + 8u * (18 + s); };            // [18,22) MMA -> E TMA
+    const uint32_t bar_p_full = bars + 8u * 22, bar_p_smem = bars + 8u * 23;
+    auto bar_q_full  = [&](int t) { return bars + 8u * (24 + t); };            // [24,28)
+    auto bar_q_empty = [&](int t) { return bars + 8u * (28 + t); };            // [28,32)
+    auto bar_acc_full  = [&](int b) { return bars + 8u * (32 + b); };
+    auto bar_acc_empty = [&](int b) { return bars + 8u * (34 + b); };
+    const uint32_t tmem_slot = bars + 8u * 37;
 
     const int tile = blockIdx.x;
     const int layer = tc_find_layer(layers, n_layers, tile);
@@ -230,9 +233,10 @@ apply_tc_kernel(const LayerRef* __restrict__ layers, int n_layers, int K, int R,
 
     if (threadIdx.x == 0) {
         for (int r = 0; r < TC_NRAW; ++r) { mbar_init(bar_raw_full(r), 1); mbar_init(bar_raw_empty(r), TC_PRODUCER_WARPS); }
-        for (int s = 0; s < TC_SA; ++s) { mbar_init(bar_full_w(s), TC_PRODUCER_WARPS); mbar_init(bar_full_e(s), 1); mbar_init(bar_empty(s), 1); }
+        for (int s = 0; s < TC_SA; ++s) { mbar_init(bar_full_w(s), TC_PRODUCER_WARPS); mbar_init(bar_empty(s), 1); }
+        for (int s = 0; s < 4; ++s) { mbar_init(bar_full_e(s), 1); mbar_init(bar_empty_e(s), 1); mbar_init(bar_q_full(s), 1); mbar_init(bar_q_empty(s), 1); }
         mbar_init(bar_p_full, 1); mbar_init(bar_p_smem, TC_PRODUCER_WARPS);
-        for (int t = 0; t < 2; ++t) { mbar_init(bar_q_full(t), 1); mbar_init(bar_q_empty(t), 1); mbar_init(bar_acc_full(t), 1); mbar_init(bar_acc_empty(t), TC_PRODUCER_WARPS); }
+        for (int t = 0; t < 2; ++t) { mbar_init(bar_acc_full(t), 1); mbar_init(bar_acc_empty(t), TC_PRODUCER_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == WARP_MMA) {   // MMA warp owns the TMEM allocation (all 512 columns: one CTA per SM)
@@ -249,13 +253,14 @@ apply_tc_kernel(const LayerRef* __restrict__ layers, int n_layers, int K, int R,
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
+    const int NE = L.ne, NQ = L.nq;
     auto raw_st = [&](int r) { return base + (uint32_t)(r * 16384); };
-    auto stage_w_hi = [&](int s) { return base + (uint32_t)(L.a_off + s * L.stage_a_bytes); };
-    auto stage_w_lo = [&](int s) { return base + (uint32_t)(L.a_off + s * L.stage_a_bytes + 16384); };
-    auto stage_e_hi = [&](int s) { return base + (uint32_t)(L.a_off + s * L.stage_a_bytes + 32768); };
-    auto stage_e_lo = [&](int s) { return base + (uint32_t)(L.a_off + s * L.stage_a_bytes + 32768 + R * 128); };
-    auto p_hi_atom = [&](int rc) { return base + (uint32_t)(L.a_off + rc * 16384); };
-    auto p_lo_atom = [&](int rc) { return base + (uint32_t)(L.a_off + TC_TILE_M * R * 4 + rc * 16384); };
+    auto stage_e_hi = [&](int s) { return base + (uint32_t)(L.e_off + s * L.e_stage_bytes); };
+    auto stage_e_lo = [&](int s) { return base + (uint32_t)(L.e_off + s * L.e_stage_bytes + R * 128); };
+    auto stage_w_hi = [&](int s) { return base + (uint32_t)(L.w_off + s * 32768); };
+    auto stage_w_lo = [&](int s) { return base + (uint32_t)(L.w_off + s * 32768 + 16384); };
+    auto p_hi_atom = [&](int rc) { return base + (uint32_t)(L.p_off + rc * 16384); };
+    auto p_lo_atom = [&](int rc) { return base + (uint32_t)(L.p_off + TC_TILE_M * R * 4 + rc * 16384); };
     auto qt_hi_st = [&](int t) { return base + (uint32_t)(t * 32768); };
     auto qt_lo_st = [&](int t) { return base + (uint32_t)(t * 32768 + 16384); };
 
@@ -363,22 +368,23 @@ apply_tc_kernel(const LayerRef* __restrict__ layers, int n_layers, int K, int R,
         if (lane == 0) {
             const uint32_t e_bytes = 2u * (uint32_t)R * 128u;
             for (int c = 0; c < n_chunks; ++c) {
-                const int s = c % TC_SA;
-                mbar_wait(bar_empty(s), (uint32_t)(((c / TC_SA) & 1) ^ 1));
+                const int s = c % NE;
+                mbar_wait(bar_empty_e(s), (uint32_t)(((c / NE) & 1) ^ 1));
                 mbar_arrive_expect_tx(bar_full_e(s), e_bytes);
                 tma_load_2d(stage_e_hi(s), &maps.e_hi, bar_full_e(s), c * 32, 0);
                 tma_load_2d(stage_e_lo(s), &maps.e_lo, bar_full_e(s), c * 32, 0);
             }
-            // the Qt stages alias the raw ring: wait until the transform warps have drained every raw stage
+            // the Qt ring aliases the raw ring and the E ring: both must be drained (all phase A MMAs complete)
             for (int r = 0; r < TC_NRAW; ++r) {
                 const int uses = (n_chunks - r + TC_NRAW - 1) / TC_NRAW;      // completed phases of raw_empty[r]
                 if (uses > 0) mbar_wait(bar_raw_empty(r), (uint32_t)((uses - 1) & 1));
             }
+            mbar_wait(bar_p_full, 0);
             int it = 0;
             for (int kc = 0; kc < n_kc; ++kc)
                 for (int rc = 0; rc < n_rc; ++rc, ++it) {
-                    const int t = it % TC_QT_STAGES;
-                    const uint32_t ph = (uint32_t)((it / TC_QT_STAGES) & 1);
+                    const int t = it % NQ;
+                    const uint32_t ph = (uint32_t)((it / NQ) & 1);
                     mbar_wait(bar_q_empty(t), ph ^ 1u);
                     mbar_arrive_expect_tx(bar_q_full(t), 32768u);
                     tma_load_2d(qt_hi_st(t), &maps.qt_hi, bar_q_full(t), rc * 32, kc * 128);
@@ -390,13 +396,12 @@ apply_tc_kernel(const LayerRef* __restrict__ layers, int n_layers, int K, int R,
         if (lane == 0) {
             const uint32_t idesc_a = umma_idesc_tf32(128, R);
             for (int c = 0; c < n_chunks; ++c) {
-                const int s = c % TC_SA;
-                const uint32_t ph = (uint32_t)((c / TC_SA) & 1);
-                mbar_wait(bar_full_w(s), ph);
-                mbar_wait(bar_full_e(s), ph);
+                const int s = c % TC_SA, se = c % NE;
+                mbar_wait(bar_full_w(s), (uint32_t)((c / TC_SA) & 1));
+                mbar_wait(bar_full_e(se), (uint32_t)((c / NE) & 1));
                 tc_fence_after();
                 const uint64_t a_hi = umma_desc_sw128(stage_w_hi(s)), a_lo = umma_desc_sw128(stage_w_lo(s));
-                const uint64_t b_hi = umma_desc_sw128(stage_e_hi(s)), b_lo = umma_desc_sw128(stage_e_lo(s));
+                const uint64_t b_hi = umma_desc_sw128(stage_e_hi(se)), b_lo = umma_desc_sw128(stage_e_lo(se));
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {          // 4 x (8 tf32 = 32 bytes) inside the 128-byte swizzle atom
                     const uint64_t adv = (uint64_t)(k * 2);
@@ -405,6 +410,7 @@ apply_tc_kernel(const LayerRef* __restrict__ layers, int n_layers, int K, int R,
                     umma_tf32(tmem_base, a_hi + adv, b_lo + adv, idesc_a, 1);
                 }
                 umma_commit(bar_empty(s));
+                umma_commit(bar_empty_e(se));
             }
             umma_commit(bar_p_full);
             // ---- phase B ----
@@ -418,8 +424,8 @@ apply_tc_kernel(const LayerRef* __restrict__ layers, int n_layers, int K, int R,
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + 256u + 128u * (uint32_t)b;
                 for (int rc = 0; rc < n_rc; ++rc, ++it) {
-                    const int t = it % TC_QT_STAGES;
-                    const uint32_t ph = (uint32_t)((it / TC_QT_STAGES) & 1);
+                    const int t = it % NQ;
+                    const uint32_t ph = (uint32_t)((it / NQ) & 1);
                     mbar_wait(bar_q_full(t), ph);
                     tc_fence_after();
                     const uint64_t a_hi = umma_desc_sw128(qt_hi_st(t)), a_lo = umma_desc_sw128(qt_lo_st(t));

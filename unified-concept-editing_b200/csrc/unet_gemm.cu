@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(UG_THREADS, 2) unet_gemm_kernel(const __grid_c
                 const int s = it % UG_STAGES;
                 mbar_wait(bar_empty(s), (uint32_t)(((it / UG_STAGES) & 1) ^ 1));
                 const uint32_t a_dst = base + s * UG_STAGE_BYTES, b_dst = a_dst + UG_BM * UG_BK * 2;
-                mbar_arrive_expect_tx(bar_full(s), UG_STAGE_BYTES);
+                mbar_arrive_expect_tx(bar_full(s), (uint32_t)(g.a_bytes + UG_BN * UG_BK * 2));
                 const int tap = it / kpt, c0 = (it % kpt) * UG_BK;
                 if (g.conv) {
                     const int ky = tap / 3, kx = tap % 3;
@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(UG_THREADS, 2) unet_gemm_kernel(const __grid_c
             img = img0 + ti;
             const int hh = h0 + rem / g.tw, ww = w0 + rem % g.tw;
             row = ((long)img * g.Ho + hh) * g.Wo + ww;
-            row_ok = true;
+            row_ok = r < g.tile_rows;
         } else {
             row = (long)m_tile * UG_BM + r;
             row_ok = row < g.M;
@@ -202,6 +202,7 @@ static int encode_bf16_map(CUtensorMap* m, const void* ptr, int rank, const long
 int gemm_desc_linear(GemmDesc* g, const void* A, long lda, long a_b1_stride, long a_b2_stride, const void* B, long ldb,
                      long b_b1_stride, long b_b2_stride, int M, int N, int Kd, int b1cnt, int b2cnt, int a_batched, int b_batched) {
     memset(g, 0, sizeof(*g));
+    g->m_tiles = (M + UG_BM - 1) / UG_BM; g->tile_rows = UG_BM; g->a_bytes = UG_BM * UG_BK * 2;
     g->M = M; g->N = N; g->Kd = Kd; g->batch = b1cnt * b2cnt; g->b1cnt = b1cnt; g->conv = 0; g->taps = 1; g->cin = Kd; g->alpha = 1.f;
     g->a_batched = a_batched; g->b_batched = b_batched;
     {
@@ -229,9 +230,12 @@ int gemm_desc_conv(GemmDesc* g, const void* act_nhwc, int NB, int Hin, int Win, 
     g->M = NB * Ho * Wo; g->N = Cout; g->Kd = g->taps * Cin;
     // output rectangle of 128 pixels
     int tw = Wo < 128 ? Wo : 128, th = 128 / tw; if (th > Ho) th = Ho;
-    int tn = 128 / (tw * th);
-    if (tw * th * tn != 128 || Wo % tw || Ho % th || NB % tn) return -2;
+    int tn = 128 / (tw * th); if (tn > NB) tn = NB;
+    if (tw * th * tn > 128 || Wo % tw || Ho % th || NB % tn) return -2;
     g->tw = tw; g->th = th; g->tn = tn;
+    g->tile_rows = tw * th * tn;                       // < 128 on tiny spatial levels: the remaining accumulator rows are ignored
+    g->a_bytes = g->tile_rows * UG_BK * 2;
+    g->m_tiles = (NB / tn) * (Ho / th) * (Wo / tw);
     {
         long dims[4] = {Cin, Win, Hin, NB}, str[4] = {1, Cin, (long)Win * Cin, (long)Hin * Win * Cin};
         int box[4] = {UG_BK, (tw - 1) * stride + 1, (th - 1) * stride + 1, tn};
@@ -254,7 +258,7 @@ int gemm_launch(const GemmDesc& g, cudaStream_t st) {
         if (e != cudaSuccess) return (int)e;
         configured = true;
     }
-    dim3 grid((g.N + UG_BN - 1) / UG_BN, (g.M + UG_BM - 1) / UG_BM, g.batch);
+    dim3 grid((g.N + UG_BN - 1) / UG_BN, g.m_tiles, g.batch);
     unet_gemm_kernel<<<grid, UG_THREADS, UG_SMEM, st>>>(g);
     return (int)cudaGetLastError();
 }

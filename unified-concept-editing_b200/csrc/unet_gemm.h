@@ -14,6 +14,9 @@ struct GemmDesc {
     int a_batched, b_batched;  // whether the operand's tensor map is indexed by (b1, b2)
     int conv, taps, cin, stride, pad;
     int tw, th, tn, Wo, Ho, NBimg;
+    int m_tiles;               // grid.y
+    int tile_rows;             // valid rows of an A tile (conv rectangles smaller than 128 pixels), else 128
+    int a_bytes;               // bytes one A-tile TMA delivers (expect_tx)
     int rows_per_img;          // linear: image index of a row = row / rows_per_img (for rowbias); 0 = none
     float alpha;
     void* out; int out_fp32; long ldo, out_b1_stride, out_b2_stride;

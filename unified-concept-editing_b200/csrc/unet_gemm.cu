@@ -35,9 +35,13 @@ __global__ void __launch_bounds__(UG_THREADS, 2) unet_gemm_kernel(const __grid_c
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     const int n_tile = blockIdx.x, m_tile = blockIdx.y;
-    const int b1 = blockIdx.z % g.b1cnt, b2 = blockIdx.z / g.b1cnt;
+    const int zb = (g.ksplit > 1) ? 0 : blockIdx.z, zk = (g.ksplit > 1) ? blockIdx.z : 0;
+    const int b1 = zb % g.b1cnt, b2 = zb / g.b1cnt;
     const int kpt = g.cin / UG_BK + ((g.cin % UG_BK) ? 1 : 0);     // k-iterations per tap
-    const int n_k = g.taps * kpt;
+    const int n_k_total = g.taps * kpt;
+    const int k_begin = (g.ksplit > 1) ? (int)((long)n_k_total * zk / g.ksplit) : 0;
+    const int k_end = (g.ksplit > 1) ? (int)((long)n_k_total * (zk + 1) / g.ksplit) : n_k_total;
+    const int n_k = k_end - k_begin;
 
     // conv: decode the output rectangle of this m-tile
     int img0 = 0, h0 = 0, w0 = 0;
@@ -69,7 +73,8 @@ __global__ void __launch_bounds__(UG_THREADS, 2) unet_gemm_kernel(const __grid_c
                 mbar_wait(bar_empty(s), (uint32_t)(((it / UG_STAGES) & 1) ^ 1));
                 const uint32_t a_dst = base + s * UG_STAGE_BYTES, b_dst = a_dst + UG_BM * UG_BK * 2;
                 mbar_arrive_expect_tx(bar_full(s), (uint32_t)(g.a_bytes + UG_BN * UG_BK * 2));
-                const int tap = it / kpt, c0 = (it % kpt) * UG_BK;
+                const int kit = k_begin + it;
+                const int tap = kit / kpt, c0 = (kit % kpt) * UG_BK;
                 if (g.conv) {
                     const int ky = tap / 3, kx = tap % 3;
                     tma_load_4d(a_dst, &g.tmA, bar_full(s), c0, w0 * g.stride + kx - g.pad, h0 * g.stride + ky - g.pad, img0);
@@ -129,6 +134,12 @@ __global__ void __launch_bounds__(UG_THREADS, 2) unet_gemm_kernel(const __grid_c
             for (int i = 0; i < 32; ++i) f[i] = g.alpha * __uint_as_float(v[i]);
             const int n0 = n_base + c;
             const bool full = (n0 + 32 <= g.N);
+            if (g.ksplit > 1) {            // partial sum of this k range; the epilogue terms are applied by the finalize pass
+                float* wp = g.splitk_ws + row * (long)g.N + n0;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) if (full || n0 + i < g.N) atomicAdd(wp + i, f[i]);
+                continue;
+            }
             if (g.bias) {
 #pragma unroll
                 for (int i = 0; i < 32; ++i) if (full || n0 + i < g.N) f[i] += g.bias[n0 + i];
@@ -251,6 +262,39 @@ int gemm_desc_conv(GemmDesc* g, const void* act_nhwc, int NB, int Hin, int Win, 
     return 0;
 }
 
+// out = ws (+bias) (+rowbias[img]) (+residual); ws <- 0.  One thread per 4 consecutive columns.
+__global__ void __launch_bounds__(256) splitk_finalize_kernel(GemmDesc g, int rows_per_img) {
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int nv = g.N / 4;
+    if (idx >= (long)g.M * nv) return;
+    const long row = idx / nv; const int n0 = (int)(idx % nv) * 4;
+    float4* wp = reinterpret_cast<float4*>(g.splitk_ws + row * g.N + n0);
+    float4 v = *wp;
+    *wp = make_float4(0.f, 0.f, 0.f, 0.f);
+    float f[4] = {v.x, v.y, v.z, v.w};
+    if (g.bias) { for (int i = 0; i < 4; ++i) f[i] += g.bias[n0 + i]; }
+    if (g.rowbias) { const float* rb = g.rowbias + (row / rows_per_img) * g.N + n0; for (int i = 0; i < 4; ++i) f[i] += rb[i]; }
+    if (g.residual) { const __nv_bfloat16* rp = g.residual + row * g.ldr + n0; for (int i = 0; i < 4; ++i) f[i] += __bfloat162float(rp[i]); }
+    if (g.out_fp32) {
+        float* op = reinterpret_cast<float*>(g.out) + row * g.ldo + n0;
+        for (int i = 0; i < 4; ++i) op[i] = f[i];
+    } else {
+        __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(g.out) + row * g.ldo + n0;
+        for (int i = 0; i < 4; ++i) op[i] = __float2bfloat16(f[i]);
+    }
+}
+
+int gemm_choose_ksplit(const GemmDesc& g, int sm_count) {
+    if (g.batch != 1 || (g.N % 4)) return 1;
+    const int ctas = ((g.N + UG_BN - 1) / UG_BN) * g.m_tiles;
+    if (ctas * 2 > sm_count) return 1;
+    const int kpt = g.cin / UG_BK + ((g.cin % UG_BK) ? 1 : 0);
+    const int n_k = g.taps * kpt;
+    int ks = (2 * sm_count + ctas - 1) / ctas;
+    if (ks > n_k / 4) ks = n_k / 4;          // keep at least 4 k-iterations per CTA
+    return ks < 2 ? 1 : ks;
+}
+
 int gemm_launch(const GemmDesc& g, cudaStream_t st) {
     static bool configured = false;
     if (!configured) {
@@ -258,9 +302,17 @@ int gemm_launch(const GemmDesc& g, cudaStream_t st) {
         if (e != cudaSuccess) return (int)e;
         configured = true;
     }
-    dim3 grid((g.N + UG_BN - 1) / UG_BN, g.m_tiles, g.batch);
+    dim3 grid((g.N + UG_BN - 1) / UG_BN, g.m_tiles, g.ksplit > 1 ? g.ksplit : g.batch);
     unet_gemm_kernel<<<grid, UG_THREADS, UG_SMEM, st>>>(g);
-    return (int)cudaGetLastError();
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return (int)e;
+    if (g.ksplit > 1) {
+        const long n = (long)g.M * (g.N / 4);
+        const int rows_per_img = g.conv ? g.Ho * g.Wo : (g.rows_per_img > 0 ? g.rows_per_img : 1);
+        splitk_finalize_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(g, rows_per_img);
+        e = cudaGetLastError();
+    }
+    return (int)e;
 }
 
 }  // namespace uce

@@ -18,6 +18,8 @@ struct GemmDesc {
     int tile_rows;             // valid rows of an A tile (conv rectangles smaller than 128 pixels), else 128
     int a_bytes;               // bytes one A-tile TMA delivers (expect_tx)
     int rows_per_img;          // linear: image index of a row = row / rows_per_img (for rowbias); 0 = none
+    int ksplit;                // > 1: the k loop is split over grid.z; partial sums are atomically added into splitk_ws (fp32 [M,N])
+    float* splitk_ws;          // zero on entry; gemm_splitk_finalize applies the epilogue and re-zeroes it
     float alpha;
     void* out; int out_fp32; long ldo, out_b1_stride, out_b2_stride;
     const float* bias;         // [N]
@@ -31,5 +33,7 @@ int gemm_desc_linear(GemmDesc* g, const void* A, long lda, long a_b1_stride, lon
 int gemm_desc_conv(GemmDesc* g, const void* act_nhwc, int NB, int Hin, int Win, int Cin, const void* w_tapmajor, int Cout,
                    int ksize, int stride);
 int gemm_launch(const GemmDesc& g, cudaStream_t st);
+// Picks a split factor for under-filled grids (batch == 1 only); returns it (1 = no split).
+int gemm_choose_ksplit(const GemmDesc& g, int sm_count);
 
 }  // namespace uce

@@ -254,12 +254,22 @@ def run_ours(args, rank, world, local_rank):
         sharded = bench_sharded(solver, prob, dev, rank, world, args)
 
     denoise = None
-    if rank == 0 and not args.no_denoise:
+    if not args.no_denoise:
+        # prompts are sharded data-parallel over the GPUs with no steady-state collective:
+        # every rank runs its own denoise loop; rank 0 reports the slowest rank's per-GPU rate and the aggregate.
         try:
             denoise = bench_denoise(dev, args)
         except Exception as exc:      # the solver line is the contract; report the denoise failure instead of losing it
             denoise = {"error": f"{type(exc).__name__}: {exc}"}
             log(f"denoise bench failed: {denoise['error']}")
+        if world > 1:
+            allv = [None] * world
+            dist.all_gather_object(allv, denoise.get("value"))
+            if rank == 0 and all(v is not None for v in allv):
+                denoise["per_gpu_steps_per_s"] = allv
+                denoise["value"] = min(allv)
+                denoise["aggregate_steps_per_s"] = sum(allv)
+                denoise["n_gpus"] = world
     if rank == 0:
         ms_per_step = total_ms / args.steps
         value = world * n / (ms_per_step / 1e3)

@@ -1,0 +1,22 @@
+"""torchrun --nproc-per-node 2: the erase driver with projections sharded over ranks and ONE NCCL all-gather must
+reproduce the single-GPU result bit for bit (same kernels, same inputs)."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch, torch.distributed as dist
+from oracle.fake_pipe import FakePipe, layer_table
+from uce_b200.erase import UCE
+
+rank, local = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+pipe = FakePipe(layer_table("sd14"), seed=1, correlated=True)
+edit = [f"artist {i}" for i in range(20)]; guide = ["art"] * 20; pres = [f"thing {i}" for i in range(30)]
+single = UCE(pipe, edit, guide, pres, 1.0, 1.0, 0.5, None, "x", device=f"cuda:{local}", verbose=False)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+sharded = UCE(pipe, edit, guide, pres, 1.0, 1.0, 0.5, None, "x", device=f"cuda:{local}", verbose=False)
+ok = all(torch.equal(single[k].cpu(), sharded[k].cpu()) for k in single) and len(sharded) == 32
+t = torch.tensor([int(ok)], device=f"cuda:{local}")
+dist.all_reduce(t, op=dist.ReduceOp.MIN)
+if rank == 0:
+    print("sharded == single on every rank:", bool(t.item()), "keys", len(sharded))
+dist.destroy_process_group()
+sys.exit(0 if t.item() else 1)

@@ -32,7 +32,7 @@ constexpr int TC_TILE_M = 128;
 constexpr int TC_PRODUCER_WARPS = 8;
 constexpr int TC_THREADS = (TC_PRODUCER_WARPS + 3) * 32;   // + W TMA warp + E/Qt TMA warp + MMA warp
 constexpr int TC_NRAW = 5;                                  // raw W chunks in flight per SM (5 x 16 KB by TMA)
-constexpr int TC_SA = 2;                                    // hi/lo MMA stages
+constexpr int TC_SA = 4;                                    // hi/lo A-operand stages in tensor memory
 constexpr int TC_MAX_LAYERS = 160;                          // per-launch tensor maps for W_old (one per projection)
 constexpr int WARP_W_TMA = TC_PRODUCER_WARPS, WARP_E_TMA = TC_PRODUCER_WARPS + 1, WARP_MMA = TC_PRODUCER_WARPS + 2;
 
@@ -209,7 +209,8 @@ __host__ __device__ inline TcSmem tc_smem_layout(int R) {
     s.total = s.bar_off + 512;
     return s;
 }
-// Tensor-memory columns: [0,R) P accumulator | [128,256) two A stages {W_hi 32 cols, W_lo 32 cols} | [256,512) phase B accumulators
+// Tensor-memory columns: [0,R) P accumulator | [128,384) four A stages {W_hi 32 cols, W_lo 32 cols} (phase A only) |
+// [256,512) phase B accumulators (alias the last two A stages: the tensor pipe executes phase B after phase A)
 constexpr uint32_t TC_A_COL0 = 128;
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -225,16 +226,16 @@ apply_tc_kernel(const LayerRef* __restrict__ layers, int n_layers, int K, int R,
     const uint32_t bars = base + L.bar_off;
     auto bar_raw_full  = [&](int r) { return bars + 8u * r; };                 // [0,5)   W TMA -> transform warps
     auto bar_raw_empty = [&](int r) { return bars + 8u * (5 + r); };           // [5,10)
-    auto bar_full_w = [&](int s) { return bars + 8u * (10 + s); };             // [10,12) transform warps -> MMA
-    auto bar_empty  = [&](int s) { return bars + 8u * (12 + s); };             // [12,14) MMA -> transform warps
-    auto bar_full_e  = [&](int s) { return bars + 8u * (14 + s); };            // [14,18) E TMA -> MMA
-    auto bar_empty_e = [&](int s) { return bars + 8u * (18 + s); };            // [18,22) MMA -> E TMA
-    const uint32_t bar_p_full = bars + 8u * 22, bar_p_smem = bars + 8u * 23;
-    auto bar_q_full  = [&](int t) { return bars + 8u * (24 + t); };            // [24,28)
-    auto bar_q_empty = [&](int t) { return bars + 8u * (28 + t); };            // [28,32)
-    auto bar_acc_full  = [&](int b) { return bars + 8u * (32 + b); };
-    auto bar_acc_empty = [&](int b) { return bars + 8u * (34 + b); };
-    const uint32_t tmem_slot = bars + 8u * 37;
+    auto bar_full_w = [&](int s) { return bars + 8u * (10 + s); };             // [10,14) transform warps -> MMA (A stage in TMEM written)
+    auto bar_empty  = [&](int s) { return bars + 8u * (14 + s); };             // [14,18) MMA -> transform warps
+    auto bar_full_e  = [&](int s) { return bars + 8u * (18 + s); };            // [18,22) E TMA -> MMA
+    auto bar_empty_e = [&](int s) { return bars + 8u * (22 + s); };            // [22,26) MMA -> E TMA
+    const uint32_t bar_p_full = bars + 8u * 26, bar_p_smem = bars + 8u * 27;
+    auto bar_q_full  = [&](int t) { return bars + 8u * (28 + t); };            // [28,32)
+    auto bar_q_empty = [&](int t) { return bars + 8u * (32 + t); };            // [32,36)
+    auto bar_acc_full  = [&](int b) { return bars + 8u * (36 + b); };
+    auto bar_acc_empty = [&](int b) { return bars + 8u * (38 + b); };
+    const uint32_t tmem_slot = bars + 8u * 41;
 
     const int tile = blockIdx.x;
     const int layer = tc_find_layer(layers, n_layers, tile);

@@ -26,7 +26,7 @@ using bf16 = __nv_bfloat16;
 using uce::GemmDesc;
 struct Act { bf16* p; int n, h, w, c; long pixels() const { return (long)n * h * w; } };
 struct Weight { std::vector<long> shape; bf16* b = nullptr; float* f = nullptr; long elems = 0; int kind = 0; };
-// kind: 0 fp32 as is, 1 bf16 as is ([N,K] linear / 1x1 conv), 2 conv3x3 -> bf16 tap-major, 3 attention q/k/v (pad heads, bf16),
+// kind: 6 conv_in fp32 [ci][ky][kx][co]; 0 fp32 as is, 1 bf16 as is ([N,K] linear / 1x1 conv), 2 conv3x3 -> bf16 tap-major, 3 attention q/k/v (pad heads, bf16),
 //       4 attention out projection (pad head columns, bf16), 5 conv_out fp32 [o][ky][kx][c]
 
 int pad64(int x) { return (x + 63) / 64 * 64; }
@@ -126,7 +126,7 @@ void build_inventory(sd_unet* u) {
 bool ends_with(const std::string& s, const char* suf) { const size_t n = strlen(suf); return s.size() >= n && s.compare(s.size() - n, n, suf) == 0; }
 
 int weight_kind(const std::string& name, const std::vector<long>& shp) {
-    if (name == "conv_in.weight") return 0;
+    if (name == "conv_in.weight") return 6;
     if (name == "conv_out.weight") return 5;
     if (shp.size() == 4) return shp[2] == 3 ? 2 : 1;
     if (shp.size() == 2) {
@@ -445,6 +445,11 @@ int sd_unet_set_weight(sd_unet* u, const char* name, const float* data, const lo
         const long co = shp[0], ci = shp[1];
         tmp.resize(n);
         for (long o = 0; o < co; ++o) for (long c = 0; c < ci; ++c) for (int k = 0; k < 9; ++k) tmp[(o * 9 + k) * ci + c] = data[(o * ci + c) * 9 + k];
+        src = tmp.data();
+    } else if (kind == 6) {     // conv_in [Cout][Cin][3][3] -> [Cin][ky][kx][Cout]
+        const long co = shp[0], ci = shp[1];
+        tmp.resize(n);
+        for (long o = 0; o < co; ++o) for (long c = 0; c < ci; ++c) for (int k = 0; k < 9; ++k) tmp[(c * 9 + k) * co + o] = data[(o * ci + c) * 9 + k];
         src = tmp.data();
     } else if (kind == 3) {     // [C, K] -> [heads*dhp, K], zero rows for the head padding
         const long C = shp[0], K = shp[1]; const int dh = (int)(C / heads), dhp = pad64(dh);

@@ -290,8 +290,9 @@ int gemm_choose_ksplit(const GemmDesc& g, int sm_count) {
     if (ctas * 2 > sm_count) return 1;
     const int kpt = g.cin / UG_BK + ((g.cin % UG_BK) ? 1 : 0);
     const int n_k = g.taps * kpt;
+    if (n_k < 40) return 1;                  // short reductions: the finalize pass would cost more than the split gains
     int ks = (2 * sm_count + ctas - 1) / ctas;
-    if (ks > n_k / 4) ks = n_k / 4;          // keep at least 4 k-iterations per CTA
+    if (ks > n_k / 8) ks = n_k / 8;          // keep at least 8 k-iterations per CTA
     return ks < 2 ? 1 : ks;
 }
 

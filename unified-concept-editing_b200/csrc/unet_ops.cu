@@ -199,8 +199,10 @@ __global__ void __launch_bounds__(256) concat_c_kernel(const __nv_bfloat16* __re
     *reinterpret_cast<uint4*>(y + idx * 8) = u;
 }
 
-// conv_in: 3x3, 4 -> Cout, input NCHW (fp32 latents), output NHWC bf16.  One thread per (pixel, 8 output channels).
-__global__ void __launch_bounds__(256) conv_in_kernel(const float* __restrict__ x, const float* __restrict__ w /*[Cout][4][3][3]*/,
+// conv_in: 3x3, 4 -> Cout, input NCHW (fp32 latents), output NHWC bf16.  One thread per (pixel, 8 output channels);
+// weights are stored [ci][ky][kx][Cout] so that the 8 channels of a thread are two float4 loads and a warp reads
+// consecutive addresses (the whole table is 46 KB and stays in L1).
+__global__ void __launch_bounds__(256) conv_in_kernel(const float* __restrict__ x, const float* __restrict__ w /*[4][3][3][Cout]*/,
                                                       const float* __restrict__ bias, __nv_bfloat16* __restrict__ y, int NB, int H, int W, int Cout) {
     const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
     const int vpp = Cout / 8;
@@ -210,16 +212,19 @@ __global__ void __launch_bounds__(256) conv_in_kernel(const float* __restrict__ 
     float acc[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc[i] = bias[v * 8 + i];
+#pragma unroll
     for (int ci = 0; ci < 4; ++ci)
+#pragma unroll
         for (int ky = 0; ky < 3; ++ky) {
             const int iy = hh + ky - 1;
-            if (iy < 0 || iy >= H) continue;
+#pragma unroll
             for (int kx = 0; kx < 3; ++kx) {
                 const int ix = ww + kx - 1;
-                if (ix < 0 || ix >= W) continue;
-                const float xv = x[(((long)n * 4 + ci) * H + iy) * W + ix];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) acc[i] += xv * w[(((v * 8 + i) * 4 + ci) * 3 + ky) * 3 + kx];
+                const float xv = (iy >= 0 && iy < H && ix >= 0 && ix < W) ? x[(((long)n * 4 + ci) * H + iy) * W + ix] : 0.f;
+                const float4* wp = reinterpret_cast<const float4*>(w + (long)((ci * 3 + ky) * 3 + kx) * Cout + v * 8);
+                const float4 w0 = wp[0], w1 = wp[1];
+                acc[0] += xv * w0.x; acc[1] += xv * w0.y; acc[2] += xv * w0.z; acc[3] += xv * w0.w;
+                acc[4] += xv * w1.x; acc[5] += xv * w1.y; acc[6] += xv * w1.z; acc[7] += xv * w1.w;
             }
         }
     *reinterpret_cast<uint4*>(y + idx * 8) = pack8(acc);
@@ -299,7 +304,7 @@ int op_groupnorm(const __nv_bfloat16* x, __nv_bfloat16* y, int NB, int HW, int C
                  float eps, int silu, cudaStream_t st) {
     cudaError_t e = cudaMemsetAsync(stats, 0, (size_t)NB * G * 2 * sizeof(float), st);
     if (e != cudaSuccess) return (int)e;
-    const int pix_per_cta = HW >= 1024 ? 64 : (HW >= 64 ? 16 : HW);
+    const int pix_per_cta = HW >= 64 ? 16 : HW;      // many small slabs: the per-thread pixel walk is latency-bound
     gn_stats_kernel<<<dim3((HW + pix_per_cta - 1) / pix_per_cta, NB), 256, 2 * G * sizeof(float), st>>>(x, HW, C, G, pix_per_cta, stats);
     OPS_CHECK();
     const long n_vec = (long)NB * HW * C / 8;

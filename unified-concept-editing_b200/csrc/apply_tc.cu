@@ -25,6 +25,8 @@
 #include "uce_ws.h"
 #include <cuda.h>
 #include <cstdint>
+#include <cstdlib>
+#include <vector>
 
 namespace uce {
 
@@ -209,13 +211,21 @@ __host__ __device__ inline TcSmem tc_smem_layout(int R) {
     s.total = s.bar_off + 512;
     return s;
 }
-// Tensor-memory columns: [0,R) P accumulator | [128,384) four A stages {W_hi 32 cols, W_lo 32 cols} (phase A only) |
-// [256,512) phase B accumulators (alias the last two A stages: the tensor pipe executes phase B after phase A)
-constexpr uint32_t TC_A_COL0 = 128;
+// Tensor-memory columns
+//   phase A: [0,2R) P accumulator as two halves  hi.hi + lo.hi | hi.lo   (the B operand stacks E_hi over E_lo, so the
+//            hi.hi and hi.lo products come out of ONE N = 2R MMA: the single issuing thread, ~60 cycles per
+//            tcgen05.mma, is the limiter with 32-cycle MMAs — 2 instead of 3 instructions per k-step)
+//            [256,512) four A stages {W_hi 32 cols, W_lo 32 cols}
+//   phase B: two ping-pong accumulators of 256 columns, [0,256) and [256,512), again as two halves (B = P_hi over P_lo)
+constexpr uint32_t TC_A_COL0 = 256;
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
 apply_tc_kernel(const LayerRef* __restrict__ layers, int n_layers, int K, int R,
-                const __grid_constant__ TcMaps maps, const __grid_constant__ TcWMaps wmaps) {
+                const __grid_constant__ TcMaps maps, const __grid_constant__ TcWMaps wmaps, long long* __restrict__ trace) {
+    // optional timeline of CTA 0 (UCE_TC_TRACE=<file>): trace[(role * 64 + index) * 4 + event] = clock64()
+    auto tr = [&](int role, int idx, int ev) {
+        if (trace && blockIdx.x == 0 && idx < 64) trace[(role * 64 + idx) * 4 + ev] = clock64();
+    };
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // dynamic smem base is at least 16-byte aligned; swizzled tiles need 1024
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -274,8 +284,8 @@ apply_tc_kernel(const LayerRef* __restrict__ layers, int n_layers, int K, int R,
     auto raw_st = [&](int r) { return base + (uint32_t)(r * 16384); };
     auto stage_e_hi = [&](int s) { return base + (uint32_t)(L.e_off + s * L.e_stage_bytes); };
     auto stage_e_lo = [&](int s) { return base + (uint32_t)(L.e_off + s * L.e_stage_bytes + R * 128); };
-    auto p_hi_atom = [&](int rc) { return base + (uint32_t)(L.p_off + rc * 16384); };
-    auto p_lo_atom = [&](int rc) { return base + (uint32_t)(L.p_off + TC_TILE_M * R * 4 + rc * 16384); };
+    auto p_hi_atom = [&](int rc) { return base + (uint32_t)(L.p_off + rc * 32768); };              // [P_hi(rc) 128 rows | P_lo(rc) 128 rows]
+    auto p_lo_atom = [&](int rc) { return base + (uint32_t)(L.p_off + rc * 32768 + 16384); };
     auto qt_hi_st = [&](int t) { return base + (uint32_t)(t * 32768); };
     auto qt_lo_st = [&](int t) { return base + (uint32_t)(t * 32768 + 16384); };
 
@@ -288,6 +298,7 @@ apply_tc_kernel(const LayerRef* __restrict__ layers, int n_layers, int K, int R,
         for (int c = 0; c < n_chunks; ++c) {
             const int r = c % TC_NRAW, s = c % TC_SA;
             mbar_wait(bar_raw_full(r), (uint32_t)((c / TC_NRAW) & 1));
+            if (threadIdx.x == 0) tr(1, c, 0);
             const uint32_t raw = raw_st(r);
             float4 v[4];
 #pragma unroll
@@ -305,6 +316,7 @@ apply_tc_kernel(const LayerRef* __restrict__ layers, int n_layers, int K, int R,
                 }
             }
             mbar_wait(bar_empty(s), (uint32_t)(((c / TC_SA) & 1) ^ 1));      // the MMAs that read this A stage have completed
+            if (threadIdx.x == 0) tr(1, c, 1);
             tc_fence_after();
             const uint32_t ta = tmem_base + ((uint32_t)(32 * tq) << 16) + TC_A_COL0 + (uint32_t)(64 * s + 16 * thalf);
             tmem_st16(ta, hi);
@@ -313,15 +325,20 @@ apply_tc_kernel(const LayerRef* __restrict__ layers, int n_layers, int K, int R,
             tc_fence_before();
             __syncwarp();
             if (lane == 0) { mbar_arrive(bar_full_w(s)); mbar_arrive(bar_raw_empty(r)); }
+            if (threadIdx.x == 0) tr(1, c, 2);
         }
         // ---- P: TMEM -> registers -> hi/lo -> swizzled smem (B operand of phase B) ----
         const int q = warp & 3, half = warp >> 2;
         const int prow = 32 * q + lane;            // TMEM lane == row of the tile
         mbar_wait(bar_p_full, 0);
+        if (threadIdx.x == 0) tr(6, 0, 0);
         tc_fence_after();
         for (int rc = half; rc < n_rc; rc += 2) {
-            uint32_t v[32];
+            uint32_t v[32], v2[32];
             tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(rc * 32), v);
+            tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(R + rc * 32), v2);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(v2[i]));
             const uint32_t hb = p_hi_atom(rc), lb = p_lo_atom(rc);
 #pragma unroll
             for (int ch = 0; ch < 8; ++ch) {
@@ -352,13 +369,18 @@ apply_tc_kernel(const LayerRef* __restrict__ layers, int n_layers, int K, int R,
 #pragma unroll
                 for (int i = 0; i < 64; ++i) w[i] = (jrow0 + i < rows_valid) ? ldg_f32(wp + (size_t)i * K) : 0.f;
             }
+            if (threadIdx.x == 0) tr(5, kc, 0);
             mbar_wait(bar_acc_full(b), (uint32_t)((kc >> 1) & 1));
+            if (threadIdx.x == 0) tr(5, kc, 1);
             tc_fence_after();
             float* op = w_new + (size_t)jrow0 * K + col;
 #pragma unroll
             for (int g = 0; g < 2; ++g) {
-                uint32_t v[32];
-                tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(256 + 128 * b + jrow0 + 32 * g), v);
+                uint32_t v[32], v2[32];
+                tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(256 * b + jrow0 + 32 * g), v);
+                tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(256 * b + 128 + jrow0 + 32 * g), v2);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(v2[i]));
                 if (rows_valid == TC_TILE_M) {
 #pragma unroll
                     for (int i = 0; i < 32; ++i) stg_f32_hint(op + (size_t)(32 * g + i) * K, w[32 * g + i] + __uint_as_float(v[i]), pol_stream);
@@ -371,6 +393,7 @@ apply_tc_kernel(const LayerRef* __restrict__ layers, int n_layers, int K, int R,
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_acc_empty(b));
+            if (threadIdx.x == 0) tr(5, kc, 2);
         }
     } else if (warp == WARP_W_TMA) {
         // =============================== TMA warp 1: raw W chunks, TC_NRAW deep ===============================
@@ -380,6 +403,7 @@ apply_tc_kernel(const LayerRef* __restrict__ layers, int n_layers, int K, int R,
             for (int c = 0; c < n_chunks; ++c) {
                 const int r = c % TC_NRAW;
                 mbar_wait(bar_raw_empty(r), (uint32_t)(((c / TC_NRAW) & 1) ^ 1));
+                tr(0, c, 0);
                 mbar_arrive_expect_tx(bar_raw_full(r), 16384u);
                 tma_load_2d_hint(raw_st(r), wm, bar_raw_full(r), c * 32, lt * TC_TILE_M, pol_keep);
             }
@@ -391,6 +415,7 @@ apply_tc_kernel(const LayerRef* __restrict__ layers, int n_layers, int K, int R,
             for (int c = 0; c < n_chunks; ++c) {
                 const int s = c % NE;
                 mbar_wait(bar_empty_e(s), (uint32_t)(((c / NE) & 1) ^ 1));
+                tr(2, c, 0);
                 mbar_arrive_expect_tx(bar_full_e(s), e_bytes);
                 tma_load_2d(stage_e_hi(s), &maps.e_hi, bar_full_e(s), c * 32, 0);
                 tma_load_2d(stage_e_lo(s), &maps.e_lo, bar_full_e(s), c * 32, 0);
@@ -415,52 +440,55 @@ apply_tc_kernel(const LayerRef* __restrict__ layers, int n_layers, int K, int R,
     } else {
         // =============================== MMA issuer ===============================
         if (lane == 0) {
-            const uint32_t idesc_a = umma_idesc_tf32(128, R);
+            const uint32_t idesc_a = umma_idesc_tf32(128, 2 * R), idesc_a2 = umma_idesc_tf32(128, R);
             for (int c = 0; c < n_chunks; ++c) {
                 const int s = c % TC_SA, se = c % NE;
                 mbar_wait(bar_full_w(s), (uint32_t)((c / TC_SA) & 1));
+                tr(3, c, 0);
                 mbar_wait(bar_full_e(se), (uint32_t)((c / NE) & 1));
+                tr(3, c, 1);
                 tc_fence_after();
                 const uint32_t a_hi = tmem_base + TC_A_COL0 + (uint32_t)(64 * s), a_lo = a_hi + 32u;
-                const uint64_t b_hi = umma_desc_sw128(stage_e_hi(se)), b_lo = umma_desc_sw128(stage_e_lo(se));
+                const uint64_t b_hi = umma_desc_sw128(stage_e_hi(se));     // E_hi rows followed by E_lo rows: one 2R-row tile
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {          // 8 tf32 per step: 8 TMEM columns of A, 32 bytes inside the swizzle atom of B
                     const uint64_t adv = (uint64_t)(k * 2);
-                    umma_tf32_ts(tmem_base, a_hi + 8u * k, b_hi + adv, idesc_a, (c | k) != 0);
-                    umma_tf32_ts(tmem_base, a_lo + 8u * k, b_hi + adv, idesc_a, 1);
-                    umma_tf32_ts(tmem_base, a_hi + 8u * k, b_lo + adv, idesc_a, 1);
+                    umma_tf32_ts(tmem_base, a_hi + 8u * k, b_hi + adv, idesc_a, (c | k) != 0);     // N = 2R: [hi.hi | hi.lo]
+                    umma_tf32_ts(tmem_base, a_lo + 8u * k, b_hi + adv, idesc_a2, 1);               // N = R : += lo.hi on the first half
                 }
                 umma_commit(bar_empty(s));
                 umma_commit(bar_empty_e(se));
+                tr(3, c, 2);
             }
             umma_commit(bar_p_full);
             // ---- phase B ----
             mbar_wait(bar_p_smem, 0);
             tc_fence_after();
-            const uint32_t idesc_b = umma_idesc_tf32(128, 128);
+            const uint32_t idesc_b = umma_idesc_tf32(128, 256), idesc_b2 = umma_idesc_tf32(128, 128);
             int it = 0;
             for (int kc = 0; kc < n_kc; ++kc) {
                 const int b = kc & 1;
                 mbar_wait(bar_acc_empty(b), (uint32_t)(((kc >> 1) & 1) ^ 1));
+                tr(4, kc, 0);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + 256u + 128u * (uint32_t)b;
+                const uint32_t d_tmem = tmem_base + 256u * (uint32_t)b;
                 for (int rc = 0; rc < n_rc; ++rc, ++it) {
                     const int t = it % NQ;
                     const uint32_t ph = (uint32_t)((it / NQ) & 1);
                     mbar_wait(bar_q_full(t), ph);
                     tc_fence_after();
                     const uint64_t a_hi = umma_desc_sw128(qt_hi_st(t)), a_lo = umma_desc_sw128(qt_lo_st(t));
-                    const uint64_t b_hi = umma_desc_sw128(p_hi_atom(rc)), b_lo = umma_desc_sw128(p_lo_atom(rc));
+                    const uint64_t b_hi = umma_desc_sw128(p_hi_atom(rc));      // P_hi rows followed by P_lo rows: 256-row tile
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         const uint64_t adv = (uint64_t)(k * 2);
-                        umma_tf32(d_tmem, a_hi + adv, b_hi + adv, idesc_b, (rc | k) != 0);
-                        umma_tf32(d_tmem, a_lo + adv, b_hi + adv, idesc_b, 1);
-                        umma_tf32(d_tmem, a_hi + adv, b_lo + adv, idesc_b, 1);
+                        umma_tf32(d_tmem, a_hi + adv, b_hi + adv, idesc_b, (rc | k) != 0);     // N = 256: [hi.hi | hi.lo]
+                        umma_tf32(d_tmem, a_lo + adv, b_hi + adv, idesc_b2, 1);                // N = 128: += lo.hi
                     }
                     umma_commit(bar_q_empty(t));
                 }
                 umma_commit(bar_acc_full(b));
+                tr(4, kc, 1);
             }
         }
     }
@@ -545,9 +573,28 @@ int apply_tc_lowrank(uce_ws* ws, const LayerRef* layers_dev, const LayerRef* lay
         UCE_CUDA(cudaFuncSetAttribute(apply_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured = smem;
     }
-    apply_tc_kernel<<<total_tiles, TC_THREADS, smem, st>>>(layers_dev, n_layers, K, R, maps, wmaps);
+    long long* trace = nullptr;
+    const char* trace_path = getenv("UCE_TC_TRACE");
+    if (trace_path) { UCE_CUDA(cudaMalloc(&trace, 7 * 64 * 4 * sizeof(long long))); UCE_CUDA(cudaMemsetAsync(trace, 0, 7 * 64 * 4 * sizeof(long long), st)); }
+    apply_tc_kernel<<<total_tiles, TC_THREADS, smem, st>>>(layers_dev, n_layers, K, R, maps, wmaps, trace);
     UCE_LAUNCH_CHECK();
     *launches += 1;
+    if (trace) {   // debugging aid: dump the timeline of CTA 0 (synchronises)
+        std::vector<long long> h(7 * 64 * 4);
+        UCE_CUDA(cudaStreamSynchronize(st));
+        UCE_CUDA(cudaMemcpy(h.data(), trace, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+        UCE_CUDA(cudaFree(trace));
+        if (FILE* f = fopen(trace_path, "w")) {
+            long long t0 = 0;
+            for (long long v : h) if (v && (!t0 || v < t0)) t0 = v;
+            const char* roles[7] = {"w_tma", "transform", "e_tma", "mma_a", "mma_b", "epilogue", "pconv"};
+            for (int r = 0; r < 7; ++r) for (int i = 0; i < 64; ++i) {
+                const long long* e = &h[(r * 64 + i) * 4];
+                if (e[0] || e[1] || e[2]) fprintf(f, "%s %d %lld %lld %lld\n", roles[r], i, e[0] ? e[0] - t0 : -1, e[1] ? e[1] - t0 : -1, e[2] ? e[2] - t0 : -1);
+            }
+            fclose(f);
+        }
+    }
     return 0;
 }
 

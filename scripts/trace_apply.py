@@ -13,6 +13,9 @@ for _ in range(3):
     s.factor(p["C"].cuda(), p["G"].cuda(), p["scales"], p["n_edit"], p["lamb"]); s.apply(W, out)
 torch.cuda.synchronize()
 os.environ["UCE_TC_TRACE"] = "gpurun_out/tc_trace.txt"
+os.environ["UCE_CHOL_TRACE"] = "gpurun_out/chol_trace.txt"
 s.factor(p["C"].cuda(), p["G"].cuda(), p["scales"], p["n_edit"], p["lamb"]); s.apply(W, out)
 torch.cuda.synchronize()
 print(open("gpurun_out/tc_trace.txt").read())
+print("CHOL phases (index, cycles since start, delta):")
+print(open("gpurun_out/chol_trace.txt").read())

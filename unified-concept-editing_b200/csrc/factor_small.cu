@@ -11,6 +11,7 @@
 // Same algebra and same fp64 precision as the general path (trainscripts/uce_sd_erase.py:63,71,79,82 — the
 // mat2 accumulation and its inverse — done once per edit).
 #include "uce_ws.h"
+#include <cstdlib>
 
 namespace uce {
 
@@ -74,16 +75,22 @@ __device__ __forceinline__ int fs_blk(int bi, int bj) { return (bi * (bi + 1) / 
 
 // 1 / sqrt(d) in fp64 without the slow software sqrt/div: fp32 seed + 3 Newton steps (relative error < 1e-15)
 __device__ __forceinline__ double fs_rsqrt(double d) {
-    double y = (double)rsqrtf((float)d);
-#pragma unroll
-    for (int i = 0; i < 3; ++i) y = y * (1.5 - 0.5 * d * y * y);
-    return y;
+    // fp32 seed (2^-22) + two residual-form Newton steps: 6 dependent fp64 operations (fp64 latency dominates the
+    // 160 sequential pivots of the factorisation), relative error at fp64 round-off
+    const double y0 = (double)rsqrtf((float)d);
+    double e = fma(-d, y0 * y0, 1.0);
+    double y = fma(0.5 * y0, e, y0);
+    e = fma(-d, y * y, 1.0);
+    return fma(0.5 * y, e, y);
 }
 
 __global__ void __launch_bounds__(FS_T, 1)
 chol_small_kernel(double* __restrict__ Hg, int n, int n_pad, const double* __restrict__ dadd, int n_pres, int n_edit,
-                  double* __restrict__ Z, int ldz, int write_back, int* flag) {
+                  double* __restrict__ Z, int ldz, int write_back, int* flag, long long* __restrict__ trace) {
     extern __shared__ double smem_d[];
+    int trn = 0;
+    auto tr = [&]() { if (trace && threadIdx.x == 0 && trn < 64) trace[trn++] = clock64(); };
+    tr();
     const int nblk = n_pad / FS_NB;
     double* SB = smem_d;
     double* XS = SB + (nblk * (nblk + 1) / 2) * FS_BLK;
@@ -106,6 +113,7 @@ chol_small_kernel(double* __restrict__ Hg, int n, int n_pad, const double* __res
         XS[r * xl + j] = (r == n_pres + j) ? 1.0 : 0.0;
     }
     __syncthreads();
+    tr();   // 1: loaded
 
     for (int kb = 0; kb < nblk; ++kb) {
         double* D = SB + fs_blk(kb, kb);
@@ -115,16 +123,18 @@ chol_small_kernel(double* __restrict__ Hg, int n, int n_pad, const double* __res
             bool bad = false;
             for (int j = 0; j < FS_NB; ++j) {
                 // four independent partial sums: the fp64 FMA chain, not the loads, is the critical path here
-                double acc = D[lane * (FS_NB + 1) + j], a1 = 0.0, a2 = 0.0, a3 = 0.0;
+                double acc = D[lane * (FS_NB + 1) + j], a1 = 0.0, a2 = 0.0, a3 = 0.0, a4 = 0.0, a5 = 0.0, a6 = 0.0, a7 = 0.0;
                 const double* ri = D + lane * (FS_NB + 1);
                 const double* rj = D + j * (FS_NB + 1);
                 int k = 0;
-                for (; k + 4 <= j; k += 4) {
+                for (; k + 8 <= j; k += 8) {
                     acc = fma(-ri[k], rj[k], acc); a1 = fma(-ri[k + 1], rj[k + 1], a1);
                     a2 = fma(-ri[k + 2], rj[k + 2], a2); a3 = fma(-ri[k + 3], rj[k + 3], a3);
+                    a4 = fma(-ri[k + 4], rj[k + 4], a4); a5 = fma(-ri[k + 5], rj[k + 5], a5);
+                    a6 = fma(-ri[k + 6], rj[k + 6], a6); a7 = fma(-ri[k + 7], rj[k + 7], a7);
                 }
                 for (; k < j; ++k) acc = fma(-ri[k], rj[k], acc);
-                acc += (a1 + a2) + a3;
+                acc += ((a1 + a2) + (a3 + a4)) + ((a5 + a6) + a7);
                 double d = __shfl_sync(0xffffffffu, acc, j);
                 if (!(d > 0.0)) { bad = true; d = 1.0; }
                 const double y = fs_rsqrt(d);
@@ -135,6 +145,7 @@ chol_small_kernel(double* __restrict__ Hg, int n, int n_pad, const double* __res
             if (bad && lane == 0) atomicCAS(flag, 0, 1 + kb);
         }
         __syncthreads();
+        tr();   // diag block factored
         // (b) inverse of L_kk by column sweeps (warp = column c, lane = row): x_j = (delta_jc - acc_j) / L_jj
         for (int c = warp; c < FS_NB; c += NW) {
             double acc = 0.0, mine = 0.0;
@@ -147,6 +158,7 @@ chol_small_kernel(double* __restrict__ Hg, int n, int n_pad, const double* __res
             if (lane > c) D[c * (FS_NB + 1) + lane] = mine;      // strict upper triangle <- transposed strict lower of L^-1
         }
         __syncthreads();
+        tr();   // inverse done
         const int mb = nblk - kb - 1;                            // block rows below
         if (mb > 0) {
             // (c) panel  L_ik = H_ik L_kk^-T  for the mb blocks below (staged: updated in place)
@@ -175,22 +187,41 @@ chol_small_kernel(double* __restrict__ Hg, int n, int n_pad, const double* __res
             }
             __syncthreads();
             // (d) trailing update of the lower block triangle:  H_ij -= L_ik L_jk^T
+            //     4 x 4 register tiles: 8 shared-memory loads per 16 fp64 FMAs (the update is smem-bandwidth bound otherwise)
             const int npairs = mb * (mb + 1) / 2;
-            for (int idx = tid; idx < npairs * FS_NB * FS_NB; idx += FS_T) {
-                int pr = idx / (FS_NB * FS_NB), ti = 0;
+            for (int idx = tid; idx < npairs * 64; idx += FS_T) {
+                int pr = idx >> 6, ti = 0;
                 while ((ti + 1) * (ti + 2) / 2 <= pr) ++ti;
                 const int tj = pr - ti * (ti + 1) / 2;
-                const int rr = (idx >> 5) & 31, c = idx & 31;
-                if (ti == tj && c > rr) continue;
-                const double* A = SB + fs_blk(kb + 1 + ti, kb) + rr * (FS_NB + 1);
-                const double* B = SB + fs_blk(kb + 1 + tj, kb) + c * (FS_NB + 1);
-                double s2 = 0.0;
-#pragma unroll 8
-                for (int j = 0; j < FS_NB; ++j) s2 = fma(A[j], B[j], s2);
-                SB[fs_blk(kb + 1 + ti, kb + 1 + tj) + rr * (FS_NB + 1) + c] -= s2;
+                const int r0 = ((idx >> 3) & 7) * 4, c0 = (idx & 7) * 4;
+                if (ti == tj && c0 > r0 + 3) continue;
+                const double* A = SB + fs_blk(kb + 1 + ti, kb) + r0 * (FS_NB + 1);
+                const double* B = SB + fs_blk(kb + 1 + tj, kb) + c0 * (FS_NB + 1);
+                double acc[4][4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j2 = 0; j2 < 4; ++j2) acc[i][j2] = 0.0;
+#pragma unroll 4
+                for (int j = 0; j < FS_NB; ++j) {
+                    double a[4], b[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) { a[i] = A[i * (FS_NB + 1) + j]; b[i] = B[i * (FS_NB + 1) + j]; }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+#pragma unroll
+                        for (int j2 = 0; j2 < 4; ++j2) acc[i][j2] = fma(a[i], b[j2], acc[i][j2]);
+                }
+                double* Cb = SB + fs_blk(kb + 1 + ti, kb + 1 + tj);
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j2 = 0; j2 < 4; ++j2)
+                        if (ti != tj || c0 + j2 <= r0 + i) Cb[(r0 + i) * (FS_NB + 1) + c0 + j2] -= acc[i][j2];
             }
             __syncthreads();
         }
+        tr();   // panel + trailing done
     }
     if (write_back) {   // debug: L back to global (row-major [n_pad][n_pad], zeros above the diagonal)
         for (int idx = tid; idx < n_pad * n_pad; idx += FS_T) {
@@ -224,16 +255,22 @@ chol_small_kernel(double* __restrict__ Hg, int n, int n_pad, const double* __res
         }
         __syncthreads();
         const int rest = n_pad - (o + FS_NB);
-        for (int idx = tid; idx < rest * n_edit; idx += FS_T) {
-            const int r = o + FS_NB + idx / n_edit, j = idx % n_edit;
+        for (int idx = tid; idx < (rest / 4) * n_edit; idx += FS_T) {     // 4 rows x 1 rhs column per thread
+            const int r = o + FS_NB + 4 * (idx / n_edit), j = idx % n_edit;
             const double* A = SB + fs_blk(r >> 5, kb) + (r & 31) * (FS_NB + 1);
-            double s2 = 0.0;
-#pragma unroll 8
-            for (int c = 0; c < FS_NB; ++c) s2 = fma(A[c], XS[(o + c) * xl + j], s2);
-            XS[r * xl + j] -= s2;
+            double s4[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll 4
+            for (int c = 0; c < FS_NB; ++c) {
+                const double x = XS[(o + c) * xl + j];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) s4[i] = fma(A[i * (FS_NB + 1) + c], x, s4[i]);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) XS[(r + i) * xl + j] -= s4[i];
         }
         __syncthreads();
     }
+    tr();   // forward substitution done
     // ---- backward substitution  L^T Z = Y ----
     for (int kb = nblk - 1; kb >= 0; --kb) {
         const double* D = SB + fs_blk(kb, kb);
@@ -257,17 +294,25 @@ chol_small_kernel(double* __restrict__ Hg, int n, int n_pad, const double* __res
             if (idx < FS_NB * n_edit) XS[(o + idx / n_edit) * xl + idx % n_edit] = out[it];
         }
         __syncthreads();
-        for (int idx = tid; idx < o * n_edit; idx += FS_T) {
-            const int r = idx / n_edit, j = idx % n_edit;
-            const double* A = SB + fs_blk(kb, r >> 5) + (r & 31);          // L[o + c][r] = block(kb, r/32)[c][r%32]
-            double s2 = 0.0;
-#pragma unroll 8
-            for (int c = 0; c < FS_NB; ++c) s2 = fma(A[c * (FS_NB + 1)], XS[(o + c) * xl + j], s2);
-            XS[r * xl + j] -= s2;
+        for (int idx = tid; idx < (o / 4) * n_edit; idx += FS_T) {        // 4 rows x 1 rhs column per thread
+            const int r = 4 * (idx / n_edit), j = idx % n_edit;
+            const double* A = SB + fs_blk(kb, r >> 5) + (r & 31);          // L[o + c][r + i] = block(kb, r/32)[c][r%32 + i]
+            double s4[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll 4
+            for (int c = 0; c < FS_NB; ++c) {
+                const double x = XS[(o + c) * xl + j];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) s4[i] = fma(A[c * (FS_NB + 1) + i], x, s4[i]);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) XS[(r + i) * xl + j] -= s4[i];
         }
         __syncthreads();
     }
+    tr();   // backward substitution done
     for (int idx = tid; idx < n * n_edit; idx += FS_T) Z[(long)(idx / n_edit) * ldz + idx % n_edit] = XS[(idx / n_edit) * xl + idx % n_edit];
+    __syncthreads();
+    tr();
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -357,8 +402,21 @@ int factor_small(uce_ws* ws, const float* C, const float* G, int n, int n_pres, 
         UCE_CUDA(cudaFuncSetAttribute(chol_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
         conf_c = smem_c;
     }
-    chol_small_kernel<<<1, FS_T, smem_c, st>>>(ws->H, n, n_pad, ws->diag_add, n_pres, n_edit, ws->X, ldz, ws->debug, ws->flag);
+    long long* trace = nullptr;
+    const char* trace_path = getenv("UCE_CHOL_TRACE");
+    if (trace_path) { UCE_CUDA(cudaMalloc(&trace, 64 * sizeof(long long))); UCE_CUDA(cudaMemsetAsync(trace, 0, 64 * sizeof(long long), st)); }
+    chol_small_kernel<<<1, FS_T, smem_c, st>>>(ws->H, n, n_pad, ws->diag_add, n_pres, n_edit, ws->X, ldz, ws->debug, ws->flag, trace);
     UCE_LAUNCH_CHECK(); ++*launches;
+    if (trace) {   // debugging aid: phase boundaries of the single factor CTA (synchronises)
+        long long h[64];
+        UCE_CUDA(cudaStreamSynchronize(st));
+        UCE_CUDA(cudaMemcpy(h, trace, sizeof(h), cudaMemcpyDeviceToHost));
+        UCE_CUDA(cudaFree(trace));
+        if (FILE* f = fopen(trace_path, "w")) {
+            for (int i = 0; i < 64 && h[i]; ++i) fprintf(f, "%d %lld %lld\n", i, h[i] - h[0], i ? h[i] - h[i - 1] : 0LL);
+            fclose(f);
+        }
+    }
     const size_t smem_q = (size_t)n * n_edit * sizeof(double) + (size_t)n * 33 * sizeof(float);
     static size_t conf_q = 0;
     if (conf_q < smem_q) {

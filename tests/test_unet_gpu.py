@@ -135,3 +135,41 @@ def test_sd14_shapes_forward_matches_oracle():
     print("SD-1.4 per-tap relative error:", {k: round(v, 4) for k, v in rep.items()})
     assert rep["eps"] < 5e-2 and torch.isfinite(out).all(), rep
     eng.close()
+
+
+def test_batch8_images_per_prompt():
+    """BASELINE config 5 uses --num_images_per_prompt 8 (16 samples per U-Net call): batch handling of every kernel
+    (image index of the time-embedding bias, attention batching, conv rectangles spanning images)."""
+    from uce_b200.unet import UNetEngine
+    cfg, P = _tiny()
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(16, 4, 16, 16, generator=g)
+    ctx = torch.randn(16, 77, cfg["cross_attention_dim"], generator=g)
+    ref = U.unet_forward(P, x, 321.0, ctx, cfg)
+    eng = UNetEngine(cfg, batch=16, H=16, W=16)
+    eng.load_state_dict(P)
+    eng.finalize()
+    out = eng.forward(x.cuda(), 321.0, ctx.cuda()).cpu()
+    per_sample = [_rel(out[i], ref[i]) for i in range(16)]
+    assert max(per_sample) < 5e-2, per_sample
+    eng.close()
+
+
+def test_edited_weights_overlay_changes_only_attn2():
+    """set_weight after finalize (load_state_dict(strict=False) of the UCE artifact) takes effect in place."""
+    from uce_b200.unet import UNetEngine
+    cfg, P = _tiny()
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(2, 4, 16, 16, generator=g)
+    ctx = torch.randn(2, 77, cfg["cross_attention_dim"], generator=g)
+    eng = UNetEngine(cfg, batch=2, H=16, W=16)
+    eng.load_state_dict(P)
+    eng.finalize()
+    base = eng.forward(x.cuda(), 500.0, ctx.cuda()).cpu()
+    key = "mid_block.attentions.0.transformer_blocks.0.attn2.to_v.weight"
+    eng.load_state_dict({key: P[key] * -1.0, "not.a.unet.key": torch.zeros(1)}, strict=False)
+    P2 = dict(P); P2[key] = P[key] * -1.0
+    ref = U.unet_forward(P2, x, 500.0, ctx, cfg)
+    out = eng.forward(x.cuda(), 500.0, ctx.cuda()).cpu()
+    assert _rel(out, ref) < 5e-2 and _rel(out, base) > 1e-3
+    eng.close()

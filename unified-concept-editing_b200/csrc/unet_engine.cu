@@ -5,11 +5,13 @@
 #include "../../include/sd_unet_b200.h"
 #include "unet_gemm.h"
 #include "unet_ops.h"
+#include "unet_attn.h"
 #include <cuda_bf16.h>
 #include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <functional>
 #include <map>
 #include <string>
@@ -34,7 +36,7 @@ int pad64(int x) { return (x + 63) / 64 * 64; }
 
 struct sd_unet {
     sd_unet_config cfg;
-    int device, NB, H, W, sm_count = 148, n_split = 0;
+    int device, NB, H, W, sm_count = 148, n_split = 0, n_fused_attn = 0;
     bool finalized = false;
     std::map<std::string, Weight> w;
     std::map<std::string, std::vector<long>> expected;          // name -> shape
@@ -223,6 +225,13 @@ struct Builder {
             g.out = vt; g.out_fp32 = 0; g.ldo = Lkp; g.out_b1_stride = (long)HD * Lkp;
             gemm(g);
         }
+        const bool fused = uce::attn_fused_supported(dhp) && !getenv("UCE_NO_FLASH");
+        if (fused) {   // flash-style kernel: no score matrix in HBM
+            uce::AttnDesc ad;
+            if (uce::attn_desc_make(&ad, q, k, vt, o, NB, heads, dhp, L, Lk, Lkp, 1.f / sqrtf((float)dh))) { rc = rc ? rc : SD_E_STATE; sd_err("attention tensor maps failed"); return; }
+            push([ad](cudaStream_t st) { return uce::attn_launch(ad, st); });
+            ++u->n_fused_attn;
+        } else {
         float* S = u->S_scratch; bf16* P = u->P_scratch;
         {   // S[b,h] [L, Lk] = q[b,:,h] k[b,:,h]^T / sqrt(dh)
             GemmDesc g;
@@ -238,6 +247,7 @@ struct Builder {
             if (uce::gemm_desc_linear(&g, P, Lkp, L * Lkp, (long)heads * L * Lkp, vt, Lkp, (long)dhp * Lkp, (long)HD * Lkp, (int)L, dhp, Lk, heads, NB, 1, 1)) { rc = rc ? rc : SD_E_STATE; return; }
             g.out = o; g.out_fp32 = 0; g.ldo = HD; g.out_b1_stride = dhp; g.out_b2_stride = L * HD;
             gemm(g);
+        }
         }
         // h += o Wo^T + bias   (in place: every element is read then written by the same thread)
         {

@@ -281,10 +281,22 @@ def run_ours(args, rank, world, local_rank):
         peak_bw, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)") if "hbm_gbs" in peaks else (6650.0, "fallback (B200_PROFILING.md)")
         # algorithmic bytes of the apply: read W_old once + write W_new once (fp32) + E and Q once
         alg_bytes = 2 * w_bytes + 2 * 4 * K * max(info["rank"], 1)
+        traffic, traffic_src = None, None          # DRAM bytes of one launch from the committed ncu --set full capture of this command
+        try:
+            prof = os.path.join(ROOT, "profiles", "r01_apply_tc_ncu.txt")
+            vals = {}
+            for ln in open(prof):
+                f = ln.split()
+                if len(f) >= 3 and f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                    vals[f[0]] = float(f[1]) * {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}[f[2]]
+            if len(vals) == 2 and args.workload == "cfg2":
+                traffic, traffic_src = sum(vals.values()), "profiles/r01_apply_tc_ncu.txt (dram__bytes_read.sum + dram__bytes_write.sum; the written tile partly stays in L2 at kernel end)"
+        except Exception:
+            pass
         dom_ms = a1_ms + a2_ms
         achieved = alg_bytes / (dom_ms / 1e3) / 1e9
         roof = {"bound": "hbm", "kernel": "apply (W_new = W_old + (W_old E^T) Q over all projections)", "achieved": achieved,
-                "peak": peak_bw, "unit": "GB/s", "frac": achieved / peak_bw, "traffic": None, "peak_source": peak_src,
+                "peak": peak_bw, "unit": "GB/s", "frac": achieved / peak_bw, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "algorithmic_bytes": alg_bytes, "kernel_ms": dom_ms, "stage_ms": [a1_ms, a2_ms], "factor_ms": f_ms}
         cpu = None
         if not args.no_cpu:

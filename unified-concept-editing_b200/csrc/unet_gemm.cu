@@ -10,8 +10,7 @@
 //   coordinates are zero-filled by the TMA unit (= the conv padding), stride 2 uses the tensor map's element
 //   strides.  Weights are stored tap-major [Cout][ky][kx][Cin].
 // * warp roles: warp 0 TMA producer, warp 1 MMA issuer (+TMEM alloc), warps 2-5 epilogue (TMEM -> registers ->
-//   bias / time-embedding / residual -> bf16 or fp32 global stores).  96 KB smem -> two CTAs per SM overlap each
-//   other's epilogues.
+//   bias / time-embedding / residual -> bf16 or fp32 global stores).
 #include "tc_common.cuh"
 #include "unet_gemm.h"
 #include <cuda_bf16.h>
@@ -19,19 +18,20 @@
 namespace uce {
 using namespace tc;
 
-constexpr int UG_BM = 128, UG_BN = 128, UG_BK = 64, UG_STAGES = 3;
+constexpr int UG_BM = 128, UG_BN = 128, UG_BK = 64, UG_MAX_STAGES = 6;
 constexpr int UG_THREADS = 192;
 constexpr int UG_STAGE_BYTES = (UG_BM + UG_BN) * UG_BK * 2;     // 32 KB
-constexpr int UG_SMEM = UG_STAGES * UG_STAGE_BYTES + 1024 + 256;
+inline int ug_smem_bytes(int stages) { return stages * UG_STAGE_BYTES + 1024 + 256; }
 
 __global__ void __launch_bounds__(UG_THREADS, 2) unet_gemm_kernel(const __grid_constant__ GemmDesc g) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t bars = base + UG_STAGES * UG_STAGE_BYTES;
+    const int NS = g.stages;
+    const uint32_t bars = base + NS * UG_STAGE_BYTES;
     auto bar_full = [&](int s) { return bars + 8u * s; };
-    auto bar_empty = [&](int s) { return bars + 8u * (UG_STAGES + s); };
-    const uint32_t bar_acc = bars + 8u * (2 * UG_STAGES);
-    const uint32_t tmem_slot = bars + 8u * (2 * UG_STAGES + 1);
+    auto bar_empty = [&](int s) { return bars + 8u * (UG_MAX_STAGES + s); };
+    const uint32_t bar_acc = bars + 8u * (2 * UG_MAX_STAGES);
+    const uint32_t tmem_slot = bars + 8u * (2 * UG_MAX_STAGES + 1);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     const int n_tile = blockIdx.x, m_tile = blockIdx.y;
@@ -54,7 +54,7 @@ __global__ void __launch_bounds__(UG_THREADS, 2) unet_gemm_kernel(const __grid_c
     }
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < UG_STAGES; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1); }
+        for (int s = 0; s < NS; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1); }
         mbar_init(bar_acc, 1);
         mbar_fence_init();
         tma_prefetch_desc(&g.tmA); tma_prefetch_desc(&g.tmB);
@@ -69,8 +69,8 @@ __global__ void __launch_bounds__(UG_THREADS, 2) unet_gemm_kernel(const __grid_c
     if (warp == 0) {
         if (lane == 0) {
             for (int it = 0; it < n_k; ++it) {
-                const int s = it % UG_STAGES;
-                mbar_wait(bar_empty(s), (uint32_t)(((it / UG_STAGES) & 1) ^ 1));
+                const int s = it % NS;
+                mbar_wait(bar_empty(s), (uint32_t)(((it / NS) & 1) ^ 1));
                 const uint32_t a_dst = base + s * UG_STAGE_BYTES, b_dst = a_dst + UG_BM * UG_BK * 2;
                 mbar_arrive_expect_tx(bar_full(s), (uint32_t)(g.a_bytes + UG_BN * UG_BK * 2));
                 const int kit = k_begin + it;
@@ -86,10 +86,14 @@ __global__ void __launch_bounds__(UG_THREADS, 2) unet_gemm_kernel(const __grid_c
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            const uint32_t idesc = idesc_bf16(UG_BM, UG_BN);
+            // N of this tile's MMAs = the valid columns rounded up to 16 (a 128 x 256 tile variant was measured and was not
+            // faster end to end: fewer CTAs on the many under-filled grids of the U-Net offset the cheaper issue)
+            int n_valid = g.N - n_tile * UG_BN;
+            n_valid = n_valid >= UG_BN ? UG_BN : ((n_valid + 15) & ~15);
+            const uint32_t idesc = idesc_bf16(UG_BM, n_valid);
             for (int it = 0; it < n_k; ++it) {
-                const int s = it % UG_STAGES;
-                mbar_wait(bar_full(s), (uint32_t)((it / UG_STAGES) & 1));
+                const int s = it % NS;
+                mbar_wait(bar_full(s), (uint32_t)((it / NS) & 1));
                 fence_after();
                 const uint64_t a_desc = umma_desc_sw128(base + s * UG_STAGE_BYTES);
                 const uint64_t b_desc = umma_desc_sw128(base + s * UG_STAGE_BYTES + UG_BM * UG_BK * 2);
@@ -284,6 +288,12 @@ __global__ void __launch_bounds__(256) splitk_finalize_kernel(GemmDesc g, int ro
     }
 }
 
+// Under-filled grids (at most one CTA per SM) take the deep pipeline; grids with >= 2 CTAs per SM keep 3 stages each.
+int gemm_choose_stages(const GemmDesc& g, int sm_count) {
+    const long ctas = (long)((g.N + UG_BN - 1) / UG_BN) * g.m_tiles * (g.ksplit > 1 ? g.ksplit : g.batch);
+    return ctas <= (long)sm_count + sm_count / 4 ? UG_MAX_STAGES : 3;
+}
+
 int gemm_choose_ksplit(const GemmDesc& g, int sm_count) {
     if (g.batch != 1 || (g.N % 4)) return 1;
     const int ctas = ((g.N + UG_BN - 1) / UG_BN) * g.m_tiles;
@@ -299,12 +309,14 @@ int gemm_choose_ksplit(const GemmDesc& g, int sm_count) {
 int gemm_launch(const GemmDesc& g, cudaStream_t st) {
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(unet_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, UG_SMEM);
+        cudaError_t e = cudaFuncSetAttribute(unet_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ug_smem_bytes(UG_MAX_STAGES));
         if (e != cudaSuccess) return (int)e;
         configured = true;
     }
     dim3 grid((g.N + UG_BN - 1) / UG_BN, g.m_tiles, g.ksplit > 1 ? g.ksplit : g.batch);
-    unet_gemm_kernel<<<grid, UG_THREADS, UG_SMEM, st>>>(g);
+    const int stages = g.stages >= 2 && g.stages <= UG_MAX_STAGES ? g.stages : 3;
+    GemmDesc gg = g; gg.stages = stages;
+    unet_gemm_kernel<<<grid, UG_THREADS, ug_smem_bytes(stages), st>>>(gg);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
     if (g.ksplit > 1) {

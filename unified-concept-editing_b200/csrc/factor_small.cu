@@ -187,6 +187,8 @@ chol_small_kernel(double* __restrict__ Hg, int n, int n_pad, const double* __res
             }
             __syncthreads();
             // (d) trailing update of the lower block triangle:  H_ij -= L_ik L_jk^T
+            //     (a lookahead variant — warp 0 factoring the next diagonal block meanwhile — was measured and was slower:
+            //      a single warp of fp64 work is latency-bound either way)
             //     4 x 4 register tiles: 8 shared-memory loads per 16 fp64 FMAs (the update is smem-bandwidth bound otherwise)
             const int npairs = mb * (mb + 1) / 2;
             for (int idx = tid; idx < npairs * 64; idx += FS_T) {
@@ -317,33 +319,34 @@ chol_small_kernel(double* __restrict__ Hg, int n, int n_pad, const double* __res
 
 // ---------------------------------------------------------------------------------------------------------
 // Q[j, k] = sum_r Z[r, j] Cp[r, k]  (fp64 accumulate), emitted as Q, Qt and the tf32 hi/lo splits of Qt.
-// grid: K / 32 column tiles; 256 threads; Z staged in shared memory.
+// grid (K / 32 column tiles, r_pad / 8 row groups); 256 threads = 8 rows of Q x 32 columns; the 8 needed columns of Z and
+// the 32 needed columns of Cp are staged in shared memory.
 __global__ void __launch_bounds__(256) q_emit_kernel(const double* __restrict__ Z, int ldz, const float* __restrict__ Cp, int n,
                                                      int n_edit, int r_pad, int K, float* __restrict__ Q, float* __restrict__ Qt,
                                                      float* __restrict__ Qt_hi, float* __restrict__ Qt_lo) {
-    extern __shared__ double Zs[];                    // [n][n_edit]
-    float* Cs = reinterpret_cast<float*>(Zs + (size_t)n * n_edit);   // [n][33]
-    const int k0 = blockIdx.x * 32, tid = threadIdx.x;
-    for (int idx = tid; idx < n * n_edit; idx += 256) Zs[idx] = Z[(long)(idx / n_edit) * ldz + idx % n_edit];
+    __shared__ double Zs[FS_MAX_N][8];
+    __shared__ float Cs[FS_MAX_N][33];
+    const int k0 = blockIdx.x * 32, j0 = blockIdx.y * 8, tid = threadIdx.x;
+    for (int idx = tid; idx < n * 8; idx += 256) {
+        const int r = idx >> 3, jj = idx & 7;
+        Zs[r][jj] = (j0 + jj < n_edit) ? Z[(long)r * ldz + j0 + jj] : 0.0;
+    }
     for (int idx = tid; idx < n * 32; idx += 256) {
         const int r = idx / 32, c = idx % 32;
-        Cs[r * 33 + c] = (k0 + c < K) ? Cp[(long)r * K + k0 + c] : 0.f;
+        Cs[r][c] = (k0 + c < K) ? Cp[(long)r * K + k0 + c] : 0.f;
     }
     __syncthreads();
-    const int c = tid % 32;
-    for (int j = tid / 32; j < r_pad; j += 8) {
-        double s = 0.0;
-        if (j < n_edit) {
-#pragma unroll 4
-            for (int r = 0; r < n; ++r) s = fma(Zs[r * n_edit + j], (double)Cs[r * 33 + c], s);
-        }
-        const float v = (float)s;
-        if (k0 + c < K) {
-            Q[(long)j * K + k0 + c] = v;
-            const long t = (long)(k0 + c) * r_pad + j;
-            const float h = fs_tf32_hi(v);
-            Qt[t] = v; Qt_hi[t] = h; Qt_lo[t] = v - h;
-        }
+    const int c = tid % 32, jj = tid / 32, j = j0 + jj;
+    double s0 = 0.0, s1 = 0.0;
+    int r = 0;
+    for (; r + 2 <= n; r += 2) { s0 = fma(Zs[r][jj], (double)Cs[r][c], s0); s1 = fma(Zs[r + 1][jj], (double)Cs[r + 1][c], s1); }
+    if (r < n) s0 = fma(Zs[r][jj], (double)Cs[r][c], s0);
+    const float v = (float)(s0 + s1);      // rows j >= n_edit (rank padding) come out as exact zeros
+    if (k0 + c < K && j < r_pad) {
+        Q[(long)j * K + k0 + c] = v;
+        const long t = (long)(k0 + c) * r_pad + j;
+        const float h = fs_tf32_hi(v);
+        Qt[t] = v; Qt_hi[t] = h; Qt_lo[t] = v - h;
     }
 }
 
@@ -417,13 +420,7 @@ int factor_small(uce_ws* ws, const float* C, const float* G, int n, int n_pres, 
             fclose(f);
         }
     }
-    const size_t smem_q = (size_t)n * n_edit * sizeof(double) + (size_t)n * 33 * sizeof(float);
-    static size_t conf_q = 0;
-    if (conf_q < smem_q) {
-        UCE_CUDA(cudaFuncSetAttribute(q_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_q));
-        conf_q = smem_q;
-    }
-    q_emit_kernel<<<ceil_div(K, 32), 256, smem_q, st>>>(ws->X, ldz, ws->Cp, n, n_edit, ws->rank_pad, K, ws->Q, ws->Qt, ws->Qt_hi, ws->Qt_lo);
+    q_emit_kernel<<<dim3(ceil_div(K, 32), ws->rank_pad / 8), 256, 0, st>>>(ws->X, ldz, ws->Cp, n, n_edit, ws->rank_pad, K, ws->Q, ws->Qt, ws->Qt_hi, ws->Qt_lo);
     UCE_LAUNCH_CHECK(); ++*launches;
     return 0;
 }

@@ -157,7 +157,7 @@ struct Builder {
             g.ksplit = ks; g.splitk_ws = ws;
             ++u->n_split;
         }
-        g.stages = uce::gemm_choose_stages(g, u->sm_count);
+        g.stages = uce::gemm_choose_stages(g, u->sm_count, &g.katoms);
         push([g](cudaStream_t st) { return uce::gemm_launch(g, st); });
     }
 

@@ -20,14 +20,15 @@ using namespace tc;
 
 constexpr int UG_BM = 128, UG_BN = 128, UG_BK = 64, UG_MAX_STAGES = 6;
 constexpr int UG_THREADS = 192;
-constexpr int UG_STAGE_BYTES = (UG_BM + UG_BN) * UG_BK * 2;     // 32 KB
-inline int ug_smem_bytes(int stages) { return stages * UG_STAGE_BYTES + 1024 + 256; }
+constexpr int UG_ATOM_BYTES = (UG_BM + UG_BN) * UG_BK * 2;      // 32 KB: one 64-wide k atom of A and of B
+inline int ug_smem_bytes(int stages, int katoms) { return stages * katoms * UG_ATOM_BYTES + 1024 + 256; }
 
 __global__ void __launch_bounds__(UG_THREADS, 2) unet_gemm_kernel(const __grid_constant__ GemmDesc g) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const int NS = g.stages;
-    const uint32_t bars = base + NS * UG_STAGE_BYTES;
+    const int NS = g.stages, KA = g.katoms;
+    const int stage_bytes = KA * UG_ATOM_BYTES;
+    const uint32_t bars = base + NS * stage_bytes;
     auto bar_full = [&](int s) { return bars + 8u * s; };
     auto bar_empty = [&](int s) { return bars + 8u * (UG_MAX_STAGES + s); };
     const uint32_t bar_acc = bars + 8u * (2 * UG_MAX_STAGES);
@@ -41,7 +42,8 @@ __global__ void __launch_bounds__(UG_THREADS, 2) unet_gemm_kernel(const __grid_c
     const int n_k_total = g.taps * kpt;
     const int k_begin = (g.ksplit > 1) ? (int)((long)n_k_total * zk / g.ksplit) : 0;
     const int k_end = (g.ksplit > 1) ? (int)((long)n_k_total * (zk + 1) / g.ksplit) : n_k_total;
-    const int n_k = k_end - k_begin;
+    const int n_atoms = k_end - k_begin;                   // 64-wide k atoms of this CTA
+    const int n_k = (n_atoms + KA - 1) / KA;               // pipeline iterations
 
     // conv: decode the output rectangle of this m-tile
     int img0 = 0, h0 = 0, w0 = 0;
@@ -71,17 +73,21 @@ __global__ void __launch_bounds__(UG_THREADS, 2) unet_gemm_kernel(const __grid_c
             for (int it = 0; it < n_k; ++it) {
                 const int s = it % NS;
                 mbar_wait(bar_empty(s), (uint32_t)(((it / NS) & 1) ^ 1));
-                const uint32_t a_dst = base + s * UG_STAGE_BYTES, b_dst = a_dst + UG_BM * UG_BK * 2;
-                mbar_arrive_expect_tx(bar_full(s), (uint32_t)(g.a_bytes + UG_BN * UG_BK * 2));
-                const int kit = k_begin + it;
-                const int tap = kit / kpt, c0 = (kit % kpt) * UG_BK;
-                if (g.conv) {
-                    const int ky = tap / 3, kx = tap % 3;
-                    tma_load_4d(a_dst, &g.tmA, bar_full(s), c0, w0 * g.stride + kx - g.pad, h0 * g.stride + ky - g.pad, img0);
-                } else {
-                    tma_load_4d(a_dst, &g.tmA, bar_full(s), c0, m_tile * UG_BM, g.a_batched ? b1 : 0, g.a_batched ? b2 : 0);
+                const int na = min(KA, n_atoms - it * KA);
+                mbar_arrive_expect_tx(bar_full(s), (uint32_t)(na * (g.a_bytes + UG_BN * UG_BK * 2)));
+                for (int a = 0; a < na; ++a) {
+                    const uint32_t a_dst = base + s * stage_bytes + a * (UG_BM * UG_BK * 2);
+                    const uint32_t b_dst = base + s * stage_bytes + KA * (UG_BM * UG_BK * 2) + a * (UG_BN * UG_BK * 2);
+                    const int kit = k_begin + it * KA + a;
+                    const int tap = kit / kpt, c0 = (kit % kpt) * UG_BK;
+                    if (g.conv) {
+                        const int ky = tap / 3, kx = tap % 3;
+                        tma_load_4d(a_dst, &g.tmA, bar_full(s), c0, w0 * g.stride + kx - g.pad, h0 * g.stride + ky - g.pad, img0);
+                    } else {
+                        tma_load_4d(a_dst, &g.tmA, bar_full(s), c0, m_tile * UG_BM, g.a_batched ? b1 : 0, g.a_batched ? b2 : 0);
+                    }
+                    tma_load_4d(b_dst, &g.tmB, bar_full(s), tap * g.cin + c0, n_tile * UG_BN, g.b_batched ? b1 : 0, g.b_batched ? b2 : 0);
                 }
-                tma_load_4d(b_dst, &g.tmB, bar_full(s), tap * g.cin + c0, n_tile * UG_BN, g.b_batched ? b1 : 0, g.b_batched ? b2 : 0);
             }
         }
     } else if (warp == 1) {
@@ -95,11 +101,14 @@ __global__ void __launch_bounds__(UG_THREADS, 2) unet_gemm_kernel(const __grid_c
                 const int s = it % NS;
                 mbar_wait(bar_full(s), (uint32_t)((it / NS) & 1));
                 fence_after();
-                const uint64_t a_desc = umma_desc_sw128(base + s * UG_STAGE_BYTES);
-                const uint64_t b_desc = umma_desc_sw128(base + s * UG_STAGE_BYTES + UG_BM * UG_BK * 2);
+                const int na = min(KA, n_atoms - it * KA);
+                for (int a = 0; a < na; ++a) {
+                    const uint64_t a_desc = umma_desc_sw128(base + s * stage_bytes + a * (UG_BM * UG_BK * 2));
+                    const uint64_t b_desc = umma_desc_sw128(base + s * stage_bytes + KA * (UG_BM * UG_BK * 2) + a * (UG_BN * UG_BK * 2));
 #pragma unroll
-                for (int k = 0; k < UG_BK / 16; ++k)
-                    umma_bf16(tmem_base, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (it | k) != 0);
+                    for (int k = 0; k < UG_BK / 16; ++k)
+                        umma_bf16(tmem_base, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (it | a | k) != 0);
+                }
                 umma_commit(bar_empty(s));
             }
             umma_commit(bar_acc);
@@ -288,9 +297,14 @@ __global__ void __launch_bounds__(256) splitk_finalize_kernel(GemmDesc g, int ro
     }
 }
 
-// Under-filled grids (at most one CTA per SM) take the deep pipeline; grids with >= 2 CTAs per SM keep 3 stages each.
-int gemm_choose_stages(const GemmDesc& g, int sm_count) {
+// Pipeline shape.  Measured on the SD-1.4 schedule (profiles/): neither a deeper pipeline (6 stages), nor two k atoms per
+// barrier round trip, nor 128 x 256 tiles changed the end-to-end step time — the mid-size GEMMs of the U-Net (80-320 CTAs of
+// 128 x 128 tiles streaming 32 KB per k-iteration) sit at ~8 TB/s of L2->SM operand traffic.  Raising the arithmetic
+// intensity per L2 byte (2-CTA tcgen05.mma with multicast TMA) is the next step; until then: 3 single-atom stages with two
+// CTAs per SM for full grids, 6 stages for under-filled ones.
+int gemm_choose_stages(const GemmDesc& g, int sm_count, int* katoms) {
     const long ctas = (long)((g.N + UG_BN - 1) / UG_BN) * g.m_tiles * (g.ksplit > 1 ? g.ksplit : g.batch);
+    *katoms = 1;
     return ctas <= (long)sm_count + sm_count / 4 ? UG_MAX_STAGES : 3;
 }
 
@@ -309,14 +323,15 @@ int gemm_choose_ksplit(const GemmDesc& g, int sm_count) {
 int gemm_launch(const GemmDesc& g, cudaStream_t st) {
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(unet_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ug_smem_bytes(UG_MAX_STAGES));
+        cudaError_t e = cudaFuncSetAttribute(unet_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ug_smem_bytes(UG_MAX_STAGES, 1));
         if (e != cudaSuccess) return (int)e;
         configured = true;
     }
     dim3 grid((g.N + UG_BN - 1) / UG_BN, g.m_tiles, g.ksplit > 1 ? g.ksplit : g.batch);
-    const int stages = g.stages >= 2 && g.stages <= UG_MAX_STAGES ? g.stages : 3;
-    GemmDesc gg = g; gg.stages = stages;
-    unet_gemm_kernel<<<grid, UG_THREADS, ug_smem_bytes(stages), st>>>(gg);
+    GemmDesc gg = g;
+    gg.katoms = (g.katoms == 2) ? 2 : 1;
+    gg.stages = (g.stages >= 2 && g.stages * gg.katoms <= UG_MAX_STAGES) ? g.stages : 3;
+    unet_gemm_kernel<<<grid, UG_THREADS, ug_smem_bytes(gg.stages, gg.katoms), st>>>(gg);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
     if (g.ksplit > 1) {

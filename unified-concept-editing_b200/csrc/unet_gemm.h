@@ -18,6 +18,7 @@ struct GemmDesc {
     int tile_rows;             // valid rows of an A tile (conv rectangles smaller than 128 pixels), else 128
     int a_bytes;               // bytes one A-tile TMA delivers (expect_tx)
     int rows_per_img;          // linear: image index of a row = row / rows_per_img (for rowbias); 0 = none
+    int katoms;                // 64-wide k atoms per pipeline stage (1 or 2): 2 halves the barrier round trips of the single MMA thread
     int stages;                // TMA->MMA pipeline depth (3: two CTAs per SM; 6: one CTA per SM, hides the TMA latency of under-filled grids)
     int ksplit;                // > 1: the k loop is split over grid.z; partial sums are atomically added into splitk_ws (fp32 [M,N])
     float* splitk_ws;          // zero on entry; gemm_splitk_finalize applies the epilogue and re-zeroes it
@@ -36,6 +37,6 @@ int gemm_desc_conv(GemmDesc* g, const void* act_nhwc, int NB, int Hin, int Win, 
 int gemm_launch(const GemmDesc& g, cudaStream_t st);
 // Picks a split factor for under-filled grids (batch == 1 only); returns it (1 = no split).
 int gemm_choose_ksplit(const GemmDesc& g, int sm_count);
-int gemm_choose_stages(const GemmDesc& g, int sm_count);
+int gemm_choose_stages(const GemmDesc& g, int sm_count, int* katoms);
 
 }  // namespace uce

@@ -1,4 +1,4 @@
-"""Two eager SD-1.4-shaped U-Net calls (for an ncu launch list)."""
+"""Two eager SD-1.4-shaped U-Net calls; the second one is bracketed by cudaProfilerStart/Stop (for an ncu launch list)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -9,7 +9,10 @@ state = unet_random_state(SD14, seed=0)
 eng = UNetEngine(SD14, batch=2, H=64, W=64)
 eng.load_state_dict(state); eng.finalize()
 x = torch.randn(2, 4, 64, 64).cuda(); ctx = torch.randn(2, 77, 768).cuda()
-for _ in range(2):
-    out = eng.forward(x, 481.0, ctx)
+out = eng.forward(x, 481.0, ctx)
 torch.cuda.synchronize()
+torch.cuda.profiler.start()          # ncu --profile-from-start off: exactly one U-Net call is listed
+out = eng.forward(x, 481.0, ctx)
+torch.cuda.synchronize()
+torch.cuda.profiler.stop()
 print("ok", float(out.abs().mean()))

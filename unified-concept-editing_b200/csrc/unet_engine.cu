@@ -46,6 +46,8 @@ struct sd_unet {
     // fixed I/O buffers
     float* x_in = nullptr; float* ctx_f32 = nullptr; bf16* ctx = nullptr; float* eps = nullptr;
     float* d_t = nullptr; float* h_t = nullptr;
+    float* splitk_ws = nullptr; size_t splitk_cap = 0;
+    static constexpr int MAX_GN = 256; int n_gn = 0;
     float* gn_stats = nullptr; float* S_scratch = nullptr; bf16* P_scratch = nullptr;
     bf16* temb_tap = nullptr;
 
@@ -149,12 +151,10 @@ struct Builder {
     const Weight& W(const std::string& n) { return u->w.at(n); }
     void push(std::function<int(cudaStream_t)> f) { u->ops.push_back(std::move(f)); }
     void gemm(GemmDesc g) {
-        const int ks = uce::gemm_choose_ksplit(g, u->sm_count);
-        if (ks > 1) {
-            float* ws = nullptr;
-            if (!rc) rc = u->alloc(&ws, (size_t)g.M * g.N);
-            if (!rc && cudaMemset(ws, 0, (size_t)g.M * g.N * sizeof(float)) != cudaSuccess) rc = SD_E_STATE;
-            g.ksplit = ks; g.splitk_ws = ws;
+        int ks = uce::gemm_choose_ksplit(g, u->sm_count);
+        while (ks > 1 && (size_t)ks * g.M * g.N > u->splitk_cap) --ks;
+        if (ks > 1) {                         // every split GEMM shares one scratch: the schedule is a single in-order stream
+            g.ksplit = ks; g.splitk_ws = u->splitk_ws;
             ++u->n_split;
         }
         g.stages = uce::gemm_choose_stages(g, u->sm_count, &g.katoms);
@@ -180,7 +180,9 @@ struct Builder {
     }
     void groupnorm(const Act& x, const Act& y, const std::string& p, float eps, int silu) {
         const float* ga = W(p + ".weight").f; const float* be = W(p + ".bias").f;
-        float* stats = u->gn_stats; const int G = u->cfg.norm_groups;
+        const int G = u->cfg.norm_groups;
+        if (u->n_gn >= sd_unet::MAX_GN) { rc = rc ? rc : SD_E_STATE; sd_err("too many GroupNorm calls"); return; }
+        float* stats = u->gn_stats + (size_t)(u->n_gn++) * u->NB * G * 2;      // own slice; all cleared by one memset per forward
         push([=](cudaStream_t st) { return uce::op_groupnorm(x.p, y.p, x.n, x.h * x.w, x.c, G, stats, ga, be, eps, silu, st); });
     }
     void layernorm(const bf16* x, bf16* y, long rows, int C, const std::string& p) {
@@ -310,7 +312,9 @@ int build_schedule(sd_unet* u) {
     if ((rc = u->alloc(&u->eps, (size_t)NB * c.out_channels * H * W))) return rc;
     if ((rc = u->alloc(&u->d_t, 4))) return rc;
     SD_CUDA(cudaMallocHost((void**)&u->h_t, sizeof(float)));
-    if ((rc = u->alloc(&u->gn_stats, (size_t)NB * c.norm_groups * 2))) return rc;
+    if ((rc = u->alloc(&u->gn_stats, (size_t)sd_unet::MAX_GN * NB * c.norm_groups * 2))) return rc;
+    u->splitk_cap = (size_t)(3 * u->sm_count) * 128 * 128;      // gemm_choose_ksplit targets ~2 CTAs per SM of 128 x 128 partial tiles
+    if ((rc = u->alloc(&u->splitk_ws, u->splitk_cap))) return rc;
     {   // attention scratch: largest (L x Lk) over the attention levels
         size_t mx = 0;
         for (int i = 0; i < nl; ++i) {
@@ -322,6 +326,7 @@ int build_schedule(sd_unet* u) {
         if ((rc = u->alloc(&u->P_scratch, (size_t)NB * c.heads * mx))) return rc;
     }
     // ---- inputs ----
+    B.push([u](cudaStream_t st) { return (int)cudaMemsetAsync(u->gn_stats, 0, (size_t)u->n_gn * u->NB * u->cfg.norm_groups * 2 * sizeof(float), st); });
     {
         float* cf = u->ctx_f32; bf16* cb = u->ctx; const long n = (long)NB * c.context_len * c.cross_attention_dim;
         B.push([=](cudaStream_t st) { f32_to_bf16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(cf, cb, n); return (int)cudaGetLastError(); });

@@ -147,10 +147,16 @@ __global__ void __launch_bounds__(UG_THREADS, 2) unet_gemm_kernel(const __grid_c
             for (int i = 0; i < 32; ++i) f[i] = g.alpha * __uint_as_float(v[i]);
             const int n0 = n_base + c;
             const bool full = (n0 + 32 <= g.N);
-            if (g.ksplit > 1) {            // partial sum of this k range; the epilogue terms are applied by the finalize pass
-                float* wp = g.splitk_ws + row * (long)g.N + n0;
+            if (g.ksplit > 1) {            // partial sum of this k range -> its own slab; the finalize pass sums the slabs in a
+                                           // fixed order (deterministic, unlike atomics) and applies the epilogue terms
+                float* wp = g.splitk_ws + ((long)zk * g.M + row) * (long)g.N + n0;
+                if (full) {                // N % 4 == 0 is a precondition of splitting
 #pragma unroll
-                for (int i = 0; i < 32; ++i) if (full || n0 + i < g.N) atomicAdd(wp + i, f[i]);
+                    for (int j = 0; j < 8; ++j) *reinterpret_cast<float4*>(wp + 4 * j) = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) if (n0 + i < g.N) wp[i] = f[i];
+                }
                 continue;
             }
             if (g.bias) {
@@ -275,17 +281,22 @@ int gemm_desc_conv(GemmDesc* g, const void* act_nhwc, int NB, int Hin, int Win, 
     return 0;
 }
 
-// out = ws (+bias) (+rowbias[img]) (+residual); ws <- 0.  One thread per 4 consecutive columns.
+// out = sum_z ws[z] (+bias) (+rowbias[img]) (+residual).  One thread per 4 consecutive columns.
 __global__ void __launch_bounds__(256) splitk_finalize_kernel(GemmDesc g, int rows_per_img) {
     const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
     const int nv = g.N / 4;
     if (idx >= (long)g.M * nv) return;
     const long row = idx / nv; const int n0 = (int)(idx % nv) * 4;
-    float4* wp = reinterpret_cast<float4*>(g.splitk_ws + row * g.N + n0);
-    float4 v = *wp;
-    *wp = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float* wp = g.splitk_ws + row * g.N + n0;
+    const long slab = (long)g.M * g.N;
+    float4 v = *reinterpret_cast<const float4*>(wp);
+#pragma unroll 4
+    for (int z = 1; z < g.ksplit; ++z) {
+        const float4 t = *reinterpret_cast<const float4*>(wp + z * slab);
+        v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
+    }
     float f[4] = {v.x, v.y, v.z, v.w};
-    if (g.bias) { for (int i = 0; i < 4; ++i) f[i] += g.bias[n0 + i]; }
+    if (g.bias) { const float4 b = *reinterpret_cast<const float4*>(g.bias + n0); f[0] += b.x; f[1] += b.y; f[2] += b.z; f[3] += b.w; }
     if (g.rowbias) { const float* rb = g.rowbias + (row / rows_per_img) * g.N + n0; for (int i = 0; i < 4; ++i) f[i] += rb[i]; }
     if (g.residual) { const __nv_bfloat16* rp = g.residual + row * g.ldr + n0; for (int i = 0; i < 4; ++i) f[i] += __bfloat162float(rp[i]); }
     if (g.out_fp32) {

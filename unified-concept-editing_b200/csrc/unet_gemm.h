@@ -20,8 +20,8 @@ struct GemmDesc {
     int rows_per_img;          // linear: image index of a row = row / rows_per_img (for rowbias); 0 = none
     int katoms;                // 64-wide k atoms per pipeline stage (1 or 2): 2 halves the barrier round trips of the single MMA thread
     int stages;                // TMA->MMA pipeline depth (3: two CTAs per SM; 6: one CTA per SM, hides the TMA latency of under-filled grids)
-    int ksplit;                // > 1: the k loop is split over grid.z; partial sums are atomically added into splitk_ws (fp32 [M,N])
-    float* splitk_ws;          // zero on entry; gemm_splitk_finalize applies the epilogue and re-zeroes it
+    int ksplit;                // > 1: the k loop is split over grid.z; CTA z stores its partial sums into slab z of splitk_ws (fp32 [ksplit,M,N])
+    float* splitk_ws;          // shared scratch; the finalize pass sums the slabs in order and applies the epilogue
     float alpha;
     void* out; int out_fp32; long ldo, out_b1_stride, out_b2_stride;
     const float* bias;         // [N]

@@ -34,7 +34,9 @@ __device__ __forceinline__ float silu_f(float x) { return x / (1.f + __expf(-x))
 
 // ---------------------------------------------------------------------------------------------- GroupNorm
 // stats[(img*G + g)*2 + {0,1}] += (sum, sum of squares) over the pixels of this CTA's slab.
-// grid (slabs, NB); block 256.
+// grid (slabs, NB); block 256 laid out as (pixel lane, 8-channel column): consecutive threads read consecutive 16 B of a
+// pixel (coalesced), 256 / (C/8) pixel lanes walk the slab; per-channel partial sums stay in registers and are binned into
+// the group accumulators (shared, then one global atomic per group and CTA) at the end.
 __global__ void __launch_bounds__(256) gn_stats_kernel(const __nv_bfloat16* __restrict__ x, int HW, int C, int G, int pix_per_cta,
                                                        float* __restrict__ stats) {
     extern __shared__ float red[];                 // [2 * G]
@@ -44,23 +46,29 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const __nv_bfloat16* __re
     __syncthreads();
     const __nv_bfloat16* base = x + ((long)img * HW + p0) * C;
     const int npix = min(pix_per_cta, HW - p0);
-    // a thread owns one 8-channel column (coalesced across the warp) and walks the slab's pixels; per-channel partial
-    // sums stay in registers and are binned into the group accumulators once at the end
-    for (int cv = threadIdx.x; cv < vec_per_pix; cv += blockDim.x) {
-        float s[8], ss[8];
+    const int tpc = min(vec_per_pix, (int)blockDim.x), lanes = blockDim.x / tpc;
+    const int cl = threadIdx.x % tpc, pl = threadIdx.x / tpc;
+    if (pl < lanes) {
+        for (int cv = cl; cv < vec_per_pix; cv += tpc) {
+            float s[8], ss[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { s[i] = 0.f; ss[i] = 0.f; }
+            for (int i = 0; i < 8; ++i) { s[i] = 0.f; ss[i] = 0.f; }
 #pragma unroll 4
-        for (int p = 0; p < npix; ++p) {
-            float f[8];
-            unpack8(*reinterpret_cast<const uint4*>(base + (long)p * C + cv * 8), f);
+            for (int p = pl; p < npix; p += lanes) {
+                float f[8];
+                unpack8(*reinterpret_cast<const uint4*>(base + (long)p * C + cv * 8), f);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) { s[i] += f[i]; ss[i] += f[i] * f[i]; }
-        }
+                for (int i = 0; i < 8; ++i) { s[i] += f[i]; ss[i] += f[i] * f[i]; }
+            }
+            // channels of one 8-vector fall into at most two groups when cpg >= 8 (every SD level): pre-reduce per group
+            int g_prev = (cv * 8) / cpg; float a = 0.f, b = 0.f;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int g = (cv * 8 + i) / cpg;
-            atomicAdd(&red[2 * g], s[i]); atomicAdd(&red[2 * g + 1], ss[i]);
+            for (int i = 0; i < 8; ++i) {
+                const int g = (cv * 8 + i) / cpg;
+                if (g != g_prev) { atomicAdd(&red[2 * g_prev], a); atomicAdd(&red[2 * g_prev + 1], b); a = 0.f; b = 0.f; g_prev = g; }
+                a += s[i]; b += ss[i];
+            }
+            atomicAdd(&red[2 * g_prev], a); atomicAdd(&red[2 * g_prev + 1], b);
         }
     }
     __syncthreads();
@@ -302,9 +310,10 @@ __global__ void __launch_bounds__(256) cfg_step_kernel(const float* __restrict__
 
 int op_groupnorm(const __nv_bfloat16* x, __nv_bfloat16* y, int NB, int HW, int C, int G, float* stats, const float* gamma, const float* beta,
                  float eps, int silu, cudaStream_t st) {
-    cudaError_t e = cudaMemsetAsync(stats, 0, (size_t)NB * G * 2 * sizeof(float), st);
-    if (e != cudaSuccess) return (int)e;
-    const int pix_per_cta = HW >= 64 ? 16 : HW;      // many small slabs: the per-thread pixel walk is latency-bound
+    // `stats` is this call's own zeroed slice (the engine clears every slice with one memset per forward)
+    const int slabs_target = max(1, 256 / NB);
+    int pix_per_cta = (HW + slabs_target - 1) / slabs_target;
+    if (pix_per_cta < 8) pix_per_cta = HW < 8 ? HW : 8;
     gn_stats_kernel<<<dim3((HW + pix_per_cta - 1) / pix_per_cta, NB), 256, 2 * G * sizeof(float), st>>>(x, HW, C, G, pix_per_cta, stats);
     OPS_CHECK();
     const long n_vec = (long)NB * HW * C / 8;

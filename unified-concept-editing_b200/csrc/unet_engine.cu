@@ -151,6 +151,7 @@ struct Builder {
     const Weight& W(const std::string& n) { return u->w.at(n); }
     void push(std::function<int(cudaStream_t)> f) { u->ops.push_back(std::move(f)); }
     void gemm(GemmDesc g) {
+        if (!getenv("UCE_NO_PAIR") && uce::gemm_enable_pair(&g) < 0) { rc = rc ? rc : SD_E_STATE; sd_err("tensor map encode failed (pair)"); return; }
         int ks = uce::gemm_choose_ksplit(g, u->sm_count);
         while (ks > 1 && (size_t)ks * g.M * g.N > u->splitk_cap) --ks;
         if (ks > 1) {                         // every split GEMM shares one scratch: the schedule is a single in-order stream

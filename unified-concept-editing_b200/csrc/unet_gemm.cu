@@ -23,8 +23,132 @@ constexpr int UG_THREADS = 192;
 constexpr int UG_ATOM_BYTES = (UG_BM + UG_BN) * UG_BK * 2;      // 32 KB: one 64-wide k atom of A and of B
 inline int ug_smem_bytes(int stages, int katoms) { return stages * katoms * UG_ATOM_BYTES + 1024 + 256; }
 
+#ifdef UG_TRACE      // scripts/gemm_probe.cu: clock64 stamps of CTA (0,0,0)
+__device__ long long ug_trace[16];
+#define UG_STAMP(i) do { if ((blockIdx.x | blockIdx.y | blockIdx.z) == 0) ug_trace[i] = clock64(); } while (0)
+#else
+#define UG_STAMP(i) do { } while (0)
+#endif
+
+
+// ---- epilogue shared by both GEMM kernels: TMEM lane = tile row; `bn` accumulator columns starting at global column n_base.
+// The bias / time-embedding / residual operands of a 32-column chunk are fetched (vector loads) BEFORE the accumulator is
+// needed — chunk 0 while the main loop is still running, chunk c+1 right after chunk c's values are consumed — so their
+// latency is off the critical path (the first version paid ~3000 cycles per chunk on dependent scalar loads).
+struct EpiOperands { float4 b[8]; uint4 r[4]; };
+__device__ __forceinline__ void epi_fetch(const GemmDesc& g, EpiOperands& o, bool active, int n0, int img, long rbase) {
+    const bool full = active && (n0 + 32 <= g.N);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o.b[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) o.r[j] = make_uint4(0u, 0u, 0u, 0u);
+    if (!active || g.ksplit > 1) return;
+    if (g.bias) {
+        if (full) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o.b[j] = __ldg(reinterpret_cast<const float4*>(g.bias + n0) + j);
+        } else {
+            float* bf = reinterpret_cast<float*>(o.b);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) if (n0 + i < g.N) bf[i] = g.bias[n0 + i];
+        }
+    }
+    if (g.rowbias) {
+        const float* rb = g.rowbias + (long)img * g.N + n0;
+        float* bf = reinterpret_cast<float*>(o.b);
+        if (full && ((g.N & 3) == 0)) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { const float4 t = __ldg(reinterpret_cast<const float4*>(rb) + j); bf[4 * j] += t.x; bf[4 * j + 1] += t.y; bf[4 * j + 2] += t.z; bf[4 * j + 3] += t.w; }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) if (n0 + i < g.N) bf[i] += rb[i];
+        }
+    }
+    if (g.residual) {
+        const __nv_bfloat16* rp = g.residual + rbase + n0;
+        if (full && ((g.ldr & 7) == 0)) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) o.r[j] = *reinterpret_cast<const uint4*>(rp + 8 * j);
+        } else {
+            __nv_bfloat16* rh = reinterpret_cast<__nv_bfloat16*>(o.r);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) if (n0 + i < g.N) rh[i] = rp[i];
+        }
+    }
+}
+
+__device__ __forceinline__ void gemm_epilogue(const GemmDesc& g, uint32_t tmem_base, uint32_t bar_acc, int q, long row, bool row_ok, int img,
+                                              int n_base, int bn, int zk, int b1, int b2) {
+    const long obase = (long)b1 * g.out_b1_stride + (long)b2 * g.out_b2_stride + row * g.ldo;
+    const long rbase = (long)b1 * g.res_b1_stride + (long)b2 * g.res_b2_stride + row * g.ldr;
+    EpiOperands eo;
+    epi_fetch(g, eo, row_ok && n_base < g.N, n_base, img, rbase);
+    mbar_wait(bar_acc, 0);
+    fence_after();
+    if (threadIdx.x == 64) UG_STAMP(5);
+#pragma unroll 1
+    for (int c = 0; c < bn; c += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)c, v);
+        const int n0 = n_base + c;
+        const bool active = row_ok && n0 < g.N;
+        float f[32];
+        {
+            const float* bf = reinterpret_cast<const float*>(eo.b);
+            const __nv_bfloat162* rh = reinterpret_cast<const __nv_bfloat162*>(eo.r);
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+                const float2 t2 = __bfloat1622float2(rh[i / 2]);
+                f[i] = fmaf(g.alpha, __uint_as_float(v[i]), bf[i] + t2.x);
+                f[i + 1] = fmaf(g.alpha, __uint_as_float(v[i + 1]), bf[i + 1] + t2.y);
+            }
+        }
+        if (c + 32 < bn) epi_fetch(g, eo, row_ok && n0 + 32 < g.N, n0 + 32, img, rbase);      // operands of the next chunk
+        if (!active) continue;
+        const bool full = (n0 + 32 <= g.N);
+        if (g.ksplit > 1) {            // partial sum of this k range -> its own slab; the finalize pass sums the slabs in a
+                                       // fixed order (deterministic, unlike atomics) and applies the epilogue terms
+            float* wp = g.splitk_ws + ((long)zk * g.M + row) * (long)g.N + n0;
+            if (full) {                // N % 4 == 0 is a precondition of splitting
+#pragma unroll
+                for (int j = 0; j < 8; ++j) *reinterpret_cast<float4*>(wp + 4 * j) = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) if (n0 + i < g.N) wp[i] = f[i];
+            }
+            continue;
+        }
+        if (g.out_fp32) {
+            float* op = reinterpret_cast<float*>(g.out) + obase + n0;
+            if (full && ((g.ldo & 3) == 0)) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) *reinterpret_cast<float4*>(op + 4 * j) = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) if (n0 + i < g.N) op[i] = f[i];
+            }
+        } else {
+            __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(g.out) + obase + n0;
+            if (full && ((g.ldo & 7) == 0)) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    uint4 u;
+                    __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) h2[e] = __floats2bfloat162_rn(f[8 * j + 2 * e], f[8 * j + 2 * e + 1]);
+                    *reinterpret_cast<uint4*>(op + 8 * j) = u;
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) if (n0 + i < g.N) op[i] = __float2bfloat16(f[i]);
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(UG_THREADS, 2) unet_gemm_kernel(const __grid_constant__ GemmDesc g) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
+    if (threadIdx.x == 0) UG_STAMP(0);
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const int NS = g.stages, KA = g.katoms;
     const int stage_bytes = KA * UG_ATOM_BYTES;
@@ -67,10 +191,12 @@ __global__ void __launch_bounds__(UG_THREADS, 2) unet_gemm_kernel(const __grid_c
     fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+    if (threadIdx.x == 0) UG_STAMP(1);
 
     if (warp == 0) {
         if (lane == 0) {
             for (int it = 0; it < n_k; ++it) {
+                if (it == 1) UG_STAMP(2);
                 const int s = it % NS;
                 mbar_wait(bar_empty(s), (uint32_t)(((it / NS) & 1) ^ 1));
                 const int na = min(KA, n_atoms - it * KA);
@@ -101,6 +227,7 @@ __global__ void __launch_bounds__(UG_THREADS, 2) unet_gemm_kernel(const __grid_c
                 const int s = it % NS;
                 mbar_wait(bar_full(s), (uint32_t)((it / NS) & 1));
                 fence_after();
+                if (it == 0) UG_STAMP(3);
                 const int na = min(KA, n_atoms - it * KA);
                 for (int a = 0; a < na; ++a) {
                     const uint64_t a_desc = umma_desc_sw128(base + s * stage_bytes + a * (UG_BM * UG_BK * 2));
@@ -112,6 +239,7 @@ __global__ void __launch_bounds__(UG_THREADS, 2) unet_gemm_kernel(const __grid_c
                 umma_commit(bar_empty(s));
             }
             umma_commit(bar_acc);
+            UG_STAMP(4);
         }
     } else {
         // ---- epilogue: TMEM lane = tile row ----
@@ -132,87 +260,164 @@ __global__ void __launch_bounds__(UG_THREADS, 2) unet_gemm_kernel(const __grid_c
             row_ok = row < g.M;
             if (g.rows_per_img > 0) img = (int)(row / g.rows_per_img);
         }
-        mbar_wait(bar_acc, 0);
-        fence_after();
-        const int n_base = n_tile * UG_BN;
-        const long obase = (long)b1 * g.out_b1_stride + (long)b2 * g.out_b2_stride + row * g.ldo;
-        const long rbase = (long)b1 * g.res_b1_stride + (long)b2 * g.res_b2_stride + row * g.ldr;
-#pragma unroll 1
-        for (int c = 0; c < UG_BN; c += 32) {
-            uint32_t v[32];
-            tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)c, v);
-            if (!row_ok || n_base + c >= g.N) continue;
-            float f[32];
-#pragma unroll
-            for (int i = 0; i < 32; ++i) f[i] = g.alpha * __uint_as_float(v[i]);
-            const int n0 = n_base + c;
-            const bool full = (n0 + 32 <= g.N);
-            if (g.ksplit > 1) {            // partial sum of this k range -> its own slab; the finalize pass sums the slabs in a
-                                           // fixed order (deterministic, unlike atomics) and applies the epilogue terms
-                float* wp = g.splitk_ws + ((long)zk * g.M + row) * (long)g.N + n0;
-                if (full) {                // N % 4 == 0 is a precondition of splitting
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) *reinterpret_cast<float4*>(wp + 4 * j) = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) if (n0 + i < g.N) wp[i] = f[i];
-                }
-                continue;
-            }
-            if (g.bias) {
-#pragma unroll
-                for (int i = 0; i < 32; ++i) if (full || n0 + i < g.N) f[i] += g.bias[n0 + i];
-            }
-            if (g.rowbias) {
-                const float* rb = g.rowbias + (long)img * g.N + n0;
-#pragma unroll
-                for (int i = 0; i < 32; ++i) if (full || n0 + i < g.N) f[i] += rb[i];
-            }
-            if (g.residual) {
-                const __nv_bfloat16* rp = g.residual + rbase + n0;
-                if (full && ((g.ldr & 7) == 0)) {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const uint4 u = *reinterpret_cast<const uint4*>(rp + 8 * j);
-                        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) { const float2 t2 = __bfloat1622float2(h2[e]); f[8 * j + 2 * e] += t2.x; f[8 * j + 2 * e + 1] += t2.y; }
-                    }
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) if (n0 + i < g.N) f[i] += __bfloat162float(rp[i]);
-                }
-            }
-            if (g.out_fp32) {
-                float* op = reinterpret_cast<float*>(g.out) + obase + n0;
-                if (full && ((g.ldo & 3) == 0)) {
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) *reinterpret_cast<float4*>(op + 4 * j) = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) if (n0 + i < g.N) op[i] = f[i];
-                }
-            } else {
-                __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(g.out) + obase + n0;
-                if (full && ((g.ldo & 7) == 0)) {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        uint4 u;
-                        __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&u);
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) h2[e] = __floats2bfloat162_rn(f[8 * j + 2 * e], f[8 * j + 2 * e + 1]);
-                        *reinterpret_cast<uint4*>(op + 8 * j) = u;
-                    }
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) if (n0 + i < g.N) op[i] = __float2bfloat16(f[i]);
-                }
-            }
-        }
+        gemm_epilogue(g, tmem_base, bar_acc, q, row, row_ok, img, n_tile * UG_BN, UG_BN, zk, b1, b2);
     }
+    if (threadIdx.x == 64) UG_STAMP(6);
     fence_before();
     __syncthreads();
     if (warp == 1) { fence_after(); tmem_dealloc(tmem_base, UG_BN); }
+    if (threadIdx.x == 0) UG_STAMP(7);
+}
+
+
+// ------------------------------------------------------------------------------------------ CTA-pair kernel
+// Same GEMM on a 256 x bn tile per CLUSTER of two CTAs (tcgen05.mma.cta_group::2, M = 256): each CTA of the pair owns 128
+// rows (its own A tile and TMEM accumulator) and stages only HALF of the B tile; the tensor cores of both SMs read both
+// halves.  An SM ingests ~40 B/clk through TMA (scripts/gemm_probe.cu), a 128 x 128 x 64 step of the single-CTA kernel costs
+// it 32 KB for 64 MMA-cycles x 4: the pair halves the B bytes per flop and allows bn up to 256, i.e. up to 2x the
+// flops per ingested byte.  Protocol per stage: both CTAs' TMA loads signal the LEADER's full barrier (cta_group::2 TMA,
+// peer bit cleared in the barrier address); the leader issues the MMAs and commits, multicast, to the empty barrier of both.
+constexpr uint32_t UG_PEER_MASK = 0xFEFFFFFFu;            // shared::cluster address bit 24 = CTA rank within the pair
+constexpr int UG2_STAGE_BYTES = 32768;                     // A 16 KB + B half (<= 128 rows) 16 KB
+
+__device__ __forceinline__ void tma_load_4d_pair(uint32_t dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                 ::"r"(dst), "l"((uint64_t)map), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {     // arrives on the barrier at this offset in BOTH CTAs
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+
+__global__ void __launch_bounds__(UG_THREADS, 2) unet_gemm_pair_kernel(const __grid_constant__ GemmDesc g) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    if (threadIdx.x == 0) UG_STAMP(0);
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const int NS = g.stages;
+    const uint32_t bars = base + NS * UG2_STAGE_BYTES;
+    auto bar_full = [&](int s) { return bars + 8u * s; };
+    auto bar_empty = [&](int s) { return bars + 8u * (UG_MAX_STAGES + s); };
+    const uint32_t bar_acc = bars + 8u * (2 * UG_MAX_STAGES);
+    const uint32_t tmem_slot = bars + 8u * (2 * UG_MAX_STAGES + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+
+    const int bn = g.bn;
+    const int m_tile = blockIdx.x, n_tile = blockIdx.y, zk = blockIdx.z;     // the pair is two consecutive m-tiles: clusters of (2,1,1)
+    const int n_base = n_tile * bn;
+    int n_mma = g.N - n_base;                                  // columns of this tile's MMAs: valid columns rounded up to 32
+    n_mma = n_mma >= bn ? bn : ((n_mma + 31) & ~31);
+    const int n_half = n_mma / 2;
+    const int kpt = g.cin / UG_BK + ((g.cin % UG_BK) ? 1 : 0);
+    const int n_k_total = g.taps * kpt;
+    const int k_begin = (g.ksplit > 1) ? (int)((long)n_k_total * zk / g.ksplit) : 0;
+    const int k_end = (g.ksplit > 1) ? (int)((long)n_k_total * (zk + 1) / g.ksplit) : n_k_total;
+    const int n_k = k_end - k_begin;
+
+    int img0 = 0, h0 = 0, w0 = 0;
+    if (g.conv) {
+        const int tiles_w = g.Wo / g.tw, tiles_h = g.Ho / g.th;
+        int t = m_tile;
+        w0 = (t % tiles_w) * g.tw; t /= tiles_w;
+        h0 = (t % tiles_h) * g.th; t /= tiles_h;
+        img0 = t * g.tn;                                       // a padding m-tile (odd tile count) lands beyond the last image: zero fill
+    }
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NS; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1); }
+        mbar_init(bar_acc, 1);
+        mbar_fence_init();
+        tma_prefetch_desc(&g.tmA); tma_prefetch_desc(&g.tmB);
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)g.tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    fence_before();
+    cluster_sync_all();                                        // the peer's barriers exist before anything signals them
+    fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+    if (threadIdx.x == 0) UG_STAMP(1);
+
+    const int b_bytes = (bn / 2) * UG_BK * 2;
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int it = 0; it < n_k; ++it) {
+                if (it == 1) UG_STAMP(2);
+                const int s = it % NS;
+                mbar_wait(bar_empty(s), (uint32_t)(((it / NS) & 1) ^ 1));
+                // the leader's barrier counts the bytes of both CTAs (a peer load may land before this expect_tx: the
+                // transaction count is signed, and the phase cannot complete before the leader's own arrival)
+                if (rank == 0) mbar_arrive_expect_tx(bar_full(s), (uint32_t)(2 * (g.a_bytes + b_bytes)));
+                const uint32_t lead_bar = bar_full(s) & UG_PEER_MASK;
+                const uint32_t a_dst = base + s * UG2_STAGE_BYTES, b_dst = a_dst + UG_BM * UG_BK * 2;
+                const int kit = k_begin + it;
+                const int tap = kit / kpt, c0 = (kit % kpt) * UG_BK;
+                if (g.conv) {
+                    const int ky = tap / 3, kx = tap % 3;
+                    tma_load_4d_pair(a_dst, &g.tmA, lead_bar, c0, w0 * g.stride + kx - g.pad, h0 * g.stride + ky - g.pad, img0);
+                } else {
+                    tma_load_4d_pair(a_dst, &g.tmA, lead_bar, c0, m_tile * UG_BM, 0, 0);
+                }
+                tma_load_4d_pair(b_dst, &g.tmB, lead_bar, tap * g.cin + c0, n_base + (int)rank * n_half, 0, 0);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && rank == 0) {
+            const uint32_t idesc = idesc_bf16(2 * UG_BM, n_mma);
+            for (int it = 0; it < n_k; ++it) {
+                const int s = it % NS;
+                mbar_wait(bar_full(s), (uint32_t)((it / NS) & 1));
+                fence_after();
+                if (it == 0) UG_STAMP(3);
+                const uint64_t a_desc = umma_desc_sw128(base + s * UG2_STAGE_BYTES);
+                const uint64_t b_desc = umma_desc_sw128(base + s * UG2_STAGE_BYTES + UG_BM * UG_BK * 2);
+#pragma unroll
+                for (int k = 0; k < UG_BK / 16; ++k)
+                    umma_bf16_pair(tmem_base, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (it | k) != 0);
+                umma_commit_pair(bar_empty(s));
+            }
+            umma_commit_pair(bar_acc);
+            UG_STAMP(4);
+        }
+    } else {
+        const int q = warp & 3;
+        const int r = 32 * q + lane;
+        long row; int img = 0; bool row_ok;
+        if (g.conv) {
+            const int per_img = g.th * g.tw;
+            const int ti = r / per_img, rem = r % per_img;
+            img = img0 + ti;
+            const int hh = h0 + rem / g.tw, ww = w0 + rem % g.tw;
+            row = ((long)img * g.Ho + hh) * g.Wo + ww;
+            row_ok = m_tile < g.m_tiles;
+        } else {
+            row = (long)m_tile * UG_BM + r;
+            row_ok = row < g.M;
+            if (g.rows_per_img > 0) img = (int)(row / g.rows_per_img);
+        }
+        gemm_epilogue(g, tmem_base, bar_acc, q, row, row_ok, img, n_base, bn, zk, 0, 0);
+    }
+    if (threadIdx.x == 64) UG_STAMP(6);
+    fence_before();
+    cluster_sync_all();                                        // neither CTA may free TMEM / exit while the pair's MMAs or barriers are live
+    if (warp == 1) {
+        fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)g.tmem_cols) : "memory");
+    }
+    if (threadIdx.x == 0) UG_STAMP(7);
 }
 
 // ------------------------------------------------------------------------------------------ host
@@ -235,6 +440,7 @@ int gemm_desc_linear(GemmDesc* g, const void* A, long lda, long a_b1_stride, lon
     g->m_tiles = (M + UG_BM - 1) / UG_BM; g->tile_rows = UG_BM; g->a_bytes = UG_BM * UG_BK * 2;
     g->M = M; g->N = N; g->Kd = Kd; g->batch = b1cnt * b2cnt; g->b1cnt = b1cnt; g->conv = 0; g->taps = 1; g->cin = Kd; g->alpha = 1.f;
     g->a_batched = a_batched; g->b_batched = b_batched;
+    g->b_ptr = B; g->b_ld = ldb;
     {
         long dims[4] = {Kd, M, a_batched ? b1cnt : 1, a_batched ? b2cnt : 1};
         long str[4] = {1, lda, a_batched && a_b1_stride ? a_b1_stride : (long)M * lda, a_batched && a_b2_stride ? a_b2_stride : (long)M * lda};
@@ -258,6 +464,7 @@ int gemm_desc_conv(GemmDesc* g, const void* act_nhwc, int NB, int Hin, int Win, 
     g->conv = 1; g->taps = ksize * ksize; g->cin = Cin; g->stride = stride; g->pad = pad; g->alpha = 1.f;
     g->Ho = Ho; g->Wo = Wo; g->NBimg = NB; g->batch = 1; g->b1cnt = 1; g->a_batched = 0; g->b_batched = 0;
     g->M = NB * Ho * Wo; g->N = Cout; g->Kd = g->taps * Cin;
+    g->b_ptr = w_tapmajor; g->b_ld = (long)g->taps * Cin;
     // output rectangle of 128 pixels
     int tw = Wo < 128 ? Wo : 128, th = 128 / tw; if (th > Ho) th = Ho;
     int tn = 128 / (tw * th); if (tn > NB) tn = NB;
@@ -313,15 +520,37 @@ __global__ void __launch_bounds__(256) splitk_finalize_kernel(GemmDesc g, int ro
 // 128 x 128 tiles streaming 32 KB per k-iteration) sit at ~8 TB/s of L2->SM operand traffic.  Raising the arithmetic
 // intensity per L2 byte (2-CTA tcgen05.mma with multicast TMA) is the next step; until then: 3 single-atom stages with two
 // CTAs per SM for full grids, 6 stages for under-filled ones.
+static int gemm_ctas(const GemmDesc& g);
 int gemm_choose_stages(const GemmDesc& g, int sm_count, int* katoms) {
-    const long ctas = (long)((g.N + UG_BN - 1) / UG_BN) * g.m_tiles * (g.ksplit > 1 ? g.ksplit : g.batch);
+    const long ctas = (long)gemm_ctas(g) * (g.ksplit > 1 ? g.ksplit : g.batch);
     *katoms = 1;
     return ctas <= (long)sm_count + sm_count / 4 ? UG_MAX_STAGES : 3;
 }
 
+// CTA count of the (unsplit) grid
+static int gemm_ctas(const GemmDesc& g) {
+    if (g.pair) return ((g.N + g.bn - 1) / g.bn) * ((g.m_tiles + 1) / 2 * 2);
+    return ((g.N + UG_BN - 1) / UG_BN) * g.m_tiles;
+}
+
+// Switch a descriptor to the CTA-pair kernel when the problem allows it: full 128-row tiles, at least two of them, no batch.
+// The tile width is N split evenly into ceil(N/256) tiles, rounded up to 32 (so each CTA stages a multiple of 16 B rows).
+int gemm_enable_pair(GemmDesc* g) {
+    if (g->batch != 1 || g->m_tiles < 2 || g->tile_rows != UG_BM || g->N < 64 || !g->b_ptr) return 0;
+    const int n_tiles = (g->N + 255) / 256;
+    int bn = ((g->N + n_tiles - 1) / n_tiles + 31) & ~31;
+    if (bn > 256) bn = 256;
+    g->pair = 1; g->bn = bn; g->tmem_cols = bn <= 128 ? 128 : 256;
+    long dims[4] = {g->Kd, g->N, 1, 1};
+    long str[4] = {1, g->b_ld, (long)g->N * g->b_ld, (long)g->N * g->b_ld};
+    int box[4] = {UG_BK, bn / 2, 1, 1};
+    if (encode_bf16_map(&g->tmB, g->b_ptr, 4, dims, str, box, nullptr)) return -1;
+    return 1;
+}
+
 int gemm_choose_ksplit(const GemmDesc& g, int sm_count) {
     if (g.batch != 1 || (g.N % 4)) return 1;
-    const int ctas = ((g.N + UG_BN - 1) / UG_BN) * g.m_tiles;
+    const int ctas = gemm_ctas(g);
     if (ctas * 2 > sm_count) return 1;
     const int kpt = g.cin / UG_BK + ((g.cin % UG_BK) ? 1 : 0);
     const int n_k = g.taps * kpt;
@@ -337,6 +566,40 @@ int gemm_launch(const GemmDesc& g, cudaStream_t st) {
         cudaError_t e = cudaFuncSetAttribute(unet_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ug_smem_bytes(UG_MAX_STAGES, 1));
         if (e != cudaSuccess) return (int)e;
         configured = true;
+    }
+    if (g.pair) {
+        static bool configured2 = false;
+        if (!configured2) {
+            cudaError_t e = cudaFuncSetAttribute(unet_gemm_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, UG_MAX_STAGES * UG2_STAGE_BYTES + 1024 + 256);
+            if (e != cudaSuccess) return (int)e;
+            configured2 = true;
+        }
+        GemmDesc gg = g;
+        gg.stages = (g.stages >= 2 && g.stages <= UG_MAX_STAGES) ? g.stages : 3;
+        dim3 grid((g.m_tiles + 1) / 2 * 2, (g.N + g.bn - 1) / g.bn, g.ksplit > 1 ? g.ksplit : 1);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = grid; cfg.blockDim = dim3(UG_THREADS, 1, 1);
+        cfg.dynamicSmemBytes = (size_t)(gg.stages * UG2_STAGE_BYTES + 1024 + 256); cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;     // cta_group::2 pairs form along x
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        cudaError_t e = cudaLaunchKernelEx(&cfg, unet_gemm_pair_kernel, gg);
+        if (e == cudaSuccess) e = cudaGetLastError();
+        if (e != cudaSuccess) {
+            int nc = -1;
+            cudaOccupancyMaxActiveClusters(&nc, unet_gemm_pair_kernel, &cfg);
+            fprintf(stderr, "uce: pair GEMM launch failed (%s): grid %u x %u x %u, smem %zu, max active clusters %d\n", cudaGetErrorString(e),
+                    grid.x, grid.y, grid.z, cfg.dynamicSmemBytes, nc);
+        }
+        if (e != cudaSuccess) return (int)e;
+        if (g.ksplit > 1) {
+            const long n = (long)g.M * (g.N / 4);
+            const int rows_per_img = g.conv ? g.Ho * g.Wo : (g.rows_per_img > 0 ? g.rows_per_img : 1);
+            splitk_finalize_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(g, rows_per_img);
+            e = cudaGetLastError();
+        }
+        return (int)e;
     }
     dim3 grid((g.N + UG_BN - 1) / UG_BN, g.m_tiles, g.ksplit > 1 ? g.ksplit : g.batch);
     GemmDesc gg = g;

@@ -22,6 +22,8 @@ struct GemmDesc {
     int stages;                // TMA->MMA pipeline depth (3: two CTAs per SM; 6: one CTA per SM, hides the TMA latency of under-filled grids)
     int ksplit;                // > 1: the k loop is split over grid.z; CTA z stores its partial sums into slab z of splitk_ws (fp32 [ksplit,M,N])
     float* splitk_ws;          // shared scratch; the finalize pass sums the slabs in order and applies the epilogue
+    int pair, bn, tmem_cols;   // pair = 1: CTA-pair kernel (cta_group::2) on 256 x bn tiles, each CTA staging bn/2 rows of B
+    const void* b_ptr; long b_ld;   // B operand as given to gemm_desc_* (gemm_enable_pair re-encodes its tensor map)
     float alpha;
     void* out; int out_fp32; long ldo, out_b1_stride, out_b2_stride;
     const float* bias;         // [N]
@@ -35,6 +37,9 @@ int gemm_desc_linear(GemmDesc* g, const void* A, long lda, long a_b1_stride, lon
 int gemm_desc_conv(GemmDesc* g, const void* act_nhwc, int NB, int Hin, int Win, int Cin, const void* w_tapmajor, int Cout,
                    int ksize, int stride);
 int gemm_launch(const GemmDesc& g, cudaStream_t st);
+// Returns 1 when the descriptor was switched to the CTA-pair kernel, 0 when not applicable, < 0 on error. Call before
+// gemm_choose_ksplit / gemm_choose_stages.
+int gemm_enable_pair(GemmDesc* g);
 // Picks a split factor for under-filled grids (batch == 1 only); returns it (1 = no split).
 int gemm_choose_ksplit(const GemmDesc& g, int sm_count);
 int gemm_choose_stages(const GemmDesc& g, int sm_count, int* katoms);

@@ -49,6 +49,7 @@ int main(int argc, char** argv) {
         while (ks > 1 && (size_t)ks * g.M * g.N > ws_cap) --ks;
         if (argc > 1) ks = atoi(argv[1]) > 0 ? atoi(argv[1]) : ks;
         if (ks > 1) { g.ksplit = ks; g.splitk_ws = ws; }
+        if (!getenv("UCE_NO_TMA_EPI")) gemm_enable_tma_epilogue(&g);
         g.stages = gemm_choose_stages(g, sm, &g.katoms);
         const int ctas = (g.pair ? ((N + g.bn - 1) / g.bn) * ((g.m_tiles + 1) / 2 * 2) : ((N + 127) / 128) * g.m_tiles) * (ks > 1 ? ks : 1);
         for (int i = 0; i < 3; ++i) { int lr = gemm_launch(g, 0); if (lr) { printf("%s: launch failed %d\n", s.name, lr); break; } }

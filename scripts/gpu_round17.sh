@@ -1,5 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
+echo "== gemm check"; timeout 300 ./scripts/gemm_check.bin | cut -c1-150
 echo "== probe (pair)"
 timeout 120 ./scripts/gemm_probe.bin > gpurun_out/probe_pair.txt 2>&1; echo "rc=$?"
 cat gpurun_out/probe_pair.txt | cut -c1-330

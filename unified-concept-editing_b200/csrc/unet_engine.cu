@@ -158,6 +158,7 @@ struct Builder {
             g.ksplit = ks; g.splitk_ws = u->splitk_ws;
             ++u->n_split;
         }
+        if (!getenv("UCE_NO_TMA_EPI") && uce::gemm_enable_tma_epilogue(&g) < 0) { rc = rc ? rc : SD_E_STATE; sd_err("tensor map encode failed (epilogue)"); return; }
         g.stages = uce::gemm_choose_stages(g, u->sm_count, &g.katoms);
         push([g](cudaStream_t st) { return uce::gemm_launch(g, st); });
     }

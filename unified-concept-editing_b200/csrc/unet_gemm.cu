@@ -270,6 +270,112 @@ __global__ void __launch_bounds__(UG_THREADS, 2) unet_gemm_kernel(const __grid_c
 }
 
 
+
+// ---- TMA epilogue (CTA-pair kernel): the row-per-lane register epilogue above issues 16-byte accesses to 32 different
+// lines per warp instruction (bias / residual / output), which made the epilogue as long as a 20-iteration main loop.  Here the
+// residual tile is fetched by TMA into 128B-swizzled shared memory while the main loop runs, the accumulator is combined with
+// it IN PLACE (lane = row: the swizzle makes the 16-byte accesses of a quarter-warp conflict-free), and each [128 rows x 64
+// columns] box leaves through one TMA store (which also clips rows >= M and columns >= N).  Split-K partial tiles take the
+// same route as fp32 [128 x 32] boxes into their slab.
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                 ::"l"((uint64_t)map), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_store_5d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3, int c4) {
+    asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
+                 ::"l"((uint64_t)map), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ uint4 lds128(uint32_t a) { uint4 v; asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a)); return v; }
+__device__ __forceinline__ void sts128(uint32_t a, const uint4& v) { asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory"); }
+
+// c1..c3: tile coordinates of the row dimension(s): linear (m0, 0, 0), conv (w0, h0, img0)
+__device__ __forceinline__ void gemm_epilogue_tma(const GemmDesc& g, uint32_t tmem_base, uint32_t bar_acc, uint32_t bar_res, uint32_t stage,
+                                                  uint32_t res_base, uint32_t sbias, int q, int lane, int img, bool row_ok, int n_base, int bn,
+                                                  int c1, int c2, int c3, int zk) {
+    const int r = 32 * q + lane, et = threadIdx.x - 64;
+    const uint32_t lane_base = (uint32_t)(32 * q) << 16;
+    const int n_cols = min(bn, g.N - n_base);
+    for (int i = et; i < bn; i += 128) {
+        const float b = (g.bias && g.ksplit <= 1 && n_base + i < g.N) ? g.bias[n_base + i] : 0.f;
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(sbias + 4u * i), "f"(b) : "memory");
+    }
+    epi_bar_sync();
+    if (g.tma_epi == 1 && g.residual) mbar_wait(bar_res, 0);
+    mbar_wait(bar_acc, 0);
+    fence_after();
+    if (threadIdx.x == 64) UG_STAMP(5);
+    const uint32_t row_off = (uint32_t)r * 128u, sw = (uint32_t)(r & 7);
+    if (g.tma_epi == 1) {
+        const uint32_t obuf = g.residual ? res_base : stage;           // combine in place when there is a residual tile
+        const int n_boxes = (n_cols + 63) / 64;
+        for (int b = 0; b < n_boxes; ++b) {
+            const uint32_t box = obuf + (uint32_t)b * 16384u;
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+                uint32_t v[32];
+                tmem_ld32(tmem_base + lane_base + (uint32_t)(b * 64 + hf * 32), v);
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                    const int j = hf * 4 + jj, col = b * 64 + j * 8;
+                    const uint32_t off = row_off + (((uint32_t)j ^ sw) << 4);
+                    float add[8];
+                    {
+                        const uint4 b0 = lds128(sbias + 4u * col), b1 = lds128(sbias + 4u * col + 16u);
+                        add[0] = __uint_as_float(b0.x); add[1] = __uint_as_float(b0.y); add[2] = __uint_as_float(b0.z); add[3] = __uint_as_float(b0.w);
+                        add[4] = __uint_as_float(b1.x); add[5] = __uint_as_float(b1.y); add[6] = __uint_as_float(b1.z); add[7] = __uint_as_float(b1.w);
+                    }
+                    if (g.rowbias && row_ok && n_base + col < g.N) {
+                        const float4* rb = reinterpret_cast<const float4*>(g.rowbias + (long)img * g.N + n_base + col);
+                        const float4 t0 = __ldg(rb), t1 = __ldg(rb + 1);
+                        add[0] += t0.x; add[1] += t0.y; add[2] += t0.z; add[3] += t0.w; add[4] += t1.x; add[5] += t1.y; add[6] += t1.z; add[7] += t1.w;
+                    }
+                    if (g.residual) {
+                        const uint4 rr = lds128(box + off);
+                        const __nv_bfloat162* rh = reinterpret_cast<const __nv_bfloat162*>(&rr);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) { const float2 t2 = __bfloat1622float2(rh[e]); add[2 * e] += t2.x; add[2 * e + 1] += t2.y; }
+                    }
+                    uint4 o;
+                    __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        oh[e] = __floats2bfloat162_rn(fmaf(g.alpha, __uint_as_float(v[jj * 8 + 2 * e]), add[2 * e]),
+                                                      fmaf(g.alpha, __uint_as_float(v[jj * 8 + 2 * e + 1]), add[2 * e + 1]));
+                    sts128(box + off, o);
+                }
+            }
+            fence_proxy_async();
+            epi_bar_sync();
+            if (threadIdx.x == 64) { tma_store_4d(&g.tmO, box, n_base + b * 64, c1, c2, c3); tma_store_commit(); }
+        }
+    } else {                       // split-K partial sums: fp32 boxes of 32 columns into slab zk
+        const int n_boxes = (n_cols + 31) / 32;
+        for (int b = 0; b < n_boxes; ++b) {
+            const uint32_t box = stage + (uint32_t)b * 16384u;
+            uint32_t v[32];
+            tmem_ld32(tmem_base + lane_base + (uint32_t)(b * 32), v);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                uint4 o;
+                o.x = __float_as_uint(g.alpha * __uint_as_float(v[4 * j])); o.y = __float_as_uint(g.alpha * __uint_as_float(v[4 * j + 1]));
+                o.z = __float_as_uint(g.alpha * __uint_as_float(v[4 * j + 2])); o.w = __float_as_uint(g.alpha * __uint_as_float(v[4 * j + 3]));
+                sts128(box + row_off + (((uint32_t)j ^ sw) << 4), o);
+            }
+            fence_proxy_async();
+            epi_bar_sync();
+            if (threadIdx.x == 64) {
+                if (g.conv) tma_store_5d(&g.tmP, box, n_base + b * 32, c1, c2, c3, zk);
+                else tma_store_4d(&g.tmP, box, n_base + b * 32, c1, zk, 0);
+                tma_store_commit();
+            }
+        }
+    }
+    if (threadIdx.x == 64) tma_store_wait_read();        // shared memory must stay alive until the bulk stores have read it
+}
+
 // ------------------------------------------------------------------------------------------ CTA-pair kernel
 // Same GEMM on a 256 x bn tile per CLUSTER of two CTAs (tcgen05.mma.cta_group::2, M = 256): each CTA of the pair owns 128
 // rows (its own A tile and TMEM accumulator) and stages only HALF of the B tile; the tensor cores of both SMs read both
@@ -310,6 +416,9 @@ __global__ void __launch_bounds__(UG_THREADS, 2) unet_gemm_pair_kernel(const __g
     auto bar_empty = [&](int s) { return bars + 8u * (UG_MAX_STAGES + s); };
     const uint32_t bar_acc = bars + 8u * (2 * UG_MAX_STAGES);
     const uint32_t tmem_slot = bars + 8u * (2 * UG_MAX_STAGES + 1);
+    const uint32_t bar_res = bars + 8u * (2 * UG_MAX_STAGES + 2);
+    const uint32_t sbias = bars + 256u;                        // bn floats
+    const uint32_t res_base = bars + 2048u;                    // residual / output staging boxes (1024-aligned: NS * 32 KB + 2 KB)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
 
@@ -336,9 +445,11 @@ __global__ void __launch_bounds__(UG_THREADS, 2) unet_gemm_pair_kernel(const __g
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < NS; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1); }
-        mbar_init(bar_acc, 1);
+        mbar_init(bar_acc, 1); mbar_init(bar_res, 1);
         mbar_fence_init();
         tma_prefetch_desc(&g.tmA); tma_prefetch_desc(&g.tmB);
+        if (g.tma_epi == 1) { tma_prefetch_desc(&g.tmO); if (g.residual) tma_prefetch_desc(&g.tmR); }
+        if (g.tma_epi == 2) tma_prefetch_desc(&g.tmP);
     }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)g.tmem_cols) : "memory");
@@ -352,8 +463,14 @@ __global__ void __launch_bounds__(UG_THREADS, 2) unet_gemm_pair_kernel(const __g
     if (threadIdx.x == 0) UG_STAMP(1);
 
     const int b_bytes = (bn / 2) * UG_BK * 2;
+    const int ec1 = g.conv ? w0 : m_tile * UG_BM, ec2 = g.conv ? h0 : 0, ec3 = g.conv ? img0 : 0;     // row coordinates of this tile
     if (warp == 0) {
         if (lane == 0) {
+            if (g.tma_epi == 1 && g.residual) {               // residual tile -> its own shared-memory boxes, ahead of the operands
+                const int n_boxes = (min(bn, g.N - n_base) + 63) / 64;
+                mbar_arrive_expect_tx(bar_res, (uint32_t)(n_boxes * 16384));
+                for (int b = 0; b < n_boxes; ++b) tma_load_4d(res_base + (uint32_t)b * 16384u, &g.tmR, bar_res, n_base + b * 64, ec1, ec2, ec3);
+            }
             for (int it = 0; it < n_k; ++it) {
                 if (it == 1) UG_STAMP(2);
                 const int s = it % NS;
@@ -408,7 +525,8 @@ __global__ void __launch_bounds__(UG_THREADS, 2) unet_gemm_pair_kernel(const __g
             row_ok = row < g.M;
             if (g.rows_per_img > 0) img = (int)(row / g.rows_per_img);
         }
-        gemm_epilogue(g, tmem_base, bar_acc, q, row, row_ok, img, n_base, bn, zk, 0, 0);
+        if (g.tma_epi) gemm_epilogue_tma(g, tmem_base, bar_acc, bar_res, base, res_base, sbias, q, lane, img, row_ok, n_base, bn, ec1, ec2, ec3, zk);
+        else gemm_epilogue(g, tmem_base, bar_acc, q, row, row_ok, img, n_base, bn, zk, 0, 0);
     }
     if (threadIdx.x == 64) UG_STAMP(6);
     fence_before();
@@ -421,17 +539,21 @@ __global__ void __launch_bounds__(UG_THREADS, 2) unet_gemm_pair_kernel(const __g
 }
 
 // ------------------------------------------------------------------------------------------ host
-static int encode_bf16_map(CUtensorMap* m, const void* ptr, int rank, const long* dims, const long* strides_elems,
-                           const int* box, const int* estr) {
+static int encode_map(CUtensorMap* m, bool f32, const void* ptr, int rank, const long* dims, const long* strides_elems,
+                      const int* box, const int* estr) {
     EncodeTiledFn enc = tensor_map_encoder();
     if (!enc) return -1;
     cuuint64_t gd[5]; cuuint64_t gs[4]; cuuint32_t bx[5]; cuuint32_t es[5];
     for (int i = 0; i < rank; ++i) { gd[i] = (cuuint64_t)dims[i]; bx[i] = (cuuint32_t)box[i]; es[i] = (cuuint32_t)(estr ? estr[i] : 1); }
-    for (int i = 1; i < rank; ++i) gs[i - 1] = (cuuint64_t)strides_elems[i] * 2;
-    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), gd, gs, bx, es,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+    for (int i = 1; i < rank; ++i) gs[i - 1] = (cuuint64_t)strides_elems[i] * (f32 ? 4 : 2);
+    CUresult r = enc(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), gd, gs,
+                     bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? 0 : (int)r;
+}
+static int encode_bf16_map(CUtensorMap* m, const void* ptr, int rank, const long* dims, const long* strides_elems,
+                           const int* box, const int* estr) {
+    return encode_map(m, false, ptr, rank, dims, strides_elems, box, estr);
 }
 
 int gemm_desc_linear(GemmDesc* g, const void* A, long lda, long a_b1_stride, long a_b2_stride, const void* B, long ldb,
@@ -538,7 +660,7 @@ static int gemm_ctas(const GemmDesc& g) {
 int gemm_enable_pair(GemmDesc* g) {
     if (g->batch != 1 || g->m_tiles < 2 || g->tile_rows != UG_BM || g->N < 64 || !g->b_ptr) return 0;
     const int n_tiles = (g->N + 255) / 256;
-    int bn = ((g->N + n_tiles - 1) / n_tiles + 31) & ~31;
+    int bn = ((g->N + n_tiles - 1) / n_tiles + 63) & ~63;      // multiple of 64: the epilogue's 64-column TMA boxes never straddle two tiles
     if (bn > 256) bn = 256;
     g->pair = 1; g->bn = bn; g->tmem_cols = bn <= 128 ? 128 : 256;
     long dims[4] = {g->Kd, g->N, 1, 1};
@@ -546,6 +668,57 @@ int gemm_enable_pair(GemmDesc* g) {
     int box[4] = {UG_BK, bn / 2, 1, 1};
     if (encode_bf16_map(&g->tmB, g->b_ptr, 4, dims, str, box, nullptr)) return -1;
     return 1;
+}
+
+
+// Output / residual / split-K-slab tensor maps of the TMA epilogue (pair kernel).  Call once out, residual, ksplit and
+// splitk_ws are final.  Returns 1 when enabled, 0 when the register epilogue stays, < 0 on error.
+int gemm_enable_tma_epilogue(GemmDesc* g) {
+    g->tma_epi = 0;
+    if (!g->pair || g->batch != 1) return 0;
+    const long N = g->N;
+    if (g->ksplit > 1) {
+        if (g->conv) {
+            long dims[5] = {N, g->Wo, g->Ho, g->NBimg, g->ksplit};
+            long str[5] = {1, N, (long)g->Wo * N, (long)g->Ho * g->Wo * N, (long)g->M * N};
+            int box[5] = {32, g->tw, g->th, g->tn, 1};
+            if (encode_map(&g->tmP, true, g->splitk_ws, 5, dims, str, box, nullptr)) return -1;
+        } else {
+            long dims[4] = {N, g->M, g->ksplit, 1};
+            long str[4] = {1, N, (long)g->M * N, (long)g->M * N * g->ksplit};
+            int box[4] = {32, UG_BM, 1, 1};
+            if (encode_map(&g->tmP, true, g->splitk_ws, 4, dims, str, box, nullptr)) return -1;
+        }
+        g->tma_epi = 2;
+        return 1;
+    }
+    if (g->out_fp32 || (g->ldo & 7) || (N & 7) || (g->residual && (g->ldr & 7))) return 0;
+    if (((uintptr_t)g->out & 15) || ((uintptr_t)g->residual & 15)) return 0;
+    for (int pass = 0; pass < 2; ++pass) {
+        const void* ptr = pass == 0 ? g->out : (const void*)g->residual;
+        const long ld = pass == 0 ? g->ldo : g->ldr;
+        if (!ptr) continue;
+        CUtensorMap* m = pass == 0 ? &g->tmO : &g->tmR;
+        if (g->conv) {
+            long dims[4] = {N, g->Wo, g->Ho, g->NBimg};
+            long str[4] = {1, ld, (long)g->Wo * ld, (long)g->Ho * g->Wo * ld};
+            int box[4] = {64, g->tw, g->th, g->tn};
+            if (encode_bf16_map(m, ptr, 4, dims, str, box, nullptr)) return -1;
+        } else {
+            long dims[4] = {N, g->M, 1, 1};
+            long str[4] = {1, ld, (long)g->M * ld, (long)g->M * ld};
+            int box[4] = {64, UG_BM, 1, 1};
+            if (encode_bf16_map(m, ptr, 4, dims, str, box, nullptr)) return -1;
+        }
+    }
+    g->tma_epi = 1;
+    return 1;
+}
+
+// Dynamic shared memory of a pair-kernel launch: pipeline stages, barriers + bias (2 KB), residual boxes, alignment slack.
+static size_t pair_smem_bytes(const GemmDesc& g, int stages) {
+    const int res_boxes = (g.tma_epi == 1 && g.residual) ? (g.bn + 63) / 64 : 0;
+    return (size_t)stages * UG2_STAGE_BYTES + 2048 + (size_t)res_boxes * 16384 + 1024;
 }
 
 int gemm_choose_ksplit(const GemmDesc& g, int sm_count) {
@@ -570,16 +743,22 @@ int gemm_launch(const GemmDesc& g, cudaStream_t st) {
     if (g.pair) {
         static bool configured2 = false;
         if (!configured2) {
-            cudaError_t e = cudaFuncSetAttribute(unet_gemm_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, UG_MAX_STAGES * UG2_STAGE_BYTES + 1024 + 256);
+            cudaError_t e = cudaFuncSetAttribute(unet_gemm_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
             if (e != cudaSuccess) return (int)e;
             configured2 = true;
         }
         GemmDesc gg = g;
         gg.stages = (g.stages >= 2 && g.stages <= UG_MAX_STAGES) ? g.stages : 3;
+        {   // output staging of the TMA epilogue lives in the (then idle) pipeline stages unless it is done in place on the residual
+            const int boxes = g.tma_epi == 2 ? (g.bn + 31) / 32 : ((g.tma_epi == 1 && !g.residual) ? (g.bn + 63) / 64 : 0);
+            const int need = (boxes * 16384 + UG2_STAGE_BYTES - 1) / UG2_STAGE_BYTES;
+            if (gg.stages < need) gg.stages = need;
+            while (gg.stages > 2 && pair_smem_bytes(g, gg.stages) > 227 * 1024) --gg.stages;
+        }
         dim3 grid((g.m_tiles + 1) / 2 * 2, (g.N + g.bn - 1) / g.bn, g.ksplit > 1 ? g.ksplit : 1);
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = grid; cfg.blockDim = dim3(UG_THREADS, 1, 1);
-        cfg.dynamicSmemBytes = (size_t)(gg.stages * UG2_STAGE_BYTES + 1024 + 256); cfg.stream = st;
+        cfg.dynamicSmemBytes = pair_smem_bytes(g, gg.stages); cfg.stream = st;
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;     // cta_group::2 pairs form along x

@@ -4,6 +4,8 @@
 #include <cuda.h>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
+#include <utility>
 
 namespace uce {
 namespace tc {
@@ -117,6 +119,25 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 }
 
 }  // namespace tc
+
+
+// ---- programmatic dependent launch (PDL): every kernel of the U-Net schedule is launched with the stream-serialization
+// attribute, signals `launch_dependents` on entry and executes `griddepcontrol.wait` before it touches anything an earlier
+// kernel produced — so the next kernel's launch latency, barrier/TMEM setup and weight prefetch overlap this kernel's tail.
+// Without the launch attribute (UCE_NO_PDL, or plain <<<>>> launches) both instructions are no-ops.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+inline bool pdl_enabled() { static int v = -1; if (v < 0) v = getenv("UCE_NO_PDL") ? 0 : 1; return v != 0; }
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int cluster_x, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[2]; unsigned n = 0;
+    if (cluster_x > 1) { attr[n].id = cudaLaunchAttributeClusterDimension; attr[n].val.clusterDim.x = (unsigned)cluster_x; attr[n].val.clusterDim.y = 1; attr[n].val.clusterDim.z = 1; ++n; }
+    if (pdl_enabled()) { attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[n].val.programmaticStreamSerializationAllowed = 1; ++n; }
+    cfg.attrs = attr; cfg.numAttrs = n;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
 
 // ---- host: tensor-map encoding through the driver entry point (no libcuda link dependency) ----
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,

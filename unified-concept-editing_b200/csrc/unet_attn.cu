@@ -75,6 +75,7 @@ __host__ __device__ inline uint32_t fa_tmem_cols(int dhp) { return 128 + dhp <= 
 
 __global__ void __launch_bounds__(FA_THREADS, 2) unet_attn_kernel(const __grid_constant__ AttnDesc g) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
+    pdl_launch();
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const int dhp = g.dhp;
     const FaSmem L = fa_smem_layout(dhp);
@@ -105,6 +106,7 @@ __global__ void __launch_bounds__(FA_THREADS, 2) unet_attn_kernel(const __grid_c
     fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+    pdl_wait();                                        // q, k, v^T are written by the projections launched just before
 
     auto k_st = [&](int s) { return base + (uint32_t)(L.k_off + s * L.kv_bytes); };
     auto v_st = [&](int s) { return base + (uint32_t)(L.v_off + s * L.kv_bytes); };
@@ -309,8 +311,8 @@ int attn_launch(const AttnDesc& g, cudaStream_t st) {
         configured = smem;
     }
     dim3 grid((g.L + FA_BM - 1) / FA_BM, g.heads, g.NB);
-    unet_attn_kernel<<<grid, FA_THREADS, smem, st>>>(g);
-    return (int)cudaGetLastError();
+    cudaError_t e = launch_k(unet_attn_kernel, grid, dim3(FA_THREADS), (size_t)smem, st, 1, g);
+    return (int)(e == cudaSuccess ? cudaGetLastError() : e);
 }
 
 }  // namespace uce

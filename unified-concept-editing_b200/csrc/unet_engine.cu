@@ -3,6 +3,7 @@
 // launches of unet_gemm.cu (tcgen05 GEMM / implicit-GEMM conv) and unet_ops.cu (norms, softmax, elementwise).
 // Everything is allocated and described once in finalize(); forward() only enqueues, so a step is CUDA-graph capturable.
 #include "../../include/sd_unet_b200.h"
+#include "tc_common.cuh"
 #include "unet_gemm.h"
 #include "unet_ops.h"
 #include "unet_attn.h"
@@ -290,10 +291,12 @@ struct Builder {
 };
 
 __global__ void f32_to_bf16_kernel(const float* x, bf16* y, long n) {
+    uce::pdl_launch(); uce::pdl_wait();
     long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) y[i] = __float2bfloat16(x[i]);
 }
 __global__ void timestep_from_dev_kernel(const float* t, int dim, int NB, bf16* out) {
+    uce::pdl_launch(); uce::pdl_wait();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int half = dim / 2;
     if (i >= half) return;
@@ -331,7 +334,7 @@ int build_schedule(sd_unet* u) {
     B.push([u](cudaStream_t st) { return (int)cudaMemsetAsync(u->gn_stats, 0, (size_t)u->n_gn * u->NB * u->cfg.norm_groups * 2 * sizeof(float), st); });
     {
         float* cf = u->ctx_f32; bf16* cb = u->ctx; const long n = (long)NB * c.context_len * c.cross_attention_dim;
-        B.push([=](cudaStream_t st) { f32_to_bf16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(cf, cb, n); return (int)cudaGetLastError(); });
+        B.push([=](cudaStream_t st) { return (int)uce::launch_k(f32_to_bf16_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, 1, cf, cb, n); });
     }
     // ---- time embedding ----
     bf16 *te0 = nullptr, *t1 = nullptr, *t1s = nullptr, *temb = nullptr, *st_emb = nullptr;
@@ -342,7 +345,7 @@ int build_schedule(sd_unet* u) {
     if ((rc = u->alloc(&st_emb, (size_t)NB * c.temb_dim))) return rc;
     {
         const float* dt = u->d_t; const int d0 = ch[0];
-        B.push([=](cudaStream_t st) { timestep_from_dev_kernel<<<(d0 / 2 + 127) / 128, 128, 0, st>>>(dt, d0, NB, te0); return (int)cudaGetLastError(); });
+        B.push([=](cudaStream_t st) { return (int)uce::launch_k(timestep_from_dev_kernel, dim3((d0 / 2 + 127) / 128), dim3(128), 0, st, 1, dt, d0, NB, te0); });
     }
     B.linear(te0, NB, ch[0], "time_embedding.linear_1.weight", B.W("time_embedding.linear_1.bias").f, nullptr, t1, false);
     { const long n = (long)NB * c.temb_dim; B.push([=](cudaStream_t st) { return uce::op_silu(t1, t1s, n, st); }); }

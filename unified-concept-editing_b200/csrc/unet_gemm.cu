@@ -148,6 +148,7 @@ __device__ __forceinline__ void gemm_epilogue(const GemmDesc& g, uint32_t tmem_b
 
 __global__ void __launch_bounds__(UG_THREADS, 2) unet_gemm_kernel(const __grid_constant__ GemmDesc g) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
+    pdl_launch();
     if (threadIdx.x == 0) UG_STAMP(0);
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const int NS = g.stages, KA = g.katoms;
@@ -195,25 +196,37 @@ __global__ void __launch_bounds__(UG_THREADS, 2) unet_gemm_kernel(const __grid_c
 
     if (warp == 0) {
         if (lane == 0) {
-            for (int it = 0; it < n_k; ++it) {
-                if (it == 1) UG_STAMP(2);
+            // which = 1: B (weights: not produced by an earlier kernel of the schedule unless batched), 2: A, 3: both
+            auto load_stage = [&](int it, int which) {
                 const int s = it % NS;
-                mbar_wait(bar_empty(s), (uint32_t)(((it / NS) & 1) ^ 1));
                 const int na = min(KA, n_atoms - it * KA);
-                mbar_arrive_expect_tx(bar_full(s), (uint32_t)(na * (g.a_bytes + UG_BN * UG_BK * 2)));
+                if (which & 1) mbar_arrive_expect_tx(bar_full(s), (uint32_t)(na * (g.a_bytes + UG_BN * UG_BK * 2)));
                 for (int a = 0; a < na; ++a) {
                     const uint32_t a_dst = base + s * stage_bytes + a * (UG_BM * UG_BK * 2);
                     const uint32_t b_dst = base + s * stage_bytes + KA * (UG_BM * UG_BK * 2) + a * (UG_BN * UG_BK * 2);
                     const int kit = k_begin + it * KA + a;
                     const int tap = kit / kpt, c0 = (kit % kpt) * UG_BK;
-                    if (g.conv) {
-                        const int ky = tap / 3, kx = tap % 3;
-                        tma_load_4d(a_dst, &g.tmA, bar_full(s), c0, w0 * g.stride + kx - g.pad, h0 * g.stride + ky - g.pad, img0);
-                    } else {
-                        tma_load_4d(a_dst, &g.tmA, bar_full(s), c0, m_tile * UG_BM, g.a_batched ? b1 : 0, g.a_batched ? b2 : 0);
+                    if (which & 2) {
+                        if (g.conv) {
+                            const int ky = tap / 3, kx = tap % 3;
+                            tma_load_4d(a_dst, &g.tmA, bar_full(s), c0, w0 * g.stride + kx - g.pad, h0 * g.stride + ky - g.pad, img0);
+                        } else {
+                            tma_load_4d(a_dst, &g.tmA, bar_full(s), c0, m_tile * UG_BM, g.a_batched ? b1 : 0, g.a_batched ? b2 : 0);
+                        }
                     }
-                    tma_load_4d(b_dst, &g.tmB, bar_full(s), tap * g.cin + c0, n_tile * UG_BN, g.b_batched ? b1 : 0, g.b_batched ? b2 : 0);
+                    if (which & 1) tma_load_4d(b_dst, &g.tmB, bar_full(s), tap * g.cin + c0, n_tile * UG_BN, g.b_batched ? b1 : 0, g.b_batched ? b2 : 0);
                 }
+            };
+            // weight tiles of the first stages are requested before the dependency wait: they overlap the previous kernel's tail
+            const int pre = min(NS, n_k);
+            const bool early_b = !g.b_batched;
+            if (early_b) for (int it = 0; it < pre; ++it) load_stage(it, 1);
+            pdl_wait();
+            for (int it = 0; it < pre; ++it) load_stage(it, early_b ? 2 : 3);
+            for (int it = pre; it < n_k; ++it) {
+                if (it == pre) UG_STAMP(2);
+                mbar_wait(bar_empty(it % NS), (uint32_t)(((it / NS) & 1) ^ 1));
+                load_stage(it, 3);
             }
         }
     } else if (warp == 1) {
@@ -260,6 +273,7 @@ __global__ void __launch_bounds__(UG_THREADS, 2) unet_gemm_kernel(const __grid_c
             row_ok = row < g.M;
             if (g.rows_per_img > 0) img = (int)(row / g.rows_per_img);
         }
+        pdl_wait();                                   // residual / time-embedding rows come from earlier kernels
         gemm_epilogue(g, tmem_base, bar_acc, q, row, row_ok, img, n_tile * UG_BN, UG_BN, zk, b1, b2);
     }
     if (threadIdx.x == 64) UG_STAMP(6);
@@ -408,6 +422,7 @@ __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile
 
 __global__ void __launch_bounds__(UG_THREADS, 2) unet_gemm_pair_kernel(const __grid_constant__ GemmDesc g) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
+    pdl_launch();
     if (threadIdx.x == 0) UG_STAMP(0);
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const int NS = g.stages;
@@ -466,29 +481,40 @@ __global__ void __launch_bounds__(UG_THREADS, 2) unet_gemm_pair_kernel(const __g
     const int ec1 = g.conv ? w0 : m_tile * UG_BM, ec2 = g.conv ? h0 : 0, ec3 = g.conv ? img0 : 0;     // row coordinates of this tile
     if (warp == 0) {
         if (lane == 0) {
-            if (g.tma_epi == 1 && g.residual) {               // residual tile -> its own shared-memory boxes, ahead of the operands
-                const int n_boxes = (min(bn, g.N - n_base) + 63) / 64;
-                mbar_arrive_expect_tx(bar_res, (uint32_t)(n_boxes * 16384));
-                for (int b = 0; b < n_boxes; ++b) tma_load_4d(res_base + (uint32_t)b * 16384u, &g.tmR, bar_res, n_base + b * 64, ec1, ec2, ec3);
-            }
-            for (int it = 0; it < n_k; ++it) {
-                if (it == 1) UG_STAMP(2);
+            // which = 1: this CTA's half of the B (weight) tile, 2: its A tile, 3: both
+            auto load_stage = [&](int it, int which) {
                 const int s = it % NS;
-                mbar_wait(bar_empty(s), (uint32_t)(((it / NS) & 1) ^ 1));
                 // the leader's barrier counts the bytes of both CTAs (a peer load may land before this expect_tx: the
                 // transaction count is signed, and the phase cannot complete before the leader's own arrival)
-                if (rank == 0) mbar_arrive_expect_tx(bar_full(s), (uint32_t)(2 * (g.a_bytes + b_bytes)));
+                if ((which & 1) && rank == 0) mbar_arrive_expect_tx(bar_full(s), (uint32_t)(2 * (g.a_bytes + b_bytes)));
                 const uint32_t lead_bar = bar_full(s) & UG_PEER_MASK;
                 const uint32_t a_dst = base + s * UG2_STAGE_BYTES, b_dst = a_dst + UG_BM * UG_BK * 2;
                 const int kit = k_begin + it;
                 const int tap = kit / kpt, c0 = (kit % kpt) * UG_BK;
-                if (g.conv) {
-                    const int ky = tap / 3, kx = tap % 3;
-                    tma_load_4d_pair(a_dst, &g.tmA, lead_bar, c0, w0 * g.stride + kx - g.pad, h0 * g.stride + ky - g.pad, img0);
-                } else {
-                    tma_load_4d_pair(a_dst, &g.tmA, lead_bar, c0, m_tile * UG_BM, 0, 0);
+                if (which & 2) {
+                    if (g.conv) {
+                        const int ky = tap / 3, kx = tap % 3;
+                        tma_load_4d_pair(a_dst, &g.tmA, lead_bar, c0, w0 * g.stride + kx - g.pad, h0 * g.stride + ky - g.pad, img0);
+                    } else {
+                        tma_load_4d_pair(a_dst, &g.tmA, lead_bar, c0, m_tile * UG_BM, 0, 0);
+                    }
                 }
-                tma_load_4d_pair(b_dst, &g.tmB, lead_bar, tap * g.cin + c0, n_base + (int)rank * n_half, 0, 0);
+                if (which & 1) tma_load_4d_pair(b_dst, &g.tmB, lead_bar, tap * g.cin + c0, n_base + (int)rank * n_half, 0, 0);
+            };
+            // weight tiles of the first stages are requested before the dependency wait: they overlap the previous kernel's tail
+            const int pre = min(NS, n_k);
+            for (int it = 0; it < pre; ++it) load_stage(it, 1);
+            pdl_wait();
+            if (g.tma_epi == 1 && g.residual) {               // residual tile -> its own shared-memory boxes, ahead of the activations
+                const int n_boxes = (min(bn, g.N - n_base) + 63) / 64;
+                mbar_arrive_expect_tx(bar_res, (uint32_t)(n_boxes * 16384));
+                for (int b = 0; b < n_boxes; ++b) tma_load_4d(res_base + (uint32_t)b * 16384u, &g.tmR, bar_res, n_base + b * 64, ec1, ec2, ec3);
+            }
+            for (int it = 0; it < pre; ++it) load_stage(it, 2);
+            for (int it = pre; it < n_k; ++it) {
+                if (it == pre) UG_STAMP(2);
+                mbar_wait(bar_empty(it % NS), (uint32_t)(((it / NS) & 1) ^ 1));
+                load_stage(it, 3);
             }
         }
     } else if (warp == 1) {
@@ -525,6 +551,7 @@ __global__ void __launch_bounds__(UG_THREADS, 2) unet_gemm_pair_kernel(const __g
             row_ok = row < g.M;
             if (g.rows_per_img > 0) img = (int)(row / g.rows_per_img);
         }
+        pdl_wait();                                   // bias is a weight, but rowbias / residual come from earlier kernels
         if (g.tma_epi) gemm_epilogue_tma(g, tmem_base, bar_acc, bar_res, base, res_base, sbias, q, lane, img, row_ok, n_base, bn, ec1, ec2, ec3, zk);
         else gemm_epilogue(g, tmem_base, bar_acc, q, row, row_ok, img, n_base, bn, zk, 0, 0);
     }
@@ -612,6 +639,7 @@ int gemm_desc_conv(GemmDesc* g, const void* act_nhwc, int NB, int Hin, int Win, 
 
 // out = sum_z ws[z] (+bias) (+rowbias[img]) (+residual).  One thread per 4 consecutive columns.
 __global__ void __launch_bounds__(256) splitk_finalize_kernel(GemmDesc g, int rows_per_img) {
+    pdl_launch(); pdl_wait();
     const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
     const int nv = g.N / 4;
     if (idx >= (long)g.M * nv) return;
@@ -756,27 +784,17 @@ int gemm_launch(const GemmDesc& g, cudaStream_t st) {
             while (gg.stages > 2 && pair_smem_bytes(g, gg.stages) > 227 * 1024) --gg.stages;
         }
         dim3 grid((g.m_tiles + 1) / 2 * 2, (g.N + g.bn - 1) / g.bn, g.ksplit > 1 ? g.ksplit : 1);
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = grid; cfg.blockDim = dim3(UG_THREADS, 1, 1);
-        cfg.dynamicSmemBytes = pair_smem_bytes(g, gg.stages); cfg.stream = st;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;     // cta_group::2 pairs form along x
-        cfg.attrs = attr; cfg.numAttrs = 1;
-        cudaError_t e = cudaLaunchKernelEx(&cfg, unet_gemm_pair_kernel, gg);
+        // clusters of (2,1,1): cta_group::2 pairs form along x
+        cudaError_t e = launch_k(unet_gemm_pair_kernel, grid, dim3(UG_THREADS), pair_smem_bytes(g, gg.stages), st, 2, gg);
         if (e == cudaSuccess) e = cudaGetLastError();
-        if (e != cudaSuccess) {
-            int nc = -1;
-            cudaOccupancyMaxActiveClusters(&nc, unet_gemm_pair_kernel, &cfg);
-            fprintf(stderr, "uce: pair GEMM launch failed (%s): grid %u x %u x %u, smem %zu, max active clusters %d\n", cudaGetErrorString(e),
-                    grid.x, grid.y, grid.z, cfg.dynamicSmemBytes, nc);
-        }
+        if (e != cudaSuccess)
+            fprintf(stderr, "uce: pair GEMM launch failed (%s): grid %u x %u x %u, smem %zu\n", cudaGetErrorString(e), grid.x, grid.y, grid.z,
+                    pair_smem_bytes(g, gg.stages));
         if (e != cudaSuccess) return (int)e;
         if (g.ksplit > 1) {
             const long n = (long)g.M * (g.N / 4);
             const int rows_per_img = g.conv ? g.Ho * g.Wo : (g.rows_per_img > 0 ? g.rows_per_img : 1);
-            splitk_finalize_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(g, rows_per_img);
-            e = cudaGetLastError();
+            e = launch_k(splitk_finalize_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, 1, g, rows_per_img);
         }
         return (int)e;
     }
@@ -784,14 +802,13 @@ int gemm_launch(const GemmDesc& g, cudaStream_t st) {
     GemmDesc gg = g;
     gg.katoms = (g.katoms == 2) ? 2 : 1;
     gg.stages = (g.stages >= 2 && g.stages * gg.katoms <= UG_MAX_STAGES) ? g.stages : 3;
-    unet_gemm_kernel<<<grid, UG_THREADS, ug_smem_bytes(gg.stages, gg.katoms), st>>>(gg);
-    cudaError_t e = cudaGetLastError();
+    cudaError_t e = launch_k(unet_gemm_kernel, grid, dim3(UG_THREADS), ug_smem_bytes(gg.stages, gg.katoms), st, 1, gg);
+    if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
     if (g.ksplit > 1) {
         const long n = (long)g.M * (g.N / 4);
         const int rows_per_img = g.conv ? g.Ho * g.Wo : (g.rows_per_img > 0 ? g.rows_per_img : 1);
-        splitk_finalize_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(g, rows_per_img);
-        e = cudaGetLastError();
+        e = launch_k(splitk_finalize_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, 1, g, rows_per_img);
     }
     return (int)e;
 }

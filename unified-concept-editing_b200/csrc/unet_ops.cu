@@ -3,6 +3,7 @@
 // fused classifier-free-guidance + scheduler update.  Activations are NHWC bf16; all kernels use 16-byte vector
 // accesses along the channel dimension and warp-shuffle reductions.
 #include "unet_ops.h"
+#include "tc_common.cuh"
 #include <cuda_bf16.h>
 #include <cstdint>
 
@@ -39,6 +40,7 @@ __device__ __forceinline__ float silu_f(float x) { return x / (1.f + __expf(-x))
 // the group accumulators (shared, then one global atomic per group and CTA) at the end.
 __global__ void __launch_bounds__(256) gn_stats_kernel(const __nv_bfloat16* __restrict__ x, int HW, int C, int G, int pix_per_cta,
                                                        float* __restrict__ stats) {
+    pdl_launch(); pdl_wait();
     extern __shared__ float red[];                 // [2 * G]
     const int img = blockIdx.y, p0 = blockIdx.x * pix_per_cta;
     const int vec_per_pix = C / 8, cpg = C / G;
@@ -79,6 +81,7 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const __nv_bfloat16* __re
 __global__ void __launch_bounds__(256) gn_apply_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, long n_vec, int HW,
                                                        int C, int G, const float* __restrict__ stats, const float* __restrict__ gamma,
                                                        const float* __restrict__ beta, float eps, int silu) {
+    pdl_launch(); pdl_wait();
     const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= n_vec) return;
     const int vec_per_pix = C / 8, cpg = C / G;
@@ -104,6 +107,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const __nv_bfloat16* __re
 // one warp per row of C channels (C % 8 == 0, C <= 1280): row cached in registers (two-pass variance).
 __global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, long rows, int C,
                                                         const float* __restrict__ gamma, const float* __restrict__ beta, float eps) {
+    pdl_launch(); pdl_wait();
     const long row = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= rows) return;
@@ -142,6 +146,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __r
 // ---------------------------------------------------------------------------------------------- softmax
 // P[row, 0:ldp] (bf16) = softmax(S[row, 0:Lk]) (fp32 logits, already scaled), zero beyond Lk.  One CTA of 128 threads per row.
 __global__ void __launch_bounds__(128) softmax_kernel(const float* __restrict__ S, long lds, __nv_bfloat16* __restrict__ P, long ldp, int Lk) {
+    pdl_launch(); pdl_wait();
     __shared__ float red[4];
     const long row = blockIdx.x;
     const float* s = S + row * lds;
@@ -166,6 +171,7 @@ __global__ void __launch_bounds__(128) softmax_kernel(const float* __restrict__ 
 // ---------------------------------------------------------------------------------------------- elementwise
 // GEGLU: y[r, c] = x[r, c] * gelu_erf(x[r, 4C' + c]),  x [rows, 2*H], y [rows, H]
 __global__ void __launch_bounds__(256) geglu_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, long rows, int Hd) {
+    pdl_launch(); pdl_wait();
     const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
     const int vpr = Hd / 8;
     if (idx >= rows * vpr) return;
@@ -179,12 +185,14 @@ __global__ void __launch_bounds__(256) geglu_kernel(const __nv_bfloat16* __restr
 }
 
 __global__ void __launch_bounds__(256) silu_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, long n) {
+    pdl_launch(); pdl_wait();
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) y[i] = __float2bfloat16(silu_f(__bfloat162float(x[i])));
 }
 
 // nearest 2x upsample, NHWC
 __global__ void __launch_bounds__(256) upsample2x_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int NB, int H, int W, int C) {
+    pdl_launch(); pdl_wait();
     const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
     const int vpp = C / 8;
     const long total = (long)NB * 4 * H * W * vpp;
@@ -198,6 +206,7 @@ __global__ void __launch_bounds__(256) upsample2x_kernel(const __nv_bfloat16* __
 // channel concat: y[..., 0:C1] = a, y[..., C1:C1+C2] = b
 __global__ void __launch_bounds__(256) concat_c_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b,
                                                        __nv_bfloat16* __restrict__ y, long pixels, int C1, int C2) {
+    pdl_launch(); pdl_wait();
     const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
     const int vpp = (C1 + C2) / 8;
     if (idx >= pixels * vpp) return;
@@ -212,6 +221,7 @@ __global__ void __launch_bounds__(256) concat_c_kernel(const __nv_bfloat16* __re
 // consecutive addresses (the whole table is 46 KB and stays in L1).
 __global__ void __launch_bounds__(256) conv_in_kernel(const float* __restrict__ x, const float* __restrict__ w /*[4][3][3][Cout]*/,
                                                       const float* __restrict__ bias, __nv_bfloat16* __restrict__ y, int NB, int H, int W, int Cout) {
+    pdl_launch(); pdl_wait();
     const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
     const int vpp = Cout / 8;
     if (idx >= (long)NB * H * W * vpp) return;
@@ -241,6 +251,7 @@ __global__ void __launch_bounds__(256) conv_in_kernel(const float* __restrict__ 
 // conv_out: 3x3, Cin -> 4, input NHWC bf16 (already normalised + SiLU), output NCHW fp32.  One warp per pixel.
 __global__ void __launch_bounds__(256) conv_out_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w /*[4][3][3][Cin]*/,
                                                        const float* __restrict__ bias, float* __restrict__ y, int NB, int H, int W, int Cin) {
+    pdl_launch(); pdl_wait();
     const long pix = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (pix >= (long)NB * H * W) return;
@@ -275,6 +286,7 @@ __global__ void __launch_bounds__(256) conv_out_kernel(const __nv_bfloat16* __re
 
 // sinusoidal timestep embedding [cos | sin] (flip_sin_to_cos, freq_shift 0), fp32 math, bf16 out, same t for all images
 __global__ void timestep_embedding_kernel(float t, int dim, int NB, __nv_bfloat16* __restrict__ out) {
+    pdl_launch(); pdl_wait();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int half = dim / 2;
     if (i >= half) return;
@@ -293,6 +305,7 @@ __global__ void __launch_bounds__(256) cfg_step_kernel(const float* __restrict__
                                                        const float* __restrict__ h1, const float* __restrict__ h2, const float* __restrict__ h3,
                                                        float c0, float c1, float c2, float c3, float cx, float ce,
                                                        const float* __restrict__ x_in, float* __restrict__ x_out) {
+    pdl_launch(); pdl_wait();
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float eu = eps2[i], et = eps2[n + i];
@@ -314,66 +327,66 @@ int op_groupnorm(const __nv_bfloat16* x, __nv_bfloat16* y, int NB, int HW, int C
     const int slabs_target = max(1, 256 / NB);
     int pix_per_cta = (HW + slabs_target - 1) / slabs_target;
     if (pix_per_cta < 8) pix_per_cta = HW < 8 ? HW : 8;
-    gn_stats_kernel<<<dim3((HW + pix_per_cta - 1) / pix_per_cta, NB), 256, 2 * G * sizeof(float), st>>>(x, HW, C, G, pix_per_cta, stats);
+    if (launch_k(gn_stats_kernel, dim3((HW + pix_per_cta - 1) / pix_per_cta, NB), dim3(256), 2 * G * sizeof(float), st, 1, x, HW, C, G, pix_per_cta, stats) != cudaSuccess) return (int)cudaGetLastError();
     OPS_CHECK();
     const long n_vec = (long)NB * HW * C / 8;
-    gn_apply_kernel<<<(unsigned)((n_vec + 255) / 256), 256, 0, st>>>(x, y, n_vec, HW, C, G, stats, gamma, beta, eps, silu);
+    if (launch_k(gn_apply_kernel, dim3((unsigned)((n_vec + 255) / 256)), dim3(256), 0, st, 1, x, y, n_vec, HW, C, G, stats, gamma, beta, eps, silu) != cudaSuccess) return (int)cudaGetLastError();
     OPS_CHECK();
     return 0;
 }
 int op_layernorm(const __nv_bfloat16* x, __nv_bfloat16* y, long rows, int C, const float* gamma, const float* beta, float eps, cudaStream_t st) {
-    layernorm_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(x, y, rows, C, gamma, beta, eps);
+    if (launch_k(layernorm_kernel, dim3((unsigned)((rows + 7) / 8)), dim3(256), 0, st, 1, x, y, rows, C, gamma, beta, eps) != cudaSuccess) return (int)cudaGetLastError();
     OPS_CHECK();
     return 0;
 }
 int op_softmax(const float* S, long lds, __nv_bfloat16* P, long ldp, long rows, int Lk, cudaStream_t st) {
-    softmax_kernel<<<(unsigned)rows, 128, 0, st>>>(S, lds, P, ldp, Lk);
+    if (launch_k(softmax_kernel, dim3((unsigned)rows), dim3(128), 0, st, 1, S, lds, P, ldp, Lk) != cudaSuccess) return (int)cudaGetLastError();
     OPS_CHECK();
     return 0;
 }
 int op_geglu(const __nv_bfloat16* x, __nv_bfloat16* y, long rows, int Hd, cudaStream_t st) {
     const long n = rows * (Hd / 8);
-    geglu_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, y, rows, Hd);
+    if (launch_k(geglu_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, 1, x, y, rows, Hd) != cudaSuccess) return (int)cudaGetLastError();
     OPS_CHECK();
     return 0;
 }
 int op_silu(const __nv_bfloat16* x, __nv_bfloat16* y, long n, cudaStream_t st) {
-    silu_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, y, n);
+    if (launch_k(silu_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, 1, x, y, n) != cudaSuccess) return (int)cudaGetLastError();
     OPS_CHECK();
     return 0;
 }
 int op_upsample2x(const __nv_bfloat16* x, __nv_bfloat16* y, int NB, int H, int W, int C, cudaStream_t st) {
     const long n = (long)NB * 4 * H * W * (C / 8);
-    upsample2x_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, y, NB, H, W, C);
+    if (launch_k(upsample2x_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, 1, x, y, NB, H, W, C) != cudaSuccess) return (int)cudaGetLastError();
     OPS_CHECK();
     return 0;
 }
 int op_concat_c(const __nv_bfloat16* a, const __nv_bfloat16* b, __nv_bfloat16* y, long pixels, int C1, int C2, cudaStream_t st) {
     const long n = pixels * ((C1 + C2) / 8);
-    concat_c_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(a, b, y, pixels, C1, C2);
+    if (launch_k(concat_c_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, 1, a, b, y, pixels, C1, C2) != cudaSuccess) return (int)cudaGetLastError();
     OPS_CHECK();
     return 0;
 }
 int op_conv_in(const float* x, const float* w, const float* bias, __nv_bfloat16* y, int NB, int H, int W, int Cout, cudaStream_t st) {
     const long n = (long)NB * H * W * (Cout / 8);
-    conv_in_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, w, bias, y, NB, H, W, Cout);
+    if (launch_k(conv_in_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, 1, x, w, bias, y, NB, H, W, Cout) != cudaSuccess) return (int)cudaGetLastError();
     OPS_CHECK();
     return 0;
 }
 int op_conv_out(const __nv_bfloat16* x, const float* w, const float* bias, float* y, int NB, int H, int W, int Cin, cudaStream_t st) {
     const long pix = (long)NB * H * W;
-    conv_out_kernel<<<(unsigned)((pix + 7) / 8), 256, 0, st>>>(x, w, bias, y, NB, H, W, Cin);
+    if (launch_k(conv_out_kernel, dim3((unsigned)((pix + 7) / 8)), dim3(256), 0, st, 1, x, w, bias, y, NB, H, W, Cin) != cudaSuccess) return (int)cudaGetLastError();
     OPS_CHECK();
     return 0;
 }
 int op_timestep_embedding(float t, int dim, int NB, __nv_bfloat16* out, cudaStream_t st) {
-    timestep_embedding_kernel<<<(dim / 2 + 127) / 128, 128, 0, st>>>(t, dim, NB, out);
+    if (launch_k(timestep_embedding_kernel, dim3((dim / 2 + 127) / 128), dim3(128), 0, st, 1, t, dim, NB, out) != cudaSuccess) return (int)cudaGetLastError();
     OPS_CHECK();
     return 0;
 }
 int op_cfg_step(const float* eps2, long n, float gs, float* eps_out, const float* h1, const float* h2, const float* h3, float c0, float c1,
                 float c2, float c3, float cx, float ce, const float* x_in, float* x_out, cudaStream_t st) {
-    cfg_step_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(eps2, n, gs, eps_out, h1, h2, h3, c0, c1, c2, c3, cx, ce, x_in, x_out);
+    if (launch_k(cfg_step_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, 1, eps2, n, gs, eps_out, h1, h2, h3, c0, c1, c2, c3, cx, ce, x_in, x_out) != cudaSuccess) return (int)cudaGetLastError();
     OPS_CHECK();
     return 0;
 }

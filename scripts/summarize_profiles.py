@@ -62,6 +62,10 @@ WANT = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "la
 launch_table(os.path.join(G, "launches.csv"), os.path.join(P, f"{tag}_solver_launches.txt"), "edit-solve (cfg2) kernel launch list",
              "ncu --metrics gpu__time_duration.sum --clock-control none python bench.py --steps 3 --warmup 3 --no-graph --no-cpu --no-denoise")
 launch_table(os.path.join(G, "launches_unet.csv"), os.path.join(P, f"{tag}_unet_launches.txt"), "one SD-1.4 U-Net call (NB=2, 64x64 latents) kernel launch list",
-             "ncu --metrics gpu__time_duration.sum --clock-control none -s 230 python scripts/unet_profile.py")
+             "ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off python scripts/unet_profile.py")
 raw_metrics(os.path.join(G, "prof_apply_tc.ncu-rep"), os.path.join(P, f"{tag}_apply_tc_ncu.txt"), "apply_tc_kernel (dominant kernel of the edit solve)", WANT)
 raw_metrics(os.path.join(G, "prof_chol_small.ncu-rep"), os.path.join(P, f"{tag}_chol_small_ncu.txt"), "chol_small_kernel (single-CTA factor)", WANT)
+raw_metrics(os.path.join(G, "prof_unet_gemm_pair.ncu-rep"), os.path.join(P, f"{tag}_unet_gemm_pair_ncu.txt"),
+            "unet_gemm_pair_kernel (third pair-GEMM launch of one SD-1.4 U-Net call: 128 CTAs = 64 pairs, 64x64 level, 320 channels)", WANT)
+raw_metrics(os.path.join(G, "prof_unet_attn.ncu-rep"), os.path.join(P, f"{tag}_unet_attn_ncu.txt"),
+            "unet_attn_kernel (first launch of one SD-1.4 U-Net call: self-attention over 4096 tokens, 8 heads, head dim 40 padded to 64)", WANT)

@@ -1,0 +1,27 @@
+#!/bin/bash
+# session 2, call 1: two-CTA apply (apply_tc2.cu) + register-resident diagonal factor: parity, traces, bench per variant
+set -u
+mkdir -p gpurun_out
+S=gpurun_out/status.txt; : > $S
+echo "== pytest tc2" | tee -a $S
+timeout 600 python -m pytest tests/test_solver_gpu.py -m gpu -q -x -p no:cacheprovider -k "two_cta or cfg2_full_model or intermediates" > gpurun_out/pytest_tc2.log 2>&1; echo "rc=$?" | tee -a $S
+tail -15 gpurun_out/pytest_tc2.log
+echo "== pytest solver rest" | tee -a $S
+timeout 900 python -m pytest tests/test_solver_gpu.py tests/test_drivers_gpu.py -m gpu -q -p no:cacheprovider -k "not two_cta and not cfg2_full_model and not intermediates" > gpurun_out/pytest_solver.log 2>&1; echo "rc=$?" | tee -a $S
+tail -5 gpurun_out/pytest_solver.log
+echo "== traces" | tee -a $S
+timeout 300 python scripts/trace_apply.py > gpurun_out/trace.log 2>&1; echo "rc=$?" | tee -a $S
+for v in "2 128" "3 128" "3 96" "3 88" "3 64"; do
+  set -- $v
+  echo "== bench impl $1 tile_rows $2" | tee -a $S
+  UCE_TC2_TILE_ROWS=$2 timeout 300 python bench.py --no-cpu --no-denoise --apply-impl $1 > gpurun_out/bench_$1_$2.json 2> gpurun_out/bench_$1_$2.err; echo "rc=$?" | tee -a $S
+  grep -E "profiled|timed region|e2e" gpurun_out/bench_$1_$2.err | tee -a $S
+done
+echo "== ncu launches (solver, auto impl)" | tee -a $S
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 100 --csv --log-file gpurun_out/launches.csv \
+    python bench.py --steps 3 --warmup 3 --no-graph --no-cpu --no-denoise > gpurun_out/ncu_bench.log 2>&1; echo "rc=$?" | tee -a $S
+grep -E "apply_tc2|chol_small|gram|q_emit|pack" gpurun_out/launches.csv | awk -F'","' '{print $5, $NF}' | sort | uniq -c | sort -rn | head -5
+echo "== ncu full apply_tc2" | tee -a $S
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:apply_tc2_kernel -s 3 -c 1 -f -o gpurun_out/prof_apply_tc2 \
+    python bench.py --steps 3 --warmup 3 --no-graph --no-cpu --no-denoise > gpurun_out/ncu_full.log 2>&1; echo "rc=$?" | tee -a $S
+ls -la gpurun_out/*.ncu-rep 2>/dev/null

@@ -106,7 +106,7 @@ def test_intermediates(n_edit, n_pres, K, fimpl):
     s.close()
 
 
-@pytest.mark.parametrize("impl", [1, 2])
+@pytest.mark.parametrize("impl", [1, 2, 3])
 def test_cfg2_full_model(impl):
     """BASELINE configs[1]: 50 erase + 100 preserve, all 32 SD-1.4 projections."""
     from uce_b200.synthetic import problem
@@ -283,5 +283,32 @@ def test_tcgen05_apply_matches_simt_and_oracle(n_edit, K, dims):
         assert O.rel_fro(b, a) <= 1e-5, ("tc vs simt", O.rel_fro(b, a))     # two fp32-fidelity paths, different summation orders
     tc2 = _run(s, C, G, scales, n_edit, 0.5, W, impl=2, inplace=True)
     for a, b in zip(tc, tc2):
+        assert torch.equal(a, b)
+    s.close()
+
+
+@pytest.mark.parametrize("tile_rows", [128, 88, 40])
+@pytest.mark.parametrize("n_edit,K,dims", [(2, 768, [320, 320]), (33, 768, [128, 64, 200]), (50, 768, [320, 640, 1280]),
+                                           (64, 256, [128, 384, 8]), (10, 2048, [640, 1280])])
+def test_two_cta_tcgen05_apply(n_edit, K, dims, tile_rows, monkeypatch):
+    """apply_tc2.cu (two co-resident CTAs per SM, rank pad <= 64) against the SIMT fp32 apply and the fp64 oracle:
+    full and ragged row tiles (UCE_TC2_TILE_ROWS), row tails, in place, SD-1.4 and SDXL text widths."""
+    from uce_b200.synthetic import concept_rows, weights
+    monkeypatch.setenv("UCE_TC2_TILE_ROWS", str(tile_rows))
+    n_pres = 20
+    rows = concept_rows(n_edit + n_pres + n_edit, K, seed=n_edit)
+    C, G = rows[: n_edit + n_pres], rows[n_edit + n_pres:]
+    W = weights(dims, K, seed=4)
+    scales = [1.0] * (n_edit + n_pres)
+    s = _solver(K, C.shape[0])
+    simt = _run(s, C, G, scales, n_edit, 0.5, W, impl=1)
+    tc = _run(s, C, G, scales, n_edit, 0.5, W, impl=3)
+    assert s.info()["launches_apply"] == 1
+    exact = O.erase_exact_f64(W, C[:n_edit], G, C[n_edit:], 1.0, 1.0, 0.5)
+    for a, b, e in zip(simt, tc, exact):
+        assert O.rel_fro(b, e) <= TOL_EXACT, ("tc2 vs exact", O.rel_fro(b, e), O.rel_fro(a, e))
+        assert O.rel_fro(b, a) <= 1e-5, ("tc2 vs simt", O.rel_fro(b, a))
+    inpl = _run(s, C, G, scales, n_edit, 0.5, W, impl=3, inplace=True)
+    for a, b in zip(tc, inpl):
         assert torch.equal(a, b)
     s.close()

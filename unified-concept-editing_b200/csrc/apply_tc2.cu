@@ -1,0 +1,488 @@
+// Fused low-rank apply, second generation: TWO co-resident CTAs per SM (rank_pad <= 64).
+//
+//   W_new[rows,:] = W_old[rows,:] + (W_old[rows,:] E^T) Q            (uce_sd_erase.py:45-82, see apply.cu)
+//
+// Same algebra, operands and fp32 fidelity (3xTF32, lo.lo dropped) as apply_tc.cu.  What changes is the shape of a CTA:
+// apply_tc.cu runs ONE 352-thread CTA per SM with all 512 TMEM columns and 198 KB of shared memory, so the HBM read
+// phase (A) and the L2-read / HBM-write phase (B) of a row tile run strictly one after the other on every SM, and the
+// 200 row tiles of an SD-1.4 edit take two waves on 148 SMs (ncu: SMs 55 % active, profiles/r01_apply_tc_ncu.txt).
+// Here a CTA is half as large — 224 threads, 256 TMEM columns, <= 98 KB of shared memory — so two of them share an SM:
+//   * all row tiles of an SD-1.4 edit are resident at once (296 slots): no second wave;
+//   * phase A of one tile overlaps phase B of the other: the SM's TMA ingest, tensor pipe and store path stay busy.
+//
+//   phase A  P[128,R] = W_tile[128,K] . E[R,K]^T in TMEM columns [0,R)
+//            * W TMA warp: raw fp32 chunks [tile_rows x 32] into a 3-deep ring (L2 evict_last)
+//            * 4 transform warps (thread = tile row = TMEM lane): hi = rna_tf32(w), lo = w - hi, tcgen05.st into one
+//              of three 64-column A stages at TMEM columns [64,256)
+//            * E TMA warp: [R x 32] tiles of the pre-split E_hi, E_lo (3-deep ring)
+//            * MMA thread: per 8-wide k-step  hi.hi + hi.lo + lo.hi  (three N = R MMAs, A from TMEM)
+//   phase B  dW^T[128 W columns, 128 rows] = Qt[128,R] . P[128,R]^T per 128-column chunk, two ping-pong accumulators
+//            at TMEM columns [0,128) and [128,256) (they alias phase A, which is drained by then)
+//            * P: TMEM -> registers -> hi/lo -> swizzled smem (B operand)
+//            * Qt_hi / Qt_lo [128 x 32] tiles by TMA through a ring of 16 KB slots
+//            * epilogue (lane = W column, register = tile row): coalesced W_old addend loads (L2 hits, issued one
+//              32-row group ahead) and W_new stores (L2 evict_first)
+//
+// tile_rows (<= 128, multiple of 8) is a launch parameter: the TMA box, the row stride between tiles and the rows a CTA
+// stores; the MMAs always run M = 128 (rows beyond the box compute garbage that is never stored: rows are independent).
+#include "uce_ws.h"
+#include "tc_common.cuh"
+#include <cstdint>
+#include <cstdlib>
+#include <vector>
+
+namespace uce {
+namespace tc2 {
+using namespace uce::tc;
+
+constexpr int PW = 4;                                   // transform / P-conversion / epilogue warps
+constexpr int THREADS = (PW + 3) * 32;                  // + W TMA warp + E/Qt TMA warp + MMA warp
+constexpr int NRAW = 3, NSA = 3, NE = 3;
+constexpr int MAX_LAYERS = 160;
+constexpr int WARP_W_TMA = PW, WARP_E_TMA = PW + 1, WARP_MMA = PW + 2;
+constexpr uint32_t A_COL0 = 64;                         // A stages {W_hi 32 cols, W_lo 32 cols} at TMEM columns [64,256)
+constexpr uint32_t TMEM_COLS = 256;
+
+struct Maps { CUtensorMap e_hi, e_lo, qt_hi, qt_lo; };
+struct WMaps { CUtensorMap w[MAX_LAYERS]; };
+
+__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+          "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]),
+          "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]),
+          "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31]) : "memory");
+}
+__device__ __forceinline__ float tf32_hi(float x) {
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+    return __uint_as_float(u);
+}
+__device__ __forceinline__ uint64_t l2_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ float ldg_f32(const float* p) {
+    float r;
+    asm volatile("ld.global.f32 %0, [%1];" : "=f"(r) : "l"(p) : "memory");
+    return r;
+}
+__device__ __forceinline__ void stg_f32_hint(float* p, float v, uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(p), "f"(v), "l"(pol) : "memory");
+}
+__device__ __forceinline__ float4 lds_v4(uint32_t addr) {
+    float4 r;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(addr) : "memory");
+    return r;
+}
+__device__ __forceinline__ void sts_v4(uint32_t addr, float a, float b, float c, float d) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_hint(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, uint64_t pol) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+                 ::"r"(dst), "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1), "l"(pol) : "memory");
+}
+__device__ __forceinline__ int find_layer(const LayerRef* layers, int n_layers, int tile) {
+    int lo = 0, hi = n_layers - 1;
+    while (lo < hi) {
+        int mid = (lo + hi + 1) >> 1;
+        if (layers[mid].tile_begin <= tile) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+
+// Shared-memory carve-up (bytes), identical on host and device.
+//   phase A   [0, 48K) raw ring: NRAW x 16 KB slots (a [tile_rows x 32] fp32 chunk of W each)
+//             [48K, 48K + NE * e_stage) E ring: {E_hi R*128 B, E_lo R*128 B} per stage
+//   phase B   [0, nq * 16K) Qt ring (one [128 x 32] tile of Qt_hi or Qt_lo per slot)
+//             [nq * 16K, + 2*128*R*4) P_hi | P_lo per 32-wide r atom       (aliases phase A, written after it is drained)
+struct Smem { int nq, e_stage, e_off, p_off, bar_off, total; };
+__host__ __device__ inline Smem smem_layout(int R) {
+    Smem s;
+    s.nq = (R <= 32) ? 3 : 2;
+    s.e_stage = 2 * R * 128;
+    s.e_off = NRAW * 16384;
+    s.p_off = s.nq * 16384;
+    const int end_a = s.e_off + NE * s.e_stage;
+    const int end_b = s.p_off + 2 * 128 * R * 4;
+    s.bar_off = end_a > end_b ? end_a : end_b;
+    s.total = s.bar_off + 512;
+    return s;
+}
+
+__global__ void __launch_bounds__(THREADS, 2)
+apply_tc2_kernel(const LayerRef* __restrict__ layers, int n_layers, int K, int R, int tile_rows,
+                 const __grid_constant__ Maps maps, const __grid_constant__ WMaps wmaps, long long* __restrict__ trace) {
+    // optional timeline of CTA 0 (UCE_TC_TRACE=<file>): trace[(role * 64 + index) * 4 + event] = clock64()
+    auto tr = [&](int role, int idx, int ev) {
+        if (trace && blockIdx.x == 0 && idx < 64) trace[(role * 64 + idx) * 4 + ev] = clock64();
+    };
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;      // swizzled tiles need 1024-byte alignment
+    const Smem L = smem_layout(R);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    // ---- barriers ----
+    const uint32_t bars = base + L.bar_off;
+    auto bar_raw_full  = [&](int r) { return bars + 8u * r; };                 // [0,3)   W TMA -> transform warps
+    auto bar_raw_empty = [&](int r) { return bars + 8u * (3 + r); };           // [3,6)
+    auto bar_a_full    = [&](int s) { return bars + 8u * (6 + s); };           // [6,9)   transform warps -> MMA (A stage written)
+    auto bar_a_empty   = [&](int s) { return bars + 8u * (9 + s); };           // [9,12)  MMA -> transform warps
+    auto bar_e_full    = [&](int s) { return bars + 8u * (12 + s); };          // [12,15) E TMA -> MMA
+    auto bar_e_empty   = [&](int s) { return bars + 8u * (15 + s); };          // [15,18)
+    const uint32_t bar_p_full = bars + 8u * 18, bar_p_smem = bars + 8u * 19;
+    auto bar_q_full    = [&](int t) { return bars + 8u * (20 + t); };          // [20,23)
+    auto bar_q_empty   = [&](int t) { return bars + 8u * (23 + t); };          // [23,26)
+    auto bar_acc_full  = [&](int b) { return bars + 8u * (26 + b); };          // [26,28)
+    auto bar_acc_empty = [&](int b) { return bars + 8u * (28 + b); };          // [28,30)
+    const uint32_t tmem_slot = bars + 8u * 30;
+
+    const int tile = blockIdx.x;
+    const int layer = find_layer(layers, n_layers, tile);
+    const LayerRef Lr = layers[layer];
+    const int row0 = (tile - Lr.tile_begin) * tile_rows;
+    const int rows_valid = min(tile_rows, Lr.d - row0);
+    const float* __restrict__ w_old = Lr.w_old + (size_t)row0 * K;
+    float* __restrict__ w_new = Lr.w_new + (size_t)row0 * K;
+    const int n_chunks = K / 32;          // phase A k-chunks (32 fp32 = one swizzle atom row)
+    const int n_kc = K / 128;             // phase B chunks of 128 W columns
+    const int n_rc = R / 32;              // r atoms
+    const int NQ = L.nq;
+
+    if (threadIdx.x == 0) {
+        for (int r = 0; r < NRAW; ++r) { mbar_init(bar_raw_full(r), 1); mbar_init(bar_raw_empty(r), PW); }
+        for (int s = 0; s < NSA; ++s) { mbar_init(bar_a_full(s), PW); mbar_init(bar_a_empty(s), 1); }
+        for (int s = 0; s < NE; ++s) { mbar_init(bar_e_full(s), 1); mbar_init(bar_e_empty(s), 1); }
+        for (int t = 0; t < 3; ++t) { mbar_init(bar_q_full(t), 1); mbar_init(bar_q_empty(t), 1); }
+        mbar_init(bar_p_full, 1); mbar_init(bar_p_smem, PW);
+        for (int b = 0; b < 2; ++b) { mbar_init(bar_acc_full(b), 1); mbar_init(bar_acc_empty(b), PW); }
+        mbar_fence_init();
+    }
+    if (warp == WARP_MMA) tmem_alloc(tmem_slot, TMEM_COLS);      // half of the SM's tensor memory: the co-resident CTA owns the rest
+    if (warp == WARP_E_TMA && lane == 0) {
+        tma_prefetch_desc(&wmaps.w[layer]);
+        tma_prefetch_desc(&maps.e_hi); tma_prefetch_desc(&maps.e_lo); tma_prefetch_desc(&maps.qt_hi); tma_prefetch_desc(&maps.qt_lo);
+    }
+    fence_before();
+    __syncthreads();
+    fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    auto raw_st = [&](int r) { return base + (uint32_t)(r * 16384); };
+    auto stage_e_hi = [&](int s) { return base + (uint32_t)(L.e_off + s * L.e_stage); };
+    auto stage_e_lo = [&](int s) { return base + (uint32_t)(L.e_off + s * L.e_stage + R * 128); };
+    auto p_hi_atom = [&](int rc) { return base + (uint32_t)(L.p_off + rc * 32768); };              // [P_hi(rc) 128 rows | P_lo(rc) 128 rows]
+    auto p_lo_atom = [&](int rc) { return base + (uint32_t)(L.p_off + rc * 32768 + 16384); };
+    auto qt_slot = [&](int t) { return base + (uint32_t)(t * 16384); };
+
+    if (warp < PW) {
+        // =============================== W transform, then P conversion, then epilogue ===============================
+        const int trow = 32 * warp + lane;               // tile row == TMEM lane
+        const bool row_live = trow < rows_valid;
+        const uint32_t lane_base = tmem_base + ((uint32_t)(32 * warp) << 16);
+        for (int c = 0; c < n_chunks; ++c) {
+            const int r = c % NRAW, s = c % NSA;
+            mbar_wait(bar_raw_full(r), (uint32_t)((c / NRAW) & 1));
+            if (threadIdx.x == 0) tr(1, c, 0);
+            const uint32_t raw = raw_st(r) + (uint32_t)(trow * 128);
+            uint32_t hi[32], lo[32];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (row_live) v = lds_v4(raw + (uint32_t)(((j ^ (trow & 7)) << 4)));      // swizzled 16-byte slot the TMA wrote
+                const float x[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float h = tf32_hi(x[e]);
+                    hi[4 * j + e] = __float_as_uint(h);
+                    lo[4 * j + e] = __float_as_uint(x[e] - h);
+                }
+            }
+            mbar_wait(bar_a_empty(s), (uint32_t)(((c / NSA) & 1) ^ 1));      // the MMAs that read this A stage have completed
+            if (threadIdx.x == 0) tr(1, c, 1);
+            fence_after();
+            const uint32_t ta = lane_base + A_COL0 + (uint32_t)(64 * s);
+            tmem_st32(ta, hi);
+            tmem_st32(ta + 32u, lo);
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            fence_before();
+            __syncwarp();
+            if (lane == 0) { mbar_arrive(bar_a_full(s)); mbar_arrive(bar_raw_empty(r)); }
+            if (threadIdx.x == 0) tr(1, c, 2);
+        }
+        // ---- P: TMEM -> registers -> hi/lo -> swizzled smem (B operand of phase B) ----
+        mbar_wait(bar_p_full, 0);
+        if (threadIdx.x == 0) tr(6, 0, 0);
+        fence_after();
+        for (int rc = 0; rc < n_rc; ++rc) {
+            uint32_t v[32];
+            tmem_ld32(lane_base + (uint32_t)(rc * 32), v);
+            const uint32_t hb = p_hi_atom(rc), lb = p_lo_atom(rc);
+#pragma unroll
+            for (int ch = 0; ch < 8; ++ch) {
+                const uint32_t off = (uint32_t)(trow * 128 + ((ch ^ (trow & 7)) << 4));
+                const float a = __uint_as_float(v[4 * ch]), b = __uint_as_float(v[4 * ch + 1]);
+                const float cc = __uint_as_float(v[4 * ch + 2]), d = __uint_as_float(v[4 * ch + 3]);
+                const float ha = tf32_hi(a), hb2 = tf32_hi(b), hc = tf32_hi(cc), hd = tf32_hi(d);
+                sts_v4(hb + off, ha, hb2, hc, hd);
+                sts_v4(lb + off, a - ha, b - hb2, cc - hc, d - hd);
+            }
+        }
+        fence_proxy_async();
+        fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_p_smem);
+        // ---- epilogue: W_new = W_old + dW, transposed accumulator (lane = W column, TMEM column = tile row) ----
+        // groups of 32 tile rows; the addend of group t+1 is requested before group t is combined and stored
+        const uint64_t pol_stream = l2_evict_first();
+        const int n_groups = n_kc * 4;
+        float wa[32], wb[32];
+        auto load_addend = [&](float (&w)[32], int t) {
+            const int kc = t >> 2, g = t & 3;
+            const float* wp = w_old + (size_t)(32 * g) * K + (kc * 128 + 32 * warp + lane);
+            const int live = rows_valid - 32 * g;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) w[i] = (i < live) ? ldg_f32(wp + (size_t)i * K) : 0.f;
+        };
+        auto finish_group = [&](float (&w)[32], int t) {
+            const int kc = t >> 2, g = t & 3, b = kc & 1;
+            if (g == 0) {
+                mbar_wait(bar_acc_full(b), (uint32_t)((kc >> 1) & 1));
+                if (threadIdx.x == 0) tr(5, kc, 1);
+                fence_after();
+            }
+            uint32_t v[32];
+            tmem_ld32(lane_base + (uint32_t)(128 * b + 32 * g), v);
+            float* op = w_new + (size_t)(32 * g) * K + (kc * 128 + 32 * warp + lane);
+            const int live = rows_valid - 32 * g;
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+                if (i < live) stg_f32_hint(op + (size_t)i * K, w[i] + __uint_as_float(v[i]), pol_stream);
+            if (g == 3) {
+                fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_acc_empty(b));
+                if (threadIdx.x == 0) tr(5, kc, 2);
+            }
+        };
+        load_addend(wa, 0);
+        if (threadIdx.x == 0) tr(5, 0, 0);
+        for (int t = 0; t < n_groups; t += 2) {          // n_groups is a multiple of 4
+            load_addend(wb, t + 1);
+            finish_group(wa, t);
+            if (t + 2 < n_groups) load_addend(wa, t + 2);
+            finish_group(wb, t + 1);
+        }
+    } else if (warp == WARP_W_TMA) {
+        // =============================== TMA warp 1: raw W chunks ===============================
+        if (lane == 0) {
+            const uint64_t pol_keep = l2_evict_last();     // the tile is read again by the epilogue: keep it in L2
+            const CUtensorMap* wm = &wmaps.w[layer];
+            const uint32_t bytes = (uint32_t)tile_rows * 128u;
+            for (int c = 0; c < n_chunks; ++c) {
+                const int r = c % NRAW;
+                mbar_wait(bar_raw_empty(r), (uint32_t)(((c / NRAW) & 1) ^ 1));
+                tr(0, c, 0);
+                mbar_arrive_expect_tx(bar_raw_full(r), bytes);
+                tma_load_2d_hint(raw_st(r), wm, bar_raw_full(r), c * 32, row0, pol_keep);
+            }
+        }
+    } else if (warp == WARP_E_TMA) {
+        // =============================== TMA warp 2: E tiles (phase A), Qt tiles (phase B) ===============================
+        if (lane == 0) {
+            const uint32_t e_bytes = 2u * (uint32_t)R * 128u;
+            for (int c = 0; c < n_chunks; ++c) {
+                const int s = c % NE;
+                mbar_wait(bar_e_empty(s), (uint32_t)(((c / NE) & 1) ^ 1));
+                tr(2, c, 0);
+                mbar_arrive_expect_tx(bar_e_full(s), e_bytes);
+                tma_load_2d(stage_e_hi(s), &maps.e_hi, bar_e_full(s), c * 32, 0);
+                tma_load_2d(stage_e_lo(s), &maps.e_lo, bar_e_full(s), c * 32, 0);
+            }
+            // the Qt ring aliases the raw ring: every phase-A MMA has completed once P is final, and an MMA on an A stage
+            // completes only after all four transform warps have read that raw chunk
+            mbar_wait(bar_p_full, 0);
+            int it = 0;
+            for (int kc = 0; kc < n_kc; ++kc)
+                for (int rc = 0; rc < n_rc; ++rc)
+                    for (int hl = 0; hl < 2; ++hl, ++it) {
+                        const int t = it % NQ;
+                        mbar_wait(bar_q_empty(t), (uint32_t)(((it / NQ) & 1) ^ 1));
+                        mbar_arrive_expect_tx(bar_q_full(t), 16384u);
+                        tma_load_2d(qt_slot(t), hl ? &maps.qt_lo : &maps.qt_hi, bar_q_full(t), rc * 32, kc * 128);
+                    }
+        }
+    } else {
+        // =============================== MMA issuer ===============================
+        if (lane == 0) {
+            const uint32_t idesc_a = idesc_tf32(128, R);
+            for (int c = 0; c < n_chunks; ++c) {
+                const int s = c % NSA, se = c % NE;
+                mbar_wait(bar_e_full(se), (uint32_t)((c / NE) & 1));
+                tr(3, c, 0);
+                mbar_wait(bar_a_full(s), (uint32_t)((c / NSA) & 1));
+                tr(3, c, 1);
+                fence_after();
+                const uint32_t a_hi = tmem_base + A_COL0 + (uint32_t)(64 * s), a_lo = a_hi + 32u;
+                const uint64_t b_hi = umma_desc_sw128(stage_e_hi(se)), b_lo = umma_desc_sw128(stage_e_lo(se));
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {          // 8 tf32 per step: 8 TMEM columns of A, 32 bytes inside the swizzle atom of B
+                    const uint64_t adv = (uint64_t)(k * 2);
+                    umma_tf32_ts(tmem_base, a_hi + 8u * k, b_hi + adv, idesc_a, (c | k) != 0);
+                    umma_tf32_ts(tmem_base, a_hi + 8u * k, b_lo + adv, idesc_a, 1);
+                    umma_tf32_ts(tmem_base, a_lo + 8u * k, b_hi + adv, idesc_a, 1);
+                }
+                umma_commit(bar_a_empty(s));
+                umma_commit(bar_e_empty(se));
+                tr(3, c, 2);
+            }
+            umma_commit(bar_p_full);
+            // ---- phase B ----
+            mbar_wait(bar_p_smem, 0);
+            fence_after();
+            const uint32_t idesc_b = idesc_tf32(128, 128);
+            int it = 0;
+            for (int kc = 0; kc < n_kc; ++kc) {
+                const int b = kc & 1;
+                mbar_wait(bar_acc_empty(b), (uint32_t)(((kc >> 1) & 1) ^ 1));
+                tr(4, kc, 0);
+                fence_after();
+                const uint32_t d_tmem = tmem_base + 128u * (uint32_t)b;
+                for (int rc = 0; rc < n_rc; ++rc) {
+                    const uint64_t b_hi = umma_desc_sw128(p_hi_atom(rc)), b_lo = umma_desc_sw128(p_lo_atom(rc));
+                    int t = it % NQ;
+                    mbar_wait(bar_q_full(t), (uint32_t)((it / NQ) & 1));
+                    fence_after();
+                    uint64_t a = umma_desc_sw128(qt_slot(t));                 // Qt_hi tile: hi.hi + hi.lo
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const uint64_t adv = (uint64_t)(k * 2);
+                        umma_tf32(d_tmem, a + adv, b_hi + adv, idesc_b, (rc | k) != 0);
+                        umma_tf32(d_tmem, a + adv, b_lo + adv, idesc_b, 1);
+                    }
+                    umma_commit(bar_q_empty(t));
+                    ++it;
+                    t = it % NQ;
+                    mbar_wait(bar_q_full(t), (uint32_t)((it / NQ) & 1));
+                    fence_after();
+                    a = umma_desc_sw128(qt_slot(t));                          // Qt_lo tile: lo.hi
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const uint64_t adv = (uint64_t)(k * 2);
+                        umma_tf32(d_tmem, a + adv, b_hi + adv, idesc_b, 1);
+                    }
+                    umma_commit(bar_q_empty(t));
+                    ++it;
+                }
+                umma_commit(bar_acc_full(b));
+                tr(4, kc, 1);
+            }
+        }
+    }
+    // ---- teardown ----
+    fence_before();
+    __syncthreads();
+    if (warp == WARP_MMA) {
+        fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+// row-major [rows, cols] fp32, box [box_rows, 32 cols], 128B swizzle
+static int make_map(CUtensorMap* m, const float* ptr, int rows, int cols, int box_rows) {
+    EncodeTiledFn enc = tensor_map_encoder();
+    if (!enc) { set_error("cuTensorMapEncodeTiled entry point not found"); return UCE_E_STATE; }
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)cols * sizeof(float)};
+    cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1u, 1u};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return UCE_E_STATE; }
+    return 0;
+}
+
+}  // namespace tc2
+
+bool apply_tc2_available(const uce_ws* ws) {
+    const int R = ws->rank_pad;
+    return ws->K % 128 == 0 && (R == 32 || R == 64) && !ws->dense && ws->rank > 0 && tensor_map_encoder() != nullptr;
+}
+
+// Rows per tile: UCE_TC2_TILE_ROWS (multiple of 8 in [8,128], read on every call) or 128.
+int apply_tc2_tile_rows() {
+    if (const char* e = getenv("UCE_TC2_TILE_ROWS")) {
+        const int t = atoi(e);
+        if (t >= 8 && t <= 128 && t % 8 == 0) return t;
+    }
+    return 128;
+}
+
+int apply_tc2_lowrank(uce_ws* ws, const LayerRef* layers_dev, const LayerRef* layers_host, int n_layers, int total_tiles,
+                      int tile_rows, cudaStream_t st, int* launches) {
+    using namespace tc2;
+    const int K = ws->K, R = ws->rank_pad;
+    if (!apply_tc2_available(ws)) { set_error("two-CTA tcgen05 apply unavailable for K=%d rank_pad=%d dense=%d", K, R, ws->dense); return UCE_E_STATE; }
+    if (n_layers > MAX_LAYERS) { set_error("tcgen05 apply takes at most %d projections per call", MAX_LAYERS); return UCE_E_STATE; }
+    for (int l = 0; l < n_layers; ++l)
+        if (((uintptr_t)layers_host[l].w_old & 15) || ((uintptr_t)layers_host[l].w_new & 15)) { set_error("tcgen05 apply needs 16-byte aligned weights"); return UCE_E_ARG; }
+    Maps maps;
+    static WMaps wmaps;      // 20 KB: kept off the stack; copied into the launch by value
+    int rc;
+    if ((rc = make_map(&maps.e_hi, ws->E_hi, R, K, R))) return rc;
+    if ((rc = make_map(&maps.e_lo, ws->E_lo, R, K, R))) return rc;
+    if ((rc = make_map(&maps.qt_hi, ws->Qt_hi, K, R, 128))) return rc;
+    if ((rc = make_map(&maps.qt_lo, ws->Qt_lo, K, R, 128))) return rc;
+    for (int l = 0; l < n_layers; ++l)
+        if ((rc = make_map(&wmaps.w[l], layers_host[l].w_old, layers_host[l].d, K, tile_rows))) return rc;
+    const Smem L = smem_layout(R);
+    const int smem = L.total + 1024;   // slack for the manual 1024-byte alignment
+    static int configured = 0;
+    if (configured < smem) {
+        UCE_CUDA(cudaFuncSetAttribute(apply_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        UCE_CUDA(cudaFuncSetAttribute(apply_tc2_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        configured = smem;
+    }
+    long long* trace = nullptr;
+    const char* trace_path = getenv("UCE_TC_TRACE");
+    if (trace_path) { UCE_CUDA(cudaMalloc(&trace, 7 * 64 * 4 * sizeof(long long))); UCE_CUDA(cudaMemsetAsync(trace, 0, 7 * 64 * 4 * sizeof(long long), st)); }
+    apply_tc2_kernel<<<total_tiles, THREADS, smem, st>>>(layers_dev, n_layers, K, R, tile_rows, maps, wmaps, trace);
+    UCE_LAUNCH_CHECK();
+    *launches += 1;
+    if (trace) {   // debugging aid: dump the timeline of CTA 0 (synchronises)
+        std::vector<long long> h(7 * 64 * 4);
+        UCE_CUDA(cudaStreamSynchronize(st));
+        UCE_CUDA(cudaMemcpy(h.data(), trace, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+        UCE_CUDA(cudaFree(trace));
+        if (FILE* f = fopen(trace_path, "w")) {
+            long long t0 = 0;
+            for (long long v : h) if (v && (!t0 || v < t0)) t0 = v;
+            const char* roles[7] = {"w_tma", "transform", "e_tma", "mma_a", "mma_b", "epilogue", "pconv"};
+            for (int r = 0; r < 7; ++r) for (int i = 0; i < 64; ++i) {
+                const long long* e = &h[(r * 64 + i) * 4];
+                if (e[0] || e[1] || e[2]) fprintf(f, "%s %d %lld %lld %lld\n", roles[r], i, e[0] ? e[0] - t0 : -1, e[1] ? e[1] - t0 : -1, e[2] ? e[2] - t0 : -1);
+            }
+            fclose(f);
+        }
+    }
+    return 0;
+}
+
+}  // namespace uce

@@ -84,6 +84,36 @@ __device__ __forceinline__ double fs_rsqrt(double d) {
     return fma(0.5 * y, e, y);
 }
 
+// Cholesky of one 32 x 32 diagonal block (pitch 33, lower triangle) by ONE warp, register resident: lane = row,
+// a[c] = column c of that row; right-looking, pivot and column broadcasts by shuffles.  Kept out of line so that its
+// 64 registers of matrix state do not compete with the rest of chol_small_kernel.
+__device__ __noinline__ void fs_potrf_warp(double* __restrict__ D, double* __restrict__ invd_blk, int lane, int* flag, int kb) {
+    double a[FS_NB];
+#pragma unroll
+    for (int c = 0; c < FS_NB; ++c) a[c] = D[lane * (FS_NB + 1) + c];
+    bool bad = false;
+    double yinv = 1.0;
+#pragma unroll
+    for (int j = 0; j < FS_NB; ++j) {
+        double d = __shfl_sync(0xffffffffu, a[j], j);
+        if (!(d > 0.0)) { bad = true; d = 1.0; }
+        const double y = fs_rsqrt(d);
+        const double l = (lane == j) ? d * y : a[j] * y;      // L[lane][j] for lanes >= j (unused garbage above the diagonal)
+        a[j] = l;
+        if (lane == j) yinv = y;
+#pragma unroll
+        for (int k = j + 1; k < FS_NB; ++k) {                 // a[lane][k] -= L[lane][j] L[k][j]   (k = j + 1 first: the next pivot)
+            const double lk = __shfl_sync(0xffffffffu, l, k);
+            a[k] = fma(-l, lk, a[k]);
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < FS_NB; ++c)
+        if (c <= lane) D[lane * (FS_NB + 1) + c] = a[c];
+    invd_blk[lane] = yinv;
+    if (bad && lane == 0) atomicCAS(flag, 0, 1 + kb);
+}
+
 __global__ void __launch_bounds__(FS_T, 1)
 chol_small_kernel(double* __restrict__ Hg, int n, int n_pad, const double* __restrict__ dadd, int n_pres, int n_edit,
                   double* __restrict__ Z, int ldz, int write_back, int* flag, long long* __restrict__ trace) {
@@ -118,32 +148,11 @@ chol_small_kernel(double* __restrict__ Hg, int n, int n_pad, const double* __res
     for (int kb = 0; kb < nblk; ++kb) {
         double* D = SB + fs_blk(kb, kb);
         const int o = kb * FS_NB;
-        // (a) left-looking Cholesky of the diagonal block by one warp (lane = row); no stores inside the dot products
-        if (warp == 0) {
-            bool bad = false;
-            for (int j = 0; j < FS_NB; ++j) {
-                // four independent partial sums: the fp64 FMA chain, not the loads, is the critical path here
-                double acc = D[lane * (FS_NB + 1) + j], a1 = 0.0, a2 = 0.0, a3 = 0.0, a4 = 0.0, a5 = 0.0, a6 = 0.0, a7 = 0.0;
-                const double* ri = D + lane * (FS_NB + 1);
-                const double* rj = D + j * (FS_NB + 1);
-                int k = 0;
-                for (; k + 8 <= j; k += 8) {
-                    acc = fma(-ri[k], rj[k], acc); a1 = fma(-ri[k + 1], rj[k + 1], a1);
-                    a2 = fma(-ri[k + 2], rj[k + 2], a2); a3 = fma(-ri[k + 3], rj[k + 3], a3);
-                    a4 = fma(-ri[k + 4], rj[k + 4], a4); a5 = fma(-ri[k + 5], rj[k + 5], a5);
-                    a6 = fma(-ri[k + 6], rj[k + 6], a6); a7 = fma(-ri[k + 7], rj[k + 7], a7);
-                }
-                for (; k < j; ++k) acc = fma(-ri[k], rj[k], acc);
-                acc += ((a1 + a2) + (a3 + a4)) + ((a5 + a6) + a7);
-                double d = __shfl_sync(0xffffffffu, acc, j);
-                if (!(d > 0.0)) { bad = true; d = 1.0; }
-                const double y = fs_rsqrt(d);
-                if (lane == j) { D[j * (FS_NB + 1) + j] = d * y; invd[o + j] = y; }
-                else if (lane > j) D[lane * (FS_NB + 1) + j] = acc * y;
-                __syncwarp();
-            }
-            if (bad && lane == 0) atomicCAS(flag, 0, 1 + kb);
-        }
+        // (a) Cholesky of the diagonal block by one warp, REGISTER resident (lane = row, a[c] = column c of that row):
+        //     right-looking, pivot and column broadcasts by shuffles.  The chain between two pivots is one shuffle, the
+        //     reciprocal square root, one multiply, one shuffle and one FMA (~200 cycles); the shared-memory left-looking
+        //     version it replaces needed ~830 (dependent LDS -> DFMA chains and a store/load round trip per column).
+        if (warp == 0) fs_potrf_warp(D, invd + o, lane, flag, kb);
         __syncthreads();
         tr();   // diag block factored
         // (b) inverse of L_kk by column sweeps (warp = column c, lane = row): x_j = (delta_jc - acc_j) / L_jj

@@ -73,6 +73,12 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         }
     }
 }
+// one lane of a converged warp (see tc_common.cuh: behind `lane == 0` ptxas wraps every UTCHMMA / UTMALDG in an ELECT loop)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -397,12 +403,13 @@ apply_tc_kernel(const LayerRef* __restrict__ layers, int n_layers, int K, int R,
         }
     } else if (warp == WARP_W_TMA) {
         // =============================== TMA warp 1: raw W chunks, TC_NRAW deep ===============================
-        if (lane == 0) {
-            const uint64_t pol_keep = l2_policy_evict_last();     // the tile is read again by the epilogue: keep it in L2
-            const CUtensorMap* wm = &wmaps.w[layer];
-            for (int c = 0; c < n_chunks; ++c) {
-                const int r = c % TC_NRAW;
-                mbar_wait(bar_raw_empty(r), (uint32_t)(((c / TC_NRAW) & 1) ^ 1));
+        const uint64_t pol_keep = l2_policy_evict_last();     // the tile is read again by the epilogue: keep it in L2
+        const CUtensorMap* wm = &wmaps.w[layer];
+        for (int c = 0; c < n_chunks; ++c) {
+            const int r = c % TC_NRAW;
+            mbar_wait(bar_raw_empty(r), (uint32_t)(((c / TC_NRAW) & 1) ^ 1));
+            __syncwarp();
+            if (elect_one()) {
                 tr(0, c, 0);
                 mbar_arrive_expect_tx(bar_raw_full(r), 16384u);
                 tma_load_2d_hint(raw_st(r), wm, bar_raw_full(r), c * 32, lt * TC_TILE_M, pol_keep);
@@ -410,44 +417,49 @@ apply_tc_kernel(const LayerRef* __restrict__ layers, int n_layers, int K, int R,
         }
     } else if (warp == WARP_E_TMA) {
         // =============================== TMA warp 2: E tiles (phase A), Qt tiles (phase B) ===============================
-        if (lane == 0) {
-            const uint32_t e_bytes = 2u * (uint32_t)R * 128u;
-            for (int c = 0; c < n_chunks; ++c) {
-                const int s = c % NE;
-                mbar_wait(bar_empty_e(s), (uint32_t)(((c / NE) & 1) ^ 1));
+        const uint32_t e_bytes = 2u * (uint32_t)R * 128u;
+        for (int c = 0; c < n_chunks; ++c) {
+            const int s = c % NE;
+            mbar_wait(bar_empty_e(s), (uint32_t)(((c / NE) & 1) ^ 1));
+            __syncwarp();
+            if (elect_one()) {
                 tr(2, c, 0);
                 mbar_arrive_expect_tx(bar_full_e(s), e_bytes);
                 tma_load_2d(stage_e_hi(s), &maps.e_hi, bar_full_e(s), c * 32, 0);
                 tma_load_2d(stage_e_lo(s), &maps.e_lo, bar_full_e(s), c * 32, 0);
             }
-            // the Qt ring aliases the raw ring and the E ring: both must be drained (all phase A MMAs complete)
-            for (int r = 0; r < TC_NRAW; ++r) {
-                const int uses = (n_chunks - r + TC_NRAW - 1) / TC_NRAW;      // completed phases of raw_empty[r]
-                if (uses > 0) mbar_wait(bar_raw_empty(r), (uint32_t)((uses - 1) & 1));
-            }
-            mbar_wait(bar_p_full, 0);
-            int it = 0;
-            for (int kc = 0; kc < n_kc; ++kc)
-                for (int rc = 0; rc < n_rc; ++rc, ++it) {
-                    const int t = it % NQ;
-                    const uint32_t ph = (uint32_t)((it / NQ) & 1);
-                    mbar_wait(bar_q_empty(t), ph ^ 1u);
+        }
+        // the Qt ring aliases the raw ring and the E ring: both must be drained (all phase A MMAs complete)
+        for (int r = 0; r < TC_NRAW; ++r) {
+            const int uses = (n_chunks - r + TC_NRAW - 1) / TC_NRAW;      // completed phases of raw_empty[r]
+            if (uses > 0) mbar_wait(bar_raw_empty(r), (uint32_t)((uses - 1) & 1));
+        }
+        mbar_wait(bar_p_full, 0);
+        int it = 0;
+        for (int kc = 0; kc < n_kc; ++kc)
+            for (int rc = 0; rc < n_rc; ++rc, ++it) {
+                const int t = it % NQ;
+                const uint32_t ph = (uint32_t)((it / NQ) & 1);
+                mbar_wait(bar_q_empty(t), ph ^ 1u);
+                __syncwarp();
+                if (elect_one()) {
                     mbar_arrive_expect_tx(bar_q_full(t), 32768u);
                     tma_load_2d(qt_hi_st(t), &maps.qt_hi, bar_q_full(t), rc * 32, kc * 128);
                     tma_load_2d(qt_lo_st(t), &maps.qt_lo, bar_q_full(t), rc * 32, kc * 128);
                 }
-        }
+            }
     } else {
         // =============================== MMA issuer ===============================
-        if (lane == 0) {
-            const uint32_t idesc_a = umma_idesc_tf32(128, 2 * R), idesc_a2 = umma_idesc_tf32(128, R);
-            for (int c = 0; c < n_chunks; ++c) {
-                const int s = c % TC_SA, se = c % NE;
-                mbar_wait(bar_full_w(s), (uint32_t)((c / TC_SA) & 1));
-                tr(3, c, 0);
-                mbar_wait(bar_full_e(se), (uint32_t)((c / NE) & 1));
+        // the whole warp runs the loops and the barrier waits (converged); ONE elected lane issues the MMAs and commits
+        const uint32_t idesc_a = umma_idesc_tf32(128, 2 * R), idesc_a2 = umma_idesc_tf32(128, R);
+        for (int c = 0; c < n_chunks; ++c) {
+            const int s = c % TC_SA, se = c % NE;
+            mbar_wait(bar_full_w(s), (uint32_t)((c / TC_SA) & 1));
+            mbar_wait(bar_full_e(se), (uint32_t)((c / NE) & 1));
+            tc_fence_after();
+            __syncwarp();
+            if (elect_one()) {
                 tr(3, c, 1);
-                tc_fence_after();
                 const uint32_t a_hi = tmem_base + TC_A_COL0 + (uint32_t)(64 * s), a_lo = a_hi + 32u;
                 const uint64_t b_hi = umma_desc_sw128(stage_e_hi(se));     // E_hi rows followed by E_lo rows: one 2R-row tile
 #pragma unroll
@@ -458,25 +470,28 @@ apply_tc_kernel(const LayerRef* __restrict__ layers, int n_layers, int K, int R,
                 }
                 umma_commit(bar_empty(s));
                 umma_commit(bar_empty_e(se));
+                if (c == n_chunks - 1) umma_commit(bar_p_full);
                 tr(3, c, 2);
             }
-            umma_commit(bar_p_full);
-            // ---- phase B ----
-            mbar_wait(bar_p_smem, 0);
+        }
+        // ---- phase B ----
+        mbar_wait(bar_p_smem, 0);
+        tc_fence_after();
+        const uint32_t idesc_b = umma_idesc_tf32(128, 256), idesc_b2 = umma_idesc_tf32(128, 128);
+        int it = 0;
+        for (int kc = 0; kc < n_kc; ++kc) {
+            const int b = kc & 1;
+            mbar_wait(bar_acc_empty(b), (uint32_t)(((kc >> 1) & 1) ^ 1));
             tc_fence_after();
-            const uint32_t idesc_b = umma_idesc_tf32(128, 256), idesc_b2 = umma_idesc_tf32(128, 128);
-            int it = 0;
-            for (int kc = 0; kc < n_kc; ++kc) {
-                const int b = kc & 1;
-                mbar_wait(bar_acc_empty(b), (uint32_t)(((kc >> 1) & 1) ^ 1));
-                tr(4, kc, 0);
+            const uint32_t d_tmem = tmem_base + 256u * (uint32_t)b;
+            for (int rc = 0; rc < n_rc; ++rc, ++it) {
+                const int t = it % NQ;
+                const uint32_t ph = (uint32_t)((it / NQ) & 1);
+                mbar_wait(bar_q_full(t), ph);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + 256u * (uint32_t)b;
-                for (int rc = 0; rc < n_rc; ++rc, ++it) {
-                    const int t = it % NQ;
-                    const uint32_t ph = (uint32_t)((it / NQ) & 1);
-                    mbar_wait(bar_q_full(t), ph);
-                    tc_fence_after();
+                __syncwarp();
+                if (elect_one()) {
+                    if (rc == 0) tr(4, kc, 0);
                     const uint64_t a_hi = umma_desc_sw128(qt_hi_st(t)), a_lo = umma_desc_sw128(qt_lo_st(t));
                     const uint64_t b_hi = umma_desc_sw128(p_hi_atom(rc));      // P_hi rows followed by P_lo rows: 256-row tile
 #pragma unroll
@@ -486,9 +501,8 @@ apply_tc_kernel(const LayerRef* __restrict__ layers, int n_layers, int K, int R,
                         umma_tf32(d_tmem, a_lo + adv, b_hi + adv, idesc_b2, 1);                // N = 128: += lo.hi
                     }
                     umma_commit(bar_q_empty(t));
+                    if (rc == n_rc - 1) { umma_commit(bar_acc_full(b)); tr(4, kc, 1); }
                 }
-                umma_commit(bar_acc_full(b));
-                tr(4, kc, 1);
             }
         }
     }

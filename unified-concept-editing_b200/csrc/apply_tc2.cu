@@ -63,6 +63,15 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32
           "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]),
           "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31]) : "memory");
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
 __device__ __forceinline__ float tf32_hi(float x) {
     uint32_t u;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
@@ -253,7 +262,7 @@ apply_tc2_kernel(const LayerRef* __restrict__ layers, int n_layers, int K, int R
         // groups of 32 tile rows; the addend of group t+1 is requested before group t is combined and stored
         const uint64_t pol_stream = l2_evict_first();
         const int n_groups = n_kc * 4;
-        float wa[32], wb[32];
+        float w0[32], w1[32], w2[32];
         auto load_addend = [&](float (&w)[32], int t) {
             const int kc = t >> 2, g = t & 3;
             const float* wp = w_old + (size_t)(32 * g) * K + (kc * 128 + 32 * warp + lane);
@@ -268,13 +277,16 @@ apply_tc2_kernel(const LayerRef* __restrict__ layers, int n_layers, int K, int R
                 if (threadIdx.x == 0) tr(5, kc, 1);
                 fence_after();
             }
-            uint32_t v[32];
-            tmem_ld32(lane_base + (uint32_t)(128 * b + 32 * g), v);
             float* op = w_new + (size_t)(32 * g) * K + (kc * 128 + 32 * warp + lane);
             const int live = rows_valid - 32 * g;
 #pragma unroll
-            for (int i = 0; i < 32; ++i)
-                if (i < live) stg_f32_hint(op + (size_t)i * K, w[i] + __uint_as_float(v[i]), pol_stream);
+            for (int h = 0; h < 2; ++h) {
+                uint32_t v[16];
+                tmem_ld16(lane_base + (uint32_t)(128 * b + 32 * g + 16 * h), v);
+#pragma unroll
+                for (int i = 0; i < 16; ++i)
+                    if (16 * h + i < live) stg_f32_hint(op + (size_t)(16 * h + i) * K, w[16 * h + i] + __uint_as_float(v[i]), pol_stream);
+            }
             if (g == 3) {
                 fence_before();
                 __syncwarp();
@@ -282,23 +294,33 @@ apply_tc2_kernel(const LayerRef* __restrict__ layers, int n_layers, int K, int R
                 if (threadIdx.x == 0) tr(5, kc, 2);
             }
         };
-        load_addend(wa, 0);
+        // two groups (64 loads per thread, 32 KB per CTA) are always in flight ahead of the group being combined
+        load_addend(w0, 0);
+        load_addend(w1, 1);
         if (threadIdx.x == 0) tr(5, 0, 0);
-        for (int t = 0; t < n_groups; t += 2) {          // n_groups is a multiple of 4
-            load_addend(wb, t + 1);
-            finish_group(wa, t);
-            if (t + 2 < n_groups) load_addend(wa, t + 2);
-            finish_group(wb, t + 1);
+        for (int t = 0; t < n_groups; t += 3) {
+            if (t + 2 < n_groups) load_addend(w2, t + 2);
+            finish_group(w0, t);
+            if (t + 1 < n_groups) {
+                if (t + 3 < n_groups) load_addend(w0, t + 3);
+                finish_group(w1, t + 1);
+            }
+            if (t + 2 < n_groups) {
+                if (t + 4 < n_groups) load_addend(w1, t + 4);
+                finish_group(w2, t + 2);
+            }
         }
     } else if (warp == WARP_W_TMA) {
         // =============================== TMA warp 1: raw W chunks ===============================
-        if (lane == 0) {
-            const uint64_t pol_keep = l2_evict_last();     // the tile is read again by the epilogue: keep it in L2
-            const CUtensorMap* wm = &wmaps.w[layer];
-            const uint32_t bytes = (uint32_t)tile_rows * 128u;
-            for (int c = 0; c < n_chunks; ++c) {
-                const int r = c % NRAW;
-                mbar_wait(bar_raw_empty(r), (uint32_t)(((c / NRAW) & 1) ^ 1));
+        // (all lanes wait, one elected lane issues: see elect_one() in tc_common.cuh)
+        const uint64_t pol_keep = l2_evict_last();     // the tile is read again by the epilogue: keep it in L2
+        const CUtensorMap* wm = &wmaps.w[layer];
+        const uint32_t bytes = (uint32_t)tile_rows * 128u;
+        for (int c = 0; c < n_chunks; ++c) {
+            const int r = c % NRAW;
+            mbar_wait(bar_raw_empty(r), (uint32_t)(((c / NRAW) & 1) ^ 1));
+            __syncwarp();
+            if (elect_one()) {
                 tr(0, c, 0);
                 mbar_arrive_expect_tx(bar_raw_full(r), bytes);
                 tma_load_2d_hint(raw_st(r), wm, bar_raw_full(r), c * 32, row0, pol_keep);
@@ -306,40 +328,45 @@ apply_tc2_kernel(const LayerRef* __restrict__ layers, int n_layers, int K, int R
         }
     } else if (warp == WARP_E_TMA) {
         // =============================== TMA warp 2: E tiles (phase A), Qt tiles (phase B) ===============================
-        if (lane == 0) {
-            const uint32_t e_bytes = 2u * (uint32_t)R * 128u;
-            for (int c = 0; c < n_chunks; ++c) {
-                const int s = c % NE;
-                mbar_wait(bar_e_empty(s), (uint32_t)(((c / NE) & 1) ^ 1));
+        const uint32_t e_bytes = 2u * (uint32_t)R * 128u;
+        for (int c = 0; c < n_chunks; ++c) {
+            const int s = c % NE;
+            mbar_wait(bar_e_empty(s), (uint32_t)(((c / NE) & 1) ^ 1));
+            __syncwarp();
+            if (elect_one()) {
                 tr(2, c, 0);
                 mbar_arrive_expect_tx(bar_e_full(s), e_bytes);
                 tma_load_2d(stage_e_hi(s), &maps.e_hi, bar_e_full(s), c * 32, 0);
                 tma_load_2d(stage_e_lo(s), &maps.e_lo, bar_e_full(s), c * 32, 0);
             }
-            // the Qt ring aliases the raw ring: every phase-A MMA has completed once P is final, and an MMA on an A stage
-            // completes only after all four transform warps have read that raw chunk
-            mbar_wait(bar_p_full, 0);
-            int it = 0;
-            for (int kc = 0; kc < n_kc; ++kc)
-                for (int rc = 0; rc < n_rc; ++rc)
-                    for (int hl = 0; hl < 2; ++hl, ++it) {
-                        const int t = it % NQ;
-                        mbar_wait(bar_q_empty(t), (uint32_t)(((it / NQ) & 1) ^ 1));
+        }
+        // the Qt ring aliases the raw ring: every phase-A MMA has completed once P is final, and an MMA on an A stage
+        // completes only after all four transform warps have read that raw chunk
+        mbar_wait(bar_p_full, 0);
+        int it = 0;
+        for (int kc = 0; kc < n_kc; ++kc)
+            for (int rc = 0; rc < n_rc; ++rc)
+                for (int hl = 0; hl < 2; ++hl, ++it) {
+                    const int t = it % NQ;
+                    mbar_wait(bar_q_empty(t), (uint32_t)(((it / NQ) & 1) ^ 1));
+                    __syncwarp();
+                    if (elect_one()) {
                         mbar_arrive_expect_tx(bar_q_full(t), 16384u);
                         tma_load_2d(qt_slot(t), hl ? &maps.qt_lo : &maps.qt_hi, bar_q_full(t), rc * 32, kc * 128);
                     }
-        }
+                }
     } else {
         // =============================== MMA issuer ===============================
-        if (lane == 0) {
-            const uint32_t idesc_a = idesc_tf32(128, R);
-            for (int c = 0; c < n_chunks; ++c) {
-                const int s = c % NSA, se = c % NE;
-                mbar_wait(bar_e_full(se), (uint32_t)((c / NE) & 1));
-                tr(3, c, 0);
-                mbar_wait(bar_a_full(s), (uint32_t)((c / NSA) & 1));
+        // the whole warp runs the loops and the barrier waits (converged); ONE elected lane issues the MMAs and commits
+        const uint32_t idesc_a = idesc_tf32(128, R);
+        for (int c = 0; c < n_chunks; ++c) {
+            const int s = c % NSA, se = c % NE;
+            mbar_wait(bar_e_full(se), (uint32_t)((c / NE) & 1));
+            mbar_wait(bar_a_full(s), (uint32_t)((c / NSA) & 1));
+            fence_after();
+            __syncwarp();
+            if (elect_one()) {
                 tr(3, c, 1);
-                fence_after();
                 const uint32_t a_hi = tmem_base + A_COL0 + (uint32_t)(64 * s), a_lo = a_hi + 32u;
                 const uint64_t b_hi = umma_desc_sw128(stage_e_hi(se)), b_lo = umma_desc_sw128(stage_e_lo(se));
 #pragma unroll
@@ -351,26 +378,29 @@ apply_tc2_kernel(const LayerRef* __restrict__ layers, int n_layers, int K, int R
                 }
                 umma_commit(bar_a_empty(s));
                 umma_commit(bar_e_empty(se));
+                if (c == n_chunks - 1) umma_commit(bar_p_full);
                 tr(3, c, 2);
             }
-            umma_commit(bar_p_full);
-            // ---- phase B ----
-            mbar_wait(bar_p_smem, 0);
+        }
+        // ---- phase B ----
+        mbar_wait(bar_p_smem, 0);
+        fence_after();
+        const uint32_t idesc_b = idesc_tf32(128, 128);
+        int it = 0;
+        for (int kc = 0; kc < n_kc; ++kc) {
+            const int b = kc & 1;
+            mbar_wait(bar_acc_empty(b), (uint32_t)(((kc >> 1) & 1) ^ 1));
             fence_after();
-            const uint32_t idesc_b = idesc_tf32(128, 128);
-            int it = 0;
-            for (int kc = 0; kc < n_kc; ++kc) {
-                const int b = kc & 1;
-                mbar_wait(bar_acc_empty(b), (uint32_t)(((kc >> 1) & 1) ^ 1));
-                tr(4, kc, 0);
+            const uint32_t d_tmem = tmem_base + 128u * (uint32_t)b;
+            for (int rc = 0; rc < n_rc; ++rc) {
+                const uint64_t b_hi = umma_desc_sw128(p_hi_atom(rc)), b_lo = umma_desc_sw128(p_lo_atom(rc));
+                int t = it % NQ;
+                mbar_wait(bar_q_full(t), (uint32_t)((it / NQ) & 1));
                 fence_after();
-                const uint32_t d_tmem = tmem_base + 128u * (uint32_t)b;
-                for (int rc = 0; rc < n_rc; ++rc) {
-                    const uint64_t b_hi = umma_desc_sw128(p_hi_atom(rc)), b_lo = umma_desc_sw128(p_lo_atom(rc));
-                    int t = it % NQ;
-                    mbar_wait(bar_q_full(t), (uint32_t)((it / NQ) & 1));
-                    fence_after();
-                    uint64_t a = umma_desc_sw128(qt_slot(t));                 // Qt_hi tile: hi.hi + hi.lo
+                __syncwarp();
+                if (elect_one()) {
+                    if (rc == 0) tr(4, kc, 0);
+                    const uint64_t a = umma_desc_sw128(qt_slot(t));                 // Qt_hi tile: hi.hi + hi.lo
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         const uint64_t adv = (uint64_t)(k * 2);
@@ -378,21 +408,23 @@ apply_tc2_kernel(const LayerRef* __restrict__ layers, int n_layers, int K, int R
                         umma_tf32(d_tmem, a + adv, b_lo + adv, idesc_b, 1);
                     }
                     umma_commit(bar_q_empty(t));
-                    ++it;
-                    t = it % NQ;
-                    mbar_wait(bar_q_full(t), (uint32_t)((it / NQ) & 1));
-                    fence_after();
-                    a = umma_desc_sw128(qt_slot(t));                          // Qt_lo tile: lo.hi
+                }
+                ++it;
+                t = it % NQ;
+                mbar_wait(bar_q_full(t), (uint32_t)((it / NQ) & 1));
+                fence_after();
+                __syncwarp();
+                if (elect_one()) {
+                    const uint64_t a = umma_desc_sw128(qt_slot(t));                 // Qt_lo tile: lo.hi
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         const uint64_t adv = (uint64_t)(k * 2);
                         umma_tf32(d_tmem, a + adv, b_hi + adv, idesc_b, 1);
                     }
                     umma_commit(bar_q_empty(t));
-                    ++it;
+                    if (rc == n_rc - 1) { umma_commit(bar_acc_full(b)); tr(4, kc, 1); }
                 }
-                umma_commit(bar_acc_full(b));
-                tr(4, kc, 1);
+                ++it;
             }
         }
     }

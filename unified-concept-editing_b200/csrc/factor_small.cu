@@ -84,33 +84,32 @@ __device__ __forceinline__ double fs_rsqrt(double d) {
     return fma(0.5 * y, e, y);
 }
 
-// Cholesky of one 32 x 32 diagonal block (pitch 33, lower triangle) by ONE warp, register resident: lane = row,
-// a[c] = column c of that row; right-looking, pivot and column broadcasts by shuffles.  Kept out of line so that its
-// 64 registers of matrix state do not compete with the rest of chol_small_kernel.
+// Cholesky of one 32 x 32 diagonal block (pitch 33, lower triangle) by ONE warp, register resident and ROLLED:
+// lane = row, and at the top of step j register a[k] holds column j + k of that row — the trailing update writes column
+// j + k into a[k - 1], so the register file shifts left by one column per step and every index stays static.  The body is
+// ~110 instructions executed 32 times: a fully unrolled factorisation (1 600 straight-line instructions) was measured at
+// 61 k cycles on its first call of a launch — this kernel is one CTA that runs once, its code arrives through a cold
+// instruction cache — and 12.6 k afterwards; the left-looking shared-memory version before it took 26 k per block.
+// Columns j + k >= 32 do not exist: those lanes / registers hold finite garbage that never reaches a stored value.
 __device__ __noinline__ void fs_potrf_warp(double* __restrict__ D, double* __restrict__ invd_blk, int lane, int* flag, int kb) {
     double a[FS_NB];
 #pragma unroll
     for (int c = 0; c < FS_NB; ++c) a[c] = D[lane * (FS_NB + 1) + c];
     bool bad = false;
-    double yinv = 1.0;
-#pragma unroll
+#pragma unroll 1
     for (int j = 0; j < FS_NB; ++j) {
-        double d = __shfl_sync(0xffffffffu, a[j], j);
+        double d = __shfl_sync(0xffffffffu, a[0], j);
         if (!(d > 0.0)) { bad = true; d = 1.0; }
         const double y = fs_rsqrt(d);
-        const double l = (lane == j) ? d * y : a[j] * y;      // L[lane][j] for lanes >= j (unused garbage above the diagonal)
-        a[j] = l;
-        if (lane == j) yinv = y;
+        const double l = (lane == j) ? d * y : a[0] * y;      // L[lane][j] for lanes >= j
+        if (lane >= j) D[lane * (FS_NB + 1) + j] = l;
+        if (lane == j) invd_blk[j] = y;
 #pragma unroll
-        for (int k = j + 1; k < FS_NB; ++k) {                 // a[lane][k] -= L[lane][j] L[k][j]   (k = j + 1 first: the next pivot)
-            const double lk = __shfl_sync(0xffffffffu, l, k);
-            a[k] = fma(-l, lk, a[k]);
+        for (int k = 1; k < FS_NB; ++k) {                     // A[lane][j + k] -= L[lane][j] L[j + k][j]   (k = 1 first: the next pivot)
+            const double lk = __shfl_sync(0xffffffffu, l, (j + k) & 31);
+            a[k - 1] = fma(-l, lk, a[k]);
         }
     }
-#pragma unroll
-    for (int c = 0; c < FS_NB; ++c)
-        if (c <= lane) D[lane * (FS_NB + 1) + c] = a[c];
-    invd_blk[lane] = yinv;
     if (bad && lane == 0) atomicCAS(flag, 0, 1 + kb);
 }
 
@@ -128,73 +127,106 @@ chol_small_kernel(double* __restrict__ Hg, int n, int n_pad, const double* __res
     double* invd = XS + n_pad * xl;               // [n_pad]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int NW = FS_T / 32;
+    constexpr int P = FS_NB + 1;                  // block pitch
 
-    // ---- load the lower block triangle (+ diagonal term, identity padding) ----
-    for (int bi = 0, b = 0; bi < nblk; ++bi)
-        for (int bj = 0; bj <= bi; ++bj, ++b)
-            for (int idx = tid; idx < FS_NB * FS_NB; idx += FS_T) {
-                const int rr = idx >> 5, cc = idx & 31, r = bi * FS_NB + rr, c = bj * FS_NB + cc;
-                double v = (r < n && c <= r) ? Hg[(long)r * n_pad + c] : 0.0;
-                if (r == c) v = (r < n) ? v + dadd[r] : 1.0;
-                SB[b * FS_BLK + rr * (FS_NB + 1) + cc] = v;
+    // ---- load the lower block triangle (+ diagonal term, identity padding): warp = block row, lane = column; the global
+    //      loads of eight rows are requested before the first one is used (the old one-element-per-iteration loop spent
+    //      23 k cycles here, one exposed HBM/L2 latency per iteration) ----
+    {
+        const int nb = nblk * (nblk + 1) / 2;
+        for (int b0 = 0; b0 < nb; b0 += 4) {
+            double v[4][2];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int b = b0 + u;
+                int bi = 0;
+                while ((bi + 1) * (bi + 2) / 2 <= b) ++bi;
+                const int bj = b - bi * (bi + 1) / 2, c = bj * FS_NB + lane;
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    const int r = bi * FS_NB + warp * 2 + half;
+                    double x = (b < nb && r < n && c <= r) ? Hg[(long)r * n_pad + c] : 0.0;
+                    if (r == c) x = (r < n) ? x + dadd[r] : 1.0;
+                    v[u][half] = x;
+                }
             }
-    for (int idx = tid; idx < n_pad * n_edit; idx += FS_T) {
-        const int r = idx / n_edit, j = idx % n_edit;
-        XS[r * xl + j] = (r == n_pres + j) ? 1.0 : 0.0;
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (b0 + u < nb) {
+#pragma unroll
+                    for (int half = 0; half < 2; ++half) SB[(b0 + u) * FS_BLK + (warp * 2 + half) * P + lane] = v[u][half];
+                }
+        }
     }
+    for (int r = warp; r < n_pad; r += NW)
+        for (int j = lane; j < n_edit; j += 32) XS[r * xl + j] = (r == n_pres + j) ? 1.0 : 0.0;
     __syncthreads();
     tr();   // 1: loaded
 
     for (int kb = 0; kb < nblk; ++kb) {
         double* D = SB + fs_blk(kb, kb);
         const int o = kb * FS_NB;
-        // (a) Cholesky of the diagonal block by one warp, REGISTER resident (lane = row, a[c] = column c of that row):
-        //     right-looking, pivot and column broadcasts by shuffles.  The chain between two pivots is one shuffle, the
-        //     reciprocal square root, one multiply, one shuffle and one FMA (~200 cycles); the shared-memory left-looking
-        //     version it replaces needed ~830 (dependent LDS -> DFMA chains and a store/load round trip per column).
+        // (a) Cholesky of the diagonal block by one warp (see fs_potrf_warp)
         if (warp == 0) fs_potrf_warp(D, invd + o, lane, flag, kb);
         __syncthreads();
         tr();   // diag block factored
-        // (b) inverse of L_kk by column sweeps (warp = column c, lane = row): x_j = (delta_jc - acc_j) / L_jj
-        for (int c = warp; c < FS_NB; c += NW) {
-            double acc = 0.0, mine = 0.0;
-            for (int j = c; j < FS_NB; ++j) {
-                const double cand = ((lane == c) ? 1.0 : 0.0) - acc;
-                const double xj = __shfl_sync(0xffffffffu, cand, j) * invd[o + j];
-                if (lane == j) mine = xj;
-                if (lane > j) acc = fma(D[lane * (FS_NB + 1) + j], xj, acc);
+        // (b) inverse of L_kk by column sweeps (lane = row): x_j = (delta_jc - acc_j) / L_jj.  A warp carries its two
+        //     columns (c, c + 16) through ONE sweep: the second chain is identically zero until j reaches c + 16.
+        {
+            const int c1 = warp, c2 = warp + NW;
+            double acc1 = 0.0, acc2 = 0.0, mine1 = 0.0, mine2 = 0.0;
+            for (int j = c1; j < FS_NB; ++j) {
+                const double cand1 = ((lane == c1) ? 1.0 : 0.0) - acc1, cand2 = ((lane == c2) ? 1.0 : 0.0) - acc2;
+                const double iv = invd[o + j];
+                const double x1 = __shfl_sync(0xffffffffu, cand1, j) * iv, x2 = __shfl_sync(0xffffffffu, cand2, j) * iv;
+                if (lane == j) { mine1 = x1; mine2 = x2; }
+                if (lane > j) {
+                    const double l = D[lane * P + j];
+                    acc1 = fma(l, x1, acc1); acc2 = fma(l, x2, acc2);
+                }
             }
-            if (lane > c) D[c * (FS_NB + 1) + lane] = mine;      // strict upper triangle <- transposed strict lower of L^-1
+            if (lane > c1) D[c1 * P + lane] = mine1;            // strict upper triangle <- transposed strict lower of L^-1
+            if (lane > c2) D[c2 * P + lane] = mine2;
         }
         __syncthreads();
         tr();   // inverse done
         const int mb = nblk - kb - 1;                            // block rows below
         if (mb > 0) {
-            // (c) panel  L_ik = H_ik L_kk^-T  for the mb blocks below (staged: updated in place)
-            double out[FS_MAX_N * FS_NB / FS_T];
+            // (c) panel  L_ik = H_ik L_kk^-T  for the mb blocks below, in place (staged through registers).
+            //     Task = 4 rows x 1 column, lanes = the 32 columns: the H rows are warp broadcasts, the L^-1 coefficients
+            //     consecutive doubles; fixed trip count with the triangle applied as a select, so the loads batch.
+            double out[2][4];
 #pragma unroll
-            for (int it = 0; it < FS_MAX_N * FS_NB / FS_T; ++it) {
+            for (int it = 0; it < 2; ++it) {
                 const int idx = tid + it * FS_T;
-                out[it] = 0.0;
-                if (idx < mb * FS_NB * FS_NB) {
-                    const int bi = kb + 1 + idx / (FS_NB * FS_NB), rr = (idx >> 5) & 31, c = idx & 31;
-                    const double* A = SB + fs_blk(bi, kb) + rr * (FS_NB + 1);
-                    double s2 = A[c] * invd[o + c];                                  // j == c term (diagonal of L^-1)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) out[it][i] = 0.0;
+                if (idx < mb * 256) {
+                    const int c = idx & 31, rq = idx >> 5;
+                    const double* A = SB + fs_blk(kb + 1 + (rq >> 3), kb) + (rq & 7) * 4 * P;
+                    const double dcc = invd[o + c];
 #pragma unroll 8
-                    for (int j = 0; j < c; ++j) s2 = fma(A[j], D[j * (FS_NB + 1) + c], s2);   // Linv[c][j] stored at D[j][c]
-                    out[it] = s2;
+                    for (int j = 0; j < FS_NB; ++j) {
+                        const double raw = D[j * P + c];                                   // Linv[c][j] for j < c
+                        const double coef = (j < c) ? raw : ((j == c) ? dcc : 0.0);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) out[it][i] = fma(A[i * P + j], coef, out[it][i]);
+                    }
                 }
             }
             __syncthreads();
 #pragma unroll
-            for (int it = 0; it < FS_MAX_N * FS_NB / FS_T; ++it) {
+            for (int it = 0; it < 2; ++it) {
                 const int idx = tid + it * FS_T;
-                if (idx < mb * FS_NB * FS_NB) {
-                    const int bi = kb + 1 + idx / (FS_NB * FS_NB), rr = (idx >> 5) & 31, c = idx & 31;
-                    SB[fs_blk(bi, kb) + rr * (FS_NB + 1) + c] = out[it];
+                if (idx < mb * 256) {
+                    const int c = idx & 31, rq = idx >> 5;
+                    double* A = SB + fs_blk(kb + 1 + (rq >> 3), kb) + (rq & 7) * 4 * P;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) A[i * P + c] = out[it][i];
                 }
             }
             __syncthreads();
+            tr();   // panel done
             // (d) trailing update of the lower block triangle:  H_ij -= L_ik L_jk^T
             //     (a lookahead variant — warp 0 factoring the next diagonal block meanwhile — was measured and was slower:
             //      a single warp of fp64 work is latency-bound either way)
@@ -206,8 +238,8 @@ chol_small_kernel(double* __restrict__ Hg, int n, int n_pad, const double* __res
                 const int tj = pr - ti * (ti + 1) / 2;
                 const int r0 = ((idx >> 3) & 7) * 4, c0 = (idx & 7) * 4;
                 if (ti == tj && c0 > r0 + 3) continue;
-                const double* A = SB + fs_blk(kb + 1 + ti, kb) + r0 * (FS_NB + 1);
-                const double* B = SB + fs_blk(kb + 1 + tj, kb) + c0 * (FS_NB + 1);
+                const double* A = SB + fs_blk(kb + 1 + ti, kb) + r0 * P;
+                const double* B = SB + fs_blk(kb + 1 + tj, kb) + c0 * P;
                 double acc[4][4];
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
@@ -217,7 +249,7 @@ chol_small_kernel(double* __restrict__ Hg, int n, int n_pad, const double* __res
                 for (int j = 0; j < FS_NB; ++j) {
                     double a[4], b[4];
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) { a[i] = A[i * (FS_NB + 1) + j]; b[i] = B[i * (FS_NB + 1) + j]; }
+                    for (int i = 0; i < 4; ++i) { a[i] = A[i * P + j]; b[i] = B[i * P + j]; }
 #pragma unroll
                     for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -228,100 +260,110 @@ chol_small_kernel(double* __restrict__ Hg, int n, int n_pad, const double* __res
                 for (int i = 0; i < 4; ++i)
 #pragma unroll
                     for (int j2 = 0; j2 < 4; ++j2)
-                        if (ti != tj || c0 + j2 <= r0 + i) Cb[(r0 + i) * (FS_NB + 1) + c0 + j2] -= acc[i][j2];
+                        if (ti != tj || c0 + j2 <= r0 + i) Cb[(r0 + i) * P + c0 + j2] -= acc[i][j2];
             }
             __syncthreads();
         }
-        tr();   // panel + trailing done
+        tr();   // trailing done
     }
     if (write_back) {   // debug: L back to global (row-major [n_pad][n_pad], zeros above the diagonal)
         for (int idx = tid; idx < n_pad * n_pad; idx += FS_T) {
             const int r = idx / n_pad, c = idx % n_pad;
-            Hg[idx] = (c <= r) ? SB[fs_blk(r >> 5, c >> 5) + (r & 31) * (FS_NB + 1) + (c & 31)] : 0.0;
+            Hg[idx] = (c <= r) ? SB[fs_blk(r >> 5, c >> 5) + (r & 31) * P + (c & 31)] : 0.0;
         }
     }
 
-    // ---- forward substitution  L Y = rhs  (block rows above the first edit row stay zero) ----
-    constexpr int XR = FS_NB * FS_MAX_RHS / FS_T;      // staged outputs per thread for one 32 x n_edit block
+    // ---- substitutions.  Thread = (row quad rq, right-hand side j): tid = rq * 64 + j, so no division by n_edit, the
+    //      right-hand-side reads are consecutive across lanes and the matrix coefficients are warp broadcasts. ----
+    const int sj = tid & 63, rq = tid >> 6;           // 8 row quads x 64 rhs slots
+    const bool s_on = sj < n_edit;
+    // forward  L Y = rhs  (block rows above the first edit row stay zero)
     for (int kb = n_pres / FS_NB; kb < nblk; ++kb) {
         const double* D = SB + fs_blk(kb, kb);
         const int o = kb * FS_NB;
-        double out[XR];
+        double out[4] = {0.0, 0.0, 0.0, 0.0};
+        if (s_on) {                                   // Y_k = L_kk^-1 X_k : Linv[rr][c] (c < rr) is stored at D[c][rr]
+            double iv[4];
 #pragma unroll
-        for (int it = 0; it < XR; ++it) {
-            const int idx = tid + it * FS_T;
-            out[it] = 0.0;
-            if (idx < FS_NB * n_edit) {
-                const int rr = idx / n_edit, j = idx % n_edit;
-                double s2 = invd[o + rr] * XS[(o + rr) * xl + j];
-                for (int c = 0; c < rr; ++c) s2 = fma(D[c * (FS_NB + 1) + rr], XS[(o + c) * xl + j], s2);   // Linv[rr][c]
-                out[it] = s2;
-            }
-        }
-        __syncthreads();
-#pragma unroll
-        for (int it = 0; it < XR; ++it) {
-            const int idx = tid + it * FS_T;
-            if (idx < FS_NB * n_edit) XS[(o + idx / n_edit) * xl + idx % n_edit] = out[it];
-        }
-        __syncthreads();
-        const int rest = n_pad - (o + FS_NB);
-        for (int idx = tid; idx < (rest / 4) * n_edit; idx += FS_T) {     // 4 rows x 1 rhs column per thread
-            const int r = o + FS_NB + 4 * (idx / n_edit), j = idx % n_edit;
-            const double* A = SB + fs_blk(r >> 5, kb) + (r & 31) * (FS_NB + 1);
-            double s4[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll 4
+            for (int i = 0; i < 4; ++i) iv[i] = invd[o + 4 * rq + i];
+#pragma unroll 8
             for (int c = 0; c < FS_NB; ++c) {
-                const double x = XS[(o + c) * xl + j];
+                const double x = XS[(o + c) * xl + sj];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) s4[i] = fma(A[i * (FS_NB + 1) + c], x, s4[i]);
+                for (int i = 0; i < 4; ++i) {
+                    const int rr = 4 * rq + i;
+                    const double raw = D[c * P + rr];
+                    out[i] = fma((c < rr) ? raw : ((c == rr) ? iv[i] : 0.0), x, out[i]);
+                }
+            }
+        }
+        __syncthreads();
+        if (s_on) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) XS[(o + 4 * rq + i) * xl + sj] = out[i];
+        }
+        __syncthreads();
+        const int rest = n_pad - (o + FS_NB);         // X_i -= L_ik Y_k for the block rows below
+        for (int r = o + FS_NB + 4 * rq; r < o + FS_NB + rest; r += 32) {
+            if (!s_on) break;
+            const double* A = SB + fs_blk(r >> 5, kb) + (r & 31) * P;
+            double s4[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll 8
+            for (int c = 0; c < FS_NB; ++c) {
+                const double x = XS[(o + c) * xl + sj];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) s4[i] = fma(A[i * P + c], x, s4[i]);
             }
 #pragma unroll
-            for (int i = 0; i < 4; ++i) XS[(r + i) * xl + j] -= s4[i];
+            for (int i = 0; i < 4; ++i) XS[(r + i) * xl + sj] -= s4[i];
         }
         __syncthreads();
     }
     tr();   // forward substitution done
-    // ---- backward substitution  L^T Z = Y ----
+    // backward  L^T Z = Y
     for (int kb = nblk - 1; kb >= 0; --kb) {
         const double* D = SB + fs_blk(kb, kb);
         const int o = kb * FS_NB;
-        double out[XR];
+        double out[4] = {0.0, 0.0, 0.0, 0.0};
+        if (s_on) {                                   // Z_k = L_kk^-T Y_k : Linv[c][rr] (c > rr) is stored at D[rr][c]
+            double iv[4];
 #pragma unroll
-        for (int it = 0; it < XR; ++it) {
-            const int idx = tid + it * FS_T;
-            out[it] = 0.0;
-            if (idx < FS_NB * n_edit) {
-                const int rr = idx / n_edit, j = idx % n_edit;
-                double s2 = invd[o + rr] * XS[(o + rr) * xl + j];
-                for (int c = rr + 1; c < FS_NB; ++c) s2 = fma(D[rr * (FS_NB + 1) + c], XS[(o + c) * xl + j], s2);   // Linv[c][rr]
-                out[it] = s2;
+            for (int i = 0; i < 4; ++i) iv[i] = invd[o + 4 * rq + i];
+#pragma unroll 8
+            for (int c = 0; c < FS_NB; ++c) {
+                const double x = XS[(o + c) * xl + sj];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int rr = 4 * rq + i;
+                    const double raw = D[rr * P + c];
+                    out[i] = fma((c > rr) ? raw : ((c == rr) ? iv[i] : 0.0), x, out[i]);
+                }
             }
         }
         __syncthreads();
+        if (s_on) {
 #pragma unroll
-        for (int it = 0; it < XR; ++it) {
-            const int idx = tid + it * FS_T;
-            if (idx < FS_NB * n_edit) XS[(o + idx / n_edit) * xl + idx % n_edit] = out[it];
+            for (int i = 0; i < 4; ++i) XS[(o + 4 * rq + i) * xl + sj] = out[i];
         }
         __syncthreads();
-        for (int idx = tid; idx < (o / 4) * n_edit; idx += FS_T) {        // 4 rows x 1 rhs column per thread
-            const int r = 4 * (idx / n_edit), j = idx % n_edit;
+        for (int r = 4 * rq; r < o; r += 32) {        // X_i -= L_ki^T Z_k for the block rows above
+            if (!s_on) break;
             const double* A = SB + fs_blk(kb, r >> 5) + (r & 31);          // L[o + c][r + i] = block(kb, r/32)[c][r%32 + i]
             double s4[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll 4
+#pragma unroll 8
             for (int c = 0; c < FS_NB; ++c) {
-                const double x = XS[(o + c) * xl + j];
+                const double x = XS[(o + c) * xl + sj];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) s4[i] = fma(A[c * (FS_NB + 1) + i], x, s4[i]);
+                for (int i = 0; i < 4; ++i) s4[i] = fma(A[c * P + i], x, s4[i]);
             }
 #pragma unroll
-            for (int i = 0; i < 4; ++i) XS[(r + i) * xl + j] -= s4[i];
+            for (int i = 0; i < 4; ++i) XS[(r + i) * xl + sj] -= s4[i];
         }
         __syncthreads();
     }
     tr();   // backward substitution done
-    for (int idx = tid; idx < n * n_edit; idx += FS_T) Z[(long)(idx / n_edit) * ldz + idx % n_edit] = XS[(idx / n_edit) * xl + idx % n_edit];
+    for (int r = warp; r < n; r += NW)
+        for (int j = lane; j < n_edit; j += 32) Z[(long)r * ldz + j] = XS[r * xl + j];
     __syncthreads();
     tr();
 }

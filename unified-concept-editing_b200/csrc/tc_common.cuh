@@ -44,6 +44,15 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         }
     }
 }
+// One lane of a CONVERGED warp.  Issue tcgen05.mma / commit / TMA under `if (elect_one())`, never under `if (lane == 0)`:
+// behind a per-thread predicate ptxas wraps every uniform-datapath instruction (UTCHMMA, UTMALDG, UTCBAR) in an
+// ELECT / BRA.U.ANY loop over the active lanes — measured at ~57 cycles per tcgen05.mma, more than a 32-cycle N = 64 MMA takes
+// to execute — while behind elect.sync they are emitted back to back.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }

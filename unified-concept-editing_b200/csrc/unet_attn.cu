@@ -112,28 +112,38 @@ __global__ void __launch_bounds__(FA_THREADS, 2) unet_attn_kernel(const __grid_c
     auto v_st = [&](int s) { return base + (uint32_t)(L.v_off + s * L.kv_bytes); };
 
     if (warp == 0) {
-        if (lane == 0) {
+        // all lanes run the loop and the barrier waits; one elected lane issues (see elect_one() in tc_common.cuh)
+        if (elect_one()) {
             mbar_arrive_expect_tx(bar_q, (uint32_t)L.q_bytes);
             for (int a = 0; a < n_at; ++a) tma_load_4d(base + a * 16384, &g.tmQ, bar_q, a * 64, q_tile * FA_BM, head, img);
-            for (int j = 0; j < n_kt; ++j) {
-                const int s = j % NS;
-                const uint32_t ph = (uint32_t)(((j / NS) & 1) ^ 1);
-                mbar_wait(bar_k_empty(s), ph);
+        }
+        __syncwarp();
+        for (int j = 0; j < n_kt; ++j) {
+            const int s = j % NS;
+            const uint32_t ph = (uint32_t)(((j / NS) & 1) ^ 1);
+            mbar_wait(bar_k_empty(s), ph);
+            __syncwarp();
+            if (elect_one()) {
                 mbar_arrive_expect_tx(bar_k_full(s), (uint32_t)L.kv_bytes);
                 for (int a = 0; a < n_at; ++a) tma_load_4d(k_st(s) + a * 16384, &g.tmK, bar_k_full(s), a * 64, j * FA_BN, head, img);
-                mbar_wait(bar_v_empty(s), ph);
+            }
+            mbar_wait(bar_v_empty(s), ph);
+            __syncwarp();
+            if (elect_one()) {
                 mbar_arrive_expect_tx(bar_v_full(s), (uint32_t)L.kv_bytes);
                 for (int a = 0; a < 2; ++a) tma_load_4d(v_st(s) + a * (dhp * 128), &g.tmV, bar_v_full(s), j * FA_BN + a * 64, 0, head, img);
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            const uint32_t idesc_s = idesc_bf16(FA_BM, FA_BN), idesc_o = idesc_bf16(FA_BM, dhp);
-            mbar_wait(bar_q, 0);
-            auto issue_qk = [&](int j) {
-                const int s = j % NS;
-                mbar_wait(bar_k_full(s), (uint32_t)((j / NS) & 1));
-                fence_after();
+        // the whole warp runs the loop and the barrier waits (converged); ONE elected lane issues the MMAs and commits
+        const uint32_t idesc_s = idesc_bf16(FA_BM, FA_BN), idesc_o = idesc_bf16(FA_BM, dhp);
+        mbar_wait(bar_q, 0);
+        auto issue_qk = [&](int j) {
+            const int s = j % NS;
+            mbar_wait(bar_k_full(s), (uint32_t)((j / NS) & 1));
+            fence_after();
+            __syncwarp();
+            if (elect_one()) {
                 for (int a = 0; a < n_at; ++a) {
                     const uint64_t qd = umma_desc_sw128(base + a * 16384), kd = umma_desc_sw128(k_st(s) + a * 16384);
 #pragma unroll
@@ -141,22 +151,25 @@ __global__ void __launch_bounds__(FA_THREADS, 2) unet_attn_kernel(const __grid_c
                 }
                 umma_commit(bar_k_empty(s));
                 umma_commit(bar_s_full);          // also: every earlier PV is complete (in-order pipe) -> O may be rescaled
-            };
-            issue_qk(0);
-            for (int j = 0; j < n_kt; ++j) {
-                const int s = j % NS;
-                mbar_wait(bar_v_full(s), (uint32_t)((j / NS) & 1));
-                mbar_wait(bar_p_full, (uint32_t)(j & 1));
-                fence_after();
+            }
+        };
+        issue_qk(0);
+        for (int j = 0; j < n_kt; ++j) {
+            const int s = j % NS;
+            mbar_wait(bar_v_full(s), (uint32_t)((j / NS) & 1));
+            mbar_wait(bar_p_full, (uint32_t)(j & 1));
+            fence_after();
+            __syncwarp();
+            if (elect_one()) {
 #pragma unroll
                 for (int ks = 0; ks < 8; ++ks) {          // 128 keys = 8 x 16; P: 8 TMEM columns per step; V^T: two 64-key atoms
                     const uint64_t vd = umma_desc_sw128(v_st(s) + (ks >> 2) * (dhp * 128)) + 2u * (ks & 3);
                     umma_bf16_ts(tmem_base + FA_O_COL, tmem_base + FA_P_COL + 8u * ks, vd, idesc_o, (j | ks) != 0);
                 }
                 umma_commit(bar_v_empty(s));
-                if (j + 1 < n_kt) issue_qk(j + 1);        // overwrites S (and the P alias) strictly after PV(j) in the pipe
-                else umma_commit(bar_o_done);
+                if (j + 1 >= n_kt) umma_commit(bar_o_done);
             }
+            if (j + 1 < n_kt) issue_qk(j + 1);            // overwrites S (and the P alias) strictly after PV(j) in the pipe
         }
     } else {
         // ---- softmax / correction / epilogue: thread = query row ----

@@ -195,51 +195,54 @@ __global__ void __launch_bounds__(UG_THREADS, 2) unet_gemm_kernel(const __grid_c
     if (threadIdx.x == 0) UG_STAMP(1);
 
     if (warp == 0) {
-        if (lane == 0) {
-            // which = 1: B (weights: not produced by an earlier kernel of the schedule unless batched), 2: A, 3: both
-            auto load_stage = [&](int it, int which) {
-                const int s = it % NS;
-                const int na = min(KA, n_atoms - it * KA);
-                if (which & 1) mbar_arrive_expect_tx(bar_full(s), (uint32_t)(na * (g.a_bytes + UG_BN * UG_BK * 2)));
-                for (int a = 0; a < na; ++a) {
-                    const uint32_t a_dst = base + s * stage_bytes + a * (UG_BM * UG_BK * 2);
-                    const uint32_t b_dst = base + s * stage_bytes + KA * (UG_BM * UG_BK * 2) + a * (UG_BN * UG_BK * 2);
-                    const int kit = k_begin + it * KA + a;
-                    const int tap = kit / kpt, c0 = (kit % kpt) * UG_BK;
-                    if (which & 2) {
-                        if (g.conv) {
-                            const int ky = tap / 3, kx = tap % 3;
-                            tma_load_4d(a_dst, &g.tmA, bar_full(s), c0, w0 * g.stride + kx - g.pad, h0 * g.stride + ky - g.pad, img0);
-                        } else {
-                            tma_load_4d(a_dst, &g.tmA, bar_full(s), c0, m_tile * UG_BM, g.a_batched ? b1 : 0, g.a_batched ? b2 : 0);
-                        }
+        // all lanes run the loop and the barrier waits; one elected lane issues (see elect_one() in tc_common.cuh)
+        // which = 1: B (weights: not produced by an earlier kernel of the schedule unless batched), 2: A, 3: both
+        auto load_stage = [&](int it, int which) {
+            const int s = it % NS;
+            const int na = min(KA, n_atoms - it * KA);
+            if (which & 1) mbar_arrive_expect_tx(bar_full(s), (uint32_t)(na * (g.a_bytes + UG_BN * UG_BK * 2)));
+            for (int a = 0; a < na; ++a) {
+                const uint32_t a_dst = base + s * stage_bytes + a * (UG_BM * UG_BK * 2);
+                const uint32_t b_dst = base + s * stage_bytes + KA * (UG_BM * UG_BK * 2) + a * (UG_BN * UG_BK * 2);
+                const int kit = k_begin + it * KA + a;
+                const int tap = kit / kpt, c0 = (kit % kpt) * UG_BK;
+                if (which & 2) {
+                    if (g.conv) {
+                        const int ky = tap / 3, kx = tap % 3;
+                        tma_load_4d(a_dst, &g.tmA, bar_full(s), c0, w0 * g.stride + kx - g.pad, h0 * g.stride + ky - g.pad, img0);
+                    } else {
+                        tma_load_4d(a_dst, &g.tmA, bar_full(s), c0, m_tile * UG_BM, g.a_batched ? b1 : 0, g.a_batched ? b2 : 0);
                     }
-                    if (which & 1) tma_load_4d(b_dst, &g.tmB, bar_full(s), tap * g.cin + c0, n_tile * UG_BN, g.b_batched ? b1 : 0, g.b_batched ? b2 : 0);
                 }
-            };
-            // weight tiles of the first stages are requested before the dependency wait: they overlap the previous kernel's tail
-            const int pre = min(NS, n_k);
-            const bool early_b = !g.b_batched;
-            if (early_b) for (int it = 0; it < pre; ++it) load_stage(it, 1);
-            pdl_wait();
-            for (int it = 0; it < pre; ++it) load_stage(it, early_b ? 2 : 3);
-            for (int it = pre; it < n_k; ++it) {
-                if (it == pre) UG_STAMP(2);
-                mbar_wait(bar_empty(it % NS), (uint32_t)(((it / NS) & 1) ^ 1));
-                load_stage(it, 3);
+                if (which & 1) tma_load_4d(b_dst, &g.tmB, bar_full(s), tap * g.cin + c0, n_tile * UG_BN, g.b_batched ? b1 : 0, g.b_batched ? b2 : 0);
             }
+        };
+        // weight tiles of the first stages are requested before the dependency wait: they overlap the previous kernel's tail
+        const int pre = min(NS, n_k);
+        const bool early_b = !g.b_batched;
+        if (early_b && elect_one()) for (int it = 0; it < pre; ++it) load_stage(it, 1);
+        __syncwarp();
+        pdl_wait();
+        if (elect_one()) for (int it = 0; it < pre; ++it) load_stage(it, early_b ? 2 : 3);
+        __syncwarp();
+        for (int it = pre; it < n_k; ++it) {
+            if (it == pre && lane == 0) UG_STAMP(2);
+            mbar_wait(bar_empty(it % NS), (uint32_t)(((it / NS) & 1) ^ 1));
+            __syncwarp();
+            if (elect_one()) load_stage(it, 3);
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            // N of this tile's MMAs = the valid columns rounded up to 16 (a 128 x 256 tile variant was measured and was not
-            // faster end to end: fewer CTAs on the many under-filled grids of the U-Net offset the cheaper issue)
-            int n_valid = g.N - n_tile * UG_BN;
-            n_valid = n_valid >= UG_BN ? UG_BN : ((n_valid + 15) & ~15);
-            const uint32_t idesc = idesc_bf16(UG_BM, n_valid);
-            for (int it = 0; it < n_k; ++it) {
-                const int s = it % NS;
-                mbar_wait(bar_full(s), (uint32_t)((it / NS) & 1));
-                fence_after();
+        // N of this tile's MMAs = the valid columns rounded up to 16 (a 128 x 256 tile variant was measured and was not
+        // faster end to end: fewer CTAs on the many under-filled grids of the U-Net offset the cheaper issue)
+        int n_valid = g.N - n_tile * UG_BN;
+        n_valid = n_valid >= UG_BN ? UG_BN : ((n_valid + 15) & ~15);
+        const uint32_t idesc = idesc_bf16(UG_BM, n_valid);
+        for (int it = 0; it < n_k; ++it) {
+            const int s = it % NS;
+            mbar_wait(bar_full(s), (uint32_t)((it / NS) & 1));
+            fence_after();
+            __syncwarp();
+            if (elect_one()) {
                 if (it == 0) UG_STAMP(3);
                 const int na = min(KA, n_atoms - it * KA);
                 for (int a = 0; a < na; ++a) {
@@ -250,9 +253,8 @@ __global__ void __launch_bounds__(UG_THREADS, 2) unet_gemm_kernel(const __grid_c
                         umma_bf16(tmem_base, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (it | a | k) != 0);
                 }
                 umma_commit(bar_empty(s));
+                if (it == n_k - 1) { umma_commit(bar_acc); UG_STAMP(4); }
             }
-            umma_commit(bar_acc);
-            UG_STAMP(4);
         }
     } else {
         // ---- epilogue: TMEM lane = tile row ----
@@ -480,60 +482,67 @@ __global__ void __launch_bounds__(UG_THREADS, 2) unet_gemm_pair_kernel(const __g
     const int b_bytes = (bn / 2) * UG_BK * 2;
     const int ec1 = g.conv ? w0 : m_tile * UG_BM, ec2 = g.conv ? h0 : 0, ec3 = g.conv ? img0 : 0;     // row coordinates of this tile
     if (warp == 0) {
-        if (lane == 0) {
-            // which = 1: this CTA's half of the B (weight) tile, 2: its A tile, 3: both
-            auto load_stage = [&](int it, int which) {
-                const int s = it % NS;
-                // the leader's barrier counts the bytes of both CTAs (a peer load may land before this expect_tx: the
-                // transaction count is signed, and the phase cannot complete before the leader's own arrival)
-                if ((which & 1) && rank == 0) mbar_arrive_expect_tx(bar_full(s), (uint32_t)(2 * (g.a_bytes + b_bytes)));
-                const uint32_t lead_bar = bar_full(s) & UG_PEER_MASK;
-                const uint32_t a_dst = base + s * UG2_STAGE_BYTES, b_dst = a_dst + UG_BM * UG_BK * 2;
-                const int kit = k_begin + it;
-                const int tap = kit / kpt, c0 = (kit % kpt) * UG_BK;
-                if (which & 2) {
-                    if (g.conv) {
-                        const int ky = tap / 3, kx = tap % 3;
-                        tma_load_4d_pair(a_dst, &g.tmA, lead_bar, c0, w0 * g.stride + kx - g.pad, h0 * g.stride + ky - g.pad, img0);
-                    } else {
-                        tma_load_4d_pair(a_dst, &g.tmA, lead_bar, c0, m_tile * UG_BM, 0, 0);
-                    }
+        // all lanes run the loop and the barrier waits; one elected lane issues (see elect_one() in tc_common.cuh)
+        // which = 1: this CTA's half of the B (weight) tile, 2: its A tile, 3: both
+        auto load_stage = [&](int it, int which) {
+            const int s = it % NS;
+            // the leader's barrier counts the bytes of both CTAs (a peer load may land before this expect_tx: the
+            // transaction count is signed, and the phase cannot complete before the leader's own arrival)
+            if ((which & 1) && rank == 0) mbar_arrive_expect_tx(bar_full(s), (uint32_t)(2 * (g.a_bytes + b_bytes)));
+            const uint32_t lead_bar = bar_full(s) & UG_PEER_MASK;
+            const uint32_t a_dst = base + s * UG2_STAGE_BYTES, b_dst = a_dst + UG_BM * UG_BK * 2;
+            const int kit = k_begin + it;
+            const int tap = kit / kpt, c0 = (kit % kpt) * UG_BK;
+            if (which & 2) {
+                if (g.conv) {
+                    const int ky = tap / 3, kx = tap % 3;
+                    tma_load_4d_pair(a_dst, &g.tmA, lead_bar, c0, w0 * g.stride + kx - g.pad, h0 * g.stride + ky - g.pad, img0);
+                } else {
+                    tma_load_4d_pair(a_dst, &g.tmA, lead_bar, c0, m_tile * UG_BM, 0, 0);
                 }
-                if (which & 1) tma_load_4d_pair(b_dst, &g.tmB, lead_bar, tap * g.cin + c0, n_base + (int)rank * n_half, 0, 0);
-            };
-            // weight tiles of the first stages are requested before the dependency wait: they overlap the previous kernel's tail
-            const int pre = min(NS, n_k);
-            for (int it = 0; it < pre; ++it) load_stage(it, 1);
-            pdl_wait();
+            }
+            if (which & 1) tma_load_4d_pair(b_dst, &g.tmB, lead_bar, tap * g.cin + c0, n_base + (int)rank * n_half, 0, 0);
+        };
+        // weight tiles of the first stages are requested before the dependency wait: they overlap the previous kernel's tail
+        const int pre = min(NS, n_k);
+        if (elect_one()) for (int it = 0; it < pre; ++it) load_stage(it, 1);
+        __syncwarp();
+        pdl_wait();
+        if (elect_one()) {
             if (g.tma_epi == 1 && g.residual) {               // residual tile -> its own shared-memory boxes, ahead of the activations
                 const int n_boxes = (min(bn, g.N - n_base) + 63) / 64;
                 mbar_arrive_expect_tx(bar_res, (uint32_t)(n_boxes * 16384));
                 for (int b = 0; b < n_boxes; ++b) tma_load_4d(res_base + (uint32_t)b * 16384u, &g.tmR, bar_res, n_base + b * 64, ec1, ec2, ec3);
             }
             for (int it = 0; it < pre; ++it) load_stage(it, 2);
-            for (int it = pre; it < n_k; ++it) {
-                if (it == pre) UG_STAMP(2);
-                mbar_wait(bar_empty(it % NS), (uint32_t)(((it / NS) & 1) ^ 1));
-                load_stage(it, 3);
-            }
+        }
+        __syncwarp();
+        for (int it = pre; it < n_k; ++it) {
+            if (it == pre && lane == 0) UG_STAMP(2);
+            mbar_wait(bar_empty(it % NS), (uint32_t)(((it / NS) & 1) ^ 1));
+            __syncwarp();
+            if (elect_one()) load_stage(it, 3);
         }
     } else if (warp == 1) {
-        if (lane == 0 && rank == 0) {
+        if (rank == 0) {
+            // the whole warp of the leader CTA runs the loop and the barrier waits; ONE elected lane issues the MMAs and commits
             const uint32_t idesc = idesc_bf16(2 * UG_BM, n_mma);
             for (int it = 0; it < n_k; ++it) {
                 const int s = it % NS;
                 mbar_wait(bar_full(s), (uint32_t)((it / NS) & 1));
                 fence_after();
-                if (it == 0) UG_STAMP(3);
-                const uint64_t a_desc = umma_desc_sw128(base + s * UG2_STAGE_BYTES);
-                const uint64_t b_desc = umma_desc_sw128(base + s * UG2_STAGE_BYTES + UG_BM * UG_BK * 2);
+                __syncwarp();
+                if (elect_one()) {
+                    if (it == 0) UG_STAMP(3);
+                    const uint64_t a_desc = umma_desc_sw128(base + s * UG2_STAGE_BYTES);
+                    const uint64_t b_desc = umma_desc_sw128(base + s * UG2_STAGE_BYTES + UG_BM * UG_BK * 2);
 #pragma unroll
-                for (int k = 0; k < UG_BK / 16; ++k)
-                    umma_bf16_pair(tmem_base, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (it | k) != 0);
-                umma_commit_pair(bar_empty(s));
+                    for (int k = 0; k < UG_BK / 16; ++k)
+                        umma_bf16_pair(tmem_base, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (it | k) != 0);
+                    umma_commit_pair(bar_empty(s));
+                    if (it == n_k - 1) { umma_commit_pair(bar_acc); UG_STAMP(4); }
+                }
             }
-            umma_commit_pair(bar_acc);
-            UG_STAMP(4);
         }
     } else {
         const int q = warp & 3;

@@ -120,7 +120,7 @@ int apply_dev(uce_ws* ws, const float* const* W_old, float* const* W_new, const 
     LayerRef* hl = ws->h_layers + slot_begin;
     // apply_impl: 0 auto, 1 SIMT, 2 tcgen05 with one CTA per SM (apply_tc.cu), 3 tcgen05 with two CTAs per SM (apply_tc2.cu, rank_pad <= 64)
     const bool lowrank = !ws->dense && ws->rank > 0;
-    const bool use_tc2 = lowrank && ((ws->apply_impl == 3) || (ws->apply_impl == 0 && apply_tc2_available(ws) && n_layers <= 160));
+    const bool use_tc2 = lowrank && ((ws->apply_impl == 3) || (ws->apply_impl == 0 && apply_tc2_available(ws) && n_layers <= 96));
     const bool use_tc = !use_tc2 && lowrank && ((ws->apply_impl == 2) || (ws->apply_impl == 0 && apply_tc_available(ws) && n_layers <= 160));
     const int tile_rows = use_tc2 ? apply_tc2_tile_rows() : (use_tc ? 128 : SG_BM);
     int tiles = 0; bool inplace = false;

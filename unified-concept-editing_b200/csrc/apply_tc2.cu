@@ -1,4 +1,5 @@
-// Fused low-rank apply, second generation: TWO co-resident CTAs per SM (rank_pad <= 64).
+// Fused low-rank apply, second generation: TWO co-resident CTAs per SM (rank_pad <= 64), everything that touches HBM or L2
+// moves through TMA.
 //
 //   W_new[rows,:] = W_old[rows,:] + (W_old[rows,:] E^T) Q            (uce_sd_erase.py:45-82, see apply.cu)
 //
@@ -6,25 +7,30 @@
 // apply_tc.cu runs ONE 352-thread CTA per SM with all 512 TMEM columns and 198 KB of shared memory, so the HBM read
 // phase (A) and the L2-read / HBM-write phase (B) of a row tile run strictly one after the other on every SM, and the
 // 200 row tiles of an SD-1.4 edit take two waves on 148 SMs (ncu: SMs 55 % active, profiles/r01_apply_tc_ncu.txt).
-// Here a CTA is half as large — 224 threads, 256 TMEM columns, <= 98 KB of shared memory — so two of them share an SM:
+// Here a CTA is half as large — 224 threads, 256 TMEM columns, <= 105 KB of shared memory — so two of them share an SM:
 //   * all row tiles of an SD-1.4 edit are resident at once (296 slots): no second wave;
 //   * phase A of one tile overlaps phase B of the other: the SM's TMA ingest, tensor pipe and store path stay busy.
 //
 //   phase A  P[128,R] = W_tile[128,K] . E[R,K]^T in TMEM columns [0,R)
-//            * W TMA warp: raw fp32 chunks [tile_rows x 32] into a 3-deep ring (L2 evict_last)
+//            * W TMA warp: raw fp32 chunks [tile_rows x 32] into a 4-deep ring (L2 evict_last)
 //            * 4 transform warps (thread = tile row = TMEM lane): hi = rna_tf32(w), lo = w - hi, tcgen05.st into one
 //              of three 64-column A stages at TMEM columns [64,256)
-//            * E TMA warp: [R x 32] tiles of the pre-split E_hi, E_lo (3-deep ring)
-//            * MMA thread: per 8-wide k-step  hi.hi + hi.lo + lo.hi  (three N = R MMAs, A from TMEM)
-//   phase B  dW^T[128 W columns, 128 rows] = Qt[128,R] . P[128,R]^T per 128-column chunk, two ping-pong accumulators
-//            at TMEM columns [0,128) and [128,256) (they alias phase A, which is drained by then)
-//            * P: TMEM -> registers -> hi/lo -> swizzled smem (B operand)
-//            * Qt_hi / Qt_lo [128 x 32] tiles by TMA through a ring of 16 KB slots
-//            * epilogue (lane = W column, register = tile row): coalesced W_old addend loads (L2 hits, issued one
-//              32-row group ahead) and W_new stores (L2 evict_first)
+//            * E TMA warp: [R x 32] tiles of the pre-split E_hi, E_lo (2-deep ring, L2 resident)
+//            * MMA warp: per 8-wide k-step  hi.hi + hi.lo + lo.hi  (three N = R MMAs, A from TMEM)
+//   phase B  dW[128 rows, 32 cols] = P[128,R] . Q[R, 32 cols] per UNIT of 32 W columns, four 32-column accumulators
+//            at TMEM columns [128,256)
+//            * P stays in tensor memory: read back, split, stored as P_hi [0,R) | P_lo [R,2R) — the A operand
+//            * Qt_hi / Qt_lo [32 x 32] tiles (B operand) by TMA through a ring of 4 KB slots
+//            * the W_old addend of a unit arrives by TMA in a [tile_rows x 32] box (ring of 5, L2 hits), the epilogue
+//              warps add the accumulator IN PLACE (lane = row; the 128B swizzle makes the 16-byte accesses
+//              conflict-free) and the box leaves through ONE TMA store.
+//            Why not registers: the first version of this kernel loaded the addend with ld.global into registers, two
+//            32-row groups ahead — 16 k cycles per 128 columns (profiles/r01_apply_tc2_timeline.txt): every wait on
+//            a load scoreboard waits for ALL loads in flight on it, so register prefetch never overlapped anything.
+//            TMA keeps three boxes (48 KB) in flight per CTA with no register or scoreboard involvement.
 //
 // tile_rows (<= 128, multiple of 8) is a launch parameter: the TMA box, the row stride between tiles and the rows a CTA
-// stores; the MMAs always run M = 128 (rows beyond the box compute garbage that is never stored: rows are independent).
+// stores; the MMAs always run M = 128 (rows beyond the box are zero and never stored: rows are independent).
 #include "uce_ws.h"
 #include "tc_common.cuh"
 #include <cstdint>
@@ -37,14 +43,17 @@ using namespace uce::tc;
 
 constexpr int PW = 4;                                   // transform / P-conversion / epilogue warps
 constexpr int THREADS = (PW + 3) * 32;                  // + W TMA warp + E/Qt TMA warp + MMA warp
-constexpr int NRAW = 3, NSA = 3, NE = 3;
-constexpr int MAX_LAYERS = 160;
+constexpr int NRAW = 4, NSA = 3, NE = 2;
+constexpr int NB = 5;                                   // addend / output boxes (16 KB each)
+constexpr int NACC = 4;                                 // 32-column accumulators
+constexpr int MAX_LAYERS = 96;                          // two tensor maps per projection travel as kernel parameters
 constexpr int WARP_W_TMA = PW, WARP_E_TMA = PW + 1, WARP_MMA = PW + 2;
 constexpr uint32_t A_COL0 = 64;                         // A stages {W_hi 32 cols, W_lo 32 cols} at TMEM columns [64,256)
+constexpr uint32_t ACC_COL0 = 128;
 constexpr uint32_t TMEM_COLS = 256;
 
 struct Maps { CUtensorMap e_hi, e_lo, qt_hi, qt_lo; };
-struct WMaps { CUtensorMap w[MAX_LAYERS]; };
+struct WMaps { CUtensorMap in[MAX_LAYERS], out[MAX_LAYERS]; };
 
 __device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
@@ -116,20 +125,29 @@ __device__ __forceinline__ int find_layer(const LayerRef* layers, int n_layers, 
     return lo;
 }
 
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1, uint64_t pol) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;"
+                 ::"l"((uint64_t)map), "r"(src), "r"(c0), "r"(c1), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void tma_store_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(PW * 32) : "memory"); }
+
 // Shared-memory carve-up (bytes), identical on host and device.
-//   phase A   [0, 48K) raw ring: NRAW x 16 KB slots (a [tile_rows x 32] fp32 chunk of W each)
-//             [48K, 48K + NE * e_stage) E ring: {E_hi R*128 B, E_lo R*128 B} per stage
-//   phase B   [0, nq * 16K) Qt ring (one [128 x 32] tile of Qt_hi or Qt_lo per slot)
-//             [nq * 16K, + 2*128*R*4) P_hi | P_lo per 32-wide r atom       (aliases phase A, written after it is drained)
-struct Smem { int nq, e_stage, e_off, p_off, bar_off, total; };
+//   phase A   [0, 64K) raw ring: NRAW x 16 KB slots (a [tile_rows x 32] fp32 chunk of W each)
+//             [64K, 64K + NE * e_stage) E ring: {E_hi R*128 B, E_lo R*128 B} per stage
+//   phase B   [0, 80K) NB boxes of 16 KB (addend in, W_new out), then nq Qt slots of 4 KB   (aliases phase A, used after it is drained)
+struct Smem { int nq, e_stage, e_off, q_off, bar_off, total; };
 __host__ __device__ inline Smem smem_layout(int R) {
     Smem s;
-    s.nq = (R <= 32) ? 3 : 2;
+    s.nq = 6;
     s.e_stage = 2 * R * 128;
     s.e_off = NRAW * 16384;
-    s.p_off = s.nq * 16384;
+    s.q_off = NB * 16384;
     const int end_a = s.e_off + NE * s.e_stage;
-    const int end_b = s.p_off + 2 * 128 * R * 4;
+    const int end_b = s.q_off + s.nq * 4096;
     s.bar_off = end_a > end_b ? end_a : end_b;
     s.total = s.bar_off + 512;
     return s;
@@ -149,43 +167,44 @@ apply_tc2_kernel(const LayerRef* __restrict__ layers, int n_layers, int K, int R
 
     // ---- barriers ----
     const uint32_t bars = base + L.bar_off;
-    auto bar_raw_full  = [&](int r) { return bars + 8u * r; };                 // [0,3)   W TMA -> transform warps
-    auto bar_raw_empty = [&](int r) { return bars + 8u * (3 + r); };           // [3,6)
-    auto bar_a_full    = [&](int s) { return bars + 8u * (6 + s); };           // [6,9)   transform warps -> MMA (A stage written)
-    auto bar_a_empty   = [&](int s) { return bars + 8u * (9 + s); };           // [9,12)  MMA -> transform warps
-    auto bar_e_full    = [&](int s) { return bars + 8u * (12 + s); };          // [12,15) E TMA -> MMA
-    auto bar_e_empty   = [&](int s) { return bars + 8u * (15 + s); };          // [15,18)
-    const uint32_t bar_p_full = bars + 8u * 18, bar_p_smem = bars + 8u * 19;
-    auto bar_q_full    = [&](int t) { return bars + 8u * (20 + t); };          // [20,23)
-    auto bar_q_empty   = [&](int t) { return bars + 8u * (23 + t); };          // [23,26)
-    auto bar_acc_full  = [&](int b) { return bars + 8u * (26 + b); };          // [26,28)
-    auto bar_acc_empty = [&](int b) { return bars + 8u * (28 + b); };          // [28,30)
-    const uint32_t tmem_slot = bars + 8u * 30;
+    auto bar_raw_full  = [&](int r) { return bars + 8u * r; };                 // [0,4)   W TMA -> transform warps
+    auto bar_raw_empty = [&](int r) { return bars + 8u * (4 + r); };           // [4,8)
+    auto bar_a_full    = [&](int s) { return bars + 8u * (8 + s); };           // [8,11)  transform warps -> MMA (A stage written)
+    auto bar_a_empty   = [&](int s) { return bars + 8u * (11 + s); };          // [11,14) MMA -> transform warps
+    auto bar_e_full    = [&](int s) { return bars + 8u * (14 + s); };          // [14,16) E TMA -> MMA
+    auto bar_e_empty   = [&](int s) { return bars + 8u * (16 + s); };          // [16,18)
+    const uint32_t bar_p_full = bars + 8u * 18, bar_p_ready = bars + 8u * 19;
+    auto bar_q_full    = [&](int t) { return bars + 8u * (20 + t); };          // [20,28)
+    auto bar_q_empty   = [&](int t) { return bars + 8u * (28 + t); };          // [28,36)
+    auto bar_acc_full  = [&](int a) { return bars + 8u * (36 + a); };          // [36,40)
+    auto bar_acc_empty = [&](int a) { return bars + 8u * (40 + a); };          // [40,44)
+    auto bar_box_full  = [&](int b) { return bars + 8u * (44 + b); };          // [44,49)
+    auto bar_box_empty = [&](int b) { return bars + 8u * (49 + b); };          // [49,54)
+    const uint32_t tmem_slot = bars + 8u * 54;
 
     const int tile = blockIdx.x;
     const int layer = find_layer(layers, n_layers, tile);
     const LayerRef Lr = layers[layer];
     const int row0 = (tile - Lr.tile_begin) * tile_rows;
     const int rows_valid = min(tile_rows, Lr.d - row0);
-    const float* __restrict__ w_old = Lr.w_old + (size_t)row0 * K;
-    float* __restrict__ w_new = Lr.w_new + (size_t)row0 * K;
-    const int n_chunks = K / 32;          // phase A k-chunks (32 fp32 = one swizzle atom row)
-    const int n_kc = K / 128;             // phase B chunks of 128 W columns
+    const int n_chunks = K / 32;          // phase A k-chunks (32 fp32 = one swizzle atom row) == phase B units of 32 W columns
     const int n_rc = R / 32;              // r atoms
     const int NQ = L.nq;
+    const uint32_t box_bytes = (uint32_t)tile_rows * 128u;
 
     if (threadIdx.x == 0) {
         for (int r = 0; r < NRAW; ++r) { mbar_init(bar_raw_full(r), 1); mbar_init(bar_raw_empty(r), PW); }
         for (int s = 0; s < NSA; ++s) { mbar_init(bar_a_full(s), PW); mbar_init(bar_a_empty(s), 1); }
         for (int s = 0; s < NE; ++s) { mbar_init(bar_e_full(s), 1); mbar_init(bar_e_empty(s), 1); }
-        for (int t = 0; t < 3; ++t) { mbar_init(bar_q_full(t), 1); mbar_init(bar_q_empty(t), 1); }
-        mbar_init(bar_p_full, 1); mbar_init(bar_p_smem, PW);
-        for (int b = 0; b < 2; ++b) { mbar_init(bar_acc_full(b), 1); mbar_init(bar_acc_empty(b), PW); }
+        for (int t = 0; t < 8; ++t) { mbar_init(bar_q_full(t), 1); mbar_init(bar_q_empty(t), 1); }
+        mbar_init(bar_p_full, 1); mbar_init(bar_p_ready, PW);
+        for (int a = 0; a < NACC; ++a) { mbar_init(bar_acc_full(a), 1); mbar_init(bar_acc_empty(a), PW); }
+        for (int b = 0; b < NB; ++b) { mbar_init(bar_box_full(b), 1); mbar_init(bar_box_empty(b), 1); }
         mbar_fence_init();
     }
     if (warp == WARP_MMA) tmem_alloc(tmem_slot, TMEM_COLS);      // half of the SM's tensor memory: the co-resident CTA owns the rest
     if (warp == WARP_E_TMA && lane == 0) {
-        tma_prefetch_desc(&wmaps.w[layer]);
+        tma_prefetch_desc(&wmaps.in[layer]); tma_prefetch_desc(&wmaps.out[layer]);
         tma_prefetch_desc(&maps.e_hi); tma_prefetch_desc(&maps.e_lo); tma_prefetch_desc(&maps.qt_hi); tma_prefetch_desc(&maps.qt_lo);
     }
     fence_before();
@@ -197,25 +216,26 @@ apply_tc2_kernel(const LayerRef* __restrict__ layers, int n_layers, int K, int R
     auto raw_st = [&](int r) { return base + (uint32_t)(r * 16384); };
     auto stage_e_hi = [&](int s) { return base + (uint32_t)(L.e_off + s * L.e_stage); };
     auto stage_e_lo = [&](int s) { return base + (uint32_t)(L.e_off + s * L.e_stage + R * 128); };
-    auto p_hi_atom = [&](int rc) { return base + (uint32_t)(L.p_off + rc * 32768); };              // [P_hi(rc) 128 rows | P_lo(rc) 128 rows]
-    auto p_lo_atom = [&](int rc) { return base + (uint32_t)(L.p_off + rc * 32768 + 16384); };
-    auto qt_slot = [&](int t) { return base + (uint32_t)(t * 16384); };
+    auto box_st = [&](int b) { return base + (uint32_t)(b * 16384); };
+    auto qt_slot = [&](int t) { return base + (uint32_t)(L.q_off + t * 4096); };
 
     if (warp < PW) {
         // =============================== W transform, then P conversion, then epilogue ===============================
         const int trow = 32 * warp + lane;               // tile row == TMEM lane
         const bool row_live = trow < rows_valid;
         const uint32_t lane_base = tmem_base + ((uint32_t)(32 * warp) << 16);
+        const uint32_t row_off = (uint32_t)(trow * 128);
+        const uint32_t sw = (uint32_t)(trow & 7);
         for (int c = 0; c < n_chunks; ++c) {
             const int r = c % NRAW, s = c % NSA;
             mbar_wait(bar_raw_full(r), (uint32_t)((c / NRAW) & 1));
             if (threadIdx.x == 0) tr(1, c, 0);
-            const uint32_t raw = raw_st(r) + (uint32_t)(trow * 128);
+            const uint32_t raw = raw_st(r) + row_off;
             uint32_t hi[32], lo[32];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (row_live) v = lds_v4(raw + (uint32_t)(((j ^ (trow & 7)) << 4)));      // swizzled 16-byte slot the TMA wrote
+                if (row_live) v = lds_v4(raw + (((uint32_t)j ^ sw) << 4));      // swizzled 16-byte slot the TMA wrote
                 const float x[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
@@ -236,94 +256,94 @@ apply_tc2_kernel(const LayerRef* __restrict__ layers, int n_layers, int K, int R
             if (lane == 0) { mbar_arrive(bar_a_full(s)); mbar_arrive(bar_raw_empty(r)); }
             if (threadIdx.x == 0) tr(1, c, 2);
         }
-        // ---- P: TMEM -> registers -> hi/lo -> swizzled smem (B operand of phase B) ----
+        // ---- P: TMEM -> registers -> hi | lo -> TMEM columns [0,R) | [R,2R)  (A operand of phase B) ----
         mbar_wait(bar_p_full, 0);
         if (threadIdx.x == 0) tr(6, 0, 0);
         fence_after();
         for (int rc = 0; rc < n_rc; ++rc) {
-            uint32_t v[32];
+            uint32_t v[32], lo[32];
             tmem_ld32(lane_base + (uint32_t)(rc * 32), v);
-            const uint32_t hb = p_hi_atom(rc), lb = p_lo_atom(rc);
 #pragma unroll
-            for (int ch = 0; ch < 8; ++ch) {
-                const uint32_t off = (uint32_t)(trow * 128 + ((ch ^ (trow & 7)) << 4));
-                const float a = __uint_as_float(v[4 * ch]), b = __uint_as_float(v[4 * ch + 1]);
-                const float cc = __uint_as_float(v[4 * ch + 2]), d = __uint_as_float(v[4 * ch + 3]);
-                const float ha = tf32_hi(a), hb2 = tf32_hi(b), hc = tf32_hi(cc), hd = tf32_hi(d);
-                sts_v4(hb + off, ha, hb2, hc, hd);
-                sts_v4(lb + off, a - ha, b - hb2, cc - hc, d - hd);
+            for (int i = 0; i < 32; ++i) {
+                const float x = __uint_as_float(v[i]), h = tf32_hi(x);
+                v[i] = __float_as_uint(h);
+                lo[i] = __float_as_uint(x - h);
             }
+            tmem_st32(lane_base + (uint32_t)(rc * 32), v);
+            tmem_st32(lane_base + (uint32_t)(R + rc * 32), lo);
         }
-        fence_proxy_async();
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(bar_p_smem);
-        // ---- epilogue: W_new = W_old + dW, transposed accumulator (lane = W column, TMEM column = tile row) ----
-        // groups of 32 tile rows; the addend of group t+1 is requested before group t is combined and stored
+        if (lane == 0) mbar_arrive(bar_p_ready);
+        if (threadIdx.x == 0) tr(6, 0, 1);
+        // ---- epilogue: per unit of 32 W columns, box += accumulator (in place, swizzled smem), one TMA store per box ----
         const uint64_t pol_stream = l2_evict_first();
-        const int n_groups = n_kc * 4;
-        float w0[32], w1[32], w2[32];
-        auto load_addend = [&](float (&w)[32], int t) {
-            const int kc = t >> 2, g = t & 3;
-            const float* wp = w_old + (size_t)(32 * g) * K + (kc * 128 + 32 * warp + lane);
-            const int live = rows_valid - 32 * g;
+        const CUtensorMap* om = &wmaps.out[layer];
+        for (int u = 0; u < n_chunks; ++u) {
+            const int b = u % NB, a = u % NACC;
+            mbar_wait(bar_acc_full(a), (uint32_t)((u / NACC) & 1));
+            fence_after();
+            uint32_t v[32];
+            tmem_ld32(lane_base + ACC_COL0 + (uint32_t)(32 * a), v);
+            fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_acc_empty(a));
+            mbar_wait(bar_box_full(b), (uint32_t)((u / NB) & 1));
+            if (threadIdx.x == 0) tr(5, u, 0);
+            if (row_live) {
+                const uint32_t row = box_st(b) + row_off;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) w[i] = (i < live) ? ldg_f32(wp + (size_t)i * K) : 0.f;
-        };
-        auto finish_group = [&](float (&w)[32], int t) {
-            const int kc = t >> 2, g = t & 3, b = kc & 1;
-            if (g == 0) {
-                mbar_wait(bar_acc_full(b), (uint32_t)((kc >> 1) & 1));
-                if (threadIdx.x == 0) tr(5, kc, 1);
-                fence_after();
+                for (int j = 0; j < 8; ++j) {
+                    const uint32_t addr = row + (((uint32_t)j ^ sw) << 4);
+                    const float4 w = lds_v4(addr);
+                    sts_v4(addr, w.x + __uint_as_float(v[4 * j]), w.y + __uint_as_float(v[4 * j + 1]),
+                           w.z + __uint_as_float(v[4 * j + 2]), w.w + __uint_as_float(v[4 * j + 3]));
+                }
             }
-            float* op = w_new + (size_t)(32 * g) * K + (kc * 128 + 32 * warp + lane);
-            const int live = rows_valid - 32 * g;
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                uint32_t v[16];
-                tmem_ld16(lane_base + (uint32_t)(128 * b + 32 * g + 16 * h), v);
-#pragma unroll
-                for (int i = 0; i < 16; ++i)
-                    if (16 * h + i < live) stg_f32_hint(op + (size_t)(16 * h + i) * K, w[16 * h + i] + __uint_as_float(v[i]), pol_stream);
-            }
-            if (g == 3) {
-                fence_before();
+            fence_proxy_async();
+            epi_bar_sync();
+            if (warp == 0) {
+                if (elect_one()) {
+                    tma_store_2d(om, box_st(b), u * 32, row0, pol_stream);
+                    tma_store_commit();
+                    if (u > 0) {                                   // the previous box has been read out: hand it back to the loader
+                        tma_store_wait_read<1>();
+                        mbar_arrive(bar_box_empty((u - 1) % NB));
+                    }
+                    tr(5, u, 1);
+                }
                 __syncwarp();
-                if (lane == 0) mbar_arrive(bar_acc_empty(b));
-                if (threadIdx.x == 0) tr(5, kc, 2);
-            }
-        };
-        // two groups (64 loads per thread, 32 KB per CTA) are always in flight ahead of the group being combined
-        load_addend(w0, 0);
-        load_addend(w1, 1);
-        if (threadIdx.x == 0) tr(5, 0, 0);
-        for (int t = 0; t < n_groups; t += 3) {
-            if (t + 2 < n_groups) load_addend(w2, t + 2);
-            finish_group(w0, t);
-            if (t + 1 < n_groups) {
-                if (t + 3 < n_groups) load_addend(w0, t + 3);
-                finish_group(w1, t + 1);
-            }
-            if (t + 2 < n_groups) {
-                if (t + 4 < n_groups) load_addend(w1, t + 4);
-                finish_group(w2, t + 2);
             }
         }
+        if (warp == 0 && elect_one()) tma_store_wait_read<0>();   // smem must outlive the last store's read
     } else if (warp == WARP_W_TMA) {
-        // =============================== TMA warp 1: raw W chunks ===============================
+        // =============================== TMA warp 1: raw W chunks (phase A), addend boxes (phase B) ===============================
         // (all lanes wait, one elected lane issues: see elect_one() in tc_common.cuh)
         const uint64_t pol_keep = l2_evict_last();     // the tile is read again by the epilogue: keep it in L2
-        const CUtensorMap* wm = &wmaps.w[layer];
-        const uint32_t bytes = (uint32_t)tile_rows * 128u;
+        const uint64_t pol_last_use = l2_evict_first();
+        const CUtensorMap* wm = &wmaps.in[layer];
         for (int c = 0; c < n_chunks; ++c) {
             const int r = c % NRAW;
             mbar_wait(bar_raw_empty(r), (uint32_t)(((c / NRAW) & 1) ^ 1));
             __syncwarp();
             if (elect_one()) {
                 tr(0, c, 0);
-                mbar_arrive_expect_tx(bar_raw_full(r), bytes);
+                mbar_arrive_expect_tx(bar_raw_full(r), box_bytes);
                 tma_load_2d_hint(raw_st(r), wm, bar_raw_full(r), c * 32, row0, pol_keep);
+            }
+        }
+        // the boxes alias the raw / E rings: every phase-A MMA has completed once P is final, and an MMA on an A stage
+        // completes only after all four transform warps have read that raw chunk
+        mbar_wait(bar_p_full, 0);
+        for (int u = 0; u < n_chunks; ++u) {
+            const int b = u % NB;
+            mbar_wait(bar_box_empty(b), (uint32_t)(((u / NB) & 1) ^ 1));
+            __syncwarp();
+            if (elect_one()) {
+                tr(0, u, 1);
+                mbar_arrive_expect_tx(bar_box_full(b), box_bytes);
+                tma_load_2d_hint(box_st(b), wm, bar_box_full(b), u * 32, row0, pol_last_use);
             }
         }
     } else if (warp == WARP_E_TMA) {
@@ -340,19 +360,17 @@ apply_tc2_kernel(const LayerRef* __restrict__ layers, int n_layers, int K, int R
                 tma_load_2d(stage_e_lo(s), &maps.e_lo, bar_e_full(s), c * 32, 0);
             }
         }
-        // the Qt ring aliases the raw ring: every phase-A MMA has completed once P is final, and an MMA on an A stage
-        // completes only after all four transform warps have read that raw chunk
-        mbar_wait(bar_p_full, 0);
+        mbar_wait(bar_p_full, 0);                      // the Qt slots alias the E ring
         int it = 0;
-        for (int kc = 0; kc < n_kc; ++kc)
+        for (int u = 0; u < n_chunks; ++u)
             for (int rc = 0; rc < n_rc; ++rc)
                 for (int hl = 0; hl < 2; ++hl, ++it) {
                     const int t = it % NQ;
                     mbar_wait(bar_q_empty(t), (uint32_t)(((it / NQ) & 1) ^ 1));
                     __syncwarp();
                     if (elect_one()) {
-                        mbar_arrive_expect_tx(bar_q_full(t), 16384u);
-                        tma_load_2d(qt_slot(t), hl ? &maps.qt_lo : &maps.qt_hi, bar_q_full(t), rc * 32, kc * 128);
+                        mbar_arrive_expect_tx(bar_q_full(t), 4096u);
+                        tma_load_2d(qt_slot(t), hl ? &maps.qt_lo : &maps.qt_hi, bar_q_full(t), rc * 32, u * 32);
                     }
                 }
     } else {
@@ -382,30 +400,30 @@ apply_tc2_kernel(const LayerRef* __restrict__ layers, int n_layers, int K, int R
                 tr(3, c, 2);
             }
         }
-        // ---- phase B ----
-        mbar_wait(bar_p_smem, 0);
+        // ---- phase B: D[128 rows, 32 cols] = P_hi Qt_hi^T + P_lo Qt_hi^T + P_hi Qt_lo^T, A from tensor memory ----
+        mbar_wait(bar_p_ready, 0);
         fence_after();
-        const uint32_t idesc_b = idesc_tf32(128, 128);
+        const uint32_t idesc_b = idesc_tf32(128, 32);
+        const uint32_t p_hi = tmem_base, p_lo = tmem_base + (uint32_t)R;
         int it = 0;
-        for (int kc = 0; kc < n_kc; ++kc) {
-            const int b = kc & 1;
-            mbar_wait(bar_acc_empty(b), (uint32_t)(((kc >> 1) & 1) ^ 1));
+        for (int u = 0; u < n_chunks; ++u) {
+            const int a = u % NACC;
+            mbar_wait(bar_acc_empty(a), (uint32_t)(((u / NACC) & 1) ^ 1));
             fence_after();
-            const uint32_t d_tmem = tmem_base + 128u * (uint32_t)b;
+            const uint32_t d_tmem = tmem_base + ACC_COL0 + 32u * (uint32_t)a;
             for (int rc = 0; rc < n_rc; ++rc) {
-                const uint64_t b_hi = umma_desc_sw128(p_hi_atom(rc)), b_lo = umma_desc_sw128(p_lo_atom(rc));
                 int t = it % NQ;
                 mbar_wait(bar_q_full(t), (uint32_t)((it / NQ) & 1));
                 fence_after();
                 __syncwarp();
                 if (elect_one()) {
-                    if (rc == 0) tr(4, kc, 0);
-                    const uint64_t a = umma_desc_sw128(qt_slot(t));                 // Qt_hi tile: hi.hi + hi.lo
+                    if (rc == 0) tr(4, u, 0);
+                    const uint64_t bq = umma_desc_sw128(qt_slot(t));                 // Qt_hi tile: hi.hi + lo.hi
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         const uint64_t adv = (uint64_t)(k * 2);
-                        umma_tf32(d_tmem, a + adv, b_hi + adv, idesc_b, (rc | k) != 0);
-                        umma_tf32(d_tmem, a + adv, b_lo + adv, idesc_b, 1);
+                        umma_tf32_ts(d_tmem, p_hi + (uint32_t)(rc * 32 + 8 * k), bq + adv, idesc_b, (rc | k) != 0);
+                        umma_tf32_ts(d_tmem, p_lo + (uint32_t)(rc * 32 + 8 * k), bq + adv, idesc_b, 1);
                     }
                     umma_commit(bar_q_empty(t));
                 }
@@ -415,14 +433,12 @@ apply_tc2_kernel(const LayerRef* __restrict__ layers, int n_layers, int K, int R
                 fence_after();
                 __syncwarp();
                 if (elect_one()) {
-                    const uint64_t a = umma_desc_sw128(qt_slot(t));                 // Qt_lo tile: lo.hi
+                    const uint64_t bq = umma_desc_sw128(qt_slot(t));                 // Qt_lo tile: hi.lo
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const uint64_t adv = (uint64_t)(k * 2);
-                        umma_tf32(d_tmem, a + adv, b_hi + adv, idesc_b, 1);
-                    }
+                    for (int k = 0; k < 4; ++k)
+                        umma_tf32_ts(d_tmem, p_hi + (uint32_t)(rc * 32 + 8 * k), bq + (uint64_t)(k * 2), idesc_b, 1);
                     umma_commit(bar_q_empty(t));
-                    if (rc == n_rc - 1) { umma_commit(bar_acc_full(b)); tr(4, kc, 1); }
+                    if (rc == n_rc - 1) { umma_commit(bar_acc_full(a)); tr(4, u, 1); }
                 }
                 ++it;
             }
@@ -476,14 +492,16 @@ int apply_tc2_lowrank(uce_ws* ws, const LayerRef* layers_dev, const LayerRef* la
     for (int l = 0; l < n_layers; ++l)
         if (((uintptr_t)layers_host[l].w_old & 15) || ((uintptr_t)layers_host[l].w_new & 15)) { set_error("tcgen05 apply needs 16-byte aligned weights"); return UCE_E_ARG; }
     Maps maps;
-    static WMaps wmaps;      // 20 KB: kept off the stack; copied into the launch by value
+    static WMaps wmaps;      // 24 KB: kept off the stack; copied into the launch by value
     int rc;
     if ((rc = make_map(&maps.e_hi, ws->E_hi, R, K, R))) return rc;
     if ((rc = make_map(&maps.e_lo, ws->E_lo, R, K, R))) return rc;
-    if ((rc = make_map(&maps.qt_hi, ws->Qt_hi, K, R, 128))) return rc;
-    if ((rc = make_map(&maps.qt_lo, ws->Qt_lo, K, R, 128))) return rc;
-    for (int l = 0; l < n_layers; ++l)
-        if ((rc = make_map(&wmaps.w[l], layers_host[l].w_old, layers_host[l].d, K, tile_rows))) return rc;
+    if ((rc = make_map(&maps.qt_hi, ws->Qt_hi, K, R, 32))) return rc;
+    if ((rc = make_map(&maps.qt_lo, ws->Qt_lo, K, R, 32))) return rc;
+    for (int l = 0; l < n_layers; ++l) {
+        if ((rc = make_map(&wmaps.in[l], layers_host[l].w_old, layers_host[l].d, K, tile_rows))) return rc;
+        if ((rc = make_map(&wmaps.out[l], layers_host[l].w_new, layers_host[l].d, K, tile_rows))) return rc;
+    }
     const Smem L = smem_layout(R);
     const int smem = L.total + 1024;   // slack for the manual 1024-byte alignment
     static int configured = 0;

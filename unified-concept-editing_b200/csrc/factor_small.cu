@@ -104,9 +104,11 @@ __device__ __noinline__ void fs_potrf_warp(double* __restrict__ D, double* __res
         const double l = (lane == j) ? d * y : a[0] * y;      // L[lane][j] for lanes >= j
         if (lane >= j) D[lane * (FS_NB + 1) + j] = l;
         if (lane == j) invd_blk[j] = y;
+        const int kmax = FS_NB - 1 - j;                       // columns j + k <= 31 exist (warp-uniform early exit)
 #pragma unroll
         for (int k = 1; k < FS_NB; ++k) {                     // A[lane][j + k] -= L[lane][j] L[j + k][j]   (k = 1 first: the next pivot)
-            const double lk = __shfl_sync(0xffffffffu, l, (j + k) & 31);
+            if (k > kmax) break;
+            const double lk = __shfl_sync(0xffffffffu, l, j + k);
             a[k - 1] = fma(-l, lk, a[k]);
         }
     }
@@ -133,30 +135,28 @@ chol_small_kernel(double* __restrict__ Hg, int n, int n_pad, const double* __res
     //      loads of eight rows are requested before the first one is used (the old one-element-per-iteration loop spent
     //      23 k cycles here, one exposed HBM/L2 latency per iteration) ----
     {
+        constexpr int MAXB = (FS_MAX_N / FS_NB) * (FS_MAX_N / FS_NB + 1) / 2;     // 15 blocks: ALL loads are requested before any is used
         const int nb = nblk * (nblk + 1) / 2;
-        for (int b0 = 0; b0 < nb; b0 += 4) {
-            double v[4][2];
+        double v[MAXB][2];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int b = b0 + u;
-                int bi = 0;
-                while ((bi + 1) * (bi + 2) / 2 <= b) ++bi;
-                const int bj = b - bi * (bi + 1) / 2, c = bj * FS_NB + lane;
+        for (int b = 0; b < MAXB; ++b) {
+            int bi = 0;
+            while ((bi + 1) * (bi + 2) / 2 <= b) ++bi;
+            const int bj = b - bi * (bi + 1) / 2, c = bj * FS_NB + lane;
 #pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                    const int r = bi * FS_NB + warp * 2 + half;
-                    double x = (b < nb && r < n && c <= r) ? Hg[(long)r * n_pad + c] : 0.0;
-                    if (r == c) x = (r < n) ? x + dadd[r] : 1.0;
-                    v[u][half] = x;
-                }
+            for (int half = 0; half < 2; ++half) {
+                const int r = bi * FS_NB + warp * 2 + half;
+                double x = (b < nb && r < n && c <= r) ? Hg[(long)r * n_pad + c] : 0.0;
+                if (r == c) x = (r < n) ? x + dadd[r] : 1.0;
+                v[b][half] = x;
             }
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-                if (b0 + u < nb) {
-#pragma unroll
-                    for (int half = 0; half < 2; ++half) SB[(b0 + u) * FS_BLK + (warp * 2 + half) * P + lane] = v[u][half];
-                }
         }
+#pragma unroll
+        for (int b = 0; b < MAXB; ++b)
+            if (b < nb) {
+#pragma unroll
+                for (int half = 0; half < 2; ++half) SB[b * FS_BLK + (warp * 2 + half) * P + lane] = v[b][half];
+            }
     }
     for (int r = warp; r < n_pad; r += NW)
         for (int j = lane; j < n_edit; j += 32) XS[r * xl + j] = (r == n_pres + j) ? 1.0 : 0.0;
@@ -273,49 +273,60 @@ chol_small_kernel(double* __restrict__ Hg, int n, int n_pad, const double* __res
         }
     }
 
-    // ---- substitutions.  Thread = (row quad rq, right-hand side j): tid = rq * 64 + j, so no division by n_edit, the
-    //      right-hand-side reads are consecutive across lanes and the matrix coefficients are warp broadcasts. ----
-    const int sj = tid & 63, rq = tid >> 6;           // 8 row quads x 64 rhs slots
-    const bool s_on = sj < n_edit;
+    // ---- substitutions.  Register tiles of 8 rows x 2 right-hand sides (lane -> columns lane and lane + 32): the matrix
+    //      coefficients are warp broadcasts (one shared-memory wavefront each), the right-hand sides consecutive doubles,
+    //      12 wavefronts per 16 FMAs per lane.  (4 x 1 tiles were measured at 60 k cycles for the backward sweep: the loop
+    //      was bound by shared-memory wavefronts, 6 per 4 FMAs.)  Warp = one row octet: all block rows of an update step
+    //      are covered in ONE pass. ----
+    const bool on0 = lane < n_edit, on1 = lane + 32 < n_edit;
     // forward  L Y = rhs  (block rows above the first edit row stay zero)
     for (int kb = n_pres / FS_NB; kb < nblk; ++kb) {
         const double* D = SB + fs_blk(kb, kb);
         const int o = kb * FS_NB;
-        double out[4] = {0.0, 0.0, 0.0, 0.0};
-        if (s_on) {                                   // Y_k = L_kk^-1 X_k : Linv[rr][c] (c < rr) is stored at D[c][rr]
-            double iv[4];
+        double out[8][2];
+        if (warp < 4) {                               // Y_k = L_kk^-1 X_k : Linv[rr][c] (c < rr) is stored at D[c][rr]
 #pragma unroll
-            for (int i = 0; i < 4; ++i) iv[i] = invd[o + 4 * rq + i];
-#pragma unroll 8
+            for (int i = 0; i < 8; ++i) out[i][0] = out[i][1] = 0.0;
+#pragma unroll 4
             for (int c = 0; c < FS_NB; ++c) {
-                const double x = XS[(o + c) * xl + sj];
+                const double x0 = on0 ? XS[(o + c) * xl + lane] : 0.0, x1 = on1 ? XS[(o + c) * xl + lane + 32] : 0.0;
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int rr = 4 * rq + i;
+                for (int i = 0; i < 8; ++i) {
+                    const int rr = 8 * warp + i;
                     const double raw = D[c * P + rr];
-                    out[i] = fma((c < rr) ? raw : ((c == rr) ? iv[i] : 0.0), x, out[i]);
+                    const double coef = (c < rr) ? raw : ((c == rr) ? invd[o + rr] : 0.0);
+                    out[i][0] = fma(coef, x0, out[i][0]); out[i][1] = fma(coef, x1, out[i][1]);
                 }
             }
         }
         __syncthreads();
-        if (s_on) {
+        if (warp < 4) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) XS[(o + 4 * rq + i) * xl + sj] = out[i];
+            for (int i = 0; i < 8; ++i) {
+                if (on0) XS[(o + 8 * warp + i) * xl + lane] = out[i][0];
+                if (on1) XS[(o + 8 * warp + i) * xl + lane + 32] = out[i][1];
+            }
         }
         __syncthreads();
-        const int rest = n_pad - (o + FS_NB);         // X_i -= L_ik Y_k for the block rows below
-        for (int r = o + FS_NB + 4 * rq; r < o + FS_NB + rest; r += 32) {
-            if (!s_on) break;
+        for (int r = o + FS_NB + 8 * warp; r < n_pad; r += 8 * NW) {     // X_i -= L_ik Y_k for the block rows below
             const double* A = SB + fs_blk(r >> 5, kb) + (r & 31) * P;
-            double s4[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll 8
-            for (int c = 0; c < FS_NB; ++c) {
-                const double x = XS[(o + c) * xl + sj];
+            double s8[8][2];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) s4[i] = fma(A[i * P + c], x, s4[i]);
+            for (int i = 0; i < 8; ++i) s8[i][0] = s8[i][1] = 0.0;
+#pragma unroll 4
+            for (int c = 0; c < FS_NB; ++c) {
+                const double x0 = on0 ? XS[(o + c) * xl + lane] : 0.0, x1 = on1 ? XS[(o + c) * xl + lane + 32] : 0.0;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const double av = A[i * P + c];
+                    s8[i][0] = fma(av, x0, s8[i][0]); s8[i][1] = fma(av, x1, s8[i][1]);
+                }
             }
 #pragma unroll
-            for (int i = 0; i < 4; ++i) XS[(r + i) * xl + sj] -= s4[i];
+            for (int i = 0; i < 8; ++i) {
+                if (on0) XS[(r + i) * xl + lane] -= s8[i][0];
+                if (on1) XS[(r + i) * xl + lane + 32] -= s8[i][1];
+            }
         }
         __syncthreads();
     }
@@ -324,40 +335,50 @@ chol_small_kernel(double* __restrict__ Hg, int n, int n_pad, const double* __res
     for (int kb = nblk - 1; kb >= 0; --kb) {
         const double* D = SB + fs_blk(kb, kb);
         const int o = kb * FS_NB;
-        double out[4] = {0.0, 0.0, 0.0, 0.0};
-        if (s_on) {                                   // Z_k = L_kk^-T Y_k : Linv[c][rr] (c > rr) is stored at D[rr][c]
-            double iv[4];
+        double out[8][2];
+        if (warp < 4) {                               // Z_k = L_kk^-T Y_k : Linv[c][rr] (c > rr) is stored at D[rr][c]
 #pragma unroll
-            for (int i = 0; i < 4; ++i) iv[i] = invd[o + 4 * rq + i];
-#pragma unroll 8
+            for (int i = 0; i < 8; ++i) out[i][0] = out[i][1] = 0.0;
+#pragma unroll 4
             for (int c = 0; c < FS_NB; ++c) {
-                const double x = XS[(o + c) * xl + sj];
+                const double x0 = on0 ? XS[(o + c) * xl + lane] : 0.0, x1 = on1 ? XS[(o + c) * xl + lane + 32] : 0.0;
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int rr = 4 * rq + i;
+                for (int i = 0; i < 8; ++i) {
+                    const int rr = 8 * warp + i;
                     const double raw = D[rr * P + c];
-                    out[i] = fma((c > rr) ? raw : ((c == rr) ? iv[i] : 0.0), x, out[i]);
+                    const double coef = (c > rr) ? raw : ((c == rr) ? invd[o + rr] : 0.0);
+                    out[i][0] = fma(coef, x0, out[i][0]); out[i][1] = fma(coef, x1, out[i][1]);
                 }
             }
         }
         __syncthreads();
-        if (s_on) {
+        if (warp < 4) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) XS[(o + 4 * rq + i) * xl + sj] = out[i];
+            for (int i = 0; i < 8; ++i) {
+                if (on0) XS[(o + 8 * warp + i) * xl + lane] = out[i][0];
+                if (on1) XS[(o + 8 * warp + i) * xl + lane + 32] = out[i][1];
+            }
         }
         __syncthreads();
-        for (int r = 4 * rq; r < o; r += 32) {        // X_i -= L_ki^T Z_k for the block rows above
-            if (!s_on) break;
+        for (int r = 8 * warp; r < o; r += 8 * NW) {  // X_i -= L_ki^T Z_k for the block rows above
             const double* A = SB + fs_blk(kb, r >> 5) + (r & 31);          // L[o + c][r + i] = block(kb, r/32)[c][r%32 + i]
-            double s4[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll 8
-            for (int c = 0; c < FS_NB; ++c) {
-                const double x = XS[(o + c) * xl + sj];
+            double s8[8][2];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) s4[i] = fma(A[c * P + i], x, s4[i]);
+            for (int i = 0; i < 8; ++i) s8[i][0] = s8[i][1] = 0.0;
+#pragma unroll 4
+            for (int c = 0; c < FS_NB; ++c) {
+                const double x0 = on0 ? XS[(o + c) * xl + lane] : 0.0, x1 = on1 ? XS[(o + c) * xl + lane + 32] : 0.0;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const double av = A[c * P + i];
+                    s8[i][0] = fma(av, x0, s8[i][0]); s8[i][1] = fma(av, x1, s8[i][1]);
+                }
             }
 #pragma unroll
-            for (int i = 0; i < 4; ++i) XS[(r + i) * xl + sj] -= s4[i];
+            for (int i = 0; i < 8; ++i) {
+                if (on0) XS[(r + i) * xl + lane] -= s8[i][0];
+                if (on1) XS[(r + i) * xl + lane + 32] -= s8[i][1];
+            }
         }
         __syncthreads();
     }

@@ -43,8 +43,9 @@ using namespace uce::tc;
 
 constexpr int PW = 4;                                   // transform / P-conversion / epilogue warps
 constexpr int THREADS = (PW + 3) * 32;                  // + W TMA warp + E/Qt TMA warp + MMA warp
-constexpr int NRAW = 4, NSA = 3, NE = 2;
+constexpr int NRAW = 5, NSA = 3, NE = 2;
 constexpr int NB = 5;                                   // addend / output boxes (16 KB each)
+constexpr int NQ = 2;                                   // Qt slots: all hi/lo tiles of one 32-column unit (<= 16 KB) per slot
 constexpr int NACC = 4;                                 // 32-column accumulators
 constexpr int MAX_LAYERS = 96;                          // two tensor maps per projection travel as kernel parameters
 constexpr int WARP_W_TMA = PW, WARP_E_TMA = PW + 1, WARP_MMA = PW + 2;
@@ -135,19 +136,20 @@ template <int N> __device__ __forceinline__ void tma_store_wait_read() {
 }
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(PW * 32) : "memory"); }
 
-// Shared-memory carve-up (bytes), identical on host and device.
-//   phase A   [0, 64K) raw ring: NRAW x 16 KB slots (a [tile_rows x 32] fp32 chunk of W each)
-//             [64K, 64K + NE * e_stage) E ring: {E_hi R*128 B, E_lo R*128 B} per stage
-//   phase B   [0, 80K) NB boxes of 16 KB (addend in, W_new out), then nq Qt slots of 4 KB   (aliases phase A, used after it is drained)
-struct Smem { int nq, e_stage, e_off, q_off, bar_off, total; };
+// Shared-memory carve-up (bytes), identical on host and device.  The dynamic shared-memory window of a kernel without
+// static shared memory starts 1024-byte aligned (checked at run time), so no alignment slack is carried: two CTAs of
+// 112.5 KB fit the SM's 228 KB only without it.
+//   phase A   [0, 80K) raw ring: NRAW x 16 KB slots (a [tile_rows x 32] fp32 chunk of W each)
+//             [80K, 80K + NE * e_stage) E ring: {E_hi R*128 B, E_lo R*128 B} per stage
+//   phase B   [0, 80K) NB boxes of 16 KB (addend in, W_new out), then NQ Qt slots of 16 KB   (aliases phase A, used after it is drained)
+struct Smem { int e_stage, e_off, q_off, bar_off, total; };
 __host__ __device__ inline Smem smem_layout(int R) {
     Smem s;
-    s.nq = 6;
     s.e_stage = 2 * R * 128;
     s.e_off = NRAW * 16384;
     s.q_off = NB * 16384;
     const int end_a = s.e_off + NE * s.e_stage;
-    const int end_b = s.q_off + s.nq * 4096;
+    const int end_b = s.q_off + NQ * 16384;
     s.bar_off = end_a > end_b ? end_a : end_b;
     s.total = s.bar_off + 512;
     return s;
@@ -161,26 +163,30 @@ apply_tc2_kernel(const LayerRef* __restrict__ layers, int n_layers, int K, int R
         if (trace && blockIdx.x == 0 && idx < 64) trace[(role * 64 + idx) * 4 + ev] = clock64();
     };
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;      // swizzled tiles need 1024-byte alignment
+    const uint32_t base = smem_u32(smem_raw);                          // swizzled tiles need 1024-byte alignment
+    if (base & 1023u) {
+        if (threadIdx.x == 0) printf("uce apply_tc2: dynamic shared memory base %u is not 1024-byte aligned\n", base);
+        __trap();
+    }
     const Smem L = smem_layout(R);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     // ---- barriers ----
     const uint32_t bars = base + L.bar_off;
-    auto bar_raw_full  = [&](int r) { return bars + 8u * r; };                 // [0,4)   W TMA -> transform warps
-    auto bar_raw_empty = [&](int r) { return bars + 8u * (4 + r); };           // [4,8)
-    auto bar_a_full    = [&](int s) { return bars + 8u * (8 + s); };           // [8,11)  transform warps -> MMA (A stage written)
-    auto bar_a_empty   = [&](int s) { return bars + 8u * (11 + s); };          // [11,14) MMA -> transform warps
-    auto bar_e_full    = [&](int s) { return bars + 8u * (14 + s); };          // [14,16) E TMA -> MMA
-    auto bar_e_empty   = [&](int s) { return bars + 8u * (16 + s); };          // [16,18)
-    const uint32_t bar_p_full = bars + 8u * 18, bar_p_ready = bars + 8u * 19;
-    auto bar_q_full    = [&](int t) { return bars + 8u * (20 + t); };          // [20,28)
-    auto bar_q_empty   = [&](int t) { return bars + 8u * (28 + t); };          // [28,36)
-    auto bar_acc_full  = [&](int a) { return bars + 8u * (36 + a); };          // [36,40)
-    auto bar_acc_empty = [&](int a) { return bars + 8u * (40 + a); };          // [40,44)
-    auto bar_box_full  = [&](int b) { return bars + 8u * (44 + b); };          // [44,49)
-    auto bar_box_empty = [&](int b) { return bars + 8u * (49 + b); };          // [49,54)
-    const uint32_t tmem_slot = bars + 8u * 54;
+    auto bar_raw_full  = [&](int r) { return bars + 8u * r; };                 // [0,5)   W TMA -> transform warps
+    auto bar_raw_empty = [&](int r) { return bars + 8u * (5 + r); };           // [5,10)
+    auto bar_a_full    = [&](int s) { return bars + 8u * (10 + s); };          // [10,13) transform warps -> MMA (A stage written)
+    auto bar_a_empty   = [&](int s) { return bars + 8u * (13 + s); };          // [13,16) MMA -> transform warps
+    auto bar_e_full    = [&](int s) { return bars + 8u * (16 + s); };          // [16,18) E TMA -> MMA
+    auto bar_e_empty   = [&](int s) { return bars + 8u * (18 + s); };          // [18,20)
+    const uint32_t bar_p_full = bars + 8u * 20, bar_p_ready = bars + 8u * 21;
+    auto bar_q_full    = [&](int t) { return bars + 8u * (22 + t); };          // [22,24) Qt TMA -> MMA (all tiles of a unit)
+    auto bar_q_empty   = [&](int t) { return bars + 8u * (24 + t); };          // [24,26)
+    auto bar_acc_full  = [&](int a) { return bars + 8u * (26 + a); };          // [26,30) MMA -> epilogue
+    auto bar_acc_empty = [&](int a) { return bars + 8u * (30 + a); };          // [30,34)
+    auto bar_box_full  = [&](int b) { return bars + 8u * (34 + b); };          // [34,39) addend TMA -> epilogue
+    auto bar_box_ready = [&](int b) { return bars + 8u * (39 + b); };          // [39,44) epilogue -> W TMA warp (box holds W_new)
+    const uint32_t tmem_slot = bars + 8u * 44;
 
     const int tile = blockIdx.x;
     const int layer = find_layer(layers, n_layers, tile);
@@ -189,17 +195,16 @@ apply_tc2_kernel(const LayerRef* __restrict__ layers, int n_layers, int K, int R
     const int rows_valid = min(tile_rows, Lr.d - row0);
     const int n_chunks = K / 32;          // phase A k-chunks (32 fp32 = one swizzle atom row) == phase B units of 32 W columns
     const int n_rc = R / 32;              // r atoms
-    const int NQ = L.nq;
     const uint32_t box_bytes = (uint32_t)tile_rows * 128u;
 
     if (threadIdx.x == 0) {
         for (int r = 0; r < NRAW; ++r) { mbar_init(bar_raw_full(r), 1); mbar_init(bar_raw_empty(r), PW); }
         for (int s = 0; s < NSA; ++s) { mbar_init(bar_a_full(s), PW); mbar_init(bar_a_empty(s), 1); }
         for (int s = 0; s < NE; ++s) { mbar_init(bar_e_full(s), 1); mbar_init(bar_e_empty(s), 1); }
-        for (int t = 0; t < 8; ++t) { mbar_init(bar_q_full(t), 1); mbar_init(bar_q_empty(t), 1); }
+        for (int t = 0; t < NQ; ++t) { mbar_init(bar_q_full(t), 1); mbar_init(bar_q_empty(t), 1); }
         mbar_init(bar_p_full, 1); mbar_init(bar_p_ready, PW);
         for (int a = 0; a < NACC; ++a) { mbar_init(bar_acc_full(a), 1); mbar_init(bar_acc_empty(a), PW); }
-        for (int b = 0; b < NB; ++b) { mbar_init(bar_box_full(b), 1); mbar_init(bar_box_empty(b), 1); }
+        for (int b = 0; b < NB; ++b) { mbar_init(bar_box_full(b), 1); mbar_init(bar_box_ready(b), PW); }
         mbar_fence_init();
     }
     if (warp == WARP_MMA) tmem_alloc(tmem_slot, TMEM_COLS);      // half of the SM's tensor memory: the co-resident CTA owns the rest
@@ -217,7 +222,7 @@ apply_tc2_kernel(const LayerRef* __restrict__ layers, int n_layers, int K, int R
     auto stage_e_hi = [&](int s) { return base + (uint32_t)(L.e_off + s * L.e_stage); };
     auto stage_e_lo = [&](int s) { return base + (uint32_t)(L.e_off + s * L.e_stage + R * 128); };
     auto box_st = [&](int b) { return base + (uint32_t)(b * 16384); };
-    auto qt_slot = [&](int t) { return base + (uint32_t)(L.q_off + t * 4096); };
+    auto qt_tile = [&](int t, int i) { return base + (uint32_t)(L.q_off + t * 16384 + i * 4096); };     // tile i = 2 * rc + (0 hi, 1 lo)
 
     if (warp < PW) {
         // =============================== W transform, then P conversion, then epilogue ===============================
@@ -277,9 +282,7 @@ apply_tc2_kernel(const LayerRef* __restrict__ layers, int n_layers, int K, int R
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_p_ready);
         if (threadIdx.x == 0) tr(6, 0, 1);
-        // ---- epilogue: per unit of 32 W columns, box += accumulator (in place, swizzled smem), one TMA store per box ----
-        const uint64_t pol_stream = l2_evict_first();
-        const CUtensorMap* om = &wmaps.out[layer];
+        // ---- epilogue: per unit of 32 W columns, box += accumulator (in place, swizzled smem); the W TMA warp stores the box ----
         for (int u = 0; u < n_chunks; ++u) {
             const int b = u % NB, a = u % NACC;
             mbar_wait(bar_acc_full(a), (uint32_t)((u / NACC) & 1));
@@ -301,22 +304,11 @@ apply_tc2_kernel(const LayerRef* __restrict__ layers, int n_layers, int K, int R
                            w.z + __uint_as_float(v[4 * j + 2]), w.w + __uint_as_float(v[4 * j + 3]));
                 }
             }
-            fence_proxy_async();
-            epi_bar_sync();
-            if (warp == 0) {
-                if (elect_one()) {
-                    tma_store_2d(om, box_st(b), u * 32, row0, pol_stream);
-                    tma_store_commit();
-                    if (u > 0) {                                   // the previous box has been read out: hand it back to the loader
-                        tma_store_wait_read<1>();
-                        mbar_arrive(bar_box_empty((u - 1) % NB));
-                    }
-                    tr(5, u, 1);
-                }
-                __syncwarp();
-            }
+            fence_proxy_async();                       // generic-proxy writes -> visible to the TMA store
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_box_ready(b));
+            if (threadIdx.x == 0) tr(5, u, 1);
         }
-        if (warp == 0 && elect_one()) tma_store_wait_read<0>();   // smem must outlive the last store's read
     } else if (warp == WARP_W_TMA) {
         // =============================== TMA warp 1: raw W chunks (phase A), addend boxes (phase B) ===============================
         // (all lanes wait, one elected lane issues: see elect_one() in tc_common.cuh)
@@ -336,16 +328,37 @@ apply_tc2_kernel(const LayerRef* __restrict__ layers, int n_layers, int K, int R
         // the boxes alias the raw / E rings: every phase-A MMA has completed once P is final, and an MMA on an A stage
         // completes only after all four transform warps have read that raw chunk
         mbar_wait(bar_p_full, 0);
+        __syncwarp();
+        const uint64_t pol_stream = l2_evict_first();
+        const CUtensorMap* om = &wmaps.out[layer];
+        if (elect_one()) {
+            for (int u = 0; u < NB && u < n_chunks; ++u) {
+                mbar_arrive_expect_tx(bar_box_full(u), box_bytes);
+                tma_load_2d_hint(box_st(u), wm, bar_box_full(u), u * 32, row0, pol_last_use);
+            }
+        }
+        __syncwarp();
+        // box u: W_new is complete -> TMA store; once the PREVIOUS store has been read out of shared memory its box takes
+        // the addend of unit u - 1 + NB.  (One thread issues every store: bulk async-groups are per thread.)
         for (int u = 0; u < n_chunks; ++u) {
             const int b = u % NB;
-            mbar_wait(bar_box_empty(b), (uint32_t)(((u / NB) & 1) ^ 1));
+            mbar_wait(bar_box_ready(b), (uint32_t)((u / NB) & 1));
             __syncwarp();
             if (elect_one()) {
                 tr(0, u, 1);
-                mbar_arrive_expect_tx(bar_box_full(b), box_bytes);
-                tma_load_2d_hint(box_st(b), wm, bar_box_full(b), u * 32, row0, pol_last_use);
+                tma_store_2d(om, box_st(b), u * 32, row0, pol_stream);
+                tma_store_commit();
+                const int nu = u - 1 + NB;
+                if (u >= 1 && nu < n_chunks) {
+                    tma_store_wait_read<1>();
+                    const int nb = nu % NB;             // == (u - 1) % NB
+                    mbar_arrive_expect_tx(bar_box_full(nb), box_bytes);
+                    tma_load_2d_hint(box_st(nb), wm, bar_box_full(nb), nu * 32, row0, pol_last_use);
+                }
             }
         }
+        __syncwarp();
+        if (elect_one()) tma_store_wait_read<0>();     // shared memory must outlive the last store's read
     } else if (warp == WARP_E_TMA) {
         // =============================== TMA warp 2: E tiles (phase A), Qt tiles (phase B) ===============================
         const uint32_t e_bytes = 2u * (uint32_t)R * 128u;
@@ -361,18 +374,19 @@ apply_tc2_kernel(const LayerRef* __restrict__ layers, int n_layers, int K, int R
             }
         }
         mbar_wait(bar_p_full, 0);                      // the Qt slots alias the E ring
-        int it = 0;
-        for (int u = 0; u < n_chunks; ++u)
-            for (int rc = 0; rc < n_rc; ++rc)
-                for (int hl = 0; hl < 2; ++hl, ++it) {
-                    const int t = it % NQ;
-                    mbar_wait(bar_q_empty(t), (uint32_t)(((it / NQ) & 1) ^ 1));
-                    __syncwarp();
-                    if (elect_one()) {
-                        mbar_arrive_expect_tx(bar_q_full(t), 4096u);
-                        tma_load_2d(qt_slot(t), hl ? &maps.qt_lo : &maps.qt_hi, bar_q_full(t), rc * 32, u * 32);
-                    }
+        const uint32_t q_bytes = (uint32_t)(n_rc * 2) * 4096u;
+        for (int u = 0; u < n_chunks; ++u) {
+            const int t = u % NQ;
+            mbar_wait(bar_q_empty(t), (uint32_t)(((u / NQ) & 1) ^ 1));
+            __syncwarp();
+            if (elect_one()) {
+                mbar_arrive_expect_tx(bar_q_full(t), q_bytes);        // ONE barrier for all hi/lo tiles of the unit
+                for (int rc = 0; rc < n_rc; ++rc) {
+                    tma_load_2d(qt_tile(t, 2 * rc), &maps.qt_hi, bar_q_full(t), rc * 32, u * 32);
+                    tma_load_2d(qt_tile(t, 2 * rc + 1), &maps.qt_lo, bar_q_full(t), rc * 32, u * 32);
                 }
+            }
+        }
     } else {
         // =============================== MMA issuer ===============================
         // the whole warp runs the loops and the barrier waits (converged); ONE elected lane issues the MMAs and commits
@@ -405,42 +419,29 @@ apply_tc2_kernel(const LayerRef* __restrict__ layers, int n_layers, int K, int R
         fence_after();
         const uint32_t idesc_b = idesc_tf32(128, 32);
         const uint32_t p_hi = tmem_base, p_lo = tmem_base + (uint32_t)R;
-        int it = 0;
         for (int u = 0; u < n_chunks; ++u) {
-            const int a = u % NACC;
+            const int a = u % NACC, t = u % NQ;
             mbar_wait(bar_acc_empty(a), (uint32_t)(((u / NACC) & 1) ^ 1));
+            mbar_wait(bar_q_full(t), (uint32_t)((u / NQ) & 1));
             fence_after();
-            const uint32_t d_tmem = tmem_base + ACC_COL0 + 32u * (uint32_t)a;
-            for (int rc = 0; rc < n_rc; ++rc) {
-                int t = it % NQ;
-                mbar_wait(bar_q_full(t), (uint32_t)((it / NQ) & 1));
-                fence_after();
-                __syncwarp();
-                if (elect_one()) {
-                    if (rc == 0) tr(4, u, 0);
-                    const uint64_t bq = umma_desc_sw128(qt_slot(t));                 // Qt_hi tile: hi.hi + lo.hi
+            __syncwarp();
+            if (elect_one()) {
+                tr(4, u, 0);
+                const uint32_t d_tmem = tmem_base + ACC_COL0 + 32u * (uint32_t)a;
+                for (int rc = 0; rc < n_rc; ++rc) {
+                    const uint64_t bq_hi = umma_desc_sw128(qt_tile(t, 2 * rc)), bq_lo = umma_desc_sw128(qt_tile(t, 2 * rc + 1));
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         const uint64_t adv = (uint64_t)(k * 2);
-                        umma_tf32_ts(d_tmem, p_hi + (uint32_t)(rc * 32 + 8 * k), bq + adv, idesc_b, (rc | k) != 0);
-                        umma_tf32_ts(d_tmem, p_lo + (uint32_t)(rc * 32 + 8 * k), bq + adv, idesc_b, 1);
+                        const uint32_t col = (uint32_t)(rc * 32 + 8 * k);
+                        umma_tf32_ts(d_tmem, p_hi + col, bq_hi + adv, idesc_b, (rc | k) != 0);      // hi.hi
+                        umma_tf32_ts(d_tmem, p_lo + col, bq_hi + adv, idesc_b, 1);                  // lo.hi
+                        umma_tf32_ts(d_tmem, p_hi + col, bq_lo + adv, idesc_b, 1);                  // hi.lo
                     }
-                    umma_commit(bar_q_empty(t));
                 }
-                ++it;
-                t = it % NQ;
-                mbar_wait(bar_q_full(t), (uint32_t)((it / NQ) & 1));
-                fence_after();
-                __syncwarp();
-                if (elect_one()) {
-                    const uint64_t bq = umma_desc_sw128(qt_slot(t));                 // Qt_lo tile: hi.lo
-#pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        umma_tf32_ts(d_tmem, p_hi + (uint32_t)(rc * 32 + 8 * k), bq + (uint64_t)(k * 2), idesc_b, 1);
-                    umma_commit(bar_q_empty(t));
-                    if (rc == n_rc - 1) { umma_commit(bar_acc_full(a)); tr(4, u, 1); }
-                }
-                ++it;
+                umma_commit(bar_q_empty(t));
+                umma_commit(bar_acc_full(a));
+                tr(4, u, 1);
             }
         }
     }
@@ -503,7 +504,7 @@ int apply_tc2_lowrank(uce_ws* ws, const LayerRef* layers_dev, const LayerRef* la
         if ((rc = make_map(&wmaps.out[l], layers_host[l].w_new, layers_host[l].d, K, tile_rows))) return rc;
     }
     const Smem L = smem_layout(R);
-    const int smem = L.total + 1024;   // slack for the manual 1024-byte alignment
+    const int smem = L.total;          // no alignment slack: see smem_layout
     static int configured = 0;
     if (configured < smem) {
         UCE_CUDA(cudaFuncSetAttribute(apply_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));

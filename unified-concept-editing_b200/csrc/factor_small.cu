@@ -91,27 +91,36 @@ __device__ __forceinline__ double fs_rsqrt(double d) {
 // 61 k cycles on its first call of a launch — this kernel is one CTA that runs once, its code arrives through a cold
 // instruction cache — and 12.6 k afterwards; the left-looking shared-memory version before it took 26 k per block.
 // Columns j + k >= 32 do not exist: those lanes / registers hold finite garbage that never reaches a stored value.
+// One pivot step with the trailing update limited to KM columns (straight-line: the shuffles of all columns are issued
+// ahead of the FMAs; a per-column early exit was measured 1.8x SLOWER — the branches serialise shuffle and FMA latencies).
+template <int KM>
+__device__ __forceinline__ void fs_potrf_step(double (&a)[FS_NB], double* __restrict__ D, double* __restrict__ invd_blk, int lane, int j, bool& bad) {
+    double d = __shfl_sync(0xffffffffu, a[0], j);
+    if (!(d > 0.0)) { bad = true; d = 1.0; }
+    const double y = fs_rsqrt(d);
+    const double l = (lane == j) ? d * y : a[0] * y;      // L[lane][j] for lanes >= j
+    if (lane >= j) D[lane * (FS_NB + 1) + j] = l;
+    if (lane == j) invd_blk[j] = y;
+#pragma unroll
+    for (int k = 1; k <= KM; ++k) {                       // A[lane][j + k] -= L[lane][j] L[j + k][j]   (k = 1 first: the next pivot)
+        const double lk = __shfl_sync(0xffffffffu, l, (j + k) & 31);
+        a[k - 1] = fma(-l, lk, a[k]);
+    }
+}
 __device__ __noinline__ void fs_potrf_warp(double* __restrict__ D, double* __restrict__ invd_blk, int lane, int* flag, int kb) {
     double a[FS_NB];
 #pragma unroll
     for (int c = 0; c < FS_NB; ++c) a[c] = D[lane * (FS_NB + 1) + c];
     bool bad = false;
+    // columns j + k <= 31 exist: 31, 23, 15 and 7 trailing columns for the four quarters of the block
 #pragma unroll 1
-    for (int j = 0; j < FS_NB; ++j) {
-        double d = __shfl_sync(0xffffffffu, a[0], j);
-        if (!(d > 0.0)) { bad = true; d = 1.0; }
-        const double y = fs_rsqrt(d);
-        const double l = (lane == j) ? d * y : a[0] * y;      // L[lane][j] for lanes >= j
-        if (lane >= j) D[lane * (FS_NB + 1) + j] = l;
-        if (lane == j) invd_blk[j] = y;
-        const int kmax = FS_NB - 1 - j;                       // columns j + k <= 31 exist (warp-uniform early exit)
-#pragma unroll
-        for (int k = 1; k < FS_NB; ++k) {                     // A[lane][j + k] -= L[lane][j] L[j + k][j]   (k = 1 first: the next pivot)
-            if (k > kmax) break;
-            const double lk = __shfl_sync(0xffffffffu, l, j + k);
-            a[k - 1] = fma(-l, lk, a[k]);
-        }
-    }
+    for (int j = 0; j < 8; ++j) fs_potrf_step<31>(a, D, invd_blk, lane, j, bad);
+#pragma unroll 1
+    for (int j = 8; j < 16; ++j) fs_potrf_step<23>(a, D, invd_blk, lane, j, bad);
+#pragma unroll 1
+    for (int j = 16; j < 24; ++j) fs_potrf_step<15>(a, D, invd_blk, lane, j, bad);
+#pragma unroll 1
+    for (int j = 24; j < 32; ++j) fs_potrf_step<7>(a, D, invd_blk, lane, j, bad);
     if (bad && lane == 0) atomicCAS(flag, 0, 1 + kb);
 }
 

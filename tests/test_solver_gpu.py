@@ -106,7 +106,7 @@ def test_intermediates(n_edit, n_pres, K, fimpl):
     s.close()
 
 
-@pytest.mark.parametrize("impl", [1, 2, 3])
+@pytest.mark.parametrize("impl", [1, 2, 3, 4])
 def test_cfg2_full_model(impl):
     """BASELINE configs[1]: 50 erase + 100 preserve, all 32 SD-1.4 projections."""
     from uce_b200.synthetic import problem
@@ -309,6 +309,37 @@ def test_two_cta_tcgen05_apply(n_edit, K, dims, tile_rows, monkeypatch):
         assert O.rel_fro(b, e) <= TOL_EXACT, ("tc2 vs exact", O.rel_fro(b, e), O.rel_fro(a, e))
         assert O.rel_fro(b, a) <= 1e-5, ("tc2 vs simt", O.rel_fro(b, a))
     inpl = _run(s, C, G, scales, n_edit, 0.5, W, impl=3, inplace=True)
+    for a, b in zip(tc, inpl):
+        assert torch.equal(a, b)
+    s.close()
+
+
+@pytest.mark.parametrize("block_rows", [None, 128, 40])
+@pytest.mark.parametrize("n_edit,K,dims", [(2, 768, [320, 320]), (33, 768, [128, 64, 200]), (50, 768, [320, 640, 1280]),
+                                           (64, 256, [128, 384, 8]), (10, 2048, [640, 1280]), (5, 128, [300] * 40)])
+def test_two_block_tcgen05_apply(n_edit, K, dims, block_rows, monkeypatch):
+    """apply_tc3.cu (two row blocks per CTA, host tile plan, rank pad <= 64) against the SIMT fp32 apply and the fp64 oracle:
+    planned / full / short blocks (UCE_TC3_BLOCK_ROWS), a lone trailing block, several waves, in place."""
+    from uce_b200.synthetic import concept_rows, weights
+    if block_rows is None:
+        monkeypatch.delenv("UCE_TC3_BLOCK_ROWS", raising=False)
+    else:
+        monkeypatch.setenv("UCE_TC3_BLOCK_ROWS", str(block_rows))
+    n_pres = 20
+    rows = concept_rows(n_edit + n_pres + n_edit, K, seed=n_edit)
+    C, G = rows[: n_edit + n_pres], rows[n_edit + n_pres:]
+    W = weights(dims, K, seed=4)
+    scales = [1.0] * (n_edit + n_pres)
+    s = _solver(K, C.shape[0])
+    simt = _run(s, C, G, scales, n_edit, 0.5, W, impl=1)
+    tc = _run(s, C, G, scales, n_edit, 0.5, W, impl=4)
+    assert s.info()["launches_apply"] == 1
+    exact = O.erase_exact_f64(W[:4], C[:n_edit], G, C[n_edit:], 1.0, 1.0, 0.5)
+    for a, b, e in zip(simt, tc, exact):
+        assert O.rel_fro(b, e) <= TOL_EXACT, ("tc3 vs exact", O.rel_fro(b, e), O.rel_fro(a, e))
+    for a, b in zip(simt, tc):
+        assert O.rel_fro(b, a) <= 1e-5, ("tc3 vs simt", O.rel_fro(b, a))
+    inpl = _run(s, C, G, scales, n_edit, 0.5, W, impl=4, inplace=True)
     for a, b in zip(tc, inpl):
         assert torch.equal(a, b)
     s.close()

@@ -10,6 +10,7 @@
 #include "uce_ws.h"
 #include "gemm_simt.cuh"
 #include <algorithm>
+#include <vector>
 
 namespace uce {
 
@@ -19,6 +20,10 @@ bool apply_tc2_available(const uce_ws* ws);                 // apply_tc2.cu
 int apply_tc2_tile_rows();
 int apply_tc2_lowrank(uce_ws* ws, const LayerRef* layers_dev, const LayerRef* layers_host, int n_layers, int total_tiles,
                       int tile_rows, cudaStream_t st, int* launches);
+bool apply_tc3_available(const uce_ws* ws, int n_layers);   // apply_tc3.cu
+int apply_tc3_plan(const uce_ws* ws, const int* d, int n_layers, int* tile_rows, int* tile_begin);
+int apply_tc3_lowrank(uce_ws* ws, const LayerRef* layers_dev, const LayerRef* layers_host, int n_layers, int total_tiles,
+                      cudaStream_t st, int* launches);
 
 __device__ __forceinline__ int find_layer(const LayerRef* layers, int n_layers, int tile) {
     int lo = 0, hi = n_layers - 1;
@@ -118,17 +123,27 @@ int apply_dev(uce_ws* ws, const float* const* W_old, float* const* W_new, const 
     slot_begin = ws->ring_pos;
     ws->ring_pos += n_layers;
     LayerRef* hl = ws->h_layers + slot_begin;
-    // apply_impl: 0 auto, 1 SIMT, 2 tcgen05 with one CTA per SM (apply_tc.cu), 3 tcgen05 with two CTAs per SM (apply_tc2.cu, rank_pad <= 64)
+    // apply_impl: 0 auto, 1 SIMT, 2 tcgen05 one 128-row tile per CTA (apply_tc.cu), 3 tcgen05 two CTAs per SM (apply_tc2.cu,
+    // rank_pad <= 64), 4 tcgen05 two row blocks per CTA in one balanced wave (apply_tc3.cu, rank_pad <= 64)
     const bool lowrank = !ws->dense && ws->rank > 0;
-    const bool use_tc2 = lowrank && ((ws->apply_impl == 3) || (ws->apply_impl == 0 && apply_tc2_available(ws) && n_layers <= 96));
-    const bool use_tc = !use_tc2 && lowrank && ((ws->apply_impl == 2) || (ws->apply_impl == 0 && apply_tc_available(ws) && n_layers <= 160));
+    const bool use_tc3 = lowrank && ((ws->apply_impl == 4) || (ws->apply_impl == 0 && apply_tc3_available(ws, n_layers)));
+    const bool use_tc2 = !use_tc3 && lowrank && (ws->apply_impl == 3);
+    const bool use_tc = !use_tc3 && !use_tc2 && lowrank && ((ws->apply_impl == 2) || (ws->apply_impl == 0 && apply_tc_available(ws) && n_layers <= 160));
     const int tile_rows = use_tc2 ? apply_tc2_tile_rows() : (use_tc ? 128 : SG_BM);
     int tiles = 0; bool inplace = false;
     for (int l = 0; l < n_layers; ++l) {
         if (!W_old[l] || !W_new[l] || d[l] <= 0) { set_error("layer %d: null pointer or d <= 0", l); return UCE_E_ARG; }
-        hl[l] = LayerRef{W_old[l], W_new[l], d[l], tiles};
-        tiles += ceil_div(d[l], tile_rows);
         inplace |= (W_old[l] == W_new[l]);
+    }
+    if (use_tc3) {
+        std::vector<int> trows(n_layers), tbeg(n_layers);
+        tiles = apply_tc3_plan(ws, d, n_layers, trows.data(), tbeg.data());
+        for (int l = 0; l < n_layers; ++l) hl[l] = LayerRef{W_old[l], W_new[l], d[l], tbeg[l], trows[l]};
+    } else {
+        for (int l = 0; l < n_layers; ++l) {
+            hl[l] = LayerRef{W_old[l], W_new[l], d[l], tiles, 0};
+            tiles += ceil_div(d[l], tile_rows);
+        }
     }
     LayerRef* dl = ws->layers_dev + slot_begin;
     UCE_CUDA(cudaMemcpyAsync(dl, hl, n_layers * sizeof(LayerRef), cudaMemcpyHostToDevice, st));
@@ -144,7 +159,7 @@ int apply_dev(uce_ws* ws, const float* const* W_old, float* const* W_new, const 
         if (prof) UCE_CUDA(cudaEventRecord(ws->pev[4], st));
         return 0;
     }
-    const size_t need = (use_tc || use_tc2) ? 0 : (ws->dense ? (inplace ? (size_t)tiles * SG_BM * K : 0) : (size_t)tiles * SG_BM * r_pad);
+    const size_t need = (use_tc || use_tc2 || use_tc3) ? 0 : (ws->dense ? (inplace ? (size_t)tiles * SG_BM * K : 0) : (size_t)tiles * SG_BM * r_pad);
     // P scratch is shared by successive apply calls; they are ordered on one stream (host path: s_compute)
     if (need > ws->P_cap) {
         if (ws->P) { UCE_CUDA(cudaStreamSynchronize(st)); UCE_CUDA(cudaFree(ws->P)); ws->P = nullptr; }
@@ -152,7 +167,10 @@ int apply_dev(uce_ws* ws, const float* const* W_old, float* const* W_new, const 
         UCE_CUDA(cudaMalloc(&ws->P, ws->P_cap * sizeof(float)));
     }
     if (!ws->dense) {
-        if (use_tc2) {
+        if (use_tc3) {
+            int rc = apply_tc3_lowrank(ws, dl, hl, n_layers, tiles, st, &launches);
+            if (rc) return rc;
+        } else if (use_tc2) {
             int rc = apply_tc2_lowrank(ws, dl, hl, n_layers, tiles, tile_rows, st, &launches);
             if (rc) return rc;
         } else if (use_tc) {

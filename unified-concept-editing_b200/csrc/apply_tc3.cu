@@ -1,73 +1,67 @@
-// Fused low-rank apply, second generation: TWO co-resident CTAs per SM (rank_pad <= 64), everything that touches HBM or L2
-// moves through TMA.
+// Fused low-rank apply, third generation: ONE CTA per SM that carries TWO row blocks through a single E / Qt stream.
 //
 //   W_new[rows,:] = W_old[rows,:] + (W_old[rows,:] E^T) Q            (uce_sd_erase.py:45-82, see apply.cu)
 //
-// Same algebra, operands and fp32 fidelity (3xTF32, lo.lo dropped) as apply_tc.cu.  What changes is the shape of a CTA:
-// apply_tc.cu runs ONE 352-thread CTA per SM with all 512 TMEM columns and 198 KB of shared memory, so the HBM read
-// phase (A) and the L2-read / HBM-write phase (B) of a row tile run strictly one after the other on every SM, and the
-// 200 row tiles of an SD-1.4 edit take two waves on 148 SMs (ncu: SMs 55 % active, profiles/r01_apply_tc_ncu.txt).
-// Here a CTA is half as large — 224 threads, 256 TMEM columns, <= 105 KB of shared memory — so two of them share an SM:
-//   * all row tiles of an SD-1.4 edit are resident at once (296 slots): no second wave;
-//   * phase A of one tile overlaps phase B of the other: the SM's TMA ingest, tensor pipe and store path stay busy.
+// Same algebra, operands and fp32 fidelity (3xTF32, lo.lo dropped) as apply_tc.cu / apply_tc2.cu.  Why a third shape:
+// the timelines and ncu captures of apply_tc2.cu (profiles/) show that an SM moves ~35-45 B/clk through TMA whatever
+// the ring depths are, and that a row tile of 128 rows costs 1.57 MB of TMA ingest: its W rows twice (phase A, then the
+// addend of phase B; 2 x 393 KB) plus the WHOLE of E_hi|E_lo and Qt_hi|Qt_lo (2 x 393 KB) — the low-rank operands are
+// as large as the tile.  Two co-resident 128-row CTAs therefore stream E and Qt twice per SM, and with 200 tiles on
+// 148 SMs a third of the SMs carry twice the bytes of the others.  Here:
+//   * a CTA owns TWO row blocks of `h` rows (h <= 128, chosen per projection by the host so that ALL CTAs of an edit
+//     form one balanced wave: SD-1.4 -> 144 CTAs of 160-192 rows); both blocks share every E / Qt tile in shared memory:
+//     ingest per SM falls from 3.14 MB to ~1.9 MB;
+//   * 512 TMEM columns and 225 KB of shared memory belong to one CTA: 5-deep rings of block pairs.
 //
-//   phase A  P[128,R] = W_tile[128,K] . E[R,K]^T in TMEM columns [0,R)
-//            * W TMA warp: raw fp32 chunks [tile_rows x 32] into a 4-deep ring (L2 evict_last)
-//            * 4 transform warps (thread = tile row = TMEM lane): hi = rna_tf32(w), lo = w - hi, tcgen05.st into one
-//              of three 64-column A stages at TMEM columns [64,256)
-//            * E TMA warp: [R x 32] tiles of the pre-split E_hi, E_lo (2-deep ring, L2 resident)
-//            * MMA warp: per 8-wide k-step  hi.hi + hi.lo + lo.hi  (three N = R MMAs, A from TMEM)
-//   phase B  dW[128 rows, 32 cols] = P[128,R] . Q[R, 32 cols] per UNIT of 32 W columns, four 32-column accumulators
-//            at TMEM columns [128,256)
-//            * P stays in tensor memory: read back, split, stored as P_hi [0,R) | P_lo [R,2R) — the A operand
-//            * Qt_hi / Qt_lo [32 x 32] tiles (B operand) by TMA through a ring of 4 KB slots
-//            * the W_old addend of a unit arrives by TMA in a [tile_rows x 32] box (ring of 5, L2 hits), the epilogue
-//              warps add the accumulator IN PLACE (lane = row; the 128B swizzle makes the 16-byte accesses
-//              conflict-free) and the box leaves through ONE TMA store.
-//            Why not registers: the first version of this kernel loaded the addend with ld.global into registers, two
-//            32-row groups ahead — 16 k cycles per 128 columns (profiles/r01_apply_tc2_timeline.txt): every wait on
-//            a load scoreboard waits for ALL loads in flight on it, so register prefetch never overlapped anything.
-//            TMA keeps three boxes (48 KB) in flight per CTA with no register or scoreboard involvement.
-//
-// tile_rows (<= 128, multiple of 8) is a launch parameter: the TMA box, the row stride between tiles and the rows a CTA
-// stores; the MMAs always run M = 128 (rows beyond the box are zero and never stored: rows are independent).
+//   phase A  P_g[128,R] = W_g[128,K] . E[R,K]^T for both blocks g, TMEM columns [64g, 64g + R)
+//            * W TMA warp: per 32-column chunk one [h x 32] box per block (L2 evict_last), 5-deep ring
+//            * 8 transform warps (group g = warp / 4 works on block g; thread = row = TMEM lane): hi / lo split (integer
+//              round + mask + one subtraction: no conversion-pipe instruction), tcgen05.st into A stage (s, g)
+//            * E TMA warp: [R x 32] tiles of E_hi, E_lo, 3-deep ring
+//            * MMA warp (converged, one elected lane issues): per block and 8-wide k-step hi.hi + hi.lo + lo.hi (N = R, A from TMEM)
+//   phase B  dW_g[128 rows, 32 cols] = P_g . Q[:, 32 cols] per unit of 32 W columns
+//            * P_g stays in tensor memory: hi in place, lo in freed A-stage columns; A operand of the phase-B MMAs
+//            * Qt_hi / Qt_lo [32 x 32] tiles of a unit under ONE barrier, 2 slots
+//            * per unit and block a [h x 32] box: W_old addend in by TMA, accumulator added in place (swizzled smem, lane =
+//              row), W_new out by TMA store; the W TMA warp issues stores and reloads (6-deep ring of box pairs)
 #include "tc_apply_common.cuh"
 #include <cstdint>
 #include <cstdlib>
 #include <vector>
 
 namespace uce {
-namespace tc2 {
+namespace tc3 {
 using namespace uce::tc;
 using namespace uce::tca;
 
-constexpr int PW = 4;                                   // transform / P-conversion / epilogue warps
+constexpr int NBLK = 2;                                 // row blocks per CTA
+constexpr int PW = 4 * NBLK;                            // transform / P-conversion / epilogue warps (4 per block)
 constexpr int THREADS = (PW + 3) * 32;                  // + W TMA warp + E/Qt TMA warp + MMA warp
-constexpr int NRAW = 5, NSA = 3, NE = 2;
-constexpr int NB = 5;                                   // addend / output boxes (16 KB each)
-constexpr int NQ = 2;                                   // Qt slots: all hi/lo tiles of one 32-column unit (<= 16 KB) per slot
-constexpr int NACC = 4;                                 // 32-column accumulators
+constexpr int NRAW = 5, NSA = 3, NE = 3;
+constexpr int NB = 6;                                   // addend / output box pairs (2 x 16 KB each)
+constexpr int NACC = 4;                                 // accumulator pairs (2 x 32 columns)
+constexpr int NQ = 2;                                   // Qt slots (all hi/lo tiles of one unit, <= 16 KB)
 constexpr int MAX_LAYERS = 96;                          // two tensor maps per projection travel as kernel parameters
 constexpr int WARP_W_TMA = PW, WARP_E_TMA = PW + 1, WARP_MMA = PW + 2;
-constexpr uint32_t A_COL0 = 64;                         // A stages {W_hi 32 cols, W_lo 32 cols} at TMEM columns [64,256)
-constexpr uint32_t ACC_COL0 = 128;
-constexpr uint32_t TMEM_COLS = 256;
+constexpr uint32_t TMEM_COLS = 512;
+// tensor-memory columns
+__host__ __device__ constexpr uint32_t col_p(int g) { return 64u * g; }                       // phase A accumulator / phase B P_hi
+__host__ __device__ constexpr uint32_t col_stage(int s, int g) { return 128u + 128u * s + 64u * g; }   // {W_hi 32, W_lo 32}
+__host__ __device__ constexpr uint32_t col_plo(int g) { return 128u + 64u * g; }              // phase B P_lo (freed A stage 0)
+__host__ __device__ constexpr uint32_t col_acc(int a, int g) { return 256u + 64u * a + 32u * g; }
 
 struct Maps { CUtensorMap e_hi, e_lo, qt_hi, qt_lo; };
 struct WMaps { CUtensorMap in[MAX_LAYERS], out[MAX_LAYERS]; };
 
-// Shared-memory carve-up (bytes), identical on host and device.  The dynamic shared-memory window of a kernel without
-// static shared memory starts 1024-byte aligned (checked at run time), so no alignment slack is carried: two CTAs of
-// 112.5 KB fit the SM's 228 KB only without it.
-//   phase A   [0, 80K) raw ring: NRAW x 16 KB slots (a [tile_rows x 32] fp32 chunk of W each)
-//             [80K, 80K + NE * e_stage) E ring: {E_hi R*128 B, E_lo R*128 B} per stage
-//   phase B   [0, 80K) NB boxes of 16 KB (addend in, W_new out), then NQ Qt slots of 16 KB   (aliases phase A, used after it is drained)
+// Shared-memory carve-up (bytes), identical on host and device; the dynamic window starts 1024-byte aligned (checked).
+//   phase A   [0, 160K) raw ring: NRAW stages x NBLK slots of 16 KB     [160K, + NE * e_stage) E ring {E_hi | E_lo}
+//   phase B   [0, 192K) NB box pairs of 2 x 16 KB                        [192K, + NQ * 16K) Qt slots     (aliases phase A)
 struct Smem { int e_stage, e_off, q_off, bar_off, total; };
 __host__ __device__ inline Smem smem_layout(int R) {
     Smem s;
     s.e_stage = 2 * R * 128;
-    s.e_off = NRAW * 16384;
-    s.q_off = NB * 16384;
+    s.e_off = NRAW * NBLK * 16384;
+    s.q_off = NB * NBLK * 16384;
     const int end_a = s.e_off + NE * s.e_stage;
     const int end_b = s.q_off + NQ * 16384;
     s.bar_off = end_a > end_b ? end_a : end_b;
@@ -75,8 +69,17 @@ __host__ __device__ inline Smem smem_layout(int R) {
     return s;
 }
 
-__global__ void __launch_bounds__(THREADS, 2)
-apply_tc2_kernel(const LayerRef* __restrict__ layers, int n_layers, int K, int R, int tile_rows,
+__device__ __forceinline__ int find_layer(const LayerRef* layers, int n_layers, int tile) {
+    int lo = 0, hi = n_layers - 1;
+    while (lo < hi) {
+        int mid = (lo + hi + 1) >> 1;
+        if (layers[mid].tile_begin <= tile) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+
+__global__ void __launch_bounds__(THREADS, 1)
+apply_tc3_kernel(const LayerRef* __restrict__ layers, int n_layers, int K, int R,
                  const __grid_constant__ Maps maps, const __grid_constant__ WMaps wmaps, long long* __restrict__ trace) {
     // optional timeline of CTA 0 (UCE_TC_TRACE=<file>): trace[(role * 64 + index) * 4 + event] = clock64()
     auto tr = [&](int role, int idx, int ev) {
@@ -85,7 +88,7 @@ apply_tc2_kernel(const LayerRef* __restrict__ layers, int n_layers, int K, int R
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const uint32_t base = smem_u32(smem_raw);                          // swizzled tiles need 1024-byte alignment
     if (base & 1023u) {
-        if (threadIdx.x == 0) printf("uce apply_tc2: dynamic shared memory base %u is not 1024-byte aligned\n", base);
+        if (threadIdx.x == 0) printf("uce apply_tc3: dynamic shared memory base %u is not 1024-byte aligned\n", base);
         __trap();
     }
     const Smem L = smem_layout(R);
@@ -95,27 +98,29 @@ apply_tc2_kernel(const LayerRef* __restrict__ layers, int n_layers, int K, int R
     const uint32_t bars = base + L.bar_off;
     auto bar_raw_full  = [&](int r) { return bars + 8u * r; };                 // [0,5)   W TMA -> transform warps
     auto bar_raw_empty = [&](int r) { return bars + 8u * (5 + r); };           // [5,10)
-    auto bar_a_full    = [&](int s) { return bars + 8u * (10 + s); };          // [10,13) transform warps -> MMA (A stage written)
+    auto bar_a_full    = [&](int s) { return bars + 8u * (10 + s); };          // [10,13) transform warps -> MMA (A stages of both blocks written)
     auto bar_a_empty   = [&](int s) { return bars + 8u * (13 + s); };          // [13,16) MMA -> transform warps
-    auto bar_e_full    = [&](int s) { return bars + 8u * (16 + s); };          // [16,18) E TMA -> MMA
-    auto bar_e_empty   = [&](int s) { return bars + 8u * (18 + s); };          // [18,20)
-    const uint32_t bar_p_full = bars + 8u * 20, bar_p_ready = bars + 8u * 21;
-    auto bar_q_full    = [&](int t) { return bars + 8u * (22 + t); };          // [22,24) Qt TMA -> MMA (all tiles of a unit)
-    auto bar_q_empty   = [&](int t) { return bars + 8u * (24 + t); };          // [24,26)
-    auto bar_acc_full  = [&](int a) { return bars + 8u * (26 + a); };          // [26,30) MMA -> epilogue
-    auto bar_acc_empty = [&](int a) { return bars + 8u * (30 + a); };          // [30,34)
-    auto bar_box_full  = [&](int b) { return bars + 8u * (34 + b); };          // [34,39) addend TMA -> epilogue
-    auto bar_box_ready = [&](int b) { return bars + 8u * (39 + b); };          // [39,44) epilogue -> W TMA warp (box holds W_new)
-    const uint32_t tmem_slot = bars + 8u * 44;
+    auto bar_e_full    = [&](int s) { return bars + 8u * (16 + s); };          // [16,19) E TMA -> MMA
+    auto bar_e_empty   = [&](int s) { return bars + 8u * (19 + s); };          // [19,22)
+    const uint32_t bar_p_full = bars + 8u * 22, bar_p_ready = bars + 8u * 23;
+    auto bar_q_full    = [&](int t) { return bars + 8u * (24 + t); };          // [24,26) Qt TMA -> MMA (all tiles of a unit)
+    auto bar_q_empty   = [&](int t) { return bars + 8u * (26 + t); };          // [26,28)
+    auto bar_acc_full  = [&](int a) { return bars + 8u * (28 + a); };          // [28,32) MMA -> epilogue
+    auto bar_acc_empty = [&](int a) { return bars + 8u * (32 + a); };          // [32,36)
+    auto bar_box_full  = [&](int b) { return bars + 8u * (36 + b); };          // [36,42) addend TMA -> epilogue
+    auto bar_box_ready = [&](int b) { return bars + 8u * (42 + b); };          // [42,48) epilogue -> W TMA warp (boxes hold W_new)
+    const uint32_t tmem_slot = bars + 8u * 48;
 
     const int tile = blockIdx.x;
     const int layer = find_layer(layers, n_layers, tile);
     const LayerRef Lr = layers[layer];
-    const int row0 = (tile - Lr.tile_begin) * tile_rows;
-    const int rows_valid = min(tile_rows, Lr.d - row0);
+    const int h = Lr.tile_rows;                                  // rows per block (multiple of 8, <= 128)
+    const int row0 = (tile - Lr.tile_begin) * NBLK * h;
+    const int rows_valid0 = max(0, min(h, Lr.d - row0)), rows_valid1 = max(0, min(h, Lr.d - (row0 + h)));
+    const int n_act = rows_valid1 > 0 ? 2 : 1;                   // active blocks (block 0 always has rows)
     const int n_chunks = K / 32;          // phase A k-chunks (32 fp32 = one swizzle atom row) == phase B units of 32 W columns
     const int n_rc = R / 32;              // r atoms
-    const uint32_t box_bytes = (uint32_t)tile_rows * 128u;
+    const uint32_t box_bytes = (uint32_t)h * 128u;
 
     if (threadIdx.x == 0) {
         for (int r = 0; r < NRAW; ++r) { mbar_init(bar_raw_full(r), 1); mbar_init(bar_raw_empty(r), PW); }
@@ -127,7 +132,7 @@ apply_tc2_kernel(const LayerRef* __restrict__ layers, int n_layers, int K, int R
         for (int b = 0; b < NB; ++b) { mbar_init(bar_box_full(b), 1); mbar_init(bar_box_ready(b), PW); }
         mbar_fence_init();
     }
-    if (warp == WARP_MMA) tmem_alloc(tmem_slot, TMEM_COLS);      // half of the SM's tensor memory: the co-resident CTA owns the rest
+    if (warp == WARP_MMA) tmem_alloc(tmem_slot, TMEM_COLS);      // all of the SM's tensor memory: one CTA per SM
     if (warp == WARP_E_TMA && lane == 0) {
         tma_prefetch_desc(&wmaps.in[layer]); tma_prefetch_desc(&wmaps.out[layer]);
         tma_prefetch_desc(&maps.e_hi); tma_prefetch_desc(&maps.e_lo); tma_prefetch_desc(&maps.qt_hi); tma_prefetch_desc(&maps.qt_lo);
@@ -138,41 +143,37 @@ apply_tc2_kernel(const LayerRef* __restrict__ layers, int n_layers, int K, int R
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
-    auto raw_st = [&](int r) { return base + (uint32_t)(r * 16384); };
+    auto raw_st = [&](int r, int g) { return base + (uint32_t)((r * NBLK + g) * 16384); };
     auto stage_e_hi = [&](int s) { return base + (uint32_t)(L.e_off + s * L.e_stage); };
     auto stage_e_lo = [&](int s) { return base + (uint32_t)(L.e_off + s * L.e_stage + R * 128); };
-    auto box_st = [&](int b) { return base + (uint32_t)(b * 16384); };
+    auto box_st = [&](int b, int g) { return base + (uint32_t)((b * NBLK + g) * 16384); };
     auto qt_tile = [&](int t, int i) { return base + (uint32_t)(L.q_off + t * 16384 + i * 4096); };     // tile i = 2 * rc + (0 hi, 1 lo)
 
     if (warp < PW) {
-        // =============================== W transform, then P conversion, then epilogue ===============================
-        const int trow = 32 * warp + lane;               // tile row == TMEM lane
-        const bool row_live = trow < rows_valid;
-        const uint32_t lane_base = tmem_base + ((uint32_t)(32 * warp) << 16);
+        // =============================== W transform, then P conversion, then epilogue (group g = block g) ===============================
+        const int g = warp >> 2, wq = warp & 3;
+        const int trow = 32 * wq + lane;                 // row of the block == TMEM lane
+        const bool row_live = trow < (g ? rows_valid1 : rows_valid0);
+        const uint32_t lane_base = tmem_base + ((uint32_t)(32 * wq) << 16);
         const uint32_t row_off = (uint32_t)(trow * 128);
         const uint32_t sw = (uint32_t)(trow & 7);
         for (int c = 0; c < n_chunks; ++c) {
             const int r = c % NRAW, s = c % NSA;
             mbar_wait(bar_raw_full(r), (uint32_t)((c / NRAW) & 1));
             if (threadIdx.x == 0) tr(1, c, 0);
-            const uint32_t raw = raw_st(r) + row_off;
+            const uint32_t raw = raw_st(r, g) + row_off;
             uint32_t hi[32], lo[32];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (row_live) v = lds_v4(raw + (((uint32_t)j ^ sw) << 4));      // swizzled 16-byte slot the TMA wrote
-                const float x[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const float h = tf32_hi(x[e]);
-                    hi[4 * j + e] = __float_as_uint(h);
-                    lo[4 * j + e] = __float_as_uint(x[e] - h);
-                }
+                tf32_split(v.x, hi[4 * j], lo[4 * j]);         tf32_split(v.y, hi[4 * j + 1], lo[4 * j + 1]);
+                tf32_split(v.z, hi[4 * j + 2], lo[4 * j + 2]); tf32_split(v.w, hi[4 * j + 3], lo[4 * j + 3]);
             }
             mbar_wait(bar_a_empty(s), (uint32_t)(((c / NSA) & 1) ^ 1));      // the MMAs that read this A stage have completed
             if (threadIdx.x == 0) tr(1, c, 1);
             fence_after();
-            const uint32_t ta = lane_base + A_COL0 + (uint32_t)(64 * s);
+            const uint32_t ta = lane_base + col_stage(s, g);
             tmem_st32(ta, hi);
             tmem_st32(ta + 32u, lo);
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
@@ -181,21 +182,17 @@ apply_tc2_kernel(const LayerRef* __restrict__ layers, int n_layers, int K, int R
             if (lane == 0) { mbar_arrive(bar_a_full(s)); mbar_arrive(bar_raw_empty(r)); }
             if (threadIdx.x == 0) tr(1, c, 2);
         }
-        // ---- P: TMEM -> registers -> hi | lo -> TMEM columns [0,R) | [R,2R)  (A operand of phase B) ----
+        // ---- P_g: TMEM -> registers -> hi (in place) | lo (freed A-stage columns): the A operand of phase B ----
         mbar_wait(bar_p_full, 0);
         if (threadIdx.x == 0) tr(6, 0, 0);
         fence_after();
         for (int rc = 0; rc < n_rc; ++rc) {
             uint32_t v[32], lo[32];
-            tmem_ld32(lane_base + (uint32_t)(rc * 32), v);
+            tmem_ld32(lane_base + col_p(g) + (uint32_t)(rc * 32), v);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                const float x = __uint_as_float(v[i]), h = tf32_hi(x);
-                v[i] = __float_as_uint(h);
-                lo[i] = __float_as_uint(x - h);
-            }
-            tmem_st32(lane_base + (uint32_t)(rc * 32), v);
-            tmem_st32(lane_base + (uint32_t)(R + rc * 32), lo);
+            for (int i = 0; i < 32; ++i) tf32_split(__uint_as_float(v[i]), v[i], lo[i]);
+            tmem_st32(lane_base + col_p(g) + (uint32_t)(rc * 32), v);
+            tmem_st32(lane_base + col_plo(g) + (uint32_t)(rc * 32), lo);
         }
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         fence_before();
@@ -208,14 +205,14 @@ apply_tc2_kernel(const LayerRef* __restrict__ layers, int n_layers, int K, int R
             mbar_wait(bar_acc_full(a), (uint32_t)((u / NACC) & 1));
             fence_after();
             uint32_t v[32];
-            tmem_ld32(lane_base + ACC_COL0 + (uint32_t)(32 * a), v);
+            tmem_ld32(lane_base + col_acc(a, g), v);
             fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_acc_empty(a));
             mbar_wait(bar_box_full(b), (uint32_t)((u / NB) & 1));
             if (threadIdx.x == 0) tr(5, u, 0);
             if (row_live) {
-                const uint32_t row = box_st(b) + row_off;
+                const uint32_t row = box_st(b, g) + row_off;
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     const uint32_t addr = row + (((uint32_t)j ^ sw) << 4);
@@ -230,50 +227,51 @@ apply_tc2_kernel(const LayerRef* __restrict__ layers, int n_layers, int K, int R
             if (threadIdx.x == 0) tr(5, u, 1);
         }
     } else if (warp == WARP_W_TMA) {
-        // =============================== TMA warp 1: raw W chunks (phase A), addend boxes (phase B) ===============================
+        // =============================== TMA warp 1: raw W chunks (phase A), addend boxes in / W_new boxes out (phase B) ===============================
         // (all lanes wait, one elected lane issues: see elect_one() in tc_common.cuh)
-        const uint64_t pol_keep = l2_evict_last();     // the tile is read again by the epilogue: keep it in L2
+        const uint64_t pol_keep = l2_evict_last();     // the rows are read again as the addend: keep them in L2
         const uint64_t pol_last_use = l2_evict_first();
         const CUtensorMap* wm = &wmaps.in[layer];
+        const uint32_t pair_bytes = box_bytes * (uint32_t)n_act;
         for (int c = 0; c < n_chunks; ++c) {
             const int r = c % NRAW;
             mbar_wait(bar_raw_empty(r), (uint32_t)(((c / NRAW) & 1) ^ 1));
             __syncwarp();
             if (elect_one()) {
                 tr(0, c, 0);
-                mbar_arrive_expect_tx(bar_raw_full(r), box_bytes);
-                tma_load_2d_hint(raw_st(r), wm, bar_raw_full(r), c * 32, row0, pol_keep);
+                mbar_arrive_expect_tx(bar_raw_full(r), pair_bytes);
+                for (int g = 0; g < n_act; ++g) tma_load_2d_hint(raw_st(r, g), wm, bar_raw_full(r), c * 32, row0 + g * h, pol_keep);
             }
         }
         // the boxes alias the raw / E rings: every phase-A MMA has completed once P is final, and an MMA on an A stage
-        // completes only after all four transform warps have read that raw chunk
+        // completes only after the transform warps have read that raw chunk
         mbar_wait(bar_p_full, 0);
         __syncwarp();
         const uint64_t pol_stream = l2_evict_first();
         const CUtensorMap* om = &wmaps.out[layer];
         if (elect_one()) {
             for (int u = 0; u < NB && u < n_chunks; ++u) {
-                mbar_arrive_expect_tx(bar_box_full(u), box_bytes);
-                tma_load_2d_hint(box_st(u), wm, bar_box_full(u), u * 32, row0, pol_last_use);
+                mbar_arrive_expect_tx(bar_box_full(u), pair_bytes);
+                for (int g = 0; g < n_act; ++g) tma_load_2d_hint(box_st(u, g), wm, bar_box_full(u), u * 32, row0 + g * h, pol_last_use);
             }
         }
         __syncwarp();
-        // box u: W_new is complete -> TMA store; once the PREVIOUS store has been read out of shared memory its box takes
-        // the addend of unit u - 1 + NB.  (One thread issues every store: bulk async-groups are per thread.)
+        // unit u: W_new is complete -> TMA stores; once the PREVIOUS unit's stores have been read out of shared memory its
+        // boxes take the addend of unit u - 1 + NB.  (One thread issues every store: bulk async-groups are per thread.)
         for (int u = 0; u < n_chunks; ++u) {
             const int b = u % NB;
             mbar_wait(bar_box_ready(b), (uint32_t)((u / NB) & 1));
             __syncwarp();
             if (elect_one()) {
                 tr(0, u, 1);
-                tma_store_2d(om, box_st(b), u * 32, row0, pol_stream);
+                for (int g = 0; g < n_act; ++g) tma_store_2d(om, box_st(b, g), u * 32, row0 + g * h, pol_stream);
                 tma_store_commit();
                 const int nu = u - 1 + NB;
                 if (u >= 1 && nu < n_chunks) {
                     tma_store_wait_read<1>();
                     const int nb = nu % NB;             // == (u - 1) % NB
-                    mbar_arrive_expect_tx(bar_box_full(nb), box_bytes);
-                    tma_load_2d_hint(box_st(nb), wm, bar_box_full(nb), nu * 32, row0, pol_last_use);
+                    mbar_arrive_expect_tx(bar_box_full(nb), pair_bytes);
+                    for (int g = 0; g < n_act; ++g) tma_load_2d_hint(box_st(nb, g), wm, bar_box_full(nb), nu * 32, row0 + g * h, pol_last_use);
                 }
             }
         }
@@ -319,14 +317,17 @@ apply_tc2_kernel(const LayerRef* __restrict__ layers, int n_layers, int K, int R
             __syncwarp();
             if (elect_one()) {
                 tr(3, c, 1);
-                const uint32_t a_hi = tmem_base + A_COL0 + (uint32_t)(64 * s), a_lo = a_hi + 32u;
                 const uint64_t b_hi = umma_desc_sw128(stage_e_hi(se)), b_lo = umma_desc_sw128(stage_e_lo(se));
+                for (int g = 0; g < n_act; ++g) {
+                    const uint32_t a_hi = tmem_base + col_stage(s, g), a_lo = a_hi + 32u;
+                    const uint32_t d_tmem = tmem_base + col_p(g);
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {          // 8 tf32 per step: 8 TMEM columns of A, 32 bytes inside the swizzle atom of B
-                    const uint64_t adv = (uint64_t)(k * 2);
-                    umma_tf32_ts(tmem_base, a_hi + 8u * k, b_hi + adv, idesc_a, (c | k) != 0);
-                    umma_tf32_ts(tmem_base, a_hi + 8u * k, b_lo + adv, idesc_a, 1);
-                    umma_tf32_ts(tmem_base, a_lo + 8u * k, b_hi + adv, idesc_a, 1);
+                    for (int k = 0; k < 4; ++k) {      // 8 tf32 per step: 8 TMEM columns of A, 32 bytes inside the swizzle atom of B
+                        const uint64_t adv = (uint64_t)(k * 2);
+                        umma_tf32_ts(d_tmem, a_hi + 8u * k, b_hi + adv, idesc_a, (c | k) != 0);
+                        umma_tf32_ts(d_tmem, a_hi + 8u * k, b_lo + adv, idesc_a, 1);
+                        umma_tf32_ts(d_tmem, a_lo + 8u * k, b_hi + adv, idesc_a, 1);
+                    }
                 }
                 umma_commit(bar_a_empty(s));
                 umma_commit(bar_e_empty(se));
@@ -334,11 +335,10 @@ apply_tc2_kernel(const LayerRef* __restrict__ layers, int n_layers, int K, int R
                 tr(3, c, 2);
             }
         }
-        // ---- phase B: D[128 rows, 32 cols] = P_hi Qt_hi^T + P_lo Qt_hi^T + P_hi Qt_lo^T, A from tensor memory ----
+        // ---- phase B: D_g[128 rows, 32 cols] = P_hi Qt_hi^T + P_lo Qt_hi^T + P_hi Qt_lo^T, A from tensor memory ----
         mbar_wait(bar_p_ready, 0);
         fence_after();
         const uint32_t idesc_b = idesc_tf32(128, 32);
-        const uint32_t p_hi = tmem_base, p_lo = tmem_base + (uint32_t)R;
         for (int u = 0; u < n_chunks; ++u) {
             const int a = u % NACC, t = u % NQ;
             mbar_wait(bar_acc_empty(a), (uint32_t)(((u / NACC) & 1) ^ 1));
@@ -347,16 +347,19 @@ apply_tc2_kernel(const LayerRef* __restrict__ layers, int n_layers, int K, int R
             __syncwarp();
             if (elect_one()) {
                 tr(4, u, 0);
-                const uint32_t d_tmem = tmem_base + ACC_COL0 + 32u * (uint32_t)a;
-                for (int rc = 0; rc < n_rc; ++rc) {
-                    const uint64_t bq_hi = umma_desc_sw128(qt_tile(t, 2 * rc)), bq_lo = umma_desc_sw128(qt_tile(t, 2 * rc + 1));
+                for (int g = 0; g < n_act; ++g) {
+                    const uint32_t d_tmem = tmem_base + col_acc(a, g);
+                    const uint32_t p_hi = tmem_base + col_p(g), p_lo = tmem_base + col_plo(g);
+                    for (int rc = 0; rc < n_rc; ++rc) {
+                        const uint64_t bq_hi = umma_desc_sw128(qt_tile(t, 2 * rc)), bq_lo = umma_desc_sw128(qt_tile(t, 2 * rc + 1));
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const uint64_t adv = (uint64_t)(k * 2);
-                        const uint32_t col = (uint32_t)(rc * 32 + 8 * k);
-                        umma_tf32_ts(d_tmem, p_hi + col, bq_hi + adv, idesc_b, (rc | k) != 0);      // hi.hi
-                        umma_tf32_ts(d_tmem, p_lo + col, bq_hi + adv, idesc_b, 1);                  // lo.hi
-                        umma_tf32_ts(d_tmem, p_hi + col, bq_lo + adv, idesc_b, 1);                  // hi.lo
+                        for (int k = 0; k < 4; ++k) {
+                            const uint64_t adv = (uint64_t)(k * 2);
+                            const uint32_t col = (uint32_t)(rc * 32 + 8 * k);
+                            umma_tf32_ts(d_tmem, p_hi + col, bq_hi + adv, idesc_b, (rc | k) != 0);      // hi.hi
+                            umma_tf32_ts(d_tmem, p_lo + col, bq_hi + adv, idesc_b, 1);                  // lo.hi
+                            umma_tf32_ts(d_tmem, p_hi + col, bq_lo + adv, idesc_b, 1);                  // hi.lo
+                        }
                     }
                 }
                 umma_commit(bar_q_empty(t));
@@ -388,28 +391,47 @@ static int make_map(CUtensorMap* m, const float* ptr, int rows, int cols, int bo
     return 0;
 }
 
-}  // namespace tc2
+}  // namespace tc3
 
-bool apply_tc2_available(const uce_ws* ws) {
+bool apply_tc3_available(const uce_ws* ws, int n_layers) {
     const int R = ws->rank_pad;
-    return ws->K % 128 == 0 && (R == 32 || R == 64) && !ws->dense && ws->rank > 0 && tensor_map_encoder() != nullptr;
+    return ws->K % 128 == 0 && (R == 32 || R == 64) && !ws->dense && ws->rank > 0 && n_layers <= tc3::MAX_LAYERS &&
+           tensor_map_encoder() != nullptr;
 }
 
-// Rows per tile: UCE_TC2_TILE_ROWS (multiple of 8 in [8,128], read on every call) or 128.
-int apply_tc2_tile_rows() {
-    if (const char* e = getenv("UCE_TC2_TILE_ROWS")) {
+// Tile plan: rows per block for every projection (tile_rows[l]; a CTA owns two blocks) and the total number of CTAs.
+// When the whole edit fits one wave of CTAs (one per SM) the block height is the SMALLEST that still fits — the most
+// even spread of rows, hence of TMA bytes, over the SMs — and is then evened out inside each projection; otherwise
+// blocks are 128 rows.  UCE_TC3_BLOCK_ROWS (multiple of 8 in [8,128]) overrides the search.
+int apply_tc3_plan(const uce_ws* ws, const int* d, int n_layers, int* tile_rows, int* tile_begin) {
+    auto count = [&](int H) { long t = 0; for (int l = 0; l < n_layers; ++l) t += ceil_div(d[l], 2 * H); return t; };
+    int H = 128;
+    int forced = 0;
+    if (const char* e = getenv("UCE_TC3_BLOCK_ROWS")) {
         const int t = atoi(e);
-        if (t >= 8 && t <= 128 && t % 8 == 0) return t;
+        if (t >= 8 && t <= 128 && t % 8 == 0) { H = t; forced = 1; }
     }
-    return 128;
+    const int sms = ws->sm_count > 0 ? ws->sm_count : 148;
+    if (!forced && count(128) <= sms)
+        for (int t = 8; t <= 128; t += 8)
+            if (count(t) <= sms) { H = t; break; }
+    int tiles = 0;
+    for (int l = 0; l < n_layers; ++l) {
+        const int nt = ceil_div(d[l], 2 * H);
+        int hl = forced ? H : round_up(ceil_div(d[l], 2 * nt), 8);       // even split of the projection's rows over its CTAs
+        if (hl > 128) hl = 128;
+        tile_rows[l] = hl;
+        tile_begin[l] = tiles;
+        tiles += ceil_div(d[l], 2 * hl);
+    }
+    return tiles;
 }
 
-int apply_tc2_lowrank(uce_ws* ws, const LayerRef* layers_dev, const LayerRef* layers_host, int n_layers, int total_tiles,
-                      int tile_rows, cudaStream_t st, int* launches) {
-    using namespace tc2;
+int apply_tc3_lowrank(uce_ws* ws, const LayerRef* layers_dev, const LayerRef* layers_host, int n_layers, int total_tiles,
+                      cudaStream_t st, int* launches) {
+    using namespace tc3;
     const int K = ws->K, R = ws->rank_pad;
-    if (!apply_tc2_available(ws)) { set_error("two-CTA tcgen05 apply unavailable for K=%d rank_pad=%d dense=%d", K, R, ws->dense); return UCE_E_STATE; }
-    if (n_layers > MAX_LAYERS) { set_error("tcgen05 apply takes at most %d projections per call", MAX_LAYERS); return UCE_E_STATE; }
+    if (!apply_tc3_available(ws, n_layers)) { set_error("two-block tcgen05 apply unavailable for K=%d rank_pad=%d dense=%d layers=%d", K, R, ws->dense, n_layers); return UCE_E_STATE; }
     for (int l = 0; l < n_layers; ++l)
         if (((uintptr_t)layers_host[l].w_old & 15) || ((uintptr_t)layers_host[l].w_new & 15)) { set_error("tcgen05 apply needs 16-byte aligned weights"); return UCE_E_ARG; }
     Maps maps;
@@ -420,34 +442,33 @@ int apply_tc2_lowrank(uce_ws* ws, const LayerRef* layers_dev, const LayerRef* la
     if ((rc = make_map(&maps.qt_hi, ws->Qt_hi, K, R, 32))) return rc;
     if ((rc = make_map(&maps.qt_lo, ws->Qt_lo, K, R, 32))) return rc;
     for (int l = 0; l < n_layers; ++l) {
-        if ((rc = make_map(&wmaps.in[l], layers_host[l].w_old, layers_host[l].d, K, tile_rows))) return rc;
-        if ((rc = make_map(&wmaps.out[l], layers_host[l].w_new, layers_host[l].d, K, tile_rows))) return rc;
+        if ((rc = make_map(&wmaps.in[l], layers_host[l].w_old, layers_host[l].d, K, layers_host[l].tile_rows))) return rc;
+        if ((rc = make_map(&wmaps.out[l], layers_host[l].w_new, layers_host[l].d, K, layers_host[l].tile_rows))) return rc;
     }
     const Smem L = smem_layout(R);
-    const int smem = L.total;          // no alignment slack: see smem_layout
+    const int smem = L.total;
     static int configured = 0;
     if (configured < smem) {
-        UCE_CUDA(cudaFuncSetAttribute(apply_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        UCE_CUDA(cudaFuncSetAttribute(apply_tc2_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        UCE_CUDA(cudaFuncSetAttribute(apply_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured = smem;
     }
     long long* trace = nullptr;
     const char* trace_path = getenv("UCE_TC_TRACE");
     if (trace_path) { UCE_CUDA(cudaMalloc(&trace, 7 * 64 * 4 * sizeof(long long))); UCE_CUDA(cudaMemsetAsync(trace, 0, 7 * 64 * 4 * sizeof(long long), st)); }
-    apply_tc2_kernel<<<total_tiles, THREADS, smem, st>>>(layers_dev, n_layers, K, R, tile_rows, maps, wmaps, trace);
+    apply_tc3_kernel<<<total_tiles, THREADS, smem, st>>>(layers_dev, n_layers, K, R, maps, wmaps, trace);
     UCE_LAUNCH_CHECK();
     *launches += 1;
     if (trace) {   // debugging aid: dump the timeline of CTA 0 (synchronises)
-        std::vector<long long> h(7 * 64 * 4);
+        std::vector<long long> hbuf(7 * 64 * 4);
         UCE_CUDA(cudaStreamSynchronize(st));
-        UCE_CUDA(cudaMemcpy(h.data(), trace, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+        UCE_CUDA(cudaMemcpy(hbuf.data(), trace, hbuf.size() * sizeof(long long), cudaMemcpyDeviceToHost));
         UCE_CUDA(cudaFree(trace));
         if (FILE* f = fopen(trace_path, "w")) {
             long long t0 = 0;
-            for (long long v : h) if (v && (!t0 || v < t0)) t0 = v;
+            for (long long v : hbuf) if (v && (!t0 || v < t0)) t0 = v;
             const char* roles[7] = {"w_tma", "transform", "e_tma", "mma_a", "mma_b", "epilogue", "pconv"};
             for (int r = 0; r < 7; ++r) for (int i = 0; i < 64; ++i) {
-                const long long* e = &h[(r * 64 + i) * 4];
+                const long long* e = &hbuf[(r * 64 + i) * 4];
                 if (e[0] || e[1] || e[2]) fprintf(f, "%s %d %lld %lld %lld\n", roles[r], i, e[0] ? e[0] - t0 : -1, e[1] ? e[1] - t0 : -1, e[2] ? e[2] - t0 : -1);
             }
             fclose(f);

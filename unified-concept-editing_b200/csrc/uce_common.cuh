@@ -40,6 +40,7 @@ struct LayerRef {
     float*       w_new;
     int          d;          // rows (out_features of attn2.to_k / to_v)
     int          tile_begin; // first row-tile index of this layer in the flattened tile list
+    int          tile_rows;  // rows per block of this layer (apply_tc3.cu: chosen per projection by the host planner; 0 elsewhere)
 };
 
 }  // namespace uce

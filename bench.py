@@ -282,22 +282,43 @@ def run_ours(args, rank, world, local_rank):
         # algorithmic bytes of the apply: read W_old once + write W_new once (fp32) + E and Q once
         alg_bytes = 2 * w_bytes + 2 * 4 * K * max(info["rank"], 1)
         traffic, traffic_src = None, None          # DRAM bytes of one launch from the committed ncu --set full capture of this command
+        impl_name = {0: "auto", 1: "simt", 2: "tc", 3: "tc2", 4: "tc3"}.get(args.apply_impl or 0, "auto")
+        prof_file = {"auto": "r01_apply_tc3_ncu.txt", "tc3": "r01_apply_tc3_ncu.txt", "tc2": "r01_apply_tc2_ncu.txt", "tc": "r01_apply_tc_ncu.txt"}.get(impl_name)
         try:
-            prof = os.path.join(ROOT, "profiles", "r01_apply_tc_ncu.txt")
+            prof = os.path.join(ROOT, "profiles", prof_file)
             vals = {}
             for ln in open(prof):
                 f = ln.split()
                 if len(f) >= 3 and f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
                     vals[f[0]] = float(f[1]) * {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}[f[2]]
             if len(vals) == 2 and args.workload == "cfg2":
-                traffic, traffic_src = sum(vals.values()), "profiles/r01_apply_tc_ncu.txt (dram__bytes_read.sum + dram__bytes_write.sum; the written tile partly stays in L2 at kernel end)"
+                traffic, traffic_src = sum(vals.values()), f"profiles/{prof_file} (dram__bytes_read.sum + dram__bytes_write.sum; part of the written rows still sits in L2 at kernel end)"
         except Exception:
             pass
         dom_ms = a1_ms + a2_ms
+        apply_kernel = {"auto": "apply_tc3_kernel", "tc3": "apply_tc3_kernel", "tc2": "apply_tc2_kernel", "tc": "apply_tc_kernel", "simt": "apply_simt_*"}[impl_name]
+        copy_ref = None
+        try:      # context only: a flat device-to-device copy of the same footprint, same rotation, same events
+            n_el = w_bytes // 4
+            cs = [torch.empty(n_el, device=dev) for _ in range(2 * min(R, 3))]
+            hh = len(cs) // 2
+            for i in range(4):
+                cs[hh + i % hh].copy_(cs[i % hh])
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c0.record()
+            for i in range(20):
+                cs[hh + i % hh].copy_(cs[i % hh])
+            c1.record(); torch.cuda.synchronize(dev)
+            c_ms = c0.elapsed_time(c1) / 20
+            copy_ref = {"what": "torch copy_ of one flat fp32 buffer of the same bytes (read once, write once)", "ms": c_ms, "GB/s": 2 * w_bytes / c_ms / 1e6}
+            del cs
+        except Exception:
+            pass
         achieved = alg_bytes / (dom_ms / 1e3) / 1e9
-        roof = {"bound": "hbm", "kernel": "apply (W_new = W_old + (W_old E^T) Q over all projections)", "achieved": achieved,
+        roof = {"bound": "hbm", "kernel": "apply (W_new = W_old + (W_old E^T) Q over all projections, one launch: " + apply_kernel + ")", "achieved": achieved,
                 "peak": peak_bw, "unit": "GB/s", "frac": achieved / peak_bw, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
-                "algorithmic_bytes": alg_bytes, "kernel_ms": dom_ms, "stage_ms": [a1_ms, a2_ms], "factor_ms": f_ms}
+                "algorithmic_bytes": alg_bytes, "kernel_ms": dom_ms, "stage_ms": [a1_ms, a2_ms], "factor_ms": f_ms,
+                "copy_reference": copy_ref}
         cpu = None
         if not args.no_cpu:
             log(f"cpu baseline on {host_threads()} threads ...")

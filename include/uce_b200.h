@@ -57,10 +57,17 @@ const char  *uce_last_error(void);
 int uce_ws_create(int device, int K, int max_rows, uce_ws **out);
 int uce_ws_destroy(uce_ws *ws);
 
-/* Select the apply kernel: 0 = auto (tcgen05 3xTF32 when available), 1 = SIMT fp32,
- * 2 = tcgen05 3xTF32. Returns the previous value. Both are hand-written CUDA; there is no
- * CPU path. */
+/* Select the apply kernel: 0 = auto (the fastest tcgen05 3xTF32 kernel that takes the shape), 1 = SIMT fp32,
+ * 2 = tcgen05, one 128-row tile per CTA (rank pad <= 128), 3 = tcgen05, two co-resident CTAs per SM (rank pad <= 64),
+ * 4 = tcgen05, two row blocks per CTA in one planned wave (rank pad <= 64, <= 96 projections per call).
+ * Returns the previous value. All are hand-written CUDA; there is no CPU path. */
 int uce_ws_set_apply_impl(uce_ws *ws, int impl);
+
+/* Host-only helper (no GPU needed): the row-block plan the two-block apply (impl 4) uses for `n_layers` projections of
+ * d[l] rows (out_features of attn2.to_k / to_v, uce_sd_erase.py:15-22) on a GPU with `sm_count` SMs.  A CTA owns two
+ * blocks of block_rows[l] rows of projection l; first_cta[l] is the index of its first CTA.  Returns the number of CTAs
+ * (> 0) or a negative UCE_E_* code.  UCE_TC3_BLOCK_ROWS in the environment overrides the search (debugging aid). */
+int uce_plan_row_blocks(int sm_count, const int *d, int n_layers, int *block_rows, int *first_cta);
 
 /* Select the factor path: 0 = auto (single-CTA low-latency kernel when n <= 160 rows and the dual system
  * applies, general blocked path otherwise), 1 = always the general blocked path. Returns the previous value. */

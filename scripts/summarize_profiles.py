@@ -63,7 +63,12 @@ launch_table(os.path.join(G, "launches.csv"), os.path.join(P, f"{tag}_solver_lau
              "ncu --metrics gpu__time_duration.sum --clock-control none python bench.py --steps 3 --warmup 3 --no-graph --no-cpu --no-denoise")
 launch_table(os.path.join(G, "launches_unet.csv"), os.path.join(P, f"{tag}_unet_launches.txt"), "one SD-1.4 U-Net call (NB=2, 64x64 latents) kernel launch list",
              "ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off python scripts/unet_profile.py")
-raw_metrics(os.path.join(G, "prof_apply_tc.ncu-rep"), os.path.join(P, f"{tag}_apply_tc_ncu.txt"), "apply_tc_kernel (dominant kernel of the edit solve)", WANT)
+WANT += ["l1tex__m_xbar2l1tex_read_bytes.sum", "l1tex__m_l1tex2xbar_write_bytes.sum", "lts__throughput.avg.pct_of_peak_sustained_elapsed"]
+raw_metrics(os.path.join(G, "prof_apply_tc3.ncu-rep"), os.path.join(P, f"{tag}_apply_tc3_ncu.txt"),
+            "apply_tc3_kernel (the apply of the edit solve: two row blocks per CTA, one planned wave)", WANT)
+raw_metrics(os.path.join(G, "prof_apply_tc2.ncu-rep"), os.path.join(P, f"{tag}_apply_tc2_ncu.txt"),
+            "apply_tc2_kernel (two co-resident CTAs per SM; apply impl 3)", WANT)
+raw_metrics(os.path.join(G, "prof_apply_tc.ncu-rep"), os.path.join(P, f"{tag}_apply_tc_ncu.txt"), "apply_tc_kernel (one 128-row tile per CTA; apply impl 2)", WANT)
 raw_metrics(os.path.join(G, "prof_chol_small.ncu-rep"), os.path.join(P, f"{tag}_chol_small_ncu.txt"), "chol_small_kernel (single-CTA factor)", WANT)
 raw_metrics(os.path.join(G, "prof_unet_gemm_pair.ncu-rep"), os.path.join(P, f"{tag}_unet_gemm_pair_ncu.txt"),
             "unet_gemm_pair_kernel (third pair-GEMM launch of one SD-1.4 U-Net call: 128 CTAs = 64 pairs, 64x64 level, 320 channels)", WANT)

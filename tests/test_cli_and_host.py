@@ -116,3 +116,44 @@ def test_no_gpu_fails_loudly():
     from uce_b200.unet import UNetEngine
     with pytest.raises(RuntimeError):
         UNetEngine(device="cuda:0")
+
+
+def _plan(sm_count, dims):
+    import ctypes as C
+    from uce_b200 import _native
+    n = len(dims)
+    d = (C.c_int * n)(*dims)
+    rows, first = (C.c_int * n)(), (C.c_int * n)()
+    total = _native.lib().uce_plan_row_blocks(sm_count, d, n, rows, first)
+    return total, list(rows), list(first)
+
+
+def test_row_block_plan_covers_every_row_once(monkeypatch):
+    """Host-side tile plan of the two-block tcgen05 apply (apply_tc3.cu): every row of every projection belongs to exactly one
+    CTA, block heights are multiples of 8 in [8,128], and an SD-1.4 edit (uce_sd_erase.py:15-22: 10x320 + 10x640 + 12x1280
+    rows) is ONE balanced wave on a 148-SM B200."""
+    from uce_b200.synthetic import SD14_DIMS
+    monkeypatch.delenv("UCE_TC3_BLOCK_ROWS", raising=False)
+    cases = [(148, list(SD14_DIMS)), (148, [320] * 4), (148, [8]), (148, [1000, 24, 136]), (148, [1280] * 96), (132, list(SD14_DIMS)),
+             (148, [300] * 40)]
+    for sms, dims in cases:
+        total, rows, first = _plan(sms, dims)
+        assert total > 0
+        cta = 0
+        for dl, h, f in zip(dims, rows, first):
+            assert 8 <= h <= 128 and h % 8 == 0, (dims, rows)
+            assert f == cta
+            n_cta = -(-dl // (2 * h))
+            assert (n_cta - 1) * 2 * h < dl <= n_cta * 2 * h      # the last CTA is not empty, all rows covered
+            cta += n_cta
+        assert cta == total
+    total, rows, _ = _plan(148, list(SD14_DIMS))
+    assert total <= 148 and min(rows) >= 64, (total, rows)            # one wave, no short blocks
+    per_cta = [2 * h for h in rows]
+    assert max(per_cta) <= 1.25 * (sum(SD14_DIMS) / total), per_cta  # balanced: no CTA far above the mean row count
+    monkeypatch.setenv("UCE_TC3_BLOCK_ROWS", "40")
+    total, rows, _ = _plan(148, [300] * 40)
+    assert rows == [40] * 40 and total == 40 * 4
+    import ctypes as C
+    from uce_b200 import _native
+    assert _native.lib().uce_plan_row_blocks(148, None, 1, None, None) == _native.UCE_E_ARG

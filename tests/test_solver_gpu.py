@@ -316,7 +316,7 @@ def test_two_cta_tcgen05_apply(n_edit, K, dims, tile_rows, monkeypatch):
 
 @pytest.mark.parametrize("block_rows", [None, 128, 40])
 @pytest.mark.parametrize("n_edit,K,dims", [(2, 768, [320, 320]), (33, 768, [128, 64, 200]), (50, 768, [320, 640, 1280]),
-                                           (64, 256, [128, 384, 8]), (10, 2048, [640, 1280]), (5, 128, [300] * 40)])
+                                           (64, 256, [128, 384, 8]), (10, 2048, [640, 1280]), (5, 128, [300] * 40), (3, 128, [64] * 140)])
 def test_two_block_tcgen05_apply(n_edit, K, dims, block_rows, monkeypatch):
     """apply_tc3.cu (two row blocks per CTA, host tile plan, rank pad <= 64) against the SIMT fp32 apply and the fp64 oracle:
     planned / full / short blocks (UCE_TC3_BLOCK_ROWS), a lone trailing block, several waves, in place."""
@@ -333,7 +333,7 @@ def test_two_block_tcgen05_apply(n_edit, K, dims, block_rows, monkeypatch):
     s = _solver(K, C.shape[0])
     simt = _run(s, C, G, scales, n_edit, 0.5, W, impl=1)
     tc = _run(s, C, G, scales, n_edit, 0.5, W, impl=4)
-    assert s.info()["launches_apply"] == 1
+    assert s.info()["launches_apply"] == -(-len(dims) // 96)          # 96 projections per launch
     exact = O.erase_exact_f64(W[:4], C[:n_edit], G, C[n_edit:], 1.0, 1.0, 0.5)
     for a, b, e in zip(simt, tc, exact):
         assert O.rel_fro(b, e) <= TOL_EXACT, ("tc3 vs exact", O.rel_fro(b, e), O.rel_fro(a, e))

@@ -20,6 +20,7 @@ SIGNATURES = {
     "uce_ws_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
     "uce_ws_destroy": (C.c_int, [C.c_void_p]),
     "uce_ws_set_apply_impl": (C.c_int, [C.c_void_p, C.c_int]),
+    "uce_plan_row_blocks": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "uce_ws_set_factor_impl": (C.c_int, [C.c_void_p, C.c_int]),
     "uce_ws_set_debug": (C.c_int, [C.c_void_p, C.c_int]),
     "uce_ws_set_profile": (C.c_int, [C.c_void_p, C.c_int]),

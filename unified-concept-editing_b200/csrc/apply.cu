@@ -21,7 +21,7 @@ int apply_tc2_tile_rows();
 int apply_tc2_lowrank(uce_ws* ws, const LayerRef* layers_dev, const LayerRef* layers_host, int n_layers, int total_tiles,
                       int tile_rows, cudaStream_t st, int* launches);
 bool apply_tc3_available(const uce_ws* ws, int n_layers);   // apply_tc3.cu
-int apply_tc3_plan(const uce_ws* ws, const int* d, int n_layers, int* tile_rows, int* tile_begin);
+int apply_tc3_plan(int sm_count, const int* d, int n_layers, int* tile_rows, int* tile_begin);
 int apply_tc3_lowrank(uce_ws* ws, const LayerRef* layers_dev, const LayerRef* layers_host, int n_layers, int total_tiles,
                       cudaStream_t st, int* launches);
 
@@ -116,6 +116,23 @@ int apply_dev(uce_ws* ws, const float* const* W_old, float* const* W_new, const 
     int slot_begin = 0;
     const int K = ws->K;
     if (ws->mode == 0) { set_error("uce_apply before uce_factor"); return UCE_E_STATE; }
+    // the two-block tcgen05 apply carries two tensor maps per projection as kernel parameters (96 projections per launch):
+    // longer lists (SDXL: 140 projections) go through it in slices
+    constexpr int TC3_MAX = 96;
+    if (n_layers > TC3_MAX && !ws->dense && ws->rank > 0 && (ws->apply_impl == 0 || ws->apply_impl == 4) && apply_tc3_available(ws, TC3_MAX)) {
+        int total_launches = 0;
+        const bool prof = ws->profile && !no_profile;
+        if (prof) UCE_CUDA(cudaEventRecord(ws->pev[2], st));
+        for (int l0 = 0; l0 < n_layers; l0 += TC3_MAX) {
+            const int rc = apply_dev(ws, W_old + l0, W_new + l0, d + l0, std::min(TC3_MAX, n_layers - l0), st, true);
+            if (rc) return rc;
+            total_launches += ws->launches_apply;
+        }
+        ws->launches_apply = total_launches;
+        ws->pev_mid = 0;
+        if (prof) UCE_CUDA(cudaEventRecord(ws->pev[4], st));
+        return 0;
+    }
     if (n_layers > ws->layers_cap / 4) { set_error("too many layers per call (%d > %d)", n_layers, ws->layers_cap / 4); return UCE_E_STATE; }
     // The layer table is staged in a ring of pinned slots: the async H2D copy below reads the slot when it
     // EXECUTES (also on every replay of a captured graph), so consecutive calls must not share a slot.
@@ -137,7 +154,7 @@ int apply_dev(uce_ws* ws, const float* const* W_old, float* const* W_new, const 
     }
     if (use_tc3) {
         std::vector<int> trows(n_layers), tbeg(n_layers);
-        tiles = apply_tc3_plan(ws, d, n_layers, trows.data(), tbeg.data());
+        tiles = apply_tc3_plan(ws->sm_count, d, n_layers, trows.data(), tbeg.data());
         for (int l = 0; l < n_layers; ++l) hl[l] = LayerRef{W_old[l], W_new[l], d[l], tbeg[l], trows[l]};
     } else {
         for (int l = 0; l < n_layers; ++l) {

@@ -36,13 +36,13 @@ using namespace uce::tca;
 
 constexpr int NBLK = 2;                                 // row blocks per CTA
 constexpr int PW = 4 * NBLK;                            // transform / P-conversion / epilogue warps (4 per block)
-constexpr int THREADS = (PW + 3) * 32;                  // + W TMA warp + E/Qt TMA warp + MMA warp
+constexpr int THREADS = (PW + 2 + NBLK) * 32;           // + W TMA warp + E/Qt TMA warp + one MMA warp per block
 constexpr int NRAW = 5, NSA = 3, NE = 3;
 constexpr int NB = 6;                                   // addend / output box pairs (2 x 16 KB each)
 constexpr int NACC = 4;                                 // accumulator pairs (2 x 32 columns)
 constexpr int NQ = 2;                                   // Qt slots (all hi/lo tiles of one unit, <= 16 KB)
 constexpr int MAX_LAYERS = 96;                          // two tensor maps per projection travel as kernel parameters
-constexpr int WARP_W_TMA = PW, WARP_E_TMA = PW + 1, WARP_MMA = PW + 2;
+constexpr int WARP_W_TMA = PW, WARP_E_TMA = PW + 1, WARP_MMA = PW + 2;      // MMA warps: WARP_MMA + g issues block g
 constexpr uint32_t TMEM_COLS = 512;
 // tensor-memory columns
 __host__ __device__ constexpr uint32_t col_p(int g) { return 64u * g; }                       // phase A accumulator / phase B P_hi
@@ -105,11 +105,11 @@ apply_tc3_kernel(const LayerRef* __restrict__ layers, int n_layers, int K, int R
     const uint32_t bar_p_full = bars + 8u * 22, bar_p_ready = bars + 8u * 23;
     auto bar_q_full    = [&](int t) { return bars + 8u * (24 + t); };          // [24,26) Qt TMA -> MMA (all tiles of a unit)
     auto bar_q_empty   = [&](int t) { return bars + 8u * (26 + t); };          // [26,28)
-    auto bar_acc_full  = [&](int a) { return bars + 8u * (28 + a); };          // [28,32) MMA -> epilogue
-    auto bar_acc_empty = [&](int a) { return bars + 8u * (32 + a); };          // [32,36)
-    auto bar_box_full  = [&](int b) { return bars + 8u * (36 + b); };          // [36,42) addend TMA -> epilogue
-    auto bar_box_ready = [&](int b) { return bars + 8u * (42 + b); };          // [42,48) epilogue -> W TMA warp (boxes hold W_new)
-    const uint32_t tmem_slot = bars + 8u * 48;
+    auto bar_acc_full  = [&](int a, int g) { return bars + 8u * (28 + 2 * a + g); };     // [28,36) MMA warp g -> epilogue group g
+    auto bar_acc_empty = [&](int a, int g) { return bars + 8u * (36 + 2 * a + g); };     // [36,44)
+    auto bar_box_full  = [&](int b) { return bars + 8u * (44 + b); };          // [44,50) addend TMA -> epilogue
+    auto bar_box_ready = [&](int b) { return bars + 8u * (50 + b); };          // [50,56) epilogue -> W TMA warp (boxes hold W_new)
+    const uint32_t tmem_slot = bars + 8u * 56;
 
     const int tile = blockIdx.x;
     const int layer = find_layer(layers, n_layers, tile);
@@ -121,14 +121,20 @@ apply_tc3_kernel(const LayerRef* __restrict__ layers, int n_layers, int K, int R
     const int n_chunks = K / 32;          // phase A k-chunks (32 fp32 = one swizzle atom row) == phase B units of 32 W columns
     const int n_rc = R / 32;              // r atoms
     const uint32_t box_bytes = (uint32_t)h * 128u;
+    // Every CTA streams the SAME E and Qt tiles; started together they would all ask the same few L2 slices for the same
+    // lines at the same time.  CTA i walks the K dimension (phase A chunks, phase B units) starting at a different offset.
+    const int rot = (int)((blockIdx.x * 7u) % (unsigned)n_chunks);
+    auto col_of = [&](int c) { int x = c + rot; if (x >= n_chunks) x -= n_chunks; return x * 32; };
 
     if (threadIdx.x == 0) {
         for (int r = 0; r < NRAW; ++r) { mbar_init(bar_raw_full(r), 1); mbar_init(bar_raw_empty(r), PW); }
-        for (int s = 0; s < NSA; ++s) { mbar_init(bar_a_full(s), PW); mbar_init(bar_a_empty(s), 1); }
-        for (int s = 0; s < NE; ++s) { mbar_init(bar_e_full(s), 1); mbar_init(bar_e_empty(s), 1); }
-        for (int t = 0; t < NQ; ++t) { mbar_init(bar_q_full(t), 1); mbar_init(bar_q_empty(t), 1); }
-        mbar_init(bar_p_full, 1); mbar_init(bar_p_ready, PW);
-        for (int a = 0; a < NACC; ++a) { mbar_init(bar_acc_full(a), 1); mbar_init(bar_acc_empty(a), PW); }
+        // every consumer-release barrier of the MMA side counts BOTH MMA warps (an idle block's warp arrives without MMAs)
+        for (int s = 0; s < NSA; ++s) { mbar_init(bar_a_full(s), PW); mbar_init(bar_a_empty(s), NBLK); }
+        for (int s = 0; s < NE; ++s) { mbar_init(bar_e_full(s), 1); mbar_init(bar_e_empty(s), NBLK); }
+        for (int t = 0; t < NQ; ++t) { mbar_init(bar_q_full(t), 1); mbar_init(bar_q_empty(t), NBLK); }
+        mbar_init(bar_p_full, NBLK); mbar_init(bar_p_ready, PW);
+        for (int a = 0; a < NACC; ++a)
+            for (int g = 0; g < NBLK; ++g) { mbar_init(bar_acc_full(a, g), 1); mbar_init(bar_acc_empty(a, g), 4); }
         for (int b = 0; b < NB; ++b) { mbar_init(bar_box_full(b), 1); mbar_init(bar_box_ready(b), PW); }
         mbar_fence_init();
     }
@@ -157,6 +163,8 @@ apply_tc3_kernel(const LayerRef* __restrict__ layers, int n_layers, int K, int R
         const uint32_t lane_base = tmem_base + ((uint32_t)(32 * wq) << 16);
         const uint32_t row_off = (uint32_t)(trow * 128);
         const uint32_t sw = (uint32_t)(trow & 7);
+        // software pipelined: the tensor-memory stores of chunk c are left in flight while chunk c + 1 is read and split
+        // (two A stages of 2 x 32 KB are written per chunk at 256 B/clk: ~270 cycles that used to sit in every warp's loop)
         for (int c = 0; c < n_chunks; ++c) {
             const int r = c % NRAW, s = c % NSA;
             mbar_wait(bar_raw_full(r), (uint32_t)((c / NRAW) & 1));
@@ -170,18 +178,26 @@ apply_tc3_kernel(const LayerRef* __restrict__ layers, int n_layers, int K, int R
                 tf32_split(v.x, hi[4 * j], lo[4 * j]);         tf32_split(v.y, hi[4 * j + 1], lo[4 * j + 1]);
                 tf32_split(v.z, hi[4 * j + 2], lo[4 * j + 2]); tf32_split(v.w, hi[4 * j + 3], lo[4 * j + 3]);
             }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_raw_empty(r));                     // the raw chunk is in registers
+            if (c > 0) {                                                      // publish the A stage of chunk c - 1
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_a_full((c - 1) % NSA));
+            }
             mbar_wait(bar_a_empty(s), (uint32_t)(((c / NSA) & 1) ^ 1));      // the MMAs that read this A stage have completed
             if (threadIdx.x == 0) tr(1, c, 1);
             fence_after();
             const uint32_t ta = lane_base + col_stage(s, g);
             tmem_st32(ta, hi);
             tmem_st32(ta + 32u, lo);
-            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-            fence_before();
-            __syncwarp();
-            if (lane == 0) { mbar_arrive(bar_a_full(s)); mbar_arrive(bar_raw_empty(r)); }
             if (threadIdx.x == 0) tr(1, c, 2);
         }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_a_full((n_chunks - 1) % NSA));
         // ---- P_g: TMEM -> registers -> hi (in place) | lo (freed A-stage columns): the A operand of phase B ----
         mbar_wait(bar_p_full, 0);
         if (threadIdx.x == 0) tr(6, 0, 0);
@@ -202,13 +218,13 @@ apply_tc3_kernel(const LayerRef* __restrict__ layers, int n_layers, int K, int R
         // ---- epilogue: per unit of 32 W columns, box += accumulator (in place, swizzled smem); the W TMA warp stores the box ----
         for (int u = 0; u < n_chunks; ++u) {
             const int b = u % NB, a = u % NACC;
-            mbar_wait(bar_acc_full(a), (uint32_t)((u / NACC) & 1));
+            mbar_wait(bar_acc_full(a, g), (uint32_t)((u / NACC) & 1));
             fence_after();
             uint32_t v[32];
             tmem_ld32(lane_base + col_acc(a, g), v);
             fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar_acc_empty(a));
+            if (lane == 0) mbar_arrive(bar_acc_empty(a, g));
             mbar_wait(bar_box_full(b), (uint32_t)((u / NB) & 1));
             if (threadIdx.x == 0) tr(5, u, 0);
             if (row_live) {
@@ -240,19 +256,25 @@ apply_tc3_kernel(const LayerRef* __restrict__ layers, int n_layers, int K, int R
             if (elect_one()) {
                 tr(0, c, 0);
                 mbar_arrive_expect_tx(bar_raw_full(r), pair_bytes);
-                for (int g = 0; g < n_act; ++g) tma_load_2d_hint(raw_st(r, g), wm, bar_raw_full(r), c * 32, row0 + g * h, pol_keep);
+                for (int g = 0; g < n_act; ++g) tma_load_2d_hint(raw_st(r, g), wm, bar_raw_full(r), col_of(c), row0 + g * h, pol_keep);
             }
         }
-        // the boxes alias the raw / E rings: every phase-A MMA has completed once P is final, and an MMA on an A stage
-        // completes only after the transform warps have read that raw chunk
-        mbar_wait(bar_p_full, 0);
-        __syncwarp();
+        // Box pair b < NRAW occupies exactly the bytes of raw stage b: it takes the addend of unit b as soon as the transform
+        // warps have released that stage for the last time — the first addends arrive while phase A drains and P is converted.
+        // Box pairs >= NRAW alias the E ring: they wait until every phase-A MMA has completed (P final).
         const uint64_t pol_stream = l2_evict_first();
         const CUtensorMap* om = &wmaps.out[layer];
-        if (elect_one()) {
-            for (int u = 0; u < NB && u < n_chunks; ++u) {
+        for (int u = 0; u < NB && u < n_chunks; ++u) {
+            if (u < NRAW) {
+                const int uses = (n_chunks - u + NRAW - 1) / NRAW;            // chunks that went through raw stage u (>= 1)
+                mbar_wait(bar_raw_empty(u), (uint32_t)((uses - 1) & 1));
+            } else {
+                mbar_wait(bar_p_full, 0);
+            }
+            __syncwarp();
+            if (elect_one()) {
                 mbar_arrive_expect_tx(bar_box_full(u), pair_bytes);
-                for (int g = 0; g < n_act; ++g) tma_load_2d_hint(box_st(u, g), wm, bar_box_full(u), u * 32, row0 + g * h, pol_last_use);
+                for (int g = 0; g < n_act; ++g) tma_load_2d_hint(box_st(u, g), wm, bar_box_full(u), col_of(u), row0 + g * h, pol_last_use);
             }
         }
         __syncwarp();
@@ -264,14 +286,14 @@ apply_tc3_kernel(const LayerRef* __restrict__ layers, int n_layers, int K, int R
             __syncwarp();
             if (elect_one()) {
                 tr(0, u, 1);
-                for (int g = 0; g < n_act; ++g) tma_store_2d(om, box_st(b, g), u * 32, row0 + g * h, pol_stream);
+                for (int g = 0; g < n_act; ++g) tma_store_2d(om, box_st(b, g), col_of(u), row0 + g * h, pol_stream);
                 tma_store_commit();
                 const int nu = u - 1 + NB;
                 if (u >= 1 && nu < n_chunks) {
                     tma_store_wait_read<1>();
                     const int nb = nu % NB;             // == (u - 1) % NB
                     mbar_arrive_expect_tx(bar_box_full(nb), pair_bytes);
-                    for (int g = 0; g < n_act; ++g) tma_load_2d_hint(box_st(nb, g), wm, bar_box_full(nb), nu * 32, row0 + g * h, pol_last_use);
+                    for (int g = 0; g < n_act; ++g) tma_load_2d_hint(box_st(nb, g), wm, bar_box_full(nb), col_of(nu), row0 + g * h, pol_last_use);
                 }
             }
         }
@@ -287,27 +309,34 @@ apply_tc3_kernel(const LayerRef* __restrict__ layers, int n_layers, int K, int R
             if (elect_one()) {
                 tr(2, c, 0);
                 mbar_arrive_expect_tx(bar_e_full(s), e_bytes);
-                tma_load_2d(stage_e_hi(s), &maps.e_hi, bar_e_full(s), c * 32, 0);
-                tma_load_2d(stage_e_lo(s), &maps.e_lo, bar_e_full(s), c * 32, 0);
+                tma_load_2d(stage_e_hi(s), &maps.e_hi, bar_e_full(s), col_of(c), 0);
+                tma_load_2d(stage_e_lo(s), &maps.e_lo, bar_e_full(s), col_of(c), 0);
             }
         }
-        mbar_wait(bar_p_full, 0);                      // the Qt slots alias the E ring
+        // Qt slot 1 lies beyond the E ring (nothing of phase A lives there): unit 0 goes there and is fetched right away;
+        // slot 0 aliases the last E stage and waits until every phase-A MMA has completed.
         const uint32_t q_bytes = (uint32_t)(n_rc * 2) * 4096u;
         for (int u = 0; u < n_chunks; ++u) {
-            const int t = u % NQ;
+            const int t = (u + 1) % NQ;
+            if (u == 1) mbar_wait(bar_p_full, 0);
             mbar_wait(bar_q_empty(t), (uint32_t)(((u / NQ) & 1) ^ 1));
             __syncwarp();
             if (elect_one()) {
                 mbar_arrive_expect_tx(bar_q_full(t), q_bytes);        // ONE barrier for all hi/lo tiles of the unit
                 for (int rc = 0; rc < n_rc; ++rc) {
-                    tma_load_2d(qt_tile(t, 2 * rc), &maps.qt_hi, bar_q_full(t), rc * 32, u * 32);
-                    tma_load_2d(qt_tile(t, 2 * rc + 1), &maps.qt_lo, bar_q_full(t), rc * 32, u * 32);
+                    tma_load_2d(qt_tile(t, 2 * rc), &maps.qt_hi, bar_q_full(t), rc * 32, col_of(u));
+                    tma_load_2d(qt_tile(t, 2 * rc + 1), &maps.qt_lo, bar_q_full(t), rc * 32, col_of(u));
                 }
             }
         }
     } else {
-        // =============================== MMA issuer ===============================
-        // the whole warp runs the loops and the barrier waits (converged); ONE elected lane issues the MMAs and commits
+        // =============================== MMA issuers: warp WARP_MMA + g owns row block g ===============================
+        // Each warp runs its loops and barrier waits converged; ONE elected lane issues its block's MMAs and commits.  Two
+        // issuers because one could not keep the tensor pipe busy: it needs ~400 cycles of barrier round trips between
+        // chunks during which its queue runs dry (profiles/r01_apply_tc3_timeline.txt: 1 300 cycles per chunk for 770 cycles
+        // of MMAs); with two, one block's MMAs execute while the other block's issuer waits.
+        const int g = warp - WARP_MMA;
+        const bool act = g < n_act;
         const uint32_t idesc_a = idesc_tf32(128, R);
         for (int c = 0; c < n_chunks; ++c) {
             const int s = c % NSA, se = c % NE;
@@ -316,9 +345,9 @@ apply_tc3_kernel(const LayerRef* __restrict__ layers, int n_layers, int K, int R
             fence_after();
             __syncwarp();
             if (elect_one()) {
-                tr(3, c, 1);
-                const uint64_t b_hi = umma_desc_sw128(stage_e_hi(se)), b_lo = umma_desc_sw128(stage_e_lo(se));
-                for (int g = 0; g < n_act; ++g) {
+                if (act) {
+                    if (g == 0) tr(3, c, 1);
+                    const uint64_t b_hi = umma_desc_sw128(stage_e_hi(se)), b_lo = umma_desc_sw128(stage_e_lo(se));
                     const uint32_t a_hi = tmem_base + col_stage(s, g), a_lo = a_hi + 32u;
                     const uint32_t d_tmem = tmem_base + col_p(g);
 #pragma unroll
@@ -328,28 +357,32 @@ apply_tc3_kernel(const LayerRef* __restrict__ layers, int n_layers, int K, int R
                         umma_tf32_ts(d_tmem, a_hi + 8u * k, b_lo + adv, idesc_a, 1);
                         umma_tf32_ts(d_tmem, a_lo + 8u * k, b_hi + adv, idesc_a, 1);
                     }
+                    umma_commit(bar_a_empty(s));
+                    umma_commit(bar_e_empty(se));
+                    if (c == n_chunks - 1) umma_commit(bar_p_full);
+                    if (g == 0) tr(3, c, 2);
+                } else {
+                    mbar_arrive(bar_a_empty(s));
+                    mbar_arrive(bar_e_empty(se));
+                    if (c == n_chunks - 1) mbar_arrive(bar_p_full);
                 }
-                umma_commit(bar_a_empty(s));
-                umma_commit(bar_e_empty(se));
-                if (c == n_chunks - 1) umma_commit(bar_p_full);
-                tr(3, c, 2);
             }
         }
         // ---- phase B: D_g[128 rows, 32 cols] = P_hi Qt_hi^T + P_lo Qt_hi^T + P_hi Qt_lo^T, A from tensor memory ----
         mbar_wait(bar_p_ready, 0);
         fence_after();
         const uint32_t idesc_b = idesc_tf32(128, 32);
+        const uint32_t p_hi = tmem_base + col_p(g), p_lo = tmem_base + col_plo(g);
         for (int u = 0; u < n_chunks; ++u) {
-            const int a = u % NACC, t = u % NQ;
-            mbar_wait(bar_acc_empty(a), (uint32_t)(((u / NACC) & 1) ^ 1));
+            const int a = u % NACC, t = (u + 1) % NQ;
+            mbar_wait(bar_acc_empty(a, g), (uint32_t)(((u / NACC) & 1) ^ 1));
             mbar_wait(bar_q_full(t), (uint32_t)((u / NQ) & 1));
             fence_after();
             __syncwarp();
             if (elect_one()) {
-                tr(4, u, 0);
-                for (int g = 0; g < n_act; ++g) {
+                if (act) {
+                    if (g == 0) tr(4, u, 0);
                     const uint32_t d_tmem = tmem_base + col_acc(a, g);
-                    const uint32_t p_hi = tmem_base + col_p(g), p_lo = tmem_base + col_plo(g);
                     for (int rc = 0; rc < n_rc; ++rc) {
                         const uint64_t bq_hi = umma_desc_sw128(qt_tile(t, 2 * rc)), bq_lo = umma_desc_sw128(qt_tile(t, 2 * rc + 1));
 #pragma unroll
@@ -361,10 +394,13 @@ apply_tc3_kernel(const LayerRef* __restrict__ layers, int n_layers, int K, int R
                             umma_tf32_ts(d_tmem, p_hi + col, bq_lo + adv, idesc_b, 1);                  // hi.lo
                         }
                     }
+                    umma_commit(bar_q_empty(t));
+                    umma_commit(bar_acc_full(a, g));
+                    if (g == 0) tr(4, u, 1);
+                } else {
+                    mbar_arrive(bar_q_empty(t));
+                    mbar_arrive(bar_acc_full(a, g));
                 }
-                umma_commit(bar_q_empty(t));
-                umma_commit(bar_acc_full(a));
-                tr(4, u, 1);
             }
         }
     }
@@ -400,10 +436,10 @@ bool apply_tc3_available(const uce_ws* ws, int n_layers) {
 }
 
 // Tile plan: rows per block for every projection (tile_rows[l]; a CTA owns two blocks) and the total number of CTAs.
-// When the whole edit fits one wave of CTAs (one per SM) the block height is the SMALLEST that still fits — the most
-// even spread of rows, hence of TMA bytes, over the SMs — and is then evened out inside each projection; otherwise
+// When the whole edit fits one wave of CTAs (one per SM) the block height is the SMALLEST one >= 64 that still fits — the
+// most even spread of rows, hence of TMA bytes, over the SMs — and is then evened out inside each projection; otherwise
 // blocks are 128 rows.  UCE_TC3_BLOCK_ROWS (multiple of 8 in [8,128]) overrides the search.
-int apply_tc3_plan(const uce_ws* ws, const int* d, int n_layers, int* tile_rows, int* tile_begin) {
+int apply_tc3_plan(int sm_count, const int* d, int n_layers, int* tile_rows, int* tile_begin) {
     auto count = [&](int H) { long t = 0; for (int l = 0; l < n_layers; ++l) t += ceil_div(d[l], 2 * H); return t; };
     int H = 128;
     int forced = 0;
@@ -411,9 +447,12 @@ int apply_tc3_plan(const uce_ws* ws, const int* d, int n_layers, int* tile_rows,
         const int t = atoi(e);
         if (t >= 8 && t <= 128 && t % 8 == 0) { H = t; forced = 1; }
     }
-    const int sms = ws->sm_count > 0 ? ws->sm_count : 148;
+    const int sms = sm_count > 0 ? sm_count : 148;
+    // never below 64 rows per block: every CTA streams all of E and Qt (16 R K bytes, as much as 2 x 43 rows of W traffic at
+    // R = 64) whatever its height; short blocks multiply that stream (measured on the host path, whose launches cover 4
+    // projections: 8-row blocks cost 0.6 ms of the 2.6 ms end-to-end edit through L2 contention with the PCIe copies)
     if (!forced && count(128) <= sms)
-        for (int t = 8; t <= 128; t += 8)
+        for (int t = 64; t <= 128; t += 8)
             if (count(t) <= sms) { H = t; break; }
     int tiles = 0;
     for (int l = 0; l < n_layers; ++l) {

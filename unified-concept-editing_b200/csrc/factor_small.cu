@@ -73,26 +73,18 @@ constexpr int FS_MAX_RHS = 64;
 
 __device__ __forceinline__ int fs_blk(int bi, int bj) { return (bi * (bi + 1) / 2 + bj) * FS_BLK; }
 
-// 1 / sqrt(d) in fp64 without the slow software sqrt/div: fp32 seed + 3 Newton steps (relative error < 1e-15)
+// 1 / sqrt(d) in fp64 without the slow software sqrt/div
 __device__ __forceinline__ double fs_rsqrt(double d) {
-    // fp32 seed (2^-22) + two residual-form Newton steps: 6 dependent fp64 operations (fp64 latency dominates the
-    // 160 sequential pivots of the factorisation), relative error at fp64 round-off
+    // fp32 seed (relative error 2^-22) + ONE third-order (Halley) step: e = 1 - d y0^2, y = y0 + y0 e (1/2 + 3/8 e), error
+    // ~ e^3 = 2^-63.  Four dependent fp64 operations instead of the six of two Newton steps: the reciprocal square root
+    // sits on the critical path of each of the 160 sequential pivots.
     const double y0 = (double)rsqrtf((float)d);
-    double e = fma(-d, y0 * y0, 1.0);
-    double y = fma(0.5 * y0, e, y0);
-    e = fma(-d, y * y, 1.0);
-    return fma(0.5 * y, e, y);
+    const double e = fma(-(d * y0), y0, 1.0);
+    return fma(y0 * e, fma(0.375, e, 0.5), y0);
 }
 
-// Cholesky of one 32 x 32 diagonal block (pitch 33, lower triangle) by ONE warp, register resident and ROLLED:
-// lane = row, and at the top of step j register a[k] holds column j + k of that row — the trailing update writes column
-// j + k into a[k - 1], so the register file shifts left by one column per step and every index stays static.  The body is
-// ~110 instructions executed 32 times: a fully unrolled factorisation (1 600 straight-line instructions) was measured at
-// 61 k cycles on its first call of a launch — this kernel is one CTA that runs once, its code arrives through a cold
-// instruction cache — and 12.6 k afterwards; the left-looking shared-memory version before it took 26 k per block.
-// Columns j + k >= 32 do not exist: those lanes / registers hold finite garbage that never reaches a stored value.
-// One pivot step with the trailing update limited to KM columns (straight-line: the shuffles of all columns are issued
-// ahead of the FMAs; a per-column early exit was measured 1.8x SLOWER — the branches serialise shuffle and FMA latencies).
+// One pivot step with the trailing update limited to KM columns (straight-line: the column loads are issued ahead of the
+// FMAs; a per-column early exit was measured 1.8x SLOWER — the branches serialise load and FMA latencies).
 template <int KM>
 __device__ __forceinline__ void fs_potrf_step(double (&a)[FS_NB], double* __restrict__ D, double* __restrict__ invd_blk, int lane, int j, bool& bad) {
     double d = __shfl_sync(0xffffffffu, a[0], j);
@@ -101,11 +93,16 @@ __device__ __forceinline__ void fs_potrf_step(double (&a)[FS_NB], double* __rest
     const double l = (lane == j) ? d * y : a[0] * y;      // L[lane][j] for lanes >= j
     if (lane >= j) D[lane * (FS_NB + 1) + j] = l;
     if (lane == j) invd_blk[j] = y;
+    __syncwarp();
+    // L[j + k][j] was just written to shared memory by lane j + k: ONE broadcast 64-bit load per column instead of the two
+    // 32-bit shuffles a double costs (rows beyond 31 read neighbouring shared memory: finite garbage for columns that do not exist)
+    const double* Lj = D + j * (FS_NB + 1) + j;
 #pragma unroll
     for (int k = 1; k <= KM; ++k) {                       // A[lane][j + k] -= L[lane][j] L[j + k][j]   (k = 1 first: the next pivot)
-        const double lk = __shfl_sync(0xffffffffu, l, (j + k) & 31);
+        const double lk = Lj[k * (FS_NB + 1)];
         a[k - 1] = fma(-l, lk, a[k]);
     }
+    __syncwarp();
 }
 __device__ __noinline__ void fs_potrf_warp(double* __restrict__ D, double* __restrict__ invd_blk, int lane, int* flag, int kb) {
     double a[FS_NB];
@@ -288,33 +285,30 @@ chol_small_kernel(double* __restrict__ Hg, int n, int n_pad, const double* __res
     //      was bound by shared-memory wavefronts, 6 per 4 FMAs.)  Warp = one row octet: all block rows of an update step
     //      are covered in ONE pass. ----
     const bool on0 = lane < n_edit, on1 = lane + 32 < n_edit;
+    const int sj = tid & 63, q4 = tid >> 6;           // triangular multiplies: 8 row quads x 64 right-hand-side slots
     // forward  L Y = rhs  (block rows above the first edit row stay zero)
     for (int kb = n_pres / FS_NB; kb < nblk; ++kb) {
         const double* D = SB + fs_blk(kb, kb);
         const int o = kb * FS_NB;
-        double out[8][2];
-        if (warp < 4) {                               // Y_k = L_kk^-1 X_k : Linv[rr][c] (c < rr) is stored at D[c][rr]
-#pragma unroll
-            for (int i = 0; i < 8; ++i) out[i][0] = out[i][1] = 0.0;
+        // (i) Y_k = L_kk^-1 X_k on ALL warps: thread = (row quad q4, right-hand side sj); Linv[rr][c] (c < rr) is stored at D[c][rr].
+        //     (With 8 x 2 tiles only four warps had work here and the step ran at the latency of one warp per scheduler.)
+        double out[4] = {0.0, 0.0, 0.0, 0.0};
+        if (sj < n_edit) {
 #pragma unroll 4
             for (int c = 0; c < FS_NB; ++c) {
-                const double x0 = on0 ? XS[(o + c) * xl + lane] : 0.0, x1 = on1 ? XS[(o + c) * xl + lane + 32] : 0.0;
+                const double x = XS[(o + c) * xl + sj];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int rr = 8 * warp + i;
+                for (int i = 0; i < 4; ++i) {
+                    const int rr = 4 * q4 + i;
                     const double raw = D[c * P + rr];
-                    const double coef = (c < rr) ? raw : ((c == rr) ? invd[o + rr] : 0.0);
-                    out[i][0] = fma(coef, x0, out[i][0]); out[i][1] = fma(coef, x1, out[i][1]);
+                    out[i] = fma((c < rr) ? raw : ((c == rr) ? invd[o + rr] : 0.0), x, out[i]);
                 }
             }
         }
         __syncthreads();
-        if (warp < 4) {
+        if (sj < n_edit) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                if (on0) XS[(o + 8 * warp + i) * xl + lane] = out[i][0];
-                if (on1) XS[(o + 8 * warp + i) * xl + lane + 32] = out[i][1];
-            }
+            for (int i = 0; i < 4; ++i) XS[(o + 4 * q4 + i) * xl + sj] = out[i];
         }
         __syncthreads();
         for (int r = o + FS_NB + 8 * warp; r < n_pad; r += 8 * NW) {     // X_i -= L_ik Y_k for the block rows below
@@ -344,29 +338,24 @@ chol_small_kernel(double* __restrict__ Hg, int n, int n_pad, const double* __res
     for (int kb = nblk - 1; kb >= 0; --kb) {
         const double* D = SB + fs_blk(kb, kb);
         const int o = kb * FS_NB;
-        double out[8][2];
-        if (warp < 4) {                               // Z_k = L_kk^-T Y_k : Linv[c][rr] (c > rr) is stored at D[rr][c]
-#pragma unroll
-            for (int i = 0; i < 8; ++i) out[i][0] = out[i][1] = 0.0;
+        // (i) Z_k = L_kk^-T Y_k on all warps: Linv[c][rr] (c > rr) is stored at D[rr][c]
+        double out[4] = {0.0, 0.0, 0.0, 0.0};
+        if (sj < n_edit) {
 #pragma unroll 4
             for (int c = 0; c < FS_NB; ++c) {
-                const double x0 = on0 ? XS[(o + c) * xl + lane] : 0.0, x1 = on1 ? XS[(o + c) * xl + lane + 32] : 0.0;
+                const double x = XS[(o + c) * xl + sj];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int rr = 8 * warp + i;
+                for (int i = 0; i < 4; ++i) {
+                    const int rr = 4 * q4 + i;
                     const double raw = D[rr * P + c];
-                    const double coef = (c > rr) ? raw : ((c == rr) ? invd[o + rr] : 0.0);
-                    out[i][0] = fma(coef, x0, out[i][0]); out[i][1] = fma(coef, x1, out[i][1]);
+                    out[i] = fma((c > rr) ? raw : ((c == rr) ? invd[o + rr] : 0.0), x, out[i]);
                 }
             }
         }
         __syncthreads();
-        if (warp < 4) {
+        if (sj < n_edit) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                if (on0) XS[(o + 8 * warp + i) * xl + lane] = out[i][0];
-                if (on1) XS[(o + 8 * warp + i) * xl + lane + 32] = out[i][1];
-            }
+            for (int i = 0; i < 4; ++i) XS[(o + 4 * q4 + i) * xl + sj] = out[i];
         }
         __syncthreads();
         for (int r = 8 * warp; r < o; r += 8 * NW) {  // X_i -= L_ki^T Z_k for the block rows above
@@ -480,7 +469,8 @@ int factor_small(uce_ws* ws, const float* C, const float* G, int n, int n_pres, 
         if (!ws->Hcopy) UCE_CUDA(cudaMalloc(&ws->Hcopy, (size_t)ws->sys_max * ws->sys_max * sizeof(double)));
         UCE_CUDA(cudaMemcpyAsync(ws->Hcopy, ws->H, (size_t)n_pad * n_pad * sizeof(double), cudaMemcpyDeviceToDevice, st));
     }
-    const size_t smem_c = ((size_t)(nt * (nt + 1) / 2) * FS_BLK + (size_t)n_pad * (n_edit | 1) + n_pad) * sizeof(double);
+    // + 8 rows of slack: the last pivots of a diagonal block read L[j + k][j] for rows up to 38 (columns that do not exist, results unused)
+    const size_t smem_c = ((size_t)(nt * (nt + 1) / 2) * FS_BLK + (size_t)n_pad * (n_edit | 1) + n_pad + 8 * (FS_NB + 1)) * sizeof(double);
     static size_t conf_c = 0;
     if (conf_c < smem_c) {
         UCE_CUDA(cudaFuncSetAttribute(chol_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));

@@ -15,6 +15,7 @@ void set_error(const char* fmt, ...) {
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
 }
+int apply_tc3_plan(int sm_count, const int* d, int n_layers, int* tile_rows, int* tile_begin);   // apply_tc3.cu
 }  // namespace uce
 using namespace uce;
 
@@ -102,6 +103,13 @@ int uce_ws_set_apply_impl(uce_ws* ws, int impl) {
     int prev = ws->apply_impl;
     ws->apply_impl = impl;
     return prev;
+}
+
+// Host-only: the row-block plan of the two-block tcgen05 apply for `n_layers` projections of d[l] rows on `sm_count` SMs.
+int uce_plan_row_blocks(int sm_count, const int* d, int n_layers, int* block_rows, int* first_cta) {
+    if (!d || !block_rows || !first_cta || n_layers <= 0) { set_error("uce_plan_row_blocks: bad argument"); return UCE_E_ARG; }
+    for (int l = 0; l < n_layers; ++l) if (d[l] <= 0) { set_error("uce_plan_row_blocks: d[%d] <= 0", l); return UCE_E_ARG; }
+    return apply_tc3_plan(sm_count, d, n_layers, block_rows, first_cta);
 }
 
 int uce_ws_set_factor_impl(uce_ws* ws, int impl) {

@@ -74,3 +74,33 @@ raw_metrics(os.path.join(G, "prof_unet_gemm_pair.ncu-rep"), os.path.join(P, f"{t
             "unet_gemm_pair_kernel (third pair-GEMM launch of one SD-1.4 U-Net call: 128 CTAs = 64 pairs, 64x64 level, 320 channels)", WANT)
 raw_metrics(os.path.join(G, "prof_unet_attn.ncu-rep"), os.path.join(P, f"{tag}_unet_attn_ncu.txt"),
             "unet_attn_kernel (first launch of one SD-1.4 U-Net call: self-attention over 4096 tokens, 8 heads, head dim 40 padded to 64)", WANT)
+
+
+def copy_with_header(src, out, header):
+    if not os.path.isfile(src):
+        return
+    with open(out, "w") as f:
+        f.write(header)
+        f.write(open(src).read())
+    print("wrote", out)
+
+
+copy_with_header(os.path.join(G, "tc_trace.txt"), os.path.join(P, f"{tag}_apply_tc3_timeline.txt"),
+                 "# apply_tc3_kernel — per-role timeline of CTA 0 (clock64 cycles from the CTA's first event), cfg2 workload, warm run\n"
+                 "# produced by UCE_TC_TRACE=<file> (scripts/trace_apply.py); columns: role, index, then up to three timestamps\n"
+                 "#   w_tma k      : TMA pair for raw W chunk k issued | (phase B) stores of unit k issued\n"
+                 "#   transform k  : raw chunk k landed | A stage free | tcgen05.st issued\n"
+                 "#   e_tma k      : TMA for E tile k issued\n"
+                 "#   mma_a k      : - | barriers passed (block 0 issuer) | 12 tcgen05.mma + commits issued      (phase A, 24 chunks)\n"
+                 "#   mma_b u      : barriers passed | 24 tcgen05.mma + commits issued                        (phase B, 24 units of 32 W columns)\n"
+                 "#   epilogue u   : addend box landed | box += accumulator done, handed to the TMA warp\n"
+                 "#   pconv        : P final | P_hi / P_lo written back to tensor memory\n")
+copy_with_header(os.path.join(G, "chol_trace.txt"), os.path.join(P, f"{tag}_chol_small_phases.txt"),
+                 "# chol_small_kernel — phase boundaries of the single factor CTA (UCE_CHOL_TRACE), cfg2 workload (n = 150 -> 160, 50 right-hand sides)\n"
+                 "# columns: index, cycles since kernel start, cycles since the previous boundary\n"
+                 "# 1 load | per block kb = 0..4: potrf (one warp), inverse of the diagonal block, panel, trailing update | 21 forward | 22 backward | 23 write Z\n")
+copy_with_header(os.path.join(G, "fp64_probe.txt"), os.path.join(P, f"{tag}_fp64_probe.txt"),
+                 "# scripts/fp64_probe.cu on one SM of a B200: plain DFMA and tensor-core DMMA.8x8x4 both peak at 64 fp64 FMA/clk/SM\n"
+                 "# (so the fp64 tensor path offers nothing to the single-CTA factor; its GEMM-like phases are bound by shared-memory wavefronts and latency)\n")
+copy_with_header(os.path.join(G, "copy_ceiling.txt"), os.path.join(P, f"{tag}_copy_reference.txt"),
+                 "# scripts/copy_ceiling.py: flat device-to-device copy of the cfg2 footprint, rotating buffers, CUDA events (context for roofline.frac)\n")

@@ -31,6 +31,13 @@ sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 
 _T0 = time.time()
+# stdout carries exactly ONE JSON line: anything a library prints on fd 1 (NCCL's version banner, for one) goes to stderr instead
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line: dict):
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
 
 
 def log(msg):
@@ -140,7 +147,7 @@ def run_reference(args, rank, world):
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": host_threads(), "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------ ours
@@ -346,7 +353,7 @@ def run_ours(args, rank, world, local_rank):
             line["sharded"] = sharded
         if denoise:
             line["denoise"] = denoise
-        print(json.dumps(line), flush=True)
+        emit(line)
     solver.close()
 
 

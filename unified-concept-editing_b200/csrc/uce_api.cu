@@ -273,10 +273,13 @@ int uce_edit_host_f32(uce_ws* ws, const float* C, const float* G, const float* s
     std::vector<const float*> po(n_layers); std::vector<float*> pn(n_layers);
     { size_t off = 0; for (int l = 0; l < n_layers; ++l) { po[l] = ws->hostpath_W + off; pn[l] = ws->hostpath_W + off; off += (size_t)d[l] * K; } }
     int launches = 0;
+    // every upload is enqueued first: the H2D stream never waits for the host to finish encoding a group's launch
     for (int g = 0; g < ng; ++g) {
         for (int l = gbeg[g]; l < gbeg[g + 1]; ++l)
             UCE_CUDA(cudaMemcpyAsync(pn[l], W_old[l], (size_t)d[l] * K * sizeof(float), cudaMemcpyHostToDevice, ws->s_h2d));
         UCE_CUDA(cudaEventRecord(ws->ev_h2d[g], ws->s_h2d));
+    }
+    for (int g = 0; g < ng; ++g) {
         UCE_CUDA(cudaStreamWaitEvent(ws->s_compute, ws->ev_h2d[g], 0));
         rc = apply_dev(ws, po.data() + gbeg[g], pn.data() + gbeg[g], d + gbeg[g], gbeg[g + 1] - gbeg[g], ws->s_compute, true);
         if (rc) { cudaDeviceSynchronize(); return rc; }

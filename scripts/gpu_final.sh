@@ -21,10 +21,12 @@ cat gpurun_out/bench_ref.json
 echo "== probes" | tee -a $S
 timeout 120 ./scripts/fp64_probe.bin > gpurun_out/fp64_probe.txt 2>&1; echo "rc=$?" | tee -a $S
 timeout 120 python scripts/copy_ceiling.py > gpurun_out/copy_ceiling.txt 2>&1; echo "rc=$?" | tee -a $S
+timeout 120 python scripts/pcie_floor.py > gpurun_out/pcie_floor.txt 2>&1; echo "rc=$?" | tee -a $S
+timeout 200 python scripts/e2e_probe.py > gpurun_out/e2e_probe.txt 2>&1; echo "rc=$?" | tee -a $S
 timeout 300 python scripts/trace_apply.py > gpurun_out/trace.log 2>&1; echo "rc=$?" | tee -a $S
 echo "== ncu launches (solver)" | tee -a $S
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 100 --csv --log-file gpurun_out/launches.csv \
-    python bench.py --steps 3 --warmup 3 --no-graph --no-cpu --no-denoise > gpurun_out/ncu_bench.log 2>&1; echo "rc=$?" | tee -a $S
+    python bench.py --steps 3 --warmup 3 --no-graph --no-cpu --no-denoise --no-e2e > gpurun_out/ncu_bench.log 2>&1; echo "rc=$?" | tee -a $S
 echo "== ncu full apply kernels / chol_small" | tee -a $S
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:apply_tc3_kernel -s 3 -c 1 -f -o gpurun_out/prof_apply_tc3 \
     python bench.py --steps 3 --warmup 3 --no-graph --no-cpu --no-denoise > gpurun_out/ncu_full.log 2>&1; echo "rc=$?" | tee -a $S

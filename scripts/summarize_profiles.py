@@ -60,7 +60,7 @@ WANT = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "la
         "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum"]
 
 launch_table(os.path.join(G, "launches.csv"), os.path.join(P, f"{tag}_solver_launches.txt"), "edit-solve (cfg2) kernel launch list",
-             "ncu --metrics gpu__time_duration.sum --clock-control none python bench.py --steps 3 --warmup 3 --no-graph --no-cpu --no-denoise")
+             "ncu --metrics gpu__time_duration.sum --clock-control none python bench.py --steps 3 --warmup 3 --no-graph --no-cpu --no-denoise --no-e2e")
 launch_table(os.path.join(G, "launches_unet.csv"), os.path.join(P, f"{tag}_unet_launches.txt"), "one SD-1.4 U-Net call (NB=2, 64x64 latents) kernel launch list",
              "ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off python scripts/unet_profile.py")
 WANT += ["l1tex__m_xbar2l1tex_read_bytes.sum", "l1tex__m_l1tex2xbar_write_bytes.sum", "lts__throughput.avg.pct_of_peak_sustained_elapsed"]
@@ -104,3 +104,12 @@ copy_with_header(os.path.join(G, "fp64_probe.txt"), os.path.join(P, f"{tag}_fp64
                  "# (so the fp64 tensor path offers nothing to the single-CTA factor; its GEMM-like phases are bound by shared-memory wavefronts and latency)\n")
 copy_with_header(os.path.join(G, "copy_ceiling.txt"), os.path.join(P, f"{tag}_copy_reference.txt"),
                  "# scripts/copy_ceiling.py: flat device-to-device copy of the cfg2 footprint, rotating buffers, CUDA events (context for roofline.frac)\n")
+if os.path.isfile(os.path.join(G, "pcie_floor.txt")):
+    with open(os.path.join(P, f"{tag}_e2e_floor.txt"), "w") as f:
+        f.write("# Context for the end-to-end (host-buffer) number: what the PCIe link of the GPU box gives for the cfg2 footprint\n"
+                "# (scripts/pcie_floor.py), and uce_edit_host_f32 itself (scripts/e2e_probe.py).  The call takes one pinned host tensor per\n"
+                "# projection, so 32 uploads and 32 downloads are the granularity it has to work with.\n")
+        f.write(open(os.path.join(G, "pcie_floor.txt")).read())
+        if os.path.isfile(os.path.join(G, "e2e_probe.txt")):
+            f.write(open(os.path.join(G, "e2e_probe.txt")).read())
+    print("wrote", os.path.join(P, f"{tag}_e2e_floor.txt"))

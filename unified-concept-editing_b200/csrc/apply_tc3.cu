@@ -79,7 +79,7 @@ __device__ __forceinline__ int find_layer(const LayerRef* layers, int n_layers, 
 }
 
 __global__ void __launch_bounds__(THREADS, 1)
-apply_tc3_kernel(const LayerRef* __restrict__ layers, int n_layers, int K, int R,
+apply_tc3_kernel(const LayerRef* __restrict__ layers, int n_layers, int K, int R, int addend_ldgsts,
                  const __grid_constant__ Maps maps, const __grid_constant__ WMaps wmaps, long long* __restrict__ trace) {
     // optional timeline of CTA 0 (UCE_TC_TRACE=<file>): trace[(role * 64 + index) * 4 + event] = clock64()
     auto tr = [&](int role, int idx, int ev) {
@@ -135,7 +135,8 @@ apply_tc3_kernel(const LayerRef* __restrict__ layers, int n_layers, int K, int R
         mbar_init(bar_p_full, NBLK); mbar_init(bar_p_ready, PW);
         for (int a = 0; a < NACC; ++a)
             for (int g = 0; g < NBLK; ++g) { mbar_init(bar_acc_full(a, g), 1); mbar_init(bar_acc_empty(a, g), 4); }
-        for (int b = 0; b < NB; ++b) { mbar_init(bar_box_full(b), 1); mbar_init(bar_box_ready(b), PW); }
+        // addend boxes: one expect_tx arrival (TMA) or the 32 cp.async completion arrivals of the W TMA warp's lanes
+        for (int b = 0; b < NB; ++b) { mbar_init(bar_box_full(b), addend_ldgsts ? 32 : 1); mbar_init(bar_box_ready(b), PW); }
         mbar_fence_init();
     }
     if (warp == WARP_MMA) tmem_alloc(tmem_slot, TMEM_COLS);      // all of the SM's tensor memory: one CTA per SM
@@ -264,6 +265,30 @@ apply_tc3_kernel(const LayerRef* __restrict__ layers, int n_layers, int K, int R
         // Box pairs >= NRAW alias the E ring: they wait until every phase-A MMA has completed (P final).
         const uint64_t pol_stream = l2_evict_first();
         const CUtensorMap* om = &wmaps.out[layer];
+        // The addend of unit `unit` into box pair `bx`.  Two routes: TMA (one elected lane), or — addend_ldgsts — 16-byte
+        // cp.async copies issued by all 32 lanes straight into the swizzled slots, completion counted on the same mbarrier:
+        // that traffic then goes through the LSU / L1 path instead of the SM's TMA unit, which is what bounds this kernel.
+        auto load_box = [&](int unit, int bx) {
+            if (!addend_ldgsts) {
+                if (elect_one()) {
+                    mbar_arrive_expect_tx(bar_box_full(bx), pair_bytes);
+                    for (int g = 0; g < n_act; ++g) tma_load_2d_hint(box_st(bx, g), wm, bar_box_full(bx), col_of(unit), row0 + g * h, pol_last_use);
+                }
+            } else {
+                const int col = col_of(unit);
+                for (int g = 0; g < n_act; ++g) {
+                    const int rows = g ? rows_valid1 : rows_valid0;
+                    const float* src0 = Lr.w_old + (size_t)(row0 + g * h) * K + col;
+                    const uint32_t dst0 = box_st(bx, g);
+                    for (int idx = lane; idx < rows * 8; idx += 32) {            // 8 lanes = the 128 bytes of one row: coalesced
+                        const int row = idx >> 3, j = idx & 7;
+                        cp_async_16(dst0 + (uint32_t)(row * 128 + ((j ^ (row & 7)) << 4)), src0 + (size_t)row * K + 4 * j);
+                    }
+                }
+                cp_async_mbar_arrive(bar_box_full(bx));
+            }
+            __syncwarp();
+        };
         for (int u = 0; u < NB && u < n_chunks; ++u) {
             if (u < NRAW) {
                 const int uses = (n_chunks - u + NRAW - 1) / NRAW;            // chunks that went through raw stage u (>= 1)
@@ -272,10 +297,7 @@ apply_tc3_kernel(const LayerRef* __restrict__ layers, int n_layers, int K, int R
                 mbar_wait(bar_p_full, 0);
             }
             __syncwarp();
-            if (elect_one()) {
-                mbar_arrive_expect_tx(bar_box_full(u), pair_bytes);
-                for (int g = 0; g < n_act; ++g) tma_load_2d_hint(box_st(u, g), wm, bar_box_full(u), col_of(u), row0 + g * h, pol_last_use);
-            }
+            load_box(u, u);
         }
         __syncwarp();
         // unit u: W_new is complete -> TMA stores; once the PREVIOUS unit's stores have been read out of shared memory its
@@ -284,18 +306,16 @@ apply_tc3_kernel(const LayerRef* __restrict__ layers, int n_layers, int K, int R
             const int b = u % NB;
             mbar_wait(bar_box_ready(b), (uint32_t)((u / NB) & 1));
             __syncwarp();
+            const int nu = u - 1 + NB;
+            const bool reload = u >= 1 && nu < n_chunks;
             if (elect_one()) {
                 tr(0, u, 1);
                 for (int g = 0; g < n_act; ++g) tma_store_2d(om, box_st(b, g), col_of(u), row0 + g * h, pol_stream);
                 tma_store_commit();
-                const int nu = u - 1 + NB;
-                if (u >= 1 && nu < n_chunks) {
-                    tma_store_wait_read<1>();
-                    const int nb = nu % NB;             // == (u - 1) % NB
-                    mbar_arrive_expect_tx(bar_box_full(nb), pair_bytes);
-                    for (int g = 0; g < n_act; ++g) tma_load_2d_hint(box_st(nb, g), wm, bar_box_full(nb), col_of(nu), row0 + g * h, pol_last_use);
-                }
+                if (reload) tma_store_wait_read<1>();   // the previous unit's boxes have been read out
             }
+            __syncwarp();
+            if (reload) load_box(nu, nu % NB);          // nu % NB == (u - 1) % NB
         }
         __syncwarp();
         if (elect_one()) tma_store_wait_read<0>();     // shared memory must outlive the last store's read
@@ -494,7 +514,9 @@ int apply_tc3_lowrank(uce_ws* ws, const LayerRef* layers_dev, const LayerRef* la
     long long* trace = nullptr;
     const char* trace_path = getenv("UCE_TC_TRACE");
     if (trace_path) { UCE_CUDA(cudaMalloc(&trace, 7 * 64 * 4 * sizeof(long long))); UCE_CUDA(cudaMemsetAsync(trace, 0, 7 * 64 * 4 * sizeof(long long), st)); }
-    apply_tc3_kernel<<<total_tiles, THREADS, smem, st>>>(layers_dev, n_layers, K, R, maps, wmaps, trace);
+    const char* am = getenv("UCE_TC3_ADDEND");          // "tma" (default) or "ldgsts": route of the phase-B addend (see load_box)
+    const int addend_ldgsts = (am && am[0] == 'l') ? 1 : 0;
+    apply_tc3_kernel<<<total_tiles, THREADS, smem, st>>>(layers_dev, n_layers, K, R, addend_ldgsts, maps, wmaps, trace);
     UCE_LAUNCH_CHECK();
     *launches += 1;
     if (trace) {   // debugging aid: dump the timeline of CTA 0 (synchronises)

@@ -121,6 +121,17 @@ __device__ __noinline__ void fs_potrf_warp(double* __restrict__ D, double* __res
     if (bad && lane == 0) atomicCAS(flag, 0, 1 + kb);
 }
 
+// Dense copy of the inverse of one factored diagonal block:  TS[c][r] = (L^-1)[r][c] — the strict upper triangle of D as the
+// block inverse left it, 1 / L_cc on the diagonal, explicit zeros below.  The panel and the triangular multiplies of the
+// substitutions then run plain dense inner loops: with the triangle applied as a per-element select those loops were bound by
+// instruction issue (two selects and a compare per 64-bit coefficient: 5.5 k cycles per 32 x 32 x 64 multiply, measured).
+__device__ __forceinline__ void fs_build_ts(double* __restrict__ TS, const double* __restrict__ D, const double* __restrict__ invd_blk, int tid) {
+    for (int idx = tid; idx < FS_NB * FS_NB; idx += FS_T) {
+        const int c = idx >> 5, r = idx & 31;
+        TS[c * (FS_NB + 1) + r] = (c < r) ? D[c * (FS_NB + 1) + r] : ((c == r) ? invd_blk[c] : 0.0);
+    }
+}
+
 __global__ void __launch_bounds__(FS_T, 1)
 chol_small_kernel(double* __restrict__ Hg, int n, int n_pad, const double* __restrict__ dadd, int n_pres, int n_edit,
                   double* __restrict__ Z, int ldz, int write_back, int* flag, long long* __restrict__ trace) {
@@ -133,6 +144,7 @@ chol_small_kernel(double* __restrict__ Hg, int n, int n_pad, const double* __res
     double* XS = SB + (nblk * (nblk + 1) / 2) * FS_BLK;
     const int xl = n_edit | 1;
     double* invd = XS + n_pad * xl;               // [n_pad]
+    double* TS = invd + n_pad;                    // [32][33] dense copy of one block's L^-1 (see fs_build_ts)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int NW = FS_T / 32;
     constexpr int P = FS_NB + 1;                  // block pitch
@@ -169,13 +181,14 @@ chol_small_kernel(double* __restrict__ Hg, int n, int n_pad, const double* __res
     __syncthreads();
     tr();   // 1: loaded
 
+    // (a) Cholesky of a diagonal block by one warp (see fs_potrf_warp).  Block 0 here; block kb + 1 is factored by warp 0 WHILE
+    //     the other 15 warps finish the trailing update of step kb (lookahead, step (d) below).
+    if (warp == 0) fs_potrf_warp(SB + fs_blk(0, 0), invd, lane, flag, 0);
+    __syncthreads();
+    tr();   // diag block 0 factored
     for (int kb = 0; kb < nblk; ++kb) {
         double* D = SB + fs_blk(kb, kb);
         const int o = kb * FS_NB;
-        // (a) Cholesky of the diagonal block by one warp (see fs_potrf_warp)
-        if (warp == 0) fs_potrf_warp(D, invd + o, lane, flag, kb);
-        __syncthreads();
-        tr();   // diag block factored
         // (b) inverse of L_kk by column sweeps (lane = row): x_j = (delta_jc - acc_j) / L_jj.  A warp carries its two
         //     columns (c, c + 16) through ONE sweep: the second chain is identically zero until j reaches c + 16.
         {
@@ -200,7 +213,9 @@ chol_small_kernel(double* __restrict__ Hg, int n, int n_pad, const double* __res
         if (mb > 0) {
             // (c) panel  L_ik = H_ik L_kk^-T  for the mb blocks below, in place (staged through registers).
             //     Task = 4 rows x 1 column, lanes = the 32 columns: the H rows are warp broadcasts, the L^-1 coefficients
-            //     consecutive doubles; fixed trip count with the triangle applied as a select, so the loads batch.
+            //     consecutive doubles of the dense copy TS (fixed trip count, no per-element select: see fs_build_ts).
+            fs_build_ts(TS, D, invd + o, tid);
+            __syncthreads();
             double out[2][4];
 #pragma unroll
             for (int it = 0; it < 2; ++it) {
@@ -210,11 +225,9 @@ chol_small_kernel(double* __restrict__ Hg, int n, int n_pad, const double* __res
                 if (idx < mb * 256) {
                     const int c = idx & 31, rq = idx >> 5;
                     const double* A = SB + fs_blk(kb + 1 + (rq >> 3), kb) + (rq & 7) * 4 * P;
-                    const double dcc = invd[o + c];
 #pragma unroll 8
                     for (int j = 0; j < FS_NB; ++j) {
-                        const double raw = D[j * P + c];                                   // Linv[c][j] for j < c
-                        const double coef = (j < c) ? raw : ((j == c) ? dcc : 0.0);
+                        const double coef = TS[j * P + c];                                 // (L^-1)[c][j], zero for j > c
 #pragma unroll
                         for (int i = 0; i < 4; ++i) out[it][i] = fma(A[i * P + j], coef, out[it][i]);
                     }
@@ -233,17 +246,18 @@ chol_small_kernel(double* __restrict__ Hg, int n, int n_pad, const double* __res
             }
             __syncthreads();
             tr();   // panel done
-            // (d) trailing update of the lower block triangle:  H_ij -= L_ik L_jk^T
-            //     (a lookahead variant — warp 0 factoring the next diagonal block meanwhile — was measured and was slower:
-            //      a single warp of fp64 work is latency-bound either way)
-            //     4 x 4 register tiles: 8 shared-memory loads per 16 fp64 FMAs (the update is smem-bandwidth bound otherwise)
+            // (d) trailing update of the lower block triangle:  H_ij -= L_ik L_jk^T, 4 x 4 register tiles (8 shared-memory loads
+            //     per 16 fp64 FMAs).  With LOOKAHEAD: first only the next diagonal block (64 tile tasks), then warp 0 factors it
+            //     — register resident, it hardly touches shared memory — while warps 1..15 update the other blocks.  (A
+            //     lookahead around the earlier shared-memory potrf had measured slower; this one hides 12 k of the 12-17 k
+            //     cycles of every step but the last.)
             const int npairs = mb * (mb + 1) / 2;
-            for (int idx = tid; idx < npairs * 64; idx += FS_T) {
+            auto trailing_task = [&](int idx) {
                 int pr = idx >> 6, ti = 0;
                 while ((ti + 1) * (ti + 2) / 2 <= pr) ++ti;
                 const int tj = pr - ti * (ti + 1) / 2;
                 const int r0 = ((idx >> 3) & 7) * 4, c0 = (idx & 7) * 4;
-                if (ti == tj && c0 > r0 + 3) continue;
+                if (ti == tj && c0 > r0 + 3) return;
                 const double* A = SB + fs_blk(kb + 1 + ti, kb) + r0 * P;
                 const double* B = SB + fs_blk(kb + 1 + tj, kb) + c0 * P;
                 double acc[4][4];
@@ -267,6 +281,14 @@ chol_small_kernel(double* __restrict__ Hg, int n, int n_pad, const double* __res
 #pragma unroll
                     for (int j2 = 0; j2 < 4; ++j2)
                         if (ti != tj || c0 + j2 <= r0 + i) Cb[(r0 + i) * P + c0 + j2] -= acc[i][j2];
+            };
+            if (tid < 64) trailing_task(tid);                        // pair 0 = the next diagonal block (kb + 1, kb + 1)
+            __syncthreads();
+            tr();   // next diagonal block updated
+            if (warp == 0) {
+                fs_potrf_warp(SB + fs_blk(kb + 1, kb + 1), invd + o + FS_NB, lane, flag, kb + 1);
+            } else {
+                for (int idx = 64 + tid - 32; idx < npairs * 64; idx += FS_T - 32) trailing_task(idx);
             }
             __syncthreads();
         }
@@ -290,7 +312,9 @@ chol_small_kernel(double* __restrict__ Hg, int n, int n_pad, const double* __res
     for (int kb = n_pres / FS_NB; kb < nblk; ++kb) {
         const double* D = SB + fs_blk(kb, kb);
         const int o = kb * FS_NB;
-        // (i) Y_k = L_kk^-1 X_k on ALL warps: thread = (row quad q4, right-hand side sj); Linv[rr][c] (c < rr) is stored at D[c][rr].
+        fs_build_ts(TS, D, invd + o, tid);
+        __syncthreads();
+        // (i) Y_k = L_kk^-1 X_k on ALL warps: thread = (row quad q4, right-hand side sj); (L^-1)[rr][c] = TS[c][rr]
         //     (With 8 x 2 tiles only four warps had work here and the step ran at the latency of one warp per scheduler.)
         double out[4] = {0.0, 0.0, 0.0, 0.0};
         if (sj < n_edit) {
@@ -300,8 +324,7 @@ chol_small_kernel(double* __restrict__ Hg, int n, int n_pad, const double* __res
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const int rr = 4 * q4 + i;
-                    const double raw = D[c * P + rr];
-                    out[i] = fma((c < rr) ? raw : ((c == rr) ? invd[o + rr] : 0.0), x, out[i]);
+                    out[i] = fma(TS[c * P + rr], x, out[i]);
                 }
             }
         }
@@ -311,6 +334,7 @@ chol_small_kernel(double* __restrict__ Hg, int n, int n_pad, const double* __res
             for (int i = 0; i < 4; ++i) XS[(o + 4 * q4 + i) * xl + sj] = out[i];
         }
         __syncthreads();
+        tr();   // triangular multiply of this block done
         for (int r = o + FS_NB + 8 * warp; r < n_pad; r += 8 * NW) {     // X_i -= L_ik Y_k for the block rows below
             const double* A = SB + fs_blk(r >> 5, kb) + (r & 31) * P;
             double s8[8][2];
@@ -332,13 +356,16 @@ chol_small_kernel(double* __restrict__ Hg, int n, int n_pad, const double* __res
             }
         }
         __syncthreads();
+        tr();   // update of the rows below done
     }
     tr();   // forward substitution done
     // backward  L^T Z = Y
     for (int kb = nblk - 1; kb >= 0; --kb) {
         const double* D = SB + fs_blk(kb, kb);
         const int o = kb * FS_NB;
-        // (i) Z_k = L_kk^-T Y_k on all warps: Linv[c][rr] (c > rr) is stored at D[rr][c]
+        fs_build_ts(TS, D, invd + o, tid);
+        __syncthreads();
+        // (i) Z_k = L_kk^-T Y_k on all warps: (L^-T)[rr][c] = (L^-1)[c][rr] = TS[rr][c]
         double out[4] = {0.0, 0.0, 0.0, 0.0};
         if (sj < n_edit) {
 #pragma unroll 4
@@ -347,8 +374,7 @@ chol_small_kernel(double* __restrict__ Hg, int n, int n_pad, const double* __res
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const int rr = 4 * q4 + i;
-                    const double raw = D[rr * P + c];
-                    out[i] = fma((c > rr) ? raw : ((c == rr) ? invd[o + rr] : 0.0), x, out[i]);
+                    out[i] = fma(TS[rr * P + c], x, out[i]);
                 }
             }
         }
@@ -358,6 +384,7 @@ chol_small_kernel(double* __restrict__ Hg, int n, int n_pad, const double* __res
             for (int i = 0; i < 4; ++i) XS[(o + 4 * q4 + i) * xl + sj] = out[i];
         }
         __syncthreads();
+        tr();   // triangular multiply of this block done
         for (int r = 8 * warp; r < o; r += 8 * NW) {  // X_i -= L_ki^T Z_k for the block rows above
             const double* A = SB + fs_blk(kb, r >> 5) + (r & 31);          // L[o + c][r + i] = block(kb, r/32)[c][r%32 + i]
             double s8[8][2];
@@ -379,6 +406,7 @@ chol_small_kernel(double* __restrict__ Hg, int n, int n_pad, const double* __res
             }
         }
         __syncthreads();
+        tr();   // update of the rows above done
     }
     tr();   // backward substitution done
     for (int r = warp; r < n; r += NW)
@@ -470,7 +498,7 @@ int factor_small(uce_ws* ws, const float* C, const float* G, int n, int n_pres, 
         UCE_CUDA(cudaMemcpyAsync(ws->Hcopy, ws->H, (size_t)n_pad * n_pad * sizeof(double), cudaMemcpyDeviceToDevice, st));
     }
     // + 8 rows of slack: the last pivots of a diagonal block read L[j + k][j] for rows up to 38 (columns that do not exist, results unused)
-    const size_t smem_c = ((size_t)(nt * (nt + 1) / 2) * FS_BLK + (size_t)n_pad * (n_edit | 1) + n_pad + 8 * (FS_NB + 1)) * sizeof(double);
+    const size_t smem_c = ((size_t)(nt * (nt + 1) / 2) * FS_BLK + (size_t)n_pad * (n_edit | 1) + n_pad + FS_BLK + 8 * (FS_NB + 1)) * sizeof(double);
     static size_t conf_c = 0;
     if (conf_c < smem_c) {
         UCE_CUDA(cudaFuncSetAttribute(chol_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));

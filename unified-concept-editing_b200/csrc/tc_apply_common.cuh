@@ -87,6 +87,14 @@ template <int N> __device__ __forceinline__ void tma_store_wait_read() {
     asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
 }
 
+// 16-byte asynchronous copy global -> shared through the LSU path (LDGSTS, L2 only), and the arrival that makes an mbarrier
+// track the completion of all of this thread's earlier cp.async copies (the barrier's count must include these arrivals)
+__device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_mbar_arrive(uint32_t bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
 // hi = x rounded to tf32 (nearest, ties away: what cvt.rna.tf32.f32 returns for finite x), lo = x - hi.  Integer add + mask
 // instead of the conversion instruction: cvt.rna runs on the quarter-rate conversion pipe, and the transform warps execute
 // it once per W element.

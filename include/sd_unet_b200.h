@@ -50,7 +50,14 @@ int sd_unet_set_weight(sd_unet *u, const char *name, const float *data, const lo
 /* Allocate activations, build the kernel schedule and the TMA tensor maps.  Fails if a parameter is missing. */
 int sd_unet_finalize(sd_unet *u);
 
-/* eps[batch,4,H,W] (fp32, NCHW) = UNet(x[batch,4,H,W] fp32 NCHW, t, ctx[batch,context_len,cross_attention_dim] fp32). */
+/* Text context of the following steps: ctx[batch,context_len,cross_attention_dim] fp32, DEVICE pointer.  Computes the
+ * cross-attention K / V^T projections of every transformer block once — the reference's pipe(...) evaluates them at each of
+ * its num_inference_steps U-Net calls although the prompt embedding is constant over a row (generate-images-sd.py:37-42).
+ * Overwriting a parameter afterwards (sd_unet_set_weight) makes the next forward recompute them from the stored context. */
+int sd_unet_set_context(sd_unet *u, const float *ctx, void *stream);
+
+/* eps[batch,4,H,W] (fp32, NCHW) = UNet(x[batch,4,H,W] fp32 NCHW, t, ctx[batch,context_len,cross_attention_dim] fp32).
+ * ctx may be NULL after sd_unet_set_context: the step then reuses the cached context projections. */
 int sd_unet_forward(sd_unet *u, const float *x, float t, const float *ctx, float *eps, void *stream);
 
 /* Update the timestep a CUDA graph captured around sd_unet_forward will read on its next replay (the captured
@@ -65,7 +72,8 @@ int sd_cfg_step(const float *eps2, long n, float gs, float *eps_out, const float
 
 /* Introspection / tests: number of kernels one forward enqueues; copy a named intermediate (conv_in, down.i.j, mid,
  * up.i.j, temb) to HOST as fp32 NCHW (temb: [batch, temb_dim]).  `cap` = floats available in `out`. */
-int sd_unet_launch_count(sd_unet *u);
+int sd_unet_launch_count(sd_unet *u);           /* per denoise step (context given by sd_unet_set_context) */
+int sd_unet_context_launch_count(sd_unet *u);   /* per sd_unet_set_context */
 int sd_unet_read_tap(sd_unet *u, const char *name, float *out, size_t cap, int dims[4]);
 
 #ifdef __cplusplus

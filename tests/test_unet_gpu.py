@@ -175,3 +175,38 @@ def test_edited_weights_overlay_changes_only_attn2():
     out = eng.forward(x.cuda(), 500.0, ctx.cuda()).cpu()
     assert _rel(out, ref) < 5e-2 and _rel(out, base) > 1e-3
     eng.close()
+
+
+def test_context_cache_matches_per_call_context():
+    """sd_unet_set_context + forward(ctx=None) — the per-prompt cache of the cross-attention K / V^T projections
+    (generate-images-sd.py:37-42 keeps one prompt embedding over all steps of a row) — gives the same results (to the engine's run-to-run noise) as passing
+    the context with every call, follows a new context, and is recomputed after an attn2 weight is overwritten."""
+    from uce_b200.unet import UNetEngine
+    cfg, P = _tiny()
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(2, 4, 16, 16, generator=g).cuda()
+    ctx_a = torch.randn(2, 77, cfg["cross_attention_dim"], generator=g).cuda()
+    ctx_b = torch.randn(2, 77, cfg["cross_attention_dim"], generator=g).cuda()
+    eng = UNetEngine(cfg, batch=2, H=16, W=16)
+    eng.load_state_dict(P)
+    eng.finalize()
+    with pytest.raises(Exception):
+        eng.forward(x, 300.0, None)                      # no context yet
+    assert eng.context_launch_count() > 0 and eng.launch_count() > 0
+    per_call_a = eng.forward(x, 300.0, ctx_a).clone()
+    per_call_b = eng.forward(x, 300.0, ctx_b).clone()
+    noise = _rel(eng.forward(x, 300.0, ctx_a), per_call_a)             # run-to-run noise of the engine itself (fp32 atomics in GroupNorm)
+    tol = max(2e-2, 3 * noise)
+    assert _rel(per_call_a, per_call_b) > 5 * tol
+    eng.set_context(ctx_a)
+    assert _rel(eng.forward(x, 300.0, None), per_call_a) <= tol
+    assert _rel(eng.forward(x, 300.0, None), per_call_a) <= tol          # and again: nothing of the cache is consumed
+    eng.set_context(ctx_b)
+    assert _rel(eng.forward(x, 300.0, None), per_call_b) <= tol
+    key = "mid_block.attentions.0.transformer_blocks.0.attn2.to_k.weight"
+    eng.load_state_dict({key: P[key] * 0.5}, strict=False)            # edited weight: the cached K must not survive
+    P2 = dict(P); P2[key] = P[key] * 0.5
+    ref = U.unet_forward(P2, x.cpu(), 300.0, ctx_b.cpu(), cfg)
+    out = eng.forward(x, 300.0, None).cpu()
+    assert _rel(out, ref) < 5e-2 and _rel(out, per_call_b.cpu()) > 1e-3
+    eng.close()

@@ -42,7 +42,9 @@ struct sd_unet {
     std::map<std::string, Weight> w;
     std::map<std::string, std::vector<long>> expected;          // name -> shape
     std::vector<void*> allocs;
-    std::vector<std::function<int(cudaStream_t)>> ops;
+    std::vector<std::function<int(cudaStream_t)>> ops;         // one denoise step
+    std::vector<std::function<int(cudaStream_t)>> ctx_ops;     // depend on the text context (and attn2.to_k/to_v) only: run once per prompt
+    bool ctx_set = false, ctx_dirty = true;
     std::map<std::string, Act> taps;
     // fixed I/O buffers
     float* x_in = nullptr; float* ctx_f32 = nullptr; bf16* ctx = nullptr; float* eps = nullptr;
@@ -150,7 +152,8 @@ struct Builder {
     explicit Builder(sd_unet* uu) : u(uu) {}
     Act act(int n, int h, int w, int c) { Act a{nullptr, n, h, w, c}; if (!rc) rc = u->alloc(&a.p, (size_t)a.pixels() * c); return a; }
     const Weight& W(const std::string& n) { return u->w.at(n); }
-    void push(std::function<int(cudaStream_t)> f) { u->ops.push_back(std::move(f)); }
+    bool to_ctx = false;      // route the next pushes to the per-prompt list (cross-attention K / V^T of the text context)
+    void push(std::function<int(cudaStream_t)> f) { (to_ctx ? u->ctx_ops : u->ops).push_back(std::move(f)); }
     void gemm(GemmDesc g) {
         if (!getenv("UCE_NO_PAIR") && uce::gemm_enable_pair(&g) < 0) { rc = rc ? rc : SD_E_STATE; sd_err("tensor map encode failed (pair)"); return; }
         int ks = uce::gemm_choose_ksplit(g, u->sm_count);
@@ -224,13 +227,17 @@ struct Builder {
         if (!rc) rc = u->alloc(&vt, (size_t)NB * HD * Lkp);
         if (!rc) rc = u->alloc(&o, (size_t)M * HD);
         linear(q_src, M, C, a + ".to_q.weight", nullptr, nullptr, q, false, HD);
+        // K and V^T of the TEXT context do not change between denoise steps (generate-images-sd.py:37-42 runs all steps of a row
+        // with one prompt embedding): those projections go to the per-prompt list (sd_unet_set_context), not to the step.
+        to_ctx = (kv_src == u->ctx);
         linear(kv_src, (long)NB * Lk, kdim, a + ".to_k.weight", nullptr, nullptr, k, false, HD);
         {   // V^T[b] [HD, Lk] = Wv_pad [HD, kdim] . kv_src[b]^T
             GemmDesc g;
-            if (uce::gemm_desc_linear(&g, W(a + ".to_v.weight").b, kdim, 0, 0, kv_src, kdim, (long)Lk * kdim, 0, HD, Lk, kdim, NB, 1, 0, 1)) { rc = rc ? rc : SD_E_STATE; return; }
+            if (uce::gemm_desc_linear(&g, W(a + ".to_v.weight").b, kdim, 0, 0, kv_src, kdim, (long)Lk * kdim, 0, HD, Lk, kdim, NB, 1, 0, 1)) { rc = rc ? rc : SD_E_STATE; to_ctx = false; return; }
             g.out = vt; g.out_fp32 = 0; g.ldo = Lkp; g.out_b1_stride = (long)HD * Lkp;
             gemm(g);
         }
+        to_ctx = false;
         const bool fused = uce::attn_fused_supported(dhp) && !getenv("UCE_NO_FLASH");
         if (fused) {   // flash-style kernel: no score matrix in HBM
             uce::AttnDesc ad;
@@ -334,7 +341,9 @@ int build_schedule(sd_unet* u) {
     B.push([u](cudaStream_t st) { return (int)cudaMemsetAsync(u->gn_stats, 0, (size_t)u->n_gn * u->NB * u->cfg.norm_groups * 2 * sizeof(float), st); });
     {
         float* cf = u->ctx_f32; bf16* cb = u->ctx; const long n = (long)NB * c.context_len * c.cross_attention_dim;
+        B.to_ctx = true;
         B.push([=](cudaStream_t st) { return (int)uce::launch_k(f32_to_bf16_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, 1, cf, cb, n); });
+        B.to_ctx = false;
     }
     // ---- time embedding ----
     bf16 *te0 = nullptr, *t1 = nullptr, *t1s = nullptr, *temb = nullptr, *st_emb = nullptr;
@@ -455,6 +464,7 @@ int sd_unet_set_weight(sd_unet* u, const char* name, const float* data, const lo
     const int heads = u->cfg.heads;
     Weight& w = u->w[name];
     const bool fresh = w.elems == 0;
+    u->ctx_dirty = true;        // cached K / V^T of the text context may depend on this parameter (attn2.to_k / to_v)
     std::vector<float> tmp;
     const float* src = data; long out_n = n;
     if (kind == 2) {            // [Cout][Cin][3][3] -> [Cout][ky][kx][Cin]
@@ -511,16 +521,45 @@ int sd_unet_finalize(sd_unet* u) {
     return 0;
 }
 
+static int run_ctx_ops(sd_unet* u, cudaStream_t st) {
+    int i = 0;
+    for (auto& op : u->ctx_ops) {
+        int rc = op(st);
+        if (rc) { sd_err("U-Net context op %d failed: %s", i, rc > 0 ? cudaGetErrorString((cudaError_t)rc) : "descriptor error"); return rc; }
+        ++i;
+    }
+    u->ctx_dirty = false;
+    return 0;
+}
+
+int sd_unet_set_context(sd_unet* u, const float* ctx, void* stream) {
+    if (!u || !ctx) { sd_err("sd_unet_set_context: bad argument"); return SD_E_ARG; }
+    if (!u->finalized) { sd_err("sd_unet_set_context before sd_unet_finalize"); return SD_E_STATE; }
+    SD_CUDA(cudaSetDevice(u->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const sd_unet_config& c = u->cfg;
+    SD_CUDA(cudaMemcpyAsync(u->ctx_f32, ctx, (size_t)u->NB * c.context_len * c.cross_attention_dim * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    u->ctx_set = true;
+    return run_ctx_ops(u, st);
+}
+
 int sd_unet_forward(sd_unet* u, const float* x, float t, const float* ctx, float* eps, void* stream) {
-    if (!u || !x || !ctx || !eps) { sd_err("sd_unet_forward: bad argument"); return SD_E_ARG; }
+    if (!u || !x || !eps) { sd_err("sd_unet_forward: bad argument"); return SD_E_ARG; }
     if (!u->finalized) { sd_err("sd_unet_forward before sd_unet_finalize"); return SD_E_STATE; }
+    if (!ctx && !u->ctx_set) { sd_err("sd_unet_forward: ctx is NULL and sd_unet_set_context was never called"); return SD_E_STATE; }
     SD_CUDA(cudaSetDevice(u->device));
     cudaStream_t st = (cudaStream_t)stream;
     const sd_unet_config& c = u->cfg;
     *u->h_t = t;
     SD_CUDA(cudaMemcpyAsync(u->d_t, u->h_t, sizeof(float), cudaMemcpyHostToDevice, st));
     SD_CUDA(cudaMemcpyAsync(u->x_in, x, (size_t)u->NB * c.in_channels * u->H * u->W * sizeof(float), cudaMemcpyDeviceToDevice, st));
-    SD_CUDA(cudaMemcpyAsync(u->ctx_f32, ctx, (size_t)u->NB * c.context_len * c.cross_attention_dim * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if (ctx) {                       // context given with the call: (re)compute its K / V^T now
+        int rc = sd_unet_set_context(u, ctx, stream);
+        if (rc) return rc;
+    } else if (u->ctx_dirty) {       // an attn2.to_k / to_v weight was overwritten since: recompute from the stored context
+        int rc = run_ctx_ops(u, st);
+        if (rc) return rc;
+    }
     int i = 0;
     for (auto& op : u->ops) {
         int rc = op(st);
@@ -546,6 +585,7 @@ int sd_cfg_step(const float* eps2, long n, float gs, float* eps_out, const float
 }
 
 int sd_unet_launch_count(sd_unet* u) { return u ? (int)u->ops.size() : SD_E_ARG; }
+int sd_unet_context_launch_count(sd_unet* u) { return u ? (int)u->ctx_ops.size() : SD_E_ARG; }
 
 int sd_unet_read_tap(sd_unet* u, const char* name, float* out, size_t cap, int dims[4]) {
     if (!u || !name || !out) return SD_E_ARG;

@@ -35,11 +35,12 @@ class Denoiser:
         """latents [B,4,H,W] (any float dtype, device or host), ctx [2B,77,D] ordered [uncond | text] -> final latents fp32."""
         self.x.copy_(latents.to(self.x.device, torch.float32))
         ctx = ctx_uncond_text.to(self.x.device, torch.float32).contiguous()
+        self.eng.set_context(ctx)                   # cross-attention K / V^T of the prompt: once per row, not once per step
         hist = []                                   # most recent first
         free = list(self.hist)
         for plan in make_plan(scheduler, steps):
             self.x2[: self.B].copy_(self.x); self.x2[self.B:].copy_(self.x)
-            self.eng.forward(self.x2, float(plan.t), ctx, out=self.eps2)
+            self.eng.forward(self.x2, float(plan.t), None, out=self.eps2)
             if plan.save_sample:
                 self.saved.copy_(self.x)
             x_in = self.saved if plan.use_saved_sample else self.x

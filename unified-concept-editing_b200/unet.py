@@ -24,11 +24,13 @@ SD_SIGNATURES = {
     "sd_unet_destroy": (C.c_int, [C.c_void_p]),
     "sd_unet_set_weight": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.POINTER(C.c_long), C.c_int]),
     "sd_unet_finalize": (C.c_int, [C.c_void_p]),
+    "sd_unet_set_context": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "sd_unet_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
     "sd_unet_set_timestep": (C.c_int, [C.c_void_p, C.c_float]),
     "sd_cfg_step": (C.c_int, [C.c_void_p, C.c_long, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_float),
                               C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
     "sd_unet_launch_count": (C.c_int, [C.c_void_p]),
+    "sd_unet_context_launch_count": (C.c_int, [C.c_void_p]),
     "sd_unet_read_tap": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_int)]),
 }
 _bound = False
@@ -107,15 +109,29 @@ class UNetEngine:
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
-    def forward(self, x: torch.Tensor, t: float, ctx: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
-        """eps [batch,4,H,W] fp32 = UNet(x [batch,4,H,W] fp32, t, ctx [batch,context_len,ctx_dim] fp32) — device tensors."""
-        assert x.device == self.device and x.dtype == torch.float32 and x.is_contiguous() and tuple(x.shape) == (self.batch, 4, self.H, self.W)
+    def _check_ctx(self, ctx: torch.Tensor):
         assert ctx.device == self.device and ctx.dtype == torch.float32 and ctx.is_contiguous()
         assert tuple(ctx.shape) == (self.batch, self.context_len, self.cfg["cross_attention_dim"])
+
+    def set_context(self, ctx: torch.Tensor):
+        """Text context [batch,context_len,ctx_dim] fp32 of the following steps: its cross-attention K / V^T projections are
+        computed once here instead of at every denoise step (the prompt embedding is constant over a row,
+        evalscripts/generate-images-sd.py:37-42)."""
+        self._check_ctx(ctx)
+        with torch.cuda.device(self.device):
+            _check(_lib().sd_unet_set_context(self._h, C.c_void_p(ctx.data_ptr()), self._stream()))
+
+    def forward(self, x: torch.Tensor, t: float, ctx: torch.Tensor | None = None, out: torch.Tensor | None = None) -> torch.Tensor:
+        """eps [batch,4,H,W] fp32 = UNet(x [batch,4,H,W] fp32, t, ctx [batch,context_len,ctx_dim] fp32) — device tensors.
+        ctx=None reuses the context given to set_context()."""
+        assert x.device == self.device and x.dtype == torch.float32 and x.is_contiguous() and tuple(x.shape) == (self.batch, 4, self.H, self.W)
+        if ctx is not None:
+            self._check_ctx(ctx)
         if out is None:
             out = torch.empty_like(x)
         with torch.cuda.device(self.device):
-            _check(_lib().sd_unet_forward(self._h, C.c_void_p(x.data_ptr()), float(t), C.c_void_p(ctx.data_ptr()), C.c_void_p(out.data_ptr()), self._stream()))
+            _check(_lib().sd_unet_forward(self._h, C.c_void_p(x.data_ptr()), float(t), C.c_void_p(ctx.data_ptr()) if ctx is not None else None,
+                                          C.c_void_p(out.data_ptr()), self._stream()))
         return out
 
     def set_timestep(self, t: float):
@@ -123,7 +139,11 @@ class UNetEngine:
         _check(_lib().sd_unet_set_timestep(self._h, float(t)))
 
     def launch_count(self) -> int:
+        """Kernels one denoise step enqueues (context projections excluded: see context_launch_count)."""
         return _lib().sd_unet_launch_count(self._h)
+
+    def context_launch_count(self) -> int:
+        return _lib().sd_unet_context_launch_count(self._h)
 
     def read_tap(self, name: str) -> torch.Tensor:
         cap = self.batch * max(self.cfg["block_out_channels"]) * 2 * self.H * self.W

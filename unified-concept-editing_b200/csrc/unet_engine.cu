@@ -45,6 +45,7 @@ struct sd_unet {
     std::vector<std::function<int(cudaStream_t)>> ops;         // one denoise step
     std::vector<std::function<int(cudaStream_t)>> ctx_ops;     // depend on the text context (and attn2.to_k/to_v) only: run once per prompt
     bool ctx_set = false, ctx_dirty = true;
+    std::vector<uce::TembJob> temb_jobs; uce::TembJob* temb_jobs_dev = nullptr; int temb_channels = 0;   // all time_emb_proj of a call: one launch
     std::map<std::string, Act> taps;
     // fixed I/O buffers
     float* x_in = nullptr; float* ctx_f32 = nullptr; bf16* ctx = nullptr; float* eps = nullptr;
@@ -200,7 +201,9 @@ struct Builder {
         Act a1 = act(x.n, x.h, x.w, x.c);
         groupnorm(x, a1, p + ".norm1", 1e-5f, 1);
         float* tproj = nullptr; if (!rc) rc = u->alloc(&tproj, (size_t)x.n * cout);
-        linear(st_emb, x.n, u->cfg.temb_dim, p + ".time_emb_proj.weight", W(p + ".time_emb_proj.bias").f, nullptr, tproj, true);
+        (void)st_emb;         // projected for ALL resnets by the single op pushed after the time-embedding MLP (op_temb_proj_all)
+        u->temb_jobs.push_back(uce::TembJob{W(p + ".time_emb_proj.weight").b, W(p + ".time_emb_proj.bias").f, tproj, cout, u->temb_channels});
+        u->temb_channels += cout;
         Act h1 = act(x.n, x.h, x.w, cout);
         conv3(a1, p + ".conv1.weight", W(p + ".conv1.bias").f, tproj, nullptr, h1, 1);
         Act a2 = act(x.n, x.h, x.w, cout);
@@ -361,6 +364,8 @@ int build_schedule(sd_unet* u) {
     B.linear(t1s, NB, c.temb_dim, "time_embedding.linear_2.weight", B.W("time_embedding.linear_2.bias").f, nullptr, temb, false);
     { const long n = (long)NB * c.temb_dim; B.push([=](cudaStream_t st) { return uce::op_silu(temb, st_emb, n, st); }); }
     u->temb_tap = temb;
+    // every resnet's time_emb_proj in one launch (the job table is filled while the resnets below are built, uploaded at the end)
+    B.push([u, st_emb](cudaStream_t st) { return uce::op_temb_proj_all(u->temb_jobs_dev, (int)u->temb_jobs.size(), u->temb_channels, st_emb, u->NB, u->cfg.temb_dim, st); });
     // ---- conv_in ----
     Act h = B.act(NB, H, W, ch[0]);
     {
@@ -413,6 +418,10 @@ int build_schedule(sd_unet* u) {
         const float* w = B.W("conv_out.weight").f; const float* bi = B.W("conv_out.bias").f; float* e = u->eps; const int c0 = ch[0];
         if (c.out_channels != 4) { sd_err("conv_out kernel supports 4 output channels"); return SD_E_ARG; }
         B.push([=](cudaStream_t st) { return uce::op_conv_out(a.p, w, bi, e, NB, H, W, c0, st); });
+    }
+    if (!B.rc && !u->temb_jobs.empty()) {      // job table of the batched time-embedding projection
+        if ((rc = u->alloc(&u->temb_jobs_dev, u->temb_jobs.size()))) return rc;
+        SD_CUDA(cudaMemcpy(u->temb_jobs_dev, u->temb_jobs.data(), u->temb_jobs.size() * sizeof(uce::TembJob), cudaMemcpyHostToDevice));
     }
     return B.rc;
 }

@@ -355,6 +355,61 @@ int op_silu(const __nv_bfloat16* x, __nv_bfloat16* y, long n, cudaStream_t st) {
     OPS_CHECK();
     return 0;
 }
+
+// ---- all time-embedding projections of one U-Net call in ONE launch ----
+// out_j[img][n] = bias_j[n] + sum_k st_emb[img][k] W_j[n][k]  for every resnet j (diffusers ResnetBlock2D.time_emb_proj applied to
+// SiLU(temb)).  They all read the same [NB, temb_dim] input and have M = NB (2 with classifier-free guidance at bs = 1): as 22
+// separate tensor-core GEMM launches they cost ~13 us each for 2 rows of a 128-row tile.  Warp = one output channel of one job,
+// lanes stride the K dimension with 16-byte loads; weights are read once (47 MB for SD-1.4): HBM bound.
+__global__ void __launch_bounds__(256) temb_proj_all_kernel(const TembJob* __restrict__ jobs, int n_jobs, int total_channels, const __nv_bfloat16* __restrict__ st_emb,
+                                                            int NB, int K) {
+    pdl_launch();
+    const int gw = (int)((blockIdx.x * (long)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+    if (gw >= total_channels) return;
+    int j = 0;
+    while (j + 1 < n_jobs && jobs[j + 1].first_channel <= gw) ++j;
+    const TembJob jb = jobs[j];
+    const int n = gw - jb.first_channel;
+    const uint4* wrow = reinterpret_cast<const uint4*>(jb.w + (long)n * K);       // weights: not produced by an earlier kernel
+    constexpr int MAXB = 16;
+    float acc[MAXB];
+#pragma unroll
+    for (int b = 0; b < MAXB; ++b) acc[b] = 0.f;
+    pdl_wait();                                                                   // st_emb comes from the kernel before
+    for (int v = lane; v < K / 8; v += 32) {
+        const uint4 wv = wrow[v];
+        const __nv_bfloat162* w2 = reinterpret_cast<const __nv_bfloat162*>(&wv);
+#pragma unroll
+        for (int b = 0; b < MAXB; ++b) {
+            if (b < NB) {
+                const uint4 xv = reinterpret_cast<const uint4*>(st_emb + (long)b * K)[v];
+                const __nv_bfloat162* x2 = reinterpret_cast<const __nv_bfloat162*>(&xv);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float2 wf = __bfloat1622float2(w2[e]), xf = __bfloat1622float2(x2[e]);
+                    acc[b] = fmaf(wf.x, xf.x, acc[b]); acc[b] = fmaf(wf.y, xf.y, acc[b]);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int b = 0; b < MAXB; ++b) {
+        if (b < NB) {
+            float s = acc[b];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (lane == 0) jb.out[(long)b * jb.cout + n] = s + jb.bias[n];
+        }
+    }
+}
+int op_temb_proj_all(const TembJob* jobs_dev, int n_jobs, int total_channels, const __nv_bfloat16* st_emb, int NB, int K, cudaStream_t st) {
+    if (NB > 16 || K % 8) return -1;
+    const long threads = (long)total_channels * 32;
+    if (launch_k(temb_proj_all_kernel, dim3((unsigned)((threads + 255) / 256)), dim3(256), 0, st, 1, jobs_dev, n_jobs, total_channels, st_emb, NB, K) != cudaSuccess)
+        return (int)cudaGetLastError();
+    OPS_CHECK();
+    return 0;
+}
 int op_upsample2x(const __nv_bfloat16* x, __nv_bfloat16* y, int NB, int H, int W, int C, cudaStream_t st) {
     const long n = (long)NB * 4 * H * W * (C / 8);
     if (launch_k(upsample2x_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, 1, x, y, NB, H, W, C) != cudaSuccess) return (int)cudaGetLastError();

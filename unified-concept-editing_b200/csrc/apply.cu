@@ -23,7 +23,7 @@ int apply_tc2_lowrank(uce_ws* ws, const LayerRef* layers_dev, const LayerRef* la
 bool apply_tc3_available(const uce_ws* ws, int n_layers);   // apply_tc3.cu
 int apply_tc3_plan(int sm_count, const int* d, int n_layers, int* tile_rows, int* tile_begin);
 int apply_tc3_lowrank(uce_ws* ws, const LayerRef* layers_dev, const LayerRef* layers_host, int n_layers, int total_tiles,
-                      cudaStream_t st, int* launches);
+                      cudaStream_t st, int* launches, cudaEvent_t ev_begin);
 
 __device__ __forceinline__ int find_layer(const LayerRef* layers, int n_layers, int tile) {
     int lo = 0, hi = n_layers - 1;
@@ -168,7 +168,7 @@ int apply_dev(uce_ws* ws, const float* const* W_old, float* const* W_new, const 
     const int r_pad = ws->rank_pad;
     const bool prof = ws->profile && !no_profile;
     ws->pev_mid = 0;
-    if (prof) UCE_CUDA(cudaEventRecord(ws->pev[2], st));
+    if (prof && !use_tc3) UCE_CUDA(cudaEventRecord(ws->pev[2], st));      // apply_tc3 records it itself, right before its launch
     if (ws->rank == 0) {   // no active edit rows: the edit is the identity
         copy_layers_kernel<<<tiles, 256, 0, st>>>(dl, n_layers, K);
         UCE_LAUNCH_CHECK(); ++launches;
@@ -185,7 +185,7 @@ int apply_dev(uce_ws* ws, const float* const* W_old, float* const* W_new, const 
     }
     if (!ws->dense) {
         if (use_tc3) {
-            int rc = apply_tc3_lowrank(ws, dl, hl, n_layers, tiles, st, &launches);
+            int rc = apply_tc3_lowrank(ws, dl, hl, n_layers, tiles, st, &launches, prof ? ws->pev[2] : nullptr);
             if (rc) return rc;
         } else if (use_tc2) {
             int rc = apply_tc2_lowrank(ws, dl, hl, n_layers, tiles, tile_rows, st, &launches);

@@ -487,7 +487,7 @@ int apply_tc3_plan(int sm_count, const int* d, int n_layers, int* tile_rows, int
 }
 
 int apply_tc3_lowrank(uce_ws* ws, const LayerRef* layers_dev, const LayerRef* layers_host, int n_layers, int total_tiles,
-                      cudaStream_t st, int* launches) {
+                      cudaStream_t st, int* launches, cudaEvent_t ev_begin) {
     using namespace tc3;
     const int K = ws->K, R = ws->rank_pad;
     if (!apply_tc3_available(ws, n_layers)) { set_error("two-block tcgen05 apply unavailable for K=%d rank_pad=%d dense=%d layers=%d", K, R, ws->dense, n_layers); return UCE_E_STATE; }
@@ -514,6 +514,9 @@ int apply_tc3_lowrank(uce_ws* ws, const LayerRef* layers_dev, const LayerRef* la
     long long* trace = nullptr;
     const char* trace_path = getenv("UCE_TC_TRACE");
     if (trace_path) { UCE_CUDA(cudaMalloc(&trace, 7 * 64 * 4 * sizeof(long long))); UCE_CUDA(cudaMemsetAsync(trace, 0, 7 * 64 * 4 * sizeof(long long), st)); }
+    // profiling: the begin event goes right before the launch — recorded earlier it would also time whatever the GPU idles while
+    // the host encodes the tensor maps above (visible when the factor before it is short: cfg3 measured 65 us for a 33 us kernel)
+    if (ev_begin) UCE_CUDA(cudaEventRecord(ev_begin, st));
     const char* am = getenv("UCE_TC3_ADDEND");          // "tma" (default) or "ldgsts": route of the phase-B addend (see load_box)
     const int addend_ldgsts = (am && am[0] == 'l') ? 1 : 0;
     apply_tc3_kernel<<<total_tiles, THREADS, smem, st>>>(layers_dev, n_layers, K, R, addend_ldgsts, maps, wmaps, trace);

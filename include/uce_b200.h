@@ -132,6 +132,21 @@ int uce_ws_info(uce_ws *ws, int *mode, int *rank, int *dense, int *sys_n, int *l
  * Synchronises the device. `cap_bytes` is the size of `out`. */
 int uce_ws_debug_read(uce_ws *ws, int which, void *out, size_t cap_bytes);
 
+/* ---- the UCE artifact: host-only, no GPU needed ----------------------------------------------------------------------
+ * The reference stores ONLY the edited attn2.to_k / to_v weights, fp32, key = module path + ".weight", with
+ * safetensors.torch.save_file (trainscripts/uce_sd_erase.py:85-88; uce_sd_debias.py writes the same way) and reads them back with
+ * load_file + load_state_dict(strict=False) (evalscripts/generate-images-sd.py:17-19).  uce_artifact_write_f32 produces the
+ * byte-identical file for the same dictionary (n two-dimensional fp32 tensors data[i] of rows[i] x cols[i], HOST pointers — pinned
+ * staging buffers can be written without another copy); the reader opens any safetensors file and reads its F32 tensors. */
+typedef struct uce_artifact uce_artifact;
+int uce_artifact_write_f32(const char *path, int n, const char *const *names, const float *const *data, const long *rows, const long *cols);
+int uce_artifact_open(const char *path, uce_artifact **out);
+int uce_artifact_count(const uce_artifact *a);
+/* name / dtype point into the handle (valid until close); shape receives ndim <= 8 extents */
+int uce_artifact_entry(const uce_artifact *a, int i, const char **name, const char **dtype, int *ndim, long shape[8]);
+int uce_artifact_read_f32(uce_artifact *a, int i, float *dst, size_t cap_elems);
+int uce_artifact_close(uce_artifact *a);
+
 #ifdef __cplusplus
 }
 #endif

@@ -32,6 +32,12 @@ SIGNATURES = {
     "uce_ws_check": (C.c_int, [C.c_void_p, C.c_void_p]),
     "uce_ws_info": (C.c_int, [C.c_void_p] + [C.POINTER(C.c_int)] * 6),
     "uce_ws_debug_read": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]),
+    "uce_artifact_write_f32": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(C.c_char_p), _PP_F, C.POINTER(C.c_long), C.POINTER(C.c_long)]),
+    "uce_artifact_open": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
+    "uce_artifact_count": (C.c_int, [C.c_void_p]),
+    "uce_artifact_entry": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), C.POINTER(C.c_int), C.POINTER(C.c_long)]),
+    "uce_artifact_read_f32": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]),
+    "uce_artifact_close": (C.c_int, [C.c_void_p]),
 }
 
 

@@ -78,9 +78,9 @@ def UCE(pipe, clip, edit_concepts, debias_concepts, preserve_concepts, edit_scal
     elapsed = time.time() - start
     state = {name + ".weight": w for name, w in zip(names, current)}
     if save_dir is not None:
-        from safetensors.torch import save_file
+        from .artifact import save_artifact       # byte-identical to safetensors.torch.save_file (tests/test_artifact.py)
         os.makedirs(save_dir, exist_ok=True)
-        save_file({k: v.detach().cpu().contiguous() for k, v in state.items()}, os.path.join(save_dir, exp_name + ".safetensors"))
+        save_artifact(state, os.path.join(save_dir, exp_name + ".safetensors"))
     if own:
         solver.close()
     if verbose:

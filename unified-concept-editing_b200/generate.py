@@ -77,8 +77,8 @@ def generate_images(model_id, uce_model_path, prompts_path, save_path, exp_name=
         pipe = DiffusionPipeline.from_pretrained(model_id, torch_dtype=torch_dtype, safety_checker=None).to(device)
     state = {k: v for k, v in pipe.unet.state_dict().items()}
     if uce_model_path is not None:
-        from safetensors.torch import load_file
-        state.update(load_file(uce_model_path))          # load_state_dict(strict=False) semantics (generate-images-sd.py:17-19)
+        from .artifact import load_artifact
+        state.update(load_artifact(uce_model_path))      # load_state_dict(strict=False) semantics (generate-images-sd.py:17-19)
     latent = getattr(pipe, "latent_size", 64)
     eng = UNetEngine(unet_config, batch=2 * num_images_per_prompt, H=latent, W=latent, device=device)
     eng.load_state_dict(state, strict=False)

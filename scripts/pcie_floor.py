@@ -18,7 +18,7 @@ for _ in range(2): run(True, True, 2)
 a, b, c = run(True, False), run(False, True), run(True, True)
 print(f"H2D 76.7 MB: {a:.3f} ms ({4*n/a/1e6:.1f} GB/s)   D2H: {b:.3f} ms ({4*n/b/1e6:.1f} GB/s)   both at once: {c:.3f} ms")
 # the same bytes as 32 per-projection copies (the granularity uce_edit_host_f32 sees: one host tensor per projection)
-from uce_b200_dims import DIMS
+from uce_b200_dims import DIMS  # scripts/uce_b200_dims.py
 hs_in = [torch.randn(d * 768).pin_memory() for d in DIMS]
 hs_out = [torch.empty(d * 768).pin_memory() for d in DIMS]
 offs = [0]

@@ -157,3 +157,19 @@ def test_row_block_plan_covers_every_row_once(monkeypatch):
     import ctypes as C
     from uce_b200 import _native
     assert _native.lib().uce_plan_row_blocks(148, None, 1, None, None) == _native.UCE_E_ARG
+
+
+def test_generation_rows_are_dealt_round_robin_after_the_case_filter():
+    """generate-images-sd.py:29-35: inclusive from_case / till_case filter; our ranks then take every world-th surviving row,
+    so the union over ranks is exactly the reference's row list, in order, without overlap."""
+    import pandas as pd
+    from uce_b200.generate import rows_for_rank
+    df = pd.DataFrame({"prompt": [f"p{i}" for i in range(11)], "evaluation_seed": list(range(100, 111)), "case_number": [0, 1, 2, 3, 5, 8, 9, 10, 12, 40, 41]})
+    ref = [r.case_number for _, r in df.iterrows() if 1 <= r.case_number <= 40]            # the reference's loop
+    assert [r.case_number for r in rows_for_rank(df, 1, 40, 0, 1)] == ref
+    for world in (2, 3, 8):
+        parts = [[r.case_number for r in rows_for_rank(df, 1, 40, rk, world)] for rk in range(world)]
+        assert sorted(sum(parts, [])) == ref and sum(len(p) for p in parts) == len(ref)
+        assert all(parts[rk] == ref[rk::world] for rk in range(world))
+        assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
+    assert rows_for_rank(df, 100, 200, 0, 2) == []

@@ -63,6 +63,13 @@ def _rank_world():
     return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
 
 
+def rows_for_rank(df, from_case, till_case, rank, world):
+    """CSV rows this rank generates: the reference's inclusive case filter (evalscripts/generate-images-sd.py:33), then the
+    surviving rows dealt round-robin to the ranks (prompts data-parallel, no collective in steady state: SURVEY.md 8e)."""
+    kept = [row for _, row in df.iterrows() if from_case <= row.case_number <= till_case]
+    return kept[rank::world]
+
+
 def generate_images(model_id, uce_model_path, prompts_path, save_path, exp_name="test", device="cuda:0", torch_dtype=torch.bfloat16,
                     guidance_scale=7.5, num_inference_steps=100, num_images_per_prompt=10, from_case=0, till_case=1000000,
                     pipe=None, scheduler="pndm", unet_config=SD14):
@@ -89,15 +96,8 @@ def generate_images(model_id, uce_model_path, prompts_path, save_path, exp_name=
     folder = f"{save_path}/{exp_name}"
     os.makedirs(folder, exist_ok=True)
     rank, world = _rank_world()
-    idx = 0
-    for _, row in df.iterrows():
+    for row in rows_for_rank(df, from_case, till_case, rank, world):
         case_number = row.case_number
-        if not (case_number >= from_case and case_number <= till_case):
-            continue
-        mine = (idx % world) == rank
-        idx += 1
-        if not mine:
-            continue
         prompt, seed = str(row.prompt), row.evaluation_seed
         text, uncond = pipe.encode_prompt(prompt=prompt, device=device, num_images_per_prompt=num_images_per_prompt,
                                           do_classifier_free_guidance=True)[:2]

@@ -173,3 +173,16 @@ def test_generation_rows_are_dealt_round_robin_after_the_case_filter():
         assert all(parts[rk] == ref[rk::world] for rk in range(world))
         assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
     assert rows_for_rank(df, 100, 200, 0, 2) == []
+
+
+def test_public_headers_are_plain_c(tmp_path):
+    """The drop-in boundary is a C ABI: both headers must compile as C11 on their own (no torch / CUDA types in the signatures)."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    src = tmp_path / "hdr.c"
+    src.write_text(f'#include "{ROOT}/include/uce_b200.h"\n#include "{ROOT}/include/sd_unet_b200.h"\nint main(void) {{ return 0; }}\n')
+    r = subprocess.run([gcc, "-std=c11", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", str(src)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr

@@ -148,6 +148,12 @@ int uce_artifact_entry(const uce_artifact *a, int i, const char **name, const ch
 int uce_artifact_read_f32(uce_artifact *a, int i, float *dst, size_t cap_elems);
 int uce_artifact_close(uce_artifact *a);
 
+/* ---- PNG writer for the generated images (host-only) ------------------------------------------------------------------
+ * The reference saves every image of a CSV row as {case_number}_{num}.png with PIL (evalscripts/generate-images-sd.py:45-46).
+ * rgb: H x W x 3 bytes, row-major.  level 0..9 (zlib; other values = 6).  threads <= 0 = all host cores: the image is deflated in
+ * stripes of rows in parallel and stitched into one zlib stream.  Lossless: any PNG reader returns rgb exactly. */
+int uce_png_write_rgb8(const char *path, const unsigned char *rgb, int H, int W, int level, int threads);
+
 #ifdef __cplusplus
 }
 #endif

@@ -38,6 +38,7 @@ SIGNATURES = {
     "uce_artifact_entry": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), C.POINTER(C.c_int), C.POINTER(C.c_long)]),
     "uce_artifact_read_f32": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]),
     "uce_artifact_close": (C.c_int, [C.c_void_p]),
+    "uce_png_write_rgb8": (C.c_int, [C.c_char_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]),
 }
 
 

@@ -11,6 +11,7 @@ import os
 
 import torch
 
+from .png import save_png
 from .schedulers import make_plan
 from .unet import UNetEngine, cfg_step
 from .unet_spec import SD14
@@ -107,7 +108,7 @@ def generate_images(model_id, uce_model_path, prompts_path, save_path, exp_name=
         out = den.run(lat, ctx, steps=num_inference_steps, guidance_scale=guidance_scale, scheduler=scheduler)
         images = pipe.decode_latents_to_pil(out) if hasattr(pipe, "decode_latents_to_pil") else _decode(pipe, out, torch_dtype)
         for num, im in enumerate(images):
-            im.save(f"{folder}/{case_number}_{num}.png")
+            save_png(f"{folder}/{case_number}_{num}.png", im)          # lossless, parallel deflate (csrc/png.cu); same file name as :46
     eng.close()
 
 

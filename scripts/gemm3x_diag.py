@@ -23,10 +23,9 @@ def run(n_edit, K, dims):
         col = [float(d[:, c:c + 32].norm() / (dw[:, c:c + 32].norm() + 1e-30)) for c in range(0, K, 32)]
         row = [float(d[r:r + 32].norm() / (dw[r:r + 32].norm() + 1e-30)) for r in range(0, x.shape[0], 32)]
         print("  total rel err of the UPDATE", float(d.norm() / dw.norm()))
-        print("  per 32-col block:", " ".join(f"{v:.1e}" for v in col))
         print("  per 32-row block:", " ".join(f"{v:.1e}" for v in row))
     s.close()
 
-run(200, 512, [200])
-run(200, 512, [320, 200])
-run(64, 256, [72, 8, 128])
+for d in ([72], [136], [192], [256], [264], [200, 320]):
+    run(200, 512, d)
+run(40, 512, [200])

@@ -15,12 +15,13 @@
 //     fetched into the same boxes) -> TMA stores
 //
 // STATUS (round 1): opt-in only — apply impl 5 (uce_ws_set_apply_impl / UCE_APPLY_IMPL=5), never chosen automatically; the SIMT
-// kernels remain the high-rank path.  Two short hardware runs at the very end of the round (scripts/gemm3x_diag.py,
+// kernels remain the high-rank path.  Three short hardware runs at the very end of the round (scripts/gemm3x_diag.py,
 // profiles/r01_gemm3x_diag_*.txt): no hang, no trap, and the update agrees with the SIMT apply to 5e-6 for rank pads 64 / 96 / 224 /
-// 256 on projections of 320, 128, 72 and 8 rows — but for a projection of 200 rows at rank pad 224 the first 32 rows of BOTH of
-// its row tiles (TMEM lanes 0-31, the rows of warp 0) come out 4e-2..1e-1 off, in both launches, while a 320-row projection in
-// the same launch is exact.  Not understood yet; tests/test_solver_gpu.py::test_highrank_tcgen05_apply stays skipped
-// (UCE_TEST_GEMM3X=1 runs it).  Round 2 starts here.
+// 256 in most launches — but NOT in all of them: a 200-row projection came out 4e-2..1e-1 off in the first 32 rows of both of its
+// row tiles in one process and exact in the next one; a 264-row projection was off in its last 8 rows (the first rows of its third
+// tile).  Always the rows of warp 0 (TMEM lanes 0-31) of a tile, and not reproducible per shape: a race, not an indexing error.
+// Warp 0 differs from warps 1-3 only in the epilogue (it issues the TMA stores).  tests/test_solver_gpu.py::
+// test_highrank_tcgen05_apply stays skipped (UCE_TEST_GEMM3X=1 runs it).  Round 2 starts here.
 #include "tc_apply_common.cuh"
 #include <cstdint>
 #include <cstdlib>

@@ -129,6 +129,10 @@ gemm3x_kernel(const LayerRef* __restrict__ layers, int n_layers, int mode, int K
         const uint32_t lane_base = tmem_base + ((uint32_t)(32 * warp) << 16);
         const uint32_t row_off = (uint32_t)(trow * 128);
         const uint32_t sw = (uint32_t)(trow & 7);
+        // The stores into tensor memory are waited for (tcgen05.wait::st) BEFORE the registers they read are written again.  A
+        // software-pipelined variant that left them in flight across the next chunk's split was measured neutral in time, and the
+        // same pattern in apply_gemm3x.cu intermittently garbled one chunk of one warp's rows: the source registers of an
+        // asynchronous tcgen05.st are not safe to overwrite before the wait, just as tcgen05.ld results are not safe to read.
         for (int c = 0; c < n_chunks; ++c) {
             const int r = c % NRAW, s = c % NSA;
             mbar_wait(bar_raw_full(r), (uint32_t)((c / NRAW) & 1));
@@ -140,24 +144,16 @@ gemm3x_kernel(const LayerRef* __restrict__ layers, int n_layers, int mode, int K
                 tf32_split(v.x, hi[4 * j], lo[4 * j]);         tf32_split(v.y, hi[4 * j + 1], lo[4 * j + 1]);
                 tf32_split(v.z, hi[4 * j + 2], lo[4 * j + 2]); tf32_split(v.w, hi[4 * j + 3], lo[4 * j + 3]);
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_raw_empty(r));
-            if (c > 0) {                                                      // publish the A stage of chunk c - 1
-                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-                fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bar_a_full((c - 1) % NSA));
-            }
-            mbar_wait(bar_a_empty(s), (uint32_t)(((c / NSA) & 1) ^ 1));
+            mbar_wait(bar_a_empty(s), (uint32_t)(((c / NSA) & 1) ^ 1));      // the MMAs that read this A stage have completed
             fence_after();
             const uint32_t ta = lane_base + A_COL0 + (uint32_t)(64 * s);
             tmem_st32(ta, hi);
             tmem_st32(ta + 32u, lo);
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            fence_before();
+            __syncwarp();
+            if (lane == 0) { mbar_arrive(bar_a_full(s)); mbar_arrive(bar_raw_empty(r)); }
         }
-        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-        fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_a_full((n_chunks - 1) % NSA));
         // ---- epilogue: accumulator (+ addend box) -> swizzled boxes -> TMA stores ----
         mbar_wait(bar_acc_full, 0);
         fence_after();

@@ -196,8 +196,8 @@ apply_tc2_kernel(const LayerRef* __restrict__ layers, int n_layers, int K, int R
             }
             tmem_st32(lane_base + (uint32_t)(rc * 32), v);
             tmem_st32(lane_base + (uint32_t)(R + rc * 32), lo);
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");      // before v / lo are written again (next rc)
         }
-        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_p_ready);

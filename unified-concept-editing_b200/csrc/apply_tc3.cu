@@ -204,8 +204,8 @@ apply_tc3_kernel(const LayerRef* __restrict__ layers, int n_layers, int K, int R
             for (int i = 0; i < 32; ++i) tf32_split(__uint_as_float(v[i]), v[i], lo[i]);
             tmem_st32(lane_base + col_p(g) + (uint32_t)(rc * 32), v);
             tmem_st32(lane_base + col_plo(g) + (uint32_t)(rc * 32), lo);
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");      // before v / lo are written again (next rc)
         }
-        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_p_ready);

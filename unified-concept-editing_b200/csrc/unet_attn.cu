@@ -215,6 +215,7 @@ __global__ void __launch_bounds__(FA_THREADS, 2) unet_attn_kernel(const __grid_c
 #pragma unroll
                     for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
                     tmem_st32(tmem_base + lane_base + FA_O_COL + (uint32_t)c0, o);
+                    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");      // o[] is loaded into again by the next iteration
                 }
             }
             l *= alpha;
@@ -244,6 +245,7 @@ __global__ void __launch_bounds__(FA_THREADS, 2) unet_attn_kernel(const __grid_c
                     pk[16 + i / 2] = *reinterpret_cast<const uint32_t*>(&pb);
                 }
                 tmem_st32(tmem_base + lane_base + FA_P_COL + 32u * hf, pk);
+                if (hf == 0) asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");     // pk[] is rewritten by the second half (the store after it is waited for below)
             }
             l += (s0 + s1) + (s2 + s3);
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");

@@ -20,18 +20,40 @@ from .concepts import embed_concepts, select_projections
 from .solver import EditSolver
 
 
+def _rank_world():
+    if torch.distributed.is_available() and torch.distributed.is_initialized():
+        return torch.distributed.get_rank(), torch.distributed.get_world_size()
+    return 0, 1
+
+
 def get_ratios(pipe, clip, uce_module_names, uce_weights, edit_concepts, debias_concepts, desired_ratios, max_diff,
                step_size=0.1, num_images_per_prompt=10, num_inference_steps=20, guidance_scale=7.5):
     """Mirror of uce_sd_debias.py:14-35 (``step_size`` is accepted and unused, as there)."""
     state = {name + ".weight": w for name, w in zip(uce_module_names, uce_weights)}
     pipe.unet.load_state_dict(state, strict=False)
-    direction_scale = []
-    for concept in edit_concepts:
+    # Multi-GPU (SURVEY.md 8e): the edit concepts are dealt round-robin to the ranks — each rank generates and classifies only its
+    # own — and ONE all-reduce of the [n_edit, n_debias] label-count matrix (plus the image counts) gives every rank the same ratios.
+    rank, world = _rank_world()
+    counts = np.zeros((len(edit_concepts), len(debias_concepts)), dtype=np.float64)
+    totals = np.zeros(len(edit_concepts), dtype=np.float64)
+    for i, concept in enumerate(edit_concepts):
+        if i % world != rank:
+            continue
         images = pipe(concept, num_inference_steps=num_inference_steps, num_images_per_prompt=num_images_per_prompt,
                       guidance_scale=guidance_scale).images
         results = clip(images, candidate_labels=debias_concepts)
         top1 = np.array([r[0]["label"] for r in results])
-        ratios = np.array([want - (np.sum(top1 == c) / len(top1)) for c, want in zip(debias_concepts, desired_ratios)])
+        counts[i] = [np.sum(top1 == c) for c in debias_concepts]
+        totals[i] = len(top1)
+    if world > 1:
+        dev = torch.device("cuda", torch.cuda.current_device()) if torch.distributed.get_backend() == "nccl" else torch.device("cpu")
+        t = torch.from_numpy(np.concatenate([counts.ravel(), totals])).to(dev)
+        torch.distributed.all_reduce(t)
+        t = t.cpu().numpy()
+        counts, totals = t[: counts.size].reshape(counts.shape), t[counts.size:]
+    direction_scale = []
+    for i in range(len(edit_concepts)):
+        ratios = np.array([want - (counts[i, j] / totals[i]) for j, want in zip(range(len(debias_concepts)), desired_ratios)])      # uce_sd_debias.py:29
         if max(ratios) < max_diff and abs(min(ratios)) < max_diff:
             ratios = 0 * ratios
         direction_scale.append(ratios)
@@ -77,7 +99,7 @@ def UCE(pipe, clip, edit_concepts, debias_concepts, preserve_concepts, edit_scal
         iterations += 1
     elapsed = time.time() - start
     state = {name + ".weight": w for name, w in zip(names, current)}
-    if save_dir is not None:
+    if save_dir is not None and _rank_world()[0] == 0:          # every rank holds the same weights: one writer
         from .artifact import save_artifact       # byte-identical to safetensors.torch.save_file (tests/test_artifact.py)
         os.makedirs(save_dir, exist_ok=True)
         save_artifact(state, os.path.join(save_dir, exp_name + ".safetensors"))

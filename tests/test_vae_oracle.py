@@ -1,0 +1,32 @@
+"""Oracle of the VAE decode (oracle/vae_oracle.py; groundwork for SURVEY.md 8(f) rank 1): parameter inventory of the published
+SD-1.x layout, shapes, fp64-vs-fp32 self-consistency.  CPU only."""
+import torch
+
+from oracle import vae_oracle as V
+from uce_b200.vae_spec import SD14_VAE, SD14_VAE_DECODER_PARAMS, decoder_param_count, decoder_param_shapes, tiny_vae_config
+
+
+def test_sd14_decoder_inventory():
+    assert decoder_param_count(SD14_VAE) == SD14_VAE_DECODER_PARAMS == 49_490_179
+    assert decoder_param_count(SD14_VAE, with_post_quant=True) == 49_490_179 + 20
+    s = decoder_param_shapes(SD14_VAE)
+    assert s["decoder.conv_in.weight"] == (512, 4, 3, 3) and s["decoder.conv_out.weight"] == (3, 128, 3, 3)
+    assert s["decoder.mid_block.attentions.0.to_q.weight"] == (512, 512)
+    assert s["decoder.up_blocks.2.resnets.0.conv_shortcut.weight"] == (256, 512, 1, 1)
+    assert "decoder.up_blocks.3.upsamplers.0.conv.weight" not in s and "decoder.up_blocks.2.upsamplers.0.conv.weight" in s
+    assert all(not k.endswith("time_emb_proj.weight") for k in s)
+
+
+def test_tiny_decode_shapes_and_precision():
+    cfg = tiny_vae_config()
+    P = V.random_weights(cfg, seed=1)
+    g = torch.Generator().manual_seed(0)
+    lat = torch.randn(2, 4, 6, 5, generator=g) * cfg["scaling_factor"]
+    taps = {}
+    y32 = V.decode(P, lat, cfg, taps=taps)
+    assert y32.shape == (2, 3, 12, 10) and taps["mid"].shape == (2, 32, 6, 5) and torch.isfinite(y32).all()
+    P64 = {k: v.double() for k, v in P.items()}
+    y64 = V.decode(P64, lat.double(), cfg)
+    assert float((y32.double() - y64).norm() / y64.norm()) < 1e-5
+    u8 = V.to_uint8(y32)
+    assert u8.dtype == torch.uint8 and u8.shape == (2, 12, 10, 3)

@@ -278,13 +278,14 @@ int apply_gemm3x_highrank(uce_ws* ws, const LayerRef* layers_dev, const LayerRef
     if (!apply_gemm3x_available(ws, n_layers)) { set_error("tcgen05 high-rank apply unavailable for K=%d rank_pad=%d dense=%d layers=%d", K, R, ws->dense, n_layers); return UCE_E_STATE; }
     for (int l = 0; l < n_layers; ++l)
         if (((uintptr_t)layers_host[l].w_old & 15) || ((uintptr_t)layers_host[l].w_new & 15)) { set_error("tcgen05 apply needs 16-byte aligned weights"); return UCE_E_ARG; }
-    static WMaps wmaps;
+    static thread_local WMaps wmaps;      // kept off the stack, one per host thread (handles are independent); copied into the launch by value
     int rc;
     for (int l = 0; l < n_layers; ++l) {
         if ((rc = make_map(&wmaps.in[l], layers_host[l].w_old, layers_host[l].d, K, 128))) return rc;
         if ((rc = make_map(&wmaps.out[l], layers_host[l].w_new, layers_host[l].d, K, 128))) return rc;
     }
-    static int configured = 0;
+    static thread_local int configured_dev[64] = {0};      // opt-in shared-memory size is a per-device function attribute
+    int& configured = configured_dev[ws->device & 63];
     for (int pass = 0; pass < 2; ++pass) {
         // pass 0: P[M, R] = W_old[M, K] . E[R, K]^T        pass 1: W_new[M, K] = W_old + P[M, R] . Qt[K, R]^T
         const int N = pass ? K : R, Kd = pass ? R : K;

@@ -572,7 +572,7 @@ int apply_tc_lowrank(uce_ws* ws, const LayerRef* layers_dev, const LayerRef* lay
     for (int l = 0; l < n_layers; ++l)
         if (((uintptr_t)layers_host[l].w_old & 15) || ((uintptr_t)layers_host[l].w_new & 15)) { set_error("tcgen05 apply needs 16-byte aligned weights"); return UCE_E_ARG; }
     TcMaps maps;
-    static TcWMaps wmaps;      // 20 KB: kept off the stack; copied into the launch by value
+    static thread_local TcWMaps wmaps;      // kept off the stack, one per host thread (handles are independent); copied into the launch by value
     int rc;
     if ((rc = make_map(&maps.e_hi, ws->E_hi, R, K, R))) return rc;
     if ((rc = make_map(&maps.e_lo, ws->E_lo, R, K, R))) return rc;
@@ -582,7 +582,8 @@ int apply_tc_lowrank(uce_ws* ws, const LayerRef* layers_dev, const LayerRef* lay
         if ((rc = make_map(&wmaps.w[l], layers_host[l].w_old, layers_host[l].d, K, TC_TILE_M))) return rc;
     const TcSmem L = tc_smem_layout(R);
     const int smem = L.total + 1024;   // slack for the manual 1024-byte alignment
-    static int configured = 0;
+    static thread_local int configured_dev[64] = {0};      // opt-in shared-memory size is a per-device function attribute
+    int& configured = configured_dev[ws->device & 63];
     if (configured < smem) {
         UCE_CUDA(cudaFuncSetAttribute(apply_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured = smem;

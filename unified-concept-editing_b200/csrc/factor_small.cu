@@ -499,7 +499,8 @@ int factor_small(uce_ws* ws, const float* C, const float* G, int n, int n_pres, 
     }
     // + 8 rows of slack: the last pivots of a diagonal block read L[j + k][j] for rows up to 38 (columns that do not exist, results unused)
     const size_t smem_c = ((size_t)(nt * (nt + 1) / 2) * FS_BLK + (size_t)n_pad * (n_edit | 1) + n_pad + FS_BLK + 8 * (FS_NB + 1)) * sizeof(double);
-    static size_t conf_c = 0;
+    static thread_local size_t conf_dev[64] = {0};        // per-device function attribute
+    size_t& conf_c = conf_dev[ws->device & 63];
     if (conf_c < smem_c) {
         UCE_CUDA(cudaFuncSetAttribute(chol_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
         conf_c = smem_c;

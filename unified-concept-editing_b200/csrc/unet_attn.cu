@@ -319,7 +319,10 @@ int attn_desc_make(AttnDesc* g, const void* q, const void* k, const void* vt, vo
 int attn_launch(const AttnDesc& g, cudaStream_t st) {
     const FaSmem L = fa_smem_layout(g.dhp);
     const int smem = L.total + 1024;
-    static int configured = 0;
+    int dev = 0;
+    cudaGetDevice(&dev);                                   // the opt-in shared-memory size is a per-device function attribute
+    static thread_local int configured_dev[64] = {0};
+    int& configured = configured_dev[dev & 63];
     if (configured < smem) {
         cudaError_t e = cudaFuncSetAttribute(unet_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return (int)e;

@@ -771,14 +771,17 @@ int gemm_choose_ksplit(const GemmDesc& g, int sm_count) {
 }
 
 int gemm_launch(const GemmDesc& g, cudaStream_t st) {
-    static bool configured = false;
+    int dev = 0;
+    cudaGetDevice(&dev);                                   // the opt-in shared-memory size is a per-device function attribute
+    static thread_local bool configured_dev[64] = {false}, configured2_dev[64] = {false};
+    bool& configured = configured_dev[dev & 63];
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(unet_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ug_smem_bytes(UG_MAX_STAGES, 1));
         if (e != cudaSuccess) return (int)e;
         configured = true;
     }
     if (g.pair) {
-        static bool configured2 = false;
+        bool& configured2 = configured2_dev[dev & 63];
         if (!configured2) {
             cudaError_t e = cudaFuncSetAttribute(unet_gemm_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
             if (e != cudaSuccess) return (int)e;

@@ -105,6 +105,20 @@ def test_sd_unet_c_abi_exports_every_declared_symbol():
     assert declared == set(unet.SD_SIGNATURES), declared ^ set(unet.SD_SIGNATURES)
 
 
+def test_sd_vae_c_abi_exports_every_declared_symbol():
+    from uce_b200 import _native, vae
+    hdr = open(os.path.join(ROOT, "include", "sd_vae_b200.h")).read()
+    declared = set(re.findall(r"\b(sd_vae_[a-z0-9_]+)\s*\(", hdr))
+    lib = ctypes.CDLL(_native.LIB_PATH)
+    for sym in declared:
+        assert hasattr(lib, sym), sym
+    assert declared == set(vae.VAE_SIGNATURES), declared ^ set(vae.VAE_SIGNATURES)
+    # the ctypes mirror of sd_vae_config has the header's layout (4 + 4 + 4 + 16 + 4 + 4 + 4 bytes, no padding)
+    assert ctypes.sizeof(vae.SDVaeConfig) == 40
+    cs = vae._cfg_struct(vae.SD14_VAE)
+    assert list(cs.block_out_channels) == [128, 256, 512, 512] and cs.n_levels == 4 and abs(cs.scaling_factor - 0.18215) < 1e-7
+
+
 def test_no_gpu_fails_loudly():
     from uce_b200.solver import EditSolver
     if torch.cuda.is_available():
@@ -116,6 +130,9 @@ def test_no_gpu_fails_loudly():
     from uce_b200.unet import UNetEngine
     with pytest.raises(RuntimeError):
         UNetEngine(device="cuda:0")
+    from uce_b200.vae import VAEDecoderEngine
+    with pytest.raises(RuntimeError):
+        VAEDecoderEngine(device="cuda:0")
 
 
 def _plan(sm_count, dims):
@@ -183,6 +200,6 @@ def test_public_headers_are_plain_c(tmp_path):
     if gcc is None:
         pytest.skip("gcc not available")
     src = tmp_path / "hdr.c"
-    src.write_text(f'#include "{ROOT}/include/uce_b200.h"\n#include "{ROOT}/include/sd_unet_b200.h"\nint main(void) {{ return 0; }}\n')
+    src.write_text(f'#include "{ROOT}/include/uce_b200.h"\n#include "{ROOT}/include/sd_unet_b200.h"\n#include "{ROOT}/include/sd_vae_b200.h"\nint main(void) {{ return 0; }}\n')
     r = subprocess.run([gcc, "-std=c11", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", str(src)], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr

@@ -1,0 +1,103 @@
+"""VAE decoder engine (include/sd_vae_b200.h) against the CPU restatement oracle/vae_oracle.py of
+``vae.decode(latents / scaling_factor)`` + the uint8 conversion (evalscripts/generate-images-sd.py:37-46,
+evalscripts/concept_algebra.py:126-135).
+
+OPT-IN in round 1: written after the round's GPU budget was spent, so it has not run on hardware yet.  It runs only with
+UCE_TEST_VAE=1 (scripts/gpu_r2_start.sh sets it); once green it loses the gate and generate_images() gets the engine by default.
+
+Tolerance: the engine stores activations and GEMM operands in bf16 (fp32 accumulation), like the reference's bf16 pipeline
+(generate-images-sd.py:76); the oracle runs in fp32 on the same bf16-rounded weights.  Relative RMS error of the decoder output
+<= 3e-2 (the U-Net engine's bar, tests/test_unet_gpu.py) and at most 2 % of the uint8 channels may differ by more than 3 levels."""
+import os
+
+import pytest
+import torch
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(os.environ.get("UCE_TEST_VAE") != "1", reason="opt-in until validated on hardware (UCE_TEST_VAE=1)")]
+
+TOL_REL_RMS = 3e-2
+
+
+def _bf16_weights(P):
+    keep_f32 = ("norm", "bias", "post_quant_conv", "conv_in", "conv_out")
+    return {k: (v if any(t in k for t in keep_f32) else v.to(torch.bfloat16).float()) for k, v in P.items()}
+
+
+def _run(cfg, batch, h, w, seed, taps=()):
+    from oracle import vae_oracle as VO
+    from uce_b200.vae import VAEDecoderEngine
+    if taps:
+        os.environ["UCE_VAE_TAPS"] = "1"
+    P = VO.random_weights(cfg, seed=seed)
+    eng = VAEDecoderEngine(cfg, batch=batch, h=h, w=w)
+    eng.load_state_dict(P)
+    eng.finalize()
+    g = torch.Generator().manual_seed(seed + 1)
+    lat = torch.randn((batch, 4, h, w), generator=g) * cfg["scaling_factor"] * 3.0
+    rgb, img = eng.decode(lat.cuda(), want_image=True)
+    torch.cuda.synchronize()
+    ref_taps = {}
+    ref = VO.decode(_bf16_weights(P), lat, cfg, taps=ref_taps)
+    got_taps = {t: eng.read_tap(t) for t in taps}
+    n = eng.launch_count()
+    eng.close()
+    os.environ.pop("UCE_VAE_TAPS", None)
+    return ref, VO.to_uint8(ref), img.cpu(), rgb.cpu(), ref_taps, got_taps, n
+
+
+def _rel_rms(a, b):
+    return float((a.double() - b.double()).pow(2).mean().sqrt() / b.double().pow(2).mean().sqrt())
+
+
+def _check(ref, ref8, img, rgb):
+    assert img.shape == ref.shape and rgb.shape == ref8.shape and rgb.dtype == torch.uint8
+    assert torch.isfinite(img).all()
+    assert _rel_rms(img, ref) <= TOL_REL_RMS, _rel_rms(img, ref)
+    d = (rgb.int() - ref8.int()).abs()
+    assert float((d > 3).float().mean()) <= 0.02, (float((d > 3).float().mean()), int(d.max()))
+    # the uint8 conversion itself is exact on the engine's own fp32 output (round half to even, like torch.round)
+    from oracle import vae_oracle as VO
+    assert torch.equal(rgb, VO.to_uint8(img))
+
+
+def test_tiny_decoder_matches_oracle_with_taps():
+    from uce_b200.vae_spec import tiny_vae_config
+    cfg = tiny_vae_config(ch=(64, 128), groups=8)
+    ref, ref8, img, rgb, rt, gt, n = _run(cfg, batch=2, h=16, w=16, seed=3, taps=("mid", "up.0", "up.1"))
+    for name in ("mid", "up.0", "up.1"):
+        assert gt[name].shape == rt[name].shape
+        assert _rel_rms(gt[name], rt[name]) <= TOL_REL_RMS, (name, _rel_rms(gt[name], rt[name]))
+    _check(ref, ref8, img, rgb)
+    assert n > 0
+
+
+@pytest.mark.parametrize("batch,h,w", [(1, 16, 16), (2, 8, 32)])
+def test_sd14_decoder_small_latents(batch, h, w):
+    """The real SD-1.4 decoder configuration (49 490 179 parameters) on small latents: every conv rectangle shape of the four levels."""
+    from uce_b200.vae_spec import SD14_VAE
+    ref, ref8, img, rgb, *_ = _run(SD14_VAE, batch=batch, h=h, w=w, seed=5)
+    _check(ref, ref8, img, rgb)
+
+
+def test_sd14_decoder_full_size_properties():
+    """64 x 64 latents -> 512 x 512 (BASELINE cfg5 image size): too slow for the CPU oracle per image at full size in a unit test, so
+    check size-independent properties — determinism, batch independence (image i does not depend on its batch mates)."""
+    from oracle import vae_oracle as VO
+    from uce_b200.vae import VAEDecoderEngine
+    from uce_b200.vae_spec import SD14_VAE
+    P = VO.random_weights(SD14_VAE, seed=7)
+    g = torch.Generator().manual_seed(8)
+    lat = (torch.randn((2, 4, 64, 64), generator=g) * SD14_VAE["scaling_factor"] * 3.0).cuda()
+    e2 = VAEDecoderEngine(SD14_VAE, batch=2, h=64, w=64); e2.load_state_dict(P); e2.finalize()
+    a = e2.decode(lat).clone(); b = e2.decode(lat).clone()
+    torch.cuda.synchronize()
+    assert a.shape == (2, 512, 512, 3)
+    diff = (a.int() - b.int()).abs()
+    assert int(diff.max()) <= 1 and float((diff > 0).float().mean()) < 1e-3      # GroupNorm statistics are accumulated with atomics
+    e2.close()
+    e1 = VAEDecoderEngine(SD14_VAE, batch=1, h=64, w=64); e1.load_state_dict(P); e1.finalize()
+    c = e1.decode(lat[1:2].contiguous()).clone()
+    torch.cuda.synchronize()
+    e1.close()
+    d = (c[0].int() - a[1].int()).abs()
+    assert float((d > 2).float().mean()) <= 0.01, (float((d > 2).float().mean()), int(d.max()))

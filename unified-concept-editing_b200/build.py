@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libuce_b200.so")
 SOURCES = ["uce_api.cu", "artifact.cu", "png.cu", "factor.cu", "factor_small.cu", "apply.cu", "apply_tc.cu", "apply_tc2.cu", "apply_tc3.cu", "apply_gemm3x.cu",
-           "unet_gemm.cu", "unet_ops.cu", "unet_attn.cu", "unet_engine.cu"]
+           "unet_gemm.cu", "unet_ops.cu", "unet_attn.cu", "unet_engine.cu", "vae_engine.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared", "-lcuda", "-lz"]
 
@@ -19,7 +19,7 @@ def _stale() -> bool:
     if not os.path.isfile(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", h) for h in ("uce_b200.h", "sd_unet_b200.h")]
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", h) for h in ("uce_b200.h", "sd_unet_b200.h", "sd_vae_b200.h")]
     return any(os.path.getmtime(d) > t for d in deps if os.path.isfile(d))
 
 

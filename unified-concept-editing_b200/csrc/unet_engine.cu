@@ -35,6 +35,8 @@ struct Weight { std::vector<long> shape; bf16* b = nullptr; float* f = nullptr; 
 int pad64(int x) { return (x + 63) / 64 * 64; }
 }  // namespace
 
+namespace uce { void sd_set_error(const char* msg) { snprintf(g_sd_err, sizeof(g_sd_err), "%s", msg); } }   // for vae_engine.cu: one sd_last_error() for both engines
+
 struct sd_unet {
     sd_unet_config cfg;
     int device, NB, H, W, sm_count = 148, n_split = 0, n_fused_attn = 0;

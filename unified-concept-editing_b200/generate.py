@@ -92,6 +92,7 @@ def generate_images(model_id, uce_model_path, prompts_path, save_path, exp_name=
     eng.load_state_dict(state, strict=False)
     eng.finalize()
     den = Denoiser(eng, num_images_per_prompt)
+    vae_eng = _vae_engine(pipe, num_images_per_prompt, latent, device) if os.environ.get("UCE_VAE_ENGINE") == "1" else None
 
     df = pd.read_csv(prompts_path)
     folder = f"{save_path}/{exp_name}"
@@ -106,10 +107,33 @@ def generate_images(model_id, uce_model_path, prompts_path, save_path, exp_name=
         gen = torch.Generator().manual_seed(int(seed))
         lat = torch.randn((num_images_per_prompt, 4, latent, latent), generator=gen, dtype=torch_dtype)   # CPU generator, pipe dtype
         out = den.run(lat, ctx, steps=num_inference_steps, guidance_scale=guidance_scale, scheduler=scheduler)
-        images = pipe.decode_latents_to_pil(out) if hasattr(pipe, "decode_latents_to_pil") else _decode(pipe, out, torch_dtype)
+        if vae_eng is not None:        # decoder on the B200 kernels (csrc/vae_engine.cu): uint8 [B, H, W, 3] leaves the device once
+            images = vae_eng.decode(out.contiguous()).cpu()
+        else:
+            images = pipe.decode_latents_to_pil(out) if hasattr(pipe, "decode_latents_to_pil") else _decode(pipe, out, torch_dtype)
         for num, im in enumerate(images):
             save_png(f"{folder}/{case_number}_{num}.png", im)          # lossless, parallel deflate (csrc/png.cu); same file name as :46
     eng.close()
+    if vae_eng is not None:
+        vae_eng.close()
+
+
+def _vae_engine(pipe, images, latent, device):
+    """VAE decoder engine loaded from ``pipe.vae`` (opt-in, UCE_VAE_ENGINE=1): SD-1.x decoder layout, read off the parameter shapes."""
+    from .vae import VAEDecoderEngine
+    from .vae_spec import SD14_VAE
+    state = {k: v for k, v in pipe.vae.state_dict().items()}
+    cfg = dict(SD14_VAE)
+    vcfg = getattr(pipe.vae, "config", None)
+    for key in ("block_out_channels", "layers_per_block", "scaling_factor"):
+        if vcfg is not None and getattr(vcfg, key, None) is not None:
+            cfg[key] = tuple(getattr(vcfg, key)) if key == "block_out_channels" else getattr(vcfg, key)
+    if vcfg is not None and getattr(vcfg, "norm_num_groups", None) is not None:
+        cfg["norm_groups"] = vcfg.norm_num_groups
+    ve = VAEDecoderEngine(cfg, batch=images, h=latent, w=latent, device=device)
+    ve.load_state_dict(state, strict=False)
+    ve.finalize()
+    return ve
 
 
 def _decode(pipe, latents, dtype):

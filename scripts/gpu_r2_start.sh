@@ -20,6 +20,8 @@ grep -E "profiled|timed region|e2e|denoise:" gpurun_out/bench.err | tee -a $S
 echo "== bench cfg4: SIMT high-rank apply vs apply impl 5" | tee -a $S
 timeout 300 python bench.py --workload cfg4 --no-denoise --no-cpu --steps 5 --warmup 3 > gpurun_out/bench_cfg4.json 2> gpurun_out/bench_cfg4.err; grep -E "profiled|timed region" gpurun_out/bench_cfg4.err | tee -a $S
 timeout 300 python bench.py --workload cfg4 --no-denoise --no-cpu --steps 5 --warmup 3 --apply-impl 5 > gpurun_out/bench_cfg4_g3.json 2> gpurun_out/bench_cfg4_g3.err; grep -E "profiled|timed region" gpurun_out/bench_cfg4_g3.err | tee -a $S
+echo "== EngineGenerator (debias generation rounds on the U-Net engine; opt-in test)" | tee -a $S
+UCE_TEST_ENGINE_GEN=1 timeout 300 python -m pytest tests/test_unet_gpu.py -m gpu -q -p no:cacheprovider -k engine_generator 2>&1 | tail -3 | tee -a $S
 echo "== VAE decoder engine (opt-in, never run on hardware in round 1): gated parity tests under a short timeout, then one 512x512 timing" | tee -a $S
 UCE_TEST_VAE=1 timeout 600 python -m pytest tests/test_vae_gpu.py -m gpu -q -p no:cacheprovider -x > gpurun_out/pytest_vae.log 2>&1; echo "rc=$?" | tee -a $S
 tail -15 gpurun_out/pytest_vae.log | tee -a $S

@@ -210,3 +210,38 @@ def test_context_cache_matches_per_call_context():
     out = eng.forward(x, 300.0, None).cpu()
     assert _rel(out, ref) < 5e-2 and _rel(out, per_call_b.cpu()) > 1e-3
     eng.close()
+
+
+@pytest.mark.skipif(os.environ.get("UCE_TEST_ENGINE_GEN") != "1", reason="written after the round's GPU budget was spent: opt-in until it has run on hardware (UCE_TEST_ENGINE_GEN=1)")
+def test_engine_generator_matches_oracle_loop_and_follows_weight_overlays():
+    """EngineGenerator (the generation rounds of the debias edit's get_ratios(), trainscripts/uce_sd_debias.py:14-26, on the U-Net engine):
+    same oracle loop and tolerance as generate_images above; loading edited attn2 weights changes what the next call generates, loading
+    the originals back restores it (every get_ratios call starts with such an overlay, :17-20)."""
+    import numpy as np
+    from oracle.fake_pipe import FakeGenPipe
+    from uce_b200.generate import EngineGenerator
+    cfg, P = _tiny()
+    pipe = FakeGenPipe(cfg, P, latent_size=16)
+    gen = EngineGenerator(pipe, 2, device="cuda:0", unet_config=cfg)
+    key = "down_blocks.0.attentions.0.transformer_blocks.0.attn2.to_k.weight"
+
+    def run(seed):
+        out = gen("a doctor", num_inference_steps=4, num_images_per_prompt=2, guidance_scale=2.0, generator=torch.Generator().manual_seed(seed))
+        return np.stack([np.asarray(im).astype(np.int32) for im in out.images])
+
+    def oracle(weights, seed):
+        text, uncond = pipe.encode_prompt("a doctor", num_images_per_prompt=2)
+        lat = torch.randn((2, 4, 16, 16), generator=torch.Generator().manual_seed(seed), dtype=torch.bfloat16).float()
+        return FakeGenPipe.latents_to_uint8(U.denoise_loop(weights, lat, torch.cat([uncond, text]), steps=4, guidance_scale=2.0, cfg=cfg)).astype(np.int32)
+
+    base = run(3)
+    assert np.abs(base - oracle(P, 3)).mean() < 8.0
+    gen.unet.load_state_dict({key: P[key] * -1.0}, strict=False)
+    P2 = dict(P); P2[key] = P[key] * -1.0
+    edited = run(3)
+    assert np.abs(edited - oracle(P2, 3)).mean() < 8.0
+    assert np.abs(edited - base).mean() > 0.0                      # the overlay reached the kernels (cached context K / V^T recomputed)
+    gen.unet.load_state_dict({key: P[key]}, strict=False)
+    again = run(3)
+    assert np.abs(again - base).mean() < 1.0                       # back to the original weights: equal up to the engine's run-to-run noise
+    gen.close()

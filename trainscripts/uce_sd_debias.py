@@ -32,6 +32,9 @@ def build_parser():
     p = argparse.ArgumentParser(prog="TrainUCE", description="UCE for erasing concepts in Stable Diffusion")
     for name, kw in FLAGS:
         p.add_argument("--" + name, **kw)
+    # not in the reference: which denoise loop the generation rounds of get_ratios() use
+    p.add_argument("--generator", type=str, default="pipe", choices=["pipe", "engine"],
+                   help="'pipe': the diffusers pipeline, as the reference does; 'engine': the B200 U-Net engine (default: pipe)")
     return p
 
 
@@ -61,7 +64,8 @@ def main(argv=None):
     from uce_b200.debias import UCE
     UCE(pipe, clip, edit, debias, preserve, args.edit_scale, args.preserve_scale, args.lamb, args.save_dir, exp_name,
         args.max_diff, args.step_size, args.num_images_per_prompt, args.num_inference_steps, args.guidance_scale,
-        max_iterations=args.max_iterations, desired_ratios=args.desired_ratios, device=args.device)
+        max_iterations=args.max_iterations, desired_ratios=args.desired_ratios, device=args.device,
+        generator="engine" if args.generator == "engine" else None)
 
 
 if __name__ == "__main__":

@@ -62,7 +62,13 @@ def get_ratios(pipe, clip, uce_module_names, uce_weights, edit_concepts, debias_
 
 def UCE(pipe, clip, edit_concepts, debias_concepts, preserve_concepts, edit_scale, preserve_scale, lamb, save_dir, exp_name,
         max_diff, step_size, num_images_per_prompt, num_inference_steps, guidance_scale,
-        max_iterations=30, desired_ratios=(0.5, 0.5), device="cuda:0", solver: EditSolver | None = None, verbose=True):
+        max_iterations=30, desired_ratios=(0.5, 0.5), device="cuda:0", solver: EditSolver | None = None, verbose=True,
+        generator=None):
+    """``generator``: what ``get_ratios`` generates with.  None = the caller's ``pipe`` (the reference's behaviour, uce_sd_debias.py:22-26);
+    "engine" (or UCE_DEBIAS_ENGINE=1) = an ``EngineGenerator`` built from ``pipe`` — the denoise loop of every generation round on the B200
+    U-Net engine; or any object with the same face (``.unet.load_state_dict``, ``__call__(...).images``)."""
+    if generator is None and os.environ.get("UCE_DEBIAS_ENGINE") == "1":
+        generator = "engine"
     projections = select_projections(pipe.unet)
     names = [n for n, _ in projections]
     dev = torch.device(device)
@@ -79,12 +85,19 @@ def UCE(pipe, clip, edit_concepts, debias_concepts, preserve_concepts, edit_scal
         solver = EditSolver(K, max(16, C.shape[0]), dev)
 
     pipe = pipe.to(torch.bfloat16)          # generation dtype (uce_sd_debias.py:90); the solve stays fp32
+    own_gen = False
+    if isinstance(generator, str):
+        if generator != "engine":
+            raise ValueError(f"generator must be None, 'engine' or a generator object, got {generator!r}")
+        from .generate import EngineGenerator
+        generator, own_gen = EngineGenerator(pipe, num_images_per_prompt, device=device), True
+    gen = generator if generator is not None else pipe
     current = [w.clone() for w in w_old]    # weights the next generation round uses (:45-46)
     A = np.zeros((len(edit_concepts), len(debias_concepts)), dtype=np.float64)
     start = time.time()
     iterations = 0
     for iteration in range(max_iterations):
-        direction_scale = get_ratios(pipe=pipe, clip=clip, uce_module_names=names, uce_weights=current,
+        direction_scale = get_ratios(pipe=gen, clip=clip, uce_module_names=names, uce_weights=current,
                                      edit_concepts=edit_concepts, debias_concepts=debias_concepts,
                                      desired_ratios=desired_ratios, max_diff=max_diff, step_size=step_size,
                                      num_images_per_prompt=num_images_per_prompt,
@@ -105,6 +118,8 @@ def UCE(pipe, clip, edit_concepts, debias_concepts, preserve_concepts, edit_scal
         save_artifact(state, os.path.join(save_dir, exp_name + ".safetensors"))
     if own:
         solver.close()
+    if own_gen:
+        generator.close()
     if verbose:
         print(f"\n\nDebiased concepts using UCE\nModel edited in {elapsed} seconds\n")
     return state

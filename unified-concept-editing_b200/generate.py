@@ -58,6 +58,72 @@ class Denoiser:
         return self.x
 
 
+class _EngineWeights:
+    """The ``pipe.unet`` face of EngineGenerator: ``load_state_dict(state, strict=False)`` overwrites engine parameters in place."""
+
+    def __init__(self, engine):
+        self._eng = engine
+
+    def load_state_dict(self, state, strict=False):
+        self._eng.load_state_dict(state, strict=strict)
+
+
+class _Images:
+    def __init__(self, images):
+        self.images = images
+
+
+class EngineGenerator:
+    """The part of a StableDiffusionPipeline that ``get_ratios`` of the debias edit uses (trainscripts/uce_sd_debias.py:14-26) with the
+    denoise loop on the B200 engine:  ``gen.unet.load_state_dict(edited_weights, strict=False)`` then
+    ``gen(concept, num_inference_steps=, num_images_per_prompt=, guidance_scale=).images``.
+    Text encoding stays with the wrapped ``pipe`` (``encode_prompt``); VAE decode too unless a decoder engine is given.
+    ``engine`` / ``denoiser`` can be injected (tests); otherwise a UNetEngine is built from ``pipe.unet.state_dict()``."""
+
+    def __init__(self, pipe, num_images_per_prompt, device="cuda:0", torch_dtype=torch.bfloat16, scheduler="pndm", unet_config=SD14,
+                 engine=None, denoiser=None, vae_engine=None):
+        self.pipe, self.B, self.device, self.dtype, self.scheduler = pipe, int(num_images_per_prompt), device, torch_dtype, scheduler
+        self.latent = getattr(pipe, "latent_size", 64)
+        self._own = engine is None
+        if engine is None:
+            engine = UNetEngine(unet_config, batch=2 * self.B, H=self.latent, W=self.latent, device=device)
+            engine.load_state_dict({k: v for k, v in pipe.unet.state_dict().items()}, strict=False)
+            engine.finalize()
+        self.eng = engine
+        self.den = denoiser if denoiser is not None else Denoiser(engine, self.B)
+        self.vae_eng = vae_engine
+        self.unet = _EngineWeights(engine)
+        self.calls = 0
+
+    def to(self, *a, **k):                 # uce_sd_debias.py:90 moves the pipeline to bf16: the engine already computes in bf16
+        return self
+
+    def set_progress_bar_config(self, **k):
+        pass
+
+    def __call__(self, prompt, num_inference_steps=50, num_images_per_prompt=None, guidance_scale=7.5, generator=None, **kw):
+        n = self.B if num_images_per_prompt is None else int(num_images_per_prompt)
+        if n != self.B:
+            raise ValueError(f"this generator was built for {self.B} images per prompt, got {n}")
+        text, uncond = self.pipe.encode_prompt(prompt=str(prompt), device=self.device, num_images_per_prompt=n,
+                                               do_classifier_free_guidance=True)[:2]
+        ctx = torch.cat([uncond, text]).to(torch.float32)
+        lat = torch.randn((n, 4, self.latent, self.latent), generator=generator, dtype=self.dtype)     # CPU RNG, pipeline dtype
+        out = self.den.run(lat, ctx, steps=num_inference_steps, guidance_scale=guidance_scale, scheduler=self.scheduler)
+        if self.vae_eng is not None:
+            images = list(self.vae_eng.decode(out.contiguous()).cpu().numpy())
+        elif hasattr(self.pipe, "decode_latents_to_pil"):
+            images = self.pipe.decode_latents_to_pil(out)
+        else:
+            images = _decode(self.pipe, out, self.dtype)
+        self.calls += 1
+        return _Images(images)
+
+    def close(self):
+        if self._own:
+            self.eng.close()
+
+
 def _rank_world():
     if torch.distributed.is_available() and torch.distributed.is_initialized():
         return torch.distributed.get_rank(), torch.distributed.get_world_size()

@@ -51,6 +51,10 @@ int sd_vae_finalize(sd_vae *v);
  *   rgb8[batch,H,W,3]  uint8 = round(clamp(image / 2 + 0.5, 0, 1) * 255), ties to even    (optional, may be NULL) */
 int sd_vae_decode(sd_vae *v, const float *latents, float *image, unsigned char *rgb8, void *stream);
 
+/* Parameter inventory of a configuration (host-only, no device needed): returns the number of parameters; with index >= 0 also
+ * writes the index-th (sorted by name) parameter's diffusers name into name[cap] and its shape. */
+int sd_vae_inventory(const sd_vae_config *cfg, int index, char *name, size_t cap, long shape[4], int *ndim);
+
 /* Introspection / tests: kernels one decode enqueues; copy a named intermediate (mid, up.i) to HOST as fp32 NCHW. */
 int sd_vae_launch_count(sd_vae *v);
 int sd_vae_read_tap(sd_vae *v, const char *name, float *out, size_t cap, int dims[4]);

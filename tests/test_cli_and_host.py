@@ -119,6 +119,24 @@ def test_sd_vae_c_abi_exports_every_declared_symbol():
     assert list(cs.block_out_channels) == [128, 256, 512, 512] and cs.n_levels == 4 and abs(cs.scaling_factor - 0.18215) < 1e-7
 
 
+def test_sd_vae_engine_inventory_is_the_diffusers_decoder_layout():
+    """The parameter names / shapes the native decoder engine expects (host-only query) are exactly the spec the CPU oracle is built
+    on — the SD-1.x `pipe.vae` decoder layout with its 49 490 179 + 20 parameters — so a real checkpoint loads by name."""
+    from uce_b200 import vae
+    from uce_b200.vae_spec import SD14_VAE, SD14_VAE_DECODER_PARAMS, decoder_param_shapes, tiny_vae_config
+    for cfg in (SD14_VAE, tiny_vae_config(ch=(64, 128), groups=8), tiny_vae_config(ch=(64, 64, 128), groups=8)):
+        inv = vae.engine_inventory(cfg)
+        want = {k: tuple(v) for k, v in decoder_param_shapes(cfg).items()}
+        assert inv == want, set(inv) ^ set(want)
+    n = 0
+    for shp in vae.engine_inventory(SD14_VAE).values():
+        k = 1
+        for d in shp:
+            k *= d
+        n += k
+    assert n == SD14_VAE_DECODER_PARAMS + 20
+
+
 def test_no_gpu_fails_loudly():
     from uce_b200.solver import EditSolver
     if torch.cuda.is_available():

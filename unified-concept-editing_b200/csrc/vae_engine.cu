@@ -15,7 +15,9 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <functional>
+#include <iterator>
 #include <map>
 #include <string>
 #include <vector>
@@ -449,6 +451,23 @@ int sd_vae_decode(sd_vae* v, const float* latents, float* image, unsigned char* 
 }
 
 int sd_vae_launch_count(sd_vae* v) { return v ? (int)v->ops.size() : SD_E_ARG; }
+
+int sd_vae_inventory(const sd_vae_config* cfg, int index, char* name, size_t cap, long shape[4], int* ndim) {
+    if (!cfg || cfg->n_levels < 1 || cfg->n_levels > 4 || cfg->layers_per_block < 1) { vae_err("sd_vae_inventory: bad argument"); return SD_E_ARG; }
+    sd_vae tmp;                             // host-only: the inventory depends on the configuration alone
+    tmp.cfg = *cfg;
+    build_inventory(&tmp);
+    const int n = (int)tmp.expected.size();
+    if (index < 0) return n;
+    if (index >= n || !name || !shape || !ndim) { vae_err("sd_vae_inventory: bad index / output"); return SD_E_ARG; }
+    auto it = tmp.expected.begin();
+    std::advance(it, index);
+    if (it->first.size() + 1 > cap) { vae_err("sd_vae_inventory: name buffer too small"); return SD_E_ARG; }
+    memcpy(name, it->first.c_str(), it->first.size() + 1);
+    *ndim = (int)it->second.size();
+    for (int i = 0; i < *ndim; ++i) shape[i] = it->second[i];
+    return n;
+}
 
 int sd_vae_read_tap(sd_vae* v, const char* name, float* out, size_t cap, int dims[4]) {
     if (!v || !name || !out) return SD_E_ARG;

@@ -27,6 +27,7 @@ VAE_SIGNATURES = {
     "sd_vae_finalize": (C.c_int, [C.c_void_p]),
     "sd_vae_decode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "sd_vae_launch_count": (C.c_int, [C.c_void_p]),
+    "sd_vae_inventory": (C.c_int, [C.POINTER(SDVaeConfig), C.c_int, C.c_char_p, C.c_size_t, C.POINTER(C.c_long), C.POINTER(C.c_int)]),
     "sd_vae_read_tap": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_int)]),
 }
 _bound = False
@@ -52,6 +53,22 @@ def _cfg_struct(cfg) -> SDVaeConfig:
     ch = list(cfg["block_out_channels"])
     return SDVaeConfig(cfg["latent_channels"], cfg["out_channels"], len(ch), (C.c_int * 4)(*(ch + [0] * 4)[:4]), cfg["layers_per_block"],
                        cfg["norm_groups"], float(cfg["scaling_factor"]))
+
+
+def engine_inventory(cfg=SD14_VAE) -> dict:
+    """{name: shape} of the parameters the native engine expects for ``cfg`` (host-only; no GPU needed)."""
+    cs = _cfg_struct(cfg)
+    n = _lib().sd_vae_inventory(C.byref(cs), -1, None, 0, None, None)
+    if n < 0:
+        _check(n)
+    out = {}
+    buf, shp, nd = C.create_string_buffer(256), (C.c_long * 4)(), C.c_int()
+    for i in range(n):
+        rc = _lib().sd_vae_inventory(C.byref(cs), i, buf, 256, shp, C.byref(nd))
+        if rc < 0:
+            _check(rc)
+        out[buf.value.decode()] = tuple(shp[: nd.value])
+    return out
 
 
 class VAEDecoderEngine:

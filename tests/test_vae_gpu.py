@@ -7,7 +7,8 @@ UCE_TEST_VAE=1 (scripts/gpu_r2_start.sh sets it); once green it loses the gate a
 
 Tolerance: the engine stores activations and GEMM operands in bf16 (fp32 accumulation), like the reference's bf16 pipeline
 (generate-images-sd.py:76); the oracle runs in fp32 on the same bf16-rounded weights.  Relative RMS error of the decoder output
-<= 3e-2 (the U-Net engine's bar, tests/test_unet_gpu.py) and at most 2 % of the uint8 channels may differ by more than 3 levels."""
+<= 5e-2 (the U-Net engine's bar for bf16 storage, tests/test_unet_gpu.py) and at most 2 % of the uint8 channels may differ by more
+than 3 levels."""
 import os
 
 import pytest
@@ -15,7 +16,7 @@ import torch
 
 pytestmark = [pytest.mark.gpu, pytest.mark.skipif(os.environ.get("UCE_TEST_VAE") != "1", reason="opt-in until validated on hardware (UCE_TEST_VAE=1)")]
 
-TOL_REL_RMS = 3e-2
+TOL_REL_RMS = 5e-2
 
 
 def _bf16_weights(P):

@@ -146,6 +146,7 @@ gemm3x_kernel(const LayerRef* __restrict__ layers, int n_layers, int mode, int K
             }
             mbar_wait(bar_a_empty(s), (uint32_t)(((c / NSA) & 1) ^ 1));      // the MMAs that read this A stage have completed
             fence_after();
+            __syncwarp();                                                    // lane 0 took the `if (lane == 0)` arrive path last iteration: .sync.aligned needs the warp converged
             const uint32_t ta = lane_base + A_COL0 + (uint32_t)(64 * s);
             tmem_st32(ta, hi);
             tmem_st32(ta + 32u, lo);

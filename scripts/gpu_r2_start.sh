@@ -26,3 +26,7 @@ echo "== VAE decoder engine (opt-in, never run on hardware in round 1): gated pa
 UCE_TEST_VAE=1 timeout 600 python -m pytest tests/test_vae_gpu.py -m gpu -q -p no:cacheprovider -x > gpurun_out/pytest_vae.log 2>&1; echo "rc=$?" | tee -a $S
 tail -15 gpurun_out/pytest_vae.log | tee -a $S
 timeout 300 python scripts/vae_probe.py 2>&1 | tail -6 | tee -a $S
+echo "== host path: number of copy/compute groups (default 8)" | tee -a $S
+for g in 4 8 12 16 32; do
+  UCE_HOST_GROUPS=$g timeout 200 python bench.py --no-denoise --no-cpu --steps 20 --warmup 5 2>&1 >/dev/null | grep -E "e2e" | sed "s/^/groups $g: /" | tee -a $S
+done

@@ -251,7 +251,10 @@ int uce_edit_host_f32(uce_ws* ws, const float* C, const float* G, const float* s
         ws->hostpath_W_cap = total;
     }
     // groups of layers of roughly equal bytes: enough groups to overlap H2D(g+1) / apply(g) / D2H(g-1)
-    const int target_groups = std::min(n_layers, 8);
+    // (8 by default; UCE_HOST_GROUPS overrides it for measurements: more groups shorten the pipeline's fill and drain — the first upload
+    // and the last download run alone on the link — at the price of more, smaller apply launches)
+    int target_groups = std::min(n_layers, 8);
+    if (const char* e = getenv("UCE_HOST_GROUPS")) { const int t = atoi(e); if (t >= 1) target_groups = std::min(n_layers, t); }
     const size_t per_group = (total + target_groups - 1) / target_groups;
     std::vector<int> gbeg{0};
     { size_t acc = 0; for (int l = 0; l < n_layers; ++l) { acc += (size_t)d[l] * K; if (acc >= per_group && l + 1 < n_layers) { gbeg.push_back(l + 1); acc = 0; } } }

@@ -139,9 +139,10 @@ def rows_for_rank(df, from_case, till_case, rank, world):
 
 def generate_images(model_id, uce_model_path, prompts_path, save_path, exp_name="test", device="cuda:0", torch_dtype=torch.bfloat16,
                     guidance_scale=7.5, num_inference_steps=100, num_images_per_prompt=10, from_case=0, till_case=1000000,
-                    pipe=None, scheduler="pndm", unet_config=SD14):
+                    pipe=None, scheduler="pndm", unet_config=SD14, engine=None, denoiser=None):
     """Same signature and outputs as the reference (``{save_path}/{exp_name}/{case_number}_{i}.png``); ``pipe`` lets a
-    caller inject an already-loaded (or synthetic) pipeline object."""
+    caller inject an already-loaded (or synthetic) pipeline object, ``engine`` / ``denoiser`` an already-built U-Net engine and its
+    denoise loop (tests/test_generate_golden.py drives the row loop on CPU with stand-ins)."""
     import pandas as pd
     if pipe is None:
         try:
@@ -154,10 +155,15 @@ def generate_images(model_id, uce_model_path, prompts_path, save_path, exp_name=
         from .artifact import load_artifact
         state.update(load_artifact(uce_model_path))      # load_state_dict(strict=False) semantics (generate-images-sd.py:17-19)
     latent = getattr(pipe, "latent_size", 64)
-    eng = UNetEngine(unet_config, batch=2 * num_images_per_prompt, H=latent, W=latent, device=device)
-    eng.load_state_dict(state, strict=False)
-    eng.finalize()
-    den = Denoiser(eng, num_images_per_prompt)
+    own_engine = engine is None
+    if own_engine:
+        eng = UNetEngine(unet_config, batch=2 * num_images_per_prompt, H=latent, W=latent, device=device)
+        eng.load_state_dict(state, strict=False)
+        eng.finalize()
+    else:
+        eng = engine
+        eng.load_state_dict(state, strict=False)
+    den = denoiser if denoiser is not None else Denoiser(eng, num_images_per_prompt)
     vae_eng = _vae_engine(pipe, num_images_per_prompt, latent, device) if os.environ.get("UCE_VAE_ENGINE") == "1" else None
 
     df = pd.read_csv(prompts_path)
@@ -179,7 +185,8 @@ def generate_images(model_id, uce_model_path, prompts_path, save_path, exp_name=
             images = pipe.decode_latents_to_pil(out) if hasattr(pipe, "decode_latents_to_pil") else _decode(pipe, out, torch_dtype)
         for num, im in enumerate(images):
             save_png(f"{folder}/{case_number}_{num}.png", im)          # lossless, parallel deflate (csrc/png.cu); same file name as :46
-    eng.close()
+    if own_engine:
+        eng.close()
     if vae_eng is not None:
         vae_eng.close()
 

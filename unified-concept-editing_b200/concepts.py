@@ -33,8 +33,45 @@ def concept_row(pipe, prompt: str, device) -> torch.Tensor:
     return emb[0][0, last, :].to(torch.float32)
 
 
-def embed_concepts(pipe, prompts, device) -> dict:
-    """prompt -> [K] row, each distinct prompt encoded once (uce_sd_erase.py:26-28)."""
+def can_batch_encode(pipe) -> bool:
+    """True for single-text-encoder pipelines (SD-1.x / 2.x layout) whose tokenizer and encoder can be called directly."""
+    return (getattr(pipe, "text_encoder", None) is not None and getattr(pipe, "text_encoder_2", None) is None
+            and callable(getattr(pipe, "tokenizer", None)))
+
+
+def embed_concepts_batched(pipe, prompts, device, batch_size: int = 128) -> dict:
+    """Same rows as ``embed_concepts`` from BATCHED text-encoder calls: the reference encodes one prompt per forward
+    (uce_sd_erase.py:26-42), which dominates an edit of hundreds of concepts.  What encode_prompt does for a plain
+    SD-1.x / 2.x pipeline is restated here — tokenizer with max_length padding and truncation, ``text_encoder(ids)[0]`` (the attention mask
+    is passed only if the encoder's config asks for it), no clip_skip / LoRA scale / textual inversion — and the kept row is the same
+    ``attention_mask.sum() - 2``.  Rows agree with the one-by-one path to fp32 rounding (tests/test_concepts_batched.py)."""
+    uniq = []
+    for p in prompts:
+        if p not in uniq:
+            uniq.append(p)
+    rows = {}
+    tk = pipe.tokenizer
+    use_mask = bool(getattr(getattr(pipe.text_encoder, "config", None), "use_attention_mask", False))
+    for i in range(0, len(uniq), batch_size):
+        chunk = uniq[i:i + batch_size]
+        tok = tk(chunk, padding="max_length", max_length=tk.model_max_length, truncation=True, return_tensors="pt")
+        ids, mask = tok["input_ids"], tok["attention_mask"]
+        out = pipe.text_encoder(ids.to(device), attention_mask=mask.to(device) if use_mask else None)[0]
+        last = mask.sum(dim=1) - 2
+        for j, p in enumerate(chunk):
+            rows[p] = out[j, int(last[j]), :].to(torch.float32)
+    return rows
+
+
+def embed_concepts(pipe, prompts, device, batched: bool | None = None) -> dict:
+    """prompt -> [K] row, each distinct prompt encoded once (uce_sd_erase.py:26-28).  ``batched`` (default: the UCE_BATCHED_ENCODE=1
+    environment switch) routes eligible pipelines through ``embed_concepts_batched``; otherwise one encode_prompt call per prompt, as
+    the reference does."""
+    import os
+    if batched is None:
+        batched = os.environ.get("UCE_BATCHED_ENCODE") == "1"
+    if batched and can_batch_encode(pipe):
+        return embed_concepts_batched(pipe, prompts, device)
     rows = {}
     for p in prompts:
         if p not in rows:

@@ -50,6 +50,32 @@ def _reference_get_ratios(desired, max_diff):
     return np.array(out)
 
 
+def test_get_ratios_matches_the_reference_function():
+    """tests/golden/get_ratios.json: the reference's OWN get_ratios (uce_sd_debias.py:14-35) called with the keyword form of its caller
+    (:96-107) on a recording pipeline and scripted labels (oracle/make_ratios_golden.py).  Ours, through the same call: same weights
+    loaded into pipe.unet (keys, strict=False), same pipe(...) calls with the same keyword arguments, same float64 direction scales."""
+    import json
+    from oracle.make_ratios_golden import RecordingPipe, modules, scripted_clip
+    from uce_b200.debias import get_ratios
+    gold = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "get_ratios.json")))
+    for g in gold:
+        case = g["case"]
+        pipe = RecordingPipe()
+        names, mods = modules()
+        r = get_ratios(pipe=pipe, clip=scripted_clip(case["labels"]), uce_module_names=names, uce_modules=mods, edit_concepts=g["edit"],
+                       debias_concepts=case["debias"], desired_ratios=case["desired"], max_diff=case["max_diff"], step_size=0.1,
+                       num_images_per_prompt=case["n_img"], num_inference_steps=7, guidance_scale=6.5)
+        assert pipe.loaded == g["loaded"]
+        assert pipe.calls == g["calls"]
+        assert type(r).__name__ == g["result_type"] and str(r.dtype) == g["result_dtype"]
+        assert np.array_equal(r, np.array(g["result"]))                      # bit-equal, signed zeros of the dead-band aside
+        # the weight tensors themselves are accepted in place of the modules (what debias.UCE passes), positionally as well
+        pipe2 = RecordingPipe()
+        r2 = get_ratios(pipe2, scripted_clip(case["labels"]), names, [m.weight for m in mods], g["edit"], case["debias"], case["desired"],
+                        case["max_diff"], 0.1, case["n_img"], 7, 6.5)
+        assert np.array_equal(r2, r) and pipe2.loaded == g["loaded"] and pipe2.calls == g["calls"]
+
+
 def test_get_ratios_single_process_matches_reference_arithmetic():
     from uce_b200.debias import get_ratios
     for desired, max_diff in [((0.5, 0.5), 0.05), ((0.3, 0.7), 0.15), ((0.5, 0.5), 0.35)]:

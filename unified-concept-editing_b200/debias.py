@@ -26,10 +26,16 @@ def _rank_world():
     return 0, 1
 
 
-def get_ratios(pipe, clip, uce_module_names, uce_weights, edit_concepts, debias_concepts, desired_ratios, max_diff,
-               step_size=0.1, num_images_per_prompt=10, num_inference_steps=20, guidance_scale=7.5):
-    """Mirror of uce_sd_debias.py:14-35 (``step_size`` is accepted and unused, as there)."""
-    state = {name + ".weight": w for name, w in zip(uce_module_names, uce_weights)}
+def get_ratios(pipe, clip, uce_module_names, uce_modules=None, edit_concepts=(), debias_concepts=(), desired_ratios=(), max_diff=0.05,
+               step_size=0.1, num_images_per_prompt=10, num_inference_steps=20, guidance_scale=7.5, uce_weights=None):
+    """Mirror of uce_sd_debias.py:14-35, same parameter names and order (``step_size`` is accepted and unused, as there).
+    ``uce_modules``: the edited projections as the reference passes them (modules with a ``.weight``, :16-17) or their weight tensors;
+    ``uce_weights`` is a keyword alias for the latter."""
+    if uce_modules is None:
+        uce_modules = uce_weights
+    if uce_modules is None:
+        raise TypeError("get_ratios needs uce_modules (or uce_weights)")
+    state = {name + ".weight": (m.weight if hasattr(m, "weight") else m) for name, m in zip(uce_module_names, uce_modules)}
     pipe.unet.load_state_dict(state, strict=False)
     # Multi-GPU (SURVEY.md 8e): the edit concepts are dealt round-robin to the ranks — each rank generates and classifies only its
     # own — and ONE all-reduce of the [n_edit, n_debias] label-count matrix (plus the image counts) gives every rank the same ratios.
@@ -97,7 +103,7 @@ def UCE(pipe, clip, edit_concepts, debias_concepts, preserve_concepts, edit_scal
     start = time.time()
     iterations = 0
     for iteration in range(max_iterations):
-        direction_scale = get_ratios(pipe=gen, clip=clip, uce_module_names=names, uce_weights=current,
+        direction_scale = get_ratios(pipe=gen, clip=clip, uce_module_names=names, uce_modules=current,
                                      edit_concepts=edit_concepts, debias_concepts=debias_concepts,
                                      desired_ratios=desired_ratios, max_diff=max_diff, step_size=step_size,
                                      num_images_per_prompt=num_images_per_prompt,

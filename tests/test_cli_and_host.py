@@ -221,3 +221,27 @@ def test_public_headers_are_plain_c(tmp_path):
     src.write_text(f'#include "{ROOT}/include/uce_b200.h"\n#include "{ROOT}/include/sd_unet_b200.h"\n#include "{ROOT}/include/sd_vae_b200.h"\nint main(void) {{ return 0; }}\n')
     r = subprocess.run([gcc, "-std=c11", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", str(src)], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
+
+
+def test_python_function_seam_has_the_reference_signatures():
+    """SURVEY.md 8b 'Python fn' seam: tests/golden/signatures.json holds the parameter names, order and defaults of the reference's
+    UCE() / get_ratios() / generate_images() (read with inspect from the real modules by oracle/make_signature_golden.py).  Our mirrors
+    take the same parameters in the same positions with the same defaults; anything we add comes after them and is optional."""
+    import inspect
+    import json
+    from uce_b200 import debias, erase, generate
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "signatures.json")))
+    ours = {"erase.UCE": erase.UCE, "debias.UCE": debias.UCE, "debias.get_ratios": debias.get_ratios, "generate.generate_images": generate.generate_images}
+    # defaults the mirrors widen on purpose: get_ratios gives the reference's required parameters defaults so that the weight tensors can
+    # also be passed by the keyword alias uce_weights (a reference-style call always passes them)
+    widened = {"debias.get_ratios": {"uce_modules", "edit_concepts", "debias_concepts", "desired_ratios", "max_diff"}}
+    for name, ref in gold.items():
+        params = list(inspect.signature(ours[name]).parameters.values())
+        assert [p.name for p in params[: len(ref)]] == [n for n, _ in ref], name
+        for p, (n, d) in zip(params, ref):
+            if d is None:
+                assert p.default is inspect._empty or n in widened.get(name, ()), (name, n)
+            else:
+                assert repr(p.default) == d, (name, n, repr(p.default), d)
+        for p in params[len(ref):]:
+            assert p.default is not inspect._empty, (name, p.name)            # our extras are optional

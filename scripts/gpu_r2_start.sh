@@ -30,3 +30,5 @@ echo "== host path: number of copy/compute groups (default 8)" | tee -a $S
 for g in 4 8 12 16 32; do
   UCE_HOST_GROUPS=$g timeout 200 python bench.py --no-denoise --no-cpu --steps 20 --warmup 5 2>&1 >/dev/null | grep -E "e2e" | sed "s/^/groups $g: /" | tee -a $S
 done
+echo "== plain-C consumer of the C ABI (examples/edit_host.c; opt-in test)" | tee -a $S
+UCE_TEST_C_EXAMPLE=1 timeout 200 python -m pytest tests/test_cli_and_host.py -m gpu -q -p no:cacheprovider -k plain_c_consumer 2>&1 | tail -3 | tee -a $S

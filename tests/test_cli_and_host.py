@@ -245,3 +245,43 @@ def test_python_function_seam_has_the_reference_signatures():
                 assert repr(p.default) == d, (name, n, repr(p.default), d)
         for p in params[len(ref):]:
             assert p.default is not inspect._empty, (name, p.name)            # our extras are optional
+
+
+def _build_c_example(tmp_path):
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    from uce_b200 import _native
+    libdir = os.path.dirname(_native.LIB_PATH)
+    exe = str(tmp_path / "edit_host")
+    r = subprocess.run([gcc, "-std=c11", "-O2", "-Wall", "-Wextra", "-Werror", "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "edit_host.c"),
+                        "-L" + libdir, "-luce_b200", "-Wl,-rpath," + libdir, "-lm", "-o", exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return exe
+
+
+def test_plain_c_consumer_links_and_fails_loudly_without_a_gpu(tmp_path):
+    """examples/edit_host.c uses the boundary the way a non-Python host would: it must compile as C11 against include/uce_b200.h, link
+    against libuce_b200.so alone, and — the library has no CPU path — stop with UCE_E_NO_DEVICE (exit 3) on a box without a B200."""
+    import subprocess
+    exe = _build_c_example(tmp_path)
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: the gpu-marked twin runs the edit")
+    r = subprocess.run([exe, str(tmp_path / "out.safetensors")], capture_output=True, text=True)
+    assert r.returncode == 3, (r.returncode, r.stderr)
+    assert "no B200" in r.stderr and not os.path.exists(tmp_path / "out.safetensors")
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(os.environ.get("UCE_TEST_C_EXAMPLE") != "1", reason="written after the round's GPU budget was spent: opt-in until it has run on hardware (UCE_TEST_C_EXAMPLE=1)")
+def test_plain_c_consumer_edits_on_the_gpu(tmp_path):
+    """The same program on a B200: edit from host buffers, normal-equation residual checked in C, artifact readable by safetensors."""
+    import subprocess
+    from safetensors.torch import load_file
+    exe = _build_c_example(tmp_path)
+    r = subprocess.run([exe, str(tmp_path / "out.safetensors")], capture_output=True, text=True)
+    assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
+    got = load_file(str(tmp_path / "out.safetensors"))
+    assert sorted(v.shape for v in got.values()) == [torch.Size([24, 64]), torch.Size([40, 64])] and all(v.dtype == torch.float32 for v in got.values())

@@ -30,3 +30,20 @@ def test_tiny_decode_shapes_and_precision():
     assert float((y32.double() - y64).norm() / y64.norm()) < 1e-5
     u8 = V.to_uint8(y32)
     assert u8.dtype == torch.uint8 and u8.shape == (2, 12, 10, 3)
+
+
+def test_bf16_storage_error_budget_behind_the_gpu_tolerance():
+    """Where the bars of tests/test_vae_gpu.py come from: the decoder run with bf16 weights and activations (what the engine stores;
+    torch accumulates in fp32 like the kernels) against the fp32 run on bf16-rounded weights — SD-1.4 configuration, 16 x 16 latents.
+    Measured: rel-RMS 1.1e-2, 0.56 uint8 levels mean, none of the channels more than 5 levels off.  The GPU bars (5e-2, 2 % above 3 levels)
+    leave a factor of ~5 for the different accumulation orders of the tensor-core kernels."""
+    P = V.random_weights(SD14_VAE, seed=5)
+    g = torch.Generator().manual_seed(6)
+    lat = torch.randn(1, 4, 16, 16, generator=g) * SD14_VAE["scaling_factor"] * 3.0
+    keep = ("norm", "bias", "post_quant_conv", "conv_in", "conv_out")
+    ref = V.decode({k: (v if any(t in k for t in keep) else v.to(torch.bfloat16).float()) for k, v in P.items()}, lat, SD14_VAE)
+    low = V.decode({k: v.to(torch.bfloat16) for k, v in P.items()}, lat.to(torch.bfloat16), SD14_VAE).float()
+    rel = float((low - ref).pow(2).mean().sqrt() / ref.pow(2).mean().sqrt())
+    d = (V.to_uint8(low).int() - V.to_uint8(ref).int()).abs()
+    assert rel < 2e-2, rel
+    assert float((d > 3).float().mean()) < 0.005 and float(d.float().mean()) < 1.0, (float((d > 3).float().mean()), float(d.float().mean()))

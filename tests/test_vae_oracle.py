@@ -47,3 +47,28 @@ def test_bf16_storage_error_budget_behind_the_gpu_tolerance():
     d = (V.to_uint8(low).int() - V.to_uint8(ref).int()).abs()
     assert rel < 2e-2, rel
     assert float((d > 3).float().mean()) < 0.005 and float(d.float().mean()) < 1.0, (float((d > 3).float().mean()), float(d.float().mean()))
+
+
+def test_value_bias_fold_used_by_the_engine_is_exact():
+    """csrc/vae_engine.cu produces V^T by a GEMM without the value bias and adds  bo + Wo bv  in the output projection instead (rows of
+    the softmax sum to 1).  Same result as the literal attention block, in fp64."""
+    import math
+    import torch.nn.functional as F
+    cfg = tiny_vae_config(ch=(16, 32), groups=4)
+    P = {k: v.double() for k, v in V.random_weights(cfg, seed=2).items()}
+    p = "decoder.mid_block.attentions.0"
+    for k in (p + ".to_v.bias", p + ".to_out.0.bias", p + ".to_q.bias", p + ".to_k.bias"):
+        P[k] = P[k] * 25.0                                   # make the biases matter
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(2, 32, 5, 7, generator=g, dtype=torch.float64)
+    want = V._attention(P, p, x, cfg["norm_groups"])
+    B, C, H, W = x.shape
+    h = F.group_norm(x, cfg["norm_groups"], P[p + ".group_norm.weight"], P[p + ".group_norm.bias"], eps=1e-6)
+    t = h.reshape(B, C, H * W).transpose(1, 2)
+    q = F.linear(t, P[p + ".to_q.weight"], P[p + ".to_q.bias"])
+    k = F.linear(t, P[p + ".to_k.weight"], P[p + ".to_k.bias"])
+    vt = P[p + ".to_v.weight"] @ t.transpose(1, 2)           # V^T [B, C, L], no bias
+    a = torch.softmax(q @ k.transpose(1, 2) / math.sqrt(C), dim=-1) @ vt.transpose(1, 2)
+    folded = P[p + ".to_out.0.bias"] + P[p + ".to_out.0.weight"] @ P[p + ".to_v.bias"]
+    got = x + F.linear(a, P[p + ".to_out.0.weight"], folded).transpose(1, 2).reshape(B, C, H, W)
+    assert float((got - want).abs().max()) < 1e-10

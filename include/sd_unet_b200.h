@@ -70,6 +70,10 @@ int sd_unet_set_timestep(sd_unet *u, float t);
 int sd_cfg_step(const float *eps2, long n, float gs, float *eps_out, const float *h1, const float *h2, const float *h3,
                 const float c[4], float cx, float ce, const float *x_in, float *x_out, void *stream);
 
+/* Parameter inventory of a configuration (host-only, no device needed): returns the number of parameters; with index >= 0 also
+ * writes the index-th (sorted by name) parameter's diffusers name into name[cap] and its shape. */
+int sd_unet_inventory(const sd_unet_config *cfg, int index, char *name, size_t cap, long shape[4], int *ndim);
+
 /* Introspection / tests: number of kernels one forward enqueues; copy a named intermediate (conv_in, down.i.j, mid,
  * up.i.j, temb) to HOST as fp32 NCHW (temb: [batch, temb_dim]).  `cap` = floats available in `out`. */
 int sd_unet_launch_count(sd_unet *u);           /* per denoise step (context given by sd_unet_set_context) */

@@ -119,6 +119,22 @@ def test_sd_vae_c_abi_exports_every_declared_symbol():
     assert list(cs.block_out_channels) == [128, 256, 512, 512] and cs.n_levels == 4 and abs(cs.scaling_factor - 0.18215) < 1e-7
 
 
+def test_sd_unet_engine_inventory_is_the_diffusers_unet_layout():
+    """Same for the U-Net engine: the native inventory equals the spec the CPU oracle is built on — for SD-1.4 the 859 520 964
+    parameters of the published checkpoint under their diffusers names (of which the 32 edited attn2.to_k/to_v matrices are 19 169 280)."""
+    from uce_b200 import unet
+    from uce_b200.unet_spec import SD14, param_shapes, tiny_config
+    for cfg in (SD14, tiny_config(ch=(64, 128), ctx_dim=64, heads=4, groups=8)):
+        inv = unet.engine_inventory(cfg)
+        want = {k: tuple(v) for k, v in param_shapes(cfg).items()}
+        assert inv == want, sorted(set(inv) ^ set(want))[:5]
+    inv = unet.engine_inventory(SD14)
+    count = lambda shp: int(torch.tensor(shp).prod())
+    assert sum(count(s) for s in inv.values()) == 859_520_964
+    edited = [k for k in inv if "attn2" in k and k.endswith(("to_k.weight", "to_v.weight"))]
+    assert len(edited) == 32 and sum(count(inv[k]) for k in edited) == 19_169_280
+
+
 def test_sd_vae_engine_inventory_is_the_diffusers_decoder_layout():
     """The parameter names / shapes the native decoder engine expects (host-only query) are exactly the spec the CPU oracle is built
     on — the SD-1.x `pipe.vae` decoder layout with its 49 490 179 + 20 parameters — so a real checkpoint loads by name."""

@@ -13,7 +13,9 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <functional>
+#include <iterator>
 #include <map>
 #include <string>
 #include <vector>
@@ -593,6 +595,23 @@ int sd_cfg_step(const float* eps2, long n, float gs, float* eps_out, const float
     int rc = uce::op_cfg_step(eps2, n, gs, eps_out, h1, h2, h3, c[0], c[1], c[2], c[3], cx, ce, x_in, x_out, (cudaStream_t)stream);
     if (rc) sd_err("cfg_step launch failed: %s", cudaGetErrorString((cudaError_t)rc));
     return rc;
+}
+
+int sd_unet_inventory(const sd_unet_config* cfg, int index, char* name, size_t cap, long shape[4], int* ndim) {
+    if (!cfg || cfg->n_levels < 1 || cfg->n_levels > 4 || cfg->layers_per_block < 1) { sd_err("sd_unet_inventory: bad argument"); return SD_E_ARG; }
+    sd_unet tmp;                            // host-only: the inventory depends on the configuration alone
+    tmp.cfg = *cfg;
+    build_inventory(&tmp);
+    const int n = (int)tmp.expected.size();
+    if (index < 0) return n;
+    if (index >= n || !name || !shape || !ndim) { sd_err("sd_unet_inventory: bad index / output"); return SD_E_ARG; }
+    auto it = tmp.expected.begin();
+    std::advance(it, index);
+    if (it->first.size() + 1 > cap) { sd_err("sd_unet_inventory: name buffer too small"); return SD_E_ARG; }
+    memcpy(name, it->first.c_str(), it->first.size() + 1);
+    *ndim = (int)it->second.size();
+    for (int i = 0; i < *ndim; ++i) shape[i] = it->second[i];
+    return n;
 }
 
 int sd_unet_launch_count(sd_unet* u) { return u ? (int)u->ops.size() : SD_E_ARG; }

@@ -29,6 +29,7 @@ SD_SIGNATURES = {
     "sd_unet_set_timestep": (C.c_int, [C.c_void_p, C.c_float]),
     "sd_cfg_step": (C.c_int, [C.c_void_p, C.c_long, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_float),
                               C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "sd_unet_inventory": (C.c_int, [C.POINTER(SDUnetConfig), C.c_int, C.c_char_p, C.c_size_t, C.POINTER(C.c_long), C.POINTER(C.c_int)]),
     "sd_unet_launch_count": (C.c_int, [C.c_void_p]),
     "sd_unet_context_launch_count": (C.c_int, [C.c_void_p]),
     "sd_unet_read_tap": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_int)]),
@@ -58,6 +59,22 @@ def _cfg_struct(cfg, context_len=77) -> SDUnetConfig:
     return SDUnetConfig(cfg["in_channels"], cfg["out_channels"], len(ch), (C.c_int * 4)(*pad(ch)), cfg["layers_per_block"],
                         (C.c_int * 4)(*pad(int(x) for x in cfg["down_has_attn"])), (C.c_int * 4)(*pad(int(x) for x in cfg["up_has_attn"])),
                         cfg["cross_attention_dim"], context_len, cfg["heads"], cfg["norm_groups"], cfg["temb_dim"])
+
+
+def engine_inventory(cfg=SD14, context_len=77) -> dict:
+    """{name: shape} of the parameters the native engine expects for ``cfg`` (host-only; no GPU needed)."""
+    cs = _cfg_struct(cfg, context_len)
+    n = _lib().sd_unet_inventory(C.byref(cs), -1, None, 0, None, None)
+    if n < 0:
+        _check(n)
+    out = {}
+    buf, shp, nd = C.create_string_buffer(256), (C.c_long * 4)(), C.c_int()
+    for i in range(n):
+        rc = _lib().sd_unet_inventory(C.byref(cs), i, buf, 256, shp, C.byref(nd))
+        if rc < 0:
+            _check(rc)
+        out[buf.value.decode()] = tuple(shp[: nd.value])
+    return out
 
 
 class UNetEngine:

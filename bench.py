@@ -466,7 +466,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--workload", choices=list(WORKLOAD_DESC), default="cfg2")
-    ap.add_argument("--apply-impl", type=int, default=None, help="0 auto, 1 SIMT, 2 tcgen05 (1 tile/CTA), 3 tcgen05 (2 CTAs/SM), 4 tcgen05 (2 row blocks/CTA, balanced wave)")
+    ap.add_argument("--apply-impl", type=int, default=None, help="0 auto, 1 SIMT, 2 tcgen05 (1 tile/CTA), 3 tcgen05 (2 CTAs/SM), 4 tcgen05 (2 row blocks/CTA, balanced wave), 5 / 6 high-rank tcgen05 (opt-in)")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-denoise", action="store_true", help="skip the U-Net denoise-step measurement")

@@ -60,7 +60,8 @@ int uce_ws_destroy(uce_ws *ws);
 /* Select the apply kernel: 0 = auto (the fastest tcgen05 3xTF32 kernel that takes the shape), 1 = SIMT fp32,
  * 2 = tcgen05, one 128-row tile per CTA (rank pad <= 128), 3 = tcgen05, two co-resident CTAs per SM (rank pad <= 64),
  * 4 = tcgen05, two row blocks per CTA in one planned wave (rank pad <= 64, <= 96 projections per call),
- * 5 = tcgen05 high-rank two-GEMM apply (any rank pad; opt-in only: not yet validated on hardware, never chosen by 0).
+ * 5 = tcgen05 high-rank two-GEMM apply (any rank pad; opt-in only: not yet validated on hardware, never chosen by 0),
+ * 6 = the same with both MMA operands in shared memory (the raw fp32 tile is the tf32 hi operand; opt-in only, not yet run on hardware).
  * Returns the previous value. All are hand-written CUDA; there is no CPU path. */
 int uce_ws_set_apply_impl(uce_ws *ws, int impl);
 

@@ -30,7 +30,7 @@ def ranges(idx):
     return ",".join(out)
 
 
-def run(n_edit, K, dims, repeats=6):
+def run(n_edit, K, dims, repeats=6, impl=5):
     n_pres = 20
     rows = concept_rows(n_edit + n_pres + n_edit, K, seed=n_edit)
     C, G = rows[: n_edit + n_pres].cuda(), rows[n_edit + n_pres:].cuda()
@@ -38,10 +38,10 @@ def run(n_edit, K, dims, repeats=6):
     s = EditSolver(K, C.shape[0], "cuda:0")
     sc = [1.0] * (n_edit + n_pres)
     s.set_apply_impl(1); a = [t.clone() for t in s.edit(C, G, sc, n_edit, 0.5, W)]
-    s.set_apply_impl(5)
+    s.set_apply_impl(impl)
     s.edit(C, G, sc, n_edit, 0.5, W)
     info = s.info()
-    print(f"--- n_edit {n_edit} K {K} dims {dims} rank {info['rank']} (pad {-(-info['rank'] // 32) * 32}) dense {info['dense']} apply launches {info['launches_apply']}")
+    print(f"--- impl {impl} n_edit {n_edit} K {K} dims {dims} rank {info['rank']} (pad {-(-info['rank'] // 32) * 32}) dense {info['dense']} apply launches {info['launches_apply']}")
     n_bad = 0
     for rep in range(repeats):
         b = s.edit(C, G, sc, n_edit, 0.5, W)
@@ -67,9 +67,10 @@ def run(n_edit, K, dims, repeats=6):
 
 
 if __name__ == "__main__":
-    bad = 0
-    for d in ([72], [136], [192], [256], [264], [200, 320]):
-        bad += run(200, 512, d)
-    bad += run(40, 512, [200])
-    bad += run(300, 768, [320, 640, 1280])
-    print("total rel err summary: wrong results", bad)
+    for impl in (5, 6):              # 5: A staged in tensor memory (apply_gemm3x.cu); 6: both operands in shared memory (apply_gemm3x_ss.cu)
+        bad = 0
+        for d in ([72], [136], [192], [256], [264], [200, 320]):
+            bad += run(200, 512, d, impl=impl)
+        bad += run(40, 512, [200], impl=impl)
+        bad += run(300, 768, [320, 640, 1280], impl=impl)
+        print(f"impl {impl}: wrong results in total", bad)

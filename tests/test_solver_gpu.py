@@ -349,9 +349,11 @@ def test_two_block_tcgen05_apply(n_edit, K, dims, block_rows, monkeypatch):
 
 @pytest.mark.skipif(os.environ.get("UCE_TEST_GEMM3X") != "1", reason="apply_gemm3x.cu (apply impl 5) has not been validated on hardware yet: "
                     "set UCE_TEST_GEMM3X=1 to run its parity test (round 2 starts here)")
+@pytest.mark.parametrize("g3_impl", [5, 6])
 @pytest.mark.parametrize("n_edit,K,dims", [(200, 512, [320, 200]), (96, 256, [128, 8, 300]), (1000, 2048, [640, 1280]), (40, 768, [320] * 100)])
-def test_highrank_tcgen05_apply(n_edit, K, dims):
-    """apply_gemm3x.cu (two 3xTF32 tcgen05 GEMM launches, P through an HBM scratch) against the SIMT fp32 apply and the fp64 oracle:
+def test_highrank_tcgen05_apply(n_edit, K, dims, g3_impl):
+    """apply_gemm3x.cu (impl 5: A split into tensor memory) and apply_gemm3x_ss.cu (impl 6: both operands in shared memory, raw tile as the
+    tf32 hi operand) — two 3xTF32 tcgen05 GEMM launches, P through an HBM scratch — against the SIMT fp32 apply and the fp64 oracle:
     rank pads 64..1024, ragged N tiles, row tails, more than 96 projections (sliced), in place."""
     from uce_b200.synthetic import concept_rows, weights
     n_pres = 20
@@ -363,14 +365,14 @@ def test_highrank_tcgen05_apply(n_edit, K, dims):
     simt = _run(s, C, G, scales, n_edit, 0.5, W, impl=1)
     if s.info()["dense"]:
         pytest.skip("dense factor: the two-GEMM low-rank form does not apply")
-    tc = _run(s, C, G, scales, n_edit, 0.5, W, impl=5)
+    tc = _run(s, C, G, scales, n_edit, 0.5, W, impl=g3_impl)
     assert s.info()["launches_apply"] == 2 * -(-len(dims) // 96)
     exact = O.erase_exact_f64(W[:3], C[:n_edit], G, C[n_edit:], 1.0, 1.0, 0.5)
     for a, b, e in zip(simt, tc, exact):
         assert O.rel_fro(b, e) <= TOL_EXACT, ("gemm3x vs exact", O.rel_fro(b, e), O.rel_fro(a, e))
     for a, b in zip(simt, tc):
         assert O.rel_fro(b, a) <= 1e-5, ("gemm3x vs simt", O.rel_fro(b, a))
-    inpl = _run(s, C, G, scales, n_edit, 0.5, W, impl=5, inplace=True)
+    inpl = _run(s, C, G, scales, n_edit, 0.5, W, impl=g3_impl, inplace=True)
     for a, b in zip(tc, inpl):
         assert torch.equal(a, b)
     s.close()

@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libuce_b200.so")
-SOURCES = ["uce_api.cu", "artifact.cu", "png.cu", "factor.cu", "factor_small.cu", "apply.cu", "apply_tc.cu", "apply_tc2.cu", "apply_tc3.cu", "apply_gemm3x.cu",
+SOURCES = ["uce_api.cu", "artifact.cu", "png.cu", "factor.cu", "factor_small.cu", "apply.cu", "apply_tc.cu", "apply_tc2.cu", "apply_tc3.cu", "apply_gemm3x.cu", "apply_gemm3x_ss.cu",
            "unet_gemm.cu", "unet_ops.cu", "unet_attn.cu", "unet_engine.cu", "vae_engine.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared", "-lcuda", "-lz"]

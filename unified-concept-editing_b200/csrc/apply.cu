@@ -21,6 +21,9 @@ int apply_tc2_tile_rows();
 int apply_tc2_lowrank(uce_ws* ws, const LayerRef* layers_dev, const LayerRef* layers_host, int n_layers, int total_tiles,
                       int tile_rows, cudaStream_t st, int* launches);
 bool apply_gemm3x_available(const uce_ws* ws, int n_layers);   // apply_gemm3x.cu
+bool apply_gemm3x_ss_available(const uce_ws* ws, int n_layers);   // apply_gemm3x_ss.cu
+int apply_gemm3x_ss_highrank(uce_ws* ws, const LayerRef* layers_dev, const LayerRef* layers_host, int n_layers, int total_tiles,
+                             cudaStream_t st, int* launches);
 int apply_gemm3x_highrank(uce_ws* ws, const LayerRef* layers_dev, const LayerRef* layers_host, int n_layers, int total_tiles,
                           cudaStream_t st, int* launches);
 bool apply_tc3_available(const uce_ws* ws, int n_layers);   // apply_tc3.cu
@@ -123,7 +126,8 @@ int apply_dev(uce_ws* ws, const float* const* W_old, float* const* W_new, const 
     // longer lists (SDXL: 140 projections) go through it in slices
     constexpr int TC3_MAX = 96;
     if (n_layers > TC3_MAX && !ws->dense && ws->rank > 0 &&
-        (((ws->apply_impl == 0 || ws->apply_impl == 4) && apply_tc3_available(ws, TC3_MAX)) || (ws->apply_impl == 5 && apply_gemm3x_available(ws, TC3_MAX)))) {
+        (((ws->apply_impl == 0 || ws->apply_impl == 4) && apply_tc3_available(ws, TC3_MAX)) || (ws->apply_impl == 5 && apply_gemm3x_available(ws, TC3_MAX)) ||
+         (ws->apply_impl == 6 && apply_gemm3x_ss_available(ws, TC3_MAX)))) {
         int total_launches = 0;
         const bool prof = ws->profile && !no_profile;
         if (prof) UCE_CUDA(cudaEventRecord(ws->pev[2], st));
@@ -147,8 +151,10 @@ int apply_dev(uce_ws* ws, const float* const* W_old, float* const* W_new, const 
     // apply_impl: 0 auto, 1 SIMT, 2 tcgen05 one 128-row tile per CTA (apply_tc.cu), 3 tcgen05 two CTAs per SM (apply_tc2.cu,
     // rank_pad <= 64), 4 tcgen05 two row blocks per CTA in one balanced wave (apply_tc3.cu, rank_pad <= 64),
     // 5 tcgen05 high-rank two-GEMM apply (apply_gemm3x.cu: explicit opt-in only, not yet validated on hardware)
+    // 6 the same with both operands in shared memory (apply_gemm3x_ss.cu: explicit opt-in only, not yet run on hardware)
     const bool lowrank = !ws->dense && ws->rank > 0;
-    const bool use_g3 = lowrank && ws->apply_impl == 5 && apply_gemm3x_available(ws, n_layers);
+    const bool use_g3s = lowrank && ws->apply_impl == 6 && apply_gemm3x_ss_available(ws, n_layers);
+    const bool use_g3 = use_g3s || (lowrank && ws->apply_impl == 5 && apply_gemm3x_available(ws, n_layers));
     const bool use_tc3 = !use_g3 && lowrank && ((ws->apply_impl == 4) || (ws->apply_impl == 0 && apply_tc3_available(ws, n_layers)));
     const bool use_tc2 = !use_tc3 && lowrank && (ws->apply_impl == 3);
     const bool use_tc = !use_tc3 && !use_tc2 && lowrank && ((ws->apply_impl == 2) || (ws->apply_impl == 0 && apply_tc_available(ws) && n_layers <= 160));
@@ -191,7 +197,8 @@ int apply_dev(uce_ws* ws, const float* const* W_old, float* const* W_new, const 
     }
     if (!ws->dense) {
         if (use_g3) {
-            int rc = apply_gemm3x_highrank(ws, dl, hl, n_layers, tiles, st, &launches);
+            int rc = use_g3s ? apply_gemm3x_ss_highrank(ws, dl, hl, n_layers, tiles, st, &launches)
+                             : apply_gemm3x_highrank(ws, dl, hl, n_layers, tiles, st, &launches);
             if (rc) return rc;
         } else if (use_tc3) {
             int rc = apply_tc3_lowrank(ws, dl, hl, n_layers, tiles, st, &launches, prof ? ws->pev[2] : nullptr);

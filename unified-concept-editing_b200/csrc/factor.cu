@@ -276,7 +276,7 @@ int factor_dev(uce_ws* ws, const float* C, const float* G, const float* scales, 
         UCE_RT((simt_gemm<float, float, double, float>(st, K, K, n_edit, ws->Q, 1, K, ws->E, 1, K, ws->Dt, K)));
     }
     ws->mode = dual ? 1 : 2;
-    if ((apply_tc_available(ws) && ws->apply_impl != 1) || (ws->apply_impl == 5 && !ws->dense && ws->rank > 0)) {      // tf32 hi/lo splits of E and Qt
+    if ((apply_tc_available(ws) && ws->apply_impl != 1) || ((ws->apply_impl == 5 || ws->apply_impl == 6) && !ws->dense && ws->rank > 0)) {      // tf32 hi/lo splits of E and Qt
         int rc2 = apply_tc_split_operands(ws, st, &launches);
         if (rc2) return rc2;
     }

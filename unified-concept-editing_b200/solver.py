@@ -13,7 +13,7 @@ import torch
 
 from . import _native as N
 
-APPLY_AUTO, APPLY_SIMT, APPLY_TCGEN05, APPLY_TCGEN05_2CTA, APPLY_TCGEN05_2BLOCK, APPLY_TCGEN05_HIGHRANK = 0, 1, 2, 3, 4, 5
+APPLY_AUTO, APPLY_SIMT, APPLY_TCGEN05, APPLY_TCGEN05_2CTA, APPLY_TCGEN05_2BLOCK, APPLY_TCGEN05_HIGHRANK, APPLY_TCGEN05_HIGHRANK_SS = 0, 1, 2, 3, 4, 5, 6
 
 
 def _ptr(t: torch.Tensor) -> int:

@@ -4,8 +4,9 @@
 //
 // but with BOTH MMA operands in shared memory and nothing staged in tensor memory:
 //
-//   * A_hi is the raw fp32 [128 x 32] tile exactly as the TMA delivered it (128B swizzle = the canonical K-major UMMA layout): a
-//     kind::tf32 MMA ignores the low 13 mantissa bits, i.e. it reads hi = trunc(x).  No transform, no copy.
+//   * A_hi is the raw fp32 [128 x 32] tile where the TMA delivered it (128B swizzle = the canonical K-major UMMA layout): a
+//     kind::tf32 MMA ignores the low 13 mantissa bits, i.e. it reads hi = trunc(x).  No copy (for now the truncated value is also
+//     written back in place, so that correctness does not rest on that property of the hardware).
 //   * A_lo = x - trunc(x) (exact in fp32) is written by 4 warps (thread = row) into a second [128 x 32] tile of the same stage,
 //     published to the tensor core with fence.proxy.async + mbarrier (the pattern of apply_tc.cu's phase B).
 //   * the stage (hi + lo) is released by the MMA warp's tcgen05.commit; B (E_hi|E_lo, Qt_hi|Qt_lo, pre-split with rounding by the
@@ -132,8 +133,12 @@ gemm3x_ss_kernel(const LayerRef* __restrict__ layers, int n_layers, int mode, in
             for (int j = 0; j < 8; ++j) {
                 const uint32_t off = ((uint32_t)j ^ sw) << 4;
                 const float4 v = lds_v4(raw + off);                            // rows beyond the tensor were zero-filled by TMA
-                sts_v4(lo + off, v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u), v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u),
-                       v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u), v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u));
+                const float hx = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u), hy = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+                const float hz = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u), hw = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+                sts_v4(lo + off, v.x - hx, v.y - hy, v.z - hz, v.w - hw);
+                // the truncated hi is written back in place, so the result does not depend on what the tensor core does with the low
+                // 13 bits of a tf32 operand (documented as ignored); drop this store once that has been confirmed on hardware
+                sts_v4(raw + off, hx, hy, hz, hw);
             }
             fence_proxy_async();                                               // generic writes -> visible to the tensor core's reads
             fence_before();

@@ -143,15 +143,18 @@ class Sim:
             agents[f"t{w}"] = self.transform(w)
         finite = {k for k in agents if not k.endswith("engine")}
         idle = 0
+        # skewed timing: every agent gets a random speed for the whole run (log-uniform over three decades)
+        speed = {k: 10.0 ** self.rng.uniform(-3, 0) for k in agents}
         while finite:
-            name = self.rng.choice(list(agents))
+            names = list(agents)
+            name = self.rng.choices(names, weights=[speed[k] for k in names])[0]
             before = (self.mma_done, len(self.tma_inflight), len(self.mma_queue))
             try:
                 next(agents[name])
             except StopIteration:
                 del agents[name]; finite.discard(name)
             idle = idle + 1 if before == (self.mma_done, len(self.tma_inflight), len(self.mma_queue)) else 0
-            assert idle < 200000, f"no progress (deadlock?) with {sorted(finite)} still running"
+            assert idle < 20000000, f"no progress (deadlock?) with {sorted(finite)} still running"
         assert self.epilogue_started
 
 

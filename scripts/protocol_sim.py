@@ -158,6 +158,115 @@ class Sim:
         assert self.epilogue_started
 
 
+class SimSS:
+    """csrc/apply_gemm3x_ss.cu: 3 stages of {raw = hi | lo} in shared memory, released by the MMA warp's commit."""
+    NST = 3
+
+    def __init__(self, n_chunks, rng):
+        self.n, self.rng = n_chunks, rng
+        N = self.NST
+        self.raw_full = [Barrier(2) for _ in range(N)]
+        self.lo_full = [Barrier(PW) for _ in range(N)]
+        self.st_empty = [Barrier(1) for _ in range(N)]
+        self.b_full = [Barrier(2) for _ in range(NBS)]
+        self.b_empty = [Barrier(1) for _ in range(NBS)]
+        self.acc_full = Barrier(1)
+        self.raw = [None] * N
+        self.lo = [[None] * PW for _ in range(N)]
+        self.busy = [0] * N                                       # MMAs issued on the stage (hi and lo tiles) and not yet completed
+        self.lo_pending = [0] * N                                 # lo warps that still have to read the raw tile / write their lo rows
+        self.B, self.B_busy = [None] * NBS, [0] * NBS
+        self.tma_inflight, self.mma_queue, self.mma_done, self.epilogue_started = [], [], 0, False
+
+    def wait(self, bar, parity):
+        while not bar.passed(parity):
+            yield
+
+    def tma_engine(self):
+        while True:
+            if self.tma_inflight:
+                kind, st, c = self.tma_inflight.pop(self.rng.randrange(len(self.tma_inflight)))
+                if kind == "raw":
+                    assert self.busy[st] == 0 and self.lo_pending[st] == 0, f"stage {st} overwritten while in use"
+                    self.raw[st], self.lo_pending[st] = c, PW
+                    self.raw_full[st].arrive()
+                else:
+                    assert self.B_busy[st] == 0, f"B stage {st} overwritten under a running MMA"
+                    self.B[st] = c
+                    self.b_full[st].arrive()
+            yield
+
+    def tensor_engine(self):
+        while True:
+            if self.mma_queue:
+                c, r, sb, commits = self.mma_queue.pop(0)
+                assert self.raw[r] == c and all(x == c for x in self.lo[r]), f"MMA of chunk {c} read stage {r}: hi {self.raw[r]} lo {self.lo[r]}"
+                assert self.B[sb] == c, f"MMA of chunk {c} read B stage {sb} = {self.B[sb]}"
+                self.busy[r] -= 1; self.B_busy[sb] -= 1; self.mma_done += 1
+                for bar in commits:
+                    bar.arrive()
+            yield
+
+    def a_tma(self):
+        for c in range(self.n):
+            r = c % self.NST
+            yield from self.wait(self.st_empty[r], ((c // self.NST) & 1) ^ 1)
+            self.raw_full[r].arrive()
+            self.tma_inflight.append(("raw", r, c))
+            yield
+
+    def b_tma(self):
+        for c in range(self.n):
+            s = c % NBS
+            yield from self.wait(self.b_empty[s], ((c // NBS) & 1) ^ 1)
+            self.b_full[s].arrive()
+            self.tma_inflight.append(("b", s, c))
+            yield
+
+    def lo_warp(self, w):
+        for c in range(self.n):
+            r = c % self.NST
+            yield from self.wait(self.raw_full[r], (c // self.NST) & 1)
+            assert self.raw[r] == c, f"lo warp {w} read stage {r} = {self.raw[r]} for chunk {c}"
+            assert self.busy[r] == 0, f"lo warp {w} rewrote stage {r} under a running MMA"
+            self.lo[r][w] = c
+            self.lo_pending[r] -= 1
+            yield
+            self.lo_full[r].arrive()
+            yield
+        yield from self.wait(self.acc_full, 0)
+        assert self.mma_done == self.n
+        self.epilogue_started = True
+
+    def mma(self):
+        for c in range(self.n):
+            r, sb = c % self.NST, c % NBS
+            yield from self.wait(self.b_full[sb], (c // NBS) & 1)
+            yield from self.wait(self.lo_full[r], (c // self.NST) & 1)
+            commits = [self.st_empty[r], self.b_empty[sb]] + ([self.acc_full] if c == self.n - 1 else [])
+            self.busy[r] += 1; self.B_busy[sb] += 1
+            self.mma_queue.append((c, r, sb, commits))
+            yield
+
+    def run(self):
+        agents = {"a_tma": self.a_tma(), "b_tma": self.b_tma(), "mma": self.mma(), "tma_engine": self.tma_engine(), "tensor_engine": self.tensor_engine()}
+        for w in range(PW):
+            agents[f"t{w}"] = self.lo_warp(w)
+        finite = {k for k in agents if not k.endswith("engine")}
+        speed = {k: 10.0 ** self.rng.uniform(-3, 0) for k in agents}
+        steps = 0
+        while finite:
+            names = list(agents)
+            name = self.rng.choices(names, weights=[speed[k] for k in names])[0]
+            try:
+                next(agents[name])
+            except StopIteration:
+                del agents[name]; finite.discard(name)
+            steps += 1
+            assert steps < 400_000_000, f"no termination (deadlock?) with {sorted(finite)} still running"
+        assert self.epilogue_started
+
+
 def main():
     runs = int(sys.argv[1]) if len(sys.argv) > 1 else 300
     rng = random.Random(0)
@@ -166,6 +275,10 @@ def main():
             for _ in range(runs):
                 Sim(n_chunks, pipelined, rng).run()
         print(f"{'pipelined' if pipelined else 'current  '} transform loop: {runs} random schedules x 10 chunk counts: no violation")
+    for n_chunks in (1, 2, 3, 4, 5, 7, 8, 9, 16, 24):
+        for _ in range(runs):
+            SimSS(n_chunks, rng).run()
+    print(f"shared-memory variant (apply_gemm3x_ss.cu): {runs} random schedules x 10 chunk counts: no violation")
 
 
 if __name__ == "__main__":

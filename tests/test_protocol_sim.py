@@ -46,3 +46,5 @@ def test_highrank_apply_kernel_protocol_is_sound():
     for pipelined in (True, False):
         for n_chunks in (1, 3, 4, 5, 8, 16):
             m.Sim(n_chunks, pipelined, rng).run()
+    for n_chunks in (1, 2, 3, 4, 7, 16):
+        m.SimSS(n_chunks, rng).run()                              # csrc/apply_gemm3x_ss.cu

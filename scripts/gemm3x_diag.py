@@ -72,5 +72,8 @@ if __name__ == "__main__":
         for d in ([72], [136], [192], [256], [264], [200, 320]):
             bad += run(200, 512, d, impl=impl)
         bad += run(40, 512, [200], impl=impl)
+        # every round-1 failure had rank pad 224 (BN = 224, 7 chunks in the second GEMM): does the rank pad matter?
+        for n_edit in (90, 120, 180, 250):                   # rank pads 96, 128, 192, 256
+            bad += run(n_edit, 512, [200, 320], impl=impl)
         bad += run(300, 768, [320, 640, 1280], impl=impl)
         print(f"impl {impl}: wrong results in total", bad)

@@ -11,7 +11,7 @@ echo "== high-rank tcgen05 apply: gated parity test, 5 fresh processes" | tee -a
 for i in 1 2 3 4 5; do
   UCE_TEST_GEMM3X=1 timeout 400 python -m pytest tests/test_solver_gpu.py -m gpu -q -p no:cacheprovider -k highrank_tcgen05 2>&1 | tail -12 | grep -E "passed|failed|FAILED" | tee -a $S
 done
-timeout 240 python scripts/gemm3x_diag.py > gpurun_out/gemm3x_diag.txt 2>&1; grep -E "^---|clean|wrong" gpurun_out/gemm3x_diag.txt | head -60 | tee -a $S
+timeout 400 python scripts/gemm3x_diag.py > gpurun_out/gemm3x_diag.txt 2>&1; grep -E "^---|clean|wrong" gpurun_out/gemm3x_diag.txt | head -60 | tee -a $S
 echo "== U-Net determinism" | tee -a $S
 timeout 300 python scripts/unet_determinism_probe.py 2>&1 | tail -5 | tee -a $S
 echo "== bench cfg2" | tee -a $S

@@ -50,8 +50,8 @@ class Region:
 
 
 class Sim:
-    def __init__(self, n_chunks, n_act, rng):
-        self.n, self.n_act, self.rng = n_chunks, n_act, rng
+    def __init__(self, n_chunks, n_act, rng, pipelined=False):
+        self.n, self.n_act, self.rng, self.pipelined = n_chunks, n_act, rng, pipelined
         B = Barrier
         self.raw_full = [B(1 + n_act, f"raw_full{r}") for r in range(NRAW)]
         self.raw_empty = [B(PW, f"raw_empty{r}") for r in range(NRAW)]
@@ -123,16 +123,28 @@ class Sim:
     def transform(self, g, w):
         who = f"transform warp g{g}w{w}"
         live = g < self.n_act
+        pending = None                                          # pipelined shape: A stage stored but not yet published
         for c in range(self.n):
             r, s = c % NRAW, c % NSA
             yield from self.wait(self.raw_full[r], (c // NRAW) & 1)
             if live:
                 self.slot[r][g].read(("raw", c), who)
             yield
+            if self.pipelined:                                      # the shape the round's last GPU runs validated and profiled
+                self.raw_empty[r].arrive()
+                if pending is not None:
+                    self.a_full[pending].arrive(); pending = None
+                yield
             yield from self.wait(self.a_empty[s], ((c // NSA) & 1) ^ 1)
             self.A[s][g][w].write(("A", c), 1 if live else 0, who)
             yield
-            self.a_full[s].arrive(); self.raw_empty[r].arrive()
+            if self.pipelined:
+                pending = s
+            else:
+                self.a_full[s].arrive(); self.raw_empty[r].arrive()
+                yield
+        if pending is not None:
+            self.a_full[pending].arrive()
             yield
         yield from self.wait(self.p_full, 0)
         if live and w == 0:
@@ -308,11 +320,13 @@ class Sim:
 def main():
     runs = int(sys.argv[1]) if len(sys.argv) > 1 else 40
     rng = random.Random(0)
-    for n_act in (2, 1):
-        for n_chunks in (1, 2, 3, 4, 5, 6, 7, 8, 11, 12, 16, 24):
-            for _ in range(runs):
-                Sim(n_chunks, n_act, rng).run()
-        print(f"apply_tc3 protocol, {n_act} active row block(s): {runs} random schedules x 12 chunk counts (K = 32 .. 768): no violation")
+    for pipelined in (False, True):          # False: the committed transform loop; True: the software-pipelined one the last GPU runs used
+        for n_act in (2, 1):
+            for n_chunks in (1, 2, 3, 4, 5, 6, 7, 8, 11, 12, 16, 24):
+                for _ in range(runs):
+                    Sim(n_chunks, n_act, rng, pipelined).run()
+            print(f"apply_tc3 protocol ({'pipelined' if pipelined else 'committed'} transform loop), {n_act} active row block(s): "
+                  f"{runs} random schedules x 12 chunk counts (K = 32 .. 768): no violation")
 
 
 if __name__ == "__main__":

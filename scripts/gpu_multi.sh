@@ -13,6 +13,6 @@ timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --mast
     > gpurun_out/bench_ref_2gpu.json 2> gpurun_out/bench_ref_2gpu.err; echo "rc=$?" | tee -a $S
 cat gpurun_out/bench_ref_2gpu.json
 echo "== sharded erase driver (NCCL all-gather) vs single GPU" | tee -a $S
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29513 scripts/sharded_erase_check.py \
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29513 tests/tools/sharded_erase_check.py \
     > gpurun_out/sharded_check.log 2>&1; echo "rc=$?" | tee -a $S
 tail -5 gpurun_out/sharded_check.log

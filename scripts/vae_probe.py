@@ -8,9 +8,8 @@ import sys
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from oracle import vae_oracle as VO          # random weights only (a script under scripts/, not the product)
 from uce_b200.vae import VAEDecoderEngine
-from uce_b200.vae_spec import SD14_VAE
+from uce_b200.vae_spec import SD14_VAE, decoder_param_shapes
 
 
 def conv_flops(cfg, h, w):
@@ -29,8 +28,26 @@ def conv_flops(cfg, h, w):
     return f + 2 * hh * ww * 9 * cur * 3
 
 
+def random_weights(cfg, seed=0):
+    """Seeded decoder weights of the published layout: 1/sqrt(fan_in) kernels, unit norm scales, small biases."""
+    import math
+    g = torch.Generator().manual_seed(seed)
+    P = {}
+    for name, shp in decoder_param_shapes(cfg).items():
+        if name.endswith(".weight") and len(shp) == 1:
+            P[name] = 1.0 + 0.1 * torch.randn(shp, generator=g)
+        elif name.endswith(".bias"):
+            P[name] = 0.02 * torch.randn(shp, generator=g)
+        else:
+            fan_in = 1
+            for d in shp[1:]:
+                fan_in *= d
+            P[name] = torch.randn(shp, generator=g) / math.sqrt(fan_in)
+    return P
+
+
 def main():
-    P = VO.random_weights(SD14_VAE, seed=0)
+    P = random_weights(SD14_VAE, seed=0)
     for batch in (1, 8):
         eng = VAEDecoderEngine(SD14_VAE, batch=batch, h=64, w=64)
         eng.load_state_dict(P); eng.finalize()

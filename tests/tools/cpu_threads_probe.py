@@ -1,6 +1,6 @@
 """How does the CPU restatement of the reference scale with torch threads on this host?"""
 import os, sys, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 from oracle import uce_oracle as O
 from uce_b200.synthetic import problem

@@ -1,7 +1,7 @@
 """torchrun --nproc-per-node 2: the erase driver with projections sharded over ranks and ONE NCCL all-gather must
 reproduce the single-GPU result bit for bit (same kernels, same inputs)."""
 import os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch, torch.distributed as dist
 from oracle.fake_pipe import FakePipe, layer_table
 from uce_b200.erase import UCE

@@ -1,6 +1,6 @@
 """Per-tap comparison of the CUDA U-Net engine against the CPU oracle on a tiny configuration (diagnostic)."""
 import os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 from oracle import unet_oracle as U
 from uce_b200.unet import UNetEngine

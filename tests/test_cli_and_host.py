@@ -291,7 +291,6 @@ def test_plain_c_consumer_links_and_fails_loudly_without_a_gpu(tmp_path):
 
 
 @pytest.mark.gpu
-@pytest.mark.skipif(os.environ.get("UCE_TEST_C_EXAMPLE") != "1", reason="written after the round's GPU budget was spent: opt-in until it has run on hardware (UCE_TEST_C_EXAMPLE=1)")
 def test_plain_c_consumer_edits_on_the_gpu(tmp_path):
     """The same program on a B200: edit from host buffers, normal-equation residual checked in C, artifact readable by safetensors."""
     import subprocess

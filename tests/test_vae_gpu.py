@@ -2,9 +2,6 @@
 ``vae.decode(latents / scaling_factor)`` + the uint8 conversion (evalscripts/generate-images-sd.py:37-46,
 evalscripts/concept_algebra.py:126-135).
 
-OPT-IN in round 1: written after the round's GPU budget was spent, so it has not run on hardware yet.  It runs only with
-UCE_TEST_VAE=1 (scripts/gpu_r2_start.sh sets it); once green it loses the gate and generate_images() gets the engine by default.
-
 Tolerance: the engine stores activations and GEMM operands in bf16 (fp32 accumulation), like the reference's bf16 pipeline
 (generate-images-sd.py:76); the oracle runs in fp32 on the same bf16-rounded weights.  Relative RMS error of the decoder output
 <= 5e-2 (the U-Net engine's bar for bf16 storage, tests/test_unet_gpu.py) and at most 2 % of the uint8 channels may differ by more
@@ -14,7 +11,7 @@ import os
 import pytest
 import torch
 
-pytestmark = [pytest.mark.gpu, pytest.mark.skipif(os.environ.get("UCE_TEST_VAE") != "1", reason="opt-in until validated on hardware (UCE_TEST_VAE=1)")]
+pytestmark = pytest.mark.gpu
 
 TOL_REL_RMS = 5e-2
 
@@ -96,8 +93,7 @@ def test_sd14_decoder_full_size_properties():
     a = e2.decode(lat).clone(); b = e2.decode(lat).clone()
     torch.cuda.synchronize()
     assert a.shape == (2, 512, 512, 3)
-    diff = (a.int() - b.int()).abs()
-    assert int(diff.max()) <= 1 and float((diff > 0).float().mean()) < 1e-3      # GroupNorm statistics are accumulated with atomics
+    assert torch.equal(a, b)          # bit-reproducible: GroupNorm statistics and split-K slabs are reduced in a fixed order
     e2.close()
     e1 = VAEDecoderEngine(SD14_VAE, batch=1, h=64, w=64); e1.load_state_dict(P); e1.finalize()
     c = e1.decode(lat[1:2].contiguous()).clone()

@@ -6,7 +6,7 @@
 //   dense    :  W_new = W_old + W_old D,  D = E^T Q  [K, K]   (when r > K/2)
 //
 // This file holds the fp32 SIMT implementation (grouped over projections through a flattened
-// row-tile list); apply_tc.cu holds the tcgen05 3xTF32 implementation validated against it.
+// row-tile list) and the dispatch; apply_tc3.cu / apply_gemm3x.cu hold the tcgen05 3xTF32 implementations validated against it.
 #include "uce_ws.h"
 #include "gemm_simt.cuh"
 #include <algorithm>
@@ -14,16 +14,7 @@
 
 namespace uce {
 
-int apply_tc_lowrank(uce_ws* ws, const LayerRef* layers_dev, const LayerRef* layers_host, int n_layers, int total_tiles,
-                     cudaStream_t st, int* launches);   // apply_tc.cu
-bool apply_tc2_available(const uce_ws* ws);                 // apply_tc2.cu
-int apply_tc2_tile_rows();
-int apply_tc2_lowrank(uce_ws* ws, const LayerRef* layers_dev, const LayerRef* layers_host, int n_layers, int total_tiles,
-                      int tile_rows, cudaStream_t st, int* launches);
 bool apply_gemm3x_available(const uce_ws* ws, int n_layers);   // apply_gemm3x.cu
-bool apply_gemm3x_ss_available(const uce_ws* ws, int n_layers);   // apply_gemm3x_ss.cu
-int apply_gemm3x_ss_highrank(uce_ws* ws, const LayerRef* layers_dev, const LayerRef* layers_host, int n_layers, int total_tiles,
-                             cudaStream_t st, int* launches);
 int apply_gemm3x_highrank(uce_ws* ws, const LayerRef* layers_dev, const LayerRef* layers_host, int n_layers, int total_tiles,
                           cudaStream_t st, int* launches);
 bool apply_tc3_available(const uce_ws* ws, int n_layers);   // apply_tc3.cu
@@ -125,9 +116,8 @@ int apply_dev(uce_ws* ws, const float* const* W_old, float* const* W_new, const 
     // the two-block tcgen05 apply carries two tensor maps per projection as kernel parameters (96 projections per launch):
     // longer lists (SDXL: 140 projections) go through it in slices
     constexpr int TC3_MAX = 96;
-    if (n_layers > TC3_MAX && !ws->dense && ws->rank > 0 &&
-        (((ws->apply_impl == 0 || ws->apply_impl == 4) && apply_tc3_available(ws, TC3_MAX)) || (ws->apply_impl == 5 && apply_gemm3x_available(ws, TC3_MAX)) ||
-         (ws->apply_impl == 6 && apply_gemm3x_ss_available(ws, TC3_MAX)))) {
+    if (n_layers > TC3_MAX && !ws->dense && ws->rank > 0 && ws->apply_impl != 1 &&
+        (apply_tc3_available(ws, TC3_MAX) || apply_gemm3x_available(ws, TC3_MAX))) {
         int total_launches = 0;
         const bool prof = ws->profile && !no_profile;
         if (prof) UCE_CUDA(cudaEventRecord(ws->pev[2], st));
@@ -148,17 +138,12 @@ int apply_dev(uce_ws* ws, const float* const* W_old, float* const* W_new, const 
     slot_begin = ws->ring_pos;
     ws->ring_pos += n_layers;
     LayerRef* hl = ws->h_layers + slot_begin;
-    // apply_impl: 0 auto, 1 SIMT, 2 tcgen05 one 128-row tile per CTA (apply_tc.cu), 3 tcgen05 two CTAs per SM (apply_tc2.cu,
-    // rank_pad <= 64), 4 tcgen05 two row blocks per CTA in one balanced wave (apply_tc3.cu, rank_pad <= 64),
-    // 5 tcgen05 high-rank two-GEMM apply (apply_gemm3x.cu: explicit opt-in only, not yet validated on hardware)
-    // 6 the same with both operands in shared memory (apply_gemm3x_ss.cu: explicit opt-in only, not yet run on hardware)
+    // apply_impl: 0 auto (two-block tcgen05 kernel for rank pads <= 64, the two-GEMM tcgen05 apply for every other low-rank edit,
+    // fp32 SIMT for the dense K x K form), 1 fp32 SIMT (validation twin), 4 apply_tc3.cu, 5 apply_gemm3x.cu
     const bool lowrank = !ws->dense && ws->rank > 0;
-    const bool use_g3s = lowrank && ws->apply_impl == 6 && apply_gemm3x_ss_available(ws, n_layers);
-    const bool use_g3 = use_g3s || (lowrank && ws->apply_impl == 5 && apply_gemm3x_available(ws, n_layers));
-    const bool use_tc3 = !use_g3 && lowrank && ((ws->apply_impl == 4) || (ws->apply_impl == 0 && apply_tc3_available(ws, n_layers)));
-    const bool use_tc2 = !use_tc3 && lowrank && (ws->apply_impl == 3);
-    const bool use_tc = !use_tc3 && !use_tc2 && lowrank && ((ws->apply_impl == 2) || (ws->apply_impl == 0 && apply_tc_available(ws) && n_layers <= 160));
-    const int tile_rows = use_tc2 ? apply_tc2_tile_rows() : ((use_tc || use_g3) ? 128 : SG_BM);
+    const bool use_tc3 = lowrank && (ws->apply_impl == 4 || (ws->apply_impl == 0 && apply_tc3_available(ws, n_layers)));
+    const bool use_g3 = !use_tc3 && lowrank && (ws->apply_impl == 5 || (ws->apply_impl == 0 && apply_gemm3x_available(ws, n_layers)));
+    const int tile_rows = use_g3 ? 128 : SG_BM;
     int tiles = 0; bool inplace = false;
     for (int l = 0; l < n_layers; ++l) {
         if (!W_old[l] || !W_new[l] || d[l] <= 0) { set_error("layer %d: null pointer or d <= 0", l); return UCE_E_ARG; }
@@ -188,7 +173,7 @@ int apply_dev(uce_ws* ws, const float* const* W_old, float* const* W_new, const 
         if (prof) UCE_CUDA(cudaEventRecord(ws->pev[4], st));
         return 0;
     }
-    const size_t need = use_g3 ? (size_t)tiles * 128 * r_pad : (use_tc || use_tc2 || use_tc3) ? 0 : (ws->dense ? (inplace ? (size_t)tiles * SG_BM * K : 0) : (size_t)tiles * SG_BM * r_pad);
+    const size_t need = use_g3 ? (size_t)tiles * 128 * r_pad : use_tc3 ? 0 : (ws->dense ? (inplace ? (size_t)tiles * SG_BM * K : 0) : (size_t)tiles * SG_BM * r_pad);
     // P scratch is shared by successive apply calls; they are ordered on one stream (host path: s_compute)
     if (need > ws->P_cap) {
         if (ws->P) { UCE_CUDA(cudaStreamSynchronize(st)); UCE_CUDA(cudaFree(ws->P)); ws->P = nullptr; }
@@ -197,17 +182,10 @@ int apply_dev(uce_ws* ws, const float* const* W_old, float* const* W_new, const 
     }
     if (!ws->dense) {
         if (use_g3) {
-            int rc = use_g3s ? apply_gemm3x_ss_highrank(ws, dl, hl, n_layers, tiles, st, &launches)
-                             : apply_gemm3x_highrank(ws, dl, hl, n_layers, tiles, st, &launches);
+            int rc = apply_gemm3x_highrank(ws, dl, hl, n_layers, tiles, st, &launches);
             if (rc) return rc;
         } else if (use_tc3) {
             int rc = apply_tc3_lowrank(ws, dl, hl, n_layers, tiles, st, &launches, prof ? ws->pev[2] : nullptr);
-            if (rc) return rc;
-        } else if (use_tc2) {
-            int rc = apply_tc2_lowrank(ws, dl, hl, n_layers, tiles, tile_rows, st, &launches);
-            if (rc) return rc;
-        } else if (use_tc) {
-            int rc = apply_tc_lowrank(ws, dl, hl, n_layers, tiles, st, &launches);
             if (rc) return rc;
         } else {
             apply_simt_p_kernel<<<dim3(ceil_div(r_pad, SG_BN), tiles), SG_THREADS, 0, st>>>(dl, n_layers, K, r_pad, ws->E, ws->P);

@@ -1,9 +1,10 @@
-// Fused low-rank apply, third generation: ONE CTA per SM that carries TWO row blocks through a single E / Qt stream.
+// Fused low-rank apply (rank pad <= 64): ONE CTA per SM that carries TWO row blocks through a single E / Qt stream.
 //
 //   W_new[rows,:] = W_old[rows,:] + (W_old[rows,:] E^T) Q            (uce_sd_erase.py:45-82, see apply.cu)
 //
-// Same algebra, operands and fp32 fidelity (3xTF32, lo.lo dropped) as apply_tc.cu / apply_tc2.cu.  Why a third shape:
-// the timelines and ncu captures of apply_tc2.cu (profiles/) show that an SM moves ~35-45 B/clk through TMA whatever
+// fp32 fidelity through 3xTF32 (hi.hi + hi.lo + lo.hi, lo.lo dropped).  Why this shape (two earlier ones — one 128-row tile per
+// CTA, then two co-resident CTAs per SM — were measured and retired, profiles/r01_apply_history.txt):
+// their timelines and ncu captures show that an SM moves ~35-45 B/clk through TMA whatever
 // the ring depths are, and that a row tile of 128 rows costs 1.57 MB of TMA ingest: its W rows twice (phase A, then the
 // addend of phase B; 2 x 393 KB) plus the WHOLE of E_hi|E_lo and Qt_hi|Qt_lo (2 x 393 KB) — the low-rank operands are
 // as large as the tile.  Two co-resident 128-row CTAs therefore stream E and Qt twice per SM, and with 200 tiles on

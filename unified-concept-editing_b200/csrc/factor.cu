@@ -20,6 +20,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <cstdint>
 
 namespace uce {
 
@@ -124,6 +125,27 @@ __global__ void emit_q_kernel(const double* X, int ldx, int from_x, int rank, in
         Q[(long)j * K + k] = 0.f;
     }
     Qt[(long)k * rank_pad + j] = v;
+}
+
+// hi = rna_tf32(x), lo = x - hi for the pre-split B operands of the tcgen05 apply kernels (E and Qt)
+__global__ void split_tf32_kernel(const float* __restrict__ x, float* __restrict__ hi, float* __restrict__ lo, long n) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const float v = x[i];
+        uint32_t u;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
+        const float h = __uint_as_float(u);
+        hi[i] = h; lo[i] = v - h;
+    }
+}
+static int split_operands(uce_ws* ws, cudaStream_t st, int* launches) {
+    const long n = (long)ws->rank_pad * ws->K;
+    split_tf32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ws->E, ws->E_hi, ws->E_lo, n);
+    UCE_LAUNCH_CHECK();
+    split_tf32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ws->Qt, ws->Qt_hi, ws->Qt_lo, n);
+    UCE_LAUNCH_CHECK();
+    *launches += 2;
+    return 0;
 }
 
 #define UCE_RT(expr)                                                                             \
@@ -276,8 +298,8 @@ int factor_dev(uce_ws* ws, const float* C, const float* G, const float* scales, 
         UCE_RT((simt_gemm<float, float, double, float>(st, K, K, n_edit, ws->Q, 1, K, ws->E, 1, K, ws->Dt, K)));
     }
     ws->mode = dual ? 1 : 2;
-    if ((apply_tc_available(ws) && ws->apply_impl != 1) || ((ws->apply_impl == 5 || ws->apply_impl == 6) && !ws->dense && ws->rank > 0)) {      // tf32 hi/lo splits of E and Qt
-        int rc2 = apply_tc_split_operands(ws, st, &launches);
+    if (!ws->dense && ws->rank > 0) {      // tf32 hi/lo splits of E and Qt: always, so the apply implementation may be chosen after the factor
+        int rc2 = split_operands(ws, st, &launches);
         if (rc2) return rc2;
     }
     ws->launches_factor = launches;

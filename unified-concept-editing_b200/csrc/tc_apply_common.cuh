@@ -1,4 +1,4 @@
-// Device helpers shared by the tcgen05 apply kernels apply_tc2.cu / apply_tc3.cu (sm_100a): TMEM access, TS-form MMA,
+// Device helpers shared by the tcgen05 apply kernels apply_tc3.cu / apply_gemm3x.cu (sm_100a): TMEM access, TS-form MMA,
 // L2 policies, swizzled shared-memory vectors, TMA stores, tf32 split.
 #pragma once
 #include "uce_ws.h"

@@ -19,7 +19,7 @@ struct uce_ws {
     int dense = 0;
     float lamb = 0.f;
     int launches_factor = 0, launches_apply = 0;
-    int apply_impl = 0;   // 0 auto, 1 simt, 2 tcgen05
+    int apply_impl = 0;   // 0 auto, 1 fp32 SIMT, 4 two-block tcgen05 (rank pad <= 64), 5 two-GEMM tcgen05 (any rank)
     int debug = 0;
     int force_general = 0;   // 1: always use the general blocked factor (testing)
     int profile = 0;
@@ -69,7 +69,4 @@ int apply_dev(uce_ws* ws, const float* const* W_old, float* const* W_new, const 
 // factor_small.cu
 bool factor_small_applicable(const uce_ws* ws, int n, int n_edit, bool dual);
 int factor_small(uce_ws* ws, const float* C, const float* G, int n, int n_pres, int n_edit, cudaStream_t st, int* launches);
-// apply_tc.cu
-bool apply_tc_available(const uce_ws* ws);
-int apply_tc_split_operands(uce_ws* ws, cudaStream_t st, int* launches);
 }  // namespace uce

@@ -193,7 +193,7 @@ struct Builder {
         const float* ga = W(p + ".weight").f; const float* be = W(p + ".bias").f;
         const int G = u->cfg.norm_groups;
         if (u->n_gn >= sd_unet::MAX_GN) { rc = rc ? rc : SD_E_STATE; sd_err("too many GroupNorm calls"); return; }
-        float* stats = u->gn_stats + (size_t)(u->n_gn++) * u->NB * G * 2;      // own slice; all cleared by one memset per forward
+        float* stats = u->gn_stats + (size_t)(u->n_gn++) * uce::op_groupnorm_ws_floats(u->NB, G);      // own workspace (statistics, tickets, per-CTA partials); zeroed once
         push([=](cudaStream_t st) { return uce::op_groupnorm(x.p, y.p, x.n, x.h * x.w, x.c, G, stats, ga, be, eps, silu, st); });
     }
     void layernorm(const bf16* x, bf16* y, long rows, int C, const std::string& p) {
@@ -331,7 +331,11 @@ int build_schedule(sd_unet* u) {
     if ((rc = u->alloc(&u->eps, (size_t)NB * c.out_channels * H * W))) return rc;
     if ((rc = u->alloc(&u->d_t, 4))) return rc;
     SD_CUDA(cudaMallocHost((void**)&u->h_t, sizeof(float)));
-    if ((rc = u->alloc(&u->gn_stats, (size_t)sd_unet::MAX_GN * NB * c.norm_groups * 2))) return rc;
+    {
+        const size_t gn_floats = (size_t)sd_unet::MAX_GN * uce::op_groupnorm_ws_floats(NB, c.norm_groups);
+        if ((rc = u->alloc(&u->gn_stats, gn_floats))) return rc;
+        SD_CUDA(cudaMemset(u->gn_stats, 0, gn_floats * sizeof(float)));      // ticket counters start at zero and rearm themselves
+    }
     u->splitk_cap = (size_t)(3 * u->sm_count) * 128 * 128;      // gemm_choose_ksplit targets ~2 CTAs per SM of 128 x 128 partial tiles
     if ((rc = u->alloc(&u->splitk_ws, u->splitk_cap))) return rc;
     {   // attention scratch: largest (L x Lk) over the attention levels
@@ -345,7 +349,6 @@ int build_schedule(sd_unet* u) {
         if ((rc = u->alloc(&u->P_scratch, (size_t)NB * c.heads * mx))) return rc;
     }
     // ---- inputs ----
-    B.push([u](cudaStream_t st) { return (int)cudaMemsetAsync(u->gn_stats, 0, (size_t)u->n_gn * u->NB * u->cfg.norm_groups * 2 * sizeof(float), st); });
     {
         float* cf = u->ctx_f32; bf16* cb = u->ctx; const long n = (long)NB * c.context_len * c.cross_attention_dim;
         B.to_ctx = true;

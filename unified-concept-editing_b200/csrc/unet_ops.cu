@@ -34,22 +34,26 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 __device__ __forceinline__ float silu_f(float x) { return x / (1.f + __expf(-x)); }
 
 // ---------------------------------------------------------------------------------------------- GroupNorm
-// stats[(img*G + g)*2 + {0,1}] += (sum, sum of squares) over the pixels of this CTA's slab.
-// grid (slabs, NB); block 256 laid out as (pixel lane, 8-channel column): consecutive threads read consecutive 16 B of a
-// pixel (coalesced), 256 / (C/8) pixel lanes walk the slab; per-channel partial sums stay in registers and are binned into
-// the group accumulators (shared, then one global atomic per group and CTA) at the end.
+// Statistics, bit-reproducible (no floating-point atomics anywhere):
+//   1. grid (slabs, NB); block 256 laid out as (pixel lane, 8-channel column): consecutive threads read consecutive 16 B of a
+//      pixel (coalesced), 256 / (C/8) pixel lanes walk the slab; per-channel partial sums stay in registers;
+//   2. the per-(pixel lane, channel) sums go to shared memory; warp w then folds groups w, w + 8, ... — every lane walks a
+//      fixed sequence of (pixel lane, channel) cells and the warp finishes with a fixed xor-shuffle tree;
+//   3. the CTA writes its 2 G partials to its own slot of `partials`; the CTA that draws the last ticket of the image (an
+//      INTEGER atomic) adds the slabs in slab order and writes stats[(img*G + g)*2 + {0,1}] = (sum, sum of squares); it
+//      also rearms the ticket counter, so the workspace needs clearing only once, when it is allocated.
+// Workspace per call (floats, see op_groupnorm_ws_floats): [NB * 2G stats | NB tickets | NB * slabs * 2G partials].
 __global__ void __launch_bounds__(256) gn_stats_kernel(const __nv_bfloat16* __restrict__ x, int HW, int C, int G, int pix_per_cta,
-                                                       float* __restrict__ stats) {
+                                                       float* __restrict__ stats, unsigned* __restrict__ tickets, float* __restrict__ partials) {
     pdl_launch(); pdl_wait();
-    extern __shared__ float red[];                 // [2 * G]
+    extern __shared__ float gsm[];                 // [lanes][C] sums | [lanes][C] sums of squares | [2 G] folded | [1] last flag
     const int img = blockIdx.y, p0 = blockIdx.x * pix_per_cta;
     const int vec_per_pix = C / 8, cpg = C / G;
-    for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) red[i] = 0.f;
-    __syncthreads();
     const __nv_bfloat16* base = x + ((long)img * HW + p0) * C;
     const int npix = min(pix_per_cta, HW - p0);
     const int tpc = min(vec_per_pix, (int)blockDim.x), lanes = blockDim.x / tpc;
     const int cl = threadIdx.x % tpc, pl = threadIdx.x / tpc;
+    float* sm_s = gsm; float* sm_ss = gsm + (size_t)lanes * C; float* red = gsm + (size_t)2 * lanes * C;
     if (pl < lanes) {
         for (int cv = cl; cv < vec_per_pix; cv += tpc) {
             float s[8], ss[8];
@@ -62,19 +66,47 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const __nv_bfloat16* __re
 #pragma unroll
                 for (int i = 0; i < 8; ++i) { s[i] += f[i]; ss[i] += f[i] * f[i]; }
             }
-            // channels of one 8-vector fall into at most two groups when cpg >= 8 (every SD level): pre-reduce per group
-            int g_prev = (cv * 8) / cpg; float a = 0.f, b = 0.f;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int g = (cv * 8 + i) / cpg;
-                if (g != g_prev) { atomicAdd(&red[2 * g_prev], a); atomicAdd(&red[2 * g_prev + 1], b); a = 0.f; b = 0.f; g_prev = g; }
-                a += s[i]; b += ss[i];
-            }
-            atomicAdd(&red[2 * g_prev], a); atomicAdd(&red[2 * g_prev + 1], b);
+            float4* ds = reinterpret_cast<float4*>(sm_s + (size_t)pl * C + cv * 8);
+            float4* dq = reinterpret_cast<float4*>(sm_ss + (size_t)pl * C + cv * 8);
+            ds[0] = make_float4(s[0], s[1], s[2], s[3]);     ds[1] = make_float4(s[4], s[5], s[6], s[7]);
+            dq[0] = make_float4(ss[0], ss[1], ss[2], ss[3]); dq[1] = make_float4(ss[4], ss[5], ss[6], ss[7]);
         }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) atomicAdd(&stats[(long)img * G * 2 + i], red[i]);
+    {
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+        const int cells = lanes * cpg;
+        for (int g = warp; g < G; g += nw) {
+            float a = 0.f, b = 0.f;
+            for (int e = lane; e < cells; e += 32) {
+                const int q = e / cpg, ch = g * cpg + (e - q * cpg);
+                a += sm_s[(size_t)q * C + ch]; b += sm_ss[(size_t)q * C + ch];
+            }
+            a = warp_sum_f(a); b = warp_sum_f(b);
+            if (lane == 0) { red[2 * g] = a; red[2 * g + 1] = b; }
+        }
+    }
+    __syncthreads();
+    const int slabs = gridDim.x;
+    float* mine = partials + ((size_t)img * slabs + blockIdx.x) * 2 * G;
+    for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) mine[i] = red[i];
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned t = atomicAdd(&tickets[img], 1u);
+        red[2 * G] = (t == (unsigned)slabs - 1u) ? 1.f : 0.f;
+    }
+    __syncthreads();
+    if (red[2 * G] != 0.f) {
+        __threadfence();
+        const float* all = partials + (size_t)img * slabs * 2 * G;
+        for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) {
+            float acc = 0.f;
+            for (int k = 0; k < slabs; ++k) acc += __ldcg(all + (size_t)k * 2 * G + i);
+            stats[(long)img * G * 2 + i] = acc;
+        }
+        if (threadIdx.x == 0) tickets[img] = 0u;
+    }
 }
 
 // y = (x - mean) * rstd * gamma + beta, optional SiLU.  One thread per 8-channel vector.
@@ -321,13 +353,27 @@ __global__ void __launch_bounds__(256) cfg_step_kernel(const float* __restrict__
 // ---------------------------------------------------------------------------------------------- launchers
 #define OPS_CHECK() do { cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) return (int)e_; } while (0)
 
-int op_groupnorm(const __nv_bfloat16* x, __nv_bfloat16* y, int NB, int HW, int C, int G, float* stats, const float* gamma, const float* beta,
+static inline int gn_slabs_target(int NB) { return NB >= 256 ? 1 : 256 / NB; }
+size_t op_groupnorm_ws_floats(int NB, int G) {
+    // stats + tickets + partials of the largest grid op_groupnorm launches (slabs <= gn_slabs_target + 1 after rounding)
+    return (size_t)NB * 2 * G + (size_t)NB + (size_t)NB * (gn_slabs_target(NB) + 1) * 2 * G;
+}
+int op_groupnorm(const __nv_bfloat16* x, __nv_bfloat16* y, int NB, int HW, int C, int G, float* ws, const float* gamma, const float* beta,
                  float eps, int silu, cudaStream_t st) {
-    // `stats` is this call's own zeroed slice (the engine clears every slice with one memset per forward)
-    const int slabs_target = max(1, 256 / NB);
+    // `ws` is this call's own workspace of op_groupnorm_ws_floats(NB, G) floats, zeroed ONCE when it was allocated (ticket counters)
+    if (C % 8 || C % G) return (int)cudaErrorInvalidValue;
+    float* stats = ws;
+    unsigned* tickets = reinterpret_cast<unsigned*>(ws + (size_t)NB * 2 * G);
+    float* partials = ws + (size_t)NB * 2 * G + NB;
+    const int slabs_target = gn_slabs_target(NB);
     int pix_per_cta = (HW + slabs_target - 1) / slabs_target;
     if (pix_per_cta < 8) pix_per_cta = HW < 8 ? HW : 8;
-    if (launch_k(gn_stats_kernel, dim3((HW + pix_per_cta - 1) / pix_per_cta, NB), dim3(256), 2 * G * sizeof(float), st, 1, x, HW, C, G, pix_per_cta, stats) != cudaSuccess) return (int)cudaGetLastError();
+    const int slabs = (HW + pix_per_cta - 1) / pix_per_cta;
+    if (slabs > slabs_target + 1) return (int)cudaErrorInvalidValue;
+    const int tpc = C / 8 < 256 ? C / 8 : 256, lanes = 256 / tpc;
+    const size_t smem = ((size_t)2 * lanes * C + 2 * G + 1) * sizeof(float);
+    if (smem > 48 * 1024) return (int)cudaErrorInvalidValue;
+    if (launch_k(gn_stats_kernel, dim3(slabs, NB), dim3(256), smem, st, 1, x, HW, C, G, pix_per_cta, stats, tickets, partials) != cudaSuccess) return (int)cudaGetLastError();
     OPS_CHECK();
     const long n_vec = (long)NB * HW * C / 8;
     if (launch_k(gn_apply_kernel, dim3((unsigned)((n_vec + 255) / 256)), dim3(256), 0, st, 1, x, y, n_vec, HW, C, G, stats, gamma, beta, eps, silu) != cudaSuccess) return (int)cudaGetLastError();

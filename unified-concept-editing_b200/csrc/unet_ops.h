@@ -7,7 +7,9 @@ namespace uce {
 // one time-embedding projection (ResnetBlock2D.time_emb_proj): out[NB, cout] fp32 = st_emb[NB, K] . w[cout, K]^T + bias
 struct TembJob { const __nv_bfloat16* w; const float* bias; float* out; int cout; int first_channel; };
 int op_temb_proj_all(const TembJob* jobs_dev, int n_jobs, int total_channels, const __nv_bfloat16* st_emb, int NB, int K, cudaStream_t st);
-int op_groupnorm(const __nv_bfloat16* x, __nv_bfloat16* y, int NB, int HW, int C, int G, float* stats, const float* gamma, const float* beta,
+// GroupNorm(+SiLU): `ws` = this call's own op_groupnorm_ws_floats(NB, G) floats, zeroed once at allocation (statistics are bit-reproducible)
+size_t op_groupnorm_ws_floats(int NB, int G);
+int op_groupnorm(const __nv_bfloat16* x, __nv_bfloat16* y, int NB, int HW, int C, int G, float* ws, const float* gamma, const float* beta,
                  float eps, int silu, cudaStream_t st);
 int op_layernorm(const __nv_bfloat16* x, __nv_bfloat16* y, long rows, int C, const float* gamma, const float* beta, float eps, cudaStream_t st);
 int op_softmax(const float* S, long lds, __nv_bfloat16* P, long ldp, long rows, int Lk, cudaStream_t st);

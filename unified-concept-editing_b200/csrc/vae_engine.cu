@@ -183,7 +183,7 @@ struct Builder {
         const float* ga = W(p + ".weight").f; const float* be = W(p + ".bias").f;
         const int G = v->cfg.norm_groups;
         if (v->n_gn >= sd_vae::MAX_GN) { fail("GroupNorm slot", p); return; }
-        float* stats = v->gn_stats + (size_t)(v->n_gn++) * v->NB * G * 2;      // own slice; all cleared by one memset per decode
+        float* stats = v->gn_stats + (size_t)(v->n_gn++) * uce::op_groupnorm_ws_floats(v->NB, G);      // own workspace (statistics, tickets, per-CTA partials); zeroed once
         push([=](cudaStream_t st) { return uce::op_groupnorm(x.p, y.p, x.n, x.h * x.w, x.c, G, stats, ga, be, 1e-6f, silu, st); });
     }
     // ResnetBlock2D without time embedding (temb_channels=None in the VAE), eps 1e-6.  Consumes x.
@@ -258,7 +258,11 @@ int build_schedule(sd_vae* v) {
     if ((rc = v->alloc(&v->z_in, (size_t)NB * 4 * hw))) return rc;
     if ((rc = v->alloc(&v->z_pq, (size_t)NB * 4 * hw))) return rc;
     if ((rc = v->alloc(&v->img4, (size_t)NB * 4 * HW))) return rc;
-    if ((rc = v->alloc(&v->gn_stats, (size_t)sd_vae::MAX_GN * NB * c.norm_groups * 2))) return rc;
+    {
+        const size_t gn_floats = (size_t)sd_vae::MAX_GN * uce::op_groupnorm_ws_floats(NB, c.norm_groups);
+        if ((rc = v->alloc(&v->gn_stats, gn_floats))) return rc;
+        VAE_CUDA(cudaMemset(v->gn_stats, 0, gn_floats * sizeof(float)));      // ticket counters start at zero and rearm themselves
+    }
     v->splitk_cap = (size_t)(3 * v->sm_count) * 128 * 128;
     if ((rc = v->alloc(&v->splitk_ws, v->splitk_cap))) return rc;
     {
@@ -278,7 +282,6 @@ int build_schedule(sd_vae* v) {
         if ((rc = v->alloc(&v->attn_bias, (size_t)top))) return rc;
         VAE_CUDA(cudaMemcpy(v->attn_bias, fb.data(), top * sizeof(float), cudaMemcpyHostToDevice));
     }
-    B.push([v](cudaStream_t st) { return (int)cudaMemsetAsync(v->gn_stats, 0, (size_t)v->n_gn * v->NB * v->cfg.norm_groups * 2 * sizeof(float), st); });
     {
         const float* zi = v->z_in; float* zo = v->z_pq; const float* w = B.W("post_quant_conv.weight").f; const float* b = B.W("post_quant_conv.bias").f;
         const float inv_sf = 1.f / c.scaling_factor;

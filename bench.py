@@ -173,9 +173,8 @@ def run_ours(args, rank, world, local_rank):
     if args.apply_impl is not None:
         solver.set_apply_impl(args.apply_impl)
 
-    def step(i):
-        solver.factor(Cd, Gd, prob["scales"], ne, lamb)
-        solver.apply(sets_in[i % R], sets_out[i % R])
+    def step(i):      # one complete edit: uce_edit_dev_f32 (factor + apply; the library overlaps what does not depend on the factor)
+        solver.edit(Cd, Gd, prob["scales"], ne, lamb, sets_in[i % R], sets_out[i % R], check=False)
 
     sampler = ClockSampler(local_rank)
     sampler.start()

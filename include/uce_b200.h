@@ -57,12 +57,12 @@ const char  *uce_last_error(void);
 int uce_ws_create(int device, int K, int max_rows, uce_ws **out);
 int uce_ws_destroy(uce_ws *ws);
 
-/* Select the apply kernel: 0 = auto (the fastest tcgen05 3xTF32 kernel that takes the shape), 1 = SIMT fp32,
- * 2 = tcgen05, one 128-row tile per CTA (rank pad <= 128), 3 = tcgen05, two co-resident CTAs per SM (rank pad <= 64),
- * 4 = tcgen05, two row blocks per CTA in one planned wave (rank pad <= 64, <= 96 projections per call),
- * 5 = tcgen05 high-rank two-GEMM apply (any rank pad; opt-in only: not yet validated on hardware, never chosen by 0),
- * 6 = the same with both MMA operands in shared memory (the raw fp32 tile is the tf32 hi operand; opt-in only, not yet run on hardware).
- * Returns the previous value. All are hand-written CUDA; there is no CPU path. */
+/* Select the apply kernel: 0 = auto (rank pad <= 64: the K-split two-kernel tcgen05 apply, 7; any other low-rank edit: the
+ * two-GEMM tcgen05 apply, 5; dense K x K factor: SIMT), 1 = SIMT fp32 (validation twin),
+ * 4 = tcgen05, fused one-kernel form, two row blocks per CTA in one planned wave (rank pad <= 64, K % 128 == 0),
+ * 5 = tcgen05 two-GEMM apply, P through an HBM scratch (any rank pad, K % 32 == 0),
+ * 7 = tcgen05 K-split apply: kernel A (partial products W E^T per K slice) + kernel B (update), rank pad <= 64, K % 32 == 0.
+ * Returns the previous value. All are hand-written CUDA (3xTF32, fp32 fidelity); there is no CPU path. */
 int uce_ws_set_apply_impl(uce_ws *ws, int impl);
 
 /* Host-only helper (no GPU needed): the row-block plan the two-block apply (impl 4) uses for `n_layers` projections of
@@ -108,6 +108,14 @@ int uce_factor_dev_f32(uce_ws *ws, const float *C, const float *G, const float *
  * W_new[l] may equal W_old[l] (in place). Pointer arrays and d[] are HOST arrays. */
 int uce_apply_dev_f32(uce_ws *ws, const float *const *W_old, float *const *W_new, const int *d,
                       int n_layers, void *stream);
+
+/* Factor + apply in ONE call on device buffers (same arguments as the two calls above, same results).  Knowing both halves lets the
+ * library take work off the critical path: the first kernel of the K-split apply (the partial products W_old E^T — the reference's
+ * guide outputs v* = W_old c, uce_sd_erase.py:45-53 — which need only E = G_e - C_e) runs on an internal stream WHILE the factor
+ * computes Q; only the update kernel waits for the factor.  Everything is ordered after the work already enqueued on `stream`
+ * and `stream` waits for all of it (safe under CUDA-graph capture: the internal stream joins and leaves the capture). */
+int uce_edit_dev_f32(uce_ws *ws, const float *C, const float *G, const float *scales_host, int n_rows, int n_edit, float lamb,
+                     const float *const *W_old, float *const *W_new, const int *d, int n_layers, void *stream);
 
 /* Whole edit with HOST buffers (the call a host-side integration makes): H2D of C, G and each
  * W_old[l], factor, apply, D2H of each W_new[l]; copies are pipelined against the kernels on

@@ -12,7 +12,7 @@ from uce_b200.synthetic import concept_rows, weights
 
 what = set((sys.argv[1] if len(sys.argv) > 1 else "solver,unet,vae").split(","))
 if "solver" in what:
-    for n_edit, n_pres, K, dims, impl, fimpl in [(10, 20, 256, [136, 64], 4, 0), (40, 20, 256, [136], 4, 1), (70, 10, 256, [200, 72], 5, 0), (10, 20, 256, [48], 1, 0)]:
+    for n_edit, n_pres, K, dims, impl, fimpl in [(10, 20, 256, [136, 64], 7, 0), (40, 20, 256, [136, 300, 72, 8], 7, 1), (10, 20, 256, [136, 64], 4, 0), (40, 20, 256, [136], 4, 1), (70, 10, 256, [200, 72], 5, 0), (10, 20, 256, [48], 1, 0)]:
         rows = concept_rows(n_edit + n_pres + n_edit, K, seed=n_edit)
         C, G = rows[: n_edit + n_pres], rows[n_edit + n_pres:]
         W = weights(dims, K, seed=4)

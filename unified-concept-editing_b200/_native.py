@@ -27,6 +27,8 @@ SIGNATURES = {
     "uce_ws_timings": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "uce_factor_dev_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_float), C.c_int, C.c_int, C.c_float, C.c_void_p]),
     "uce_apply_dev_f32": (C.c_int, [C.c_void_p, _PP_F, _PP_F, C.POINTER(C.c_int), C.c_int, C.c_void_p]),
+    "uce_edit_dev_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_float), C.c_int, C.c_int, C.c_float,
+                                   _PP_F, _PP_F, C.POINTER(C.c_int), C.c_int, C.c_void_p]),
     "uce_edit_host_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_float), C.c_int, C.c_int, C.c_float,
                                     _PP_F, _PP_F, C.POINTER(C.c_int), C.c_int]),
     "uce_ws_check": (C.c_int, [C.c_void_p, C.c_void_p]),

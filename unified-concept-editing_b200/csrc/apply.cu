@@ -17,6 +17,13 @@ namespace uce {
 bool apply_gemm3x_available(const uce_ws* ws, int n_layers);   // apply_gemm3x.cu
 int apply_gemm3x_highrank(uce_ws* ws, const LayerRef* layers_dev, const LayerRef* layers_host, int n_layers, int total_tiles,
                           cudaStream_t st, int* launches);
+bool apply_ab_available(const uce_ws* ws, int n_layers);    // apply_ab.cu
+int apply_ab_ksplit(int K);
+int apply_ab_plan(int sm_count, int ks, const int* d, int n_layers, int* block_rows, int* first_block);
+int apply_ab_lowrank(uce_ws* ws, const void* slots_dev, const void* slots_host, int n_slots, const LayerRef* layers_host, int n_layers,
+                     cudaStream_t st, int stage, int* launches, cudaEvent_t ev_mid);
+size_t apply_ab_slot_bytes();
+void apply_ab_fill_slots(void* slots_host, const LayerRef* layers_host, int n_layers);
 bool apply_tc3_available(const uce_ws* ws, int n_layers);   // apply_tc3.cu
 int apply_tc3_plan(int sm_count, const int* d, int n_layers, int* tile_rows, int* tile_begin);
 int apply_tc3_lowrank(uce_ws* ws, const LayerRef* layers_dev, const LayerRef* layers_host, int n_layers, int total_tiles,
@@ -108,21 +115,31 @@ __global__ void copy_layers_kernel(const LayerRef* layers, int n_layers, int K) 
     for (long i = threadIdx.x; i < (long)rows * K; i += blockDim.x) wn[i] = wo[i];
 }
 
+static bool choose_ab(const uce_ws* ws, int n_layers) {
+    const bool lowrank = !ws->dense && ws->rank > 0;
+    return lowrank && (ws->apply_impl == 7 || ws->apply_impl == 0) && apply_ab_available(ws, n_layers);
+}
+bool apply_stage_split(const uce_ws* ws, int n_layers) {
+    return ws->mode != 0 && choose_ab(ws, n_layers > 96 ? 96 : n_layers);
+}
+
 int apply_dev(uce_ws* ws, const float* const* W_old, float* const* W_new, const int* d, int n_layers, cudaStream_t st,
-              bool no_profile) {
+              bool no_profile, int stage) {
     int slot_begin = 0;
     const int K = ws->K;
     if (ws->mode == 0) { set_error("uce_apply before uce_factor"); return UCE_E_STATE; }
     // the two-block tcgen05 apply carries two tensor maps per projection as kernel parameters (96 projections per launch):
     // longer lists (SDXL: 140 projections) go through it in slices
     constexpr int TC3_MAX = 96;
+    if (stage != 0 && !choose_ab(ws, std::min(n_layers, TC3_MAX))) { set_error("staged apply needs the K-split path"); return UCE_E_STATE; }
     if (n_layers > TC3_MAX && !ws->dense && ws->rank > 0 && ws->apply_impl != 1 &&
-        (apply_tc3_available(ws, TC3_MAX) || apply_gemm3x_available(ws, TC3_MAX))) {
+        (apply_ab_available(ws, TC3_MAX) || apply_tc3_available(ws, TC3_MAX) || apply_gemm3x_available(ws, TC3_MAX))) {
+        if (stage != 0) { set_error("staged apply takes at most %d projections per call", TC3_MAX); return UCE_E_STATE; }
         int total_launches = 0;
         const bool prof = ws->profile && !no_profile;
         if (prof) UCE_CUDA(cudaEventRecord(ws->pev[2], st));
         for (int l0 = 0; l0 < n_layers; l0 += TC3_MAX) {
-            const int rc = apply_dev(ws, W_old + l0, W_new + l0, d + l0, std::min(TC3_MAX, n_layers - l0), st, true);
+            const int rc = apply_dev(ws, W_old + l0, W_new + l0, d + l0, std::min(TC3_MAX, n_layers - l0), st, true, 0);
             if (rc) return rc;
             total_launches += ws->launches_apply;
         }
@@ -138,10 +155,12 @@ int apply_dev(uce_ws* ws, const float* const* W_old, float* const* W_new, const 
     slot_begin = ws->ring_pos;
     ws->ring_pos += n_layers;
     LayerRef* hl = ws->h_layers + slot_begin;
-    // apply_impl: 0 auto (two-block tcgen05 kernel for rank pads <= 64, the two-GEMM tcgen05 apply for every other low-rank edit,
-    // fp32 SIMT for the dense K x K form), 1 fp32 SIMT (validation twin), 4 apply_tc3.cu, 5 apply_gemm3x.cu
+    // apply_impl: 0 auto (K-split two-kernel tcgen05 apply for rank pads <= 64, the two-GEMM tcgen05 apply for every other low-rank
+    // edit, fp32 SIMT for the dense K x K form), 1 fp32 SIMT (validation twin), 4 apply_tc3.cu (fused one-kernel form), 5 apply_gemm3x.cu,
+    // 7 apply_ab.cu
     const bool lowrank = !ws->dense && ws->rank > 0;
-    const bool use_tc3 = lowrank && (ws->apply_impl == 4 || (ws->apply_impl == 0 && apply_tc3_available(ws, n_layers)));
+    const bool use_ab = choose_ab(ws, n_layers);
+    const bool use_tc3 = !use_ab && lowrank && (ws->apply_impl == 4 || (ws->apply_impl == 0 && apply_tc3_available(ws, n_layers)));
     const bool use_g3 = !use_tc3 && lowrank && (ws->apply_impl == 5 || (ws->apply_impl == 0 && apply_gemm3x_available(ws, n_layers)));
     const int tile_rows = use_g3 ? 128 : SG_BM;
     int tiles = 0; bool inplace = false;
@@ -149,7 +168,31 @@ int apply_dev(uce_ws* ws, const float* const* W_old, float* const* W_new, const 
         if (!W_old[l] || !W_new[l] || d[l] <= 0) { set_error("layer %d: null pointer or d <= 0", l); return UCE_E_ARG; }
         inplace |= (W_old[l] == W_new[l]);
     }
-    if (use_tc3) {
+    const int ab_ks = use_ab ? apply_ab_ksplit(K) : 1;
+    void* slots_h = nullptr; void* slots_d = nullptr;
+    if (use_ab) {
+        std::vector<int> trows(n_layers), tbeg(n_layers);
+        tiles = apply_ab_plan(ws->sm_count, ab_ks, d, n_layers, trows.data(), tbeg.data());      // tiles = row blocks
+        for (int l = 0; l < n_layers; ++l) hl[l] = LayerRef{W_old[l], W_new[l], d[l], tbeg[l], trows[l]};
+        const size_t sb = apply_ab_slot_bytes();
+        if (!ws->slots_dev) {
+            ws->slots_cap = 32768;
+            UCE_CUDA(cudaMalloc(&ws->slots_dev, (size_t)ws->slots_cap * sb));
+            UCE_CUDA(cudaMallocHost(&ws->h_slots, (size_t)ws->slots_cap * sb));
+        }
+        if (tiles > ws->slots_cap) { set_error("too many row blocks per call (%d > %d)", tiles, ws->slots_cap); return UCE_E_STATE; }
+        if (ws->slots_pos + tiles > ws->slots_cap) ws->slots_pos = 0;      // ring, for the same reason as the layer table
+        slots_h = (char*)ws->h_slots + (size_t)ws->slots_pos * sb;
+        slots_d = (char*)ws->slots_dev + (size_t)ws->slots_pos * sb;
+        if (stage != 2) {
+            apply_ab_fill_slots(slots_h, hl, n_layers);
+            UCE_CUDA(cudaMemcpyAsync(slots_d, slots_h, (size_t)tiles * sb, cudaMemcpyHostToDevice, st));
+            ws->slots_last = ws->slots_pos;
+        } else {                                                           // stage 2 reuses the table stage 1 uploaded
+            slots_d = (char*)ws->slots_dev + (size_t)ws->slots_last * sb;
+        }
+        if (stage != 1) ws->slots_pos += tiles;
+    } else if (use_tc3) {
         std::vector<int> trows(n_layers), tbeg(n_layers);
         tiles = apply_tc3_plan(ws->sm_count, d, n_layers, trows.data(), tbeg.data());
         for (int l = 0; l < n_layers; ++l) hl[l] = LayerRef{W_old[l], W_new[l], d[l], tbeg[l], trows[l]};
@@ -173,7 +216,7 @@ int apply_dev(uce_ws* ws, const float* const* W_old, float* const* W_new, const 
         if (prof) UCE_CUDA(cudaEventRecord(ws->pev[4], st));
         return 0;
     }
-    const size_t need = use_g3 ? (size_t)tiles * 128 * r_pad : use_tc3 ? 0 : (ws->dense ? (inplace ? (size_t)tiles * SG_BM * K : 0) : (size_t)tiles * SG_BM * r_pad);
+    const size_t need = use_ab ? (size_t)ab_ks * tiles * 128 * r_pad : use_g3 ? (size_t)tiles * 128 * r_pad : use_tc3 ? 0 : (ws->dense ? (inplace ? (size_t)tiles * SG_BM * K : 0) : (size_t)tiles * SG_BM * r_pad);
     // P scratch is shared by successive apply calls; they are ordered on one stream (host path: s_compute)
     if (need > ws->P_cap) {
         if (ws->P) { UCE_CUDA(cudaStreamSynchronize(st)); UCE_CUDA(cudaFree(ws->P)); ws->P = nullptr; }
@@ -181,7 +224,11 @@ int apply_dev(uce_ws* ws, const float* const* W_old, float* const* W_new, const 
         UCE_CUDA(cudaMalloc(&ws->P, ws->P_cap * sizeof(float)));
     }
     if (!ws->dense) {
-        if (use_g3) {
+        if (use_ab) {
+            int rc = apply_ab_lowrank(ws, slots_d, slots_h, tiles, hl, n_layers, st, stage, &launches, prof ? ws->pev[3] : nullptr);
+            if (rc) return rc;
+            if (prof && stage == 0) ws->pev_mid = 1;
+        } else if (use_g3) {
             int rc = apply_gemm3x_highrank(ws, dl, hl, n_layers, tiles, st, &launches);
             if (rc) return rc;
         } else if (use_tc3) {

@@ -138,13 +138,11 @@ __global__ void split_tf32_kernel(const float* __restrict__ x, float* __restrict
         hi[i] = h; lo[i] = v - h;
     }
 }
-static int split_operands(uce_ws* ws, cudaStream_t st, int* launches) {
+static int split_operand(uce_ws* ws, const float* x, float* hi, float* lo, cudaStream_t st, int* launches) {
     const long n = (long)ws->rank_pad * ws->K;
-    split_tf32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ws->E, ws->E_hi, ws->E_lo, n);
+    split_tf32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, hi, lo, n);
     UCE_LAUNCH_CHECK();
-    split_tf32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ws->Qt, ws->Qt_hi, ws->Qt_lo, n);
-    UCE_LAUNCH_CHECK();
-    *launches += 2;
+    *launches += 1;
     return 0;
 }
 
@@ -260,6 +258,11 @@ int factor_dev(uce_ws* ws, const float* C, const float* G, const float* scales, 
     pack_rows_kernel<<<n + (ws->rank_pad - n_edit), 256, 0, st>>>(C, G, ws->src_idx, ws->diag_add, n, n_pres, ws->rank_pad, K,
                                                                   ws->Cp, ws->E, dual ? nullptr : ws->Cs64);
     UCE_RT(cudaGetLastError());
+    if (!ws->dense) {      // tf32 hi/lo split of E right away: the apply's first kernel needs nothing else (uce_edit_dev_f32 forks here)
+        int rc2 = split_operand(ws, ws->E, ws->E_hi, ws->E_lo, st, &launches);
+        if (rc2) return rc2;
+        if (ws->want_ev_E) { UCE_CUDA(cudaEventRecord(ws->ev_E, st)); ws->ev_E_recorded = 1; }
+    }
 
     const int n_sys = dual ? n : K;
     const int n_pad = round_up(n_sys, UCE_NB);
@@ -298,8 +301,8 @@ int factor_dev(uce_ws* ws, const float* C, const float* G, const float* scales, 
         UCE_RT((simt_gemm<float, float, double, float>(st, K, K, n_edit, ws->Q, 1, K, ws->E, 1, K, ws->Dt, K)));
     }
     ws->mode = dual ? 1 : 2;
-    if (!ws->dense && ws->rank > 0) {      // tf32 hi/lo splits of E and Qt: always, so the apply implementation may be chosen after the factor
-        int rc2 = split_operands(ws, st, &launches);
+    if (!ws->dense && ws->rank > 0) {      // tf32 hi/lo split of Qt: always, so the apply implementation may be chosen after the factor
+        int rc2 = split_operand(ws, ws->Qt, ws->Qt_hi, ws->Qt_lo, st, &launches);
         if (rc2) return rc2;
     }
     ws->launches_factor = launches;

@@ -493,6 +493,9 @@ int factor_small(uce_ws* ws, const float* C, const float* G, int n, int n_pres, 
     const int nt = n_pad / FS_NB;
     gram_splitk_kernel<<<dim3(nt * (nt + 1) / 2, ceil_div(K, FS_KSPLIT)), 256, 0, st>>>(ws->Cp, n, K, ws->H, n_pad);
     UCE_LAUNCH_CHECK(); ++*launches;
+    // E and its split are complete (pack kernel) and the many-CTA Gram kernel is behind us: from here on the factor is one CTA wide,
+    // the point where uce_edit_dev_f32 lets the apply's first kernel (which needs E only) start on its own stream
+    if (ws->want_ev_E) { UCE_CUDA(cudaEventRecord(ws->ev_E, st)); ws->ev_E_recorded = 1; }
     if (ws->debug) {
         if (!ws->Hcopy) UCE_CUDA(cudaMalloc(&ws->Hcopy, (size_t)ws->sys_max * ws->sys_max * sizeof(double)));
         UCE_CUDA(cudaMemcpyAsync(ws->Hcopy, ws->H, (size_t)n_pad * n_pad * sizeof(double), cudaMemcpyDeviceToDevice, st));

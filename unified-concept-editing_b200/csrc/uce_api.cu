@@ -85,12 +85,15 @@ int uce_ws_destroy(uce_ws* ws) {
     void* dev[] = {ws->Cp, ws->Cs64, ws->E, ws->Q, ws->Qt, ws->Dt, ws->E_hi, ws->E_lo, ws->Qt_hi, ws->Qt_lo, ws->H, ws->Hcopy, ws->Linv, ws->X, ws->src_idx,
                    ws->diag_add, ws->flag, ws->P, ws->layers_dev, ws->hostpath_C, ws->hostpath_G, ws->hostpath_W};
     for (void* p : dev) if (p) cudaFree(p);
-    void* host[] = {ws->h_src_idx, ws->h_diag_add, ws->h_layers, ws->h_flag};
+    if (ws->slots_dev) cudaFree(ws->slots_dev);
+    void* host[] = {ws->h_src_idx, ws->h_diag_add, ws->h_layers, ws->h_flag, ws->h_slots};
     for (void* p : host) if (p) cudaFreeHost(p);
     for (auto e : ws->pev) if (e) cudaEventDestroy(e);
     if (ws->ev_stage) cudaEventDestroy(ws->ev_stage);
     for (auto e : ws->ev_h2d) cudaEventDestroy(e);
     for (auto e : ws->ev_done) cudaEventDestroy(e);
+    if (ws->s_side) cudaStreamDestroy(ws->s_side);
+    for (cudaEvent_t e : {ws->ev_fork, ws->ev_E, ws->ev_A}) if (e) cudaEventDestroy(e);
     if (ws->s_compute) cudaStreamDestroy(ws->s_compute);
     if (ws->s_h2d) cudaStreamDestroy(ws->s_h2d);
     if (ws->s_d2h) cudaStreamDestroy(ws->s_d2h);
@@ -179,6 +182,53 @@ int uce_apply_dev_f32(uce_ws* ws, const float* const* W_old, float* const* W_new
     if (!ws || !W_old || !W_new || !d || n_layers <= 0) { set_error("uce_apply: bad argument"); return UCE_E_ARG; }
     UCE_CUDA(cudaSetDevice(ws->device));
     return apply_dev(ws, W_old, W_new, d, n_layers, (cudaStream_t)stream, false);
+}
+
+// Fork / join of the K-split apply's first kernel around the factor (see the header).
+static int edit_dev(uce_ws* ws, const float* C, const float* G, const float* scales, int n_rows, int n_edit, float lamb,
+                    const float* const* W_old, float* const* W_new, const int* d, int n_layers, cudaStream_t st, bool no_profile) {
+    if (!ws->s_side) {
+        UCE_CUDA(cudaStreamCreateWithFlags(&ws->s_side, cudaStreamNonBlocking));
+        UCE_CUDA(cudaEventCreateWithFlags(&ws->ev_fork, cudaEventDisableTiming));
+        UCE_CUDA(cudaEventCreateWithFlags(&ws->ev_E, cudaEventDisableTiming));
+        UCE_CUDA(cudaEventCreateWithFlags(&ws->ev_A, cudaEventDisableTiming));
+    }
+    const bool prof = ws->profile && !no_profile;
+    // profiling brackets each kernel with events on `stream`: everything stays serial there, so that the durations are per kernel
+    const bool overlap = !prof && getenv("UCE_NO_OVERLAP") == nullptr && n_layers <= 96;
+    if (overlap) UCE_CUDA(cudaEventRecord(ws->ev_fork, st));      // W_old is ready here (stream order of the caller)
+    ws->want_ev_E = overlap ? 1 : 0;
+    ws->ev_E_recorded = 0;
+    if (prof) UCE_CUDA(cudaEventRecord(ws->pev[0], st));
+    int rc = factor_dev(ws, C, G, scales, n_rows, n_edit, lamb, st);
+    ws->want_ev_E = 0;
+    if (prof) UCE_CUDA(cudaEventRecord(ws->pev[1], st));
+    if (rc) return rc;
+    if (overlap && ws->ev_E_recorded && ws->rank > 0 && apply_stage_split(ws, n_layers)) {
+        UCE_CUDA(cudaStreamWaitEvent(ws->s_side, ws->ev_fork, 0));
+        UCE_CUDA(cudaStreamWaitEvent(ws->s_side, ws->ev_E, 0));
+        rc = apply_dev(ws, W_old, W_new, d, n_layers, ws->s_side, true, 1);
+        const int la = ws->launches_apply;
+        if (rc) return rc;
+        UCE_CUDA(cudaEventRecord(ws->ev_A, ws->s_side));
+        UCE_CUDA(cudaStreamWaitEvent(st, ws->ev_A, 0));
+        if (prof) UCE_CUDA(cudaEventRecord(ws->pev[2], st));
+        rc = apply_dev(ws, W_old, W_new, d, n_layers, st, true, 2);
+        ws->launches_apply += la;
+        ws->pev_mid = 0;
+        if (prof) UCE_CUDA(cudaEventRecord(ws->pev[4], st));
+        return rc;
+    }
+    return apply_dev(ws, W_old, W_new, d, n_layers, st, no_profile, 0);      // records pev[2..4] itself when profiling
+}
+
+int uce_edit_dev_f32(uce_ws* ws, const float* C, const float* G, const float* scales_host, int n_rows, int n_edit, float lamb,
+                     const float* const* W_old, float* const* W_new, const int* d, int n_layers, void* stream) {
+    int rc = check_factor_args(ws, C, G, scales_host, n_rows, n_edit);
+    if (rc) return rc;
+    if (!W_old || !W_new || !d || n_layers <= 0) { set_error("uce_edit_dev: bad layer arguments"); return UCE_E_ARG; }
+    UCE_CUDA(cudaSetDevice(ws->device));
+    return edit_dev(ws, C, G, scales_host, n_rows, n_edit, lamb, W_old, W_new, d, n_layers, (cudaStream_t)stream, false);
 }
 
 int uce_ws_check(uce_ws* ws, void* stream) {

@@ -45,6 +45,9 @@ struct uce_ws {
     uce::LayerRef* layers_dev = nullptr;
     int layers_cap = 0;
     int ring_pos = 0;
+    void* slots_dev = nullptr;   // row-block table of the K-split apply (apply_ab.cu), staged like the layer table
+    void* h_slots = nullptr;
+    int slots_cap = 0, slots_pos = 0, slots_last = 0;
     int stage_pending = 0;
     cudaEvent_t ev_stage = nullptr;   // marks consumption of the factor's pinned staging
     // ---- pinned host staging ----
@@ -54,6 +57,9 @@ struct uce_ws {
     int*    h_flag = nullptr;
     // ---- host-buffer path (uce_edit_host_f32) ----
     cudaStream_t s_compute = nullptr, s_h2d = nullptr, s_d2h = nullptr;
+    cudaStream_t s_side = nullptr;                     // kernel A of the K-split apply runs here while the factor computes Q (uce_edit_dev_f32)
+    cudaEvent_t ev_fork = nullptr, ev_E = nullptr, ev_A = nullptr;
+    int want_ev_E = 0, ev_E_recorded = 0;              // factor_dev records ev_E once E / E_hi / E_lo are complete (and the Gram kernel is enqueued)
     float* hostpath_C = nullptr; float* hostpath_G = nullptr;
     float* hostpath_W = nullptr; size_t hostpath_W_cap = 0;   // device staging for all layers (in place)
     std::vector<cudaEvent_t> ev_h2d, ev_done;
@@ -64,8 +70,10 @@ namespace uce {
 int factor_dev(uce_ws* ws, const float* C, const float* G, const float* scales_host, int n_rows, int n_edit,
                float lamb, cudaStream_t st);
 // apply.cu
+// stage 0: the whole apply on `st`.  K-split apply only (apply_stage_split): stage 1 = partial products (needs E), stage 2 = update (needs Q)
 int apply_dev(uce_ws* ws, const float* const* W_old, float* const* W_new, const int* d, int n_layers,
-              cudaStream_t st, bool no_profile = false);
+              cudaStream_t st, bool no_profile = false, int stage = 0);
+bool apply_stage_split(const uce_ws* ws, int n_layers);   // true when apply_dev would take the two-kernel K-split path for this edit
 // factor_small.cu
 bool factor_small_applicable(const uce_ws* ws, int n, int n_edit, bool dual);
 int factor_small(uce_ws* ws, const float* C, const float* G, int n, int n_pres, int n_edit, cudaStream_t st, int* launches);

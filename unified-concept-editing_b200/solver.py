@@ -13,7 +13,7 @@ import torch
 
 from . import _native as N
 
-APPLY_AUTO, APPLY_SIMT, APPLY_TCGEN05, APPLY_TCGEN05_2CTA, APPLY_TCGEN05_2BLOCK, APPLY_TCGEN05_HIGHRANK, APPLY_TCGEN05_HIGHRANK_SS = 0, 1, 2, 3, 4, 5, 6
+APPLY_AUTO, APPLY_SIMT, APPLY_TCGEN05_FUSED, APPLY_TCGEN05_TWO_GEMM, APPLY_TCGEN05_KSPLIT = 0, 1, 4, 5, 7
 
 
 def _ptr(t: torch.Tensor) -> int:
@@ -117,6 +117,30 @@ class EditSolver:
             N.check(N.lib().uce_ws_check(self._h, self._stream()))
 
     def edit(self, C_rows, G_rows, scales, n_edit, lamb, W_old, W_new=None, check=True):
+        """Factor + apply in one call (uce_edit_dev_f32): the library overlaps the part of the apply that does not need the factor."""
+        self._check_rows(C_rows, G_rows, scales, n_edit)
+        Cd = C_rows.to(self.device, torch.float32).contiguous()
+        Gd = G_rows.to(self.device, torch.float32).contiguous() if n_edit else None
+        sc = (C.c_float * len(scales))(*[float(s) for s in scales])
+        L = len(W_old)
+        for w in W_old:
+            if w.device != self.device or w.dtype != torch.float32 or not w.is_contiguous() or w.dim() != 2 or w.shape[1] != self.K:
+                raise ValueError("W_old must be contiguous fp32 [d,K] tensors on the solver's device")
+        if W_new is None:
+            W_new = [torch.empty_like(w) for w in W_old]
+        po = (C.c_void_p * L)(*[_ptr(w) for w in W_old])
+        pn = (C.c_void_p * L)(*[_ptr(w) for w in W_new])
+        dd = (C.c_int * L)(*[int(w.shape[0]) for w in W_old])
+        with torch.cuda.device(self.device):
+            N.check(N.lib().uce_edit_dev_f32(self._h, C.c_void_p(_ptr(Cd)), C.c_void_p(_ptr(Gd)) if n_edit else None, sc, Cd.shape[0],
+                                             int(n_edit), float(lamb), po, pn, dd, L, self._stream()))
+        self._keep = [Cd, Gd]
+        if check:
+            self.check()
+        return list(W_new)
+
+    def edit_two_calls(self, C_rows, G_rows, scales, n_edit, lamb, W_old, W_new=None, check=True):
+        """The same edit through uce_factor_dev_f32 + uce_apply_dev_f32 (everything serial on the current stream)."""
         self.factor(C_rows, G_rows, scales, n_edit, lamb)
         out = self.apply(W_old, W_new)
         if check:

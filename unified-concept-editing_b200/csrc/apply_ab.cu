@@ -20,9 +20,10 @@
 //     chain (measured: 7e-9 x K relative to the update for the fused kernel).  The split shortens the chain to K / ks / 8 steps
 //     of three MMAs; ks is chosen so that a slice has at most 512 columns.
 //
-// Both kernels: 8 transform / epilogue warps (two sets of four; thread = row = TMEM lane; a set takes every other work item),
-// one W TMA warp, one E / Qt TMA warp, two MMA-issuing warps (every other item each: one block's MMAs execute while the other
-// issuer waits on its barriers).  fp32 fidelity through 3xTF32 (hi.hi + hi.lo + lo.hi; W and P split on the fly into tensor
+// Both kernels: 8 transform / epilogue warps (thread = row = TMEM lane), one W TMA warp, one E / Qt TMA warp, and the MMA issue —
+// kernel A: ONE warp (all MMAs into an accumulator must come from one thread: only then are they ordered), every work item goes
+// through all eight transform warps; kernel B: two issuers and two epilogue sets, every other item each (an accumulator belongs
+// to one item).  fp32 fidelity through 3xTF32 (hi.hi + hi.lo + lo.hi; W and P split on the fly into tensor
 // memory, E and Qt pre-split by the factor).  Every mbarrier wait carries the clock watchdog of tc_common.cuh.
 #include "tc_apply_common.cuh"
 #include <cstdint>
@@ -37,7 +38,8 @@ using namespace uce::tca;
 constexpr int NBLK = 3;                                 // row blocks per CTA
 constexpr int TW = 8;                                   // transform / epilogue warps (two sets of four)
 constexpr int WARP_W = TW, WARP_B = TW + 1, WARP_MMA = TW + 2;
-constexpr int THREADS = (TW + 4) * 32;                  // + W TMA warp + E/Qt TMA warp + two MMA issuers
+constexpr int THREADS_A = (TW + 3) * 32;                // + W TMA warp + E TMA warp + ONE MMA issuer
+constexpr int THREADS = (TW + 4) * 32;                  // kernel B: + W TMA warp + Qt TMA warp + two MMA issuers
 constexpr int MAX_LAYERS = 96;
 constexpr uint32_t TMEM_COLS = 512;
 // kernel A
@@ -77,7 +79,22 @@ __device__ __forceinline__ Cta cta_setup(const Slot* __restrict__ slots, int n_s
 __device__ __forceinline__ int col_of(const Cta& c, int ci) { int x = ci + c.rot; if (x >= c.ncs) x -= c.ncs; return (c.c0 + x) * 32; }
 
 // ------------------------------------------------------------------------------------------------ kernel A
-__global__ void __launch_bounds__(THREADS, 1)
+// Barrier discipline (both kernels): mbarrier waits test the PARITY of a phase, so a waiter must never be two phases away from
+// the barrier it tests — every barrier here has one fixed set of waiters that observes every one of its phases.  (A first version
+// let two transform sets and two MMA issuers take every other work item over a 5-deep ring: a waiter then skipped every other
+// phase of a slot's barriers, could pass a wait one phase early, read a half-written A stage and double-arrive — wrong rows,
+// run-to-run differences and hangs on hardware.)  Kernel A therefore runs every work item through ALL eight transform warps
+// (each takes its row's 16 columns of the 32-column chunk) and ONE MMA-issuing warp; all MMAs into an accumulator come from
+// one thread, which also orders them.
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+          "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]) : "memory");
+}
+
+__global__ void __launch_bounds__(THREADS_A, 1)
 apply_p_kernel(const Slot* __restrict__ slots, int n_slots, int K, int R, int ks, float* __restrict__ Pbuf,
                const __grid_constant__ EMaps emaps, const __grid_constant__ WIn wmaps) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -90,22 +107,22 @@ apply_p_kernel(const Slot* __restrict__ slots, int n_slots, int K, int R, int ks
     const Cta c = cta_setup(slots, n_slots, K, ks);
     const int e_stage = 2 * R * 128;
     const uint32_t bars = base + (uint32_t)(NRAW * 16384 + NE * e_stage);
-    auto bar_raw_full  = [&](int r) { return bars + 8u * r; };                 // [0,8)   W TMA -> transform set
+    auto bar_raw_full  = [&](int r) { return bars + 8u * r; };                 // [0,8)   W TMA -> transform warps
     auto bar_raw_empty = [&](int r) { return bars + 8u * (8 + r); };           // [8,16)
-    auto bar_a_full    = [&](int a) { return bars + 8u * (16 + a); };          // [16,21) transform set -> MMA issuer
+    auto bar_a_full    = [&](int a) { return bars + 8u * (16 + a); };          // [16,21) transform warps -> MMA issuer
     auto bar_a_empty   = [&](int a) { return bars + 8u * (21 + a); };          // [21,26)
-    auto bar_e_full    = [&](int s) { return bars + 8u * (26 + s); };          // [26,30) E TMA -> MMA issuers
-    auto bar_e_empty   = [&](int s) { return bars + 8u * (30 + s); };          // [30,34) one arrival per block of the chunk
+    auto bar_e_full    = [&](int s) { return bars + 8u * (26 + s); };          // [26,30) E TMA -> MMA issuer
+    auto bar_e_empty   = [&](int s) { return bars + 8u * (30 + s); };          // [30,34)
     const uint32_t bar_p_full = bars + 8u * 34, tmem_slot = bars + 8u * 35;
     auto raw_st = [&](int r) { return base + (uint32_t)(r * 16384); };
     auto e_hi_st = [&](int s) { return base + (uint32_t)(NRAW * 16384 + s * e_stage); };
     auto e_lo_st = [&](int s) { return base + (uint32_t)(NRAW * 16384 + s * e_stage + R * 128); };
 
     if (threadIdx.x == 0) {
-        for (int r = 0; r < NRAW; ++r) { mbar_init(bar_raw_full(r), 1); mbar_init(bar_raw_empty(r), 4); }
-        for (int a = 0; a < NA; ++a) { mbar_init(bar_a_full(a), 4); mbar_init(bar_a_empty(a), 1); }
-        for (int s = 0; s < NE; ++s) { mbar_init(bar_e_full(s), 1); mbar_init(bar_e_empty(s), (uint32_t)c.n_act); }
-        mbar_init(bar_p_full, 2);
+        for (int r = 0; r < NRAW; ++r) { mbar_init(bar_raw_full(r), 1); mbar_init(bar_raw_empty(r), TW); }
+        for (int a = 0; a < NA; ++a) { mbar_init(bar_a_full(a), TW); mbar_init(bar_a_empty(a), 1); }
+        for (int s = 0; s < NE; ++s) { mbar_init(bar_e_full(s), 1); mbar_init(bar_e_empty(s), 1); }
+        mbar_init(bar_p_full, 1);
         mbar_fence_init();
     }
     if (warp == WARP_MMA) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -120,57 +137,63 @@ apply_p_kernel(const Slot* __restrict__ slots, int n_slots, int K, int R, int ks
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
     if (warp < TW) {
-        // =============================== W transform (set = item parity), then the partial P to the scratch ===============================
-        const int set = warp >> 2, wq = warp & 3;
+        // =============================== W transform: every warp on every item (its rows x 16 of the chunk's 32 columns) ===============================
+        const int half = warp >> 2, wq = warp & 3;
         const int trow = 32 * wq + lane;                 // row of the block == TMEM lane
         const uint32_t lane_base = tmem_base + ((uint32_t)(32 * wq) << 16);
         const uint32_t row_off = (uint32_t)(trow * 128);
         const uint32_t sw = (uint32_t)(trow & 7);
-        int ci = 0, g = set;                              // item i = ci * n_act + g
-        while (g >= c.n_act) { g -= c.n_act; ++ci; }
-        for (int i = set; i < c.n_items; i += 2) {
+        int g = 0;
+        for (int i = 0; i < c.n_items; ++i) {
             const int r = i % NRAW, a = i % NA;
             mbar_wait(bar_raw_full(r), (uint32_t)((i / NRAW) & 1));
             const bool row_live = trow < c.sl[g].rows;
             const uint32_t raw = raw_st(r) + row_off;
-            uint32_t hi[32], lo[32];
+            uint32_t hi[16], lo[16];
 #pragma unroll
-            for (int jv = 0; jv < 8; ++jv) {
+            for (int jv = 0; jv < 4; ++jv) {
                 float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (row_live) v = lds_v4(raw + (((uint32_t)jv ^ sw) << 4));      // swizzled 16-byte slot the TMA wrote
+                if (row_live) v = lds_v4(raw + (((uint32_t)(4 * half + jv) ^ sw) << 4));      // swizzled 16-byte slot the TMA wrote
                 tf32_split(v.x, hi[4 * jv], lo[4 * jv]);         tf32_split(v.y, hi[4 * jv + 1], lo[4 * jv + 1]);
                 tf32_split(v.z, hi[4 * jv + 2], lo[4 * jv + 2]); tf32_split(v.w, hi[4 * jv + 3], lo[4 * jv + 3]);
             }
             mbar_wait(bar_a_empty(a), (uint32_t)(((i / NA) & 1) ^ 1));       // the MMAs that read this A stage have completed
             fence_after();
             __syncwarp();
-            const uint32_t ta = lane_base + A_COL0 + 64u * (uint32_t)a;
-            tmem_st32(ta, hi);
-            tmem_st32(ta + 32u, lo);
+            const uint32_t ta = lane_base + A_COL0 + 64u * (uint32_t)a + 16u * (uint32_t)half;
+            tmem_st16(ta, hi);
+            tmem_st16(ta + 32u, lo);
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             fence_before();
             __syncwarp();
             if (lane == 0) { mbar_arrive(bar_a_full(a)); mbar_arrive(bar_raw_empty(r)); }
-            g += 2;
-            while (g >= c.n_act) { g -= c.n_act; ++ci; }
+            if (++g == c.n_act) g = 0;
         }
-        // ---- the partial products of this K slice: TMEM -> registers -> scratch [slice][slot][128 rows][R] ----
+        // ---- the partial products of this K slice: TMEM -> registers -> scratch [slice][slot][128 rows][R]; a warp takes half the columns ----
         mbar_wait(bar_p_full, 0);
         fence_after();
         __syncwarp();
-        for (int gb = set; gb < c.n_act; gb += 2) {
-            float* dst = Pbuf + (((size_t)c.j * n_slots + (size_t)(c.q * NBLK + gb)) * 128 + trow) * R;
-            for (int rc = 0; rc < R / 32; ++rc) {
-                uint32_t v[32];
-                tmem_ld32(lane_base + 64u * (uint32_t)gb + 32u * (uint32_t)rc, v);
-                if (trow < c.sl[gb].rows) {
-                    float4* d4 = reinterpret_cast<float4*>(dst + 32 * rc);
+        const int cw = R / 2;                                        // columns per warp half: 32 (R = 64) or 16 (R = 32)
+        for (int gb = 0; gb < c.n_act; ++gb) {
+            float* dst = Pbuf + (((size_t)c.j * n_slots + (size_t)(c.q * NBLK + gb)) * 128 + trow) * R + half * cw;
+            const bool live = trow < c.sl[gb].rows;
+            uint32_t v[32];
+            if (cw == 32) {
+                tmem_ld32(lane_base + 64u * (uint32_t)gb + 32u * (uint32_t)half, v);
+            } else {
+                uint32_t w[16];
+                tmem_ld16(lane_base + 64u * (uint32_t)gb + 16u * (uint32_t)half, w);
 #pragma unroll
-                    for (int jv = 0; jv < 8; ++jv)
-                        d4[jv] = make_float4(__uint_as_float(v[4 * jv]), __uint_as_float(v[4 * jv + 1]), __uint_as_float(v[4 * jv + 2]), __uint_as_float(v[4 * jv + 3]));
-                }
-                __syncwarp();                          // tcgen05.ld is .sync.aligned: the warp reconverges before the next one
+                for (int e = 0; e < 16; ++e) v[e] = w[e];
             }
+            if (live) {
+                float4* d4 = reinterpret_cast<float4*>(dst);
+#pragma unroll
+                for (int jv = 0; jv < 8; ++jv)
+                    if (4 * jv < cw)
+                        d4[jv] = make_float4(__uint_as_float(v[4 * jv]), __uint_as_float(v[4 * jv + 1]), __uint_as_float(v[4 * jv + 2]), __uint_as_float(v[4 * jv + 3]));
+            }
+            __syncwarp();                              // tcgen05.ld is .sync.aligned: the warp reconverges before the next one
         }
     } else if (warp == WARP_W) {
         // =============================== TMA warp 1: raw W boxes, one per (chunk, block) ===============================
@@ -184,6 +207,7 @@ apply_p_kernel(const Slot* __restrict__ slots, int n_slots, int K, int R, int ks
                 mbar_arrive_expect_tx(bar_raw_full(r), (uint32_t)c.sl[g].h * 128u);
                 tma_load_2d_hint(raw_st(r), &wmaps.in[c.sl[g].layer], bar_raw_full(r), col_of(c, ci), c.sl[g].row0, pol_keep);
             }
+            __syncwarp();
             if (++g == c.n_act) { g = 0; ++ci; }
         }
     } else if (warp == WARP_B) {
@@ -197,45 +221,38 @@ apply_p_kernel(const Slot* __restrict__ slots, int n_slots, int K, int R, int ks
                 tma_load_2d(e_hi_st(s), &emaps.hi, bar_e_full(s), col_of(c, ci), 0);
                 tma_load_2d(e_lo_st(s), &emaps.lo, bar_e_full(s), col_of(c, ci), 0);
             }
+            __syncwarp();
         }
-    } else {
-        // =============================== MMA issuers (issuer = item parity) ===============================
-        const int t = warp - WARP_MMA;
+    } else if (warp == WARP_MMA) {
+        // =============================== the MMA issuer (one warp, converged; one elected lane issues) ===============================
         const uint32_t idesc = idesc_tf32(128, R);
-        int ci = 0, g = t;
-        while (g >= c.n_act) { g -= c.n_act; ++ci; }
-        bool any = false;
-        for (int i = t; i < c.n_items; i += 2) {
-            const int a = i % NA, se = ci % NE;
+        int i = 0;
+        for (int ci = 0; ci < c.ncs; ++ci) {
+            const int se = ci % NE;
             mbar_wait(bar_e_full(se), (uint32_t)((ci / NE) & 1));
-            mbar_wait(bar_a_full(a), (uint32_t)((i / NA) & 1));
-            fence_after();
-            __syncwarp();
-            if (elect_one()) {
-                const uint64_t b_hi = umma_desc_sw128(e_hi_st(se)), b_lo = umma_desc_sw128(e_lo_st(se));
-                const uint32_t a_hi = tmem_base + A_COL0 + 64u * (uint32_t)a, a_lo = a_hi + 32u;
-                const uint32_t d_tmem = tmem_base + 64u * (uint32_t)g;
+            for (int g = 0; g < c.n_act; ++g, ++i) {
+                const int a = i % NA;
+                mbar_wait(bar_a_full(a), (uint32_t)((i / NA) & 1));
+                fence_after();
+                __syncwarp();
+                if (elect_one()) {
+                    const uint64_t b_hi = umma_desc_sw128(e_hi_st(se)), b_lo = umma_desc_sw128(e_lo_st(se));
+                    const uint32_t a_hi = tmem_base + A_COL0 + 64u * (uint32_t)a, a_lo = a_hi + 32u;
+                    const uint32_t d_tmem = tmem_base + 64u * (uint32_t)g;
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {          // 8 tf32 per step: 8 TMEM columns of A, 32 bytes inside the swizzle atom of B
-                    const uint64_t adv = (uint64_t)(k * 2);
-                    umma_tf32_ts(d_tmem, a_hi + 8u * k, b_hi + adv, idesc, (ci | k) != 0);
-                    umma_tf32_ts(d_tmem, a_hi + 8u * k, b_lo + adv, idesc, 1);
-                    umma_tf32_ts(d_tmem, a_lo + 8u * k, b_hi + adv, idesc, 1);
+                    for (int k = 0; k < 4; ++k) {      // 8 tf32 per step: 8 TMEM columns of A, 32 bytes inside the swizzle atom of B
+                        const uint64_t adv = (uint64_t)(k * 2);
+                        umma_tf32_ts(d_tmem, a_hi + 8u * k, b_hi + adv, idesc, (ci | k) != 0);
+                        umma_tf32_ts(d_tmem, a_hi + 8u * k, b_lo + adv, idesc, 1);
+                        umma_tf32_ts(d_tmem, a_lo + 8u * k, b_hi + adv, idesc, 1);
+                    }
+                    umma_commit(bar_a_empty(a));
+                    if (g == c.n_act - 1) umma_commit(bar_e_empty(se));      // every block has consumed this E stage
+                    if (g == c.n_act - 1 && ci == c.ncs - 1) umma_commit(bar_p_full);
                 }
-                umma_commit(bar_a_empty(a));
-                umma_commit(bar_e_empty(se));
+                __syncwarp();
             }
-            __syncwarp();
-            any = true;
-            g += 2;
-            while (g >= c.n_act) { g -= c.n_act; ++ci; }
         }
-        __syncwarp();
-        if (elect_one()) {
-            if (any) umma_commit(bar_p_full);          // every MMA this thread issued has completed
-            else mbar_arrive(bar_p_full);
-        }
-        __syncwarp();
     }
     fence_before();
     __syncthreads();
@@ -401,38 +418,42 @@ apply_w_kernel(const Slot* __restrict__ slots, int n_slots, int K, int R, int ks
         }
     } else {
         // =============================== MMA issuers: D[128 rows, 32 cols] = P_hi Qt_hi^T + P_lo Qt_hi^T + P_hi Qt_lo^T ===============================
+        // An accumulator belongs to one work item and all MMAs of an item come from one thread (issuer = item parity; items on the
+        // same accumulator slot are NACC = 4 apart: the same parity, the same issuer, the same epilogue set).  Both issuers wait
+        // for EVERY unit's Qt barrier, also for a unit in which they have no item (a CTA with one block): see "barrier discipline".
         const int t = warp - WARP_MMA;
         const uint32_t idesc = idesc_tf32(128, 32);
         mbar_wait(bar_p_ready, 0);
         fence_after();
-        int u = 0, g = t;
-        while (g >= c.n_act) { g -= c.n_act; ++u; }
-        for (int i = t; i < c.n_items; i += 2) {
-            const int a = i % NACC, tq = u % NQ;
-            mbar_wait(bar_acc_empty(a), (uint32_t)(((i / NACC) & 1) ^ 1));
+        int i = 0;
+        for (int u = 0; u < c.ncs; ++u) {
+            const int tq = u % NQ;
             mbar_wait(bar_q_full(tq), (uint32_t)((u / NQ) & 1));
-            fence_after();
-            __syncwarp();
-            if (elect_one()) {
-                const uint32_t d_tmem = tmem_base + ACC_COL0 + 32u * (uint32_t)a;
-                const uint32_t p_hi = tmem_base + 64u * (uint32_t)g, p_lo = tmem_base + PLO_COL0 + 64u * (uint32_t)g;
-                for (int rc = 0; rc < n_rc; ++rc) {
-                    const uint64_t bq_hi = umma_desc_sw128(qt_tile(tq, 2 * rc)), bq_lo = umma_desc_sw128(qt_tile(tq, 2 * rc + 1));
+            for (int g = 0; g < c.n_act; ++g, ++i) {
+                if ((i & 1) != t) continue;
+                const int a = i % NACC;
+                mbar_wait(bar_acc_empty(a), (uint32_t)(((i / NACC) & 1) ^ 1));
+                fence_after();
+                __syncwarp();
+                if (elect_one()) {
+                    const uint32_t d_tmem = tmem_base + ACC_COL0 + 32u * (uint32_t)a;
+                    const uint32_t p_hi = tmem_base + 64u * (uint32_t)g, p_lo = tmem_base + PLO_COL0 + 64u * (uint32_t)g;
+                    for (int rc = 0; rc < n_rc; ++rc) {
+                        const uint64_t bq_hi = umma_desc_sw128(qt_tile(tq, 2 * rc)), bq_lo = umma_desc_sw128(qt_tile(tq, 2 * rc + 1));
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const uint64_t adv = (uint64_t)(k * 2);
-                        const uint32_t col = (uint32_t)(rc * 32 + 8 * k);
-                        umma_tf32_ts(d_tmem, p_hi + col, bq_hi + adv, idesc, (rc | k) != 0);      // hi.hi
-                        umma_tf32_ts(d_tmem, p_lo + col, bq_hi + adv, idesc, 1);                  // lo.hi
-                        umma_tf32_ts(d_tmem, p_hi + col, bq_lo + adv, idesc, 1);                  // hi.lo
+                        for (int k = 0; k < 4; ++k) {
+                            const uint64_t adv = (uint64_t)(k * 2);
+                            const uint32_t col = (uint32_t)(rc * 32 + 8 * k);
+                            umma_tf32_ts(d_tmem, p_hi + col, bq_hi + adv, idesc, (rc | k) != 0);      // hi.hi
+                            umma_tf32_ts(d_tmem, p_lo + col, bq_hi + adv, idesc, 1);                  // lo.hi
+                            umma_tf32_ts(d_tmem, p_hi + col, bq_lo + adv, idesc, 1);                  // hi.lo
+                        }
                     }
+                    umma_commit(bar_q_empty(tq));
+                    umma_commit(bar_acc_full(a));
                 }
-                umma_commit(bar_q_empty(tq));
-                umma_commit(bar_acc_full(a));
+                __syncwarp();
             }
-            __syncwarp();
-            g += 2;
-            while (g >= c.n_act) { g -= c.n_act; ++u; }
         }
     }
     fence_before();
@@ -531,7 +552,7 @@ int apply_ab_lowrank(uce_ws* ws, const void* slots_dev, const void* slots_host, 
         const int smem = smem_a(R);
         int& cf = conf_a[ws->device & 63];
         if (cf < smem) { UCE_CUDA(cudaFuncSetAttribute(apply_p_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); cf = smem; }
-        apply_p_kernel<<<grid, THREADS, smem, st>>>((const Slot*)slots_dev, n_slots, K, R, ks, ws->P, em, *reinterpret_cast<const WIn*>(&wmaps));
+        apply_p_kernel<<<grid, THREADS_A, smem, st>>>((const Slot*)slots_dev, n_slots, K, R, ks, ws->P, em, *reinterpret_cast<const WIn*>(&wmaps));
         UCE_LAUNCH_CHECK();
         *launches += 1;
     }

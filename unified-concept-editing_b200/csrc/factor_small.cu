@@ -4,9 +4,13 @@
 //   gram_splitk   H = Cp Cp^T, fp64 accumulation of exact fp32 products, 32x32 tiles x split-K over many CTAs
 //   chol_small    ONE CTA: H (+ lamb/s on the diagonal) into shared memory (lower block triangle), blocked Cholesky
 //                 (NB = 32: left-looking factorisation of the diagonal block by one warp, column-sweep inverse by all
-//                 warps, panel + trailing updates by all 512 threads), then  Z = H^-1[:, edit]  by blocked
-//                 forward/backward substitution with the right-hand sides in shared memory too
-//   q_emit        Q = Z^T Cp (fp64 accumulate) -> Q, Qt and the TF32 hi/lo splits consumed by the tcgen05 apply
+//                 warps, panel + trailing updates by all 512 threads); the factor L and the inverses of its diagonal
+//                 blocks go back to global memory
+//   solve_emit    MANY CTAs, one per 16 columns of K:  X = H^-1 Cp[:, cols]  by blocked forward substitution and the
+//                 part of the backward substitution that reaches the edit rows (they are the LAST rows), all in
+//                 shared memory; the edit rows of X are Q[:, cols] (H^-1 is symmetric:  Q = J H^-1 Cp) -> Q, Qt and the
+//                 TF32 hi/lo splits consumed by the tcgen05 apply.  (The single-CTA substitution on the n_edit unit
+//                 vectors followed by a Q = Z^T Cp kernel that this replaces cost 26 + 10 us of the 147 us factor.)
 //
 // Same algebra and same fp64 precision as the general path (trainscripts/uce_sd_erase.py:63,71,79,82 — the
 // mat2 accumulation and its inverse — done once per edit).
@@ -85,12 +89,16 @@ __device__ __forceinline__ double fs_rsqrt(double d) {
 
 // One pivot step with the trailing update limited to KM columns (straight-line: the column loads are issued ahead of the
 // FMAs; a per-column early exit was measured 1.8x SLOWER — the branches serialise load and FMA latencies).
+// `d` is the pivot A[j][j] of this step; the return value is the pivot of step j + 1.  The pivot chain does NOT go through shared
+// memory: lane j + 1 updates its own diagonal entry from its own multiplier (A[j+1][j+1] - L[j+1][j]^2 — the same fma, bit for bit,
+// that the column loop below performs for it) and broadcasts it by shuffle while the column of L travels through shared memory
+// for everybody else; the chain per pivot is shuffle -> rsqrt -> multiply -> fma instead of ... -> store -> load -> fma.
 template <int KM>
-__device__ __forceinline__ void fs_potrf_step(double (&a)[FS_NB], double* __restrict__ D, double* __restrict__ invd_blk, int lane, int j, bool& bad) {
-    double d = __shfl_sync(0xffffffffu, a[0], j);
+__device__ __forceinline__ double fs_potrf_step(double (&a)[FS_NB], double* __restrict__ D, double* __restrict__ invd_blk, int lane, int j, double d, bool& bad) {
     if (!(d > 0.0)) { bad = true; d = 1.0; }
     const double y = fs_rsqrt(d);
     const double l = (lane == j) ? d * y : a[0] * y;      // L[lane][j] for lanes >= j
+    const double d_next = __shfl_sync(0xffffffffu, fma(-l, l, a[1]), (j + 1) & 31);
     if (lane >= j) D[lane * (FS_NB + 1) + j] = l;
     if (lane == j) invd_blk[j] = y;
     __syncwarp();
@@ -98,26 +106,28 @@ __device__ __forceinline__ void fs_potrf_step(double (&a)[FS_NB], double* __rest
     // 32-bit shuffles a double costs (rows beyond 31 read neighbouring shared memory: finite garbage for columns that do not exist)
     const double* Lj = D + j * (FS_NB + 1) + j;
 #pragma unroll
-    for (int k = 1; k <= KM; ++k) {                       // A[lane][j + k] -= L[lane][j] L[j + k][j]   (k = 1 first: the next pivot)
+    for (int k = 1; k <= KM; ++k) {                       // A[lane][j + k] -= L[lane][j] L[j + k][j]
         const double lk = Lj[k * (FS_NB + 1)];
         a[k - 1] = fma(-l, lk, a[k]);
     }
     __syncwarp();
+    return d_next;
 }
 __device__ __noinline__ void fs_potrf_warp(double* __restrict__ D, double* __restrict__ invd_blk, int lane, int* flag, int kb) {
     double a[FS_NB];
 #pragma unroll
     for (int c = 0; c < FS_NB; ++c) a[c] = D[lane * (FS_NB + 1) + c];
     bool bad = false;
+    double d = __shfl_sync(0xffffffffu, a[0], 0);
     // columns j + k <= 31 exist: 31, 23, 15 and 7 trailing columns for the four quarters of the block
 #pragma unroll 1
-    for (int j = 0; j < 8; ++j) fs_potrf_step<31>(a, D, invd_blk, lane, j, bad);
+    for (int j = 0; j < 8; ++j) d = fs_potrf_step<31>(a, D, invd_blk, lane, j, d, bad);
 #pragma unroll 1
-    for (int j = 8; j < 16; ++j) fs_potrf_step<23>(a, D, invd_blk, lane, j, bad);
+    for (int j = 8; j < 16; ++j) d = fs_potrf_step<23>(a, D, invd_blk, lane, j, d, bad);
 #pragma unroll 1
-    for (int j = 16; j < 24; ++j) fs_potrf_step<15>(a, D, invd_blk, lane, j, bad);
+    for (int j = 16; j < 24; ++j) d = fs_potrf_step<15>(a, D, invd_blk, lane, j, d, bad);
 #pragma unroll 1
-    for (int j = 24; j < 32; ++j) fs_potrf_step<7>(a, D, invd_blk, lane, j, bad);
+    for (int j = 24; j < 32; ++j) d = fs_potrf_step<7>(a, D, invd_blk, lane, j, d, bad);
     if (bad && lane == 0) atomicCAS(flag, 0, 1 + kb);
 }
 
@@ -133,17 +143,15 @@ __device__ __forceinline__ void fs_build_ts(double* __restrict__ TS, const doubl
 }
 
 __global__ void __launch_bounds__(FS_T, 1)
-chol_small_kernel(double* __restrict__ Hg, int n, int n_pad, const double* __restrict__ dadd, int n_pres, int n_edit,
-                  double* __restrict__ Z, int ldz, int write_back, int* flag, long long* __restrict__ trace) {
+chol_small_kernel(double* __restrict__ Hg, int n, int n_pad, const double* __restrict__ dadd,
+                  double* __restrict__ Lg, double* __restrict__ invd_g, int write_back, int* flag, long long* __restrict__ trace) {
     extern __shared__ double smem_d[];
     int trn = 0;
     auto tr = [&]() { if (trace && threadIdx.x == 0 && trn < 64) trace[trn++] = clock64(); };
     tr();
     const int nblk = n_pad / FS_NB;
     double* SB = smem_d;
-    double* XS = SB + (nblk * (nblk + 1) / 2) * FS_BLK;
-    const int xl = n_edit | 1;
-    double* invd = XS + n_pad * xl;               // [n_pad]
+    double* invd = SB + (nblk * (nblk + 1) / 2) * FS_BLK;      // [n_pad]
     double* TS = invd + n_pad;                    // [32][33] dense copy of one block's L^-1 (see fs_build_ts)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int NW = FS_T / 32;
@@ -176,8 +184,6 @@ chol_small_kernel(double* __restrict__ Hg, int n, int n_pad, const double* __res
                 for (int half = 0; half < 2; ++half) SB[b * FS_BLK + (warp * 2 + half) * P + lane] = v[b][half];
             }
     }
-    for (int r = warp; r < n_pad; r += NW)
-        for (int j = lane; j < n_edit; j += 32) XS[r * xl + j] = (r == n_pres + j) ? 1.0 : 0.0;
     __syncthreads();
     tr();   // 1: loaded
 
@@ -301,150 +307,121 @@ chol_small_kernel(double* __restrict__ Hg, int n, int n_pad, const double* __res
         }
     }
 
-    // ---- substitutions.  Register tiles of 8 rows x 2 right-hand sides (lane -> columns lane and lane + 32): the matrix
-    //      coefficients are warp broadcasts (one shared-memory wavefront each), the right-hand sides consecutive doubles,
-    //      12 wavefronts per 16 FMAs per lane.  (4 x 1 tiles were measured at 60 k cycles for the backward sweep: the loop
-    //      was bound by shared-memory wavefronts, 6 per 4 FMAs.)  Warp = one row octet: all block rows of an update step
-    //      are covered in ONE pass. ----
-    const bool on0 = lane < n_edit, on1 = lane + 32 < n_edit;
-    const int sj = tid & 63, q4 = tid >> 6;           // triangular multiplies: 8 row quads x 64 right-hand-side slots
-    // forward  L Y = rhs  (block rows above the first edit row stay zero)
-    for (int kb = n_pres / FS_NB; kb < nblk; ++kb) {
-        const double* D = SB + fs_blk(kb, kb);
-        const int o = kb * FS_NB;
-        fs_build_ts(TS, D, invd + o, tid);
-        __syncthreads();
-        // (i) Y_k = L_kk^-1 X_k on ALL warps: thread = (row quad q4, right-hand side sj); (L^-1)[rr][c] = TS[c][rr]
-        //     (With 8 x 2 tiles only four warps had work here and the step ran at the latency of one warp per scheduler.)
-        double out[4] = {0.0, 0.0, 0.0, 0.0};
-        if (sj < n_edit) {
-#pragma unroll 4
-            for (int c = 0; c < FS_NB; ++c) {
-                const double x = XS[(o + c) * xl + sj];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int rr = 4 * q4 + i;
-                    out[i] = fma(TS[c * P + rr], x, out[i]);
-                }
-            }
+    // ---- the factor goes back to global memory for solve_emit: the block triangle as it sits in shared memory (diagonal blocks:
+    //      L_kk in the lower triangle, the strictly-lower part of L_kk^-1 transposed in the strict upper triangle), 32 x 32 blocks
+    //      of pitch 32, and 1 / L_ii ----
+    {
+        const int nb = nblk * (nblk + 1) / 2;
+        for (int idx = tid; idx < nb * FS_NB * FS_NB; idx += FS_T) {
+            const int b = idx >> 10, rc = idx & 1023;
+            Lg[idx] = SB[b * FS_BLK + (rc >> 5) * P + (rc & 31)];
         }
-        __syncthreads();
-        if (sj < n_edit) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) XS[(o + 4 * q4 + i) * xl + sj] = out[i];
-        }
-        __syncthreads();
-        tr();   // triangular multiply of this block done
-        for (int r = o + FS_NB + 8 * warp; r < n_pad; r += 8 * NW) {     // X_i -= L_ik Y_k for the block rows below
-            const double* A = SB + fs_blk(r >> 5, kb) + (r & 31) * P;
-            double s8[8][2];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) s8[i][0] = s8[i][1] = 0.0;
-#pragma unroll 4
-            for (int c = 0; c < FS_NB; ++c) {
-                const double x0 = on0 ? XS[(o + c) * xl + lane] : 0.0, x1 = on1 ? XS[(o + c) * xl + lane + 32] : 0.0;
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const double av = A[i * P + c];
-                    s8[i][0] = fma(av, x0, s8[i][0]); s8[i][1] = fma(av, x1, s8[i][1]);
-                }
-            }
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                if (on0) XS[(r + i) * xl + lane] -= s8[i][0];
-                if (on1) XS[(r + i) * xl + lane + 32] -= s8[i][1];
-            }
-        }
-        __syncthreads();
-        tr();   // update of the rows below done
+        for (int r = tid; r < n_pad; r += FS_T) invd_g[r] = invd[r];
     }
-    tr();   // forward substitution done
-    // backward  L^T Z = Y
-    for (int kb = nblk - 1; kb >= 0; --kb) {
-        const double* D = SB + fs_blk(kb, kb);
-        const int o = kb * FS_NB;
-        fs_build_ts(TS, D, invd + o, tid);
-        __syncthreads();
-        // (i) Z_k = L_kk^-T Y_k on all warps: (L^-T)[rr][c] = (L^-1)[c][rr] = TS[rr][c]
-        double out[4] = {0.0, 0.0, 0.0, 0.0};
-        if (sj < n_edit) {
-#pragma unroll 4
-            for (int c = 0; c < FS_NB; ++c) {
-                const double x = XS[(o + c) * xl + sj];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int rr = 4 * q4 + i;
-                    out[i] = fma(TS[rr * P + c], x, out[i]);
-                }
-            }
-        }
-        __syncthreads();
-        if (sj < n_edit) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) XS[(o + 4 * q4 + i) * xl + sj] = out[i];
-        }
-        __syncthreads();
-        tr();   // triangular multiply of this block done
-        for (int r = 8 * warp; r < o; r += 8 * NW) {  // X_i -= L_ki^T Z_k for the block rows above
-            const double* A = SB + fs_blk(kb, r >> 5) + (r & 31);          // L[o + c][r + i] = block(kb, r/32)[c][r%32 + i]
-            double s8[8][2];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) s8[i][0] = s8[i][1] = 0.0;
-#pragma unroll 4
-            for (int c = 0; c < FS_NB; ++c) {
-                const double x0 = on0 ? XS[(o + c) * xl + lane] : 0.0, x1 = on1 ? XS[(o + c) * xl + lane + 32] : 0.0;
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const double av = A[c * P + i];
-                    s8[i][0] = fma(av, x0, s8[i][0]); s8[i][1] = fma(av, x1, s8[i][1]);
-                }
-            }
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                if (on0) XS[(r + i) * xl + lane] -= s8[i][0];
-                if (on1) XS[(r + i) * xl + lane + 32] -= s8[i][1];
-            }
-        }
-        __syncthreads();
-        tr();   // update of the rows above done
-    }
-    tr();   // backward substitution done
-    for (int r = warp; r < n; r += NW)
-        for (int j = lane; j < n_edit; j += 32) Z[(long)r * ldz + j] = XS[r * xl + j];
-    __syncthreads();
     tr();
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Q[j, k] = sum_r Z[r, j] Cp[r, k]  (fp64 accumulate), emitted as Q, Qt and the tf32 hi/lo splits of Qt.
-// grid (K / 32 column tiles, r_pad / 8 row groups); 256 threads = 8 rows of Q x 32 columns; the 8 needed columns of Z and
-// the 32 needed columns of Cp are staged in shared memory.
-__global__ void __launch_bounds__(256) q_emit_kernel(const double* __restrict__ Z, int ldz, const float* __restrict__ Cp, int n,
-                                                     int n_edit, int r_pad, int K, float* __restrict__ Q, float* __restrict__ Qt,
-                                                     float* __restrict__ Qt_hi, float* __restrict__ Qt_lo) {
-    __shared__ double Zs[FS_MAX_N][8];
-    __shared__ float Cs[FS_MAX_N][33];
-    const int k0 = blockIdx.x * 32, j0 = blockIdx.y * 8, tid = threadIdx.x;
-    for (int idx = tid; idx < n * 8; idx += 256) {
-        const int r = idx >> 3, jj = idx & 7;
-        Zs[r][jj] = (j0 + jj < n_edit) ? Z[(long)r * ldz + j0 + jj] : 0.0;
+// X = H^-1 Cp[:, cols] for one slab of SE_CW columns, then Q[j, cols] = X[n_pres + j, cols]  (see the file header).
+//   forward   L Y = Cp[:, cols]        over all block rows
+//   backward  L^T X = Y                from the last block row up to the block row of the first edit row
+// Everything in shared memory: the block triangle of L (pitch 33, as chol_small keeps it), a dense copy TS of the current
+// diagonal block's inverse, the slab XS [n_pad][SE_CW + 1].  512 threads:
+//   triangular multiply of a 32 x SE_CW block: one output per thread;  update of the rows below / above: 4 rows x 1 column per
+//   thread (the L coefficients are warp broadcasts, the slab entries consecutive doubles).
+constexpr int SE_CW = 16;
+constexpr int SE_T = 512;
+__global__ void __launch_bounds__(SE_T, 1)
+solve_emit_kernel(const double* __restrict__ Lg, const double* __restrict__ invd_g, const float* __restrict__ Cp, int n, int n_pad,
+                  int n_pres, int n_edit, int r_pad, int K, float* __restrict__ Q, float* __restrict__ Qt, float* __restrict__ Qt_hi,
+                  float* __restrict__ Qt_lo) {
+    extern __shared__ double smem_d[];
+    constexpr int P = FS_NB + 1, XL = SE_CW + 1;
+    const int nblk = n_pad / FS_NB, nb = nblk * (nblk + 1) / 2;
+    double* SB = smem_d;
+    double* invd = SB + nb * FS_BLK;
+    double* TS = invd + n_pad;
+    double* XS = TS + FS_BLK;                     // [n_pad][XL]
+    const int tid = threadIdx.x;
+    const int k0 = blockIdx.x * SE_CW;
+    // the slab first (it does not depend on the factor kernel... but this kernel is launched behind it anyway), then L
+    for (int idx = tid; idx < n_pad * SE_CW; idx += SE_T) {
+        const int r = idx / SE_CW, c = idx % SE_CW;
+        XS[r * XL + c] = (r < n && k0 + c < K) ? (double)Cp[(long)r * K + k0 + c] : 0.0;
     }
-    for (int idx = tid; idx < n * 32; idx += 256) {
-        const int r = idx / 32, c = idx % 32;
-        Cs[r][c] = (k0 + c < K) ? Cp[(long)r * K + k0 + c] : 0.f;
+    for (int idx = tid; idx < nb * FS_NB * FS_NB; idx += SE_T) {
+        const int b = idx >> 10, rc = idx & 1023;
+        SB[b * FS_BLK + (rc >> 5) * P + (rc & 31)] = Lg[idx];
     }
+    for (int r = tid; r < n_pad; r += SE_T) invd[r] = invd_g[r];
     __syncthreads();
-    const int c = tid % 32, jj = tid / 32, j = j0 + jj;
-    double s0 = 0.0, s1 = 0.0;
-    int r = 0;
-    for (; r + 2 <= n; r += 2) { s0 = fma(Zs[r][jj], (double)Cs[r][c], s0); s1 = fma(Zs[r + 1][jj], (double)Cs[r + 1][c], s1); }
-    if (r < n) s0 = fma(Zs[r][jj], (double)Cs[r][c], s0);
-    const float v = (float)(s0 + s1);      // rows j >= n_edit (rank padding) come out as exact zeros
-    if (k0 + c < K && j < r_pad) {
-        Q[(long)j * K + k0 + c] = v;
-        const long t = (long)(k0 + c) * r_pad + j;
+    const int c = tid & (SE_CW - 1), rq = tid >> 4;           // column of the slab; row (triangular multiply) or row quad (updates)
+    // ---- forward ----
+    for (int kb = 0; kb < nblk; ++kb) {
+        const double* D = SB + fs_blk(kb, kb);
+        const int o = kb * FS_NB;
+        fs_build_ts(TS, D, invd + o, tid);
+        __syncthreads();
+        double y = 0.0;                                       // Y_k = L_kk^-1 X_k:  (L^-1)[r][j] = TS[j][r]
+#pragma unroll 8
+        for (int j = 0; j < FS_NB; ++j) y = fma(TS[j * P + rq], XS[(o + j) * XL + c], y);
+        __syncthreads();
+        XS[(o + rq) * XL + c] = y;
+        __syncthreads();
+        const int rows_below = n_pad - o - FS_NB;
+        if (4 * rq < rows_below) {                            // X_i -= L_ik Y_k for the block rows below
+            const int r = o + FS_NB + 4 * rq;
+            const double* A = SB + fs_blk(r >> 5, kb) + (r & 31) * P;
+            double s4[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll 8
+            for (int j = 0; j < FS_NB; ++j) {
+                const double x = XS[(o + j) * XL + c];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) s4[i] = fma(A[i * P + j], x, s4[i]);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) XS[(r + i) * XL + c] -= s4[i];
+        }
+        __syncthreads();
+    }
+    // ---- backward, down to the block row that holds the first edit row ----
+    const int kb_e = n_pres / FS_NB;
+    for (int kb = nblk - 1; kb >= kb_e; --kb) {
+        const double* D = SB + fs_blk(kb, kb);
+        const int o = kb * FS_NB;
+        fs_build_ts(TS, D, invd + o, tid);
+        __syncthreads();
+        double y = 0.0;                                       // X_k = L_kk^-T Y_k:  (L^-T)[r][j] = (L^-1)[j][r] = TS[r][j]
+#pragma unroll 8
+        for (int j = 0; j < FS_NB; ++j) y = fma(TS[rq * P + j], XS[(o + j) * XL + c], y);
+        __syncthreads();
+        XS[(o + rq) * XL + c] = y;
+        __syncthreads();
+        const int rows_above = o - kb_e * FS_NB;
+        if (4 * rq < rows_above) {                            // Y_i -= L_ki^T X_k for the block rows above (down to kb_e)
+            const int r = kb_e * FS_NB + 4 * rq;
+            const double* A = SB + fs_blk(kb, r >> 5) + (r & 31);            // L[o + j][r + i] = block(kb, r/32)[j][r%32 + i]
+            double s4[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll 8
+            for (int j = 0; j < FS_NB; ++j) {
+                const double x = XS[(o + j) * XL + c];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) s4[i] = fma(A[j * P + i], x, s4[i]);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) XS[(r + i) * XL + c] -= s4[i];
+        }
+        __syncthreads();
+    }
+    // ---- emit: Q [r_pad, K] row-major, Qt [K, r_pad] and its tf32 split; rows j >= n_edit (rank padding) are exact zeros ----
+    for (int idx = tid; idx < r_pad * SE_CW; idx += SE_T) {
+        const int cc = idx / r_pad, j = idx % r_pad;          // consecutive threads: consecutive j -> coalesced Qt stores
+        if (k0 + cc >= K) continue;
+        const float v = (j < n_edit) ? (float)XS[(n_pres + j) * XL + cc] : 0.f;
+        const long t = (long)(k0 + cc) * r_pad + j;
         const float h = fs_tf32_hi(v);
         Qt[t] = v; Qt_hi[t] = h; Qt_lo[t] = v - h;
+        Q[(long)j * K + k0 + cc] = v;
     }
 }
 
@@ -484,7 +461,6 @@ bool factor_small_applicable(const uce_ws* ws, int n, int n_edit, bool dual) {
 int factor_small(uce_ws* ws, const float* C, const float* G, int n, int n_pres, int n_edit, cudaStream_t st, int* launches) {
     const int K = ws->K;
     const int n_pad = round_up(n, FS_NB);
-    const int ldz = ws->max_rows;
     ws->sys_n = n_pad;
     pack_rows_split_kernel<<<n + (ws->rank_pad - n_edit), 256, 0, st>>>(C, G, ws->src_idx, n, n_pres, ws->rank_pad, K, ws->Cp, ws->E,
                                                                          ws->E_hi, ws->E_lo);
@@ -501,17 +477,26 @@ int factor_small(uce_ws* ws, const float* C, const float* G, int n, int n_pres, 
         UCE_CUDA(cudaMemcpyAsync(ws->Hcopy, ws->H, (size_t)n_pad * n_pad * sizeof(double), cudaMemcpyDeviceToDevice, st));
     }
     // + 8 rows of slack: the last pivots of a diagonal block read L[j + k][j] for rows up to 38 (columns that do not exist, results unused)
-    const size_t smem_c = ((size_t)(nt * (nt + 1) / 2) * FS_BLK + (size_t)n_pad * (n_edit | 1) + n_pad + FS_BLK + 8 * (FS_NB + 1)) * sizeof(double);
+    const size_t smem_c = ((size_t)(nt * (nt + 1) / 2) * FS_BLK + n_pad + FS_BLK + 8 * (FS_NB + 1)) * sizeof(double);
+    const size_t smem_s = ((size_t)(nt * (nt + 1) / 2) * FS_BLK + n_pad + FS_BLK + (size_t)n_pad * (SE_CW + 1)) * sizeof(double);
     static thread_local size_t conf_dev[64] = {0};        // per-device function attribute
     size_t& conf_c = conf_dev[ws->device & 63];
     if (conf_c < smem_c) {
         UCE_CUDA(cudaFuncSetAttribute(chol_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
         conf_c = smem_c;
     }
+    static thread_local size_t conf_dev_s[64] = {0};
+    size_t& conf_s = conf_dev_s[ws->device & 63];
+    if (conf_s < smem_s) {
+        UCE_CUDA(cudaFuncSetAttribute(solve_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s));
+        conf_s = smem_s;
+    }
     long long* trace = nullptr;
     const char* trace_path = getenv("UCE_CHOL_TRACE");
     if (trace_path) { UCE_CUDA(cudaMalloc(&trace, 64 * sizeof(long long))); UCE_CUDA(cudaMemsetAsync(trace, 0, 64 * sizeof(long long), st)); }
-    chol_small_kernel<<<1, FS_T, smem_c, st>>>(ws->H, n, n_pad, ws->diag_add, n_pres, n_edit, ws->X, ldz, ws->debug, ws->flag, trace);
+    static_assert(FS_MAX_N == 160, "ws->Lsmall is sized for 15 blocks + 160 reciprocals");
+    double* Lg = ws->Lsmall; double* invd_g = ws->Lsmall + 15 * 1024;
+    chol_small_kernel<<<1, FS_T, smem_c, st>>>(ws->H, n, n_pad, ws->diag_add, Lg, invd_g, ws->debug, ws->flag, trace);
     UCE_LAUNCH_CHECK(); ++*launches;
     if (trace) {   // debugging aid: phase boundaries of the single factor CTA (synchronises)
         long long h[64];
@@ -523,7 +508,8 @@ int factor_small(uce_ws* ws, const float* C, const float* G, int n, int n_pres, 
             fclose(f);
         }
     }
-    q_emit_kernel<<<dim3(ceil_div(K, 32), ws->rank_pad / 8), 256, 0, st>>>(ws->X, ldz, ws->Cp, n, n_edit, ws->rank_pad, K, ws->Q, ws->Qt, ws->Qt_hi, ws->Qt_lo);
+    solve_emit_kernel<<<ceil_div(K, SE_CW), SE_T, smem_s, st>>>(Lg, invd_g, ws->Cp, n, n_pad, n_pres, n_edit, ws->rank_pad, K, ws->Q, ws->Qt,
+                                                                ws->Qt_hi, ws->Qt_lo);
     UCE_LAUNCH_CHECK(); ++*launches;
     return 0;
 }

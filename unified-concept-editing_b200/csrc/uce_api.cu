@@ -64,6 +64,7 @@ int uce_ws_create(int device, int K, int max_rows, uce_ws** out) {
     WS_ALLOC(ws->H, (size_t)ws->sys_max * ws->sys_max * sizeof(double));
     WS_ALLOC(ws->Linv, (size_t)ws->sys_max * UCE_NB * sizeof(double));
     WS_ALLOC(ws->X, (size_t)ws->sys_max * mr * sizeof(double));
+    WS_ALLOC(ws->Lsmall, (size_t)(15 * 1024 + 160) * sizeof(double));
     WS_ALLOC(ws->src_idx, (size_t)mr * sizeof(int));
     WS_ALLOC(ws->diag_add, (size_t)mr * sizeof(double));
     WS_ALLOC(ws->flag, sizeof(int));
@@ -82,7 +83,7 @@ int uce_ws_destroy(uce_ws* ws) {
     if (!ws) return 0;
     cudaSetDevice(ws->device);
     cudaDeviceSynchronize();
-    void* dev[] = {ws->Cp, ws->Cs64, ws->E, ws->Q, ws->Qt, ws->Dt, ws->E_hi, ws->E_lo, ws->Qt_hi, ws->Qt_lo, ws->H, ws->Hcopy, ws->Linv, ws->X, ws->src_idx,
+    void* dev[] = {ws->Cp, ws->Cs64, ws->E, ws->Q, ws->Qt, ws->Dt, ws->E_hi, ws->E_lo, ws->Qt_hi, ws->Qt_lo, ws->H, ws->Hcopy, ws->Linv, ws->Lsmall, ws->X, ws->src_idx,
                    ws->diag_add, ws->flag, ws->P, ws->layers_dev, ws->hostpath_C, ws->hostpath_G, ws->hostpath_W};
     for (void* p : dev) if (p) cudaFree(p);
     if (ws->slots_dev) cudaFree(ws->slots_dev);

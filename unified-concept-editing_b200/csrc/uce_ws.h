@@ -36,6 +36,7 @@ struct uce_ws {
     double* H = nullptr;      // [sys_max, sys_max]
     double* Hcopy = nullptr;  // debug copy of the assembled system (lazily allocated)
     double* Linv = nullptr;   // [sys_max/NB][NB][NB]
+    double* Lsmall = nullptr; // low-latency factor: block triangle of L (15 blocks of 32 x 32) + 1 / L_ii (160), chol_small -> solve_emit
     double* X = nullptr;      // [sys_max, max_rows]  rhs / solution
     int*    src_idx = nullptr;   // [max_rows] API row of internal row r
     double* diag_add = nullptr;  // [max_rows] lamb / s_r  (dual)  or s_r (primal)

@@ -309,6 +309,8 @@ __global__ void f32_to_bf16_kernel(const float* x, bf16* y, long n) {
     long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) y[i] = __float2bfloat16(x[i]);
 }
+// the timestep of an eager call travels BY VALUE as a kernel argument
+__global__ void set_scalar_kernel(float* dst, float v) { *dst = v; }
 __global__ void timestep_from_dev_kernel(const float* t, int dim, int NB, bf16* out) {
     uce::pdl_launch(); uce::pdl_wait();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -566,8 +568,21 @@ int sd_unet_forward(sd_unet* u, const float* x, float t, const float* ctx, float
     SD_CUDA(cudaSetDevice(u->device));
     cudaStream_t st = (cudaStream_t)stream;
     const sd_unet_config& c = u->cfg;
-    *u->h_t = t;
-    SD_CUDA(cudaMemcpyAsync(u->d_t, u->h_t, sizeof(float), cudaMemcpyHostToDevice, st));
+    // The timestep reaches the kernels through a device scalar so that a captured CUDA graph can be replayed for every step.
+    // While capturing, the graph gets a copy node that reads the pinned scalar when the REPLAY executes (sd_unet_set_timestep
+    // before each replay; the caller must not change it again before that replay has started).  Eager calls must not use that
+    // scalar: the host runs many calls ahead of the device, and a copy that executes later would pick up the timestep of a later
+    // call (found by tests/test_unet_gpu.py::test_fifty_step_guided_loop...: 51 calls enqueued back to back drifted 2.5x more than
+    // the same calls issued one at a time).
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    SD_CUDA(cudaStreamIsCapturing(st, &cap));
+    if (cap != cudaStreamCaptureStatusNone) {
+        *u->h_t = t;
+        SD_CUDA(cudaMemcpyAsync(u->d_t, u->h_t, sizeof(float), cudaMemcpyHostToDevice, st));
+    } else {
+        set_scalar_kernel<<<1, 1, 0, st>>>(u->d_t, t);
+        SD_CUDA(cudaGetLastError());
+    }
     SD_CUDA(cudaMemcpyAsync(u->x_in, x, (size_t)u->NB * c.in_channels * u->H * u->W * sizeof(float), cudaMemcpyDeviceToDevice, st));
     if (ctx) {                       // context given with the call: (re)compute its K / V^T now
         int rc = sd_unet_set_context(u, ctx, stream);

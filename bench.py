@@ -431,17 +431,19 @@ def bench_denoise(dev, args):
 def bench_sharded(solver, prob, dev, rank, world, args):
     """One edit job, projections dealt round-robin to ranks, ONE all-gather of the edited weights."""
     import torch.distributed as dist
-    from uce_b200.sharding import all_gather_layers, shard_layers
+    from uce_b200.sharding import GatherPlan
     n, ne, K = prob["C"].shape[0], prob["n_edit"], prob["K"]
     from uce_b200.synthetic import problem
     p0 = problem(args.workload, seed=0)                    # every rank: the same job
     Cd, Gd = p0["C"].to(dev), p0["G"].to(dev)
-    mine = shard_layers(len(p0["W"]), world, rank)
-    W = [p0["W"][i].to(dev) for i in mine]
     dims = p0["dims"]
+    plan = GatherPlan(dims, K, world, rank, dev)
+    mine = plan.views_mine()
+    W = [p0["W"][i].to(dev) for i in mine]
+    outs = list(mine.values())
     def once():
-        out = solver.edit(Cd, Gd, p0["scales"], ne, p0["lamb"], W, check=False)
-        return all_gather_layers(dict(zip(mine, out)), dims, K, dev)
+        solver.edit(Cd, Gd, p0["scales"], ne, p0["lamb"], W, outs, check=False)      # W_new = slices of the gather buffer
+        return plan.gather()
     for _ in range(3):
         once()
     torch.cuda.synchronize(dev); dist.barrier()
@@ -454,7 +456,8 @@ def bench_sharded(solver, prob, dev, rank, world, args):
     t = torch.tensor([e0.elapsed_time(e1) / reps], device=dev, dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = t.item()
-    return {"ms_per_job": ms, "value": n / (ms / 1e3), "unit": UNIT, "collective": "1 all_gather_into_tensor (NCCL) of packed edited weights",
+    return {"ms_per_job": ms, "value": n / (ms / 1e3), "unit": UNIT, "collective": "1 in-place all_gather_into_tensor (NCCL) of the packed edited weights (apply kernels write into the gather buffer)",
+            "nvlink_floor_ms": (world - 1) / world * 4.0 * K * sum(dims) / 770e9 * 1e3,      # bytes every GPU must receive / measured peer bandwidth (B200_PROFILING.md)
             "scaling": "strong"}
 
 

@@ -36,6 +36,13 @@ def _worker(rank, world, port, q):
         full = all_gather_layers(local, dims, K, torch.device("cpu"))
         ref = [torch.from_numpy(e).float() for e in O.erase_exact_f64(W, rows[:2], rows[7:9], rows[2:7], 1.0, 1.0, 0.5)]
         ok = all(torch.equal(a, b) for a, b in zip(full, ref)) and len(full) == len(dims)
+        # the in-place form the drivers use: results written straight into slices of the gather buffer, one in-place all-gather
+        from uce_b200.sharding import GatherPlan
+        plan = GatherPlan(dims, K, world, rank, torch.device("cpu"))
+        for i, v in plan.views_mine().items():
+            v.copy_(local[i])
+        full2 = plan.gather()
+        ok = ok and all(torch.equal(a, b) for a, b in zip(full2, ref)) and sorted(plan.views_mine()) == mine
         q.put((rank, ok))
     finally:
         dist.destroy_process_group()

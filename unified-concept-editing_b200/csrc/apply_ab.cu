@@ -96,7 +96,11 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16
 
 __global__ void __launch_bounds__(THREADS_A, 1)
 apply_p_kernel(const Slot* __restrict__ slots, int n_slots, int K, int R, int ks, float* __restrict__ Pbuf,
-               const __grid_constant__ EMaps emaps, const __grid_constant__ WIn wmaps) {
+               const __grid_constant__ EMaps emaps, const __grid_constant__ WIn wmaps, long long* __restrict__ trace) {
+    // optional timeline of CTA 0 (UCE_AB_TRACE=<file>): trace[(role * 64 + index) * 4 + event] = clock64()
+    auto tr = [&](int role, int idx, int ev) {
+        if (trace && blockIdx.x == 0 && idx < 64) trace[(role * 64 + idx) * 4 + ev] = clock64();
+    };
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const uint32_t base = smem_u32(smem_raw);
     if (base & 1023u) {
@@ -147,6 +151,7 @@ apply_p_kernel(const Slot* __restrict__ slots, int n_slots, int K, int R, int ks
         for (int i = 0; i < c.n_items; ++i) {
             const int r = i % NRAW, a = i % NA;
             mbar_wait(bar_raw_full(r), (uint32_t)((i / NRAW) & 1));
+            if (threadIdx.x == 0) tr(1, i, 0);
             const bool row_live = trow < c.sl[g].rows;
             const uint32_t raw = raw_st(r) + row_off;
             uint32_t hi[16], lo[16];
@@ -158,6 +163,7 @@ apply_p_kernel(const Slot* __restrict__ slots, int n_slots, int K, int R, int ks
                 tf32_split(v.z, hi[4 * jv + 2], lo[4 * jv + 2]); tf32_split(v.w, hi[4 * jv + 3], lo[4 * jv + 3]);
             }
             mbar_wait(bar_a_empty(a), (uint32_t)(((i / NA) & 1) ^ 1));       // the MMAs that read this A stage have completed
+            if (threadIdx.x == 0) tr(1, i, 1);
             fence_after();
             __syncwarp();
             const uint32_t ta = lane_base + A_COL0 + 64u * (uint32_t)a + 16u * (uint32_t)half;
@@ -167,10 +173,12 @@ apply_p_kernel(const Slot* __restrict__ slots, int n_slots, int K, int R, int ks
             fence_before();
             __syncwarp();
             if (lane == 0) { mbar_arrive(bar_a_full(a)); mbar_arrive(bar_raw_empty(r)); }
+            if (threadIdx.x == 0) tr(1, i, 2);
             if (++g == c.n_act) g = 0;
         }
         // ---- the partial products of this K slice: TMEM -> registers -> scratch [slice][slot][128 rows][R]; a warp takes half the columns ----
         mbar_wait(bar_p_full, 0);
+        if (threadIdx.x == 0) tr(6, 0, 0);
         fence_after();
         __syncwarp();
         const int cw = R / 2;                                        // columns per warp half: 32 (R = 64) or 16 (R = 32)
@@ -204,6 +212,7 @@ apply_p_kernel(const Slot* __restrict__ slots, int n_slots, int K, int R, int ks
             mbar_wait(bar_raw_empty(r), (uint32_t)(((i / NRAW) & 1) ^ 1));
             __syncwarp();
             if (elect_one()) {
+                tr(0, i, 0);
                 mbar_arrive_expect_tx(bar_raw_full(r), (uint32_t)c.sl[g].h * 128u);
                 tma_load_2d_hint(raw_st(r), &wmaps.in[c.sl[g].layer], bar_raw_full(r), col_of(c, ci), c.sl[g].row0, pol_keep);
             }
@@ -236,6 +245,7 @@ apply_p_kernel(const Slot* __restrict__ slots, int n_slots, int K, int R, int ks
                 fence_after();
                 __syncwarp();
                 if (elect_one()) {
+                    tr(3, i, 0);
                     const uint64_t b_hi = umma_desc_sw128(e_hi_st(se)), b_lo = umma_desc_sw128(e_lo_st(se));
                     const uint32_t a_hi = tmem_base + A_COL0 + 64u * (uint32_t)a, a_lo = a_hi + 32u;
                     const uint32_t d_tmem = tmem_base + 64u * (uint32_t)g;
@@ -249,6 +259,7 @@ apply_p_kernel(const Slot* __restrict__ slots, int n_slots, int K, int R, int ks
                     umma_commit(bar_a_empty(a));
                     if (g == c.n_act - 1) umma_commit(bar_e_empty(se));      // every block has consumed this E stage
                     if (g == c.n_act - 1 && ci == c.ncs - 1) umma_commit(bar_p_full);
+                    tr(3, i, 1);
                 }
                 __syncwarp();
             }
@@ -265,7 +276,10 @@ apply_p_kernel(const Slot* __restrict__ slots, int n_slots, int K, int R, int ks
 // ------------------------------------------------------------------------------------------------ kernel B
 __global__ void __launch_bounds__(THREADS, 1)
 apply_w_kernel(const Slot* __restrict__ slots, int n_slots, int K, int R, int ks, const float* __restrict__ Pbuf,
-               const __grid_constant__ EMaps qmaps, const __grid_constant__ WIo wmaps) {
+               const __grid_constant__ EMaps qmaps, const __grid_constant__ WIo wmaps, long long* __restrict__ trace) {
+    auto tr = [&](int role, int idx, int ev) {
+        if (trace && blockIdx.x == 0 && idx < 64) trace[(role * 64 + idx) * 4 + ev] = clock64();
+    };
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const uint32_t base = smem_u32(smem_raw);
     if (base & 1023u) {
@@ -339,12 +353,14 @@ apply_w_kernel(const Slot* __restrict__ slots, int n_slots, int K, int R, int ks
         fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_p_ready);
+        if (threadIdx.x == 0) tr(6, 0, 1);
         // ---- epilogue: per (unit, block) box += accumulator (in place, swizzled smem); the W TMA warp stores the box ----
         int g = set;
         while (g >= c.n_act) g -= c.n_act;
         for (int i = set; i < c.n_items; i += 2) {
             const int b = i % NBX, a = i % NACC;
             mbar_wait(bar_acc_full(a), (uint32_t)((i / NACC) & 1));
+            if (threadIdx.x == 0) tr(5, i, 0);
             fence_after();
             uint32_t v[32];
             tmem_ld32(lane_base + ACC_COL0 + 32u * (uint32_t)a, v);
@@ -352,6 +368,7 @@ apply_w_kernel(const Slot* __restrict__ slots, int n_slots, int K, int R, int ks
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_acc_empty(a));
             mbar_wait(bar_box_full(b), (uint32_t)((i / NBX) & 1));
+            if (threadIdx.x == 0) tr(5, i, 1);
             if (trow < c.sl[g].rows) {
                 const uint32_t row = box_st(b) + row_off;
 #pragma unroll
@@ -365,6 +382,7 @@ apply_w_kernel(const Slot* __restrict__ slots, int n_slots, int K, int R, int ks
             fence_proxy_async();                       // generic-proxy writes -> visible to the TMA store
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_box_ready(b));
+            if (threadIdx.x == 0) tr(5, i, 2);
             g += 2;
             while (g >= c.n_act) g -= c.n_act;
         }
@@ -390,6 +408,7 @@ apply_w_kernel(const Slot* __restrict__ slots, int n_slots, int K, int R, int ks
             const int ni = i - 1 + NBX;
             const bool reload = i >= 1 && ni < c.n_items;
             if (elect_one()) {
+                tr(0, i, 0);
                 tma_store_2d(&wmaps.out[c.sl[g].layer], box_st(b), col_of(c, u), c.sl[g].row0, pol_out);
                 tma_store_commit();
                 if (reload) tma_store_wait_read<1>();   // the previous item's box has been read out
@@ -436,6 +455,7 @@ apply_w_kernel(const Slot* __restrict__ slots, int n_slots, int K, int R, int ks
                 fence_after();
                 __syncwarp();
                 if (elect_one()) {
+                    tr(4, i, 0);
                     const uint32_t d_tmem = tmem_base + ACC_COL0 + 32u * (uint32_t)a;
                     const uint32_t p_hi = tmem_base + 64u * (uint32_t)g, p_lo = tmem_base + PLO_COL0 + 64u * (uint32_t)g;
                     for (int rc = 0; rc < n_rc; ++rc) {
@@ -451,6 +471,7 @@ apply_w_kernel(const Slot* __restrict__ slots, int n_slots, int K, int R, int ks
                     }
                     umma_commit(bar_q_empty(tq));
                     umma_commit(bar_acc_full(a));
+                    tr(4, i, 1);
                 }
                 __syncwarp();
             }
@@ -545,6 +566,10 @@ int apply_ab_lowrank(uce_ws* ws, const void* slots_dev, const void* slots_host, 
     }
     static thread_local int conf_a[64] = {0}, conf_b[64] = {0};      // opt-in shared-memory size is a per-device function attribute
     const int grid = ceil_div(n_slots, NBLK) * ks;
+    long long* trace = nullptr;                                       // debugging aid: timeline of CTA 0 of both kernels (synchronises)
+    const char* trace_path = getenv("UCE_AB_TRACE");
+    constexpr int TRN = 2 * 7 * 64 * 4;
+    if (trace_path && stage == 0) { UCE_CUDA(cudaMalloc(&trace, TRN * sizeof(long long))); UCE_CUDA(cudaMemsetAsync(trace, 0, TRN * sizeof(long long), st)); }
     if (stage == 0 || stage == 1) {
         EMaps em;
         if ((rc = make_map(&em.hi, ws->E_hi, R, K, R))) return rc;
@@ -552,7 +577,7 @@ int apply_ab_lowrank(uce_ws* ws, const void* slots_dev, const void* slots_host, 
         const int smem = smem_a(R);
         int& cf = conf_a[ws->device & 63];
         if (cf < smem) { UCE_CUDA(cudaFuncSetAttribute(apply_p_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); cf = smem; }
-        apply_p_kernel<<<grid, THREADS_A, smem, st>>>((const Slot*)slots_dev, n_slots, K, R, ks, ws->P, em, *reinterpret_cast<const WIn*>(&wmaps));
+        apply_p_kernel<<<grid, THREADS_A, smem, st>>>((const Slot*)slots_dev, n_slots, K, R, ks, ws->P, em, *reinterpret_cast<const WIn*>(&wmaps), trace);
         UCE_LAUNCH_CHECK();
         *launches += 1;
     }
@@ -564,9 +589,27 @@ int apply_ab_lowrank(uce_ws* ws, const void* slots_dev, const void* slots_host, 
         const int smem = smem_b();
         int& cf = conf_b[ws->device & 63];
         if (cf < smem) { UCE_CUDA(cudaFuncSetAttribute(apply_w_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); cf = smem; }
-        apply_w_kernel<<<grid, THREADS, smem, st>>>((const Slot*)slots_dev, n_slots, K, R, ks, ws->P, qm, wmaps);
+        apply_w_kernel<<<grid, THREADS, smem, st>>>((const Slot*)slots_dev, n_slots, K, R, ks, ws->P, qm, wmaps, trace ? trace + TRN / 2 : nullptr);
         UCE_LAUNCH_CHECK();
         *launches += 1;
+    }
+    if (trace) {
+        std::vector<long long> hbuf(TRN);
+        UCE_CUDA(cudaStreamSynchronize(st));
+        UCE_CUDA(cudaMemcpy(hbuf.data(), trace, hbuf.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+        UCE_CUDA(cudaFree(trace));
+        if (FILE* f = fopen(trace_path, "w")) {
+            const char* roles[7] = {"w_tma", "transform", "e_tma", "mma_a", "mma_b", "epilogue", "p"};
+            for (int kz = 0; kz < 2; ++kz) {
+                long long t0 = 0;
+                for (int x = 0; x < TRN / 2; ++x) { const long long v = hbuf[kz * TRN / 2 + x]; if (v && (!t0 || v < t0)) t0 = v; }
+                for (int r = 0; r < 7; ++r) for (int i = 0; i < 64; ++i) {
+                    const long long* e = &hbuf[kz * TRN / 2 + (r * 64 + i) * 4];
+                    if (e[0] || e[1] || e[2]) fprintf(f, "%c %s %d %lld %lld %lld\n", kz ? 'B' : 'A', roles[r], i, e[0] ? e[0] - t0 : -1, e[1] ? e[1] - t0 : -1, e[2] ? e[2] - t0 : -1);
+                }
+            }
+            fclose(f);
+        }
     }
     return 0;
 }

@@ -6,7 +6,7 @@
 //                 (NB = 32: left-looking factorisation of the diagonal block by one warp, column-sweep inverse by all
 //                 warps, panel + trailing updates by all 512 threads); the factor L and the inverses of its diagonal
 //                 blocks go back to global memory
-//   solve_emit    MANY CTAs, one per 16 columns of K:  X = H^-1 Cp[:, cols]  by blocked forward substitution and the
+//   solve_emit    MANY CTAs, one per 8 columns of K:  X = H^-1 Cp[:, cols]  by blocked forward substitution and the
 //                 part of the backward substitution that reaches the edit rows (they are the LAST rows), all in
 //                 shared memory; the edit rows of X are Q[:, cols] (H^-1 is symmetric:  Q = J H^-1 Cp) -> Q, Qt and the
 //                 TF32 hi/lo splits consumed by the tcgen05 apply.  (The single-CTA substitution on the n_edit unit
@@ -87,31 +87,29 @@ __device__ __forceinline__ double fs_rsqrt(double d) {
     return fma(y0 * e, fma(0.375, e, 0.5), y0);
 }
 
-// One pivot step with the trailing update limited to KM columns (straight-line: the column loads are issued ahead of the
-// FMAs; a per-column early exit was measured 1.8x SLOWER — the branches serialise load and FMA latencies).
-// `d` is the pivot A[j][j] of this step; the return value is the pivot of step j + 1.  The pivot chain does NOT go through shared
-// memory: lane j + 1 updates its own diagonal entry from its own multiplier (A[j+1][j+1] - L[j+1][j]^2 — the same fma, bit for bit,
-// that the column loop below performs for it) and broadcasts it by shuffle while the column of L travels through shared memory
-// for everybody else; the chain per pivot is shuffle -> rsqrt -> multiply -> fma instead of ... -> store -> load -> fma.
+// One pivot step with the trailing update limited to KM columns (straight-line; a per-column early exit was measured 1.8x
+// SLOWER — the branches serialise load and FMA latencies).  `d` is the pivot A[j][j] of this step and `y` its reciprocal square
+// root; the step returns both for pivot j + 1.
+//   * The pivot chain does NOT go through shared memory: lane j + 1 updates its own diagonal entry from its own multiplier
+//     (A[j+1][j+1] - L[j+1][j]^2, the same fma, bit for bit, that the column loop performs for it) and broadcasts it by shuffle.
+//   * The multipliers of the trailing update travel by shuffle too, so the step has no warp barrier: it is ONE basic block, and the
+//     reciprocal square root of the NEXT pivot (cvt, MUFU, four dependent fp64 operations) is issued before the column loop and
+//     interleaves with it — the chain per pivot is max(rsqrt, update) instead of rsqrt + store + barrier + load + update
+//     (11.0 k cycles per 32 x 32 block before; fp64 results are bit-identical: same operations on the same operands).
 template <int KM>
-__device__ __forceinline__ double fs_potrf_step(double (&a)[FS_NB], double* __restrict__ D, double* __restrict__ invd_blk, int lane, int j, double d, bool& bad) {
-    if (!(d > 0.0)) { bad = true; d = 1.0; }
-    const double y = fs_rsqrt(d);
+__device__ __forceinline__ void fs_potrf_step(double (&a)[FS_NB], double* __restrict__ D, double* __restrict__ invd_blk, int lane, int j, double& d, double& y) {
     const double l = (lane == j) ? d * y : a[0] * y;      // L[lane][j] for lanes >= j
-    const double d_next = __shfl_sync(0xffffffffu, fma(-l, l, a[1]), (j + 1) & 31);
+    double d_next = __shfl_sync(0xffffffffu, fma(-l, l, a[1]), (j + 1) & 31);
+    if (!(d_next > 0.0)) d_next = -1.0;                    // flagged by the caller (garbage after the last column is harmless)
+    const double y_next = fs_rsqrt(fabs(d_next));
     if (lane >= j) D[lane * (FS_NB + 1) + j] = l;
     if (lane == j) invd_blk[j] = y;
-    __syncwarp();
-    // L[j + k][j] was just written to shared memory by lane j + k: ONE broadcast 64-bit load per column instead of the two
-    // 32-bit shuffles a double costs (rows beyond 31 read neighbouring shared memory: finite garbage for columns that do not exist)
-    const double* Lj = D + j * (FS_NB + 1) + j;
 #pragma unroll
     for (int k = 1; k <= KM; ++k) {                       // A[lane][j + k] -= L[lane][j] L[j + k][j]
-        const double lk = Lj[k * (FS_NB + 1)];
+        const double lk = __shfl_sync(0xffffffffu, l, (j + k) & 31);
         a[k - 1] = fma(-l, lk, a[k]);
     }
-    __syncwarp();
-    return d_next;
+    d = d_next; y = y_next;
 }
 __device__ __noinline__ void fs_potrf_warp(double* __restrict__ D, double* __restrict__ invd_blk, int lane, int* flag, int kb) {
     double a[FS_NB];
@@ -119,15 +117,21 @@ __device__ __noinline__ void fs_potrf_warp(double* __restrict__ D, double* __res
     for (int c = 0; c < FS_NB; ++c) a[c] = D[lane * (FS_NB + 1) + c];
     bool bad = false;
     double d = __shfl_sync(0xffffffffu, a[0], 0);
+    if (!(d > 0.0)) { bad = true; d = 1.0; }
+    double y = fs_rsqrt(d);
+    // a non-positive pivot is replaced by 1 (the factor is then meaningless; uce_ws_check reports UCE_E_NOT_SPD through `flag`)
+#define FS_STEP(KM_) do { fs_potrf_step<KM_>(a, D, invd_blk, lane, j, d, y); if (j < FS_NB - 1 && d < 0.0) { bad = true; d = 1.0; y = 1.0; } } while (0)
     // columns j + k <= 31 exist: 31, 23, 15 and 7 trailing columns for the four quarters of the block
 #pragma unroll 1
-    for (int j = 0; j < 8; ++j) d = fs_potrf_step<31>(a, D, invd_blk, lane, j, d, bad);
+    for (int j = 0; j < 8; ++j) FS_STEP(31);
 #pragma unroll 1
-    for (int j = 8; j < 16; ++j) d = fs_potrf_step<23>(a, D, invd_blk, lane, j, d, bad);
+    for (int j = 8; j < 16; ++j) FS_STEP(23);
 #pragma unroll 1
-    for (int j = 16; j < 24; ++j) d = fs_potrf_step<15>(a, D, invd_blk, lane, j, d, bad);
+    for (int j = 16; j < 24; ++j) FS_STEP(15);
 #pragma unroll 1
-    for (int j = 24; j < 32; ++j) d = fs_potrf_step<7>(a, D, invd_blk, lane, j, d, bad);
+    for (int j = 24; j < 32; ++j) FS_STEP(7);
+#undef FS_STEP
+    __syncwarp();
     if (bad && lane == 0) atomicCAS(flag, 0, 1 + kb);
 }
 
@@ -135,8 +139,8 @@ __device__ __noinline__ void fs_potrf_warp(double* __restrict__ D, double* __res
 // block inverse left it, 1 / L_cc on the diagonal, explicit zeros below.  The panel and the triangular multiplies of the
 // substitutions then run plain dense inner loops: with the triangle applied as a per-element select those loops were bound by
 // instruction issue (two selects and a compare per 64-bit coefficient: 5.5 k cycles per 32 x 32 x 64 multiply, measured).
-__device__ __forceinline__ void fs_build_ts(double* __restrict__ TS, const double* __restrict__ D, const double* __restrict__ invd_blk, int tid) {
-    for (int idx = tid; idx < FS_NB * FS_NB; idx += FS_T) {
+__device__ __forceinline__ void fs_build_ts(double* __restrict__ TS, const double* __restrict__ D, const double* __restrict__ invd_blk, int tid, int nthreads = FS_T) {
+    for (int idx = tid; idx < FS_NB * FS_NB; idx += nthreads) {
         const int c = idx >> 5, r = idx & 31;
         TS[c * (FS_NB + 1) + r] = (c < r) ? D[c * (FS_NB + 1) + r] : ((c == r) ? invd_blk[c] : 0.0);
     }
@@ -326,11 +330,12 @@ chol_small_kernel(double* __restrict__ Hg, int n, int n_pad, const double* __res
 //   forward   L Y = Cp[:, cols]        over all block rows
 //   backward  L^T X = Y                from the last block row up to the block row of the first edit row
 // Everything in shared memory: the block triangle of L (pitch 33, as chol_small keeps it), a dense copy TS of the current
-// diagonal block's inverse, the slab XS [n_pad][SE_CW + 1].  512 threads:
+// diagonal block's inverse, the slab XS [n_pad][SE_CW + 1].  256 threads:
 //   triangular multiply of a 32 x SE_CW block: one output per thread;  update of the rows below / above: 4 rows x 1 column per
-//   thread (the L coefficients are warp broadcasts, the slab entries consecutive doubles).
-constexpr int SE_CW = 16;
-constexpr int SE_T = 512;
+//   thread (the L coefficients are warp broadcasts, the slab entries consecutive doubles).  K / 8 CTAs (96 for SD-1.4): the work per
+//   CTA is small next to the fixed cost of fetching L (120 KB from L2), so narrower slabs on more SMs win (16 columns: 21 us).
+constexpr int SE_CW = 8;
+constexpr int SE_T = 256;
 __global__ void __launch_bounds__(SE_T, 1)
 solve_emit_kernel(const double* __restrict__ Lg, const double* __restrict__ invd_g, const float* __restrict__ Cp, int n, int n_pad,
                   int n_pres, int n_edit, int r_pad, int K, float* __restrict__ Q, float* __restrict__ Qt, float* __restrict__ Qt_hi,
@@ -349,24 +354,41 @@ solve_emit_kernel(const double* __restrict__ Lg, const double* __restrict__ invd
         const int r = idx / SE_CW, c = idx % SE_CW;
         XS[r * XL + c] = (r < n && k0 + c < K) ? (double)Cp[(long)r * K + k0 + c] : 0.0;
     }
-    for (int idx = tid; idx < nb * FS_NB * FS_NB; idx += SE_T) {
-        const int b = idx >> 10, rc = idx & 1023;
-        SB[b * FS_BLK + (rc >> 5) * P + (rc & 31)] = Lg[idx];
+    {   // 16-byte loads, eight in flight per thread
+        const double2* L2 = reinterpret_cast<const double2*>(Lg);
+        const int n2 = nb * FS_NB * FS_NB / 2;
+        for (int i0 = tid; i0 < n2; i0 += 8 * SE_T) {
+            double2 v[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) { const int idx = i0 + q * SE_T; v[q] = (idx < n2) ? __ldg(L2 + idx) : make_double2(0.0, 0.0); }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int idx = i0 + q * SE_T;
+                if (idx < n2) {
+                    const int e = 2 * idx, b = e >> 10, rc = e & 1023;
+                    double* d = SB + b * FS_BLK + (rc >> 5) * P + (rc & 31);
+                    d[0] = v[q].x; d[1] = v[q].y;
+                }
+            }
+        }
     }
     for (int r = tid; r < n_pad; r += SE_T) invd[r] = invd_g[r];
     __syncthreads();
-    const int c = tid & (SE_CW - 1), rq = tid >> 4;           // column of the slab; row (triangular multiply) or row quad (updates)
+    const int c = tid & (SE_CW - 1), rq = tid / SE_CW;        // column of the slab; row (triangular multiply) or row quad (updates)
     // ---- forward ----
     for (int kb = 0; kb < nblk; ++kb) {
         const double* D = SB + fs_blk(kb, kb);
         const int o = kb * FS_NB;
-        fs_build_ts(TS, D, invd + o, tid);
+        fs_build_ts(TS, D, invd + o, tid, SE_T);
         __syncthreads();
-        double y = 0.0;                                       // Y_k = L_kk^-1 X_k:  (L^-1)[r][j] = TS[j][r]
+        double y0 = 0.0, y1 = 0.0;                            // Y_k = L_kk^-1 X_k:  (L^-1)[r][j] = TS[j][r]
 #pragma unroll 8
-        for (int j = 0; j < FS_NB; ++j) y = fma(TS[j * P + rq], XS[(o + j) * XL + c], y);
+        for (int j = 0; j < FS_NB; j += 2) {
+            y0 = fma(TS[j * P + rq], XS[(o + j) * XL + c], y0);
+            y1 = fma(TS[(j + 1) * P + rq], XS[(o + j + 1) * XL + c], y1);
+        }
         __syncthreads();
-        XS[(o + rq) * XL + c] = y;
+        XS[(o + rq) * XL + c] = y0 + y1;
         __syncthreads();
         const int rows_below = n_pad - o - FS_NB;
         if (4 * rq < rows_below) {                            // X_i -= L_ik Y_k for the block rows below
@@ -389,13 +411,16 @@ solve_emit_kernel(const double* __restrict__ Lg, const double* __restrict__ invd
     for (int kb = nblk - 1; kb >= kb_e; --kb) {
         const double* D = SB + fs_blk(kb, kb);
         const int o = kb * FS_NB;
-        fs_build_ts(TS, D, invd + o, tid);
+        fs_build_ts(TS, D, invd + o, tid, SE_T);
         __syncthreads();
-        double y = 0.0;                                       // X_k = L_kk^-T Y_k:  (L^-T)[r][j] = (L^-1)[j][r] = TS[r][j]
+        double y0 = 0.0, y1 = 0.0;                            // X_k = L_kk^-T Y_k:  (L^-T)[r][j] = (L^-1)[j][r] = TS[r][j]
 #pragma unroll 8
-        for (int j = 0; j < FS_NB; ++j) y = fma(TS[rq * P + j], XS[(o + j) * XL + c], y);
+        for (int j = 0; j < FS_NB; j += 2) {
+            y0 = fma(TS[rq * P + j], XS[(o + j) * XL + c], y0);
+            y1 = fma(TS[rq * P + j + 1], XS[(o + j + 1) * XL + c], y1);
+        }
         __syncthreads();
-        XS[(o + rq) * XL + c] = y;
+        XS[(o + rq) * XL + c] = y0 + y1;
         __syncthreads();
         const int rows_above = o - kb_e * FS_NB;
         if (4 * rq < rows_above) {                            // Y_i -= L_ki^T X_k for the block rows above (down to kb_e)

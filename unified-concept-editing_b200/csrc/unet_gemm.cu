@@ -474,6 +474,8 @@ __global__ void __launch_bounds__(UG_THREADS, 2) unet_gemm_pair_kernel(const __g
     }
     fence_before();
     cluster_sync_all();                                        // the peer's barriers exist before anything signals them
+    __syncthreads();                                           // (the cluster barrier already orders the TMEM-address slot; this CTA barrier is what
+                                                               //  compute-sanitizer racecheck recognises: 2 209 false RAW reports on the slot without it)
     fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));

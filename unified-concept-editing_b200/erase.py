@@ -51,11 +51,13 @@ def UCE(pipe, edit_concepts, guide_concepts, preserve_concepts, erase_scale, pre
 
     dist_on = torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1
     if dist_on:
-        from .sharding import all_gather_layers, shard_layers
+        from .sharding import GatherPlan
         rank, world = torch.distributed.get_rank(), torch.distributed.get_world_size()
-        mine = shard_layers(len(w_old), world, rank)
-        edited = solver.edit(C.to(dev), G.to(dev) if G is not None else None, scales, n_edit, lamb, [w_old[i] for i in mine])
-        w_new = all_gather_layers(dict(zip(mine, edited)), [w.shape[0] for w in w_old], K, dev)
+        plan = GatherPlan([w.shape[0] for w in w_old], K, world, rank, dev)
+        mine = plan.views_mine()            # this rank's projections, written by the apply kernels straight into the gather buffer
+        if mine:                            # more ranks than projections: an empty shard still takes part in the collective
+            solver.edit(C.to(dev), G.to(dev) if G is not None else None, scales, n_edit, lamb, [w_old[i] for i in mine], list(mine.values()))
+        w_new = plan.gather()
         is_writer = rank == 0
     else:
         w_new = solver.edit(C.to(dev), G.to(dev) if G is not None else None, scales, n_edit, lamb, w_old)

@@ -24,7 +24,8 @@ def erase_port_f32(weights, c_edit, c_guide, c_pres, erase_scale=1.0, preserve_s
     """fp32 port of uce_sd_erase.py:45-82 on tensors.
 
     weights: list of [d_l, K] fp32; c_edit/c_guide: [Ne, K]; c_pres: [Np, K] (may be empty).
-    Returns list of W_new [d_l, K] fp32 (CPU torch).
+    Returns list of W_new [d_l, K] fp32, on the device of the inputs (CPU in the tests; bench.py also times it with the tensors on
+    cuda:0 — the reference's own execution path, torch library kernels — as context next to the CPU baseline).
     """
     out = []
     K = weights[0].shape[1]
@@ -35,7 +36,7 @@ def erase_port_f32(weights, c_edit, c_guide, c_pres, erase_scale=1.0, preserve_s
             v_guide = [w_old @ c_guide[i] for i in range(c_guide.shape[0])]
             v_pres = [w_old @ c_pres[i] for i in range(c_pres.shape[0])]
             m1 = lamb * w_old
-            m2 = lamb * torch.eye(K, dtype=torch.float32)
+            m2 = lamb * torch.eye(K, dtype=torch.float32, device=w_old.device)
             for i in range(c_edit.shape[0]):
                 c = c_edit[i].reshape(K, 1)
                 m1 += erase_scale * (v_guide[i].reshape(-1, 1) @ c.T)
@@ -116,7 +117,7 @@ def debias_port_f32(weights, c_edit, c_debias, c_pres, direction_scales, edit_sc
                 break
             for l, w_old in enumerate(weights):
                 m1 = lamb * w_old.to(torch.float32)
-                m2 = lamb * torch.eye(K, dtype=torch.float32)
+                m2 = lamb * torch.eye(K, dtype=torch.float32, device=w_old.device)
                 for i in range(c_edit.shape[0]):
                     v = v_edit[l][i]
                     for j in range(c_debias.shape[0]):

@@ -22,7 +22,21 @@ import numpy as np
 import torch
 import torch.nn.functional as F
 
-from uce_b200.unet_spec import SD14, param_shapes
+from oracle.unet_params import unet_named_parameters
+
+# The one configuration the reference uses (CompVis/stable-diffusion-v1-4/unet/config.json), restated here: the oracle does not import
+# the product's architecture table (tests/test_unet_params.py holds the two to each other).
+SD14 = dict(in_channels=4, out_channels=4, block_out_channels=(320, 640, 1280, 1280), layers_per_block=2,
+            down_has_attn=(True, True, True, False), up_has_attn=(False, True, True, True),
+            cross_attention_dim=768, heads=8, norm_groups=32, temb_dim=1280)
+
+
+def param_shapes(cfg=SD14):
+    """named_parameters() -> shape for a configuration dict of the engine's form, from the oracle's own walk of the diffusers tree."""
+    return unet_named_parameters(block_out_channels=tuple(cfg["block_out_channels"]), layers_per_block=cfg["layers_per_block"],
+                                 cross_attention_dim=cfg["cross_attention_dim"], in_channels=cfg["in_channels"], out_channels=cfg["out_channels"],
+                                 down_block_types=tuple("CrossAttnDownBlock2D" if a else "DownBlock2D" for a in cfg["down_has_attn"]),
+                                 up_block_types=tuple("CrossAttnUpBlock2D" if a else "UpBlock2D" for a in cfg["up_has_attn"]))
 
 
 # ------------------------------------------------------------------------------------------ weights

@@ -100,3 +100,28 @@ def test_rows_dealt_over_ranks_cover_the_reference_calls(world, tmp_path, monkey
         files |= set(f)
     assert sorted(got) == sorted(p for p, _ in ref)
     assert sorted(files) == g["files"]
+
+
+def test_engine_config_is_read_off_the_pipeline():
+    """generate_images() derives the engine configuration and the latent size from pipe.unet.config (the reference accepts any
+    --model_id, evalscripts/generate-images-sd.py:13-15): the SD-1.4 config maps to the engine's SD14 table, an SDXL-style U-Net is
+    refused with a message instead of failing on a weight shape."""
+    import types
+    import pytest
+    from uce_b200.generate import unet_config_of
+    from uce_b200.unet_spec import SD14
+    sd14 = dict(sample_size=64, in_channels=4, out_channels=4, layers_per_block=2, block_out_channels=[320, 640, 1280, 1280],
+                down_block_types=["CrossAttnDownBlock2D"] * 3 + ["DownBlock2D"], up_block_types=["UpBlock2D"] + ["CrossAttnUpBlock2D"] * 3,
+                cross_attention_dim=768, attention_head_dim=8, norm_num_groups=32, use_linear_projection=False)
+    pipe = types.SimpleNamespace(unet=types.SimpleNamespace(config=sd14))
+    cfg, latent = unet_config_of(pipe)
+    assert latent == 64 and all(cfg[k] == (tuple(v) if isinstance(v, (list, tuple)) else v) for k, v in SD14.items())
+    pipe.unet.config = types.SimpleNamespace(**{**sd14, "sample_size": 96})          # attribute-style config (diffusers FrozenDict)
+    assert unet_config_of(pipe)[1] == 96
+    sdxl = {**sd14, "block_out_channels": [320, 640, 1280], "down_block_types": ["DownBlock2D", "CrossAttnDownBlock2D", "CrossAttnDownBlock2D"],
+            "up_block_types": ["CrossAttnUpBlock2D", "CrossAttnUpBlock2D", "UpBlock2D"], "transformer_layers_per_block": [1, 2, 10],
+            "use_linear_projection": True, "addition_embed_type": "text_time", "cross_attention_dim": 2048}
+    pipe.unet.config = sdxl
+    with pytest.raises(NotImplementedError):
+        unet_config_of(pipe)
+    assert unet_config_of(types.SimpleNamespace(unet=types.SimpleNamespace(), latent_size=16))[1] == 16      # synthetic pipes: defaults

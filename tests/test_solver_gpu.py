@@ -403,12 +403,15 @@ def test_two_gemm_tcgen05_apply(n_edit, K, dims):
         for a, b in zip(tc, auto):
             assert torch.equal(a, b)
     exact = O.erase_exact_f64(W[:3], C[:n_edit], G, C[n_edit:], 1.0, 1.0, 0.5)
+    # this kernel sums the whole of K (pass 1) and the whole rank (pass 2) in ONE tensor-memory accumulator: tcgen05 accumulators round
+    # toward zero, so its error is a bias that grows with the chain (measured on SDXL sizes, K = 2048 and rank 1000: 2.0e-5 of W against
+    # 1.1e-6 for the fp32 SIMT twin; north_star asks 1e-4, the reference's own fp32 result is 3e-3 from exact there)
+    chain = max(K, s_rank_pad)
     for i, (a, b, e) in enumerate(zip(simt, tc, exact)):
-        chain = max(K, s_rank_pad)
         assert O.rel_fro(b, e) <= TOL_EXACT * max(1.0, chain / 768.0), ("gemm3x vs exact", O.rel_fro(b, e), "simt vs exact", O.rel_fro(a, e))
         _assert_update(b, e, W[i], ("gemm3x", n_edit, K, i), chain_cols=2 * chain)
     for a, b in zip(simt, tc):
-        assert O.rel_fro(b, a) <= 1e-5, ("gemm3x vs simt", O.rel_fro(b, a))
+        assert O.rel_fro(b, a) <= 1e-5 * max(1.0, chain / 768.0), ("gemm3x vs simt", O.rel_fro(b, a))
     inpl = _run(s, C, G, scales, n_edit, 0.5, W, impl=5, inplace=True)
     for a, b in zip(tc, inpl):
         assert torch.equal(a, b)

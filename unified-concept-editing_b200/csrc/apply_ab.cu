@@ -102,6 +102,7 @@ apply_p_kernel(const Slot* __restrict__ slots, int n_slots, int K, int R, int ks
         if (trace && blockIdx.x == 0 && idx < 64) trace[(role * 64 + idx) * 4 + ev] = clock64();
     };
     extern __shared__ __align__(1024) uint8_t smem_raw[];
+    if (threadIdx.x == 0) tr(6, 2, 0);
     const uint32_t base = smem_u32(smem_raw);
     if (base & 1023u) {
         if (threadIdx.x == 0) printf("uce apply_p: dynamic shared memory base %u is not 1024-byte aligned\n", base);
@@ -139,6 +140,7 @@ apply_p_kernel(const Slot* __restrict__ slots, int n_slots, int K, int R, int ks
     fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+    if (threadIdx.x == 0) tr(6, 2, 1);
 
     if (warp < TW) {
         // =============================== W transform: every warp on every item (its rows x 16 of the chunk's 32 columns) ===============================
@@ -267,6 +269,7 @@ apply_p_kernel(const Slot* __restrict__ slots, int n_slots, int K, int R, int ks
     }
     fence_before();
     __syncthreads();
+    if (threadIdx.x == 0) tr(6, 2, 2);
     if (warp == WARP_MMA) {
         fence_after();
         tmem_dealloc(tmem_base, TMEM_COLS);
@@ -281,6 +284,7 @@ apply_w_kernel(const Slot* __restrict__ slots, int n_slots, int K, int R, int ks
         if (trace && blockIdx.x == 0 && idx < 64) trace[(role * 64 + idx) * 4 + ev] = clock64();
     };
     extern __shared__ __align__(1024) uint8_t smem_raw[];
+    if (threadIdx.x == 0) tr(6, 2, 0);
     const uint32_t base = smem_u32(smem_raw);
     if (base & 1023u) {
         if (threadIdx.x == 0) printf("uce apply_w: dynamic shared memory base %u is not 1024-byte aligned\n", base);
@@ -317,6 +321,7 @@ apply_w_kernel(const Slot* __restrict__ slots, int n_slots, int K, int R, int ks
     fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+    if (threadIdx.x == 0) tr(6, 2, 1);
 
     if (warp < TW) {
         // =============================== P = sum of the slices' partials -> hi | lo in tensor memory; then the epilogue ===============================
@@ -479,6 +484,7 @@ apply_w_kernel(const Slot* __restrict__ slots, int n_slots, int K, int R, int ks
     }
     fence_before();
     __syncthreads();
+    if (threadIdx.x == 0) tr(6, 2, 2);
     if (warp == WARP_MMA) {
         fence_after();
         tmem_dealloc(tmem_base, TMEM_COLS);

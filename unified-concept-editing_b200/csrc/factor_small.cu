@@ -1,7 +1,8 @@
 // Low-latency path of the shared factor for the common case n <= 160 concept rows (dual system, n <= K):
-// 4 kernels instead of the ~35 launches of the general blocked path in factor.cu.
+// 3 kernels instead of the ~35 launches of the general blocked path in factor.cu.
 //
-//   gram_splitk   H = Cp Cp^T, fp64 accumulation of exact fp32 products, 32x32 tiles x split-K over many CTAs
+//   gram_pack     H = Cp Cp^T, fp64 accumulation of exact fp32 products, 32x32 tiles x split-K over many CTAs; the same launch packs
+//                 the concept rows (Cp) and E = G_e - C_e with its tf32 split in extra blocks (the Gram blocks read C directly)
 //   chol_small    ONE CTA: H (+ lamb/s on the diagonal) into shared memory (lower block triangle), blocked Cholesky
 //                 (NB = 32: left-looking factorisation of the diagonal block by one warp, column-sweep inverse by all
 //                 warps, panel + trailing updates by all 512 threads); the factor L and the inverses of its diagonal
@@ -31,9 +32,24 @@ __device__ __forceinline__ float fs_tf32_hi(float x) {
 
 // ---------------------------------------------------------------------------------------------------------
 // H[i,j] += sum_{k in split} Cp[i,k] Cp[j,k]   for tile pairs ti >= tj (lower block triangle); H pre-zeroed.
-__global__ void __launch_bounds__(256) gram_splitk_kernel(const float* __restrict__ Cp, int n, int K, double* __restrict__ H, int ld) {
+// The concept rows are read straight from the caller's C through the row order `src` (internal row r = C[src[r]]), so this kernel
+// does not wait for the pack kernel: the pack work (pack_rows_split below: Cp, E and its tf32 split) rides in the SAME launch as
+// extra blocks (blockIdx.x >= n_pairs, blockIdx.y == 0).
+__device__ void pack_rows_split_block(int r, const float* __restrict__ C, const float* __restrict__ G, const int* __restrict__ src, int n_act,
+                                      int n_pres, int rank_pad, int K, float* __restrict__ Cp, float* __restrict__ E,
+                                      float* __restrict__ E_hi, float* __restrict__ E_lo);
+__global__ void __launch_bounds__(256) gram_pack_kernel(const float* __restrict__ C, const int* __restrict__ src, int n, int K, double* __restrict__ H, int ld,
+                                                        int n_pairs, const float* __restrict__ G, int n_pres, int rank_pad, int n_pack_rows,
+                                                        float* __restrict__ Cp, float* __restrict__ E, float* __restrict__ E_hi, float* __restrict__ E_lo) {
     __shared__ double A[FS_NB][FS_KSPLIT + 1];
     __shared__ double B[FS_NB][FS_KSPLIT + 1];
+    if ((int)blockIdx.x >= n_pairs) {
+        if (blockIdx.y == 0) {
+            const int r = (int)blockIdx.x - n_pairs;
+            if (r < n_pack_rows) pack_rows_split_block(r, C, G, src, n, n_pres, rank_pad, K, Cp, E, E_hi, E_lo);
+        }
+        return;
+    }
     // decode the lower-triangular tile pair
     int p = blockIdx.x, ti = 0;
     while ((ti + 1) * (ti + 2) / 2 <= p) ++ti;
@@ -43,8 +59,8 @@ __global__ void __launch_bounds__(256) gram_splitk_kernel(const float* __restric
     for (int idx = tid; idx < FS_NB * FS_KSPLIT; idx += 256) {
         const int r = idx / FS_KSPLIT, k = idx % FS_KSPLIT;
         const int gi = ti * FS_NB + r, gj = tj * FS_NB + r, gk = k0 + k;
-        A[r][k] = (gi < n && gk < K) ? (double)Cp[(long)gi * K + gk] : 0.0;
-        B[r][k] = (gj < n && gk < K) ? (double)Cp[(long)gj * K + gk] : 0.0;
+        A[r][k] = (gi < n && gk < K) ? (double)C[(long)src[gi] * K + gk] : 0.0;
+        B[r][k] = (gj < n && gk < K) ? (double)C[(long)src[gj] * K + gk] : 0.0;
     }
     __syncthreads();
     const int tx = tid % 16, ty = tid / 16;   // 2 x 2 outputs per thread
@@ -87,29 +103,33 @@ __device__ __forceinline__ double fs_rsqrt(double d) {
     return fma(y0 * e, fma(0.375, e, 0.5), y0);
 }
 
-// One pivot step with the trailing update limited to KM columns (straight-line; a per-column early exit was measured 1.8x
-// SLOWER — the branches serialise load and FMA latencies).  `d` is the pivot A[j][j] of this step and `y` its reciprocal square
-// root; the step returns both for pivot j + 1.
-//   * The pivot chain does NOT go through shared memory: lane j + 1 updates its own diagonal entry from its own multiplier
-//     (A[j+1][j+1] - L[j+1][j]^2, the same fma, bit for bit, that the column loop performs for it) and broadcasts it by shuffle.
-//   * The multipliers of the trailing update travel by shuffle too, so the step has no warp barrier: it is ONE basic block, and the
-//     reciprocal square root of the NEXT pivot (cvt, MUFU, four dependent fp64 operations) is issued before the column loop and
-//     interleaves with it — the chain per pivot is max(rsqrt, update) instead of rsqrt + store + barrier + load + update
-//     (11.0 k cycles per 32 x 32 block before; fp64 results are bit-identical: same operations on the same operands).
+// One pivot step with the trailing update limited to KM columns (straight-line: the column loads are issued ahead of the
+// FMAs; a per-column early exit was measured 1.8x SLOWER — the branches serialise load and FMA latencies).
+// `d` is the pivot A[j][j] of this step; the return value is the pivot of step j + 1.  The pivot chain does NOT go through shared
+// memory: lane j + 1 updates its own diagonal entry from its own multiplier (A[j+1][j+1] - L[j+1][j]^2 — the same fma, bit for bit,
+// that the column loop below performs for it) and broadcasts it by shuffle while the column of L travels through shared memory
+// for everybody else (11.6 k -> 11.0 k cycles per block).  Also measured: the multipliers by shuffle instead of shared memory,
+// which removes both warp barriers and lets the next pivot's rsqrt interleave with the update — 64 shuffles per pivot cost more
+// than that buys (17.1 k cycles per block).
 template <int KM>
-__device__ __forceinline__ void fs_potrf_step(double (&a)[FS_NB], double* __restrict__ D, double* __restrict__ invd_blk, int lane, int j, double& d, double& y) {
+__device__ __forceinline__ double fs_potrf_step(double (&a)[FS_NB], double* __restrict__ D, double* __restrict__ invd_blk, int lane, int j, double d, bool& bad) {
+    if (!(d > 0.0)) { bad = true; d = 1.0; }
+    const double y = fs_rsqrt(d);
     const double l = (lane == j) ? d * y : a[0] * y;      // L[lane][j] for lanes >= j
-    double d_next = __shfl_sync(0xffffffffu, fma(-l, l, a[1]), (j + 1) & 31);
-    if (!(d_next > 0.0)) d_next = -1.0;                    // flagged by the caller (garbage after the last column is harmless)
-    const double y_next = fs_rsqrt(fabs(d_next));
+    const double d_next = __shfl_sync(0xffffffffu, fma(-l, l, a[1]), (j + 1) & 31);
     if (lane >= j) D[lane * (FS_NB + 1) + j] = l;
     if (lane == j) invd_blk[j] = y;
+    __syncwarp();
+    // L[j + k][j] was just written to shared memory by lane j + k: ONE broadcast 64-bit load per column instead of the two
+    // 32-bit shuffles a double costs (rows beyond 31 read neighbouring shared memory: finite garbage for columns that do not exist)
+    const double* Lj = D + j * (FS_NB + 1) + j;
 #pragma unroll
     for (int k = 1; k <= KM; ++k) {                       // A[lane][j + k] -= L[lane][j] L[j + k][j]
-        const double lk = __shfl_sync(0xffffffffu, l, (j + k) & 31);
+        const double lk = Lj[k * (FS_NB + 1)];
         a[k - 1] = fma(-l, lk, a[k]);
     }
-    d = d_next; y = y_next;
+    __syncwarp();
+    return d_next;
 }
 __device__ __noinline__ void fs_potrf_warp(double* __restrict__ D, double* __restrict__ invd_blk, int lane, int* flag, int kb) {
     double a[FS_NB];
@@ -117,21 +137,15 @@ __device__ __noinline__ void fs_potrf_warp(double* __restrict__ D, double* __res
     for (int c = 0; c < FS_NB; ++c) a[c] = D[lane * (FS_NB + 1) + c];
     bool bad = false;
     double d = __shfl_sync(0xffffffffu, a[0], 0);
-    if (!(d > 0.0)) { bad = true; d = 1.0; }
-    double y = fs_rsqrt(d);
-    // a non-positive pivot is replaced by 1 (the factor is then meaningless; uce_ws_check reports UCE_E_NOT_SPD through `flag`)
-#define FS_STEP(KM_) do { fs_potrf_step<KM_>(a, D, invd_blk, lane, j, d, y); if (j < FS_NB - 1 && d < 0.0) { bad = true; d = 1.0; y = 1.0; } } while (0)
     // columns j + k <= 31 exist: 31, 23, 15 and 7 trailing columns for the four quarters of the block
 #pragma unroll 1
-    for (int j = 0; j < 8; ++j) FS_STEP(31);
+    for (int j = 0; j < 8; ++j) d = fs_potrf_step<31>(a, D, invd_blk, lane, j, d, bad);
 #pragma unroll 1
-    for (int j = 8; j < 16; ++j) FS_STEP(23);
+    for (int j = 8; j < 16; ++j) d = fs_potrf_step<23>(a, D, invd_blk, lane, j, d, bad);
 #pragma unroll 1
-    for (int j = 16; j < 24; ++j) FS_STEP(15);
+    for (int j = 16; j < 24; ++j) d = fs_potrf_step<15>(a, D, invd_blk, lane, j, d, bad);
 #pragma unroll 1
-    for (int j = 24; j < 32; ++j) FS_STEP(7);
-#undef FS_STEP
-    __syncwarp();
+    for (int j = 24; j < 32; ++j) d = fs_potrf_step<7>(a, D, invd_blk, lane, j, d, bad);
     if (bad && lane == 0) atomicCAS(flag, 0, 1 + kb);
 }
 
@@ -381,28 +395,30 @@ solve_emit_kernel(const double* __restrict__ Lg, const double* __restrict__ invd
         const int o = kb * FS_NB;
         fs_build_ts(TS, D, invd + o, tid, SE_T);
         __syncthreads();
-        double y0 = 0.0, y1 = 0.0;                            // Y_k = L_kk^-1 X_k:  (L^-1)[r][j] = TS[j][r]
-#pragma unroll 8
-        for (int j = 0; j < FS_NB; j += 2) {
+        double y0 = 0.0, y1 = 0.0, y2 = 0.0, y3 = 0.0;        // Y_k = L_kk^-1 X_k:  (L^-1)[r][j] = TS[j][r]
+#pragma unroll
+        for (int j = 0; j < FS_NB; j += 4) {                  // four partial sums: a dependent fp64 fma costs ~35 cycles on this part
             y0 = fma(TS[j * P + rq], XS[(o + j) * XL + c], y0);
             y1 = fma(TS[(j + 1) * P + rq], XS[(o + j + 1) * XL + c], y1);
+            y2 = fma(TS[(j + 2) * P + rq], XS[(o + j + 2) * XL + c], y2);
+            y3 = fma(TS[(j + 3) * P + rq], XS[(o + j + 3) * XL + c], y3);
         }
         __syncthreads();
-        XS[(o + rq) * XL + c] = y0 + y1;
+        XS[(o + rq) * XL + c] = (y0 + y1) + (y2 + y3);
         __syncthreads();
         const int rows_below = n_pad - o - FS_NB;
         if (4 * rq < rows_below) {                            // X_i -= L_ik Y_k for the block rows below
             const int r = o + FS_NB + 4 * rq;
             const double* A = SB + fs_blk(r >> 5, kb) + (r & 31) * P;
-            double s4[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll 8
-            for (int j = 0; j < FS_NB; ++j) {
-                const double x = XS[(o + j) * XL + c];
+            double s4[4] = {0.0, 0.0, 0.0, 0.0}, t4[4] = {0.0, 0.0, 0.0, 0.0};      // two partial sums per row: eight independent chains
 #pragma unroll
-                for (int i = 0; i < 4; ++i) s4[i] = fma(A[i * P + j], x, s4[i]);
+            for (int j = 0; j < FS_NB; j += 2) {
+                const double x = XS[(o + j) * XL + c], x2 = XS[(o + j + 1) * XL + c];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { s4[i] = fma(A[i * P + j], x, s4[i]); t4[i] = fma(A[i * P + j + 1], x2, t4[i]); }
             }
 #pragma unroll
-            for (int i = 0; i < 4; ++i) XS[(r + i) * XL + c] -= s4[i];
+            for (int i = 0; i < 4; ++i) XS[(r + i) * XL + c] -= s4[i] + t4[i];
         }
         __syncthreads();
     }
@@ -413,28 +429,30 @@ solve_emit_kernel(const double* __restrict__ Lg, const double* __restrict__ invd
         const int o = kb * FS_NB;
         fs_build_ts(TS, D, invd + o, tid, SE_T);
         __syncthreads();
-        double y0 = 0.0, y1 = 0.0;                            // X_k = L_kk^-T Y_k:  (L^-T)[r][j] = (L^-1)[j][r] = TS[r][j]
-#pragma unroll 8
-        for (int j = 0; j < FS_NB; j += 2) {
+        double y0 = 0.0, y1 = 0.0, y2 = 0.0, y3 = 0.0;        // X_k = L_kk^-T Y_k:  (L^-T)[r][j] = (L^-1)[j][r] = TS[r][j]
+#pragma unroll
+        for (int j = 0; j < FS_NB; j += 4) {
             y0 = fma(TS[rq * P + j], XS[(o + j) * XL + c], y0);
             y1 = fma(TS[rq * P + j + 1], XS[(o + j + 1) * XL + c], y1);
+            y2 = fma(TS[rq * P + j + 2], XS[(o + j + 2) * XL + c], y2);
+            y3 = fma(TS[rq * P + j + 3], XS[(o + j + 3) * XL + c], y3);
         }
         __syncthreads();
-        XS[(o + rq) * XL + c] = y0 + y1;
+        XS[(o + rq) * XL + c] = (y0 + y1) + (y2 + y3);
         __syncthreads();
         const int rows_above = o - kb_e * FS_NB;
         if (4 * rq < rows_above) {                            // Y_i -= L_ki^T X_k for the block rows above (down to kb_e)
             const int r = kb_e * FS_NB + 4 * rq;
             const double* A = SB + fs_blk(kb, r >> 5) + (r & 31);            // L[o + j][r + i] = block(kb, r/32)[j][r%32 + i]
-            double s4[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll 8
-            for (int j = 0; j < FS_NB; ++j) {
-                const double x = XS[(o + j) * XL + c];
+            double s4[4] = {0.0, 0.0, 0.0, 0.0}, t4[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
-                for (int i = 0; i < 4; ++i) s4[i] = fma(A[j * P + i], x, s4[i]);
+            for (int j = 0; j < FS_NB; j += 2) {
+                const double x = XS[(o + j) * XL + c], x2 = XS[(o + j + 1) * XL + c];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { s4[i] = fma(A[j * P + i], x, s4[i]); t4[i] = fma(A[(j + 1) * P + i], x2, t4[i]); }
             }
 #pragma unroll
-            for (int i = 0; i < 4; ++i) XS[(r + i) * XL + c] -= s4[i];
+            for (int i = 0; i < 4; ++i) XS[(r + i) * XL + c] -= s4[i] + t4[i];
         }
         __syncthreads();
     }
@@ -451,10 +469,9 @@ solve_emit_kernel(const double* __restrict__ Lg, const double* __restrict__ invd
 }
 
 // E = G_e - C_e with its tf32 split, and the packed concept rows; one block per row.
-__global__ void pack_rows_split_kernel(const float* __restrict__ C, const float* __restrict__ G, const int* __restrict__ src, int n_act,
-                                       int n_pres, int rank_pad, int K, float* __restrict__ Cp, float* __restrict__ E,
-                                       float* __restrict__ E_hi, float* __restrict__ E_lo) {
-    const int r = blockIdx.x;
+__device__ void pack_rows_split_block(int r, const float* __restrict__ C, const float* __restrict__ G, const int* __restrict__ src, int n_act,
+                                      int n_pres, int rank_pad, int K, float* __restrict__ Cp, float* __restrict__ E,
+                                      float* __restrict__ E_hi, float* __restrict__ E_lo) {
     const int n_edit = n_act - n_pres;
     if (r < n_act) {
         const int s = src[r];
@@ -487,12 +504,10 @@ int factor_small(uce_ws* ws, const float* C, const float* G, int n, int n_pres, 
     const int K = ws->K;
     const int n_pad = round_up(n, FS_NB);
     ws->sys_n = n_pad;
-    pack_rows_split_kernel<<<n + (ws->rank_pad - n_edit), 256, 0, st>>>(C, G, ws->src_idx, n, n_pres, ws->rank_pad, K, ws->Cp, ws->E,
-                                                                         ws->E_hi, ws->E_lo);
-    UCE_LAUNCH_CHECK(); ++*launches;
     UCE_CUDA(cudaMemsetAsync(ws->H, 0, (size_t)n_pad * n_pad * sizeof(double), st));
-    const int nt = n_pad / FS_NB;
-    gram_splitk_kernel<<<dim3(nt * (nt + 1) / 2, ceil_div(K, FS_KSPLIT)), 256, 0, st>>>(ws->Cp, n, K, ws->H, n_pad);
+    const int nt = n_pad / FS_NB, n_pairs = nt * (nt + 1) / 2, n_pack = n + (ws->rank_pad - n_edit);
+    gram_pack_kernel<<<dim3(n_pairs + n_pack, ceil_div(K, FS_KSPLIT)), 256, 0, st>>>(C, ws->src_idx, n, K, ws->H, n_pad, n_pairs, G, n_pres, ws->rank_pad,
+                                                                                      n_pack, ws->Cp, ws->E, ws->E_hi, ws->E_lo);
     UCE_LAUNCH_CHECK(); ++*launches;
     // E and its split are complete (pack kernel) and the many-CTA Gram kernel is behind us: from here on the factor is one CTA wide,
     // the point where uce_edit_dev_f32 lets the apply's first kernel (which needs E only) start on its own stream

@@ -1,7 +1,6 @@
 """Edited-model image generation: drop-in for ``generate_images()`` of the reference's
-evalscripts/generate-images-sd.py:10-46 with the denoise loop (U-Net, classifier-free guidance, scheduler) on the
-B200 engine.  Text encoding and VAE decoding stay with the caller's pipeline object, exactly the pieces the
-reference also takes from diffusers (SURVEY.md §8f lists them as the next rows).
+evalscripts/generate-images-sd.py:10-46 with the denoise loop (U-Net, classifier-free guidance, scheduler) and the VAE
+decode on the B200 engines.  Text encoding stays with the caller's pipeline object.
 
 Row sharding: rank r of a torch.distributed job takes CSV rows r::world — rows are independent,
 so the steady state has no collective."""
@@ -36,6 +35,8 @@ class Denoiser:
         """latents [B,4,H,W] (any float dtype, device or host), ctx [2B,77,D] ordered [uncond | text] -> final latents fp32."""
         self.x.copy_(latents.to(self.x.device, torch.float32))
         ctx = ctx_uncond_text.to(self.x.device, torch.float32).contiguous()
+        if guidance_scale <= 1.0:                   # diffusers switches classifier-free guidance off at <= 1: the text-conditioned eps alone
+            guidance_scale = 1.0                    # (eps_u + 1 * (eps_t - eps_u); the unconditional half of the batch is still computed)
         self.eng.set_context(ctx)                   # cross-attention K / V^T of the prompt: once per row, not once per step
         hist = []                                   # most recent first
         free = list(self.hist)
@@ -137,9 +138,35 @@ def rows_for_rank(df, from_case, till_case, rank, world):
     return kept[rank::world]
 
 
+def unet_config_of(pipe, default=SD14):
+    """Engine configuration and latent size read off ``pipe.unet.config`` (a diffusers UNet2DConditionModel config); pipelines without
+    one (synthetic test pipes) get ``default``.  Architectures the engine does not implement fail here, with a message, instead
+    of with a shape mismatch deep in the weight upload (the reference accepts any --model_id; this engine is the SD-1.x U-Net)."""
+    uc = getattr(getattr(pipe, "unet", None), "config", None)
+    latent = getattr(pipe, "latent_size", None)
+    if uc is None:
+        return dict(default), (latent if latent is not None else 64)
+    get = (lambda k, d=None: uc.get(k, d)) if isinstance(uc, dict) else (lambda k, d=None: getattr(uc, k, d))
+    down, up = tuple(get("down_block_types", ())), tuple(get("up_block_types", ()))
+    ok_down = all(t in ("CrossAttnDownBlock2D", "DownBlock2D") for t in down)
+    ok_up = all(t in ("CrossAttnUpBlock2D", "UpBlock2D") for t in up)
+    tl = get("transformer_layers_per_block", 1)
+    if not down or not ok_down or not ok_up or get("use_linear_projection", False) or tl not in (1, (1,) * len(down), [1] * len(down)) \
+            or get("addition_embed_type") or get("class_embed_type") or get("in_channels", 4) != 4:
+        raise NotImplementedError("the B200 U-Net engine implements the SD-1.x UNet2DConditionModel layout (conv proj_in/out, one transformer "
+                                  f"layer per block, no added-condition embeddings); this pipeline's U-Net config is not supported: {down} / {up}")
+    ch = tuple(get("block_out_channels"))
+    ahd = get("attention_head_dim", 8)                    # SD-1.x: this config field is the NUMBER of heads (SURVEY Appendix A)
+    heads = ahd if isinstance(ahd, int) else ahd[0]
+    cfg = dict(in_channels=4, out_channels=get("out_channels", 4), block_out_channels=ch, layers_per_block=get("layers_per_block", 2),
+               down_has_attn=tuple(t == "CrossAttnDownBlock2D" for t in down), up_has_attn=tuple(t == "CrossAttnUpBlock2D" for t in up),
+               cross_attention_dim=get("cross_attention_dim", 768), heads=heads, norm_groups=get("norm_num_groups", 32), temb_dim=4 * ch[0])
+    return cfg, (latent if latent is not None else get("sample_size", 64))
+
+
 def generate_images(model_id, uce_model_path, prompts_path, save_path, exp_name="test", device="cuda:0", torch_dtype=torch.bfloat16,
                     guidance_scale=7.5, num_inference_steps=100, num_images_per_prompt=10, from_case=0, till_case=1000000,
-                    pipe=None, scheduler="pndm", unet_config=SD14, engine=None, denoiser=None):
+                    pipe=None, scheduler="pndm", unet_config=None, engine=None, denoiser=None):
     """Same signature and outputs as the reference (``{save_path}/{exp_name}/{case_number}_{i}.png``); ``pipe`` lets a
     caller inject an already-loaded (or synthetic) pipeline object, ``engine`` / ``denoiser`` an already-built U-Net engine and its
     denoise loop (tests/test_generate_golden.py drives the row loop on CPU with stand-ins)."""
@@ -154,7 +181,9 @@ def generate_images(model_id, uce_model_path, prompts_path, save_path, exp_name=
     if uce_model_path is not None:
         from .artifact import load_artifact
         state.update(load_artifact(uce_model_path))      # load_state_dict(strict=False) semantics (generate-images-sd.py:17-19)
-    latent = getattr(pipe, "latent_size", 64)
+    cfg_pipe, latent = unet_config_of(pipe)
+    if unet_config is None:
+        unet_config = cfg_pipe
     own_engine = engine is None
     if own_engine:
         eng = UNetEngine(unet_config, batch=2 * num_images_per_prompt, H=latent, W=latent, device=device)
@@ -164,7 +193,9 @@ def generate_images(model_id, uce_model_path, prompts_path, save_path, exp_name=
         eng = engine
         eng.load_state_dict(state, strict=False)
     den = denoiser if denoiser is not None else Denoiser(eng, num_images_per_prompt)
-    vae_eng = _vae_engine(pipe, num_images_per_prompt, latent, device) if os.environ.get("UCE_VAE_ENGINE") == "1" else None
+    # VAE decode on the B200 decoder engine whenever the pipeline carries a VAE (UCE_VAE_ENGINE=0 keeps the pipeline's own decode)
+    use_vae_engine = getattr(pipe, "vae", None) is not None and os.environ.get("UCE_VAE_ENGINE", "1") != "0"
+    vae_eng = _vae_engine(pipe, num_images_per_prompt, latent, device) if use_vae_engine else None
 
     df = pd.read_csv(prompts_path)
     folder = f"{save_path}/{exp_name}"

@@ -183,9 +183,12 @@ apply_p_kernel(const Slot* __restrict__ slots, int n_slots, int K, int R, int ks
         if (threadIdx.x == 0) tr(6, 0, 0);
         fence_after();
         __syncwarp();
+        // Scratch layout [slice][slot][R / 4 column quads][128 rows][4]: lane = row, so the 32 lanes of a store instruction write 512
+        // consecutive bytes (row-major [row][R] cost one L1 line per LANE: 32 cycles per store instruction, 6 k cycles for this drain,
+        // and 15 k cycles for the matching loads in kernel B).
         const int cw = R / 2;                                        // columns per warp half: 32 (R = 64) or 16 (R = 32)
         for (int gb = 0; gb < c.n_act; ++gb) {
-            float* dst = Pbuf + (((size_t)c.j * n_slots + (size_t)(c.q * NBLK + gb)) * 128 + trow) * R + half * cw;
+            float4* dst = reinterpret_cast<float4*>(Pbuf) + (((size_t)c.j * n_slots + (size_t)(c.q * NBLK + gb)) * (R / 4) + (size_t)(half * cw / 4)) * 128 + trow;
             const bool live = trow < c.sl[gb].rows;
             uint32_t v[32];
             if (cw == 32) {
@@ -197,11 +200,10 @@ apply_p_kernel(const Slot* __restrict__ slots, int n_slots, int K, int R, int ks
                 for (int e = 0; e < 16; ++e) v[e] = w[e];
             }
             if (live) {
-                float4* d4 = reinterpret_cast<float4*>(dst);
 #pragma unroll
                 for (int jv = 0; jv < 8; ++jv)
                     if (4 * jv < cw)
-                        d4[jv] = make_float4(__uint_as_float(v[4 * jv]), __uint_as_float(v[4 * jv + 1]), __uint_as_float(v[4 * jv + 2]), __uint_as_float(v[4 * jv + 3]));
+                        dst[(size_t)jv * 128] = make_float4(__uint_as_float(v[4 * jv]), __uint_as_float(v[4 * jv + 1]), __uint_as_float(v[4 * jv + 2]), __uint_as_float(v[4 * jv + 3]));
             }
             __syncwarp();                              // tcgen05.ld is .sync.aligned: the warp reconverges before the next one
         }
@@ -330,30 +332,41 @@ apply_w_kernel(const Slot* __restrict__ slots, int n_slots, int K, int R, int ks
         const uint32_t lane_base = tmem_base + ((uint32_t)(32 * wq) << 16);
         const uint32_t row_off = (uint32_t)(trow * 128);
         const uint32_t sw = (uint32_t)(trow & 7);
-        for (int gb = set; gb < c.n_act; gb += 2) {
+        // every warp on every block: a set takes half of the rank columns (32 at R = 64, 16 at R = 32); both slices' partials of a
+        // block are requested before the first add (scratch layout: see kernel A — coalesced 16-byte loads, lane = row)
+        const int cw = R / 2;
+        for (int gb = 0; gb < c.n_act; ++gb) {
             const bool live = trow < c.sl[gb].rows;
-            for (int rc = 0; rc < n_rc; ++rc) {
-                float acc[32];
+            float acc[32];
 #pragma unroll
-                for (int e = 0; e < 32; ++e) acc[e] = 0.f;
-                if (live) {
-                    for (int p = 0; p < ks; ++p) {        // fixed order: bit-reproducible
-                        const float4* s4 = reinterpret_cast<const float4*>(Pbuf + (((size_t)p * n_slots + (size_t)(c.q * NBLK + gb)) * 128 + trow) * R + 32 * rc);
+            for (int e = 0; e < 32; ++e) acc[e] = 0.f;
+            if (live) {
+                for (int p = 0; p < ks; ++p) {            // fixed order: bit-reproducible
+                    const float4* s4 = reinterpret_cast<const float4*>(Pbuf) + (((size_t)p * n_slots + (size_t)(c.q * NBLK + gb)) * (R / 4) + (size_t)(set * cw / 4)) * 128 + trow;
+                    float4 v[8];
 #pragma unroll
-                        for (int jv = 0; jv < 8; ++jv) {
-                            const float4 v = s4[jv];
-                            acc[4 * jv] += v.x; acc[4 * jv + 1] += v.y; acc[4 * jv + 2] += v.z; acc[4 * jv + 3] += v.w;
-                        }
-                    }
+                    for (int jv = 0; jv < 8; ++jv) if (4 * jv < cw) v[jv] = s4[(size_t)jv * 128];
+#pragma unroll
+                    for (int jv = 0; jv < 8; ++jv)
+                        if (4 * jv < cw) { acc[4 * jv] += v[jv].x; acc[4 * jv + 1] += v[jv].y; acc[4 * jv + 2] += v[jv].z; acc[4 * jv + 3] += v[jv].w; }
                 }
-                uint32_t hi[32], lo[32];
-#pragma unroll
-                for (int e = 0; e < 32; ++e) tf32_split(acc[e], hi[e], lo[e]);
-                __syncwarp();                          // tcgen05.st is .sync.aligned
-                tmem_st32(lane_base + 64u * (uint32_t)gb + 32u * (uint32_t)rc, hi);
-                tmem_st32(lane_base + PLO_COL0 + 64u * (uint32_t)gb + 32u * (uint32_t)rc, lo);
-                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             }
+            uint32_t hi[32], lo[32];
+#pragma unroll
+            for (int e = 0; e < 32; ++e) tf32_split(acc[e], hi[e], lo[e]);
+            __syncwarp();                              // tcgen05.st is .sync.aligned
+            const uint32_t t_hi = lane_base + 64u * (uint32_t)gb + (uint32_t)(set * cw), t_lo = t_hi + PLO_COL0;
+            if (cw == 32) {
+                tmem_st32(t_hi, hi);
+                tmem_st32(t_lo, lo);
+            } else {
+                uint32_t h16[16], l16[16];
+#pragma unroll
+                for (int e = 0; e < 16; ++e) { h16[e] = hi[e]; l16[e] = lo[e]; }
+                tmem_st16(t_hi, h16);
+                tmem_st16(t_lo, l16);
+            }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         }
         fence_before();
         __syncwarp();

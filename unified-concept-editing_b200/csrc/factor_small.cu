@@ -4,9 +4,10 @@
 //   gram_pack     H = Cp Cp^T, fp64 accumulation of exact fp32 products, 32x32 tiles x split-K over many CTAs; the same launch packs
 //                 the concept rows (Cp) and E = G_e - C_e with its tf32 split in extra blocks (the Gram blocks read C directly)
 //   chol_small    ONE CTA: H (+ lamb/s on the diagonal) into shared memory (lower block triangle), blocked Cholesky
-//                 (NB = 32: left-looking factorisation of the diagonal block by one warp, column-sweep inverse by all
-//                 warps, panel + trailing updates by all 512 threads); the factor L and the inverses of its diagonal
-//                 blocks go back to global memory
+//                 (NB = 32: left-looking factorisation of the diagonal block by one warp, panel by per-row forward
+//                 substitution, trailing update by all 512 threads with the next diagonal block first — lookahead);
+//                 the factor L goes back to global memory
+//   inv_blocks    one CTA per diagonal block: L_kk^-1 (column sweeps), in place in the global factor
 //   solve_emit    MANY CTAs, one per 8 columns of K:  X = H^-1 Cp[:, cols]  by blocked forward substitution and the
 //                 part of the backward substitution that reaches the edit rows (they are the LAST rows), all in
 //                 shared memory; the edit rows of X are Q[:, cols] (H^-1 is symmetric:  Q = J H^-1 Cp) -> Q, Qt and the
@@ -85,8 +86,8 @@ __global__ void __launch_bounds__(256) gram_pack_kernel(const float* __restrict_
 // Single-CTA Cholesky + solve, everything in shared memory:
 //   SB   lower block triangle of H, 32 x 32 blocks of pitch 33, block (bi,bj) at index bi(bi+1)/2 + bj
 //   XS   right-hand sides / solution  [n_pad][xl]   (n_edit <= 64 columns)
-// After step kb the diagonal block holds L_kk in its lower triangle, the strictly-lower part of L_kk^-1
-// transposed in its strict upper triangle, and 1 / L_ii in invd[].
+// After step kb the diagonal block holds L_kk in its lower triangle (zeros above) and invd[] holds 1 / L_ii; the inverses of the
+// diagonal blocks, which only solve_emit needs, are computed by inv_blocks_kernel on the global copy of the factor.
 constexpr int FS_T = 512;
 constexpr int FS_BLK = FS_NB * (FS_NB + 1);      // doubles per block (pitch 33)
 constexpr int FS_MAX_RHS = 64;
@@ -160,6 +161,33 @@ __device__ __forceinline__ void fs_build_ts(double* __restrict__ TS, const doubl
     }
 }
 
+// Panel row by forward substitution:  x L_kk^T = h  for ONE row h of the panel (thread = row; the row lives in registers and
+// shifts left one column per step, like the diagonal block in fs_potrf_step, so every index is static).  The coefficients
+// L_kk[j + k][j] are warp-wide broadcasts from shared memory.  Per step: one multiply (x_j = h_j / L_jj) and KM independent fmas.
+// This replaces "explicit inverse of L_kk (4.5 k cycles, all warps, a 32-step serial chain) + dense multiply (2.3-7.2 k cycles)" of
+// every block step by one 2.5 k-cycle phase; the inverses, which only the solve kernel needs, moved to their own small kernel.
+template <int KM>
+__device__ __forceinline__ void fs_trsm_step(double (&a)[FS_NB], const double* __restrict__ D, const double* __restrict__ invd_blk, double* __restrict__ row, int j) {
+    const double x = a[0] * invd_blk[j];
+    row[j] = x;
+    const double* Lj = D + j * (FS_NB + 1) + j;
+#pragma unroll
+    for (int k = 1; k <= KM; ++k) a[k - 1] = fma(-x, Lj[k * (FS_NB + 1)], a[k]);
+}
+__device__ __noinline__ void fs_trsm_row(double* __restrict__ row, const double* __restrict__ D, const double* __restrict__ invd_blk) {
+    double a[FS_NB];
+#pragma unroll
+    for (int c = 0; c < FS_NB; ++c) a[c] = row[c];
+#pragma unroll 1
+    for (int j = 0; j < 8; ++j) fs_trsm_step<31>(a, D, invd_blk, row, j);
+#pragma unroll 1
+    for (int j = 8; j < 16; ++j) fs_trsm_step<23>(a, D, invd_blk, row, j);
+#pragma unroll 1
+    for (int j = 16; j < 24; ++j) fs_trsm_step<15>(a, D, invd_blk, row, j);
+#pragma unroll 1
+    for (int j = 24; j < 32; ++j) fs_trsm_step<7>(a, D, invd_blk, row, j);
+}
+
 __global__ void __launch_bounds__(FS_T, 1)
 chol_small_kernel(double* __restrict__ Hg, int n, int n_pad, const double* __restrict__ dadd,
                   double* __restrict__ Lg, double* __restrict__ invd_g, int write_back, int* flag, long long* __restrict__ trace) {
@@ -211,63 +239,12 @@ chol_small_kernel(double* __restrict__ Hg, int n, int n_pad, const double* __res
     __syncthreads();
     tr();   // diag block 0 factored
     for (int kb = 0; kb < nblk; ++kb) {
-        double* D = SB + fs_blk(kb, kb);
+        const double* D = SB + fs_blk(kb, kb);
         const int o = kb * FS_NB;
-        // (b) inverse of L_kk by column sweeps (lane = row): x_j = (delta_jc - acc_j) / L_jj.  A warp carries its two
-        //     columns (c, c + 16) through ONE sweep: the second chain is identically zero until j reaches c + 16.
-        {
-            const int c1 = warp, c2 = warp + NW;
-            double acc1 = 0.0, acc2 = 0.0, mine1 = 0.0, mine2 = 0.0;
-            for (int j = c1; j < FS_NB; ++j) {
-                const double cand1 = ((lane == c1) ? 1.0 : 0.0) - acc1, cand2 = ((lane == c2) ? 1.0 : 0.0) - acc2;
-                const double iv = invd[o + j];
-                const double x1 = __shfl_sync(0xffffffffu, cand1, j) * iv, x2 = __shfl_sync(0xffffffffu, cand2, j) * iv;
-                if (lane == j) { mine1 = x1; mine2 = x2; }
-                if (lane > j) {
-                    const double l = D[lane * P + j];
-                    acc1 = fma(l, x1, acc1); acc2 = fma(l, x2, acc2);
-                }
-            }
-            if (lane > c1) D[c1 * P + lane] = mine1;            // strict upper triangle <- transposed strict lower of L^-1
-            if (lane > c2) D[c2 * P + lane] = mine2;
-        }
-        __syncthreads();
-        tr();   // inverse done
         const int mb = nblk - kb - 1;                            // block rows below
         if (mb > 0) {
-            // (c) panel  L_ik = H_ik L_kk^-T  for the mb blocks below, in place (staged through registers).
-            //     Task = 4 rows x 1 column, lanes = the 32 columns: the H rows are warp broadcasts, the L^-1 coefficients
-            //     consecutive doubles of the dense copy TS (fixed trip count, no per-element select: see fs_build_ts).
-            fs_build_ts(TS, D, invd + o, tid);
-            __syncthreads();
-            double out[2][4];
-#pragma unroll
-            for (int it = 0; it < 2; ++it) {
-                const int idx = tid + it * FS_T;
-#pragma unroll
-                for (int i = 0; i < 4; ++i) out[it][i] = 0.0;
-                if (idx < mb * 256) {
-                    const int c = idx & 31, rq = idx >> 5;
-                    const double* A = SB + fs_blk(kb + 1 + (rq >> 3), kb) + (rq & 7) * 4 * P;
-#pragma unroll 8
-                    for (int j = 0; j < FS_NB; ++j) {
-                        const double coef = TS[j * P + c];                                 // (L^-1)[c][j], zero for j > c
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) out[it][i] = fma(A[i * P + j], coef, out[it][i]);
-                    }
-                }
-            }
-            __syncthreads();
-#pragma unroll
-            for (int it = 0; it < 2; ++it) {
-                const int idx = tid + it * FS_T;
-                if (idx < mb * 256) {
-                    const int c = idx & 31, rq = idx >> 5;
-                    double* A = SB + fs_blk(kb + 1 + (rq >> 3), kb) + (rq & 7) * 4 * P;
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) A[i * P + c] = out[it][i];
-                }
-            }
+            // (c) panel  L_ik = H_ik L_kk^-T  for the mb blocks below, in place: one thread per panel row (fs_trsm_row)
+            if (tid < mb * FS_NB) fs_trsm_row(SB + fs_blk(kb + 1 + (tid >> 5), kb) + (tid & 31) * P, D, invd + o);
             __syncthreads();
             tr();   // panel done
             // (d) trailing update of the lower block triangle:  H_ij -= L_ik L_jk^T, 4 x 4 register tiles (8 shared-memory loads
@@ -306,7 +283,28 @@ chol_small_kernel(double* __restrict__ Hg, int n, int n_pad, const double* __res
                     for (int j2 = 0; j2 < 4; ++j2)
                         if (ti != tj || c0 + j2 <= r0 + i) Cb[(r0 + i) * P + c0 + j2] -= acc[i][j2];
             };
-            if (tid < 64) trailing_task(tid);                        // pair 0 = the next diagonal block (kb + 1, kb + 1)
+            // pair 0 = the next diagonal block (kb + 1, kb + 1), first and alone (the lookahead potrf waits for it): 4 x 2 tiles on
+            // 128 threads instead of 4 x 4 on 64 — this phase is bound by the latency of its dependent fma chains, not by throughput
+            if (tid < 128) {
+                const int r0 = (tid >> 4) * 4, c0 = (tid & 15) * 2;
+                if (c0 <= r0 + 3) {
+                    const double* A = SB + fs_blk(kb + 1, kb) + r0 * P;
+                    const double* B = SB + fs_blk(kb + 1, kb) + c0 * P;
+                    double acc[4][2] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};
+#pragma unroll 4
+                    for (int j = 0; j < FS_NB; ++j) {
+                        const double b0 = B[j], b1 = B[P + j];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) { const double av = A[i * P + j]; acc[i][0] = fma(av, b0, acc[i][0]); acc[i][1] = fma(av, b1, acc[i][1]); }
+                    }
+                    double* Cb = SB + fs_blk(kb + 1, kb + 1);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+#pragma unroll
+                        for (int j2 = 0; j2 < 2; ++j2)
+                            if (c0 + j2 <= r0 + i) Cb[(r0 + i) * P + c0 + j2] -= acc[i][j2];
+                }
+            }
             __syncthreads();
             tr();   // next diagonal block updated
             if (warp == 0) {
@@ -337,6 +335,36 @@ chol_small_kernel(double* __restrict__ Hg, int n, int n_pad, const double* __res
         for (int r = tid; r < n_pad; r += FS_T) invd_g[r] = invd[r];
     }
     tr();
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Inverses of the diagonal blocks of L, one CTA per block, in place in the global copy of the factor: the strictly-lower part of
+// L_kk^-1 goes, transposed, into the strict upper triangle of the block (solve_emit reads it through fs_build_ts).  Column sweeps
+// (lane = row): x_j = (delta_jc - acc_j) / L_jj; a warp carries its two columns (c, c + 16) through ONE sweep: the second chain is
+// identically zero until j reaches c + 16.  Off the single-CTA kernel's critical path: all blocks at once, 4.5 k cycles.
+__global__ void __launch_bounds__(FS_T, 1) inv_blocks_kernel(double* __restrict__ Lg, const double* __restrict__ invd_g) {
+    __shared__ double Ds[FS_NB * (FS_NB + 1)];
+    __shared__ double iv_s[FS_NB];
+    constexpr int P = FS_NB + 1, NW = FS_T / 32;
+    const int kb = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double* Dg = Lg + (size_t)(kb * (kb + 1) / 2 + kb) * FS_NB * FS_NB;
+    for (int idx = tid; idx < FS_NB * FS_NB; idx += FS_T) Ds[(idx >> 5) * P + (idx & 31)] = Dg[idx];
+    if (tid < FS_NB) iv_s[tid] = invd_g[kb * FS_NB + tid];
+    __syncthreads();
+    const int c1 = warp, c2 = warp + NW;
+    double acc1 = 0.0, acc2 = 0.0, mine1 = 0.0, mine2 = 0.0;
+    for (int j = c1; j < FS_NB; ++j) {
+        const double cand1 = ((lane == c1) ? 1.0 : 0.0) - acc1, cand2 = ((lane == c2) ? 1.0 : 0.0) - acc2;
+        const double iv = iv_s[j];
+        const double x1 = __shfl_sync(0xffffffffu, cand1, j) * iv, x2 = __shfl_sync(0xffffffffu, cand2, j) * iv;
+        if (lane == j) { mine1 = x1; mine2 = x2; }
+        if (lane > j) {
+            const double l = Ds[lane * P + j];
+            acc1 = fma(l, x1, acc1); acc2 = fma(l, x2, acc2);
+        }
+    }
+    if (lane > c1) Dg[c1 * FS_NB + lane] = mine1;            // strict upper triangle <- transposed strict lower of L^-1
+    if (lane > c2) Dg[c2 * FS_NB + lane] = mine2;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -548,6 +576,8 @@ int factor_small(uce_ws* ws, const float* C, const float* G, int n, int n_pres, 
             fclose(f);
         }
     }
+    inv_blocks_kernel<<<nt, FS_T, 0, st>>>(Lg, invd_g);
+    UCE_LAUNCH_CHECK(); ++*launches;
     solve_emit_kernel<<<ceil_div(K, SE_CW), SE_T, smem_s, st>>>(Lg, invd_g, ws->Cp, n, n_pad, n_pres, n_edit, ws->rank_pad, K, ws->Q, ws->Qt,
                                                                 ws->Qt_hi, ws->Qt_lo);
     UCE_LAUNCH_CHECK(); ++*launches;

@@ -341,14 +341,23 @@ apply_w_kernel(const Slot* __restrict__ slots, int n_slots, int K, int R, int ks
 #pragma unroll
             for (int e = 0; e < 32; ++e) acc[e] = 0.f;
             if (live) {
-                for (int p = 0; p < ks; ++p) {            // fixed order: bit-reproducible
-                    const float4* s4 = reinterpret_cast<const float4*>(Pbuf) + (((size_t)p * n_slots + (size_t)(c.q * NBLK + gb)) * (R / 4) + (size_t)(set * cw / 4)) * 128 + trow;
-                    float4 v[8];
-#pragma unroll
-                    for (int jv = 0; jv < 8; ++jv) if (4 * jv < cw) v[jv] = s4[(size_t)jv * 128];
+                const size_t part = (size_t)n_slots * (R / 4) * 128;      // float4 elements between two slices' partials
+                const float4* s0 = reinterpret_cast<const float4*>(Pbuf) + ((size_t)(c.q * NBLK + gb) * (R / 4) + (size_t)(set * cw / 4)) * 128 + trow;
+                for (int p = 0; p < ks; p += 2) {         // fixed order: bit-reproducible; two slices' loads in flight together
+                    const bool two = p + 1 < ks;
+                    float4 v[8], w[8];
 #pragma unroll
                     for (int jv = 0; jv < 8; ++jv)
-                        if (4 * jv < cw) { acc[4 * jv] += v[jv].x; acc[4 * jv + 1] += v[jv].y; acc[4 * jv + 2] += v[jv].z; acc[4 * jv + 3] += v[jv].w; }
+                        if (4 * jv < cw) {
+                            v[jv] = s0[(size_t)p * part + (size_t)jv * 128];
+                            w[jv] = two ? s0[(size_t)(p + 1) * part + (size_t)jv * 128] : make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
+#pragma unroll
+                    for (int jv = 0; jv < 8; ++jv)
+                        if (4 * jv < cw) {
+                            acc[4 * jv] += v[jv].x; acc[4 * jv + 1] += v[jv].y; acc[4 * jv + 2] += v[jv].z; acc[4 * jv + 3] += v[jv].w;
+                            if (two) { acc[4 * jv] += w[jv].x; acc[4 * jv + 1] += w[jv].y; acc[4 * jv + 2] += w[jv].z; acc[4 * jv + 3] += w[jv].w; }
+                        }
                 }
             }
             uint32_t hi[32], lo[32];

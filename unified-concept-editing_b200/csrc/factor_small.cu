@@ -198,9 +198,7 @@ chol_small_kernel(double* __restrict__ Hg, int n, int n_pad, const double* __res
     const int nblk = n_pad / FS_NB;
     double* SB = smem_d;
     double* invd = SB + (nblk * (nblk + 1) / 2) * FS_BLK;      // [n_pad]
-    double* TS = invd + n_pad;                    // [32][33] dense copy of one block's L^-1 (see fs_build_ts)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    constexpr int NW = FS_T / 32;
     constexpr int P = FS_NB + 1;                  // block pitch
 
     // ---- load the lower block triangle (+ diagonal term, identity padding): warp = block row, lane = column; the global
@@ -311,6 +309,12 @@ chol_small_kernel(double* __restrict__ Hg, int n, int n_pad, const double* __res
                 fs_potrf_warp(SB + fs_blk(kb + 1, kb + 1), invd + o + FS_NB, lane, flag, kb + 1);
             } else {
                 for (int idx = 64 + tid - 32; idx < npairs * 64; idx += FS_T - 32) trailing_task(idx);
+                // block column kb (L_kk and the panel below it) is final: it goes to global memory here, in the shadow of warp 0's
+                // potrf, instead of in one 4.4 k-cycle pass after the last step
+                for (int idx = tid - 32; idx < (mb + 1) * FS_NB * FS_NB; idx += FS_T - 32) {
+                    const int bi = kb + (idx >> 10), rc = idx & 1023;
+                    Lg[(size_t)(bi * (bi + 1) / 2 + kb) * (FS_NB * FS_NB) + rc] = SB[fs_blk(bi, kb) + (rc >> 5) * P + (rc & 31)];
+                }
             }
             __syncthreads();
         }
@@ -326,12 +330,10 @@ chol_small_kernel(double* __restrict__ Hg, int n, int n_pad, const double* __res
     // ---- the factor goes back to global memory for solve_emit: the block triangle as it sits in shared memory (diagonal blocks:
     //      L_kk in the lower triangle, the strictly-lower part of L_kk^-1 transposed in the strict upper triangle), 32 x 32 blocks
     //      of pitch 32, and 1 / L_ii ----
-    {
-        const int nb = nblk * (nblk + 1) / 2;
-        for (int idx = tid; idx < nb * FS_NB * FS_NB; idx += FS_T) {
-            const int b = idx >> 10, rc = idx & 1023;
-            Lg[idx] = SB[b * FS_BLK + (rc >> 5) * P + (rc & 31)];
-        }
+    {   // (the block columns before the last one were written during the steps)
+        const int kl = nblk - 1;
+        for (int idx = tid; idx < FS_NB * FS_NB; idx += FS_T)
+            Lg[(size_t)(kl * (kl + 1) / 2 + kl) * (FS_NB * FS_NB) + idx] = SB[fs_blk(kl, kl) + (idx >> 5) * P + (idx & 31)];
         for (int r = tid; r < n_pad; r += FS_T) invd_g[r] = invd[r];
     }
     tr();
@@ -438,15 +440,22 @@ solve_emit_kernel(const double* __restrict__ Lg, const double* __restrict__ invd
         if (4 * rq < rows_below) {                            // X_i -= L_ik Y_k for the block rows below
             const int r = o + FS_NB + 4 * rq;
             const double* A = SB + fs_blk(r >> 5, kb) + (r & 31) * P;
-            double s4[4] = {0.0, 0.0, 0.0, 0.0}, t4[4] = {0.0, 0.0, 0.0, 0.0};      // two partial sums per row: eight independent chains
+            double s4[4][4];                                  // four partial sums per row: sixteen independent fma chains
 #pragma unroll
-            for (int j = 0; j < FS_NB; j += 2) {
-                const double x = XS[(o + j) * XL + c], x2 = XS[(o + j + 1) * XL + c];
+            for (int i = 0; i < 4; ++i)
 #pragma unroll
-                for (int i = 0; i < 4; ++i) { s4[i] = fma(A[i * P + j], x, s4[i]); t4[i] = fma(A[i * P + j + 1], x2, t4[i]); }
+                for (int q = 0; q < 4; ++q) s4[i][q] = 0.0;
+#pragma unroll
+            for (int j = 0; j < FS_NB; j += 4) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const double x = XS[(o + j + q) * XL + c];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) s4[i][q] = fma(A[i * P + j + q], x, s4[i][q]);
+                }
             }
 #pragma unroll
-            for (int i = 0; i < 4; ++i) XS[(r + i) * XL + c] -= s4[i] + t4[i];
+            for (int i = 0; i < 4; ++i) XS[(r + i) * XL + c] -= (s4[i][0] + s4[i][1]) + (s4[i][2] + s4[i][3]);
         }
         __syncthreads();
     }
@@ -472,15 +481,22 @@ solve_emit_kernel(const double* __restrict__ Lg, const double* __restrict__ invd
         if (4 * rq < rows_above) {                            // Y_i -= L_ki^T X_k for the block rows above (down to kb_e)
             const int r = kb_e * FS_NB + 4 * rq;
             const double* A = SB + fs_blk(kb, r >> 5) + (r & 31);            // L[o + j][r + i] = block(kb, r/32)[j][r%32 + i]
-            double s4[4] = {0.0, 0.0, 0.0, 0.0}, t4[4] = {0.0, 0.0, 0.0, 0.0};
+            double s4[4][4];
 #pragma unroll
-            for (int j = 0; j < FS_NB; j += 2) {
-                const double x = XS[(o + j) * XL + c], x2 = XS[(o + j + 1) * XL + c];
+            for (int i = 0; i < 4; ++i)
 #pragma unroll
-                for (int i = 0; i < 4; ++i) { s4[i] = fma(A[j * P + i], x, s4[i]); t4[i] = fma(A[(j + 1) * P + i], x2, t4[i]); }
+                for (int q = 0; q < 4; ++q) s4[i][q] = 0.0;
+#pragma unroll
+            for (int j = 0; j < FS_NB; j += 4) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const double x = XS[(o + j + q) * XL + c];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) s4[i][q] = fma(A[(j + q) * P + i], x, s4[i][q]);
+                }
             }
 #pragma unroll
-            for (int i = 0; i < 4; ++i) XS[(r + i) * XL + c] -= s4[i] + t4[i];
+            for (int i = 0; i < 4; ++i) XS[(r + i) * XL + c] -= (s4[i][0] + s4[i][1]) + (s4[i][2] + s4[i][3]);
         }
         __syncthreads();
     }

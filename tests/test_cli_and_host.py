@@ -226,6 +226,16 @@ def test_generation_rows_are_dealt_round_robin_after_the_case_filter():
     assert rows_for_rank(df, 100, 200, 0, 2) == []
 
 
+def test_clip_text_c_abi_exports_every_declared_symbol():
+    from uce_b200 import _native, clip_text
+    hdr = open(os.path.join(ROOT, "include", "clip_text_b200.h")).read()
+    declared = set(re.findall(r"\b(clipt_[a-z0-9_]+)\s*\(", hdr))
+    lib = ctypes.CDLL(_native.LIB_PATH)
+    for sym in declared:
+        assert hasattr(lib, sym), sym
+    assert declared == set(clip_text.SIGNATURES), declared ^ set(clip_text.SIGNATURES)
+
+
 def test_public_headers_are_plain_c(tmp_path):
     """The drop-in boundary is a C ABI: both headers must compile as C11 on their own (no torch / CUDA types in the signatures)."""
     import shutil
@@ -234,7 +244,7 @@ def test_public_headers_are_plain_c(tmp_path):
     if gcc is None:
         pytest.skip("gcc not available")
     src = tmp_path / "hdr.c"
-    src.write_text(f'#include "{ROOT}/include/uce_b200.h"\n#include "{ROOT}/include/sd_unet_b200.h"\n#include "{ROOT}/include/sd_vae_b200.h"\nint main(void) {{ return 0; }}\n')
+    src.write_text(f'#include "{ROOT}/include/uce_b200.h"\n#include "{ROOT}/include/sd_unet_b200.h"\n#include "{ROOT}/include/sd_vae_b200.h"\n#include "{ROOT}/include/clip_text_b200.h"\nint main(void) {{ return 0; }}\n')
     r = subprocess.run([gcc, "-std=c11", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", str(src)], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
 

@@ -39,6 +39,32 @@ def can_batch_encode(pipe) -> bool:
             and callable(getattr(pipe, "tokenizer", None)))
 
 
+def can_use_text_engine(pipe, device) -> bool:
+    """The B200 text encoder (uce_b200.clip_text) takes a plain CLIPTextModel: one text encoder, quick-GELU MLP, no attention mask,
+    no projection — the SD-1.x layout — on a CUDA device."""
+    te = getattr(pipe, "text_encoder", None)
+    cfg = getattr(te, "config", None)
+    if not can_batch_encode(pipe) or cfg is None or not str(device).startswith("cuda") or not torch.cuda.is_available():
+        return False
+    return (getattr(cfg, "hidden_act", None) == "quick_gelu" and not getattr(cfg, "use_attention_mask", False)
+            and hasattr(te, "state_dict") and getattr(cfg, "hidden_size", 4096) <= 1024)
+
+
+def embed_concepts_engine(pipe, prompts, device, batch_size: int = 128) -> dict:
+    """``embed_concepts_batched`` with the forward on the B200 text-encoder engine (fp32 CUDA kernels, include/clip_text_b200.h): every
+    distinct prompt once, ``batch_size`` prompts per forward, the kept rows selected on the device."""
+    from .clip_text import ClipTextEngine
+    uniq = list(dict.fromkeys(prompts))
+    tk = pipe.tokenizer
+    eng = ClipTextEngine(pipe.text_encoder.state_dict(), pipe.text_encoder.config.num_attention_heads, device=device, max_batch=batch_size)
+    try:
+        tok = tk(uniq, padding="max_length", max_length=tk.model_max_length, truncation=True, return_tensors="pt")
+        rows = eng.concept_rows(tok["input_ids"], tok["attention_mask"])
+    finally:
+        eng.close()
+    return {p: rows[j] for j, p in enumerate(uniq)}
+
+
 def embed_concepts_batched(pipe, prompts, device, batch_size: int = 128) -> dict:
     """Same rows as ``embed_concepts`` from BATCHED text-encoder calls: the reference encodes one prompt per forward
     (uce_sd_erase.py:26-42), which dominates an edit of hundreds of concepts.  What encode_prompt does for a plain
@@ -64,10 +90,14 @@ def embed_concepts_batched(pipe, prompts, device, batch_size: int = 128) -> dict
 
 
 def embed_concepts(pipe, prompts, device, batched: bool | None = None) -> dict:
-    """prompt -> [K] row, each distinct prompt encoded once (uce_sd_erase.py:26-28).  ``batched`` (default: the UCE_BATCHED_ENCODE=1
-    environment switch) routes eligible pipelines through ``embed_concepts_batched``; otherwise one encode_prompt call per prompt, as
-    the reference does."""
+    """prompt -> [K] row, each distinct prompt encoded once (uce_sd_erase.py:26-28).  A pipeline with a plain SD-1.x CLIP text encoder on
+    a CUDA device goes through the B200 text-encoder engine (one batched fp32 forward; UCE_TEXT_ENGINE=0 disables it); ``batched``
+    (default: the UCE_BATCHED_ENCODE=1 environment switch) routes other single-encoder pipelines through batched calls of their own
+    torch encoder; everything else (SDXL's two encoders, synthetic test pipes) gets one encode_prompt call per prompt, as the
+    reference does."""
     import os
+    if os.environ.get("UCE_TEXT_ENGINE", "1") != "0" and can_use_text_engine(pipe, device):
+        return embed_concepts_engine(pipe, prompts, device)      # SD-1.x text encoder: one batched forward on the B200 engine
     if batched is None:
         batched = os.environ.get("UCE_BATCHED_ENCODE") == "1"
     if batched and can_batch_encode(pipe):

@@ -16,7 +16,7 @@ namespace uce {
 
 bool apply_gemm3x_available(const uce_ws* ws, int n_layers);   // apply_gemm3x.cu
 int apply_gemm3x_highrank(uce_ws* ws, const LayerRef* layers_dev, const LayerRef* layers_host, int n_layers, int total_tiles,
-                          cudaStream_t st, int* launches);
+                          cudaStream_t st, int* launches, int stage);
 bool apply_ab_available(const uce_ws* ws, int n_layers);    // apply_ab.cu
 int apply_ab_ksplit(int K);
 int apply_ab_plan(int sm_count, int ks, const int* d, int n_layers, int* block_rows, int* first_block);
@@ -119,8 +119,26 @@ static bool choose_ab(const uce_ws* ws, int n_layers) {
     const bool lowrank = !ws->dense && ws->rank > 0;
     return lowrank && (ws->apply_impl == 7 || ws->apply_impl == 0) && apply_ab_available(ws, n_layers);
 }
+static bool choose_g3(const uce_ws* ws, int n_layers) {
+    const bool lowrank = !ws->dense && ws->rank > 0;
+    if (!lowrank || choose_ab(ws, n_layers)) return false;
+    if (ws->apply_impl == 4 || (ws->apply_impl == 0 && apply_tc3_available(ws, n_layers))) return false;
+    return (ws->apply_impl == 5 || ws->apply_impl == 0) && apply_gemm3x_available(ws, n_layers);
+}
+// both two-kernel tcgen05 forms have a first kernel (W_old E^T) that needs only E: it can run beside the factor
 bool apply_stage_split(const uce_ws* ws, int n_layers) {
-    return ws->mode != 0 && choose_ab(ws, n_layers > 96 ? 96 : n_layers);
+    const int nl = n_layers > 96 ? 96 : n_layers;
+    return ws->mode != 0 && (choose_ab(ws, nl) || choose_g3(ws, nl));
+}
+// scratch floats one call of `nl` projections needs (two-kernel forms; 0 otherwise)
+static size_t staged_scratch(const uce_ws* ws, const int* d, int nl) {
+    if (choose_ab(ws, nl)) {
+        std::vector<int> a(nl), b(nl);
+        const int ks = apply_ab_ksplit(ws->K);
+        return (size_t)ks * apply_ab_plan(ws->sm_count, ks, d, nl, a.data(), b.data()) * 128 * ws->rank_pad;
+    }
+    if (choose_g3(ws, nl)) { size_t t = 0; for (int l = 0; l < nl; ++l) t += ceil_div(d[l], 128); return t * 128 * ws->rank_pad; }
+    return 0;
 }
 
 int apply_dev(uce_ws* ws, const float* const* W_old, float* const* W_new, const int* d, int n_layers, cudaStream_t st,
@@ -131,17 +149,35 @@ int apply_dev(uce_ws* ws, const float* const* W_old, float* const* W_new, const 
     // the two-block tcgen05 apply carries two tensor maps per projection as kernel parameters (96 projections per launch):
     // longer lists (SDXL: 140 projections) go through it in slices
     constexpr int TC3_MAX = 96;
-    if (stage != 0 && !choose_ab(ws, std::min(n_layers, TC3_MAX))) { set_error("staged apply needs the K-split path"); return UCE_E_STATE; }
+    if (stage != 0 && !apply_stage_split(ws, n_layers)) { set_error("staged apply needs one of the two-kernel tcgen05 paths"); return UCE_E_STATE; }
     if (n_layers > TC3_MAX && !ws->dense && ws->rank > 0 && ws->apply_impl != 1 &&
         (apply_ab_available(ws, TC3_MAX) || apply_tc3_available(ws, TC3_MAX) || apply_gemm3x_available(ws, TC3_MAX))) {
-        if (stage != 0) { set_error("staged apply takes at most %d projections per call", TC3_MAX); return UCE_E_STATE; }
+        // slices of 96 projections.  A staged call (stage 1 for every slice, later stage 2 for every slice) needs every slice's partial
+        // products at the same time: each slice gets its own part of the scratch (P_off); unstaged calls reuse one part.
+        size_t total_need = 0, max_need = 0;
+        for (int l0 = 0; l0 < n_layers; l0 += TC3_MAX) {
+            const size_t nd = staged_scratch(ws, d + l0, std::min(TC3_MAX, n_layers - l0));
+            total_need += nd; max_need = std::max(max_need, nd);
+        }
+        const size_t want = stage != 0 ? total_need : max_need;
+        if (want > ws->P_cap) {
+            if (stage == 2) { set_error("apply scratch changed between the stages"); return UCE_E_STATE; }
+            if (ws->P) { UCE_CUDA(cudaStreamSynchronize(st)); UCE_CUDA(cudaFree(ws->P)); ws->P = nullptr; }
+            ws->P_cap = want + want / 4;
+            UCE_CUDA(cudaMalloc(&ws->P, ws->P_cap * sizeof(float)));
+        }
         int total_launches = 0;
         const bool prof = ws->profile && !no_profile;
         if (prof) UCE_CUDA(cudaEventRecord(ws->pev[2], st));
+        size_t off = 0;
         for (int l0 = 0; l0 < n_layers; l0 += TC3_MAX) {
-            const int rc = apply_dev(ws, W_old + l0, W_new + l0, d + l0, std::min(TC3_MAX, n_layers - l0), st, true, 0);
+            const int nl = std::min(TC3_MAX, n_layers - l0);
+            ws->P_off = stage != 0 ? off : 0;
+            const int rc = apply_dev(ws, W_old + l0, W_new + l0, d + l0, nl, st, true, stage);
+            ws->P_off = 0;
             if (rc) return rc;
             total_launches += ws->launches_apply;
+            off += staged_scratch(ws, d + l0, nl);
         }
         ws->launches_apply = total_launches;
         ws->pev_mid = 0;
@@ -181,17 +217,19 @@ int apply_dev(uce_ws* ws, const float* const* W_old, float* const* W_new, const 
             UCE_CUDA(cudaMallocHost(&ws->h_slots, (size_t)ws->slots_cap * sb));
         }
         if (tiles > ws->slots_cap) { set_error("too many row blocks per call (%d > %d)", tiles, ws->slots_cap); return UCE_E_STATE; }
-        if (ws->slots_pos + tiles > ws->slots_cap) ws->slots_pos = 0;      // ring, for the same reason as the layer table
-        slots_h = (char*)ws->h_slots + (size_t)ws->slots_pos * sb;
-        slots_d = (char*)ws->slots_dev + (size_t)ws->slots_pos * sb;
         if (stage != 2) {
+            if (ws->slots_pos + tiles > ws->slots_cap) ws->slots_pos = 0;      // ring, for the same reason as the layer table
+            slots_h = (char*)ws->h_slots + (size_t)ws->slots_pos * sb;
+            slots_d = (char*)ws->slots_dev + (size_t)ws->slots_pos * sb;
             apply_ab_fill_slots(slots_h, hl, n_layers);
             UCE_CUDA(cudaMemcpyAsync(slots_d, slots_h, (size_t)tiles * sb, cudaMemcpyHostToDevice, st));
-            ws->slots_last = ws->slots_pos;
-        } else {                                                           // stage 2 reuses the table stage 1 uploaded
-            slots_d = (char*)ws->slots_dev + (size_t)ws->slots_last * sb;
+            if (stage == 1) ws->slots_staged.push_back(ws->slots_pos);           // stage 2 of the same slice picks this table up (FIFO)
+            ws->slots_pos += tiles;
+        } else {
+            if (ws->slots_staged.empty()) { set_error("apply stage 2 without a matching stage 1"); return UCE_E_STATE; }
+            slots_d = (char*)ws->slots_dev + (size_t)ws->slots_staged.front() * sb;
+            ws->slots_staged.erase(ws->slots_staged.begin());
         }
-        if (stage != 1) ws->slots_pos += tiles;
     } else if (use_tc3) {
         std::vector<int> trows(n_layers), tbeg(n_layers);
         tiles = apply_tc3_plan(ws->sm_count, d, n_layers, trows.data(), tbeg.data());
@@ -218,7 +256,8 @@ int apply_dev(uce_ws* ws, const float* const* W_old, float* const* W_new, const 
     }
     const size_t need = use_ab ? (size_t)ab_ks * tiles * 128 * r_pad : use_g3 ? (size_t)tiles * 128 * r_pad : use_tc3 ? 0 : (ws->dense ? (inplace ? (size_t)tiles * SG_BM * K : 0) : (size_t)tiles * SG_BM * r_pad);
     // P scratch is shared by successive apply calls; they are ordered on one stream (host path: s_compute)
-    if (need > ws->P_cap) {
+    if (ws->P_off + need > ws->P_cap) {
+        if (ws->P_off != 0 || stage == 2) { set_error("apply scratch too small for a staged / sliced call"); return UCE_E_STATE; }
         if (ws->P) { UCE_CUDA(cudaStreamSynchronize(st)); UCE_CUDA(cudaFree(ws->P)); ws->P = nullptr; }
         ws->P_cap = need + need / 4;
         UCE_CUDA(cudaMalloc(&ws->P, ws->P_cap * sizeof(float)));
@@ -229,7 +268,7 @@ int apply_dev(uce_ws* ws, const float* const* W_old, float* const* W_new, const 
             if (rc) return rc;
             if (prof && stage == 0) ws->pev_mid = 1;
         } else if (use_g3) {
-            int rc = apply_gemm3x_highrank(ws, dl, hl, n_layers, tiles, st, &launches);
+            int rc = apply_gemm3x_highrank(ws, dl, hl, n_layers, tiles, st, &launches, stage);
             if (rc) return rc;
         } else if (use_tc3) {
             int rc = apply_tc3_lowrank(ws, dl, hl, n_layers, tiles, st, &launches, prof ? ws->pev[2] : nullptr);

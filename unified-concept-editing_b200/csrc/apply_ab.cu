@@ -585,7 +585,8 @@ int apply_ab_lowrank(uce_ws* ws, const void* slots_dev, const void* slots_host, 
         if (((uintptr_t)layers_host[l].w_old & 15) || ((uintptr_t)layers_host[l].w_new & 15)) { set_error("tcgen05 apply needs 16-byte aligned weights"); return UCE_E_ARG; }
     (void)slots_host;
     const size_t need = (size_t)ks * n_slots * 128 * R;
-    if (need > ws->P_cap) { set_error("apply scratch too small (%zu > %zu floats)", need, ws->P_cap); return UCE_E_STATE; }
+    if (ws->P_off + need > ws->P_cap) { set_error("apply scratch too small (%zu > %zu floats)", ws->P_off + need, ws->P_cap); return UCE_E_STATE; }
+    float* Pscr = ws->P + ws->P_off;
     static thread_local WIo wmaps;        // kept off the stack, one per host thread; copied into the launches by value
     int rc;
     for (int l = 0; l < n_layers; ++l) {
@@ -605,7 +606,7 @@ int apply_ab_lowrank(uce_ws* ws, const void* slots_dev, const void* slots_host, 
         const int smem = smem_a(R);
         int& cf = conf_a[ws->device & 63];
         if (cf < smem) { UCE_CUDA(cudaFuncSetAttribute(apply_p_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); cf = smem; }
-        apply_p_kernel<<<grid, THREADS_A, smem, st>>>((const Slot*)slots_dev, n_slots, K, R, ks, ws->P, em, *reinterpret_cast<const WIn*>(&wmaps), trace);
+        apply_p_kernel<<<grid, THREADS_A, smem, st>>>((const Slot*)slots_dev, n_slots, K, R, ks, Pscr, em, *reinterpret_cast<const WIn*>(&wmaps), trace);
         UCE_LAUNCH_CHECK();
         *launches += 1;
     }
@@ -617,7 +618,7 @@ int apply_ab_lowrank(uce_ws* ws, const void* slots_dev, const void* slots_host, 
         const int smem = smem_b();
         int& cf = conf_b[ws->device & 63];
         if (cf < smem) { UCE_CUDA(cudaFuncSetAttribute(apply_w_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); cf = smem; }
-        apply_w_kernel<<<grid, THREADS, smem, st>>>((const Slot*)slots_dev, n_slots, K, R, ks, ws->P, qm, wmaps, trace ? trace + TRN / 2 : nullptr);
+        apply_w_kernel<<<grid, THREADS, smem, st>>>((const Slot*)slots_dev, n_slots, K, R, ks, Pscr, qm, wmaps, trace ? trace + TRN / 2 : nullptr);
         UCE_LAUNCH_CHECK();
         *launches += 1;
     }

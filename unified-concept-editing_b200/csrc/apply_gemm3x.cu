@@ -272,8 +272,9 @@ bool apply_gemm3x_available(const uce_ws* ws, int n_layers) {
 }
 
 // P scratch: total_tiles * 128 rows of rank_pad floats (ws->P, sized by the caller); tiles of 128 rows (LayerRef.tile_begin).
+// stage: 0 both passes on `st`; 1 only pass 1 (P = W_old E^T: needs E only — uce_edit_dev_f32 runs it beside the factor); 2 only pass 2
 int apply_gemm3x_highrank(uce_ws* ws, const LayerRef* layers_dev, const LayerRef* layers_host, int n_layers, int total_tiles,
-                          cudaStream_t st, int* launches) {
+                          cudaStream_t st, int* launches, int stage) {
     using namespace g3;
     const int K = ws->K, R = ws->rank_pad;
     if (!apply_gemm3x_available(ws, n_layers)) { set_error("tcgen05 high-rank apply unavailable for K=%d rank_pad=%d dense=%d layers=%d", K, R, ws->dense, n_layers); return UCE_E_STATE; }
@@ -287,14 +288,16 @@ int apply_gemm3x_highrank(uce_ws* ws, const LayerRef* layers_dev, const LayerRef
     }
     static thread_local int configured_dev[64] = {0};      // opt-in shared-memory size is a per-device function attribute
     int& configured = configured_dev[ws->device & 63];
+    float* Pscr = ws->P + ws->P_off;
     for (int pass = 0; pass < 2; ++pass) {
+        if ((stage == 1 && pass == 1) || (stage == 2 && pass == 0)) continue;
         // pass 0: P[M, R] = W_old[M, K] . E[R, K]^T        pass 1: W_new[M, K] = W_old + P[M, R] . Qt[K, R]^T
         const int N = pass ? K : R, Kd = pass ? R : K;
         const int BN = N < BN_MAX ? N : BN_MAX;
         Maps maps;
         if ((rc = make_map(&maps.b_hi, pass ? ws->Qt_hi : ws->E_hi, N, Kd, BN))) return rc;
         if ((rc = make_map(&maps.b_lo, pass ? ws->Qt_lo : ws->E_lo, N, Kd, BN))) return rc;
-        if ((rc = make_map(&maps.p, ws->P, (long)total_tiles * 128, R, 128))) return rc;
+        if ((rc = make_map(&maps.p, Pscr, (long)total_tiles * 128, R, 128))) return rc;
         const int smem = smem_layout(BN).total;
         if (configured < smem) {
             UCE_CUDA(cudaFuncSetAttribute(gemm3x_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));

@@ -196,10 +196,11 @@ static int edit_dev(uce_ws* ws, const float* C, const float* G, const float* sca
     }
     const bool prof = ws->profile && !no_profile;
     // profiling brackets each kernel with events on `stream`: everything stays serial there, so that the durations are per kernel
-    const bool overlap = !prof && getenv("UCE_NO_OVERLAP") == nullptr && n_layers <= 96;
+    const bool overlap = !prof && getenv("UCE_NO_OVERLAP") == nullptr;
     if (overlap) UCE_CUDA(cudaEventRecord(ws->ev_fork, st));      // W_old is ready here (stream order of the caller)
     ws->want_ev_E = overlap ? 1 : 0;
     ws->ev_E_recorded = 0;
+    ws->slots_staged.clear();
     if (prof) UCE_CUDA(cudaEventRecord(ws->pev[0], st));
     int rc = factor_dev(ws, C, G, scales, n_rows, n_edit, lamb, st);
     ws->want_ev_E = 0;

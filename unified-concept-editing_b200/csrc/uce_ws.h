@@ -43,12 +43,14 @@ struct uce_ws {
     int*    flag = nullptr;      // device: 0 ok, else 1 + failing block
     float*  P = nullptr;         // apply scratch [rows_pad_total, rank_pad]
     size_t  P_cap = 0;
+    size_t  P_off = 0;           // floats: the slice of the scratch the current (sliced) apply call uses
     uce::LayerRef* layers_dev = nullptr;
     int layers_cap = 0;
     int ring_pos = 0;
     void* slots_dev = nullptr;   // row-block table of the K-split apply (apply_ab.cu), staged like the layer table
     void* h_slots = nullptr;
-    int slots_cap = 0, slots_pos = 0, slots_last = 0;
+    int slots_cap = 0, slots_pos = 0;
+    std::vector<int> slots_staged;   // tables uploaded by stage-1 calls, waiting for their stage-2 call
     int stage_pending = 0;
     cudaEvent_t ev_stage = nullptr;   // marks consumption of the factor's pinned staging
     // ---- pinned host staging ----

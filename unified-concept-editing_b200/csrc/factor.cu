@@ -146,6 +146,117 @@ static int split_operand(uce_ws* ws, const float* x, float* hi, float* lo, cudaS
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Dual system, general size:  X = H^-1 Cp[:, 8 columns]  per CTA by blocked forward substitution over all rows and backward
+// substitution down to the block row of the first edit row (they are the LAST rows); the edit rows of X are Q[:, those columns]
+// (H^-1 is symmetric: Q = J H^-1 Cp) -> Q, Qt and the tf32 splits.  Same algorithm as solve_emit_kernel of the low-latency path, but L
+// (lower triangle of H after the factorisation, row-major, ld) and the dense inverses of its diagonal blocks (Linv) stay in global
+// memory / L2 and stream through a double-buffered 32 x 32 shared-memory block: the next block is fetched into registers while the
+// current one is used.  Replaces 128 launches of block triangular solves on n_edit unit vectors plus a Q = X^T Cp GEMM (1.9 of the
+// 3.6 ms general factor at BASELINE cfg4) by one launch of K / 8 CTAs.
+constexpr int SG_CW = 8;
+__global__ void __launch_bounds__(256) solve_emit_general_kernel(const double* __restrict__ L, int ld, const double* __restrict__ Linv,
+                                                                 const float* __restrict__ Cp, int n, int n_pad, int n_pres, int n_edit, int r_pad, int K,
+                                                                 float* __restrict__ Q, float* __restrict__ Qt, float* __restrict__ Qt_hi, float* __restrict__ Qt_lo) {
+    extern __shared__ double gsm_d[];
+    constexpr int NBK = UCE_NB, P = NBK + 1, XL = SG_CW + 1;
+    double* XS = gsm_d;                                   // [n_pad][XL]
+    double* BLK = XS + (size_t)n_pad * XL;                // [2][32][33]
+    const int tid = threadIdx.x, c = tid & (SG_CW - 1), r = tid >> 3;      // slab column; row of a 32-row block
+    const int lr = tid >> 3, lc = (tid & 7) * 4;          // block fetch: row, first of four columns
+    const int k0 = blockIdx.x * SG_CW, nblk = n_pad / NBK, kb_e = n_pres / NBK;
+    for (int idx = tid; idx < n_pad * SG_CW; idx += 256) {
+        const int rr = idx / SG_CW, cc = idx % SG_CW;
+        XS[rr * XL + cc] = (rr < n && k0 + cc < K) ? (double)Cp[(long)rr * K + k0 + cc] : 0.0;
+    }
+    // block sequence: phase 0 forward: (kb: inverse of the diagonal block, then L(i, kb) for i > kb); phase 1 backward:
+    // (kb from the last block down to kb_e: inverse of the diagonal block, then L(kb, i) for kb_e <= i < kb)
+    struct It { int phase, kb, i; };
+    auto valid = [&](const It& t) { return t.phase < 2; };
+    auto advance = [&](It t) {
+        if (t.phase == 0) {
+            if (t.i < 0) t.i = t.kb + 1; else ++t.i;
+            if (t.i >= nblk) { ++t.kb; t.i = -1; if (t.kb >= nblk) { t.phase = 1; t.kb = nblk - 1; } }
+        } else {
+            if (t.i < 0) t.i = kb_e; else ++t.i;
+            if (t.i >= t.kb) { --t.kb; t.i = -1; if (t.kb < kb_e) t.phase = 2; }
+        }
+        return t;
+    };
+    auto src_of = [&](const It& t, int& sld) -> const double* {
+        if (t.i < 0) { sld = NBK; return Linv + (size_t)t.kb * NBK * NBK; }
+        sld = ld;
+        return t.phase == 0 ? L + (size_t)t.i * NBK * ld + (size_t)t.kb * NBK : L + (size_t)t.kb * NBK * ld + (size_t)t.i * NBK;
+    };
+    auto fetch = [&](const It& t, double (&v)[4]) {
+        int sld; const double* s = src_of(t, sld);
+        const double2 a = *reinterpret_cast<const double2*>(s + (size_t)lr * sld + lc), b = *reinterpret_cast<const double2*>(s + (size_t)lr * sld + lc + 2);
+        v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+    };
+    It cur{0, 0, -1};
+    double nxt[4];
+    fetch(cur, nxt);
+    int buf = 0;
+    while (valid(cur)) {
+        double* B = BLK + buf * NBK * P;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) B[lr * P + lc + q] = nxt[q];
+        __syncthreads();                                   // block visible; everybody is done with the previous block and its writes to XS
+        const It nx = advance(cur);
+        if (valid(nx)) fetch(nx, nxt);                     // in flight during the work below
+        const int o = cur.kb * NBK;
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        if (cur.i < 0) {
+            // triangular multiply with the dense inverse: forward Y_k = Linv X_k (Linv[r][j]); backward X_k = Linv^T Y_k (Linv[j][r])
+            if (cur.phase == 0) {
+#pragma unroll
+                for (int j = 0; j < NBK; j += 4) {
+                    a0 = fma(B[r * P + j], XS[(o + j) * XL + c], a0);         a1 = fma(B[r * P + j + 1], XS[(o + j + 1) * XL + c], a1);
+                    a2 = fma(B[r * P + j + 2], XS[(o + j + 2) * XL + c], a2); a3 = fma(B[r * P + j + 3], XS[(o + j + 3) * XL + c], a3);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < NBK; j += 4) {
+                    a0 = fma(B[j * P + r], XS[(o + j) * XL + c], a0);           a1 = fma(B[(j + 1) * P + r], XS[(o + j + 1) * XL + c], a1);
+                    a2 = fma(B[(j + 2) * P + r], XS[(o + j + 2) * XL + c], a2); a3 = fma(B[(j + 3) * P + r], XS[(o + j + 3) * XL + c], a3);
+                }
+            }
+            __syncthreads();                               // every thread has read the old X_k
+            XS[(o + r) * XL + c] = (a0 + a1) + (a2 + a3);
+        } else {
+            // update of another block row: forward X_i -= L(i,kb) Y_k (B[r][j]); backward Y_i -= L(kb,i)^T X_k (B[j][r])
+            if (cur.phase == 0) {
+#pragma unroll
+                for (int j = 0; j < NBK; j += 4) {
+                    a0 = fma(B[r * P + j], XS[(o + j) * XL + c], a0);         a1 = fma(B[r * P + j + 1], XS[(o + j + 1) * XL + c], a1);
+                    a2 = fma(B[r * P + j + 2], XS[(o + j + 2) * XL + c], a2); a3 = fma(B[r * P + j + 3], XS[(o + j + 3) * XL + c], a3);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < NBK; j += 4) {
+                    a0 = fma(B[j * P + r], XS[(o + j) * XL + c], a0);           a1 = fma(B[(j + 1) * P + r], XS[(o + j + 1) * XL + c], a1);
+                    a2 = fma(B[(j + 2) * P + r], XS[(o + j + 2) * XL + c], a2); a3 = fma(B[(j + 3) * P + r], XS[(o + j + 3) * XL + c], a3);
+                }
+            }
+            XS[(cur.i * NBK + r) * XL + c] -= (a0 + a1) + (a2 + a3);
+        }
+        cur = nx;
+        buf ^= 1;
+    }
+    __syncthreads();
+    for (int idx = tid; idx < r_pad * SG_CW; idx += 256) {
+        const int cc = idx / r_pad, j = idx % r_pad;
+        if (k0 + cc >= K) continue;
+        const float v = (j < n_edit) ? (float)XS[(n_pres + j) * XL + cc] : 0.f;
+        const long t = (long)(k0 + cc) * r_pad + j;
+        uint32_t u;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
+        const float h = __uint_as_float(u);
+        Qt[t] = v; Qt_hi[t] = h; Qt_lo[t] = v - h;
+        Q[(long)j * K + k0 + cc] = v;
+    }
+}
+
 #define UCE_RT(expr)                                                                             \
     do {                                                                                         \
         cudaError_t _e = (expr);                                                                 \
@@ -158,7 +269,8 @@ static int split_operand(uce_ws* ws, const float* x, float* hi, float* lo, cudaS
 
 // Blocked Cholesky of the sys_n x sys_n matrix in ws->H (lower), then solve H X = rhs in place.
 // fwd_from: first block row whose rhs is non-zero (dual: rhs = unit vectors of the edit rows).
-static int cholesky_solve(uce_ws* ws, int n_pad, int n_rhs, int ldx, int fwd_from, cudaStream_t st, int& launches) {
+// factor_only: stop after the factorisation (the dual path solves with solve_emit_general_kernel instead).
+static int cholesky_solve(uce_ws* ws, int n_pad, int n_rhs, int ldx, int fwd_from, cudaStream_t st, int& launches, bool factor_only = false) {
     const int nb = UCE_NB, nblk = n_pad / nb, ld = n_pad;
     double* H = ws->H; double* X = ws->X; double* Linv = ws->Linv;
     for (int k = 0; k < nblk; ++k) {
@@ -176,6 +288,7 @@ static int cholesky_solve(uce_ws* ws, int n_pad, int n_rhs, int ldx, int fwd_fro
                                                               trail, ld, 1.0, /*lower_only=*/1)));
         }
     }
+    if (factor_only) return 0;
     // forward: L Y = rhs
     for (int k = fwd_from; k < nblk; ++k) {
         double* xk = X + (long)k * nb * ldx;
@@ -284,24 +397,39 @@ int factor_dev(uce_ws* ws, const float* C, const float* G, const float* scales, 
         if (!ws->Hcopy) UCE_CUDA(cudaMalloc(&ws->Hcopy, (size_t)ws->sys_max * ws->sys_max * sizeof(double)));
         UCE_CUDA(cudaMemcpyAsync(ws->Hcopy, ws->H, (size_t)n_pad * n_pad * sizeof(double), cudaMemcpyDeviceToDevice, st));
     }
-    fill_rhs_kernel<<<dim3(ceil_div(n_edit, 128), n_pad), 128, 0, st>>>(ws->X, ldx, n_pad, n_edit, n_pres, dual ? nullptr : ws->Cs64, K);
-    UCE_RT(cudaGetLastError());
-
-    int rc = cholesky_solve(ws, n_pad, n_edit, ldx, dual ? n_pres / UCE_NB : 0, st, launches);
-    if (rc) return rc;
-
-    if (dual) {
-        // Q[j,k] = sum_r X[r,j] Cp[r,k]
-        UCE_RT((simt_gemm<double, float, double, float>(st, n_edit, K, n, ws->X, 1, ldx, ws->Cp, 1, K, ws->Q, K)));
+    const size_t smem_sg = ((size_t)n_pad * (SG_CW + 1) + 2 * UCE_NB * (UCE_NB + 1)) * sizeof(double);
+    const bool fused_solve = dual && smem_sg <= 200 * 1024 && getenv("UCE_GENERAL_SOLVE_GEMMS") == nullptr;
+    bool qt_split_done = false;
+    if (fused_solve) {
+        int rc = cholesky_solve(ws, n_pad, n_edit, ldx, 0, st, launches, /*factor_only=*/true);
+        if (rc) return rc;
+        static thread_local size_t conf_sg[64] = {0};
+        if (conf_sg[ws->device & 63] < smem_sg) {
+            UCE_CUDA(cudaFuncSetAttribute(solve_emit_general_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sg));
+            conf_sg[ws->device & 63] = smem_sg;
+        }
+        solve_emit_general_kernel<<<ceil_div(K, SG_CW), 256, smem_sg, st>>>(ws->H, n_pad, ws->Linv, ws->Cp, n, n_pad, n_pres, n_edit, ws->rank_pad, K,
+                                                                            ws->Q, ws->Qt, ws->Qt_hi, ws->Qt_lo);
+        UCE_RT(cudaGetLastError());
+        qt_split_done = true;
+    } else {
+        fill_rhs_kernel<<<dim3(ceil_div(n_edit, 128), n_pad), 128, 0, st>>>(ws->X, ldx, n_pad, n_edit, n_pres, dual ? nullptr : ws->Cs64, K);
+        UCE_RT(cudaGetLastError());
+        int rc = cholesky_solve(ws, n_pad, n_edit, ldx, dual ? n_pres / UCE_NB : 0, st, launches);
+        if (rc) return rc;
+        if (dual) {
+            // Q[j,k] = sum_r X[r,j] Cp[r,k]
+            UCE_RT((simt_gemm<double, float, double, float>(st, n_edit, K, n, ws->X, 1, ldx, ws->Cp, 1, K, ws->Q, K)));
+        }
+        emit_q_kernel<<<dim3(ceil_div(K, 128), ws->rank_pad), 128, 0, st>>>(ws->X, ldx, dual ? 0 : 1, n_edit, ws->rank_pad, K, ws->Q, ws->Qt);
+        UCE_RT(cudaGetLastError());
     }
-    emit_q_kernel<<<dim3(ceil_div(K, 128), ws->rank_pad), 128, 0, st>>>(ws->X, ldx, dual ? 0 : 1, n_edit, ws->rank_pad, K, ws->Q, ws->Qt);
-    UCE_RT(cudaGetLastError());
     if (ws->dense) {
         // Dt[a,b] = D[b,a] = sum_j E[j,b] Q[j,a]
         UCE_RT((simt_gemm<float, float, double, float>(st, K, K, n_edit, ws->Q, 1, K, ws->E, 1, K, ws->Dt, K)));
     }
     ws->mode = dual ? 1 : 2;
-    if (!ws->dense && ws->rank > 0) {      // tf32 hi/lo split of Qt: always, so the apply implementation may be chosen after the factor
+    if (!ws->dense && ws->rank > 0 && !qt_split_done) {      // tf32 hi/lo split of Qt: always, so the apply implementation may be chosen after the factor
         int rc2 = split_operand(ws, ws->Qt, ws->Qt_hi, ws->Qt_lo, st, &launches);
         if (rc2) return rc2;
     }

@@ -236,6 +236,29 @@ def test_clip_text_c_abi_exports_every_declared_symbol():
     assert declared == set(clip_text.SIGNATURES), declared ^ set(clip_text.SIGNATURES)
 
 
+def test_clip_vision_c_abi_exports_every_declared_symbol():
+    from uce_b200 import _native, clip_zero_shot
+    hdr = open(os.path.join(ROOT, "include", "clip_vision_b200.h")).read()
+    declared = set(re.findall(r"\b(clipv_[a-z0-9_]+)\s*\(", hdr))
+    lib = ctypes.CDLL(_native.LIB_PATH)
+    for sym in declared:
+        assert hasattr(lib, sym), sym
+    assert declared == set(clip_zero_shot.SIGNATURES), declared ^ set(clip_zero_shot.SIGNATURES)
+
+
+def test_clip_engines_refuse_to_run_without_cuda():
+    """No CPU fallback: on a box without a GPU the engines raise instead of computing somewhere else."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    from uce_b200.clip_text import ClipTextEngine
+    from uce_b200.clip_zero_shot import ClipVisionEngine
+    with pytest.raises(RuntimeError):
+        ClipTextEngine({}, 4)
+    with pytest.raises(RuntimeError):
+        ClipVisionEngine({}, 4)
+
+
 def test_public_headers_are_plain_c(tmp_path):
     """The drop-in boundary is a C ABI: both headers must compile as C11 on their own (no torch / CUDA types in the signatures)."""
     import shutil
@@ -244,7 +267,7 @@ def test_public_headers_are_plain_c(tmp_path):
     if gcc is None:
         pytest.skip("gcc not available")
     src = tmp_path / "hdr.c"
-    src.write_text(f'#include "{ROOT}/include/uce_b200.h"\n#include "{ROOT}/include/sd_unet_b200.h"\n#include "{ROOT}/include/sd_vae_b200.h"\n#include "{ROOT}/include/clip_text_b200.h"\nint main(void) {{ return 0; }}\n')
+    src.write_text(f'#include "{ROOT}/include/uce_b200.h"\n#include "{ROOT}/include/sd_unet_b200.h"\n#include "{ROOT}/include/sd_vae_b200.h"\n#include "{ROOT}/include/clip_text_b200.h"\n#include "{ROOT}/include/clip_vision_b200.h"\nint main(void) {{ return 0; }}\n')
     r = subprocess.run([gcc, "-std=c11", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", str(src)], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
 

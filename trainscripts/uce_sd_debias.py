@@ -35,6 +35,10 @@ def build_parser():
     # not in the reference: which denoise loop the generation rounds of get_ratios() use
     p.add_argument("--generator", type=str, default="pipe", choices=["pipe", "engine"],
                    help="'pipe': the diffusers pipeline, as the reference does; 'engine': the B200 U-Net engine (default: pipe)")
+    # not in the reference: which classifier scores the generated images
+    p.add_argument("--classifier", type=str, default="engine", choices=["engine", "pipeline"],
+                   help="'engine': the B200 CLIP kernels on the pipeline's weights (fp32); 'pipeline': the transformers pipeline itself, "
+                        "as the reference does (default: engine)")
     return p
 
 
@@ -61,6 +65,9 @@ def main(argv=None):
     pipe = DiffusionPipeline.from_pretrained(args.model_id, torch_dtype=torch.float32, safety_checker=None).to(args.device)
     pipe.set_progress_bar_config(disable=True)
     clip = pipeline(task="zero-shot-image-classification", model="openai/clip-vit-base-patch32", torch_dtype=torch.bfloat16, device=0)
+    if args.classifier == "engine":
+        from uce_b200.clip_zero_shot import ClipZeroShotEngine
+        clip = ClipZeroShotEngine.from_pipeline(clip, device=args.device)
     from uce_b200.debias import UCE
     UCE(pipe, clip, edit, debias, preserve, args.edit_scale, args.preserve_scale, args.lamb, args.save_dir, exp_name,
         args.max_diff, args.step_size, args.num_images_per_prompt, args.num_inference_steps, args.guidance_scale,

@@ -15,7 +15,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libuce_b200.so")
 SOURCES = ["uce_api.cu", "artifact.cu", "png.cu", "factor.cu", "factor_small.cu", "apply.cu", "apply_tc3.cu", "apply_ab.cu", "apply_gemm3x.cu",
-           "unet_gemm.cu", "unet_ops.cu", "unet_attn.cu", "unet_engine.cu", "vae_engine.cu", "clip_text.cu"]
+           "unet_gemm.cu", "unet_ops.cu", "unet_attn.cu", "unet_engine.cu", "vae_engine.cu", "clip_text.cu", "clip_vision.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 CFLAGS = ARCH + ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC"]
 LDFLAGS = ARCH + ["-shared", "-Xcompiler", "-fPIC", "-lcuda", "-lz"]

@@ -89,10 +89,10 @@ class ClipTextEngine:
                 _check(_lib().clipt_encode(self._h, C.c_void_p(chunk.data_ptr()), n, T, C.c_void_p(out[b0:b0 + n].data_ptr()), self._stream()))
         return out
 
-    def concept_rows(self, input_ids: torch.Tensor, attention_mask: torch.Tensor) -> torch.Tensor:
-        """[B, width]: row ``attention_mask.sum() - 2`` of every prompt (trainscripts/uce_sd_erase.py:34-42)."""
+    def rows_at(self, input_ids: torch.Tensor, row_index: torch.Tensor) -> torch.Tensor:
+        """[B, width]: ``last_hidden_state[b, row_index[b], :]`` of every prompt."""
         ids = input_ids.detach().to("cpu", torch.int32).contiguous()
-        idx = (attention_mask.detach().to("cpu").sum(dim=1) - 2).to(torch.int32).contiguous()
+        idx = row_index.detach().to("cpu", torch.int32).contiguous()
         B, T = ids.shape
         out = torch.empty((B, self.width), dtype=torch.float32, device=self.device)
         for b0 in range(0, B, self.max_batch):
@@ -102,6 +102,10 @@ class ClipTextEngine:
                 _check(_lib().clipt_concept_rows(self._h, C.c_void_p(chunk.data_ptr()), C.c_void_p(ichunk.data_ptr()), n, T,
                                                  C.c_void_p(out[b0:b0 + n].data_ptr()), self._stream()))
         return out
+
+    def concept_rows(self, input_ids: torch.Tensor, attention_mask: torch.Tensor) -> torch.Tensor:
+        """[B, width]: row ``attention_mask.sum() - 2`` of every prompt (trainscripts/uce_sd_erase.py:34-42)."""
+        return self.rows_at(input_ids, attention_mask.detach().to("cpu").sum(dim=1) - 2)
 
     def launch_count(self) -> int:
         return _lib().clipt_launch_count(self._h)

@@ -45,8 +45,10 @@ def get_ratios(pipe, clip, uce_module_names, uce_modules=None, edit_concepts=(),
     for i, concept in enumerate(edit_concepts):
         if i % world != rank:
             continue
-        images = pipe(concept, num_inference_steps=num_inference_steps, num_images_per_prompt=num_images_per_prompt,
-                      guidance_scale=guidance_scale).images
+        out = pipe(concept, num_inference_steps=num_inference_steps, num_images_per_prompt=num_images_per_prompt, guidance_scale=guidance_scale)
+        images = out.images
+        if getattr(clip, "accepts_device_images", False) and getattr(out, "images_u8", None) is not None:
+            images = out.images_u8                 # VAE engine -> classifier engine: the pixels never leave the device
         results = clip(images, candidate_labels=debias_concepts)
         top1 = np.array([r[0]["label"] for r in results])
         counts[i] = [np.sum(top1 == c) for c in debias_concepts]

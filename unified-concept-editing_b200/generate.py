@@ -70,8 +70,12 @@ class _EngineWeights:
 
 
 class _Images:
-    def __init__(self, images):
+    """``.images`` as the pipeline returns them; ``.images_u8`` — when the VAE engine decoded — the same pixels as one uint8
+    [B, H, W, 3] tensor still on the device, for a classifier that takes them without a host round trip."""
+
+    def __init__(self, images, images_u8=None):
         self.images = images
+        self.images_u8 = images_u8
 
 
 class EngineGenerator:
@@ -111,14 +115,16 @@ class EngineGenerator:
         ctx = torch.cat([uncond, text]).to(torch.float32)
         lat = torch.randn((n, 4, self.latent, self.latent), generator=generator, dtype=self.dtype)     # CPU RNG, pipeline dtype
         out = self.den.run(lat, ctx, steps=num_inference_steps, guidance_scale=guidance_scale, scheduler=self.scheduler)
+        u8 = None
         if self.vae_eng is not None:
-            images = list(self.vae_eng.decode(out.contiguous()).cpu().numpy())
+            u8 = self.vae_eng.decode(out.contiguous())
+            images = list(u8.cpu().numpy())
         elif hasattr(self.pipe, "decode_latents_to_pil"):
             images = self.pipe.decode_latents_to_pil(out)
         else:
             images = _decode(self.pipe, out, self.dtype)
         self.calls += 1
-        return _Images(images)
+        return _Images(images, u8)
 
     def close(self):
         if self._own:

@@ -322,7 +322,7 @@ def test_two_block_tcgen05_apply(n_edit, K, dims, block_rows, monkeypatch):
     s = _solver(K, C.shape[0])
     simt = _run(s, C, G, scales, n_edit, 0.5, W, impl=1)
     tc = _run(s, C, G, scales, n_edit, 0.5, W, impl=4)
-    assert s.info()["launches_apply"] == -(-len(dims) // 96)          # 96 projections per launch
+    assert s.info()["launches_apply"] == 2 * -(-len(dims) // 96)      # per 96 projections: the layer table (written by a kernel) + one apply launch
     exact = O.erase_exact_f64(W[:4], C[:n_edit], G, C[n_edit:], 1.0, 1.0, 0.5)
     for i, (a, b, e) in enumerate(zip(simt, tc, exact)):
         assert O.rel_fro(b, e) <= TOL_EXACT, ("tc3 vs exact", O.rel_fro(b, e), O.rel_fro(a, e))
@@ -357,7 +357,7 @@ def test_ksplit_tcgen05_apply(n_edit, K, dims, block_rows, monkeypatch):
     s = _solver(K, C.shape[0])
     simt = _run(s, C, G, scales, n_edit, 0.5, W, impl=1)
     tc = _run(s, C, G, scales, n_edit, 0.5, W, impl=7)
-    assert s.info()["launches_apply"] == 2 * -(-len(dims) // 96)          # two kernels per 96 projections
+    assert s.info()["launches_apply"] == 3 * -(-len(dims) // 96)          # per 96 projections: the row-block table + two kernels
     auto = _run(s, C, G, scales, n_edit, 0.5, W, impl=0)
     for a, b in zip(tc, auto):
         assert torch.equal(a, b)                                          # the default dispatch takes this path
@@ -395,11 +395,12 @@ def test_two_gemm_tcgen05_apply(n_edit, K, dims):
     if s.info()["dense"]:
         pytest.skip("dense factor: the two-GEMM low-rank form does not apply")
     tc = _run(s, C, G, scales, n_edit, 0.5, W, impl=5)
-    assert s.info()["launches_apply"] == 2 * -(-len(dims) // 96)
+    slices = -(-len(dims) // 96)
+    assert s.info()["launches_apply"] in (3 * slices, 4 * slices)     # per 96 projections: two GEMM passes + the layer table (once per stage when pass 1 runs beside the factor)
     s_rank_pad = -(-n_edit // 32) * 32
     if n_edit > 64:
         auto = _run(s, C, G, scales, n_edit, 0.5, W, impl=0)          # the default dispatch takes this kernel
-        assert s.info()["launches_apply"] == 2 * -(-len(dims) // 96)
+        assert s.info()["launches_apply"] in (3 * slices, 4 * slices)
         for a, b in zip(tc, auto):
             assert torch.equal(a, b)
     exact = O.erase_exact_f64(W[:3], C[:n_edit], G, C[n_edit:], 1.0, 1.0, 0.5)

@@ -10,6 +10,7 @@
 #include "uce_ws.h"
 #include "gemm_simt.cuh"
 #include <algorithm>
+#include <cstring>
 #include <vector>
 
 namespace uce {
@@ -28,6 +29,27 @@ bool apply_tc3_available(const uce_ws* ws, int n_layers);   // apply_tc3.cu
 int apply_tc3_plan(int sm_count, const int* d, int n_layers, int* tile_rows, int* tile_begin);
 int apply_tc3_lowrank(uce_ws* ws, const LayerRef* layers_dev, const LayerRef* layers_host, int n_layers, int total_tiles,
                       cudaStream_t st, int* launches, cudaEvent_t ev_begin);
+
+// Small host tables (row-block slots, layer references) reach the device as KERNEL PARAMETERS, not through a copy engine: inside the
+// host-buffer call the host-to-device engine is busy with multi-megabyte weight uploads and serves copies one at a time, so a 1 KB table
+// copy waited for a whole upload group and delayed every apply — and with it every download — by one group (measured: 2.9 ms per call at
+// 4 groups where the copies alone overlap in 1.9).  Parameters are baked into a captured graph, so a replay rewrites the same table.
+struct TableChunk { unsigned int w[4096]; };                  // 16 KB per launch (kernel parameters may hold 32 KB; the K-split kernels pass 24 KB of tensor maps)
+__global__ void __launch_bounds__(256) table_write_kernel(unsigned int* dst, const __grid_constant__ TableChunk c, int n_words) {
+    for (int i = threadIdx.x; i < n_words; i += blockDim.x) dst[i] = c.w[i];
+}
+int table_upload(void* dst, const void* src_host, size_t bytes, cudaStream_t st, int* launches) {
+    const size_t words = (bytes + 3) / 4;
+    for (size_t w0 = 0; w0 < words; w0 += 4096) {
+        TableChunk c;
+        const size_t n = std::min<size_t>(4096, words - w0);
+        memcpy(c.w, (const unsigned int*)src_host + w0, std::min(n * 4, bytes - w0 * 4));
+        table_write_kernel<<<1, 256, 0, st>>>((unsigned int*)dst + w0, c, (int)n);
+        UCE_LAUNCH_CHECK();
+        if (launches) ++*launches;
+    }
+    return 0;
+}
 
 __device__ __forceinline__ int find_layer(const LayerRef* layers, int n_layers, int tile) {
     int lo = 0, hi = n_layers - 1;
@@ -206,6 +228,7 @@ int apply_dev(uce_ws* ws, const float* const* W_old, float* const* W_new, const 
     }
     const int ab_ks = use_ab ? apply_ab_ksplit(K) : 1;
     void* slots_h = nullptr; void* slots_d = nullptr;
+    int table_launches = 0;
     if (use_ab) {
         std::vector<int> trows(n_layers), tbeg(n_layers);
         tiles = apply_ab_plan(ws->sm_count, ab_ks, d, n_layers, trows.data(), tbeg.data());      // tiles = row blocks
@@ -222,7 +245,7 @@ int apply_dev(uce_ws* ws, const float* const* W_old, float* const* W_new, const 
             slots_h = (char*)ws->h_slots + (size_t)ws->slots_pos * sb;
             slots_d = (char*)ws->slots_dev + (size_t)ws->slots_pos * sb;
             apply_ab_fill_slots(slots_h, hl, n_layers);
-            UCE_CUDA(cudaMemcpyAsync(slots_d, slots_h, (size_t)tiles * sb, cudaMemcpyHostToDevice, st));
+            { int rc = table_upload(slots_d, slots_h, (size_t)tiles * sb, st, &table_launches); if (rc) return rc; }
             if (stage == 1) ws->slots_staged.push_back(ws->slots_pos);           // stage 2 of the same slice picks this table up (FIFO)
             ws->slots_pos += tiles;
         } else {
@@ -241,8 +264,8 @@ int apply_dev(uce_ws* ws, const float* const* W_old, float* const* W_new, const 
         }
     }
     LayerRef* dl = ws->layers_dev + slot_begin;
-    UCE_CUDA(cudaMemcpyAsync(dl, hl, n_layers * sizeof(LayerRef), cudaMemcpyHostToDevice, st));
-    int launches = 0;
+    int launches = table_launches;
+    if (!use_ab) { int rc = table_upload(dl, hl, n_layers * sizeof(LayerRef), st, &launches); if (rc) return rc; }    // the K-split kernels read slots + tensor maps only
     const int r_pad = ws->rank_pad;
     const bool prof = ws->profile && !no_profile;
     ws->pev_mid = 0;

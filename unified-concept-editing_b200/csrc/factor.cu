@@ -28,6 +28,13 @@ namespace uce {
 // pack: Cp[r,:] = C[src[r],:]   (all active rows, internal order)
 //       E[j,:]  = G[e_j,:] - C[e_j,:] for the active edit rows (internal rows n_pres + j); pad rows 0
 //       Cs64[r,:] = s_r * Cp[r,:]  (primal only)
+struct alignas(16) FactorTables { unsigned int w[4096]; };     // n row indices (int), padded to 8 bytes, then n diagonal terms (double)
+__global__ void __launch_bounds__(256) factor_tables_kernel(const __grid_constant__ FactorTables t, int n, int* src_idx, double* diag_add, int* flag) {
+    const double* dsrc = reinterpret_cast<const double*>(t.w + n + (n & 1));
+    for (int i = threadIdx.x; i < n; i += blockDim.x) { src_idx[i] = (int)t.w[i]; diag_add[i] = dsrc[i]; }
+    if (threadIdx.x == 0) *flag = 0;
+}
+
 __global__ void pack_rows_kernel(const float* __restrict__ C, const float* __restrict__ G,
                                  const int* __restrict__ src, const double* __restrict__ dadd, int n_act,
                                  int n_pres, int rank_pad, int K, float* __restrict__ Cp, float* __restrict__ E,
@@ -349,9 +356,20 @@ int factor_dev(uce_ws* ws, const float* C, const float* G, const float* scales, 
     }
     if (!dual && !ws->Cs64) UCE_CUDA(cudaMalloc(&ws->Cs64, (size_t)ws->max_rows * K * sizeof(double)));
     if (ws->dense && !ws->Dt) UCE_CUDA(cudaMalloc(&ws->Dt, (size_t)K * K * sizeof(float)));
-    UCE_CUDA(cudaMemcpyAsync(ws->src_idx, ws->h_src_idx, n * sizeof(int), cudaMemcpyHostToDevice, st));
-    UCE_CUDA(cudaMemcpyAsync(ws->diag_add, ws->h_diag_add, n * sizeof(double), cudaMemcpyHostToDevice, st));
-    UCE_CUDA(cudaMemsetAsync(ws->flag, 0, sizeof(int), st));
+    // row order, diagonal terms and the cleared status flag go to the device as kernel parameters: a copy-engine transfer on this stream
+    // would queue behind the weight uploads of the host-buffer call (uce_api.cu) and hold the whole factor back until they end
+    if ((size_t)n * 12 + 4 <= sizeof(FactorTables)) {
+        FactorTables t;
+        memcpy(t.w, ws->h_src_idx, (size_t)n * 4);
+        memcpy(t.w + n + (n & 1), ws->h_diag_add, (size_t)n * 8);
+        factor_tables_kernel<<<1, 256, 0, st>>>(t, n, ws->src_idx, ws->diag_add, ws->flag);
+        UCE_LAUNCH_CHECK(); ++launches;
+    } else {
+        int rc = table_upload(ws->src_idx, ws->h_src_idx, (size_t)n * sizeof(int), st, &launches);
+        if (!rc) rc = table_upload(ws->diag_add, ws->h_diag_add, (size_t)n * sizeof(double), st, &launches);
+        if (rc) return rc;
+        UCE_CUDA(cudaMemsetAsync(ws->flag, 0, sizeof(int), st));
+    }
     if (cap == cudaStreamCaptureStatusNone) { UCE_CUDA(cudaEventRecord(ws->ev_stage, st)); ws->stage_pending = 1; }
 
     if (factor_small_applicable(ws, n, n_edit, dual)) {

@@ -1,6 +1,7 @@
 // C ABI of libuce_b200 (include/uce_b200.h).
 #include "../../include/uce_b200.h"
 #include "uce_ws.h"
+#include <chrono>
 #include <cstdarg>
 #include <cstring>
 #include <cstdlib>
@@ -328,21 +329,67 @@ int uce_edit_host_f32(uce_ws* ws, const float* C, const float* G, const float* s
     std::vector<const float*> po(n_layers); std::vector<float*> pn(n_layers);
     { size_t off = 0; for (int l = 0; l < n_layers; ++l) { po[l] = ws->hostpath_W + off; pn[l] = ws->hostpath_W + off; off += (size_t)d[l] * K; } }
     int launches = 0;
-    // every upload is enqueued first: the H2D stream never waits for the host to finish encoding a group's launch
-    for (int g = 0; g < ng; ++g) {
-        for (int l = gbeg[g]; l < gbeg[g + 1]; ++l)
-            UCE_CUDA(cudaMemcpyAsync(pn[l], W_old[l], (size_t)d[l] * K * sizeof(float), cudaMemcpyHostToDevice, ws->s_h2d));
+    // (layers whose host buffers follow each other in memory — a caller that keeps its weights in one pinned arena — travel as ONE copy per
+    //  group: 32 per-projection copies in each direction cost the link 2.04 ms where two flat copies take 1.57, profiles/r01_e2e_floor.txt)
+    auto run_end = [&](const float* const* host, int l, int end) {
+        int e = l + 1;
+        while (e < end && host[e] == host[e - 1] + (size_t)d[e - 1] * K) ++e;
+        return e;
+    };
+    auto run_bytes = [&](int l, int e) { size_t b = 0; for (int i = l; i < e; ++i) b += (size_t)d[i] * K * sizeof(float); return b; };
+    auto upload = [&](int g) -> int {
+        for (int l = gbeg[g]; l < gbeg[g + 1];) {
+            const int e = run_end(W_old, l, gbeg[g + 1]);
+            UCE_CUDA(cudaMemcpyAsync(pn[l], W_old[l], run_bytes(l, e), cudaMemcpyHostToDevice, ws->s_h2d));
+            l = e;
+        }
         UCE_CUDA(cudaEventRecord(ws->ev_h2d[g], ws->s_h2d));
-    }
+        return 0;
+    };
+    // Order of submission matters: the apply of group g uploads its (tiny) block tables with an async copy of its own, and the copy engine
+    // serves host-to-device copies in submission order — tables submitted after ALL weight uploads would wait for all of them, and the
+    // downloads could not start before the last upload ended (observed: 2.9-3.2 ms instead of 2.1).  So a group's tables are submitted
+    // right after that group's weights, one group ahead of the next upload.
+    static const bool hoist = [] { const char* e = getenv("UCE_HOST_HOIST_UPLOADS"); return e && atoi(e) != 0; }();
+    // UCE_HOST_TRACE=1: device timeline of one call (timing events around every upload, apply and download), printed to stderr
+    static const bool trace = [] { const char* e = getenv("UCE_HOST_TRACE"); return e && atoi(e) != 0; }();
+    std::vector<cudaEvent_t> tev;
+    auto stamp = [&](cudaStream_t s) { if (!trace) return; cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, s); tev.push_back(e); };
+    if (hoist) for (int g = 0; g < ng; ++g) { rc = upload(g); if (rc) return rc; }
+    std::vector<double> host_t;
+    auto host_now = [&] { if (trace) host_t.push_back(std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count()); };
     for (int g = 0; g < ng; ++g) {
+        host_now();
+        stamp(ws->s_h2d);
+        if (!hoist) { rc = upload(g); if (rc) return rc; }
+        stamp(ws->s_h2d);
         UCE_CUDA(cudaStreamWaitEvent(ws->s_compute, ws->ev_h2d[g], 0));
+        stamp(ws->s_compute);
+        host_now();
         rc = apply_dev(ws, po.data() + gbeg[g], pn.data() + gbeg[g], d + gbeg[g], gbeg[g + 1] - gbeg[g], ws->s_compute, true);
         if (rc) { cudaDeviceSynchronize(); return rc; }
+        host_now();
+        stamp(ws->s_compute);
         launches += ws->launches_apply;
         UCE_CUDA(cudaEventRecord(ws->ev_done[g], ws->s_compute));
         UCE_CUDA(cudaStreamWaitEvent(ws->s_d2h, ws->ev_done[g], 0));
-        for (int l = gbeg[g]; l < gbeg[g + 1]; ++l)
-            UCE_CUDA(cudaMemcpyAsync(W_new[l], pn[l], (size_t)d[l] * K * sizeof(float), cudaMemcpyDeviceToHost, ws->s_d2h));
+        stamp(ws->s_d2h);
+        for (int l = gbeg[g]; l < gbeg[g + 1];) {
+            const int e = run_end(W_new, l, gbeg[g + 1]);
+            UCE_CUDA(cudaMemcpyAsync(W_new[l], pn[l], run_bytes(l, e), cudaMemcpyDeviceToHost, ws->s_d2h));
+            l = e;
+        }
+        stamp(ws->s_d2h);
+    }
+    if (trace) {
+        cudaDeviceSynchronize();
+        for (int g = 0; g < ng; ++g) {
+            float t[6];
+            for (int i = 0; i < 6; ++i) cudaEventElapsedTime(&t[i], tev[0], tev[6 * g + i]);
+            fprintf(stderr, "host-path group %2d: upload %7.3f-%7.3f  apply %7.3f-%7.3f  download %7.3f-%7.3f ms | host: iteration starts at %7.1f us, apply_dev encodes %6.1f-%6.1f us\n",
+                    g, t[0], t[1], t[2], t[3], t[4], t[5], host_t[3 * g] - host_t[0], host_t[3 * g + 1] - host_t[0], host_t[3 * g + 2] - host_t[0]);
+        }
+        for (cudaEvent_t e : tev) cudaEventDestroy(e);
     }
     ws->launches_apply = launches;
     UCE_CUDA(cudaStreamSynchronize(ws->s_d2h));

@@ -76,6 +76,8 @@ int factor_dev(uce_ws* ws, const float* C, const float* G, const float* scales_h
 // stage 0: the whole apply on `st`.  K-split apply only (apply_stage_split): stage 1 = partial products (needs E), stage 2 = update (needs Q)
 int apply_dev(uce_ws* ws, const float* const* W_old, float* const* W_new, const int* d, int n_layers,
               cudaStream_t st, bool no_profile = false, int stage = 0);
+// Small host table -> device memory through kernel parameters (no copy engine; see apply.cu).  `bytes` a multiple of 4.
+int table_upload(void* dst, const void* src_host, size_t bytes, cudaStream_t st, int* launches);
 bool apply_stage_split(const uce_ws* ws, int n_layers);   // true when apply_dev would take the two-kernel K-split path for this edit
 // factor_small.cu
 bool factor_small_applicable(const uce_ws* ws, int n, int n_edit, bool dual);

@@ -148,16 +148,38 @@ class EditSolver:
         return out
 
     # ------------------------------------------------------------------ host-buffer path
+    @staticmethod
+    def host_arena(dims: Sequence[int], K: int, pin: bool = True):
+        """One (pinned) host buffer holding every projection back to back, and its per-projection views ``[d_l, K]``.  A caller that keeps
+        W_old / W_new in such arenas lets ``edit_host`` move each pipeline group as ONE copy per direction instead of one per
+        projection (the 32 + 32 small copies of SD-1.4 cost the PCIe link ~0.5 ms more than flat ones, profiles/r01_e2e_floor.txt)."""
+        total = sum(int(d) * int(K) for d in dims)
+        buf = torch.empty(total, dtype=torch.float32)
+        if pin:
+            buf = buf.pin_memory()
+        views, off = [], 0
+        for d in dims:
+            n = int(d) * int(K)
+            views.append(buf[off:off + n].view(int(d), int(K)))
+            off += n
+        return buf, views
+
     def edit_host(self, C_rows, G_rows, scales, n_edit, lamb, W_old: Sequence[torch.Tensor], W_new: Sequence[torch.Tensor]):
         """Whole edit on HOST tensors (uce_edit_host_f32): copies are inside the call."""
         self._check_rows(C_rows, G_rows, scales, n_edit)
-        for t in list(W_old) + list(W_new) + [C_rows] + ([G_rows] if n_edit else []):
+        key = (tuple(w.data_ptr() for w in W_old), tuple(w.data_ptr() for w in W_new), tuple(int(w.shape[0]) for w in W_old))
+        cached = getattr(self, "_host_args", None)
+        if cached is None or cached[0] != key:                      # pointer tables are rebuilt only when the caller's buffers change
+            for t in list(W_old) + list(W_new):
+                if t.device.type != "cpu" or t.dtype != torch.float32 or not t.is_contiguous():
+                    raise ValueError("edit_host takes contiguous fp32 CPU tensors")
+            L = len(W_old)
+            cached = (key, (C.c_void_p * L)(*key[0]), (C.c_void_p * L)(*key[1]), (C.c_int * L)(*key[2]), L)
+            self._host_args = cached
+        for t in [C_rows] + ([G_rows] if n_edit else []):
             if t.device.type != "cpu" or t.dtype != torch.float32 or not t.is_contiguous():
                 raise ValueError("edit_host takes contiguous fp32 CPU tensors")
-        L = len(W_old)
-        po = (C.c_void_p * L)(*[_ptr(w) for w in W_old])
-        pn = (C.c_void_p * L)(*[_ptr(w) for w in W_new])
-        dd = (C.c_int * L)(*[int(w.shape[0]) for w in W_old])
+        _, po, pn, dd, L = cached
         sc = (C.c_float * len(scales))(*[float(s) for s in scales])
         N.check(N.lib().uce_edit_host_f32(self._h, C.c_void_p(_ptr(C_rows)), C.c_void_p(_ptr(G_rows)) if n_edit else None, sc,
                                           C_rows.shape[0], int(n_edit), float(lamb), po, pn, dd, L))

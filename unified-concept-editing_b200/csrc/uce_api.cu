@@ -308,9 +308,27 @@ int uce_edit_host_f32(uce_ws* ws, const float* C, const float* G, const float* s
     // and the last download run alone on the link — at the price of more, smaller apply launches)
     int target_groups = std::min(n_layers, 8);
     if (const char* e = getenv("UCE_HOST_GROUPS")) { const int t = atoi(e); if (t >= 1) target_groups = std::min(n_layers, t); }
-    const size_t per_group = (total + target_groups - 1) / target_groups;
+    // Group sizes are graded: the first upload and the last apply + download run alone on the link (pipeline fill and drain), so the
+    // first group is ~0.65 and the last two ~0.8 / ~0.4 of the average — the first apply cannot start before the factor ends anyway
+    // (~0.12 ms: about 6 MB of upload) — and the groups in between share the rest.  UCE_HOST_EVEN_GROUPS=1 restores equal groups.
+    static const bool even_groups = [] { const char* e = getenv("UCE_HOST_EVEN_GROUPS"); return e && atoi(e) != 0; }();
+    std::vector<double> share(target_groups, 1.0);
+    if (!even_groups && target_groups >= 4) {
+        share[0] = 0.65; share[target_groups - 1] = 0.4; share[target_groups - 2] = 0.8;
+        const double rest = (target_groups - 1.85) / (target_groups - 3);
+        for (int g = 1; g < target_groups - 2; ++g) share[g] = rest;
+    }
     std::vector<int> gbeg{0};
-    { size_t acc = 0; for (int l = 0; l < n_layers; ++l) { acc += (size_t)d[l] * K; if (acc >= per_group && l + 1 < n_layers) { gbeg.push_back(l + 1); acc = 0; } } }
+    {
+        double want = 0.0; size_t acc = 0;
+        for (int l = 0, g = 0; l < n_layers; ++l) {
+            acc += (size_t)d[l] * K;
+            const double bound = (want + share[g]) / target_groups * (double)total;
+            // close the group at the layer boundary nearest to its share
+            const size_t next = l + 1 < n_layers ? (size_t)d[l + 1] * K : 0;
+            if (l + 1 < n_layers && g + 1 < target_groups && (double)acc + 0.5 * (double)next >= bound) { gbeg.push_back(l + 1); want += share[g]; ++g; }
+        }
+    }
     gbeg.push_back(n_layers);
     const int ng = (int)gbeg.size() - 1;
     while ((int)ws->ev_h2d.size() < ng + 1) {

@@ -286,6 +286,7 @@ apply_w_kernel(const Slot* __restrict__ slots, int n_slots, int K, int R, int ks
         if (trace && blockIdx.x == 0 && idx < 64) trace[(role * 64 + idx) * 4 + ev] = clock64();
     };
     extern __shared__ __align__(1024) uint8_t smem_raw[];
+    pdl_launch();
     if (threadIdx.x == 0) tr(6, 2, 0);
     const uint32_t base = smem_u32(smem_raw);
     if (base & 1023u) {
@@ -449,6 +450,10 @@ apply_w_kernel(const Slot* __restrict__ slots, int n_slots, int K, int R, int ks
         __syncwarp();
     } else if (warp == WARP_B) {
         // =============================== TMA warp 2: Qt_hi | Qt_lo tiles of a unit under ONE barrier ===============================
+        // Programmatic dependent launch: this kernel is launched while the factor's last kernel (which writes Qt) still runs; everything
+        // above and beside this warp — barriers, tensor memory, the partial products (kernel A finished before the factor's solve was
+        // even launched) and the addend boxes of W_old — needs nothing from it.  Only the Qt tiles do: wait here.
+        pdl_wait();
         const uint32_t q_bytes = (uint32_t)(n_rc * 2) * 4096u;
         for (int u = 0; u < c.ncs; ++u) {
             const int t = u % NQ;
@@ -618,8 +623,8 @@ int apply_ab_lowrank(uce_ws* ws, const void* slots_dev, const void* slots_host, 
         const int smem = smem_b();
         int& cf = conf_b[ws->device & 63];
         if (cf < smem) { UCE_CUDA(cudaFuncSetAttribute(apply_w_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); cf = smem; }
-        apply_w_kernel<<<grid, THREADS, smem, st>>>((const Slot*)slots_dev, n_slots, K, R, ks, Pscr, qm, wmaps, trace ? trace + TRN / 2 : nullptr);
-        UCE_LAUNCH_CHECK();
+        UCE_CUDA(launch_k(apply_w_kernel, dim3(grid), dim3(THREADS), (size_t)smem, st, 1, (const Slot*)slots_dev, n_slots, K, R, ks, (const float*)Pscr, qm, wmaps,
+                          trace ? trace + TRN / 2 : (long long*)nullptr));
         *launches += 1;
     }
     if (trace) {

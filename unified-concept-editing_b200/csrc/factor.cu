@@ -17,6 +17,7 @@
 // as strided fp64 SIMT GEMMs.
 #include "uce_ws.h"
 #include "gemm_simt.cuh"
+#include "tc_common.cuh"
 #include <algorithm>
 #include <cmath>
 #include <cstring>
@@ -30,6 +31,7 @@ namespace uce {
 //       Cs64[r,:] = s_r * Cp[r,:]  (primal only)
 struct alignas(16) FactorTables { unsigned int w[4096]; };     // n row indices (int), padded to 8 bytes, then n diagonal terms (double)
 __global__ void __launch_bounds__(256) factor_tables_kernel(const __grid_constant__ FactorTables t, int n, int* src_idx, double* diag_add, int* flag) {
+    pdl_wait(); pdl_launch();
     const double* dsrc = reinterpret_cast<const double*>(t.w + n + (n & 1));
     for (int i = threadIdx.x; i < n; i += blockDim.x) { src_idx[i] = (int)t.w[i]; diag_add[i] = dsrc[i]; }
     if (threadIdx.x == 0) *flag = 0;
@@ -362,8 +364,8 @@ int factor_dev(uce_ws* ws, const float* C, const float* G, const float* scales, 
         FactorTables t;
         memcpy(t.w, ws->h_src_idx, (size_t)n * 4);
         memcpy(t.w + n + (n & 1), ws->h_diag_add, (size_t)n * 8);
-        factor_tables_kernel<<<1, 256, 0, st>>>(t, n, ws->src_idx, ws->diag_add, ws->flag);
-        UCE_LAUNCH_CHECK(); ++launches;
+        UCE_CUDA(launch_k(factor_tables_kernel, dim3(1), dim3(256), 0, st, 1, t, n, ws->src_idx, ws->diag_add, ws->flag));
+        ++launches;
     } else {
         int rc = table_upload(ws->src_idx, ws->h_src_idx, (size_t)n * sizeof(int), st, &launches);
         if (!rc) rc = table_upload(ws->diag_add, ws->h_diag_add, (size_t)n * sizeof(double), st, &launches);
@@ -450,6 +452,14 @@ int factor_dev(uce_ws* ws, const float* C, const float* G, const float* scales, 
     if (!ws->dense && ws->rank > 0 && !qt_split_done) {      // tf32 hi/lo split of Qt: always, so the apply implementation may be chosen after the factor
         int rc2 = split_operand(ws, ws->Qt, ws->Qt_hi, ws->Qt_lo, st, &launches);
         if (rc2) return rc2;
+    }
+    // the general path used H: clear the part the single-CTA factor accumulates into (it skips its own memset when H_dirty == 0)
+    if (!ws->debug) {
+        const size_t clean = std::min((size_t)ws->sys_max * ws->sys_max, (size_t)160 * 160) * sizeof(double);
+        UCE_CUDA(cudaMemsetAsync(ws->H, 0, clean, st));
+        ws->H_dirty = 0;
+    } else {
+        ws->H_dirty = 1;
     }
     ws->launches_factor = launches;
     return 0;

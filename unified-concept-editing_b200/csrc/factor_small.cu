@@ -17,6 +17,7 @@
 // Same algebra and same fp64 precision as the general path (trainscripts/uce_sd_erase.py:63,71,79,82 — the
 // mat2 accumulation and its inverse — done once per edit).
 #include "uce_ws.h"
+#include "tc_common.cuh"
 #include <cstdlib>
 
 namespace uce {
@@ -44,6 +45,7 @@ __global__ void __launch_bounds__(256) gram_pack_kernel(const float* __restrict_
                                                         float* __restrict__ Cp, float* __restrict__ E, float* __restrict__ E_hi, float* __restrict__ E_lo) {
     __shared__ double A[FS_NB][FS_KSPLIT + 1];
     __shared__ double B[FS_NB][FS_KSPLIT + 1];
+    pdl_wait(); pdl_launch();                      // the row order (src) comes from the table kernel launched right before
     if ((int)blockIdx.x >= n_pairs) {
         if (blockIdx.y == 0) {
             const int r = (int)blockIdx.x - n_pairs;
@@ -104,12 +106,14 @@ __device__ __forceinline__ double fs_rsqrt(double d) {
     return fma(y0 * e, fma(0.375, e, 0.5), y0);
 }
 
+// (Measured and rejected: taking the pivot chain through a reciprocal — d_next = A[j+1][j+1] - A[j+1][j]^2 / d, with the reciprocal
+// square root beside it — shortens the dependent chain by two fp64 operations on paper and ran 4 k cycles per block SLOWER: the
+// extra fp64 instructions cost more issue time on this part than the shorter chain saves.)
 // One pivot step with the trailing update limited to KM columns (straight-line: the column loads are issued ahead of the
 // FMAs; a per-column early exit was measured 1.8x SLOWER — the branches serialise load and FMA latencies).
 // `d` is the pivot A[j][j] of this step; the return value is the pivot of step j + 1.  The pivot chain does NOT go through shared
-// memory: lane j + 1 updates its own diagonal entry from its own multiplier (A[j+1][j+1] - L[j+1][j]^2 — the same fma, bit for bit,
-// that the column loop below performs for it) and broadcasts it by shuffle while the column of L travels through shared memory
-// for everybody else (11.6 k -> 11.0 k cycles per block).  Also measured: the multipliers by shuffle instead of shared memory,
+// memory: lane j + 1 updates its own diagonal entry itself and broadcasts it by shuffle while the column of L travels through shared
+// memory for everybody else (11.6 k -> 11.0 k cycles per block).  Also measured: the multipliers by shuffle instead of shared memory,
 // which removes both warp barriers and lets the next pivot's rsqrt interleave with the update — 64 shuffles per pivot cost more
 // than that buys (17.1 k cycles per block).
 template <int KM>
@@ -192,6 +196,7 @@ __global__ void __launch_bounds__(FS_T, 1)
 chol_small_kernel(double* __restrict__ Hg, int n, int n_pad, const double* __restrict__ dadd,
                   double* __restrict__ Lg, double* __restrict__ invd_g, int write_back, int* flag, long long* __restrict__ trace) {
     extern __shared__ double smem_d[];
+    pdl_wait(); pdl_launch();                      // inv_blocks is launched now and parks at its own wait
     int trn = 0;
     auto tr = [&]() { if (trace && threadIdx.x == 0 && trn < 64) trace[trn++] = clock64(); };
     tr();
@@ -233,6 +238,19 @@ chol_small_kernel(double* __restrict__ Hg, int n, int n_pad, const double* __res
 
     // (a) Cholesky of a diagonal block by one warp (see fs_potrf_warp).  Block 0 here; block kb + 1 is factored by warp 0 WHILE
     //     the other 15 warps finish the trailing update of step kb (lookahead, step (d) below).
+    // H is the accumulator of the Gram kernel's atomics: it is left cleared for the next factor (no memset on that critical path) —
+    // by the warps that idle during the last diagonal block's factorisation
+    auto zero_H = [&](int first, int stride) {
+        const int nbt = nblk * (nblk + 1) / 2;
+        for (int idx = first; idx < nbt * FS_NB * FS_NB; idx += stride) {
+            const int b = idx >> 10, rc = idx & 1023;
+            int bi = 0;
+            while ((bi + 1) * (bi + 2) / 2 <= b) ++bi;
+            const int bj = b - bi * (bi + 1) / 2;
+            Hg[(long)(bi * FS_NB + (rc >> 5)) * n_pad + bj * FS_NB + (rc & 31)] = 0.0;
+        }
+    };
+    if (nblk == 1 && !write_back && warp != 0) zero_H(tid - 32, FS_T - 32);
     if (warp == 0) fs_potrf_warp(SB + fs_blk(0, 0), invd, lane, flag, 0);
     __syncthreads();
     tr();   // diag block 0 factored
@@ -315,6 +333,7 @@ chol_small_kernel(double* __restrict__ Hg, int n, int n_pad, const double* __res
                     const int bi = kb + (idx >> 10), rc = idx & 1023;
                     Lg[(size_t)(bi * (bi + 1) / 2 + kb) * (FS_NB * FS_NB) + rc] = SB[fs_blk(bi, kb) + (rc >> 5) * P + (rc & 31)];
                 }
+                if (mb == 1 && !write_back) zero_H(tid - 32, FS_T - 32);     // last step: these warps have no trailing update left
             }
             __syncthreads();
         }
@@ -350,6 +369,7 @@ __global__ void __launch_bounds__(FS_T, 1) inv_blocks_kernel(double* __restrict_
     constexpr int P = FS_NB + 1, NW = FS_T / 32;
     const int kb = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     double* Dg = Lg + (size_t)(kb * (kb + 1) / 2 + kb) * FS_NB * FS_NB;
+    pdl_wait(); pdl_launch();                      // wait FIRST: solve_emit, launched by this trigger, reads the factor before its own wait
     for (int idx = tid; idx < FS_NB * FS_NB; idx += FS_T) Ds[(idx >> 5) * P + (idx & 31)] = Dg[idx];
     if (tid < FS_NB) iv_s[tid] = invd_g[kb * FS_NB + tid];
     __syncthreads();
@@ -393,30 +413,42 @@ solve_emit_kernel(const double* __restrict__ Lg, const double* __restrict__ invd
     double* XS = TS + FS_BLK;                     // [n_pad][XL]
     const int tid = threadIdx.x;
     const int k0 = blockIdx.x * SE_CW;
-    // the slab first (it does not depend on the factor kernel... but this kernel is launched behind it anyway), then L
+    // Launched (programmatically) while inv_blocks still runs: the slab, the reciprocals and the off-diagonal blocks of L come from
+    // kernels that had finished before inv_blocks passed its own wait and are loaded right away; the diagonal blocks (inverted in
+    // place by inv_blocks) after the wait.  The apply's second kernel is launched by the trigger below and prefetches beside us.
+    pdl_launch();
     for (int idx = tid; idx < n_pad * SE_CW; idx += SE_T) {
         const int r = idx / SE_CW, c = idx % SE_CW;
         XS[r * XL + c] = (r < n && k0 + c < K) ? (double)Cp[(long)r * K + k0 + c] : 0.0;
     }
-    {   // 16-byte loads, eight in flight per thread
-        const double2* L2 = reinterpret_cast<const double2*>(Lg);
-        const int n2 = nb * FS_NB * FS_NB / 2;
-        for (int i0 = tid; i0 < n2; i0 += 8 * SE_T) {
+    auto is_diag = [](int b) { int kb = 0; while ((kb + 1) * (kb + 2) / 2 <= b) ++kb; return b == kb * (kb + 1) / 2 + kb; };
+    const double2* L2 = reinterpret_cast<const double2*>(Lg);
+    const int n2 = nb * FS_NB * FS_NB / 2;
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {         // 0: off-diagonal blocks (before the wait), 1: diagonal blocks
+        if (pass == 1) pdl_wait();
+        for (int i0 = tid; i0 < n2; i0 += 8 * SE_T) {        // 16-byte loads, eight in flight per thread
             double2 v[8];
 #pragma unroll
-            for (int q = 0; q < 8; ++q) { const int idx = i0 + q * SE_T; v[q] = (idx < n2) ? __ldg(L2 + idx) : make_double2(0.0, 0.0); }
+            for (int q = 0; q < 8; ++q) {
+                const int idx = i0 + q * SE_T;
+                // plain loads: the diagonal blocks are rewritten by the kernel running beside this one (no read-only cache path)
+                v[q] = (idx < n2 && is_diag((2 * idx) >> 10) == (pass == 1)) ? L2[idx] : make_double2(0.0, 0.0);
+            }
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
                 const int idx = i0 + q * SE_T;
                 if (idx < n2) {
                     const int e = 2 * idx, b = e >> 10, rc = e & 1023;
-                    double* d = SB + b * FS_BLK + (rc >> 5) * P + (rc & 31);
-                    d[0] = v[q].x; d[1] = v[q].y;
+                    if (is_diag(b) == (pass == 1)) {
+                        double* d = SB + b * FS_BLK + (rc >> 5) * P + (rc & 31);
+                        d[0] = v[q].x; d[1] = v[q].y;
+                    }
                 }
             }
         }
+        if (pass == 0) for (int r = tid; r < n_pad; r += SE_T) invd[r] = invd_g[r];
     }
-    for (int r = tid; r < n_pad; r += SE_T) invd[r] = invd_g[r];
     __syncthreads();
     const int c = tid & (SE_CW - 1), rq = tid / SE_CW;        // column of the slab; row (triangular multiply) or row quad (updates)
     // ---- forward ----
@@ -548,11 +580,17 @@ int factor_small(uce_ws* ws, const float* C, const float* G, int n, int n_pres, 
     const int K = ws->K;
     const int n_pad = round_up(n, FS_NB);
     ws->sys_n = n_pad;
-    UCE_CUDA(cudaMemsetAsync(ws->H, 0, (size_t)n_pad * n_pad * sizeof(double), st));
+    // H accumulates the Gram kernel's atomics and must start from zero: chol_small_kernel clears what it read, so in steady state no
+    // memset sits between the table kernel and the Gram kernel (it would also break their programmatic launch edge)
+    // (the whole region any size of this path can touch, FS_MAX_N^2, so that a later call with another n_pad finds zeros too)
+    if (ws->H_dirty || ws->debug) {
+        const size_t sm = (size_t)ws->sys_max * ws->sys_max, fm = (size_t)FS_MAX_N * FS_MAX_N;
+        UCE_CUDA(cudaMemsetAsync(ws->H, 0, (sm < fm ? sm : fm) * sizeof(double), st));
+    }
     const int nt = n_pad / FS_NB, n_pairs = nt * (nt + 1) / 2, n_pack = n + (ws->rank_pad - n_edit);
-    gram_pack_kernel<<<dim3(n_pairs + n_pack, ceil_div(K, FS_KSPLIT)), 256, 0, st>>>(C, ws->src_idx, n, K, ws->H, n_pad, n_pairs, G, n_pres, ws->rank_pad,
-                                                                                      n_pack, ws->Cp, ws->E, ws->E_hi, ws->E_lo);
-    UCE_LAUNCH_CHECK(); ++*launches;
+    UCE_CUDA(launch_k(gram_pack_kernel, dim3(n_pairs + n_pack, ceil_div(K, FS_KSPLIT)), dim3(256), 0, st, 1, C, (const int*)ws->src_idx, n, K, ws->H, n_pad,
+                      n_pairs, G, n_pres, ws->rank_pad, n_pack, ws->Cp, ws->E, ws->E_hi, ws->E_lo));
+    ++*launches;
     // E and its split are complete (pack kernel) and the many-CTA Gram kernel is behind us: from here on the factor is one CTA wide,
     // the point where uce_edit_dev_f32 lets the apply's first kernel (which needs E only) start on its own stream
     if (ws->want_ev_E) { UCE_CUDA(cudaEventRecord(ws->ev_E, st)); ws->ev_E_recorded = 1; }
@@ -580,8 +618,17 @@ int factor_small(uce_ws* ws, const float* C, const float* G, int n, int n_pres, 
     if (trace_path) { UCE_CUDA(cudaMalloc(&trace, 64 * sizeof(long long))); UCE_CUDA(cudaMemsetAsync(trace, 0, 64 * sizeof(long long), st)); }
     static_assert(FS_MAX_N == 160, "ws->Lsmall is sized for 15 blocks + 160 reciprocals");
     double* Lg = ws->Lsmall; double* invd_g = ws->Lsmall + 15 * 1024;
-    chol_small_kernel<<<1, FS_T, smem_c, st>>>(ws->H, n, n_pad, ws->diag_add, Lg, invd_g, ws->debug, ws->flag, trace);
-    UCE_LAUNCH_CHECK(); ++*launches;
+    UCE_CUDA(launch_k(chol_small_kernel, dim3(1), dim3(FS_T), smem_c, st, 1, ws->H, n, n_pad, (const double*)ws->diag_add, Lg, invd_g, (int)ws->debug, ws->flag, trace));
+    ++*launches;
+    ws->H_dirty = ws->debug ? 1 : 0;
+    // the apply's first kernel goes to its own stream now (the host encodes it while the single-CTA factor runs); this stream waits for
+    // it BEFORE the last two kernels, so that the apply's second kernel directly follows solve_emit and launches programmatically
+    if (ws->hook_after_E) {
+        ws->mode = 1;                                  // this path is the dual system; the apply's planner asks
+        int rc = ws->hook_after_E(ws->hook_ctx);
+        if (rc) return rc;
+        if (ws->hook_done) UCE_CUDA(cudaStreamWaitEvent(st, ws->hook_done, 0));
+    }
     if (trace) {   // debugging aid: phase boundaries of the single factor CTA (synchronises)
         long long h[64];
         UCE_CUDA(cudaStreamSynchronize(st));
@@ -592,11 +639,11 @@ int factor_small(uce_ws* ws, const float* C, const float* G, int n, int n_pres, 
             fclose(f);
         }
     }
-    inv_blocks_kernel<<<nt, FS_T, 0, st>>>(Lg, invd_g);
-    UCE_LAUNCH_CHECK(); ++*launches;
-    solve_emit_kernel<<<ceil_div(K, SE_CW), SE_T, smem_s, st>>>(Lg, invd_g, ws->Cp, n, n_pad, n_pres, n_edit, ws->rank_pad, K, ws->Q, ws->Qt,
-                                                                ws->Qt_hi, ws->Qt_lo);
-    UCE_LAUNCH_CHECK(); ++*launches;
+    UCE_CUDA(launch_k(inv_blocks_kernel, dim3(nt), dim3(FS_T), 0, st, 1, Lg, (const double*)invd_g));
+    ++*launches;
+    UCE_CUDA(launch_k(solve_emit_kernel, dim3(ceil_div(K, SE_CW)), dim3(SE_T), smem_s, st, 1, (const double*)Lg, (const double*)invd_g, (const float*)ws->Cp, n, n_pad,
+                      n_pres, n_edit, ws->rank_pad, K, ws->Q, ws->Qt, ws->Qt_hi, ws->Qt_lo));
+    ++*launches;
     return 0;
 }
 

@@ -187,6 +187,22 @@ int uce_apply_dev_f32(uce_ws* ws, const float* const* W_old, float* const* W_new
 }
 
 // Fork / join of the K-split apply's first kernel around the factor (see the header).
+struct Stage1Hook { uce_ws* ws; const float* const* W_old; float* const* W_new; const int* d; int n_layers; int launches; int ran; };
+static int stage1_hook(void* p) {
+    Stage1Hook* h = (Stage1Hook*)p;
+    uce_ws* ws = h->ws;
+    if (!(ws->ev_E_recorded && ws->rank > 0 && apply_stage_split(ws, h->n_layers))) return 0;
+    UCE_CUDA(cudaStreamWaitEvent(ws->s_side, ws->ev_fork, 0));
+    UCE_CUDA(cudaStreamWaitEvent(ws->s_side, ws->ev_E, 0));
+    int rc = apply_dev(ws, h->W_old, h->W_new, h->d, h->n_layers, ws->s_side, true, 1);
+    if (rc) return rc;
+    h->launches = ws->launches_apply;
+    UCE_CUDA(cudaEventRecord(ws->ev_A, ws->s_side));
+    ws->hook_done = ws->ev_A;
+    h->ran = 1;
+    return 0;
+}
+
 static int edit_dev(uce_ws* ws, const float* C, const float* G, const float* scales, int n_rows, int n_edit, float lamb,
                     const float* const* W_old, float* const* W_new, const int* d, int n_layers, cudaStream_t st, bool no_profile) {
     if (!ws->s_side) {
@@ -203,10 +219,23 @@ static int edit_dev(uce_ws* ws, const float* C, const float* G, const float* sca
     ws->ev_E_recorded = 0;
     ws->slots_staged.clear();
     if (prof) UCE_CUDA(cudaEventRecord(ws->pev[0], st));
+    // single-CTA factor: the factor itself calls back (stage1_hook) once its long kernel is launched, so that the apply's first kernel is
+    // on its way early and this stream waits for it before the factor's LAST kernels — the apply's second kernel then follows solve_emit
+    // directly and is launched programmatically beside it
+    Stage1Hook hook{ws, W_old, W_new, d, n_layers, 0, 0};
+    if (overlap) { ws->hook_after_E = stage1_hook; ws->hook_ctx = &hook; }
+    ws->hook_done = nullptr;
     int rc = factor_dev(ws, C, G, scales, n_rows, n_edit, lamb, st);
     ws->want_ev_E = 0;
+    ws->hook_after_E = nullptr; ws->hook_ctx = nullptr; ws->hook_done = nullptr;
     if (prof) UCE_CUDA(cudaEventRecord(ws->pev[1], st));
     if (rc) return rc;
+    if (hook.ran) {
+        rc = apply_dev(ws, W_old, W_new, d, n_layers, st, true, 2);
+        ws->launches_apply += hook.launches;
+        ws->pev_mid = 0;
+        return rc;
+    }
     if (overlap && ws->ev_E_recorded && ws->rank > 0 && apply_stage_split(ws, n_layers)) {
         UCE_CUDA(cudaStreamWaitEvent(ws->s_side, ws->ev_fork, 0));
         UCE_CUDA(cudaStreamWaitEvent(ws->s_side, ws->ev_E, 0));

@@ -37,6 +37,12 @@ struct uce_ws {
     double* Hcopy = nullptr;  // debug copy of the assembled system (lazily allocated)
     double* Linv = nullptr;   // [sys_max/NB][NB][NB]
     double* Lsmall = nullptr; // low-latency factor: block triangle of L (15 blocks of 32 x 32) + 1 / L_ii (160), chol_small -> solve_emit
+    int     H_dirty = 1;          // 0: the part of H the single-CTA factor uses is known to be zero (that kernel clears what it read)
+    // uce_edit_dev_f32: called by the factor right after the kernel that follows the E rows has been launched — launches the apply's
+    // first kernel on the side stream; the factor then waits for hook_done before the kernels whose successor is the apply's second kernel
+    int   (*hook_after_E)(void*) = nullptr;
+    void*   hook_ctx = nullptr;
+    cudaEvent_t hook_done = nullptr;
     double* X = nullptr;      // [sys_max, max_rows]  rhs / solution
     int*    src_idx = nullptr;   // [max_rows] API row of internal row r
     double* diag_add = nullptr;  // [max_rows] lamb / s_r  (dual)  or s_r (primal)

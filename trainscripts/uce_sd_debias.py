@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Drop-in CLI for the reference's trainscripts/uce_sd_debias.py (flags and defaults :155-195)
-with every re-solve of the iterative loop on the B200 kernels."""
+with every re-solve of the iterative loop on the B200 kernels.  Under torchrun the generation / classification rounds are shared
+between the ranks (debias.get_ratios); rank 0 writes the artifact."""
 import argparse
 import os
 import sys
@@ -62,9 +63,15 @@ def main(argv=None):
         from transformers import pipeline
     except ImportError as exc:
         raise SystemExit(f"diffusers/transformers are required to load '{args.model_id}': {exc}")
+    if "RANK" in os.environ and int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        # under torchrun the edit concepts of get_ratios() are dealt to the ranks (one all-reduce of the label counts per iteration);
+        # every rank solves the same edit, rank 0 writes the artifact
+        local = int(os.environ.get("LOCAL_RANK", "0"))
+        args.device = f"cuda:{local}"
+        torch.distributed.init_process_group("nccl", device_id=torch.device(args.device))
     pipe = DiffusionPipeline.from_pretrained(args.model_id, torch_dtype=torch.float32, safety_checker=None).to(args.device)
     pipe.set_progress_bar_config(disable=True)
-    clip = pipeline(task="zero-shot-image-classification", model="openai/clip-vit-base-patch32", torch_dtype=torch.bfloat16, device=0)
+    clip = pipeline(task="zero-shot-image-classification", model="openai/clip-vit-base-patch32", torch_dtype=torch.bfloat16, device=args.device)
     if args.classifier == "engine":
         from uce_b200.clip_zero_shot import ClipZeroShotEngine
         clip = ClipZeroShotEngine.from_pipeline(clip, device=args.device)

@@ -2,8 +2,8 @@
 """Drop-in CLI for the reference's trainscripts/uce_sd_erase.py (same flags and defaults,
 :97-112; same prints, :193-195; same artifact, :85-88) with the edit solved on the B200 kernels.
 
-Extra, optional flags (not in the reference): --gpus N shards the projections over N ranks when the
-script is launched under torchrun.
+Multi-GPU (not in the reference): launched under torchrun (`python -m torch.distributed.run --nproc-per-node N ...`) the projections
+are sharded over the N ranks and gathered once at the end; there is no flag for it, the torchrun environment selects it.
 """
 import argparse
 import os

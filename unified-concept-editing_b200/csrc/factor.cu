@@ -163,7 +163,7 @@ static int split_operand(uce_ws* ws, const float* x, float* hi, float* lo, cudaS
 // memory / L2 and stream through a double-buffered 32 x 32 shared-memory block: the next block is fetched into registers while the
 // current one is used.  Replaces 128 launches of block triangular solves on n_edit unit vectors plus a Q = X^T Cp GEMM (1.9 of the
 // 3.6 ms general factor at BASELINE cfg4) by one launch of K / 8 CTAs.
-constexpr int SG_CW = 8;
+constexpr int SG_CW = 8, SG_PF = 4;
 __global__ void __launch_bounds__(256) solve_emit_general_kernel(const double* __restrict__ L, int ld, const double* __restrict__ Linv,
                                                                  const float* __restrict__ Cp, int n, int n_pad, int n_pres, int n_edit, int r_pad, int K,
                                                                  float* __restrict__ Q, float* __restrict__ Qt, float* __restrict__ Qt_hi, float* __restrict__ Qt_lo) {
@@ -202,17 +202,24 @@ __global__ void __launch_bounds__(256) solve_emit_general_kernel(const double* _
         const double2 a = *reinterpret_cast<const double2*>(s + (size_t)lr * sld + lc), b = *reinterpret_cast<const double2*>(s + (size_t)lr * sld + lc + 2);
         v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
     };
-    It cur{0, 0, -1};
-    double nxt[4];
-    fetch(cur, nxt);
+    // The blocks of L are read-only here, so they are requested SG_PF block steps ahead (registers: four doubles per thread and step):
+    // one step of work (~300 cycles) does not cover an L2 round trip (the first version, one block ahead, spent ~2 200 cycles per block).
+    It cur{0, 0, -1}, ahead{0, 0, -1};
+    double pf[SG_PF][4];
+#pragma unroll
+    for (int d = 0; d < SG_PF; ++d)
+        if (valid(ahead)) { fetch(ahead, pf[d]); ahead = advance(ahead); }
     int buf = 0;
     while (valid(cur)) {
+#pragma unroll
+      for (int d = 0; d < SG_PF; ++d) {
+        if (!valid(cur)) break;
         double* B = BLK + buf * NBK * P;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) B[lr * P + lc + q] = nxt[q];
+        for (int q = 0; q < 4; ++q) B[lr * P + lc + q] = pf[d][q];
         __syncthreads();                                   // block visible; everybody is done with the previous block and its writes to XS
         const It nx = advance(cur);
-        if (valid(nx)) fetch(nx, nxt);                     // in flight during the work below
+        if (valid(ahead)) { fetch(ahead, pf[d]); ahead = advance(ahead); }      // refill this slot: SG_PF steps ahead
         const int o = cur.kb * NBK;
         double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
         if (cur.i < 0) {
@@ -251,6 +258,7 @@ __global__ void __launch_bounds__(256) solve_emit_general_kernel(const double* _
         }
         cur = nx;
         buf ^= 1;
+      }
     }
     __syncthreads();
     for (int idx = tid; idx < r_pad * SG_CW; idx += 256) {
@@ -283,8 +291,8 @@ static int cholesky_solve(uce_ws* ws, int n_pad, int n_rhs, int ldx, int fwd_fro
     const int nb = UCE_NB, nblk = n_pad / nb, ld = n_pad;
     double* H = ws->H; double* X = ws->X; double* Linv = ws->Linv;
     for (int k = 0; k < nblk; ++k) {
-        potrf_diag_kernel<<<1, dim3(nb, nb), 0, st>>>(H, ld, k, Linv, ws->flag);
-        UCE_RT(cudaGetLastError());
+        if (getenv("UCE_OLD_POTRF")) { potrf_diag_kernel<<<1, dim3(nb, nb), 0, st>>>(H, ld, k, Linv, ws->flag); UCE_RT(cudaGetLastError()); }
+        else UCE_RT((cudaError_t)potrf_inv_general(H, ld, k, Linv, ws->flag, st));
         int rest = n_pad - (k + 1) * nb;
         if (rest > 0) {
             double* panel = H + (long)(k + 1) * nb * ld + (long)k * nb;            // [rest, nb], ld

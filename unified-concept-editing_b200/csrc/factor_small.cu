@@ -390,6 +390,50 @@ __global__ void __launch_bounds__(FS_T, 1) inv_blocks_kernel(double* __restrict_
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// General blocked path (factor.cu, systems larger than FS_MAX_N): factor diagonal block kb of H (row-major, ld) in place and emit
+// the dense inverse of its Cholesky factor — the warp-resident potrf and the column-sweep inverse of this file instead of the first
+// version's 1 024-thread kernel with three block barriers per pivot (26 us per block; 32 blocks per factor at BASELINE cfg4).
+__global__ void __launch_bounds__(FS_T, 1) potrf_inv_general_kernel(double* __restrict__ H, int ld, int kb, double* __restrict__ Linv, int* flag) {
+    constexpr int P = FS_NB + 1, NW = FS_T / 32;
+    __shared__ double D[(FS_NB + 8) * P];           // + 8 rows of slack: the last pivots read L[j + k][j] for rows up to 38
+    __shared__ double invd[FS_NB];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double* blk = H + (size_t)kb * FS_NB * ld + (size_t)kb * FS_NB;
+    for (int idx = tid; idx < (FS_NB + 8) * FS_NB; idx += FS_T) {
+        const int r = idx >> 5, c = idx & 31;
+        D[r * P + c] = (r < FS_NB && c <= r) ? blk[(size_t)r * ld + c] : 0.0;
+    }
+    __syncthreads();
+    if (warp == 0) fs_potrf_warp(D, invd, lane, flag, kb);
+    __syncthreads();
+    for (int idx = tid; idx < FS_NB * FS_NB; idx += FS_T) {
+        const int r = idx >> 5, c = idx & 31;
+        blk[(size_t)r * ld + c] = (c <= r) ? D[r * P + c] : 0.0;
+    }
+    // inverse by column sweeps (lane = row), two columns per warp: see inv_blocks_kernel
+    const int c1 = warp, c2 = warp + NW;
+    double acc1 = 0.0, acc2 = 0.0, mine1 = 0.0, mine2 = 0.0;
+    for (int j = c1; j < FS_NB; ++j) {
+        const double cand1 = ((lane == c1) ? 1.0 : 0.0) - acc1, cand2 = ((lane == c2) ? 1.0 : 0.0) - acc2;
+        const double iv = invd[j];
+        const double x1 = __shfl_sync(0xffffffffu, cand1, j) * iv, x2 = __shfl_sync(0xffffffffu, cand2, j) * iv;
+        if (lane == j) { mine1 = x1; mine2 = x2; }
+        if (lane > j) {
+            const double l = D[lane * P + j];
+            acc1 = fma(l, x1, acc1); acc2 = fma(l, x2, acc2);
+        }
+    }
+    double* out = Linv + (size_t)kb * FS_NB * FS_NB;       // dense [row][column], zeros above the diagonal
+    out[lane * FS_NB + c1] = mine1;
+    out[lane * FS_NB + c2] = mine2;
+}
+int potrf_inv_general(double* H, int ld, int kb, double* Linv, int* flag, cudaStream_t st) {
+    static_assert(FS_NB == UCE_NB && FS_T == 32 * 16, "two inverse columns per warp");
+    potrf_inv_general_kernel<<<1, FS_T, 0, st>>>(H, ld, kb, Linv, flag);
+    return (int)cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // X = H^-1 Cp[:, cols] for one slab of SE_CW columns, then Q[j, cols] = X[n_pres + j, cols]  (see the file header).
 //   forward   L Y = Cp[:, cols]        over all block rows
 //   backward  L^T X = Y                from the last block row up to the block row of the first edit row

@@ -87,5 +87,6 @@ int table_upload(void* dst, const void* src_host, size_t bytes, cudaStream_t st,
 bool apply_stage_split(const uce_ws* ws, int n_layers);   // true when apply_dev would take the two-kernel K-split path for this edit
 // factor_small.cu
 bool factor_small_applicable(const uce_ws* ws, int n, int n_edit, bool dual);
+int potrf_inv_general(double* H, int ld, int kb, double* Linv, int* flag, cudaStream_t st);     // factor_small.cu: one diagonal block of the general path
 int factor_small(uce_ws* ws, const float* C, const float* G, int n, int n_pres, int n_edit, cudaStream_t st, int* launches);
 }  // namespace uce

@@ -26,7 +26,10 @@ WANT = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "la
         "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_sector_hit_rate.pct", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
         "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active",
         "sm__warps_active.avg.pct_of_peak_sustained_active", "sm__throughput.avg.pct_of_peak_sustained_elapsed", "smsp__inst_executed.sum",
-        "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "l1tex__m_xbar2l1tex_read_bytes.sum", "l1tex__m_l1tex2xbar_write_bytes.sum"]
+        "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__m_xbar2l1tex_read_bytes.sum",
+        "l1tex__m_l1tex2xbar_write_bytes.sum", "lts__t_bytes.sum", "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio", "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio"]
 
 
 def raw_metrics(rep, out, title, row_index=0):
@@ -100,3 +103,7 @@ for name in ("bench.json", "bench_cfg1.json", "bench_cfg3.json", "bench_cfg4.jso
             print("wrote", "profiles/r02_" + name)
         except Exception as exc:
             print("skip", name, exc)
+raw_metrics(os.path.join(G, "prof_solve_general.ncu-rep"), os.path.join(P, "r02_solve_general_ncu.txt"),
+            "solve_emit_general_kernel (fp64 SIMT, 8 columns per CTA) at BASELINE cfg4 — shared-memory bound (two loads per fma); replaced by solve_emit_dmma_kernel")
+raw_metrics(os.path.join(G, "prof_solve_dmma.ncu-rep"), os.path.join(P, "r02_solve_dmma_ncu.txt"),
+            "solve_emit_dmma_kernel (fp64 tensor pipe, mma.sync m8n8k4, 16 columns per CTA, L tiles straight from L2) at BASELINE cfg4")

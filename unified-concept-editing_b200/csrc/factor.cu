@@ -274,6 +274,99 @@ __global__ void __launch_bounds__(256) solve_emit_general_kernel(const double* _
     }
 }
 
+// The same solve on the fp64 TENSOR pipe (mma.sync m8n8k4.f64), 16 columns of Cp per CTA.  ncu on the SIMT version above
+// (profiles/r02_solve_general_ncu.txt): two shared-memory loads per fma — 71 % of the shared-memory pipe's cycles, the fp64 pipe 12 %
+// active, 1.25 ms at BASELINE cfg4.  Here a warp owns an 8-row tile of the block row it works on: the A fragment (8 x 4 of a block of L)
+// comes STRAIGHT from global memory / L2 in fragment layout (eight 32-byte sectors per warp instruction, no staging, no barrier), the
+// B fragments (Y_k, 32 x 16) are loaded from the slab once per block step and kept in registers for every block of that column, and
+// the 8 x 8 result tiles are subtracted from the slab in place.  Warps 0-3 and 4-7 take alternate blocks of the column; the L tiles
+// are requested SD_PF blocks ahead.
+constexpr int SD_CW = 16, SD_XL = 20, SD_PF = 4;
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+__global__ void __launch_bounds__(256, 1) solve_emit_dmma_kernel(const double* __restrict__ L, int ld, const double* __restrict__ Linv,
+                                                                 const float* __restrict__ Cp, int n, int n_pad, int n_pres, int n_edit, int r_pad, int K,
+                                                                 float* __restrict__ Q, float* __restrict__ Qt, float* __restrict__ Qt_hi, float* __restrict__ Qt_lo) {
+    extern __shared__ double XS[];                         // [n_pad][SD_XL]
+    constexpr int NBK = UCE_NB, XL = SD_XL;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    const int m = warp & 3, grp = warp >> 2;               // 8-row tile of a block; which of the two blocks in flight (diagonal step: column tile)
+    const int k0 = blockIdx.x * SD_CW, nblk = n_pad / NBK, kb_e = n_pres / NBK;
+    for (int idx = tid; idx < n_pad * SD_CW; idx += 256) {
+        const int rr = idx / SD_CW, cc = idx % SD_CW;
+        XS[rr * XL + cc] = (rr < n && k0 + cc < K) ? (double)Cp[(long)rr * K + k0 + cc] : 0.0;
+    }
+    __syncthreads();
+    // fragments: A[g][4 ks + t], B[4 ks + t][g], C[g][2 t + {0, 1}]
+    for (int phase = 0; phase < 2; ++phase) {
+        const int kb_first = phase == 0 ? 0 : nblk - 1, kb_last = phase == 0 ? nblk - 1 : kb_e, step = phase == 0 ? 1 : -1;
+        for (int kb = kb_first; phase == 0 ? kb <= kb_last : kb >= kb_last; kb += step) {
+            const int o = kb * NBK;
+            {   // diagonal block: X_k <- Linv_kk X_k (forward) / Linv_kk^T X_k (backward); this warp: rows m, columns of tile grp
+                const double* Li = Linv + (size_t)kb * NBK * NBK;
+                double a[8], b[8];
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks) {
+                    a[ks] = phase == 0 ? Li[(m * 8 + g) * NBK + ks * 4 + t] : Li[(ks * 4 + t) * NBK + m * 8 + g];
+                    b[ks] = XS[(o + ks * 4 + t) * XL + grp * 8 + g];
+                }
+                double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0;       // two chains
+#pragma unroll
+                for (int ks = 0; ks < 8; ks += 2) { dmma884(c0, c1, a[ks], b[ks]); dmma884(e0, e1, a[ks + 1], b[ks + 1]); }
+                __syncthreads();                                    // every warp has read the old X_k
+                XS[(o + m * 8 + g) * XL + grp * 8 + 2 * t] = c0 + e0;
+                XS[(o + m * 8 + g) * XL + grp * 8 + 2 * t + 1] = c1 + e1;
+                __syncthreads();
+            }
+            // the other blocks of this column: forward X_i -= L(i, kb) Y_k for i > kb; backward Y_i -= L(kb, i)^T X_k for kb_e <= i < kb
+            const int i_lo = phase == 0 ? kb + 1 : kb_e, i_hi = phase == 0 ? nblk : kb;       // [i_lo, i_hi)
+            if (i_lo < i_hi) {
+                double yb[2][8];
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks) { yb[0][ks] = XS[(o + ks * 4 + t) * XL + g]; yb[1][ks] = XS[(o + ks * 4 + t) * XL + 8 + g]; }
+                auto load_a = [&](int i, double (&a)[8]) {
+                    const double* src = phase == 0 ? L + (size_t)(i * NBK + m * 8 + g) * ld + (size_t)o + t
+                                                   : L + (size_t)(o + t) * ld + (size_t)i * NBK + m * 8 + g;
+                    const size_t ks_stride = phase == 0 ? 4 : (size_t)4 * ld;
+#pragma unroll
+                    for (int ks = 0; ks < 8; ++ks) a[ks] = src[ks * ks_stride];
+                };
+                double pa[SD_PF][8];
+                int i_f = i_lo + grp;
+#pragma unroll
+                for (int d = 0; d < SD_PF; ++d)
+                    if (i_f < i_hi) { load_a(i_f, pa[d]); i_f += 2; }
+                for (int i = i_lo + grp; i < i_hi;) {
+#pragma unroll
+                    for (int d = 0; d < SD_PF; ++d) {
+                        if (i >= i_hi) break;
+                        double c00 = 0.0, c01 = 0.0, c10 = 0.0, c11 = 0.0;
+#pragma unroll
+                        for (int ks = 0; ks < 8; ++ks) { dmma884(c00, c01, pa[d][ks], yb[0][ks]); dmma884(c10, c11, pa[d][ks], yb[1][ks]); }
+                        if (i_f < i_hi) { load_a(i_f, pa[d]); i_f += 2; }
+                        double* x = XS + (size_t)(i * NBK + m * 8 + g) * XL + 2 * t;
+                        x[0] -= c00; x[1] -= c01; x[8] -= c10; x[9] -= c11;
+                        i += 2;
+                    }
+                }
+                __syncthreads();                                    // the column is applied: the next diagonal step reads the slab
+            }
+        }
+    }
+    for (int idx = tid; idx < r_pad * SD_CW; idx += 256) {
+        const int cc = idx / r_pad, j = idx % r_pad;
+        if (k0 + cc >= K) continue;
+        const float v = (j < n_edit) ? (float)XS[(n_pres + j) * XL + cc] : 0.f;
+        const long tq = (long)(k0 + cc) * r_pad + j;
+        uint32_t u;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
+        const float h = __uint_as_float(u);
+        Qt[tq] = v; Qt_hi[tq] = h; Qt_lo[tq] = v - h;
+        Q[(long)j * K + k0 + cc] = v;
+    }
+}
+
 #define UCE_RT(expr)                                                                             \
     do {                                                                                         \
         cudaError_t _e = (expr);                                                                 \
@@ -426,9 +519,23 @@ int factor_dev(uce_ws* ws, const float* C, const float* G, const float* scales, 
         UCE_CUDA(cudaMemcpyAsync(ws->Hcopy, ws->H, (size_t)n_pad * n_pad * sizeof(double), cudaMemcpyDeviceToDevice, st));
     }
     const size_t smem_sg = ((size_t)n_pad * (SG_CW + 1) + 2 * UCE_NB * (UCE_NB + 1)) * sizeof(double);
+    const size_t smem_sd = (size_t)n_pad * SD_XL * sizeof(double);
     const bool fused_solve = dual && smem_sg <= 200 * 1024 && getenv("UCE_GENERAL_SOLVE_GEMMS") == nullptr;
+    const bool dmma_solve = fused_solve && smem_sd <= 200 * 1024 && getenv("UCE_GENERAL_SOLVE_SIMT") == nullptr;
     bool qt_split_done = false;
-    if (fused_solve) {
+    if (dmma_solve) {
+        int rc = cholesky_solve(ws, n_pad, n_edit, ldx, 0, st, launches, /*factor_only=*/true);
+        if (rc) return rc;
+        static thread_local size_t conf_sd[64] = {0};
+        if (conf_sd[ws->device & 63] < smem_sd) {
+            UCE_CUDA(cudaFuncSetAttribute(solve_emit_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sd));
+            conf_sd[ws->device & 63] = smem_sd;
+        }
+        solve_emit_dmma_kernel<<<ceil_div(K, SD_CW), 256, smem_sd, st>>>(ws->H, n_pad, ws->Linv, ws->Cp, n, n_pad, n_pres, n_edit, ws->rank_pad, K,
+                                                                         ws->Q, ws->Qt, ws->Qt_hi, ws->Qt_lo);
+        UCE_RT(cudaGetLastError());
+        qt_split_done = true;
+    } else if (fused_solve) {
         int rc = cholesky_solve(ws, n_pad, n_edit, ldx, 0, st, launches, /*factor_only=*/true);
         if (rc) return rc;
         static thread_local size_t conf_sg[64] = {0};

@@ -19,6 +19,7 @@
 #include "uce_ws.h"
 #include "tc_common.cuh"
 #include <cstdlib>
+#include <cstring>
 
 namespace uce {
 
@@ -104,6 +105,11 @@ __device__ __forceinline__ double fs_rsqrt(double d) {
     const double y0 = (double)rsqrtf((float)d);
     const double e = fma(-(d * y0), y0, 1.0);
     return fma(y0 * e, fma(0.375, e, 0.5), y0);
+}
+
+// fp64 tensor-pipe multiply-add of one warp: D[8 x 8] += A[8 x 4] B[4 x 8];  lane = 4 g + t holds A[g][t], B[t][g], D[g][2 t + {0, 1}]
+__device__ __forceinline__ void fs_dmma884(double& d0, double& d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
 
 // (Measured and rejected: taking the pivot chain through a reciprocal — d_next = A[j+1][j+1] - A[j+1][j]^2 / d, with the reciprocal
@@ -194,7 +200,7 @@ __device__ __noinline__ void fs_trsm_row(double* __restrict__ row, const double*
 
 __global__ void __launch_bounds__(FS_T, 1)
 chol_small_kernel(double* __restrict__ Hg, int n, int n_pad, const double* __restrict__ dadd,
-                  double* __restrict__ Lg, double* __restrict__ invd_g, int write_back, int* flag, long long* __restrict__ trace) {
+                  double* __restrict__ Lg, double* __restrict__ invd_g, int write_back, int* flag, long long* __restrict__ trace, int trail_warps) {
     extern __shared__ double smem_d[];
     pdl_wait(); pdl_launch();                      // inv_blocks is launched now and parks at its own wait
     int trn = 0;
@@ -263,77 +269,72 @@ chol_small_kernel(double* __restrict__ Hg, int n, int n_pad, const double* __res
             if (tid < mb * FS_NB) fs_trsm_row(SB + fs_blk(kb + 1 + (tid >> 5), kb) + (tid & 31) * P, D, invd + o);
             __syncthreads();
             tr();   // panel done
-            // (d) trailing update of the lower block triangle:  H_ij -= L_ik L_jk^T, 4 x 4 register tiles (8 shared-memory loads
-            //     per 16 fp64 FMAs).  With LOOKAHEAD: first only the next diagonal block (64 tile tasks), then warp 0 factors it
-            //     — register resident, it hardly touches shared memory — while warps 1..15 update the other blocks.  (A
-            //     lookahead around the earlier shared-memory potrf had measured slower; this one hides 12 k of the 12-17 k
-            //     cycles of every step but the last.)
+            // (d) trailing update of the lower block triangle:  H_ij -= L_ik L_jk^T  on the fp64 tensor pipe (mma.sync m8n8k4), with
+            //     LOOKAHEAD: first only the next diagonal block — the ten 8 x 8 tiles of its lower triangle, one warp each (8 + 8
+            //     fragment loads and 8 DMMA in two chains; the SIMT form, 4 x 2 register tiles on 128 threads, took 1.7 k cycles) —
+            //     then warp 0 factors it, register resident, while warps 1..15 update the other blocks.
             const int npairs = mb * (mb + 1) / 2;
-            auto trailing_task = [&](int idx) {
-                int pr = idx >> 6, ti = 0;
-                while ((ti + 1) * (ti + 2) / 2 <= pr) ++ti;
-                const int tj = pr - ti * (ti + 1) / 2;
-                const int r0 = ((idx >> 3) & 7) * 4, c0 = (idx & 7) * 4;
-                if (ti == tj && c0 > r0 + 3) return;
-                const double* A = SB + fs_blk(kb + 1 + ti, kb) + r0 * P;
-                const double* B = SB + fs_blk(kb + 1 + tj, kb) + c0 * P;
-                double acc[4][4];
+            if (warp < 10) {
+                int tm = 0;
+                while ((tm + 1) * (tm + 2) / 2 <= warp) ++tm;
+                const int tn = warp - tm * (tm + 1) / 2, g = lane >> 2, t = lane & 3;
+                const double* A = SB + fs_blk(kb + 1, kb) + (tm * 8 + g) * P + t;
+                const double* B = SB + fs_blk(kb + 1, kb) + (tn * 8 + g) * P + t;
+                double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0;
 #pragma unroll
-                for (int i = 0; i < 4; ++i)
-#pragma unroll
-                    for (int j2 = 0; j2 < 4; ++j2) acc[i][j2] = 0.0;
-#pragma unroll 4
-                for (int j = 0; j < FS_NB; ++j) {
-                    double a[4], b[4];
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) { a[i] = A[i * P + j]; b[i] = B[i * P + j]; }
-#pragma unroll
-                    for (int i = 0; i < 4; ++i)
-#pragma unroll
-                        for (int j2 = 0; j2 < 4; ++j2) acc[i][j2] = fma(a[i], b[j2], acc[i][j2]);
-                }
-                double* Cb = SB + fs_blk(kb + 1 + ti, kb + 1 + tj);
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-#pragma unroll
-                    for (int j2 = 0; j2 < 4; ++j2)
-                        if (ti != tj || c0 + j2 <= r0 + i) Cb[(r0 + i) * P + c0 + j2] -= acc[i][j2];
-            };
-            // pair 0 = the next diagonal block (kb + 1, kb + 1), first and alone (the lookahead potrf waits for it): 4 x 2 tiles on
-            // 128 threads instead of 4 x 4 on 64 — this phase is bound by the latency of its dependent fma chains, not by throughput
-            if (tid < 128) {
-                const int r0 = (tid >> 4) * 4, c0 = (tid & 15) * 2;
-                if (c0 <= r0 + 3) {
-                    const double* A = SB + fs_blk(kb + 1, kb) + r0 * P;
-                    const double* B = SB + fs_blk(kb + 1, kb) + c0 * P;
-                    double acc[4][2] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};
-#pragma unroll 4
-                    for (int j = 0; j < FS_NB; ++j) {
-                        const double b0 = B[j], b1 = B[P + j];
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) { const double av = A[i * P + j]; acc[i][0] = fma(av, b0, acc[i][0]); acc[i][1] = fma(av, b1, acc[i][1]); }
-                    }
-                    double* Cb = SB + fs_blk(kb + 1, kb + 1);
-#pragma unroll
-                    for (int i = 0; i < 4; ++i)
-#pragma unroll
-                        for (int j2 = 0; j2 < 2; ++j2)
-                            if (c0 + j2 <= r0 + i) Cb[(r0 + i) * P + c0 + j2] -= acc[i][j2];
-                }
+                for (int ks = 0; ks < 8; ks += 2) { fs_dmma884(c0, c1, A[ks * 4], B[ks * 4]); fs_dmma884(e0, e1, A[ks * 4 + 4], B[ks * 4 + 4]); }
+                double* Cb = SB + fs_blk(kb + 1, kb + 1) + (tm * 8 + g) * P + tn * 8 + 2 * t;
+                if (tn * 8 + 2 * t <= tm * 8 + g) Cb[0] -= c0 + e0;
+                if (tn * 8 + 2 * t + 1 <= tm * 8 + g) Cb[1] -= c1 + e1;
             }
             __syncthreads();
             tr();   // next diagonal block updated
             if (warp == 0) {
                 fs_potrf_warp(SB + fs_blk(kb + 1, kb + 1), invd + o + FS_NB, lane, flag, kb + 1);
+                if (trace && lane == 0) trace[48 + kb] = clock64();
             } else {
-                for (int idx = 64 + tid - 32; idx < npairs * 64; idx += FS_T - 32) trailing_task(idx);
+                // trailing update on the fp64 tensor pipe: task = (block pair, 8-row tile); the A fragment is loaded once and swept
+                // over the pair's 8-column tiles (a diagonal pair needs the tiles on and below its diagonal only).  9 pairs at the
+                // first step = 36 tasks on 15 warps: it stays inside the shadow of warp 0's potrf (the SIMT version — 4 x 4 register
+                // tiles, 8 shared-memory loads per 16 fma — took 21.8 / 16.9 / 12.7 k cycles against the potrf's 11 k)
+                {
+                    const int g = lane >> 2, t = lane & 3;
+                    // only `trail_warps` warps, none of them on warp 0's scheduler, issue the tensor-pipe work: with all 15 the
+                    // fp64 pipe stays saturated and every fp64 instruction of the potrf chain queues behind it (trace: potrf
+                    // 22 k cycles under a 15-warp update against 11.9 k alone — the potrf IS the critical path of the phase)
+                    const int slot = (warp & 3) ? (warp >> 2) * 3 + (warp & 3) - 1 : -1;       // 0..11 for warps 1,2,3,5,6,7,...
+                    for (int task = slot; slot >= 0 && slot < trail_warps && task < (npairs - 1) * 4; task += trail_warps) {
+                        const int pr = 1 + (task >> 2), tm = task & 3;
+                        int ti = 0;
+                        while ((ti + 1) * (ti + 2) / 2 <= pr) ++ti;
+                        const int tj = pr - ti * (ti + 1) / 2;
+                        const double* A = SB + fs_blk(kb + 1 + ti, kb) + (tm * 8 + g) * P + t;
+                        double a[8];
+#pragma unroll
+                        for (int ks = 0; ks < 8; ++ks) a[ks] = A[ks * 4];
+                        const int n_tiles = (ti == tj) ? tm + 1 : 4;
+                        for (int tn = 0; tn < n_tiles; ++tn) {
+                            const double* B = SB + fs_blk(kb + 1 + tj, kb) + (tn * 8 + g) * P + t;
+                            double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0;
+#pragma unroll
+                            for (int ks = 0; ks < 8; ks += 2) { fs_dmma884(c0, c1, a[ks], B[ks * 4]); fs_dmma884(e0, e1, a[ks + 1], B[ks * 4 + 4]); }
+                            double* Cb = SB + fs_blk(kb + 1 + ti, kb + 1 + tj) + (tm * 8 + g) * P + tn * 8 + 2 * t;
+                            const bool lower = ti != tj;
+                            if (lower || tn * 8 + 2 * t <= tm * 8 + g) Cb[0] -= c0 + e0;
+                            if (lower || tn * 8 + 2 * t + 1 <= tm * 8 + g) Cb[1] -= c1 + e1;
+                        }
+                    }
+                }
+                if (trace && tid == 32) trace[32 + 3 * kb] = clock64();
                 // block column kb (L_kk and the panel below it) is final: it goes to global memory here, in the shadow of warp 0's
                 // potrf, instead of in one 4.4 k-cycle pass after the last step
                 for (int idx = tid - 32; idx < (mb + 1) * FS_NB * FS_NB; idx += FS_T - 32) {
                     const int bi = kb + (idx >> 10), rc = idx & 1023;
                     Lg[(size_t)(bi * (bi + 1) / 2 + kb) * (FS_NB * FS_NB) + rc] = SB[fs_blk(bi, kb) + (rc >> 5) * P + (rc & 31)];
                 }
+                if (trace && tid == 32) trace[33 + 3 * kb] = clock64();
                 if (mb == 1 && !write_back) zero_H(tid - 32, FS_T - 32);     // last step: these warps have no trailing update left
+                if (trace && tid == 32) trace[34 + 3 * kb] = clock64();
             }
             __syncthreads();
         }
@@ -588,6 +589,132 @@ solve_emit_kernel(const double* __restrict__ Lg, const double* __restrict__ invd
     }
 }
 
+// The same solve on the fp64 TENSOR pipe (mma.sync m8n8k4.f64).  The SIMT kernel above issues two shared-memory loads per fma and
+// is bound by shared-memory wavefronts and the latency of its dependent chains (the general path's twin measured 71 % of the
+// shared-memory pipe, 12 % of the fp64 pipe: profiles/r02_solve_general_ncu.txt).  Here a warp owns 8-row tiles: the A fragment of a
+// tile (8 x 4 of a block of L, or of the inverse of a diagonal block read through its transposed-upper-triangle storage) is eight
+// loads per thread and 32 x 32 x CW multiply-adds; the slab rows of the current block (B fragments) are read once per block step.
+// Blocks sit in shared memory with pitch 36: the 64-bit fragment loads of a warp then touch every bank pair exactly twice.
+template <int CW>
+__global__ void __launch_bounds__(SE_T, 1)
+solve_emit_dmma_kernel(const double* __restrict__ Lg, const double* __restrict__ invd_g, const float* __restrict__ Cp, int n, int n_pad,
+                       int n_pres, int n_edit, int r_pad, int K, float* __restrict__ Q, float* __restrict__ Qt, float* __restrict__ Qt_hi,
+                       float* __restrict__ Qt_lo) {
+    extern __shared__ double smem_d[];
+    constexpr int PS = 36, BLKS = FS_NB * PS, XL = CW + 4, NT = CW / 8, NW = SE_T / 32;
+    const int nblk = n_pad / FS_NB, nb = nblk * (nblk + 1) / 2;
+    double* SB = smem_d;
+    double* invd = SB + nb * BLKS;
+    double* XS = invd + n_pad;                    // [n_pad][XL]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    const int k0 = blockIdx.x * CW;
+    pdl_launch();                                  // see solve_emit_kernel: what is loaded before the wait comes from kernels that have finished
+    for (int idx = tid; idx < n_pad * CW; idx += SE_T) {
+        const int r = idx / CW, c = idx % CW;
+        XS[r * XL + c] = (r < n && k0 + c < K) ? (double)Cp[(long)r * K + k0 + c] : 0.0;
+    }
+    auto is_diag = [](int b) { int kb = 0; while ((kb + 1) * (kb + 2) / 2 <= b) ++kb; return b == kb * (kb + 1) / 2 + kb; };
+    const double2* L2 = reinterpret_cast<const double2*>(Lg);
+    const int n2 = nb * FS_NB * FS_NB / 2;
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {         // 0: off-diagonal blocks (before the wait), 1: diagonal blocks
+        if (pass == 1) pdl_wait();
+        for (int i0 = tid; i0 < n2; i0 += 8 * SE_T) {
+            double2 v[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int idx = i0 + q * SE_T;
+                v[q] = (idx < n2 && is_diag((2 * idx) >> 10) == (pass == 1)) ? L2[idx] : make_double2(0.0, 0.0);
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int idx = i0 + q * SE_T;
+                if (idx < n2) {
+                    const int e = 2 * idx, b = e >> 10, rc = e & 1023;
+                    if (is_diag(b) == (pass == 1)) {
+                        double* d = SB + b * BLKS + (rc >> 5) * PS + (rc & 31);
+                        d[0] = v[q].x; d[1] = v[q].y;
+                    }
+                }
+            }
+        }
+        if (pass == 0) for (int r = tid; r < n_pad; r += SE_T) invd[r] = invd_g[r];
+    }
+    __syncthreads();
+    auto blk = [&](int bi, int bj) { return SB + (bi * (bi + 1) / 2 + bj) * BLKS; };
+    const int kb_e = n_pres / FS_NB;
+    // fragments: A[g][4 ks + t], B[4 ks + t][g], C[g][2 t + {0, 1}]
+#pragma unroll 1
+    for (int phase = 0; phase < 2; ++phase) {      // 0 forward  L Y = Cp;  1 backward  L^T X = Y, down to the block row of the first edit row
+#pragma unroll 1
+        for (int kb = phase == 0 ? 0 : nblk - 1; phase == 0 ? kb < nblk : kb >= kb_e; kb += phase == 0 ? 1 : -1) {
+            const int o = kb * FS_NB;
+            const double* D = blk(kb, kb);
+            double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0;
+            const int dm = warp & 3, dnt = warp >> 2;            // diagonal step: 8-row tile, 8-column tile
+            if (dnt < NT) {
+                const int r = dm * 8 + g;
+                double a[8], b[8];
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks) {
+                    const int j = ks * 4 + t;
+                    // forward: (L^-1)[r][j], stored transposed in the strict upper triangle; backward: (L^-T)[r][j] = (L^-1)[j][r]
+                    const double off = phase == 0 ? D[j * PS + r] : D[r * PS + j];
+                    const bool strict = phase == 0 ? (j < r) : (r < j);
+                    a[ks] = strict ? off : (j == r ? invd[o + r] : 0.0);
+                    b[ks] = XS[(o + j) * XL + dnt * 8 + g];
+                }
+#pragma unroll
+                for (int ks = 0; ks < 8; ks += 2) { fs_dmma884(c0, c1, a[ks], b[ks]); fs_dmma884(e0, e1, a[ks + 1], b[ks + 1]); }
+            }
+            __syncthreads();                                     // every warp has read the old X_k
+            if (dnt < NT) {
+                XS[(o + dm * 8 + g) * XL + dnt * 8 + 2 * t] = c0 + e0;
+                XS[(o + dm * 8 + g) * XL + dnt * 8 + 2 * t + 1] = c1 + e1;
+            }
+            __syncthreads();
+            const int i_lo = phase == 0 ? kb + 1 : kb_e, i_hi = phase == 0 ? nblk : kb;       // the other blocks of this column
+            if (i_lo < i_hi) {
+                double yb[NT][8];
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                    for (int ks = 0; ks < 8; ++ks) yb[nt][ks] = XS[(o + ks * 4 + t) * XL + nt * 8 + g];
+                for (int tile = warp; tile < (i_hi - i_lo) * 4; tile += NW) {
+                    const int i = i_lo + (tile >> 2), m = tile & 3;
+                    // forward  X_i -= L(i, kb) Y_k:  A[r][j] = block(i, kb)[r][j];  backward  Y_i -= L(kb, i)^T X_k:  A[r][j] = block(kb, i)[j][r]
+                    const double* A = phase == 0 ? blk(i, kb) + (m * 8 + g) * PS + t : blk(kb, i) + t * PS + m * 8 + g;
+                    const int ks_stride = phase == 0 ? 4 : 4 * PS;
+                    double a[8];
+#pragma unroll
+                    for (int ks = 0; ks < 8; ++ks) a[ks] = A[ks * ks_stride];
+                    double acc[NT][2];
+#pragma unroll
+                    for (int nt = 0; nt < NT; ++nt) { acc[nt][0] = 0.0; acc[nt][1] = 0.0; }
+#pragma unroll
+                    for (int ks = 0; ks < 8; ++ks)
+#pragma unroll
+                        for (int nt = 0; nt < NT; ++nt) fs_dmma884(acc[nt][0], acc[nt][1], a[ks], yb[nt][ks]);
+                    double* x = XS + (i * FS_NB + m * 8 + g) * XL + 2 * t;
+#pragma unroll
+                    for (int nt = 0; nt < NT; ++nt) { x[nt * 8] -= acc[nt][0]; x[nt * 8 + 1] -= acc[nt][1]; }
+                }
+                __syncthreads();
+            }
+        }
+    }
+    // ---- emit: Q [r_pad, K] row-major, Qt [K, r_pad] and its tf32 split; rows j >= n_edit (rank padding) are exact zeros ----
+    for (int idx = tid; idx < r_pad * CW; idx += SE_T) {
+        const int cc = idx / r_pad, j = idx % r_pad;
+        if (k0 + cc >= K) continue;
+        const float v = (j < n_edit) ? (float)XS[(n_pres + j) * XL + cc] : 0.f;
+        const long tq = (long)(k0 + cc) * r_pad + j;
+        const float h = fs_tf32_hi(v);
+        Qt[tq] = v; Qt_hi[tq] = h; Qt_lo[tq] = v - h;
+        Q[(long)j * K + k0 + cc] = v;
+    }
+}
+
 // E = G_e - C_e with its tf32 split, and the packed concept rows; one block per row.
 __device__ void pack_rows_split_block(int r, const float* __restrict__ C, const float* __restrict__ G, const int* __restrict__ src, int n_act,
                                       int n_pres, int rank_pad, int K, float* __restrict__ Cp, float* __restrict__ E,
@@ -661,8 +788,9 @@ int factor_small(uce_ws* ws, const float* C, const float* G, int n, int n_pres, 
     const char* trace_path = getenv("UCE_CHOL_TRACE");
     if (trace_path) { UCE_CUDA(cudaMalloc(&trace, 64 * sizeof(long long))); UCE_CUDA(cudaMemsetAsync(trace, 0, 64 * sizeof(long long), st)); }
     static_assert(FS_MAX_N == 160, "ws->Lsmall is sized for 15 blocks + 160 reciprocals");
+    static const int trail_warps = [] { const char* e = getenv("UCE_CHOL_TRAIL_WARPS"); const int v = e ? atoi(e) : 6; return v < 1 ? 1 : (v > 12 ? 12 : v); }();
     double* Lg = ws->Lsmall; double* invd_g = ws->Lsmall + 15 * 1024;
-    UCE_CUDA(launch_k(chol_small_kernel, dim3(1), dim3(FS_T), smem_c, st, 1, ws->H, n, n_pad, (const double*)ws->diag_add, Lg, invd_g, (int)ws->debug, ws->flag, trace));
+    UCE_CUDA(launch_k(chol_small_kernel, dim3(1), dim3(FS_T), smem_c, st, 1, ws->H, n, n_pad, (const double*)ws->diag_add, Lg, invd_g, (int)ws->debug, ws->flag, trace, trail_warps));
     ++*launches;
     ws->H_dirty = ws->debug ? 1 : 0;
     // the apply's first kernel goes to its own stream now (the host encodes it while the single-CTA factor runs); this stream waits for
@@ -679,14 +807,37 @@ int factor_small(uce_ws* ws, const float* C, const float* G, int n, int n_pres, 
         UCE_CUDA(cudaMemcpy(h, trace, sizeof(h), cudaMemcpyDeviceToHost));
         UCE_CUDA(cudaFree(trace));
         if (FILE* f = fopen(trace_path, "w")) {
-            for (int i = 0; i < 64 && h[i]; ++i) fprintf(f, "%d %lld %lld\n", i, h[i] - h[0], i ? h[i] - h[i - 1] : 0LL);
+            for (int i = 0; i < 32 && h[i]; ++i) fprintf(f, "%d %lld %lld\n", i, h[i] - h[0], i ? h[i] - h[i - 1] : 0LL);
+            // inside the lookahead phases: 32 + 3 kb: warp 1 done with the trailing update, + 1: with the write-out, + 2: with clearing H; 48 + kb: warp 0's potrf done
+            for (int i = 32; i < 64; ++i) if (h[i]) fprintf(f, "%d %lld\n", i, h[i] - h[0]);
             fclose(f);
         }
     }
     UCE_CUDA(launch_k(inv_blocks_kernel, dim3(nt), dim3(FS_T), 0, st, 1, Lg, (const double*)invd_g));
     ++*launches;
-    UCE_CUDA(launch_k(solve_emit_kernel, dim3(ceil_div(K, SE_CW)), dim3(SE_T), smem_s, st, 1, (const double*)Lg, (const double*)invd_g, (const float*)ws->Cp, n, n_pad,
-                      n_pres, n_edit, ws->rank_pad, K, ws->Q, ws->Qt, ws->Qt_hi, ws->Qt_lo));
+    // solve: fp64 tensor-pipe kernel, 8 columns of Cp per CTA (cfg2 step: 0.1268 ms; 16 columns 0.1299; the SIMT version 0.1315 —
+    // UCE_SOLVE_EMIT=16 / simt select those for comparison)
+    static const int se_mode = [] { const char* e = getenv("UCE_SOLVE_EMIT"); return !e ? 8 : (!strcmp(e, "simt") ? 0 : (!strcmp(e, "16") ? 16 : 8)); }();
+    if (se_mode == 0) {
+        UCE_CUDA(launch_k(solve_emit_kernel, dim3(ceil_div(K, SE_CW)), dim3(SE_T), smem_s, st, 1, (const double*)Lg, (const double*)invd_g, (const float*)ws->Cp, n, n_pad,
+                          n_pres, n_edit, ws->rank_pad, K, ws->Q, ws->Qt, ws->Qt_hi, ws->Qt_lo));
+    } else {
+        const int cw = se_mode;
+        const size_t smem_d = ((size_t)(nt * (nt + 1) / 2) * FS_NB * 36 + n_pad + (size_t)n_pad * (cw + 4)) * sizeof(double);
+        static thread_local size_t conf_dev_d[2][64] = {{0}, {0}};
+        size_t& conf_d = conf_dev_d[cw == 16][ws->device & 63];
+        if (conf_d < smem_d) {
+            if (cw == 16) UCE_CUDA(cudaFuncSetAttribute(solve_emit_dmma_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_d));
+            else UCE_CUDA(cudaFuncSetAttribute(solve_emit_dmma_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_d));
+            conf_d = smem_d;
+        }
+        if (cw == 16)
+            UCE_CUDA(launch_k(solve_emit_dmma_kernel<16>, dim3(ceil_div(K, 16)), dim3(SE_T), smem_d, st, 1, (const double*)Lg, (const double*)invd_g, (const float*)ws->Cp,
+                              n, n_pad, n_pres, n_edit, ws->rank_pad, K, ws->Q, ws->Qt, ws->Qt_hi, ws->Qt_lo));
+        else
+            UCE_CUDA(launch_k(solve_emit_dmma_kernel<8>, dim3(ceil_div(K, 8)), dim3(SE_T), smem_d, st, 1, (const double*)Lg, (const double*)invd_g, (const float*)ws->Cp,
+                              n, n_pad, n_pres, n_edit, ws->rank_pad, K, ws->Q, ws->Qt, ws->Qt_hi, ws->Qt_lo));
+    }
     ++*launches;
     return 0;
 }

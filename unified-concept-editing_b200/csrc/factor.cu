@@ -83,42 +83,6 @@ __global__ void fill_rhs_kernel(double* X, int ldx, int n_pad, int n_rhs, int n_
     X[(long)r * ldx + j] = v;
 }
 
-// Factor one NB x NB diagonal block in place (lower) and emit its inverse.
-__global__ void __launch_bounds__(UCE_NB* UCE_NB) potrf_diag_kernel(double* H, int ld, int kb, double* Linv, int* flag) {
-    __shared__ double a[UCE_NB][UCE_NB + 1];
-    __shared__ double inv[UCE_NB][UCE_NB + 1];
-    const int tx = threadIdx.x, ty = threadIdx.y;
-    double* blk = H + (long)kb * UCE_NB * ld + (long)kb * UCE_NB;
-    a[ty][tx] = blk[(long)ty * ld + tx];
-    for (int j = 0; j < UCE_NB; ++j) {
-        __syncthreads();
-        if (tx == j && ty == j) {
-            double p = a[j][j];
-            if (!(p > 0.0)) { atomicCAS(flag, 0, 1 + kb); p = 1.0; }
-            a[j][j] = sqrt(p);
-        }
-        __syncthreads();
-        if (tx == j && ty > j) a[ty][j] /= a[j][j];
-        __syncthreads();
-        if (tx > j && ty >= tx) a[ty][tx] -= a[ty][j] * a[tx][j];
-    }
-    __syncthreads();
-    // inverse of the lower-triangular block: thread (ty == 0, tx = c) solves column c
-    if (ty == 0) {
-        const int c = tx;
-        for (int i = 0; i < c; ++i) inv[i][c] = 0.0;
-        inv[c][c] = 1.0 / a[c][c];
-        for (int i = c + 1; i < UCE_NB; ++i) {
-            double s = 0.0;
-            for (int j = c; j < i; ++j) s += a[i][j] * inv[j][c];
-            inv[i][c] = -s / a[i][i];
-        }
-    }
-    __syncthreads();
-    blk[(long)ty * ld + tx] = (tx <= ty) ? a[ty][tx] : 0.0;
-    Linv[((long)kb * UCE_NB + ty) * UCE_NB + tx] = inv[ty][tx];
-}
-
 // Q[j,k] (f32, ld K) and Qt[k,j] (f32, ld rank_pad) from the fp64 solution.
 //   dual  : handled by GEMM (Q = X^T Cp), this kernel only transposes Q -> Qt
 //   primal: X = Q^T [K_pad, n_rhs] -> both
@@ -384,8 +348,7 @@ static int cholesky_solve(uce_ws* ws, int n_pad, int n_rhs, int ldx, int fwd_fro
     const int nb = UCE_NB, nblk = n_pad / nb, ld = n_pad;
     double* H = ws->H; double* X = ws->X; double* Linv = ws->Linv;
     for (int k = 0; k < nblk; ++k) {
-        if (getenv("UCE_OLD_POTRF")) { potrf_diag_kernel<<<1, dim3(nb, nb), 0, st>>>(H, ld, k, Linv, ws->flag); UCE_RT(cudaGetLastError()); }
-        else UCE_RT((cudaError_t)potrf_inv_general(H, ld, k, Linv, ws->flag, st));
+        UCE_RT((cudaError_t)potrf_inv_general(H, ld, k, Linv, ws->flag, st));      // diagonal block: factor in place + dense inverse (factor_small.cu)
         int rest = n_pad - (k + 1) * nb;
         if (rest > 0) {
             double* panel = H + (long)(k + 1) * nb * ld + (long)k * nb;            // [rest, nb], ld

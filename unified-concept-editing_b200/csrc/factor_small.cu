@@ -1,18 +1,19 @@
 // Low-latency path of the shared factor for the common case n <= 160 concept rows (dual system, n <= K):
-// 3 kernels instead of the ~35 launches of the general blocked path in factor.cu.
+// five kernels that hand over by programmatic dependent launch, instead of the ~100 launches of the general blocked path in factor.cu.
 //
+//   factor_tables (factor.cu) row order, diagonal terms, status flag — as kernel parameters
 //   gram_pack     H = Cp Cp^T, fp64 accumulation of exact fp32 products, 32x32 tiles x split-K over many CTAs; the same launch packs
 //                 the concept rows (Cp) and E = G_e - C_e with its tf32 split in extra blocks (the Gram blocks read C directly)
 //   chol_small    ONE CTA: H (+ lamb/s on the diagonal) into shared memory (lower block triangle), blocked Cholesky
-//                 (NB = 32: left-looking factorisation of the diagonal block by one warp, panel by per-row forward
-//                 substitution, trailing update by all 512 threads with the next diagonal block first — lookahead);
-//                 the factor L goes back to global memory
+//                 (NB = 32: factorisation of the diagonal block by one warp, panel by per-row forward substitution, trailing
+//                 update on the fp64 tensor pipe with the next diagonal block first — lookahead); L goes back to global memory
+//                 and H is left cleared for the next factor
 //   inv_blocks    one CTA per diagonal block: L_kk^-1 (column sweeps), in place in the global factor
 //   solve_emit    MANY CTAs, one per 8 columns of K:  X = H^-1 Cp[:, cols]  by blocked forward substitution and the
-//                 part of the backward substitution that reaches the edit rows (they are the LAST rows), all in
-//                 shared memory; the edit rows of X are Q[:, cols] (H^-1 is symmetric:  Q = J H^-1 Cp) -> Q, Qt and the
-//                 TF32 hi/lo splits consumed by the tcgen05 apply.  (The single-CTA substitution on the n_edit unit
-//                 vectors followed by a Q = Z^T Cp kernel that this replaces cost 26 + 10 us of the 147 us factor.)
+//                 part of the backward substitution that reaches the edit rows (they are the LAST rows), on the fp64 tensor
+//                 pipe; the edit rows of X are Q[:, cols] (H^-1 is symmetric:  Q = J H^-1 Cp) -> Q, Qt and the
+//                 TF32 hi/lo splits consumed by the tcgen05 apply.
+//   (+ potrf_inv_general: the diagonal-block step of the general path, built from the same pieces)
 //
 // Same algebra and same fp64 precision as the general path (trainscripts/uce_sd_erase.py:63,71,79,82 — the
 // mat2 accumulation and its inverse — done once per edit).
@@ -158,17 +159,6 @@ __device__ __noinline__ void fs_potrf_warp(double* __restrict__ D, double* __res
 #pragma unroll 1
     for (int j = 24; j < 32; ++j) d = fs_potrf_step<7>(a, D, invd_blk, lane, j, d, bad);
     if (bad && lane == 0) atomicCAS(flag, 0, 1 + kb);
-}
-
-// Dense copy of the inverse of one factored diagonal block:  TS[c][r] = (L^-1)[r][c] — the strict upper triangle of D as the
-// block inverse left it, 1 / L_cc on the diagonal, explicit zeros below.  The panel and the triangular multiplies of the
-// substitutions then run plain dense inner loops: with the triangle applied as a per-element select those loops were bound by
-// instruction issue (two selects and a compare per 64-bit coefficient: 5.5 k cycles per 32 x 32 x 64 multiply, measured).
-__device__ __forceinline__ void fs_build_ts(double* __restrict__ TS, const double* __restrict__ D, const double* __restrict__ invd_blk, int tid, int nthreads = FS_T) {
-    for (int idx = tid; idx < FS_NB * FS_NB; idx += nthreads) {
-        const int c = idx >> 5, r = idx & 31;
-        TS[c * (FS_NB + 1) + r] = (c < r) ? D[c * (FS_NB + 1) + r] : ((c == r) ? invd_blk[c] : 0.0);
-    }
 }
 
 // Panel row by forward substitution:  x L_kk^T = h  for ONE row h of the panel (thread = row; the row lives in registers and
@@ -361,7 +351,7 @@ chol_small_kernel(double* __restrict__ Hg, int n, int n_pad, const double* __res
 
 // ---------------------------------------------------------------------------------------------------------
 // Inverses of the diagonal blocks of L, one CTA per block, in place in the global copy of the factor: the strictly-lower part of
-// L_kk^-1 goes, transposed, into the strict upper triangle of the block (solve_emit reads it through fs_build_ts).  Column sweeps
+// L_kk^-1 goes, transposed, into the strict upper triangle of the block (the solve kernel reads its A fragments straight from that storage).  Column sweeps
 // (lane = row): x_j = (delta_jc - acc_j) / L_jj; a warp carries its two columns (c, c + 16) through ONE sweep: the second chain is
 // identically zero until j reaches c + 16.  Off the single-CTA kernel's critical path: all blocks at once, 4.5 k cycles.
 __global__ void __launch_bounds__(FS_T, 1) inv_blocks_kernel(double* __restrict__ Lg, const double* __restrict__ invd_g) {
@@ -438,160 +428,10 @@ int potrf_inv_general(double* H, int ld, int kb, double* Linv, int* flag, cudaSt
 // X = H^-1 Cp[:, cols] for one slab of SE_CW columns, then Q[j, cols] = X[n_pres + j, cols]  (see the file header).
 //   forward   L Y = Cp[:, cols]        over all block rows
 //   backward  L^T X = Y                from the last block row up to the block row of the first edit row
-// Everything in shared memory: the block triangle of L (pitch 33, as chol_small keeps it), a dense copy TS of the current
-// diagonal block's inverse, the slab XS [n_pad][SE_CW + 1].  256 threads:
-//   triangular multiply of a 32 x SE_CW block: one output per thread;  update of the rows below / above: 4 rows x 1 column per
-//   thread (the L coefficients are warp broadcasts, the slab entries consecutive doubles).  K / 8 CTAs (96 for SD-1.4): the work per
-//   CTA is small next to the fixed cost of fetching L (120 KB from L2), so narrower slabs on more SMs win (16 columns: 21 us).
-constexpr int SE_CW = 8;
 constexpr int SE_T = 256;
-__global__ void __launch_bounds__(SE_T, 1)
-solve_emit_kernel(const double* __restrict__ Lg, const double* __restrict__ invd_g, const float* __restrict__ Cp, int n, int n_pad,
-                  int n_pres, int n_edit, int r_pad, int K, float* __restrict__ Q, float* __restrict__ Qt, float* __restrict__ Qt_hi,
-                  float* __restrict__ Qt_lo) {
-    extern __shared__ double smem_d[];
-    constexpr int P = FS_NB + 1, XL = SE_CW + 1;
-    const int nblk = n_pad / FS_NB, nb = nblk * (nblk + 1) / 2;
-    double* SB = smem_d;
-    double* invd = SB + nb * FS_BLK;
-    double* TS = invd + n_pad;
-    double* XS = TS + FS_BLK;                     // [n_pad][XL]
-    const int tid = threadIdx.x;
-    const int k0 = blockIdx.x * SE_CW;
-    // Launched (programmatically) while inv_blocks still runs: the slab, the reciprocals and the off-diagonal blocks of L come from
-    // kernels that had finished before inv_blocks passed its own wait and are loaded right away; the diagonal blocks (inverted in
-    // place by inv_blocks) after the wait.  The apply's second kernel is launched by the trigger below and prefetches beside us.
-    pdl_launch();
-    for (int idx = tid; idx < n_pad * SE_CW; idx += SE_T) {
-        const int r = idx / SE_CW, c = idx % SE_CW;
-        XS[r * XL + c] = (r < n && k0 + c < K) ? (double)Cp[(long)r * K + k0 + c] : 0.0;
-    }
-    auto is_diag = [](int b) { int kb = 0; while ((kb + 1) * (kb + 2) / 2 <= b) ++kb; return b == kb * (kb + 1) / 2 + kb; };
-    const double2* L2 = reinterpret_cast<const double2*>(Lg);
-    const int n2 = nb * FS_NB * FS_NB / 2;
-#pragma unroll 1
-    for (int pass = 0; pass < 2; ++pass) {         // 0: off-diagonal blocks (before the wait), 1: diagonal blocks
-        if (pass == 1) pdl_wait();
-        for (int i0 = tid; i0 < n2; i0 += 8 * SE_T) {        // 16-byte loads, eight in flight per thread
-            double2 v[8];
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                const int idx = i0 + q * SE_T;
-                // plain loads: the diagonal blocks are rewritten by the kernel running beside this one (no read-only cache path)
-                v[q] = (idx < n2 && is_diag((2 * idx) >> 10) == (pass == 1)) ? L2[idx] : make_double2(0.0, 0.0);
-            }
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                const int idx = i0 + q * SE_T;
-                if (idx < n2) {
-                    const int e = 2 * idx, b = e >> 10, rc = e & 1023;
-                    if (is_diag(b) == (pass == 1)) {
-                        double* d = SB + b * FS_BLK + (rc >> 5) * P + (rc & 31);
-                        d[0] = v[q].x; d[1] = v[q].y;
-                    }
-                }
-            }
-        }
-        if (pass == 0) for (int r = tid; r < n_pad; r += SE_T) invd[r] = invd_g[r];
-    }
-    __syncthreads();
-    const int c = tid & (SE_CW - 1), rq = tid / SE_CW;        // column of the slab; row (triangular multiply) or row quad (updates)
-    // ---- forward ----
-    for (int kb = 0; kb < nblk; ++kb) {
-        const double* D = SB + fs_blk(kb, kb);
-        const int o = kb * FS_NB;
-        fs_build_ts(TS, D, invd + o, tid, SE_T);
-        __syncthreads();
-        double y0 = 0.0, y1 = 0.0, y2 = 0.0, y3 = 0.0;        // Y_k = L_kk^-1 X_k:  (L^-1)[r][j] = TS[j][r]
-#pragma unroll
-        for (int j = 0; j < FS_NB; j += 4) {                  // four partial sums: a dependent fp64 fma costs ~35 cycles on this part
-            y0 = fma(TS[j * P + rq], XS[(o + j) * XL + c], y0);
-            y1 = fma(TS[(j + 1) * P + rq], XS[(o + j + 1) * XL + c], y1);
-            y2 = fma(TS[(j + 2) * P + rq], XS[(o + j + 2) * XL + c], y2);
-            y3 = fma(TS[(j + 3) * P + rq], XS[(o + j + 3) * XL + c], y3);
-        }
-        __syncthreads();
-        XS[(o + rq) * XL + c] = (y0 + y1) + (y2 + y3);
-        __syncthreads();
-        const int rows_below = n_pad - o - FS_NB;
-        if (4 * rq < rows_below) {                            // X_i -= L_ik Y_k for the block rows below
-            const int r = o + FS_NB + 4 * rq;
-            const double* A = SB + fs_blk(r >> 5, kb) + (r & 31) * P;
-            double s4[4][4];                                  // four partial sums per row: sixteen independent fma chains
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int q = 0; q < 4; ++q) s4[i][q] = 0.0;
-#pragma unroll
-            for (int j = 0; j < FS_NB; j += 4) {
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const double x = XS[(o + j + q) * XL + c];
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) s4[i][q] = fma(A[i * P + j + q], x, s4[i][q]);
-                }
-            }
-#pragma unroll
-            for (int i = 0; i < 4; ++i) XS[(r + i) * XL + c] -= (s4[i][0] + s4[i][1]) + (s4[i][2] + s4[i][3]);
-        }
-        __syncthreads();
-    }
-    // ---- backward, down to the block row that holds the first edit row ----
-    const int kb_e = n_pres / FS_NB;
-    for (int kb = nblk - 1; kb >= kb_e; --kb) {
-        const double* D = SB + fs_blk(kb, kb);
-        const int o = kb * FS_NB;
-        fs_build_ts(TS, D, invd + o, tid, SE_T);
-        __syncthreads();
-        double y0 = 0.0, y1 = 0.0, y2 = 0.0, y3 = 0.0;        // X_k = L_kk^-T Y_k:  (L^-T)[r][j] = (L^-1)[j][r] = TS[r][j]
-#pragma unroll
-        for (int j = 0; j < FS_NB; j += 4) {
-            y0 = fma(TS[rq * P + j], XS[(o + j) * XL + c], y0);
-            y1 = fma(TS[rq * P + j + 1], XS[(o + j + 1) * XL + c], y1);
-            y2 = fma(TS[rq * P + j + 2], XS[(o + j + 2) * XL + c], y2);
-            y3 = fma(TS[rq * P + j + 3], XS[(o + j + 3) * XL + c], y3);
-        }
-        __syncthreads();
-        XS[(o + rq) * XL + c] = (y0 + y1) + (y2 + y3);
-        __syncthreads();
-        const int rows_above = o - kb_e * FS_NB;
-        if (4 * rq < rows_above) {                            // Y_i -= L_ki^T X_k for the block rows above (down to kb_e)
-            const int r = kb_e * FS_NB + 4 * rq;
-            const double* A = SB + fs_blk(kb, r >> 5) + (r & 31);            // L[o + j][r + i] = block(kb, r/32)[j][r%32 + i]
-            double s4[4][4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int q = 0; q < 4; ++q) s4[i][q] = 0.0;
-#pragma unroll
-            for (int j = 0; j < FS_NB; j += 4) {
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const double x = XS[(o + j + q) * XL + c];
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) s4[i][q] = fma(A[(j + q) * P + i], x, s4[i][q]);
-                }
-            }
-#pragma unroll
-            for (int i = 0; i < 4; ++i) XS[(r + i) * XL + c] -= (s4[i][0] + s4[i][1]) + (s4[i][2] + s4[i][3]);
-        }
-        __syncthreads();
-    }
-    // ---- emit: Q [r_pad, K] row-major, Qt [K, r_pad] and its tf32 split; rows j >= n_edit (rank padding) are exact zeros ----
-    for (int idx = tid; idx < r_pad * SE_CW; idx += SE_T) {
-        const int cc = idx / r_pad, j = idx % r_pad;          // consecutive threads: consecutive j -> coalesced Qt stores
-        if (k0 + cc >= K) continue;
-        const float v = (j < n_edit) ? (float)XS[(n_pres + j) * XL + cc] : 0.f;
-        const long t = (long)(k0 + cc) * r_pad + j;
-        const float h = fs_tf32_hi(v);
-        Qt[t] = v; Qt_hi[t] = h; Qt_lo[t] = v - h;
-        Q[(long)j * K + k0 + cc] = v;
-    }
-}
-
-// The same solve on the fp64 TENSOR pipe (mma.sync m8n8k4.f64).  The SIMT kernel above issues two shared-memory loads per fma and
-// is bound by shared-memory wavefronts and the latency of its dependent chains (the general path's twin measured 71 % of the
-// shared-memory pipe, 12 % of the fp64 pipe: profiles/r02_solve_general_ncu.txt).  Here a warp owns 8-row tiles: the A fragment of a
+// The solve on the fp64 TENSOR pipe (mma.sync m8n8k4.f64).  Its SIMT predecessor issued two shared-memory loads per fma and was bound by
+// shared-memory wavefronts and the latency of its dependent chains (the general path's twin measured 71 % of the shared-memory pipe,
+// 12 % of the fp64 pipe: profiles/r02_solve_general_ncu.txt; cfg2 step 0.1315 ms with it, 0.1268 with this one).  A warp owns 8-row tiles: the A fragment of a
 // tile (8 x 4 of a block of L, or of the inverse of a diagonal block read through its transposed-upper-triangle storage) is eight
 // loads per thread and 32 x 32 x CW multiply-adds; the slab rows of the current block (B fragments) are read once per block step.
 // Blocks sit in shared memory with pitch 36: the 64-bit fragment loads of a warp then touch every bank pair exactly twice.
@@ -608,7 +448,10 @@ solve_emit_dmma_kernel(const double* __restrict__ Lg, const double* __restrict__
     double* XS = invd + n_pad;                    // [n_pad][XL]
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
     const int k0 = blockIdx.x * CW;
-    pdl_launch();                                  // see solve_emit_kernel: what is loaded before the wait comes from kernels that have finished
+    // Launched (programmatically) while inv_blocks still runs: the slab, the reciprocals and the off-diagonal blocks of L come from
+    // kernels that had finished before inv_blocks passed its own wait and are loaded right away; the diagonal blocks (inverted in
+    // place by inv_blocks) after the wait.  The apply's second kernel is launched by the trigger below and prefetches beside us.
+    pdl_launch();
     for (int idx = tid; idx < n_pad * CW; idx += SE_T) {
         const int r = idx / CW, c = idx % CW;
         XS[r * XL + c] = (r < n && k0 + c < K) ? (double)Cp[(long)r * K + k0 + c] : 0.0;
@@ -771,18 +614,11 @@ int factor_small(uce_ws* ws, const float* C, const float* G, int n, int n_pres, 
     }
     // + 8 rows of slack: the last pivots of a diagonal block read L[j + k][j] for rows up to 38 (columns that do not exist, results unused)
     const size_t smem_c = ((size_t)(nt * (nt + 1) / 2) * FS_BLK + n_pad + FS_BLK + 8 * (FS_NB + 1)) * sizeof(double);
-    const size_t smem_s = ((size_t)(nt * (nt + 1) / 2) * FS_BLK + n_pad + FS_BLK + (size_t)n_pad * (SE_CW + 1)) * sizeof(double);
     static thread_local size_t conf_dev[64] = {0};        // per-device function attribute
     size_t& conf_c = conf_dev[ws->device & 63];
     if (conf_c < smem_c) {
         UCE_CUDA(cudaFuncSetAttribute(chol_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
         conf_c = smem_c;
-    }
-    static thread_local size_t conf_dev_s[64] = {0};
-    size_t& conf_s = conf_dev_s[ws->device & 63];
-    if (conf_s < smem_s) {
-        UCE_CUDA(cudaFuncSetAttribute(solve_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s));
-        conf_s = smem_s;
     }
     long long* trace = nullptr;
     const char* trace_path = getenv("UCE_CHOL_TRACE");
@@ -815,14 +651,10 @@ int factor_small(uce_ws* ws, const float* C, const float* G, int n, int n_pres, 
     }
     UCE_CUDA(launch_k(inv_blocks_kernel, dim3(nt), dim3(FS_T), 0, st, 1, Lg, (const double*)invd_g));
     ++*launches;
-    // solve: fp64 tensor-pipe kernel, 8 columns of Cp per CTA (cfg2 step: 0.1268 ms; 16 columns 0.1299; the SIMT version 0.1315 —
-    // UCE_SOLVE_EMIT=16 / simt select those for comparison)
-    static const int se_mode = [] { const char* e = getenv("UCE_SOLVE_EMIT"); return !e ? 8 : (!strcmp(e, "simt") ? 0 : (!strcmp(e, "16") ? 16 : 8)); }();
-    if (se_mode == 0) {
-        UCE_CUDA(launch_k(solve_emit_kernel, dim3(ceil_div(K, SE_CW)), dim3(SE_T), smem_s, st, 1, (const double*)Lg, (const double*)invd_g, (const float*)ws->Cp, n, n_pad,
-                          n_pres, n_edit, ws->rank_pad, K, ws->Q, ws->Qt, ws->Qt_hi, ws->Qt_lo));
-    } else {
-        const int cw = se_mode;
+    // solve: 8 columns of Cp per CTA (cfg2 step 0.1268 ms; 16 columns, UCE_SOLVE_EMIT=16: 0.1299)
+    static const int se_cw = [] { const char* e = getenv("UCE_SOLVE_EMIT"); return (e && !strcmp(e, "16")) ? 16 : 8; }();
+    {
+        const int cw = se_cw;
         const size_t smem_d = ((size_t)(nt * (nt + 1) / 2) * FS_NB * 36 + n_pad + (size_t)n_pad * (cw + 4)) * sizeof(double);
         static thread_local size_t conf_dev_d[2][64] = {{0}, {0}};
         size_t& conf_d = conf_dev_d[cw == 16][ws->device & 63];

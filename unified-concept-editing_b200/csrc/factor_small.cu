@@ -166,26 +166,29 @@ __device__ __noinline__ void fs_potrf_warp(double* __restrict__ D, double* __res
 // L_kk[j + k][j] are warp-wide broadcasts from shared memory.  Per step: one multiply (x_j = h_j / L_jj) and KM independent fmas.
 // This replaces "explicit inverse of L_kk (4.5 k cycles, all warps, a 32-step serial chain) + dense multiply (2.3-7.2 k cycles)" of
 // every block step by one 2.5 k-cycle phase; the inverses, which only the solve kernel needs, moved to their own small kernel.
+// LS is the diagonal block with every row scaled by the reciprocal of its diagonal entry, LS[c][j] = L_kk[c][j] / L_kk[c][c]: with the
+// right-hand side scaled the same way (a_c = h_c / L_cc) a step is  x_j = a_0  and  a_c -= x_j LS[c][j] — ONE dependent fp64
+// operation per step on the chain of 32 instead of two (multiply by 1 / L_jj, then the fma): 5.5 k -> ~3 k cycles per panel.
 template <int KM>
-__device__ __forceinline__ void fs_trsm_step(double (&a)[FS_NB], const double* __restrict__ D, const double* __restrict__ invd_blk, double* __restrict__ row, int j) {
-    const double x = a[0] * invd_blk[j];
+__device__ __forceinline__ void fs_trsm_step(double (&a)[FS_NB], const double* __restrict__ LS, double* __restrict__ row, int j) {
+    const double x = a[0];
     row[j] = x;
-    const double* Lj = D + j * (FS_NB + 1) + j;
+    const double* Lj = LS + j * (FS_NB + 1) + j;
 #pragma unroll
     for (int k = 1; k <= KM; ++k) a[k - 1] = fma(-x, Lj[k * (FS_NB + 1)], a[k]);
 }
-__device__ __noinline__ void fs_trsm_row(double* __restrict__ row, const double* __restrict__ D, const double* __restrict__ invd_blk) {
+__device__ __noinline__ void fs_trsm_row(double* __restrict__ row, const double* __restrict__ LS, const double* __restrict__ invd_blk) {
     double a[FS_NB];
 #pragma unroll
-    for (int c = 0; c < FS_NB; ++c) a[c] = row[c];
+    for (int c = 0; c < FS_NB; ++c) a[c] = row[c] * invd_blk[c];
 #pragma unroll 1
-    for (int j = 0; j < 8; ++j) fs_trsm_step<31>(a, D, invd_blk, row, j);
+    for (int j = 0; j < 8; ++j) fs_trsm_step<31>(a, LS, row, j);
 #pragma unroll 1
-    for (int j = 8; j < 16; ++j) fs_trsm_step<23>(a, D, invd_blk, row, j);
+    for (int j = 8; j < 16; ++j) fs_trsm_step<23>(a, LS, row, j);
 #pragma unroll 1
-    for (int j = 16; j < 24; ++j) fs_trsm_step<15>(a, D, invd_blk, row, j);
+    for (int j = 16; j < 24; ++j) fs_trsm_step<15>(a, LS, row, j);
 #pragma unroll 1
-    for (int j = 24; j < 32; ++j) fs_trsm_step<7>(a, D, invd_blk, row, j);
+    for (int j = 24; j < 32; ++j) fs_trsm_step<7>(a, LS, row, j);
 }
 
 __global__ void __launch_bounds__(FS_T, 1)
@@ -256,7 +259,13 @@ chol_small_kernel(double* __restrict__ Hg, int n, int n_pad, const double* __res
         const int mb = nblk - kb - 1;                            // block rows below
         if (mb > 0) {
             // (c) panel  L_ik = H_ik L_kk^-T  for the mb blocks below, in place: one thread per panel row (fs_trsm_row)
-            if (tid < mb * FS_NB) fs_trsm_row(SB + fs_blk(kb + 1 + (tid >> 5), kb) + (tid & 31) * P, D, invd + o);
+            double* LS = invd + n_pad;                           // row-scaled copy of L_kk (one spare block behind the reciprocals)
+            for (int idx = tid; idx < (FS_NB + 7) * FS_NB; idx += FS_T) {      // + 7 rows that the last steps read and do not use: finite
+                const int r = idx >> 5, c = idx & 31;
+                LS[r * P + c] = (r < FS_NB && c < r) ? D[r * P + c] * invd[o + r] : 0.0;
+            }
+            __syncthreads();
+            if (tid < mb * FS_NB) fs_trsm_row(SB + fs_blk(kb + 1 + (tid >> 5), kb) + (tid & 31) * P, LS, invd + o);
             __syncthreads();
             tr();   // panel done
             // (d) trailing update of the lower block triangle:  H_ij -= L_ik L_jk^T  on the fp64 tensor pipe (mma.sync m8n8k4), with

@@ -50,14 +50,18 @@ def raw_metrics(rep, out, title, row_index=0):
 
 launch_table(os.path.join(G, "launches.csv"), os.path.join(P, "r02_solver_launches.txt"), "edit-solve (cfg2) kernel launch list: 5 steps of uce_edit_dev_f32",
              "ncu --metrics gpu__time_duration.sum --clock-control none -s 60 -c 30 python bench.py --no-cpu --no-denoise --no-e2e --no-graph --steps 6 --warmup 3")
+launch_table(os.path.join(G, "launches_cfg4.csv"), os.path.join(P, "r02_solver_launches_cfg4.txt"), "edit-solve at BASELINE cfg4 (SDXL shapes, 1000 concepts, 140 projections): kernel launch list of about one step",
+             "ncu --metrics gpu__time_duration.sum --clock-control none -s 200 -c 220 python bench.py --workload cfg4 --no-cpu --no-denoise --no-e2e --no-graph --steps 3 --warmup 2")
 launch_table(os.path.join(G, "launches_unet.csv"), os.path.join(P, "r02_unet_launches.txt"), "one SD-1.4 U-Net call (NB=2, 64x64 latents) kernel launch list",
              "ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off python scripts/unet_profile.py")
 raw_metrics(os.path.join(G, "prof_apply_w_kernel.ncu-rep"), os.path.join(P, "r02_apply_w_ncu.txt"),
             "apply_w_kernel — kernel B of the K-split apply (the dominant HBM kernel of an edit: W_new = W_old + P Q), cfg2, 148 CTAs")
 raw_metrics(os.path.join(G, "prof_apply_p_kernel.ncu-rep"), os.path.join(P, "r02_apply_p_ncu.txt"),
             "apply_p_kernel — kernel A of the K-split apply (partial W_old E^T per K slice; runs beside the factor), cfg2, 148 CTAs")
-raw_metrics(os.path.join(G, "prof_solve_emit_kernel.ncu-rep"), os.path.join(P, "r02_solve_emit_ncu.txt"),
-            "solve_emit_kernel — X = H^-1 Cp per 8-column slab, edit rows -> Q, Qt, tf32 splits; cfg2, 96 CTAs")
+raw_metrics(os.path.join(G, "prof_solve_emit_dmma_kernel.ncu-rep"), os.path.join(P, "r02_solve_emit_ncu.txt"),
+            "solve_emit_dmma_kernel<8> — X = H^-1 Cp per 8-column slab on the fp64 tensor pipe, edit rows -> Q, Qt, tf32 splits; cfg2, 96 CTAs (cold: under ncu its loads do not overlap inv_blocks)")
+raw_metrics(os.path.join(G, "prof_gram_pack_kernel.ncu-rep"), os.path.join(P, "r02_gram_pack_ncu.txt"),
+            "gram_pack_kernel — H = Cp Cp^T (fp64 split-K, 180 CTAs) + pack rows / E and its tf32 split; cfg2")
 raw_metrics(os.path.join(G, "prof_chol_small_kernel.ncu-rep"), os.path.join(P, "r02_chol_small_ncu.txt"), "chol_small_kernel — single-CTA fp64 Cholesky of the 160 x 160 dual system")
 raw_metrics(os.path.join(G, "prof_gemm3x.ncu-rep"), os.path.join(P, "r02_gemm3x_pass1_ncu.txt"),
             "gemm3x_kernel pass 1 (P = W_old E^T) — the two-GEMM tcgen05 apply at BASELINE cfg4 (SDXL shapes, 1000 erase concepts, rank pad 1024, K = 2048), first 96 projections", 0)
@@ -83,9 +87,11 @@ copy_with_header(os.path.join(G, "ab_trace.txt"), os.path.join(P, "r02_apply_ab_
                  "#   B epilogue i  : accumulator ready | addend box landed | box += accumulator done\n"
                  "#   B p 0 / p 2   : P summed, split and stored to tensor memory / kernel entry | setup done | teardown\n")
 copy_with_header(os.path.join(G, "chol_trace.txt"), os.path.join(P, "r02_chol_small_phases.txt"),
-                 "# chol_small_kernel v2 — phase boundaries of the single factor CTA (UCE_CHOL_TRACE), cfg2 (n = 150 -> 160)\n"
+                 "# chol_small_kernel — phase boundaries of the single factor CTA (UCE_CHOL_TRACE), cfg2 (n = 150 -> 160)\n"
                  "# columns: index, cycles since kernel start, cycles since the previous boundary\n"
-                 "# 1 load | 2 potrf of block 0 | per block step: panel (per-row TRSM), next diagonal block updated, lookahead potrf + trailing update + write-out | last: final block written\n")
+                 "# 1 load | 2 potrf of block 0 | per block step: panel (per-row TRSM), next diagonal block updated, lookahead potrf + trailing update + write-out | last: final block written\n"
+                 "# rows >= 32 (index, cycles since kernel start), inside the lookahead phases: 32 + 3 kb: warp 1 done with the trailing update, + 1: with the write-out of L,\n"
+                 "#   + 2: with clearing H (last step only); 48 + kb: warp 0's potrf of block kb + 1 done — the potrf is the critical path of every lookahead phase\n")
 copy_with_header(os.path.join(G, "sanitize_summary.txt"), os.path.join(P, "r02_sanitizer_summary.txt"),
                  "# compute-sanitizer over every kernel family (scripts/sanitize.sh -> tests/tools/sanitize_target.py: low-latency and general factor, K-split /\n"
                  "# fused / two-GEMM tcgen05 apply, SIMT apply, one tiny U-Net call, one tiny VAE decode; results checked against the oracles under the tool)\n"
@@ -107,3 +113,19 @@ raw_metrics(os.path.join(G, "prof_solve_general.ncu-rep"), os.path.join(P, "r02_
             "solve_emit_general_kernel (fp64 SIMT, 8 columns per CTA) at BASELINE cfg4 — shared-memory bound (two loads per fma); replaced by solve_emit_dmma_kernel")
 raw_metrics(os.path.join(G, "prof_solve_dmma.ncu-rep"), os.path.join(P, "r02_solve_dmma_ncu.txt"),
             "solve_emit_dmma_kernel (fp64 tensor pipe, mma.sync m8n8k4, 16 columns per CTA, L tiles straight from L2) at BASELINE cfg4")
+
+
+def concat(srcs, out, header):
+    parts = [open(os.path.join(G, n)).read() for n in srcs if os.path.isfile(os.path.join(G, n))]
+    if parts:
+        open(out, "w").write(header + "\n".join(parts))
+        print("wrote", out)
+
+
+concat(["e2e_sweep.txt", "e2e_trace.txt", "pcie_overlap.txt"], os.path.join(P, "r02_e2e_pipeline.txt"),
+       "# host-buffer call (uce_edit_host_f32), cfg2 footprint (76.7 MB each way): UCE_HOST_GROUPS sweep (scripts/e2e_groups_sweep.py), device timeline of a few calls\n"
+       "# (UCE_HOST_TRACE=1, scripts/e2e_trace.py: per pipeline group the upload, apply and download intervals in ms since the first upload, and when the HOST\n"
+       "# submitted them), and what the link itself does for the same bytes (scripts/pcie_overlap_probe.py)\n")
+for name in ("cfg5_n1.json", "cfg5_n2.json"):
+    if os.path.isfile(os.path.join(G, name)):
+        open(os.path.join(P, "r02_" + name), "w").write(open(os.path.join(G, name)).read())

@@ -380,7 +380,7 @@ def run_ours(args, rank, world, local_rank):
                                "frac": step_alg / (ms_per_step / 1e3) / 1e9 / peak_bw},
                 # The shared factor: Gram + pack (many CTAs), Cholesky (ONE CTA: 160 serial fp64 pivots), block inverses, solve + emit Q
                 # (K / 8 CTAs).  < 1 MB and 40 MFLOP: neither HBM nor a tensor pipe bounds it, latency does.
-                "factor": {"kernels": "gram_pack, chol_small (1 CTA), inv_blocks, solve_emit" if info["launches_factor"] <= 5 else "general blocked path (factor.cu)",
+                "factor": {"kernels": "factor_tables, gram_pack, chol_small (1 CTA), inv_blocks, solve_emit_dmma (chained by programmatic dependent launch)" if info["launches_factor"] <= 5 else "general blocked path (factor.cu)",
                            "ms": f_ms, "bound": "latency (serial fp64 pivots on one SM; dependent fp64 operations cost ~35 cycles each)"}}
         if alg_a is not None:
             roof["kernel_a"] = {"kernel": "apply_p_kernel (partial W_old E^T per K slice; runs on the library's side stream while the factor computes Q)",

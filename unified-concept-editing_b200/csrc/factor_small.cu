@@ -38,34 +38,61 @@ __device__ __forceinline__ float fs_tf32_hi(float x) {
 // H[i,j] += sum_{k in split} Cp[i,k] Cp[j,k]   for tile pairs ti >= tj (lower block triangle); H pre-zeroed.
 // The concept rows are read straight from the caller's C through the row order `src` (internal row r = C[src[r]]), so this kernel
 // does not wait for the pack kernel: the pack work (pack_rows_split below: Cp, E and its tf32 split) rides in the SAME launch as
-// extra blocks (blockIdx.x >= n_pairs, blockIdx.y == 0).
+// extra blocks (behind the Gram blocks of the 1-D grid).
 __device__ void pack_rows_split_block(int r, const float* __restrict__ C, const float* __restrict__ G, const int* __restrict__ src, int n_act,
                                       int n_pres, int rank_pad, int K, float* __restrict__ Cp, float* __restrict__ E,
                                       float* __restrict__ E_hi, float* __restrict__ E_lo);
-__global__ void __launch_bounds__(256) gram_pack_kernel(const float* __restrict__ C, const int* __restrict__ src, int n, int K, double* __restrict__ H, int ld,
+struct FsSrc { int v[FS_MAX_N]; };                // the row order as a KERNEL PARAMETER: no table to wait for, no index round trip before the rows
+__global__ void __launch_bounds__(256) gram_pack_kernel(const float* __restrict__ C, const __grid_constant__ FsSrc srcp, int n, int K, double* __restrict__ H, int ld,
                                                         int n_pairs, const float* __restrict__ G, int n_pres, int rank_pad, int n_pack_rows,
                                                         float* __restrict__ Cp, float* __restrict__ E, float* __restrict__ E_hi, float* __restrict__ E_lo) {
     __shared__ double A[FS_NB][FS_KSPLIT + 1];
     __shared__ double B[FS_NB][FS_KSPLIT + 1];
-    pdl_wait(); pdl_launch();                      // the row order (src) comes from the table kernel launched right before
-    if ((int)blockIdx.x >= n_pairs) {
-        if (blockIdx.y == 0) {
-            const int r = (int)blockIdx.x - n_pairs;
-            if (r < n_pack_rows) pack_rows_split_block(r, C, G, src, n, n_pres, rank_pad, K, Cp, E, E_hi, E_lo);
-        }
+    // Programmatic launch: this kernel starts while the table kernel in front of it still runs.  It READS only the caller's C / G
+    // (the row order arrives as a parameter), so the loads go out at once; the wait comes before the first WRITE (the previous edit's
+    // kernels may still read Cp / E / H until the table kernel, which waited for them, has finished).
+    pdl_launch();
+    const int* src = srcp.v;
+    // 1-D grid: the Gram blocks first — (tile pair, K split) = blockIdx.x % n_pairs, / n_pairs — then one block per packed row.  (The
+    // first version was a 2-D grid whose pack blocks existed once per K split and returned at once for all but one: 2 148 CTAs, 2.4 waves.)
+    const int n_gram = n_pairs * ((K + FS_KSPLIT - 1) / FS_KSPLIT);
+    if ((int)blockIdx.x >= n_gram) {
+        const int r = (int)blockIdx.x - n_gram;
+        pdl_wait();
+        if (r < n_pack_rows) pack_rows_split_block(r, C, G, src, n, n_pres, rank_pad, K, Cp, E, E_hi, E_lo);
         return;
     }
     // decode the lower-triangular tile pair
-    int p = blockIdx.x, ti = 0;
+    int p = (int)blockIdx.x % n_pairs, ti = 0;
     while ((ti + 1) * (ti + 2) / 2 <= p) ++ti;
     const int tj = p - ti * (ti + 1) / 2;
-    const int k0 = blockIdx.y * FS_KSPLIT;
+    const int k0 = ((int)blockIdx.x / n_pairs) * FS_KSPLIT;
     const int tid = threadIdx.x;
-    for (int idx = tid; idx < FS_NB * FS_KSPLIT; idx += 256) {
-        const int r = idx / FS_KSPLIT, k = idx % FS_KSPLIT;
-        const int gi = ti * FS_NB + r, gj = tj * FS_NB + r, gk = k0 + k;
-        A[r][k] = (gi < n && gk < K) ? (double)C[(long)src[gi] * K + gk] : 0.0;
-        B[r][k] = (gj < n && gk < K) ? (double)C[(long)src[gj] * K + gk] : 0.0;
+    {
+        // thread = (row r0 + 4 it, column k): ALL row indices first, then ALL values, then the stores — two memory round trips per CTA.
+        // (As one loop of "index, value, store" the compiler kept the eight iterations in order: 16 dependent round trips, 28 k cycles
+        // per CTA of which 1.3 k are arithmetic.)
+        static_assert(FS_KSPLIT == 64 && FS_NB == 32, "8 rows per thread");
+        const int k = tid & 63, r0 = tid >> 6, gk = k0 + k;
+        const bool diag = ti == tj;
+        int sa[8], sb[8];
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+            const int gi = ti * FS_NB + r0 + 4 * it, gj = tj * FS_NB + r0 + 4 * it;
+            sa[it] = (gi < n) ? src[gi] : -1;
+            sb[it] = (!diag && gj < n) ? src[gj] : -1;
+        }
+        float va[8], vb[8];
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+            va[it] = (sa[it] >= 0 && gk < K) ? C[(long)sa[it] * K + gk] : 0.f;
+            vb[it] = (sb[it] >= 0 && gk < K) ? C[(long)sb[it] * K + gk] : 0.f;
+        }
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+            A[r0 + 4 * it][k] = (double)va[it];
+            B[r0 + 4 * it][k] = (double)(diag ? va[it] : vb[it]);
+        }
     }
     __syncthreads();
     const int tx = tid % 16, ty = tid / 16;   // 2 x 2 outputs per thread
@@ -77,6 +104,7 @@ __global__ void __launch_bounds__(256) gram_pack_kernel(const float* __restrict_
         acc[0][0] = fma(a0, b0, acc[0][0]); acc[0][1] = fma(a0, b1, acc[0][1]);
         acc[1][0] = fma(a1, b0, acc[1][0]); acc[1][1] = fma(a1, b1, acc[1][1]);
     }
+    pdl_wait();
 #pragma unroll
     for (int i = 0; i < 2; ++i)
 #pragma unroll
@@ -611,7 +639,10 @@ int factor_small(uce_ws* ws, const float* C, const float* G, int n, int n_pres, 
         UCE_CUDA(cudaMemsetAsync(ws->H, 0, (sm < fm ? sm : fm) * sizeof(double), st));
     }
     const int nt = n_pad / FS_NB, n_pairs = nt * (nt + 1) / 2, n_pack = n + (ws->rank_pad - n_edit);
-    UCE_CUDA(launch_k(gram_pack_kernel, dim3(n_pairs + n_pack, ceil_div(K, FS_KSPLIT)), dim3(256), 0, st, 1, C, (const int*)ws->src_idx, n, K, ws->H, n_pad,
+    FsSrc srcp;
+    memcpy(srcp.v, ws->h_src_idx, (size_t)n * sizeof(int));
+    for (int i = n; i < FS_MAX_N; ++i) srcp.v[i] = 0;
+    UCE_CUDA(launch_k(gram_pack_kernel, dim3(n_pairs * ceil_div(K, FS_KSPLIT) + n_pack), dim3(256), 0, st, 1, C, srcp, n, K, ws->H, n_pad,
                       n_pairs, G, n_pres, ws->rank_pad, n_pack, ws->Cp, ws->E, ws->E_hi, ws->E_lo));
     ++*launches;
     // E and its split are complete (pack kernel) and the many-CTA Gram kernel is behind us: from here on the factor is one CTA wide,

@@ -94,7 +94,8 @@ copy_with_header(os.path.join(G, "chol_trace.txt"), os.path.join(P, "r02_chol_sm
                  "#   + 2: with clearing H (last step only); 48 + kb: warp 0's potrf of block kb + 1 done — the potrf is the critical path of every lookahead phase\n")
 copy_with_header(os.path.join(G, "sanitize_summary.txt"), os.path.join(P, "r02_sanitizer_summary.txt"),
                  "# compute-sanitizer over every kernel family (scripts/sanitize.sh -> tests/tools/sanitize_target.py: low-latency and general factor, K-split /\n"
-                 "# fused / two-GEMM tcgen05 apply, SIMT apply, one tiny U-Net call, one tiny VAE decode; results checked against the oracles under the tool)\n"
+                 "# fused / two-GEMM tcgen05 apply, SIMT apply, the host-buffer call, one tiny U-Net call, one tiny VAE decode, both CLIP towers; results checked\n"
+                 "# against the oracles under the tool; this is the run AFTER the programmatic-launch factor chain and the fp64 tensor-pipe kernels went in)\n"
                  "# memcheck: 0 errors.  synccheck: 0 errors.  racecheck: 0 hazards in the solver kernels; in the U-Net / VAE runs every report is the\n"
                  "# same one — 'Potential RAW hazard (CUDA barrier operation)' on 8 bytes at window offsets 0x58 and 0x1000058 (the second is the same offset in\n"
                  "# the PEER CTA's shared window) in unet_gemm_pair_kernel: the cluster pair signals mbarriers in the other CTA's shared memory (TMA complete_tx with\n"

@@ -331,6 +331,68 @@ __global__ void __launch_bounds__(256, 1) solve_emit_dmma_kernel(const double* _
     }
 }
 
+// H = Cp Cp^T for the general path on the fp64 tensor pipe: one CTA per 64 x 64 tile of the lower tile triangle, the whole K range in one
+// CTA (no split, no atomics: 136 CTAs at n = 1000, one wave).  Concept rows are fp32 — their products are exact in fp64 —, staged in
+// shared memory as floats (pitch 36: the fragment loads of a warp hit 32 different banks) and converted when a fragment is built.  A warp
+// owns 8 rows of the tile and sweeps its eight 8-column tiles: one A fragment + eight B fragments per 8 DMMA.  Replaces the generic fp64
+// SIMT GEMM (0.45 ms of the 1.9 ms factor at BASELINE cfg4).
+constexpr int GD_T = 64, GD_KC = 32, GD_P = 36;
+__global__ void __launch_bounds__(256, 1) gram_dmma_kernel(const float* __restrict__ Cp, int n, int K, double* __restrict__ H, int ld) {
+    __shared__ float As[2][GD_T * GD_P];
+    __shared__ float Bs[2][GD_T * GD_P];
+    int p = blockIdx.x, ti = 0;
+    while ((ti + 1) * (ti + 2) / 2 <= p) ++ti;
+    const int tj = p - ti * (ti + 1) / 2;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    // staging: thread = (row = tid / 4 [+ 0], 8 consecutive floats at column (tid % 4) * 8) of a 64 x 32 chunk
+    const int lr = tid >> 2, lc = (tid & 3) * 8;
+    const bool diag = ti == tj;
+    auto fetch = [&](int k0, float4 (&a)[2], float4 (&b)[2]) {
+        const int ra = ti * GD_T + lr, rb = tj * GD_T + lr;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int k = k0 + lc + 4 * h;
+            a[h] = (ra < n && k < K) ? *reinterpret_cast<const float4*>(Cp + (long)ra * K + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+            b[h] = (!diag && rb < n && k < K) ? *reinterpret_cast<const float4*>(Cp + (long)rb * K + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    };
+    auto stash = [&](int buf, const float4 (&a)[2], const float4 (&b)[2]) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            *reinterpret_cast<float4*>(&As[buf][lr * GD_P + lc + 4 * h]) = a[h];
+            *reinterpret_cast<float4*>(&Bs[buf][lr * GD_P + lc + 4 * h]) = diag ? a[h] : b[h];
+        }
+    };
+    double acc[8][2];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) { acc[nt][0] = 0.0; acc[nt][1] = 0.0; }
+    float4 pa[2], pb[2];
+    fetch(0, pa, pb);
+    stash(0, pa, pb);
+    __syncthreads();
+    const int n_chunks = (K + GD_KC - 1) / GD_KC;
+    for (int ch = 0; ch < n_chunks; ++ch) {
+        const int buf = ch & 1;
+        if (ch + 1 < n_chunks) fetch((ch + 1) * GD_KC, pa, pb);             // in flight during the 64 DMMA below
+        const float* Aw = &As[buf][(warp * 8 + g) * GD_P + t];
+        const float* Bw = &Bs[buf][g * GD_P + t];
+#pragma unroll
+        for (int ks = 0; ks < GD_KC / 4; ++ks) {
+            const double a = (double)Aw[ks * 4];
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) dmma884(acc[nt][0], acc[nt][1], a, (double)Bw[nt * 8 * GD_P + ks * 4]);
+        }
+        if (ch + 1 < n_chunks) stash(buf ^ 1, pa, pb);                     // the other buffer: everybody left it at the previous barrier
+        __syncthreads();
+    }
+    const int row = ti * GD_T + warp * 8 + g;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+        double* o = H + (long)row * ld + tj * GD_T + nt * 8 + 2 * t;
+        o[0] = acc[nt][0]; o[1] = acc[nt][1];
+    }
+}
+
 #define UCE_RT(expr)                                                                             \
     do {                                                                                         \
         cudaError_t _e = (expr);                                                                 \
@@ -468,7 +530,13 @@ int factor_dev(uce_ws* ws, const float* C, const float* G, const float* scales, 
     UCE_CUDA(cudaMemsetAsync(ws->H, 0, (size_t)n_pad * n_pad * sizeof(double), st));
     if (dual) {
         // H = Cp Cp^T (fp64 accumulate of exact fp32 products), lower tiles
-        UCE_RT((simt_gemm<float, float, double, double>(st, n, n, K, ws->Cp, K, 1, ws->Cp, K, 1, ws->H, n_pad, 1.0, nullptr, 0, 0.0, 1)));
+        if (n_pad % GD_T == 0 && K % 4 == 0 && getenv("UCE_GENERAL_GRAM_SIMT") == nullptr) {
+            const int tiles = n_pad / GD_T;
+            gram_dmma_kernel<<<tiles * (tiles + 1) / 2, 256, 0, st>>>(ws->Cp, n, K, ws->H, n_pad);
+            UCE_RT(cudaGetLastError());
+        } else {
+            UCE_RT((simt_gemm<float, float, double, double>(st, n, n, K, ws->Cp, K, 1, ws->Cp, K, 1, ws->H, n_pad, 1.0, nullptr, 0, 0.0, 1)));
+        }
         finish_diag_kernel<<<ceil_div(n_pad, 256), 256, 0, st>>>(ws->H, n_pad, n, n_pad, ws->diag_add, 0.0);
         UCE_RT(cudaGetLastError());
     } else {

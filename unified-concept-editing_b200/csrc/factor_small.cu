@@ -427,6 +427,7 @@ __global__ void __launch_bounds__(FS_T, 1) potrf_inv_general_kernel(double* __re
     __shared__ double invd[FS_NB];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     double* blk = H + (size_t)kb * FS_NB * ld + (size_t)kb * FS_NB;
+    pdl_wait(); pdl_launch();
     for (int idx = tid; idx < (FS_NB + 8) * FS_NB; idx += FS_T) {
         const int r = idx >> 5, c = idx & 31;
         D[r * P + c] = (r < FS_NB && c <= r) ? blk[(size_t)r * ld + c] : 0.0;
@@ -457,8 +458,7 @@ __global__ void __launch_bounds__(FS_T, 1) potrf_inv_general_kernel(double* __re
 }
 int potrf_inv_general(double* H, int ld, int kb, double* Linv, int* flag, cudaStream_t st) {
     static_assert(FS_NB == UCE_NB && FS_T == 32 * 16, "two inverse columns per warp");
-    potrf_inv_general_kernel<<<1, FS_T, 0, st>>>(H, ld, kb, Linv, flag);
-    return (int)cudaGetLastError();
+    return (int)launch_k(potrf_inv_general_kernel, dim3(1), dim3(FS_T), 0, st, 1, H, ld, kb, Linv, flag);
 }
 
 // ---------------------------------------------------------------------------------------------------------

@@ -5,6 +5,7 @@
 // tcgen05 kernel is validated against.  Arbitrary element strides on A and B make every
 // transpose free; 64x64x16 tiles, 256 threads, 4x4 register blocking.
 #pragma once
+#include <cstdlib>
 #include <cuda_runtime.h>
 
 namespace uce {
@@ -91,6 +92,10 @@ template <typename TA, typename TB, typename TAcc, typename TC>
 __global__ void __launch_bounds__(SG_THREADS) simt_gemm_kernel(SimtGemmArgs<TA, TB, TAcc, TC> g) {
     __shared__ TAcc As[SG_BK][SG_BM + 4];
     __shared__ TAcc Bs[SG_BK][SG_BN + 4];
+    // programmatic dependent launch (the blocked Cholesky of the general factor is ~100 of these back to back): wait for the kernel in
+    // front, then let the one behind start its launch; both are no-ops for a plain launch
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (g.lower_only && blockIdx.x > blockIdx.y) return;
     simt_gemm_tile<TA, TB, TAcc, TC>(g, blockIdx.y, blockIdx.x, As, Bs);
 }
@@ -102,8 +107,13 @@ inline cudaError_t simt_gemm(cudaStream_t st, int M, int N, int Kd, const TA* A,
     if (M <= 0 || N <= 0) return cudaSuccess;
     SimtGemmArgs<TA, TB, TAcc, TC> g{M, N, Kd, A, sa_m, sa_k, B, sb_n, sb_k, C, ldc, Add, ldadd, alpha, beta, lower_only};
     dim3 grid((N + SG_BN - 1) / SG_BN, (M + SG_BM - 1) / SG_BM);
-    simt_gemm_kernel<TA, TB, TAcc, TC><<<grid, SG_THREADS, 0, st>>>(g);
-    return cudaGetLastError();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = dim3(SG_THREADS); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[0].val.programmaticStreamSerializationAllowed = 1;
+    static const bool pdl = getenv("UCE_NO_PDL") == nullptr;
+    cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, simt_gemm_kernel<TA, TB, TAcc, TC>, g);
 }
 
 }  // namespace uce

@@ -112,6 +112,8 @@ for name in ("bench.json", "bench_cfg1.json", "bench_cfg3.json", "bench_cfg4.jso
             print("skip", name, exc)
 raw_metrics(os.path.join(G, "prof_solve_general.ncu-rep"), os.path.join(P, "r02_solve_general_ncu.txt"),
             "solve_emit_general_kernel (fp64 SIMT, 8 columns per CTA) at BASELINE cfg4 — shared-memory bound (two loads per fma); replaced by solve_emit_dmma_kernel")
+raw_metrics(os.path.join(G, "prof_gram_dmma.ncu-rep"), os.path.join(P, "r02_gram_dmma_ncu.txt"),
+            "gram_dmma_kernel — H = Cp Cp^T of the general factor on the fp64 tensor pipe (one CTA per 64 x 64 tile, whole K, no atomics) at BASELINE cfg4 (n = 1000, K = 2048)")
 raw_metrics(os.path.join(G, "prof_solve_dmma.ncu-rep"), os.path.join(P, "r02_solve_dmma_ncu.txt"),
             "solve_emit_dmma_kernel (fp64 tensor pipe, mma.sync m8n8k4, 16 columns per CTA, L tiles straight from L2) at BASELINE cfg4")
 

@@ -12,9 +12,10 @@
 // (Woodbury; the dual form never places lamb next to the O(1e5) Gram entries in fp32 —
 // SURVEY.md §7 H1.)  Internally rows are ordered preserve-first / edit-last.
 //
-// General-size path: blocked right-looking Cholesky (NB = 32) in global memory, diagonal blocks
-// factored and inverted by one CTA, panels / trailing updates / triangular solves expressed
-// as strided fp64 SIMT GEMMs.
+// General-size path (systems larger than factor_small.cu takes): Gram on the fp64 tensor pipe (gram_dmma_kernel), blocked
+// right-looking Cholesky (NB = 32) in global memory — diagonal blocks factored and inverted by one CTA, panels and trailing updates as
+// strided fp64 SIMT GEMMs launched programmatically behind each other — and for the dual system the substitution + Q emission as one
+// fp64 tensor-pipe kernel (solve_emit_dmma_kernel); the primal system keeps GEMM-based triangular solves.
 #include "uce_ws.h"
 #include "gemm_simt.cuh"
 #include "tc_common.cuh"

@@ -85,6 +85,40 @@ def test_get_ratios_single_process_matches_reference_arithmetic():
         assert pipe.calls == EDIT
 
 
+def test_get_ratios_hands_device_images_to_a_classifier_that_takes_them():
+    """EngineGenerator + VAE engine return the decoded pixels also as one uint8 tensor on the device (`images_u8`); a classifier that
+    declares `accepts_device_images` (ClipZeroShotEngine) gets that tensor instead of the host copies, any other `clip` (the
+    transformers pipeline of the reference) gets `.images` as before — same ratios either way."""
+    from uce_b200.debias import get_ratios
+
+    class Out:
+        def __init__(self, prompt, n):
+            self.images = [(prompt, i) for i in range(n)]
+            self.images_u8 = ("device", prompt, n)
+
+    class Pipe(_Pipe):
+        def __call__(self, prompt, num_inference_steps=20, num_images_per_prompt=10, guidance_scale=7.5):
+            self.calls.append(prompt)
+            return Out(prompt, num_images_per_prompt)
+
+    class DeviceClip:
+        accepts_device_images = True
+
+        def __init__(self):
+            self.seen = []
+
+        def __call__(self, images, candidate_labels):
+            self.seen.append(images)
+            return [[{"label": lab, "score": 0.9}] for lab in LABELS[images[1]]]
+
+    clip = DeviceClip()
+    got = get_ratios(Pipe(), clip, [], [], EDIT, DEB, (0.5, 0.5), 0.05)
+    assert all(isinstance(x, tuple) and x[0] == "device" for x in clip.seen) and [x[1] for x in clip.seen] == EDIT
+    assert np.array_equal(got, _reference_get_ratios((0.5, 0.5), 0.05))
+    host = get_ratios(Pipe(), _clip, [], [], EDIT, DEB, (0.5, 0.5), 0.05)          # a plain callable: the host images
+    assert np.array_equal(host, got)
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))

@@ -538,13 +538,12 @@ def bench_sharded(solver, prob, dev, rank, world, args):
     p0 = problem(args.workload, seed=0)                    # every rank: the same job
     Cd, Gd = p0["C"].to(dev), p0["G"].to(dev)
     dims = p0["dims"]
-    plan = GatherPlan(dims, K, world, rank, dev)
-    mine = plan.views_mine()
-    W = [p0["W"][i].to(dev) for i in mine]
-    outs = list(mine.values())
+    from uce_b200.sharding import default_chunks, sharded_edit
+    chunks = default_chunks(dims, K, world)
+    plan = GatherPlan(dims, K, world, rank, dev, chunks=chunks)
+    W = {i: p0["W"][i].to(dev) for i in plan.views_mine()}
     def once():
-        solver.edit(Cd, Gd, p0["scales"], ne, p0["lamb"], W, outs, check=False)      # W_new = slices of the gather buffer
-        return plan.gather()
+        return sharded_edit(solver, plan, Cd, Gd, p0["scales"], ne, p0["lamb"], W, check=False)      # W_new = slices of the gather buffer
     for _ in range(3):
         once()
     torch.cuda.synchronize(dev); dist.barrier()
@@ -557,7 +556,8 @@ def bench_sharded(solver, prob, dev, rank, world, args):
     t = torch.tensor([e0.elapsed_time(e1) / reps], device=dev, dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = t.item()
-    return {"ms_per_job": ms, "value": n / (ms / 1e3), "unit": UNIT, "collective": "1 in-place all_gather_into_tensor (NCCL) of the packed edited weights (apply kernels write into the gather buffer)",
+    return {"ms_per_job": ms, "value": n / (ms / 1e3), "unit": UNIT, "collective": f"{plan.chunks} in-place all_gather_into_tensor (NCCL) of the packed edited weights (apply kernels write into the gather buffer"
+            + ("; a chunk is gathered while the next one is computed)" if plan.chunks > 1 else ")"), "chunks": plan.chunks,
             "nvlink_floor_ms": (world - 1) / world * 4.0 * K * sum(dims) / 770e9 * 1e3,      # bytes every GPU must receive / measured peer bandwidth (B200_PROFILING.md)
             "scaling": "strong"}
 

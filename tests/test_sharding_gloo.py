@@ -43,9 +43,42 @@ def _worker(rank, world, port, q):
             v.copy_(local[i])
         full2 = plan.gather()
         ok = ok and all(torch.equal(a, b) for a, b in zip(full2, ref)) and sorted(plan.views_mine()) == mine
+        # chunked form (large edits: a chunk's all-gather overlaps the next chunk's kernels): every chunk count gives the same result,
+        # also with asynchronous collectives and with chunks in which this rank owns nothing
+        for chunks in (2, 3, 7):
+            planc = GatherPlan(dims, K, world, rank, torch.device("cpu"), chunks=chunks)
+            views = planc.views_mine()
+            works = []
+            seen = []
+            for c in range(planc.chunks):
+                for l in planc.layers_of_chunk_mine(c):
+                    views[l].copy_(local[l]); seen.append(l)
+                works.append(planc.gather_chunk(c, async_op=True))
+            for w in works:
+                w.wait()
+            fullc = [planc.view(l) for l in range(len(dims))]
+            ok = ok and sorted(seen) == mine and all(torch.equal(a, b) for a, b in zip(fullc, ref))
         q.put((rank, ok))
     finally:
         dist.destroy_process_group()
+
+
+def test_gather_plan_layout_is_a_partition():
+    """Every projection gets its own region of the packed buffer (no overlap, all inside), for any world size and chunk count; the
+    chunk regions are contiguous, in order, and hold one equal part per rank."""
+    from uce_b200.sharding import GatherPlan, default_chunks
+    from uce_b200.synthetic import SD14_DIMS, SDXL_DIMS
+    for dims, K in (([8, 24, 16, 8, 40], 32), (SD14_DIMS, 768), (SDXL_DIMS, 2048), ([5], 4), ([], 4)):
+        for world in (1, 2, 3, 8):
+            for chunks in (1, 2, 5, 64):
+                plan = GatherPlan(dims, K, world, 0, torch.device("meta"), chunks=chunks)
+                spans = sorted((plan.where[l][1], plan.where[l][1] + d * K) for l, d in enumerate(dims))
+                assert all(a1 <= b0 for (_, a1), (b0, _) in zip(spans, spans[1:])), (dims[:3], world, chunks)
+                assert not spans or (spans[0][0] >= 0 and spans[-1][1] <= plan.buf.numel())
+                assert plan.base[-1] == plan.buf.numel() == world * sum(plan.part)
+                mine = [l for r in range(world) for l in GatherPlan(dims, K, world, r, torch.device("meta"), chunks=chunks).views_mine()]
+                assert sorted(mine) == list(range(len(dims)))
+    assert default_chunks(SD14_DIMS, 768, 2) == 1 and default_chunks(SDXL_DIMS, 2048, 2) == 4 and default_chunks(SDXL_DIMS, 2048, 8) == 2
 
 
 def test_layer_sharding_allgather_world2():

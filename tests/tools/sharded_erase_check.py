@@ -15,11 +15,14 @@ edit = [f"artist {i}" for i in range(20)]; guide = ["art"] * 20; pres = [f"thing
 single = UCE(pipe, edit, guide, pres, 1.0, 1.0, 0.5, None, "x", device=f"cuda:{local}", verbose=False)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 sharded = UCE(pipe, edit, guide, pres, 1.0, 1.0, 0.5, None, "x", device=f"cuda:{local}", verbose=False)
+os.environ["UCE_SHARD_CHUNKS"] = "3"          # the chunked form large edits take: a chunk's all-gather overlaps the next chunk's kernels
+chunked = UCE(pipe, edit, guide, pres, 1.0, 1.0, 0.5, None, "x", device=f"cuda:{local}", verbose=False)
+del os.environ["UCE_SHARD_CHUNKS"]
 def rel(a, b):
     return float((a.double() - b.double()).norm() / b.double().norm())
-worst = max(rel(sharded[k].cpu(), single[k].cpu()) for k in single)
-ok = worst <= 3e-6 and len(sharded) == 32
-chk = torch.stack([sharded[k].double().sum() for k in sorted(sharded)])          # the same bytes on every rank?
+worst = max(max(rel(sharded[k].cpu(), single[k].cpu()), rel(chunked[k].cpu(), single[k].cpu())) for k in single)
+ok = worst <= 3e-6 and len(sharded) == 32 and len(chunked) == 32
+chk = torch.stack([sharded[k].double().sum() for k in sorted(sharded)] + [chunked[k].double().sum() for k in sorted(chunked)])   # the same bytes on every rank?
 lo, hi = chk.clone(), chk.clone()
 dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
 ok = ok and bool(torch.equal(lo, hi))

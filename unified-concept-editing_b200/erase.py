@@ -51,13 +51,13 @@ def UCE(pipe, edit_concepts, guide_concepts, preserve_concepts, erase_scale, pre
 
     dist_on = torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1
     if dist_on:
-        from .sharding import GatherPlan
+        from .sharding import GatherPlan, default_chunks, sharded_edit
         rank, world = torch.distributed.get_rank(), torch.distributed.get_world_size()
-        plan = GatherPlan([w.shape[0] for w in w_old], K, world, rank, dev)
-        mine = plan.views_mine()            # this rank's projections, written by the apply kernels straight into the gather buffer
-        if mine:                            # more ranks than projections: an empty shard still takes part in the collective
-            solver.edit(C.to(dev), G.to(dev) if G is not None else None, scales, n_edit, lamb, [w_old[i] for i in mine], list(mine.values()))
-        w_new = plan.gather()
+        dims = [w.shape[0] for w in w_old]
+        # this rank's projections are written by the apply kernels straight into the gather buffer; large edits go in chunks whose
+        # all-gathers overlap the next chunk's kernels; a rank without projections (more ranks than projections) still takes part
+        plan = GatherPlan(dims, K, world, rank, dev, chunks=default_chunks(dims, K, world))
+        w_new = sharded_edit(solver, plan, C.to(dev), G.to(dev) if G is not None else None, scales, n_edit, lamb, dict(enumerate(w_old)))
         is_writer = rank == 0
     else:
         w_new = solver.edit(C.to(dev), G.to(dev) if G is not None else None, scales, n_edit, lamb, w_old)

@@ -236,6 +236,19 @@ def test_clip_text_c_abi_exports_every_declared_symbol():
     assert declared == set(clip_text.SIGNATURES), declared ^ set(clip_text.SIGNATURES)
 
 
+def test_host_arena_is_one_allocation_with_back_to_back_views():
+    """EditSolver.host_arena: the layout uce_edit_host_f32 recognises (projection l + 1 starts where l ends), so a pipeline group
+    travels as one copy per direction."""
+    from uce_b200.solver import EditSolver
+    dims, K = [320, 640, 8, 1280], 96
+    buf, views = EditSolver.host_arena(dims, K, pin=False)
+    assert buf.numel() == sum(dims) * K and [tuple(v.shape) for v in views] == [(d, K) for d in dims]
+    for a, b, d in zip(views, views[1:], dims):
+        assert b.data_ptr() == a.data_ptr() + d * K * 4 and a.is_contiguous()
+    views[2].fill_(3.0)
+    assert float(buf[(320 + 640) * K]) == 3.0 and float(buf[(320 + 640 + 8) * K - 1]) == 3.0
+
+
 def test_clip_vision_c_abi_exports_every_declared_symbol():
     from uce_b200 import _native, clip_zero_shot
     hdr = open(os.path.join(ROOT, "include", "clip_vision_b200.h")).read()

@@ -8,7 +8,8 @@ cross-attention k/v projection (BASELINE configs[1] by default: SD-1.4 shapes, 5
 100 preserve concepts, 32 projections, K=768).  `value` = concepts/s with the concept rows and
 projection weights already resident in HBM (CUDA-graph replay, CUDA-event timed, max over
 ranks); `e2e` = the same metric through the host-buffer C-ABI call (uce_edit_host_f32) with
-pinned host tensors, H2D and D2H inside the timed region.  N>1: every rank solves its own
+W_old / W_new each in one pinned host arena, H2D and D2H inside the timed region (the same call on one
+pinned tensor per projection is reported beside it).  N>1: every rank solves its own
 independent edit job (weak scaling, no data-path collective); the layer-sharded single job with
 its all-gather is reported under "sharded".  `--impl reference` times the CPU restatement of the
 reference's algorithm (oracle/uce_oracle.py: the reference itself is Python and cannot travel

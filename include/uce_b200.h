@@ -120,7 +120,9 @@ int uce_edit_dev_f32(uce_ws *ws, const float *C, const float *G, const float *sc
 /* Whole edit with HOST buffers (the call a host-side integration makes): H2D of C, G and each
  * W_old[l], factor, apply, D2H of each W_new[l]; copies are pipelined against the kernels on
  * internal streams; returns after the last W_new byte has landed.  Same arguments as above but
- * every pointer is a host pointer (pinned memory gives full PCIe bandwidth). */
+ * every pointer is a host pointer (pinned memory gives full PCIe bandwidth).  Projections whose host
+ * buffers follow each other in memory (W_old[l + 1] == W_old[l] + d[l] * K, likewise W_new: a caller
+ * that keeps its weights in one pinned arena) travel as one copy per pipeline group and direction. */
 int uce_edit_host_f32(uce_ws *ws, const float *C, const float *G, const float *scales,
                       int n_rows, int n_edit, float lamb,
                       const float *const *W_old, float *const *W_new, const int *d, int n_layers);

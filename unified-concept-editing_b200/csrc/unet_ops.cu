@@ -142,14 +142,40 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const __nv_bfloat16* __re
     float f[8];
     unpack8(u, f);
     const float inv_n = 1.f / ((float)HW * cpg);
+    // the 8 channels of a vector lie in at most two groups (cpg >= 4 for every SD shape; cpg < 8 falls back to per-channel lookups):
+    // mean / rstd once per group instead of once per channel, gamma / beta as four 16-byte loads (same arithmetic, same bits)
+    const int c0 = cv * 8;
+    const float4 ga0 = *reinterpret_cast<const float4*>(gamma + c0), ga1 = *reinterpret_cast<const float4*>(gamma + c0 + 4);
+    const float4 be0 = *reinterpret_cast<const float4*>(beta + c0), be1 = *reinterpret_cast<const float4*>(beta + c0 + 4);
+    const float gam[8] = {ga0.x, ga0.y, ga0.z, ga0.w, ga1.x, ga1.y, ga1.z, ga1.w};
+    const float bet[8] = {be0.x, be0.y, be0.z, be0.w, be1.x, be1.y, be1.z, be1.w};
+    if (cpg >= 8) {
+        const int g0 = c0 / cpg, g1 = (c0 + 7) / cpg;
+        float mean[2], rstd[2];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const int c = cv * 8 + i, g = c / cpg;
-        const float s = stats[((long)img * G + g) * 2], ss = stats[((long)img * G + g) * 2 + 1];
-        const float mean = s * inv_n;
-        const float var = fmaxf(ss * inv_n - mean * mean, 0.f);
-        float v = (f[i] - mean) * rsqrtf(var + eps) * gamma[c] + beta[c];
-        f[i] = silu ? silu_f(v) : v;
+        for (int q = 0; q < 2; ++q) {
+            const int g = q ? g1 : g0;
+            const float s = stats[((long)img * G + g) * 2], ss = stats[((long)img * G + g) * 2 + 1];
+            mean[q] = s * inv_n;
+            rstd[q] = rsqrtf(fmaxf(ss * inv_n - mean[q] * mean[q], 0.f) + eps);
+        }
+        const int split = (g0 + 1) * cpg - c0;              // channels [0, split) of the vector are in g0
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int q = i < split ? 0 : 1;
+            float v = (f[i] - mean[q]) * rstd[q] * gam[i] + bet[i];
+            f[i] = silu ? silu_f(v) : v;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int c = c0 + i, g = c / cpg;
+            const float s = stats[((long)img * G + g) * 2], ss = stats[((long)img * G + g) * 2 + 1];
+            const float mean = s * inv_n;
+            const float var = fmaxf(ss * inv_n - mean * mean, 0.f);
+            float v = (f[i] - mean) * rsqrtf(var + eps) * gam[i] + bet[i];
+            f[i] = silu ? silu_f(v) : v;
+        }
     }
     *reinterpret_cast<uint4*>(y + idx * 8) = pack8(f);
 }

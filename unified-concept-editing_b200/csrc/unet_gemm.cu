@@ -665,14 +665,33 @@ __global__ void __launch_bounds__(256) splitk_finalize_kernel(GemmDesc g, int ro
     }
     float f[4] = {v.x, v.y, v.z, v.w};
     if (g.bias) { const float4 b = *reinterpret_cast<const float4*>(g.bias + n0); f[0] += b.x; f[1] += b.y; f[2] += b.z; f[3] += b.w; }
-    if (g.rowbias) { const float* rb = g.rowbias + (row / rows_per_img) * g.N + n0; for (int i = 0; i < 4; ++i) f[i] += rb[i]; }
-    if (g.residual) { const __nv_bfloat16* rp = g.residual + row * g.ldr + n0; for (int i = 0; i < 4; ++i) f[i] += __bfloat162float(rp[i]); }
+    // 16-byte / 8-byte accesses where the leading dimensions allow it (N % 4 == 0 always; ldr / ldo multiples of 4 in every U-Net use)
+    if (g.rowbias) { const float4 rb = *reinterpret_cast<const float4*>(g.rowbias + (row / rows_per_img) * g.N + n0); f[0] += rb.x; f[1] += rb.y; f[2] += rb.z; f[3] += rb.w; }
+    if (g.residual) {
+        const __nv_bfloat16* rp = g.residual + row * g.ldr + n0;
+        if ((g.ldr & 3) == 0) {
+            const uint2 r2 = *reinterpret_cast<const uint2*>(rp);
+            const __nv_bfloat162* rh = reinterpret_cast<const __nv_bfloat162*>(&r2);
+            const float2 a = __bfloat1622float2(rh[0]), b = __bfloat1622float2(rh[1]);
+            f[0] += a.x; f[1] += a.y; f[2] += b.x; f[3] += b.y;
+        } else {
+            for (int i = 0; i < 4; ++i) f[i] += __bfloat162float(rp[i]);
+        }
+    }
     if (g.out_fp32) {
         float* op = reinterpret_cast<float*>(g.out) + row * g.ldo + n0;
-        for (int i = 0; i < 4; ++i) op[i] = f[i];
+        if ((g.ldo & 3) == 0) *reinterpret_cast<float4*>(op) = make_float4(f[0], f[1], f[2], f[3]);
+        else for (int i = 0; i < 4; ++i) op[i] = f[i];
     } else {
         __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(g.out) + row * g.ldo + n0;
-        for (int i = 0; i < 4; ++i) op[i] = __float2bfloat16(f[i]);
+        if ((g.ldo & 3) == 0) {
+            uint2 o2;
+            __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o2);
+            oh[0] = __floats2bfloat162_rn(f[0], f[1]); oh[1] = __floats2bfloat162_rn(f[2], f[3]);
+            *reinterpret_cast<uint2*>(op) = o2;
+        } else {
+            for (int i = 0; i < 4; ++i) op[i] = __float2bfloat16(f[i]);
+        }
     }
 }
 

@@ -212,9 +212,12 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __r
     for (int i = 0; i < 5; ++i) {
         const int v = lane + 32 * i;
         if (v < nvec) {
+            const float4 g0 = *reinterpret_cast<const float4*>(gamma + v * 8), g1 = *reinterpret_cast<const float4*>(gamma + v * 8 + 4);
+            const float4 b0 = *reinterpret_cast<const float4*>(beta + v * 8), b1 = *reinterpret_cast<const float4*>(beta + v * 8 + 4);
+            const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w}, bt[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
             float o[8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) o[e] = (f[i][e] - mean) * rstd * gamma[v * 8 + e] + beta[v * 8 + e];
+            for (int e = 0; e < 8; ++e) o[e] = (f[i][e] - mean) * rstd * gm[e] + bt[e];
             *reinterpret_cast<uint4*>(y + row * C + v * 8) = pack8(o);
         }
     }

@@ -39,9 +39,11 @@ __device__ __forceinline__ float silu_f(float x) { return x / (1.f + __expf(-x))
 //      pixel (coalesced), 256 / (C/8) pixel lanes walk the slab; per-channel partial sums stay in registers;
 //   2. the per-(pixel lane, channel) sums go to shared memory; warp w then folds groups w, w + 8, ... — every lane walks a
 //      fixed sequence of (pixel lane, channel) cells and the warp finishes with a fixed xor-shuffle tree;
-//   3. the CTA writes its 2 G partials to its own slot of `partials`; the CTA that draws the last ticket of the image (an
-//      INTEGER atomic) adds the slabs in slab order and writes stats[(img*G + g)*2 + {0,1}] = (sum, sum of squares); it
-//      also rearms the ticket counter, so the workspace needs clearing only once, when it is allocated.
+//   3. the CTA writes its 2 G partials to its own slot of `partials`.  The slabs are added by gn_apply_kernel: each of its CTAs adds
+//      the slabs of its image in slab order (thread (part, i) takes slabs part, part + nparts, ..., the parts are added in order) — the
+//      same sums, bit for bit, in every CTA.  (The first deterministic version drew an integer ticket per CTA and let the last CTA of
+//      an image do this reduction and publish the result: a fence, an atomic round trip and a serial tail in every one of the 61
+//      statistics launches of a U-Net call.)
 // Workspace per call (floats, see op_groupnorm_ws_floats): [NB * 2G stats | NB tickets | NB * slabs * 2G partials].
 __global__ void __launch_bounds__(256) gn_stats_kernel(const __nv_bfloat16* __restrict__ x, int HW, int C, int G, int pix_per_cta,
                                                        float* __restrict__ stats, unsigned* __restrict__ tickets, float* __restrict__ partials) {
@@ -90,17 +92,18 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const __nv_bfloat16* __re
     const int slabs = gridDim.x;
     float* mine = partials + ((size_t)img * slabs + blockIdx.x) * 2 * G;
     for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) mine[i] = red[i];
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const unsigned t = atomicAdd(&tickets[img], 1u);
-        red[2 * G] = (t == (unsigned)slabs - 1u) ? 1.f : 0.f;
-    }
-    __syncthreads();
-    if (red[2 * G] != 0.f) {
-        __threadfence();
-        // fixed summation order, spread over the whole CTA: thread (part, i) adds slabs part, part + nparts, ... of statistic i with
-        // eight loads in flight; the parts are then added in order (a 2G-thread serial loop over 128 slabs cost 5 us per call)
+    // (the slabs are added by the apply kernel, every CTA for itself and all in the same fixed order: no ticket, no fence, no last CTA)
+}
+
+// y = (x - mean) * rstd * gamma + beta, optional SiLU.  grid (blocks per image, NB): a CTA first adds the statistics slabs of its image
+// (see gn_stats_kernel), then walks its share of the image's 8-channel vectors.
+__global__ void __launch_bounds__(256) gn_apply_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, long vec_per_img, int HW,
+                                                       int C, int G, const float* __restrict__ partials, int slabs, const float* __restrict__ gamma,
+                                                       const float* __restrict__ beta, float eps, int silu) {
+    pdl_launch(); pdl_wait();
+    extern __shared__ float gsm[];                 // [nparts][2G] partial sums, then [2G] sums
+    const int img = blockIdx.y;
+    {
         const float* all = partials + (size_t)img * slabs * 2 * G;
         const int n2 = 2 * G, nparts = blockDim.x / n2 > 0 ? blockDim.x / n2 : 1;
         const int i = threadIdx.x % n2, part = threadIdx.x / n2;
@@ -115,29 +118,21 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const __nv_bfloat16* __re
                 for (int u = 0; u < 8; ++u) acc += v[u];
             }
             for (; k < slabs; k += nparts) acc += __ldcg(all + (size_t)k * n2 + i);
+            gsm[part * n2 + i] = acc;
         }
-        __syncthreads();                               // gsm is free: every warp finished the folding above
-        if (part < nparts) gsm[part * n2 + i] = acc;
         __syncthreads();
-        if (threadIdx.x < n2) {
-            float t = 0.f;
+        float t = 0.f;
+        if (threadIdx.x < n2)
             for (int q = 0; q < nparts; ++q) t += gsm[q * n2 + threadIdx.x];
-            stats[(long)img * G * 2 + threadIdx.x] = t;
-        }
-        if (threadIdx.x == 0) tickets[img] = 0u;
+        __syncthreads();
+        if (threadIdx.x < n2) gsm[threadIdx.x] = t;
+        __syncthreads();
     }
-}
-
-// y = (x - mean) * rstd * gamma + beta, optional SiLU.  One thread per 8-channel vector.
-__global__ void __launch_bounds__(256) gn_apply_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, long n_vec, int HW,
-                                                       int C, int G, const float* __restrict__ stats, const float* __restrict__ gamma,
-                                                       const float* __restrict__ beta, float eps, int silu) {
-    pdl_launch(); pdl_wait();
-    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= n_vec) return;
+    const float* stats = gsm;                      // [(g) * 2 + {0, 1}] = (sum, sum of squares) of this image
     const int vec_per_pix = C / 8, cpg = C / G;
-    const int cv = (int)(idx % vec_per_pix);
-    const int img = (int)(idx / ((long)vec_per_pix * HW));
+    for (long vi = (long)blockIdx.x * blockDim.x + threadIdx.x; vi < vec_per_img; vi += (long)gridDim.x * blockDim.x) {
+    const long idx = (long)img * vec_per_img + vi;
+    const int cv = (int)(vi % vec_per_pix);
     const uint4 u = *reinterpret_cast<const uint4*>(x + idx * 8);
     float f[8];
     unpack8(u, f);
@@ -155,7 +150,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const __nv_bfloat16* __re
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
             const int g = q ? g1 : g0;
-            const float s = stats[((long)img * G + g) * 2], ss = stats[((long)img * G + g) * 2 + 1];
+            const float s = stats[g * 2], ss = stats[g * 2 + 1];
             mean[q] = s * inv_n;
             rstd[q] = rsqrtf(fmaxf(ss * inv_n - mean[q] * mean[q], 0.f) + eps);
         }
@@ -170,7 +165,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const __nv_bfloat16* __re
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const int c = c0 + i, g = c / cpg;
-            const float s = stats[((long)img * G + g) * 2], ss = stats[((long)img * G + g) * 2 + 1];
+            const float s = stats[g * 2], ss = stats[g * 2 + 1];
             const float mean = s * inv_n;
             const float var = fmaxf(ss * inv_n - mean * mean, 0.f);
             float v = (f[i] - mean) * rsqrtf(var + eps) * gam[i] + bet[i];
@@ -178,6 +173,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const __nv_bfloat16* __re
         }
     }
     *reinterpret_cast<uint4*>(y + idx * 8) = pack8(f);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------- LayerNorm
@@ -423,8 +419,15 @@ int op_groupnorm(const __nv_bfloat16* x, __nv_bfloat16* y, int NB, int HW, int C
     if (smem > 48 * 1024) return (int)cudaErrorInvalidValue;
     if (launch_k(gn_stats_kernel, dim3(slabs, NB), dim3(256), smem, st, 1, x, HW, C, G, pix_per_cta, stats, tickets, partials) != cudaSuccess) return (int)cudaGetLastError();
     OPS_CHECK();
-    const long n_vec = (long)NB * HW * C / 8;
-    if (launch_k(gn_apply_kernel, dim3((unsigned)((n_vec + 255) / 256)), dim3(256), 0, st, 1, x, y, n_vec, HW, C, G, stats, gamma, beta, eps, silu) != cudaSuccess) return (int)cudaGetLastError();
+    const long vec_per_img = (long)HW * C / 8;
+    // blocks per image: enough to fill the part (each CTA adds the slabs once, 2 G x slabs floats from L2, then strides over its vectors)
+    long bpi = (vec_per_img + 255) / 256;
+    const long cap = 4L * 148 / NB > 1 ? 4L * 148 / NB : 1;
+    if (bpi > cap) bpi = cap;
+    const int n2 = 2 * G, nparts = 256 / n2 > 0 ? 256 / n2 : 1;
+    const size_t smem_a = (size_t)(nparts * n2 > n2 ? nparts * n2 : n2) * sizeof(float);
+    if (n2 > 256) return (int)cudaErrorInvalidValue;
+    if (launch_k(gn_apply_kernel, dim3((unsigned)bpi, (unsigned)NB), dim3(256), smem_a, st, 1, x, y, vec_per_img, HW, C, G, (const float*)partials, slabs, gamma, beta, eps, silu) != cudaSuccess) return (int)cudaGetLastError();
     OPS_CHECK();
     return 0;
 }

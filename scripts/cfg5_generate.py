@@ -114,8 +114,8 @@ def main():
                 "image_steps_per_s": a.rows * a.images * a.steps / wall, "rows_this_rank": mine,
                 "unet_steps_per_s_per_gpu": mine * a.steps / dt, "png_files_rank0_sees": files,
                 "unet_engine_build_s": t_build,
-                "includes": "U-Net weight re-upload (load_state_dict of the edited weights), VAE engine construction, text tower, denoise loop, "
-                            "VAE decode, PNG encode + write; the U-Net engine itself is built once per process (unet_engine_build_s)"}
+                "includes": "VAE engine construction, text tower, denoise loop, VAE decode, PNG encode + write; the U-Net engine itself is "
+                            "built once per process (unet_engine_build_s)"}
         print(json.dumps(line), flush=True)
         if a.out:
             os.makedirs(os.path.dirname(a.out) or ".", exist_ok=True)

@@ -183,10 +183,12 @@ def generate_images(model_id, uce_model_path, prompts_path, save_path, exp_name=
         except ImportError as exc:
             raise SystemExit(f"diffusers is required to load '{model_id}' (text encoder, VAE, weights): {exc}")
         pipe = DiffusionPipeline.from_pretrained(model_id, torch_dtype=torch_dtype, safety_checker=None).to(device)
-    state = {k: v for k, v in pipe.unet.state_dict().items()}
+    # an engine built by this call gets the pipeline's U-Net weights with the UCE artifact laid over them; an engine handed in already
+    # holds its weights and gets the artifact's tensors only (load_state_dict(strict=False) semantics, generate-images-sd.py:17-19)
+    state = {k: v for k, v in pipe.unet.state_dict().items()} if engine is None else {}
     if uce_model_path is not None:
         from .artifact import load_artifact
-        state.update(load_artifact(uce_model_path))      # load_state_dict(strict=False) semantics (generate-images-sd.py:17-19)
+        state.update(load_artifact(uce_model_path))
     cfg_pipe, latent = unet_config_of(pipe)
     if unet_config is None:
         unet_config = cfg_pipe
@@ -197,7 +199,8 @@ def generate_images(model_id, uce_model_path, prompts_path, save_path, exp_name=
         eng.finalize()
     else:
         eng = engine
-        eng.load_state_dict(state, strict=False)
+        if state:
+            eng.load_state_dict(state, strict=False)
     den = denoiser if denoiser is not None else Denoiser(eng, num_images_per_prompt)
     # VAE decode on the B200 decoder engine whenever the pipeline carries a VAE (UCE_VAE_ENGINE=0 keeps the pipeline's own decode)
     use_vae_engine = getattr(pipe, "vae", None) is not None and os.environ.get("UCE_VAE_ENGINE", "1") != "0"

@@ -58,6 +58,31 @@ def _worker(rank, world, port, q):
                 w.wait()
             fullc = [planc.view(l) for l in range(len(dims))]
             ok = ok and sorted(seen) == mine and all(torch.equal(a, b) for a, b in zip(fullc, ref))
+        # sharded_edit(): the driver's loop — first non-empty chunk through the one-call edit, the others through the apply alone, one
+        # asynchronous all-gather per chunk — with a stand-in solver that writes the oracle's result into the buffers it is handed
+        from uce_b200.sharding import sharded_edit
+
+        class Solver:
+            def __init__(self):
+                self.calls = []
+            def _fill(self, w_old, w_new):
+                for wo, wn in zip(w_old, w_new):
+                    i = next(k for k, w in enumerate(W) if w is wo)
+                    wn.copy_(ref[i])
+            def edit(self, C, G, scales, n_edit, lamb, w_old, w_new, check=True):
+                self.calls.append(("edit", len(w_old))); self._fill(w_old, w_new)
+            def apply(self, w_old, w_new):
+                self.calls.append(("apply", len(w_old))); self._fill(w_old, w_new)
+            def check(self):
+                self.calls.append(("check", 0))
+
+        for chunks in (1, 2, 3):
+            plans = GatherPlan(dims, K, world, rank, torch.device("cpu"), chunks=chunks)
+            sv = Solver()
+            fulls = sharded_edit(sv, plans, None, None, [], 2, 0.5, dict(enumerate(W)))
+            kinds = [c[0] for c in sv.calls]
+            ok = ok and all(torch.equal(a, b) for a, b in zip(fulls, ref))
+            ok = ok and kinds.count("edit") == 1 and kinds[0] == "edit" and kinds[-1] == "check" and sum(c[1] for c in sv.calls) == len(mine)
         q.put((rank, ok))
     finally:
         dist.destroy_process_group()

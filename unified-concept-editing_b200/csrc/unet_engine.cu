@@ -193,7 +193,7 @@ struct Builder {
         const float* ga = W(p + ".weight").f; const float* be = W(p + ".bias").f;
         const int G = u->cfg.norm_groups;
         if (u->n_gn >= sd_unet::MAX_GN) { rc = rc ? rc : SD_E_STATE; sd_err("too many GroupNorm calls"); return; }
-        float* stats = u->gn_stats + (size_t)(u->n_gn++) * uce::op_groupnorm_ws_floats(u->NB, G);      // own workspace (statistics, tickets, per-CTA partials); zeroed once
+        float* stats = u->gn_stats + (size_t)(u->n_gn++) * uce::op_groupnorm_ws_floats(u->NB, G);      // own workspace (per-CTA partial statistics; the apply kernel adds them)
         push([=](cudaStream_t st) { return uce::op_groupnorm(x.p, y.p, x.n, x.h * x.w, x.c, G, stats, ga, be, eps, silu, st); });
     }
     void layernorm(const bf16* x, bf16* y, long rows, int C, const std::string& p) {
@@ -336,7 +336,7 @@ int build_schedule(sd_unet* u) {
     {
         const size_t gn_floats = (size_t)sd_unet::MAX_GN * uce::op_groupnorm_ws_floats(NB, c.norm_groups);
         if ((rc = u->alloc(&u->gn_stats, gn_floats))) return rc;
-        SD_CUDA(cudaMemset(u->gn_stats, 0, gn_floats * sizeof(float)));      // ticket counters start at zero and rearm themselves
+        SD_CUDA(cudaMemset(u->gn_stats, 0, gn_floats * sizeof(float)));      // (nothing in it needs a defined start any more; kept so that tools see initialised memory)
     }
     u->splitk_cap = (size_t)(3 * u->sm_count) * 128 * 128;      // gemm_choose_ksplit targets ~2 CTAs per SM of 128 x 128 partial tiles
     if ((rc = u->alloc(&u->splitk_ws, u->splitk_cap))) return rc;

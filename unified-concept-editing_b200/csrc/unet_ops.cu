@@ -44,11 +44,11 @@ __device__ __forceinline__ float silu_f(float x) { return x / (1.f + __expf(-x))
 //      same sums, bit for bit, in every CTA.  (The first deterministic version drew an integer ticket per CTA and let the last CTA of
 //      an image do this reduction and publish the result: a fence, an atomic round trip and a serial tail in every one of the 61
 //      statistics launches of a U-Net call.)
-// Workspace per call (floats, see op_groupnorm_ws_floats): [NB * 2G stats | NB tickets | NB * slabs * 2G partials].
+// Workspace per call (floats, see op_groupnorm_ws_floats): [NB * 2G + NB unused (the first version's statistics and tickets) | NB * slabs * 2G partials].
 __global__ void __launch_bounds__(256) gn_stats_kernel(const __nv_bfloat16* __restrict__ x, int HW, int C, int G, int pix_per_cta,
                                                        float* __restrict__ stats, unsigned* __restrict__ tickets, float* __restrict__ partials) {
     pdl_launch(); pdl_wait();
-    extern __shared__ float gsm[];                 // [lanes][C] sums | [lanes][C] sums of squares | [2 G] folded | [1] last flag
+    extern __shared__ float gsm[];                 // [lanes][C] sums | [lanes][C] sums of squares | [2 G] folded
     const int img = blockIdx.y, p0 = blockIdx.x * pix_per_cta;
     const int vec_per_pix = C / 8, cpg = C / G;
     const __nv_bfloat16* base = x + ((long)img * HW + p0) * C;
@@ -404,7 +404,7 @@ size_t op_groupnorm_ws_floats(int NB, int G) {
 }
 int op_groupnorm(const __nv_bfloat16* x, __nv_bfloat16* y, int NB, int HW, int C, int G, float* ws, const float* gamma, const float* beta,
                  float eps, int silu, cudaStream_t st) {
-    // `ws` is this call's own workspace of op_groupnorm_ws_floats(NB, G) floats, zeroed ONCE when it was allocated (ticket counters)
+    // `ws` is this call's own workspace of op_groupnorm_ws_floats(NB, G) floats
     if (C % 8 || C % G) return (int)cudaErrorInvalidValue;
     float* stats = ws;
     unsigned* tickets = reinterpret_cast<unsigned*>(ws + (size_t)NB * 2 * G);

@@ -183,7 +183,7 @@ struct Builder {
         const float* ga = W(p + ".weight").f; const float* be = W(p + ".bias").f;
         const int G = v->cfg.norm_groups;
         if (v->n_gn >= sd_vae::MAX_GN) { fail("GroupNorm slot", p); return; }
-        float* stats = v->gn_stats + (size_t)(v->n_gn++) * uce::op_groupnorm_ws_floats(v->NB, G);      // own workspace (statistics, tickets, per-CTA partials); zeroed once
+        float* stats = v->gn_stats + (size_t)(v->n_gn++) * uce::op_groupnorm_ws_floats(v->NB, G);      // own workspace (per-CTA partial statistics; the apply kernel adds them)
         push([=](cudaStream_t st) { return uce::op_groupnorm(x.p, y.p, x.n, x.h * x.w, x.c, G, stats, ga, be, 1e-6f, silu, st); });
     }
     // ResnetBlock2D without time embedding (temb_channels=None in the VAE), eps 1e-6.  Consumes x.
@@ -261,7 +261,7 @@ int build_schedule(sd_vae* v) {
     {
         const size_t gn_floats = (size_t)sd_vae::MAX_GN * uce::op_groupnorm_ws_floats(NB, c.norm_groups);
         if ((rc = v->alloc(&v->gn_stats, gn_floats))) return rc;
-        VAE_CUDA(cudaMemset(v->gn_stats, 0, gn_floats * sizeof(float)));      // ticket counters start at zero and rearm themselves
+        VAE_CUDA(cudaMemset(v->gn_stats, 0, gn_floats * sizeof(float)));      // (nothing in it needs a defined start any more; kept so that tools see initialised memory)
     }
     v->splitk_cap = (size_t)(3 * v->sm_count) * 128 * 128;
     if ((rc = v->alloc(&v->splitk_ws, v->splitk_cap))) return rc;

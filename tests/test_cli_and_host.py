@@ -346,3 +346,25 @@ def test_plain_c_consumer_edits_on_the_gpu(tmp_path):
     assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
     got = load_file(str(tmp_path / "out.safetensors"))
     assert sorted(v.shape for v in got.values()) == [torch.Size([24, 64]), torch.Size([40, 64])] and all(v.dtype == torch.float32 for v in got.values())
+
+
+def test_zero_shot_host_helpers():
+    """Host-side pieces of the zero-shot classifier binding that need no GPU: where the text tower pools (argmax of the ids for the
+    original checkpoints whose config says eos id 2, first end-of-text token otherwise — transformers' CLIPTextTransformer.forward) and
+    the image batching (PIL-free inputs: uint8 arrays, one 4-D array, a tensor)."""
+    import numpy as np
+    import torch
+    from uce_b200.clip_zero_shot import HYPOTHESIS_TEMPLATE, _to_u8_batch, eos_index
+    ids = torch.tensor([[49406, 320, 1125, 49407, 49407, 49407], [49406, 49407, 0, 0, 0, 0], [49406, 5, 6, 7, 8, 49407]])
+    assert eos_index(ids, 2).tolist() == [3, 1, 5] and eos_index(ids, None).tolist() == [3, 1, 5]          # legacy: argmax
+    ids2 = torch.tensor([[300, 5, 9, 301, 301], [300, 301, 7, 7, 7]])
+    assert eos_index(ids2, 301).tolist() == [3, 1]                                                           # first eos token
+    a = np.zeros((4, 4, 3), dtype=np.uint8); b = np.full((4, 4, 3), 7, dtype=np.uint8)
+    t = _to_u8_batch([a, b], "cpu")
+    assert t.dtype == torch.uint8 and tuple(t.shape) == (2, 4, 4, 3) and int(t[1].max()) == 7
+    assert tuple(_to_u8_batch(np.stack([a, b]), "cpu").shape) == (2, 4, 4, 3)
+    assert tuple(_to_u8_batch(a, "cpu").shape) == (1, 4, 4, 3)
+    assert tuple(_to_u8_batch(torch.zeros(3, 8, 8, 3, dtype=torch.uint8), "cpu").shape) == (3, 8, 8, 3)
+    with pytest.raises(ValueError):
+        _to_u8_batch([np.zeros((4, 4, 3), dtype=np.float32)], "cpu")
+    assert HYPOTHESIS_TEMPLATE.format("male") == "This is a photo of male."

@@ -293,18 +293,20 @@ static int fa_encode(CUtensorMap* m, const void* ptr, const long (&dims)[4], con
 bool attn_fused_supported(int dhp) { return dhp == 64 || dhp == 128 || dhp == 192; }
 
 int attn_desc_make(AttnDesc* g, const void* q, const void* k, const void* vt, void* out, int NB, int heads, int dhp, long L, int Lk, int Lkp,
-                   float scale) {
+                   float scale, long ldq, long ldk) {
     memset(g, 0, sizeof(*g));
     const long HD = (long)heads * dhp;
+    if (ldq <= 0) ldq = HD;
+    if (ldk <= 0) ldk = HD;
     g->NB = NB; g->heads = heads; g->dhp = dhp; g->L = (int)L; g->Lk = Lk; g->scale = scale;
     g->out = (__nv_bfloat16*)out; g->ldo = HD;
     {
-        const long dims[4] = {dhp, L, heads, NB}, str[4] = {1, HD, dhp, L * HD};
+        const long dims[4] = {dhp, L, heads, NB}, str[4] = {1, ldq, dhp, L * ldq};
         const int box[4] = {64, FA_BM, 1, 1};
         if (fa_encode(&g->tmQ, q, dims, str, box)) return -1;
     }
     {
-        const long dims[4] = {dhp, Lk, heads, NB}, str[4] = {1, HD, dhp, (long)Lk * HD};
+        const long dims[4] = {dhp, Lk, heads, NB}, str[4] = {1, ldk, dhp, (long)Lk * ldk};
         const int box[4] = {64, FA_BN, 1, 1};
         if (fa_encode(&g->tmK, k, dims, str, box)) return -1;
     }

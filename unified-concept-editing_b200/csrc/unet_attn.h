@@ -15,8 +15,9 @@ struct AttnDesc {
 };
 
 bool attn_fused_supported(int dhp);
+// ldq / ldk: row strides (elements) of q and k — heads * dhp when 0; a merged [q | k] projection passes 2 * heads * dhp for both
 int attn_desc_make(AttnDesc* g, const void* q, const void* k, const void* vt, void* out, int NB, int heads, int dhp, long L, int Lk, int Lkp,
-                   float scale);
+                   float scale, long ldq = 0, long ldk = 0);
 int attn_launch(const AttnDesc& g, cudaStream_t st);
 
 }  // namespace uce

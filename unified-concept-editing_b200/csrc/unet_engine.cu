@@ -59,6 +59,7 @@ struct sd_unet {
     float* gn_stats = nullptr; float* S_scratch = nullptr; bf16* P_scratch = nullptr;
     bf16* temb_tap = nullptr;
 
+    std::map<std::string, bf16*> qk_pool;          // self-attention block -> [2 HD, C] padded weights, to_q rows then to_k rows
     template <typename T> int alloc(T** p, size_t count) {
         void* q = nullptr;
         cudaError_t e = cudaMalloc(&q, count * sizeof(T) + 256);
@@ -229,15 +230,25 @@ struct Builder {
         const long M = (long)NB * L;
         const int Lkp = (Lk + 7) / 8 * 8;
         bf16 *q = nullptr, *k = nullptr, *vt = nullptr, *o = nullptr;
-        if (!rc) rc = u->alloc(&q, (size_t)M * HD);
-        if (!rc) rc = u->alloc(&k, (size_t)NB * Lk * HD);
+        // self-attention: q and k are projections of the same rows and their padded weights are adjacent (sd_unet_set_weight): ONE GEMM
+        // writes [q | k] rows of 2 HD columns and the attention kernel reads both halves through strided tensor maps
+        const bool qk_merged = kv_src == q_src && kdim == C && (long)Lk == L && W(a + ".to_k.weight").b == W(a + ".to_q.weight").b + (size_t)HD * C &&
+                               !getenv("UCE_NO_QK_MERGE");
+        const long ldq = qk_merged ? 2L * HD : HD, ldk = ldq;
+        if (qk_merged) {
+            if (!rc) rc = u->alloc(&q, (size_t)M * 2 * HD);
+            k = q ? q + HD : nullptr;
+        } else {
+            if (!rc) rc = u->alloc(&q, (size_t)M * HD);
+            if (!rc) rc = u->alloc(&k, (size_t)NB * Lk * HD);
+        }
         if (!rc) rc = u->alloc(&vt, (size_t)NB * HD * Lkp);
         if (!rc) rc = u->alloc(&o, (size_t)M * HD);
-        linear(q_src, M, C, a + ".to_q.weight", nullptr, nullptr, q, false, HD);
+        linear(q_src, M, C, a + ".to_q.weight", nullptr, nullptr, q, false, qk_merged ? 2 * HD : HD);
         // K and V^T of the TEXT context do not change between denoise steps (generate-images-sd.py:37-42 runs all steps of a row
         // with one prompt embedding): those projections go to the per-prompt list (sd_unet_set_context), not to the step.
         to_ctx = (kv_src == u->ctx);
-        linear(kv_src, (long)NB * Lk, kdim, a + ".to_k.weight", nullptr, nullptr, k, false, HD);
+        if (!qk_merged) linear(kv_src, (long)NB * Lk, kdim, a + ".to_k.weight", nullptr, nullptr, k, false, HD);
         {   // V^T[b] [HD, Lk] = Wv_pad [HD, kdim] . kv_src[b]^T
             GemmDesc g;
             if (uce::gemm_desc_linear(&g, W(a + ".to_v.weight").b, kdim, 0, 0, kv_src, kdim, (long)Lk * kdim, 0, HD, Lk, kdim, NB, 1, 0, 1)) { rc = rc ? rc : SD_E_STATE; to_ctx = false; return; }
@@ -248,14 +259,14 @@ struct Builder {
         const bool fused = uce::attn_fused_supported(dhp) && !getenv("UCE_NO_FLASH");
         if (fused) {   // flash-style kernel: no score matrix in HBM
             uce::AttnDesc ad;
-            if (uce::attn_desc_make(&ad, q, k, vt, o, NB, heads, dhp, L, Lk, Lkp, 1.f / sqrtf((float)dh))) { rc = rc ? rc : SD_E_STATE; sd_err("attention tensor maps failed"); return; }
+            if (uce::attn_desc_make(&ad, q, k, vt, o, NB, heads, dhp, L, Lk, Lkp, 1.f / sqrtf((float)dh), ldq, ldk)) { rc = rc ? rc : SD_E_STATE; sd_err("attention tensor maps failed"); return; }
             push([ad](cudaStream_t st) { return uce::attn_launch(ad, st); });
             ++u->n_fused_attn;
         } else {
         float* S = u->S_scratch; bf16* P = u->P_scratch;
         {   // S[b,h] [L, Lk] = q[b,:,h] k[b,:,h]^T / sqrt(dh)
             GemmDesc g;
-            if (uce::gemm_desc_linear(&g, q, HD, dhp, L * HD, k, HD, dhp, (long)Lk * HD, (int)L, Lk, dhp, heads, NB, 1, 1)) { rc = rc ? rc : SD_E_STATE; return; }
+            if (uce::gemm_desc_linear(&g, q, ldq, dhp, L * ldq, k, ldk, dhp, (long)Lk * ldk, (int)L, Lk, dhp, heads, NB, 1, 1)) { rc = rc ? rc : SD_E_STATE; return; }
             g.alpha = 1.f / sqrtf((float)dh);
             g.out = S; g.out_fp32 = 1; g.ldo = Lkp; g.out_b1_stride = L * Lkp; g.out_b2_stride = (long)heads * L * Lkp;
             gemm(g);
@@ -514,8 +525,23 @@ int sd_unet_set_weight(sd_unet* u, const char* name, const float* data, const lo
     const bool as_bf16 = (kind >= 1 && kind <= 4);
     if (fresh) {
         w.shape = shp; w.kind = kind; w.elems = out_n;
-        int rc = as_bf16 ? u->alloc(&w.b, (size_t)out_n) : u->alloc(&w.f, (size_t)out_n);
-        if (rc) return rc;
+        // the padded to_q and to_k of a SELF-attention share one allocation, q rows first: one GEMM over [2 HD, C] then projects both
+        // (attention() checks the adjacency before it relies on it)
+        const std::string nm(name);
+        const size_t pq = nm.rfind(".attn1.to_q.weight"), pk = nm.rfind(".attn1.to_k.weight");
+        if (kind == 3 && (pq != std::string::npos || pk != std::string::npos)) {
+            const std::string key = nm.substr(0, pq != std::string::npos ? pq : pk);
+            bf16*& pool = u->qk_pool[key];
+            if (!pool) {
+                int rc = u->alloc(&pool, (size_t)2 * out_n);
+                if (rc) return rc;
+                SD_CUDA(cudaMemset(pool, 0, (size_t)2 * out_n * sizeof(bf16)));
+            }
+            w.b = pool + (pk != std::string::npos ? out_n : 0);
+        } else {
+            int rc = as_bf16 ? u->alloc(&w.b, (size_t)out_n) : u->alloc(&w.f, (size_t)out_n);
+            if (rc) return rc;
+        }
     }
     if (as_bf16) {
         std::vector<bf16> hb(out_n);

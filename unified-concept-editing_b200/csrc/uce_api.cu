@@ -333,9 +333,14 @@ int uce_edit_host_f32(uce_ws* ws, const float* C, const float* G, const float* s
         ws->hostpath_W_cap = total;
     }
     // groups of layers of roughly equal bytes: enough groups to overlap H2D(g+1) / apply(g) / D2H(g-1)
-    // (8 by default; UCE_HOST_GROUPS overrides it for measurements: more groups shorten the pipeline's fill and drain — the first upload
+    // (8 or 24 by default, see below; UCE_HOST_GROUPS overrides it for measurements: more groups shorten the pipeline's fill and drain — the first upload
     // and the last download run alone on the link — at the price of more, smaller apply launches)
-    int target_groups = std::min(n_layers, 8);
+    // (measured, cfg2: weights in one pinned arena per direction — one copy per group — 6 or 8 groups 2.07 ms, 24 groups 2.47; one pinned
+    //  tensor per projection — the copies are per projection anyway — 8 groups 2.33 ms, 24 groups 2.18: profiles/r02_e2e_pipeline.txt)
+    bool contiguous = true;
+    for (int l = 1; l < n_layers && contiguous; ++l)
+        contiguous = W_old[l] == W_old[l - 1] + (size_t)d[l - 1] * K && W_new[l] == W_new[l - 1] + (size_t)d[l - 1] * K;
+    int target_groups = std::min(n_layers, contiguous ? 8 : 24);
     if (const char* e = getenv("UCE_HOST_GROUPS")) { const int t = atoi(e); if (t >= 1) target_groups = std::min(n_layers, t); }
     // Group sizes are graded: the first upload and the last apply + download run alone on the link (pipeline fill and drain), so the
     // first group is ~0.65 and the last two ~0.8 / ~0.4 of the average — the first apply cannot start before the factor ends anyway

@@ -383,6 +383,16 @@ def run_ours(args, rank, world, local_rank):
                 # (K / 8 CTAs).  < 1 MB and 40 MFLOP: neither HBM nor a tensor pipe bounds it, latency does.
                 "factor": {"kernels": "factor_tables, gram_pack, chol_small (1 CTA), inv_blocks, solve_emit_dmma (chained by programmatic dependent launch)" if info["launches_factor"] <= 5 else "general blocked path (factor.cu)",
                            "ms": f_ms, "bound": "latency (serial fp64 pivots on one SM; dependent fp64 operations cost ~35 cycles each)"}}
+        if kern.startswith("gemm3x") and not info["dense"]:
+            # the two-GEMM apply at high rank is bound by the tensor pipe, not by HBM: 3 TF32 MMAs (hi.hi, lo.hi, hi.lo) per product,
+            # two passes (P = W_old E^T, W_new = W_old + P Q): 12 sum(d) K r_pad flop; kind::tf32 runs at half the bf16 rate
+            tf32_peak = 0.5 * peaks.get("bf16_tflops", 2250.0)
+            flops = 12.0 * sum_d * K * rank_pad
+            tfl = flops / (dom_ms / 1e3) / 1e12
+            roof.update({"bound": "tensor", "achieved": tfl, "peak": tf32_peak, "unit": "TFLOP/s", "frac": tfl / tf32_peak,
+                         "peak_source": "half of MEASURED_PEAKS.json bf16_tflops (burst): kind::tf32 issues at half the bf16 rate" if "bf16_tflops" in peaks
+                         else "half of the nominal 2 250 TFLOP/s bf16 peak", "algorithmic_flops": flops,
+                         "hbm": {"achieved_GBs": achieved, "frac": achieved / peak_bw, "algorithmic_bytes": alg_bytes}})
         if alg_a is not None:
             roof["kernel_a"] = {"kernel": "apply_p_kernel (partial W_old E^T per K slice; runs on the library's side stream while the factor computes Q)",
                                 "algorithmic_bytes": alg_a, "kernel_ms": a1_ms, "achieved": alg_a / (a1_ms / 1e3) / 1e9, "frac": alg_a / (a1_ms / 1e3) / 1e9 / peak_bw}
